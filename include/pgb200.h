@@ -1,0 +1,177 @@
+/*
+ * pgb200.h -- C-ABI of libpgb200.so: the B200 (sm_100a) implementation of pilotguru's per-frame
+ * motion-annotation hot path (ORB extraction, Hamming projection matching, IMU+GPS calibration).
+ *
+ * Every entry point replaces a call boundary of the reference (file:line relative to waiwnf/pilotguru):
+ *   pgb_orb_*       thirdparty/orb-slam2/include/ORBextractor.h:51-85  (ctor, operator(), getters, mvImagePyramid)
+ *   pgb_match_*     thirdparty/orb-slam2/include/ORBmatcher.h:41-52    (SearchByProjection(Frame&,const Frame&,th,bMono),
+ *                   DescriptorDistance) with Frame.cc:234-249,331-396 grid semantics
+ *   pgb_imu_*       include/calibration/velocity.hpp:38-76 (AccelerometerCalibrator ctor, operator(), eval,
+ *                   IntegrateTrajectory, ImuTimes) and src/fit_motion.cc:156-293 (sliding-window L-BFGS driver,
+ *                   thirdparty/LBFGS/LBFGS.h:79-182)
+ *
+ * Conventions: opaque handles; caller-owned buffers; plain pointers and sizes; int status return
+ * (0 = ok, <0 = error, text via pgb_last_error()); no exceptions cross the boundary.  A handle owns one CUDA
+ * stream (or borrows the one given at creation) and is NOT thread-safe; distinct handles are independent.
+ * There is no CPU fallback: every compute entry point fails with PGB_ERR_CUDA when no sm_100 device is usable.
+ *
+ * "device pointer" arguments may come from any allocator in the process (cudaMalloc, torch, ...).
+ */
+#ifndef PGB200_H_
+#define PGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGB_OK 0
+#define PGB_ERR_INVALID (-1)  /* bad argument (mirrors the reference's CHECK/assert failures) */
+#define PGB_ERR_CUDA (-2)     /* CUDA runtime/driver failure, or no usable device */
+#define PGB_ERR_CAPACITY (-3) /* an internal or caller buffer was too small; nothing was silently truncated */
+#define PGB_ERR_NUMERIC (-4)  /* L-BFGS line-search step left [min_step, max_step] (LineSearch.h:103-107) */
+
+/* Same field order and size (28 B) as cv::KeyPoint, the element type of ORBextractor's output vector. */
+typedef struct pgb_keypoint {
+  float x, y;     /* pt, level-0 pixel coordinates (level coords * scale[octave], ORBextractor.cc:1094-1100) */
+  float size;     /* (int)(31 * scale[octave]) */
+  float angle;    /* degrees, [0,360) */
+  float response; /* FAST score */
+  int32_t octave;
+  int32_t class_id; /* always -1 */
+} pgb_keypoint;
+
+const char* pgb_last_error(void);
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+int pgb_version(void);
+/* Number of CUDA kernels launched by this library in this process so far (bench.py's gpu_launches). */
+uint64_t pgb_launch_count(void);
+
+/* ------------------------------------------------------------------ ORB extractor -------------------------- */
+typedef struct pgb_orb pgb_orb;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) (ORBextractor.cc:410-470)
+ * plus the capacity the device buffers are sized for.  stream: a cudaStream_t cast to void*, or NULL to let the
+ * handle create its own. */
+pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
+                        int min_th_fast, int max_width, int max_height, int max_batch, void* stream);
+void pgb_orb_destroy(pgb_orb*);
+
+/* Getters (ORBextractor.h:63-85). Arrays have nlevels entries. */
+int pgb_orb_levels(const pgb_orb*);
+float pgb_orb_scale_factor(const pgb_orb*);
+int pgb_orb_scale_factors(const pgb_orb*, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2);
+int pgb_orb_features_per_level(const pgb_orb*, int32_t* n_per_level);
+/* Maximum number of keypoints one frame can produce (sum over levels of quota+2): the `cap` callers need. */
+int pgb_orb_max_keypoints(const pgb_orb*);
+int pgb_orb_level_size(const pgb_orb*, int width, int height, int level, int* w, int* h);
+
+/* ORBextractor::operator() over a batch of n_frames gray images of identical size (ORBextractor.cc:1042-1104).
+ * gray: host pointer (is_device=0; copied with cudaMemcpy2DAsync inside the call) or device pointer (is_device=1).
+ * frame i starts at gray + i*frame_stride, rows are `pitch` bytes apart.
+ * Outputs are HOST buffers when is_device=0 and DEVICE buffers when is_device=1:
+ *   kps[n_frames][cap], desc[n_frames][cap][32], counts[n_frames]; level-major then octree list order.
+ * width==0 || height==0 => counts zeroed, PGB_OK (the reference returns silently on an empty image, :1045).
+ * With is_device=1 the call is asynchronous on the handle's stream. */
+int pgb_orb_extract(pgb_orb*, const uint8_t* gray, int is_device, int n_frames, int width, int height, size_t pitch,
+                    size_t frame_stride, pgb_keypoint* kps, uint8_t* desc, int32_t* counts, int cap);
+
+/* mvImagePyramid[level] of frame `frame` of the last extract call, copied to a tight host buffer (w*h bytes). */
+int pgb_orb_get_level(pgb_orb*, int frame, int level, uint8_t* out, int* w, int* h);
+/* Stage outputs of the last extract call, for parity tests (host buffers):
+ * FAST score map of a level (score = max arc threshold; 0 where not a corner at minThFAST or outside the tested
+ * region); the per-level candidate list handed to the octree (x,y relative to the 16-px border, response). */
+int pgb_orb_get_score_map(pgb_orb*, int frame, int level, uint8_t* out, int* w, int* h);
+int pgb_orb_get_candidates(pgb_orb*, int frame, int level, int32_t* xyr /*[cap][3]*/, int cap, int32_t* n);
+/* 7x7 sigma=2 fixed-point Gaussian blur of a whole level (ORBextractor.cc:1084-1085); tight host buffer. */
+int pgb_orb_get_blurred_level(pgb_orb*, int frame, int level, uint8_t* out, int* w, int* h);
+/* Run only pyramid + FAST score kernels on the frames already resident from the last extract call
+ * (used by bench.py to time the FAST kernel alone). which: 0 = pyramid, 1 = FAST score, 2 = cell NMS,
+ * 3 = octree, 4 = orientation+descriptor. Asynchronous on the handle's stream. */
+int pgb_orb_run_stage(pgb_orb*, int which);
+void* pgb_orb_stream(pgb_orb*);
+
+/* ------------------------------------------------------------------ matcher -------------------------------- */
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1651-1667) for n pairs of 32-byte descriptors (device or host
+ * pointers; host pointers are staged). Mostly a test hook for the popcount primitive. */
+int pgb_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist, int is_device, void* stream);
+
+typedef struct pgb_matcher pgb_matcher;
+/* ORBmatcher(nnratio, checkOri) (ORBmatcher.cc:42); max_feats / max_batch size the device scratch. */
+pgb_matcher* pgb_matcher_create(int device, float nnratio, int check_orientation, int max_feats, int max_batch,
+                                void* stream);
+void pgb_matcher_destroy(pgb_matcher*);
+
+/* SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) (ORBmatcher.cc:1332-1474) for n_pairs
+ * independent frame pairs.  For pair p:
+ *   current frame: cur_kps[p][cap], cur_desc[p][cap][32], cur_counts[p]
+ *   queries (the last frame's map points): q_uv[p][cap][2] projected pixel, q_octave, q_angle, q_desc[p][cap][32],
+ *   q_valid[p][cap] (0 = no map point / outlier / behind camera: skipped), q_counts[p]
+ * image bounds mnMinX..mnMaxY, th, and the extractor scale factors define the search windows.
+ * Output: match_of_cur[p][cap] = query index assigned to each current keypoint or -1 (CurrentFrame.mvpMapPoints),
+ *         n_matches[p] (the return value).  All buffers device (is_device=1) or host (0). */
+int pgb_match_by_projection(pgb_matcher*, int n_pairs, int cap, const pgb_keypoint* cur_kps, const uint8_t* cur_desc,
+                            const int32_t* cur_counts, const float* q_uv, const int32_t* q_octave,
+                            const float* q_angle, const uint8_t* q_desc, const uint8_t* q_valid,
+                            const int32_t* q_counts, float min_x, float max_x, float min_y, float max_y, float th,
+                            const float* scale_factors, int nlevels, int32_t* match_of_cur, int32_t* n_matches,
+                            int is_device);
+
+/* Convenience used by the synthetic benchmark (SURVEY.md section 8d "match stage definition"): frame t-1's
+ * keypoints act as map points projected to (x+flow_x, y+flow_y); retries with 2*th when fewer than 20 matches
+ * (Tracking.cc:876-883).  kps/desc/counts are per-frame arrays as produced by pgb_orb_extract; pairs are
+ * (prev = first_prev+p, cur = first_prev+p+1) for p in [0,n_pairs). flow[p][2]. Device buffers only. */
+int pgb_match_consecutive(pgb_matcher*, int n_pairs, int cap, const pgb_keypoint* kps, const uint8_t* desc,
+                          const int32_t* counts, const float* flow, float max_x, float max_y, float th,
+                          const float* scale_factors, int nlevels, int32_t* match_of_cur, int32_t* n_matches);
+
+/* ------------------------------------------------------------------ IMU + GPS calibration ------------------ */
+typedef struct pgb_imu pgb_imu;
+
+/* AccelerometerCalibrator's sensor series (velocity.cc:29-39): whole-recording gyro + accel, host arrays
+ * xyz[n][3] fp64, t[n] int64 usec (strictly increasing, CHECKed as align_time_series.cc:22-26).
+ * Merges the two series once (MergeTimeSeries, align_time_series.cc:29-113) and keeps them on the device. */
+pgb_imu* pgb_imu_create(int device, const double* gyro_xyz, const int64_t* gyro_t, size_t n_gyro,
+                        const double* acc_xyz, const int64_t* acc_t, size_t n_acc, void* stream);
+void pgb_imu_destroy(pgb_imu*);
+/* ImuTimes(): number of merged events, their effective timestamps and component indices (host out, may be NULL). */
+int64_t pgb_imu_merged_count(const pgb_imu*);
+int pgb_imu_merged_events(const pgb_imu*, int64_t* t_usec, int64_t* gyro_idx, int64_t* acc_idx);
+
+/* Select the reference (GPS) window: the calibrator a fit_motion window constructs (fit_motion.cc:183-190).
+ * Builds the interpolation intervals (align_time_series.cc:155-196) and runs the rotation sweep that reduces the
+ * window to per-GPS-interval constants. */
+int pgb_imu_set_window(pgb_imu*, const double* gps_v, const int64_t* gps_t, int n_gps);
+int64_t pgb_imu_window_intervals(const pgb_imu*);
+/* AccelerometerCalibrator::operator()/eval (velocity.cc:41-193): x = (g[3], h[3], v0[3]). */
+int pgb_imu_eval(pgb_imu*, const double x[9], double* loss, double grad[9]);
+/* LBFGSSolver::minimize on the current window from x (in/out) (LBFGS.h:79-182, fit_motion.cc:167-197). */
+int pgb_imu_minimize(pgb_imu*, double x[9], double* fx, int* n_iter, int max_iterations, double epsilon);
+/* IntegrateTrajectory (velocity.cc:199-256): one entry per merged event touched by the window, ascending index.
+ * Outputs host arrays of capacity cap: merged index, |v|, orientation (w,x,y,z), velocity xyz, duration usec. */
+int pgb_imu_integrate(pgb_imu*, const double x[9], int64_t cap, int64_t* merged_idx, double* speed, double* quat_wxyz,
+                      double* vel_xyz, int64_t* duration_usec, int64_t* n_out);
+
+/* ComputeAndSaveForwardVelocitiesFromImu's window loop (fit_motion.cc:156-273) for ALL sliding windows at once:
+ * windows start at GPS index 0, shift_step, 2*shift_step, ... and hold batch_size samples.  Every window's
+ * L-BFGS runs on the device.  first_window/n_windows select a contiguous shard (n_windows<0 = all) so ranks can
+ * split the windows; sums are exchanged by the caller.
+ * Outputs (host): per merged event speed_sum[n_merged], speed_cnt[n_merged] (accumulated in window order);
+ * per window x_out[w][9], fx_out[w], iters_out[w]; forward-axis accumulator fwd_sum[3] + fwd_rem[3] (KahanSum,
+ * math.hpp:8-26) may be NULL. */
+int pgb_imu_fit_windows(pgb_imu*, const double* gps_v, const int64_t* gps_t, int n_gps, int batch_size,
+                        int shift_step, int max_iterations, double epsilon, int first_window, int n_windows,
+                        double* speed_sum, int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out,
+                        double min_velocity_m_s, double min_rotation_rad, double* fwd_sum, double* fwd_rem);
+int pgb_imu_num_windows(int n_gps, int shift_step);
+
+/* SmoothTimeSeries (src/slam/smoothing.cc:56-98): host arrays in/out, device compute. */
+int pgb_smooth_time_series(int device, const double* values, const double* times, int64_t n,
+                           const double* target_times, int64_t n_target, double sigma, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGB200_H_ */

@@ -1,0 +1,169 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY (never imported by pilotguru_b200)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+
+
+def build():
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cc", ".h")) or f == "Makefile"]
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", ORACLE_DIR, "liboracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(ORACLE_DIR, "liboracle.so")
+        try:
+            so = build()
+        except Exception:
+            if not os.path.exists(so):
+                raise
+        _LIB = C.CDLL(so)
+        _LIB.pgo_orb_create.restype = C.c_void_p
+        _LIB.pgo_fast_atan2.restype = C.c_float
+        _LIB.pgo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _LIB.pgo_ic_angle.restype = C.c_float
+    return _LIB
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def resize_linear(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().pgo_resize_linear(ptr(src, u8p), src.shape[1], src.shape[0], ptr(dst, u8p), dw, dh)
+    return dst
+
+
+def fast(img: np.ndarray, th: int, nms: bool = True) -> np.ndarray:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    cap = img.size
+    out = np.empty((cap, 3), np.int32)
+    n = lib().pgo_fast(ptr(img, u8p), img.shape[1], img.shape[0], th, int(nms), ptr(out, i32p), cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def fast_score_map(img: np.ndarray, min_th: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.empty_like(img)
+    lib().pgo_fast_score_map(ptr(img, u8p), img.shape[1], img.shape[0], min_th, ptr(out, u8p))
+    return out
+
+
+def gaussian_blur7(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.empty_like(img)
+    lib().pgo_gaussian_blur7(ptr(img, u8p), img.shape[1], img.shape[0], ptr(out, u8p))
+    return out
+
+
+def fast_atan2(y: np.ndarray, x: np.ndarray) -> np.ndarray:
+    y = np.ascontiguousarray(y, np.float32); x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    lib().pgo_fast_atan2_many(ptr(y, f32p), ptr(x, f32p), ptr(out, f32p), y.size)
+    return out
+
+
+def ic_angle(img: np.ndarray, cx: int, cy: int) -> float:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    return float(lib().pgo_ic_angle(ptr(img, u8p), img.shape[1], img.shape[0], int(cx), int(cy)))
+
+
+def orb_descriptor(blurred: np.ndarray, cx: int, cy: int, angle: float) -> np.ndarray:
+    blurred = np.ascontiguousarray(blurred, dtype=np.uint8)
+    d = np.empty(32, np.uint8)
+    lib().pgo_orb_descriptor(ptr(blurred, u8p), blurred.shape[1], blurred.shape[0], int(cx), int(cy),
+                             C.c_float(angle), ptr(d, u8p))
+    return d
+
+
+def distribute_octree(xyr: np.ndarray, minX, maxX, minY, maxY, N) -> np.ndarray:
+    xyr = np.ascontiguousarray(xyr, np.int32)
+    keep = np.empty(N + 8, np.int32)
+    n = lib().pgo_distribute_octree(ptr(xyr, i32p), len(xyr), minX, maxX, minY, maxY, N, ptr(keep, i32p), len(keep))
+    assert n >= 0
+    return keep[:n].copy()
+
+
+class OrbOracle:
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.l = lib()
+        self.h = C.c_void_p(self.l.pgo_orb_create(nfeatures, C.c_float(scale), nlevels, ini_th, min_th))
+        assert self.h
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.pgo_orb_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        L = self.nlevels
+        s = np.empty(L, np.float32); inv = np.empty(L, np.float32); s2 = np.empty(L, np.float32)
+        is2 = np.empty(L, np.float32); n = np.empty(L, np.int32); um = np.empty(16, np.int32)
+        self.l.pgo_orb_tables(self.h, ptr(s, f32p), ptr(inv, f32p), ptr(s2, f32p), ptr(is2, f32p), ptr(n, i32p),
+                              ptr(um, i32p))
+        return dict(scale=s, inv_scale=inv, sigma2=s2, inv_sigma2=is2, n_per_level=n, umax=um)
+
+    def level_size(self, w, h, level):
+        lw = C.c_int(); lh = C.c_int()
+        self.l.pgo_orb_level_size(self.h, w, h, level, C.byref(lw), C.byref(lh))
+        return lw.value, lh.value
+
+    def extract(self, gray: np.ndarray):
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        cap = self.nfeatures + 2 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = self.l.pgo_orb_extract(self.h, ptr(gray, u8p), gray.shape[1], gray.shape[0], C.c_size_t(gray.shape[1]),
+                                   kps.ctypes.data_as(C.c_void_p), ptr(desc, u8p), cap)
+        assert n >= 0
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, level):
+        w = C.c_int(); h = C.c_int()
+        assert self.l.pgo_orb_get_level(self.h, level, None, C.byref(w), C.byref(h)) == 0
+        out = np.empty((h.value, w.value), np.uint8)
+        self.l.pgo_orb_get_level(self.h, level, ptr(out, u8p), C.byref(w), C.byref(h))
+        return out
+
+    def candidates(self, level):
+        n = self.l.pgo_orb_get_candidates(self.h, level, None, 0)
+        out = np.empty((max(n, 1), 3), np.int32)
+        self.l.pgo_orb_get_candidates(self.h, level, ptr(out, i32p), n)
+        return out[:n]
+
+    def level_keypoints(self, level):
+        n = self.l.pgo_orb_get_level_keypoints(self.h, level, None, 0)
+        out = np.zeros(max(n, 1), KP_DTYPE)
+        self.l.pgo_orb_get_level_keypoints(self.h, level, out.ctypes.data_as(C.c_void_p), n)
+        return out[:n]
+
+    def stage_times(self, reset=True):
+        t = np.zeros(6)
+        self.l.pgo_orb_stage_times(self.h, ptr(t, f64p), int(reset))
+        return t
