@@ -92,6 +92,9 @@ int pgb_orb_get_blurred_level(pgb_orb*, int frame, int level, uint8_t* out, int*
  * 3 = octree, 4 = orientation+descriptor. Asynchronous on the handle's stream. */
 int pgb_orb_run_stage(pgb_orb*, int which);
 void* pgb_orb_stream(pgb_orb*);
+/* Synchronise the handle's stream and report (and clear) device-side capacity flags raised by asynchronous
+ * (is_device=1) extract calls. */
+int pgb_orb_check(pgb_orb*);
 
 /* ------------------------------------------------------------------ matcher -------------------------------- */
 /* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1651-1667) for n pairs of 32-byte descriptors (device or host

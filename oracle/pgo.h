@@ -29,6 +29,16 @@ float pgo_ic_angle(const uint8_t* img, int w, int h, int cx, int cy);
 void pgo_orb_descriptor(const uint8_t* blurred, int w, int h, int cx, int cy, float angle_deg, uint8_t* desc32);
 int pgo_distribute_octree(const int32_t* xyr, int n, int minX, int maxX, int minY, int maxY, int N, int32_t* keep,
                           int cap);
+int pgo_descriptor_distance(const uint8_t* a, const uint8_t* b);
+int pgo_search_by_projection(const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, const float* q_uv,
+                             const int32_t* q_octave, const float* q_angle, const uint8_t* q_desc,
+                             const uint8_t* q_valid, int n_q, float minX, float maxX, float minY, float maxY, float th,
+                             const float* scale_factors, int nlevels, int check_ori, int32_t* match_of_cur,
+                             int32_t* best_dist_of_q);
+int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
+                          const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
+                          float maxX, float maxY, float th, const float* scale_factors, int nlevels,
+                          int32_t* match_of_cur);
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,169 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see pgo_orb.cc header for the rules).
+// CPU restatement of the reference's frame-to-frame projection matcher:
+//   thirdparty/orb-slam2/src/ORBmatcher.cc  SearchByProjection(Frame&,const Frame&,th,bMono) :1332-1474,
+//   ComputeThreeMaxima :1605-1646, DescriptorDistance :1651-1667, constants :38-40
+//   thirdparty/orb-slam2/src/Frame.cc       AssignFeaturesToGrid :234-249, GetFeaturesInArea :331-384,
+//   PosInGrid :386-396; grid 64x48 (Frame.h:37-38)
+//   thirdparty/orb-slam2/src/Tracking.cc    retry with 2*th when fewer than 20 matches :876-883
+// The Frame/MapPoint object graph is flattened to arrays: every query is a "last frame map point" already
+// projected to (u,v) with its octave, angle and representative descriptor.  Mono only (bForward/bBackward are
+// false, mvuRight = -1).  The reference has no tests for this path; parity is pinned by construction against
+// this restatement and by the brute-force property tests in tests/test_oracle_match.py.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "pgo.h"
+
+namespace {
+const int TH_HIGH = 100;
+const int HISTO_LENGTH = 30;
+const int GRID_ROWS = 48, GRID_COLS = 64;
+
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t pa, pb;
+    memcpy(&pa, a + 4 * i, 4);
+    memcpy(&pb, b + 4 * i, 4);
+    uint32_t v = pa ^ pb;
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = (int)histo[i].size();
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+}  // namespace
+
+extern "C" {
+
+int pgo_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+int pgo_search_by_projection(const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, const float* q_uv,
+                             const int32_t* q_octave, const float* q_angle, const uint8_t* q_desc,
+                             const uint8_t* q_valid, int n_q, float minX, float maxX, float minY, float maxY, float th,
+                             const float* scale_factors, int nlevels, int check_ori, int32_t* match_of_cur,
+                             int32_t* best_dist_of_q) {
+  (void)nlevels;
+  const float invW = (float)GRID_COLS / (maxX - minX);
+  const float invH = (float)GRID_ROWS / (maxY - minY);
+  // AssignFeaturesToGrid
+  static thread_local std::vector<int> grid[GRID_COLS][GRID_ROWS];
+  for (int i = 0; i < GRID_COLS; i++)
+    for (int j = 0; j < GRID_ROWS; j++) grid[i][j].clear();
+  for (int i = 0; i < n_cur; i++) {
+    int posX = (int)std::round((cur_kps[i].x - minX) * invW);
+    int posY = (int)std::round((cur_kps[i].y - minY) * invH);
+    if (posX < 0 || posX >= GRID_COLS || posY < 0 || posY >= GRID_ROWS) continue;
+    grid[posX][posY].push_back(i);
+  }
+  for (int i = 0; i < n_cur; i++) match_of_cur[i] = -1;
+  if (best_dist_of_q)
+    for (int i = 0; i < n_q; i++) best_dist_of_q[i] = -1;
+
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  std::vector<int> vIndices2;
+  for (int i = 0; i < n_q; i++) {
+    if (!q_valid[i]) continue;
+    const float u = q_uv[2 * i], v = q_uv[2 * i + 1];
+    if (u < minX || u > maxX) continue;
+    if (v < minY || v > maxY) continue;
+    const int nLastOctave = q_octave[i];
+    const float r = th * scale_factors[nLastOctave];
+    const int minLevel = nLastOctave - 1, maxLevel = nLastOctave + 1;
+    // GetFeaturesInArea
+    vIndices2.clear();
+    do {
+      const int nMinCellX = std::max(0, (int)std::floor((u - minX - r) * invW));
+      if (nMinCellX >= GRID_COLS) break;
+      const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((u - minX + r) * invW));
+      if (nMaxCellX < 0) break;
+      const int nMinCellY = std::max(0, (int)std::floor((v - minY - r) * invH));
+      if (nMinCellY >= GRID_ROWS) break;
+      const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((v - minY + r) * invH));
+      if (nMaxCellY < 0) break;
+      const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+      for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+          for (int idx : grid[ix][iy]) {
+            const pgb_keypoint& kp = cur_kps[idx];
+            if (bCheckLevels) {
+              if (kp.octave < minLevel) continue;
+              if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+            }
+            const float distx = kp.x - u, disty = kp.y - v;
+            if (std::fabs(distx) < r && std::fabs(disty) < r) vIndices2.push_back(idx);
+          }
+    } while (0);
+    if (vIndices2.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : vIndices2) {
+      if (match_of_cur[i2] >= 0) continue;  // already holds a map point with observations
+      const int dist = descriptor_distance(q_desc + (size_t)i * 32, cur_desc + (size_t)i2 * 32);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (best_dist_of_q) best_dist_of_q[i] = bestDist;
+    if (bestDist <= TH_HIGH) {
+      match_of_cur[bestIdx2] = i;
+      nmatches++;
+      if (check_ori) {
+        float rot = q_angle[i] - cur_kps[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(bestIdx2);
+      }
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int idx : rotHist[i]) { match_of_cur[idx] = -1; nmatches--; }
+  }
+  return nmatches;
+}
+
+// The synthetic benchmark's match stage: previous frame's keypoints are the map points, projected
+// by the known flow; retry at 2*th when fewer than 20 matches (Tracking.cc:876-883).
+int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
+                          const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
+                          float maxX, float maxY, float th, const float* scale_factors, int nlevels,
+                          int32_t* match_of_cur) {
+  std::vector<float> uv(2 * (size_t)n_prev), ang(n_prev);
+  std::vector<int32_t> oct(n_prev);
+  std::vector<uint8_t> valid(n_prev, 1);
+  for (int i = 0; i < n_prev; i++) {
+    uv[2 * i] = prev_kps[i].x + flow_x;
+    uv[2 * i + 1] = prev_kps[i].y + flow_y;
+    ang[i] = prev_kps[i].angle;
+    oct[i] = prev_kps[i].octave;
+  }
+  int n = pgo_search_by_projection(cur_kps, cur_desc, n_cur, uv.data(), oct.data(), ang.data(), prev_desc,
+                                   valid.data(), n_prev, 0.f, maxX, 0.f, maxY, th, scale_factors, nlevels, 1,
+                                   match_of_cur, nullptr);
+  if (n < 20)
+    n = pgo_search_by_projection(cur_kps, cur_desc, n_cur, uv.data(), oct.data(), ang.data(), prev_desc,
+                                 valid.data(), n_prev, 0.f, maxX, 0.f, maxY, 2 * th, scale_factors, nlevels, 1,
+                                 match_of_cur, nullptr);
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+"""ctypes binding of libpgb200.so (the C-ABI declared in include/pgb200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C pilotguru_b200/csrc``.  There is no
+fallback: if the shared object is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgb200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+PGB_OK, PGB_ERR_INVALID, PGB_ERR_CUDA, PGB_ERR_CAPACITY, PGB_ERR_NUMERIC = 0, -1, -2, -3, -4
+
+
+class PgbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libpgb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+vp = C.c_void_p
+_SIGS = {
+    "pgb_last_error": (C.c_char_p, []),
+    "pgb_version": (C.c_int, []),
+    "pgb_launch_count": (C.c_uint64, []),
+    "pgb_orb_create": (vp, [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "pgb_orb_destroy": (None, [vp]),
+    "pgb_orb_levels": (C.c_int, [vp]),
+    "pgb_orb_scale_factor": (C.c_float, [vp]),
+    "pgb_orb_scale_factors": (C.c_int, [vp, vp, vp, vp, vp]),
+    "pgb_orb_features_per_level": (C.c_int, [vp, vp]),
+    "pgb_orb_max_keypoints": (C.c_int, [vp]),
+    "pgb_orb_level_size": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "pgb_orb_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int]),
+    "pgb_orb_get_level": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
+    "pgb_orb_get_score_map": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
+    "pgb_orb_get_candidates": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "pgb_orb_get_blurred_level": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
+    "pgb_orb_run_stage": (C.c_int, [vp, C.c_int]),
+    "pgb_orb_stream": (vp, [vp]),
+    "pgb_orb_check": (C.c_int, [vp]),
+    "pgb_descriptor_distance": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
+    "pgb_matcher_create": (vp, [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, vp]),
+    "pgb_matcher_destroy": (None, [vp]),
+    "pgb_match_by_projection": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_float, vp, C.c_int, vp, vp, C.c_int]),
+    "pgb_match_consecutive": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp,
+                                        C.c_int, vp, vp]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/pgb200.h declares (parsed from the header; used by the CPU ABI test)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(_HERE), "include", "pgb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PgbError(PGB_ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise PgbError(rc, lib().pgb_last_error().decode("utf-8", "replace"))
+
+
+def last_error() -> str:
+    return lib().pgb_last_error().decode("utf-8", "replace")
+
+
+def launch_count() -> int:
+    return int(lib().pgb_launch_count())
+
+
+def np_ptr(a: np.ndarray) -> int:
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data

@@ -1,0 +1,507 @@
+// K8: frame-to-frame projection matching (sm_100a) and its C-ABI.
+//
+// Reference semantics (thirdparty/orb-slam2/src): ORBmatcher::SearchByProjection(Frame&,const Frame&,th,bMono=true)
+// ORBmatcher.cc:1332-1474; Frame::GetFeaturesInArea / PosInGrid Frame.cc:331-396 (64x48 grid, candidate order =
+// cell x ascending, cell y ascending, keypoint index ascending); DescriptorDistance ORBmatcher.cc:1651-1667;
+// ComputeThreeMaxima :1605-1646; TH_HIGH=100, HISTO_LENGTH=30 (:38-40); retry at 2*th below 20 matches
+// (Tracking.cc:876-883).
+//
+// One CTA per frame pair.  Phase A (all warps): one warp per query; lanes sweep the current frame's keypoints
+// (descriptors staged in shared memory), apply the window/octave/grid tests, take the 256-bit Hamming distance
+// with POPC and keep the query's candidates sorted by (distance, traversal order).  Phase B (one warp): the
+// reference's greedy loop is sequential in the query index -- a target taken by an earlier query is skipped --
+// so the queries are replayed in order, each taking the first candidate of its sorted list that is still free.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace pgb {
+
+constexpr int kMtThreads = 256;
+constexpr int kMtWarps = kMtThreads / 32;
+constexpr int kMtK = 32;        // sorted candidates kept per query
+constexpr int kMtStage = 128;   // per-warp staging of unsorted candidates
+constexpr int kThHigh = 100;
+constexpr int kHisto = 30;
+constexpr int kGridCols = 64, kGridRows = 48;
+
+struct MatchArgs {
+  int cap, nlevels, checkOri, consecutive, onlyIfBelow20;
+  float minX, maxX, minY, maxY, th;
+  float scale[16];
+  // generic mode (consecutive == 0): arrays indexed [pair][cap]
+  const pgb_keypoint* curK;
+  const uint8_t* curD;
+  const int* curN;
+  const float* qUV;
+  const int* qOct;
+  const float* qAng;
+  const uint8_t* qD;
+  const uint8_t* qValid;
+  const int* qN;
+  // consecutive mode: frame arrays [frame][cap]; pair p = (frame p, frame p+1); flow[p][2]
+  const float* flow;
+  int* matchOfCur;   // [pair][cap]
+  int* nMatches;     // [pair]
+  unsigned long long* qList;  // scratch [pair][cap][kMtK]
+  int* qCnt;                  // scratch [pair][cap] (total candidates found, may exceed kMtK)
+};
+
+__device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) {
+  int d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
+  return d;
+}
+
+struct QueryWin {
+  float u, v, r;
+  int cx0, cx1, cy0, cy1, o0, o1;
+  bool ok;
+};
+
+__device__ __forceinline__ QueryWin make_window(const MatchArgs& A, float u, float v, int octave, bool valid,
+                                                float invW, float invH) {
+  QueryWin q;
+  q.u = u; q.v = v; q.ok = false; q.r = 0; q.cx0 = q.cx1 = q.cy0 = q.cy1 = 0;
+  q.o0 = octave - 1; q.o1 = octave + 1;
+  if (!valid) return q;
+  if (u < A.minX || u > A.maxX || v < A.minY || v > A.maxY) return q;
+  if (octave < 0 || octave >= A.nlevels) return q;
+  q.r = A.th * A.scale[octave];
+  const int nMinCellX = max(0, (int)floorf((u - A.minX - q.r) * invW));
+  if (nMinCellX >= kGridCols) return q;
+  const int nMaxCellX = min(kGridCols - 1, (int)ceilf((u - A.minX + q.r) * invW));
+  if (nMaxCellX < 0) return q;
+  const int nMinCellY = max(0, (int)floorf((v - A.minY - q.r) * invH));
+  if (nMinCellY >= kGridRows) return q;
+  const int nMaxCellY = min(kGridRows - 1, (int)ceilf((v - A.minY + q.r) * invH));
+  if (nMaxCellY < 0) return q;
+  q.cx0 = nMinCellX; q.cx1 = nMaxCellX; q.cy0 = nMinCellY; q.cy1 = nMaxCellY;
+  q.ok = true;
+  return q;
+}
+
+// shared-memory layout per CTA (dynamic): for each current keypoint: 8 x u32 descriptor, x, y (float),
+// meta = posX | posY<<8 | octave<<16 | ingrid<<24, taken/bin byte.
+__global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cap = A.cap;
+  if (A.onlyIfBelow20 && A.nMatches[p] >= 20) return;
+
+  const pgb_keypoint* curK;
+  const uint8_t* curD;
+  const pgb_keypoint* prevK = nullptr;
+  const uint8_t* qD;
+  int nCur, nQ;
+  float fx = 0.f, fy = 0.f;
+  if (A.consecutive) {
+    curK = A.curK + (size_t)(p + 1) * cap;
+    curD = A.curD + (size_t)(p + 1) * cap * 32;
+    prevK = A.curK + (size_t)p * cap;
+    qD = A.curD + (size_t)p * cap * 32;
+    nCur = A.curN[p + 1];
+    nQ = A.curN[p];
+    fx = A.flow[2 * p]; fy = A.flow[2 * p + 1];
+  } else {
+    curK = A.curK + (size_t)p * cap;
+    curD = A.curD + (size_t)p * cap * 32;
+    qD = A.qD + (size_t)p * cap * 32;
+    nCur = A.curN[p];
+    nQ = A.qN[p];
+  }
+  nCur = min(nCur, cap);
+  nQ = min(nQ, cap);
+
+  uint32_t* sDesc = reinterpret_cast<uint32_t*>(smem);           // [cap][8]
+  float* sX = reinterpret_cast<float*>(sDesc + (size_t)cap * 8); // [cap]
+  float* sY = sX + cap;
+  uint32_t* sMeta = reinterpret_cast<uint32_t*>(sY + cap);       // [cap]
+  float* sAng = reinterpret_cast<float*>(sMeta + cap);           // [cap]
+  unsigned long long* sStage = reinterpret_cast<unsigned long long*>(sAng + cap);  // [warps][kMtStage]; 48*cap bytes in: 16-aligned
+  int* sBin = reinterpret_cast<int*>(sStage + kMtWarps * kMtStage);  // [cap] -1 free, else histogram bin
+  __shared__ int sHist[kHisto];
+  __shared__ int sKeep[3];
+  __shared__ int sNm;
+
+  const float invW = (float)kGridCols / (A.maxX - A.minX);
+  const float invH = (float)kGridRows / (A.maxY - A.minY);
+
+  int* matchOfCur = A.matchOfCur + (size_t)p * cap;
+  for (int i = tid; i < nCur; i += kMtThreads) {
+    const pgb_keypoint k = curK[i];
+    sX[i] = k.x; sY[i] = k.y; sAng[i] = k.angle;
+    const int posX = (int)roundf((k.x - A.minX) * invW), posY = (int)roundf((k.y - A.minY) * invH);
+    const bool in = !(posX < 0 || posX >= kGridCols || posY < 0 || posY >= kGridRows);
+    sMeta[i] = in ? ((uint32_t)posX | ((uint32_t)posY << 8) | ((uint32_t)(k.octave & 0xff) << 16) | (1u << 24)) : 0u;
+    sBin[i] = -1;
+  }
+  for (int i = tid; i < cap; i += kMtThreads) matchOfCur[i] = -1;
+  for (int i = tid; i < nCur * 8; i += kMtThreads) sDesc[i] = reinterpret_cast<const uint32_t*>(curD)[i];
+  if (tid < kHisto) sHist[tid] = 0;
+  if (tid == 0) sNm = 0;
+  __syncthreads();
+
+  unsigned long long* qList = A.qList + (size_t)p * cap * kMtK;
+  int* qCnt = A.qCnt + (size_t)p * cap;
+
+  // ---------------- phase A
+  unsigned long long* stage = sStage + warp * kMtStage;
+  for (int i = warp; i < nQ; i += kMtWarps) {
+    float u, v, ang;
+    int oct;
+    bool valid;
+    if (A.consecutive) {
+      const pgb_keypoint k = prevK[i];
+      u = k.x + fx; v = k.y + fy; oct = k.octave; valid = true; ang = k.angle;
+    } else {
+      u = A.qUV[((size_t)p * cap + i) * 2]; v = A.qUV[((size_t)p * cap + i) * 2 + 1];
+      oct = A.qOct[(size_t)p * cap + i]; valid = A.qValid[(size_t)p * cap + i] != 0;
+    }
+    (void)ang;
+    const QueryWin q = make_window(A, u, v, oct, valid, invW, invH);
+    int cnt = 0;
+    if (q.ok) {
+      uint32_t qd[8];
+#pragma unroll
+      for (int w = 0; w < 8; w++) qd[w] = reinterpret_cast<const uint32_t*>(qD)[(size_t)i * 8 + w];
+      for (int t0 = 0; t0 < nCur; t0 += 32) {
+        const int t = t0 + lane;
+        bool hit = false;
+        unsigned long long key = 0;
+        if (t < nCur) {
+          const uint32_t m = sMeta[t];
+          const int posX = m & 0xff, posY = (m >> 8) & 0xff, o = (m >> 16) & 0xff;
+          if ((m >> 24) && posX >= q.cx0 && posX <= q.cx1 && posY >= q.cy0 && posY <= q.cy1 && o >= q.o0 && o <= q.o1) {
+            const float dx = sX[t] - q.u, dy = sY[t] - q.v;
+            if (fabsf(dx) < q.r && fabsf(dy) < q.r) {
+              const int d = hamming256(qd, sDesc + (size_t)t * 8);
+              key = ((unsigned long long)d << 40) | ((unsigned long long)(posX * kGridRows + posY) << 20) | (unsigned)t;
+              hit = true;
+            }
+          }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int pos = cnt + __popc(bal & ((1u << lane) - 1));
+          if (pos < kMtStage) stage[pos] = key;
+        }
+        cnt += __popc(bal);
+      }
+      __syncwarp();
+      // rank-sort the staged keys (distinct by construction) and keep the kMtK smallest
+      const int ns = min(cnt, kMtStage);
+      for (int a = lane; a < ns; a += 32) {
+        const unsigned long long ka = stage[a];
+        int rank = 0;
+        for (int b = 0; b < ns; b++) rank += (stage[b] < ka);
+        if (rank < kMtK) qList[(size_t)i * kMtK + rank] = ka;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) qCnt[i] = cnt;
+  }
+  __syncthreads();
+
+  // ---------------- phase B: greedy replay in query order
+  if (warp == 0) {
+    const float factor = 1.0f / kHisto;
+    int nm = 0;
+    for (int i = 0; i < nQ; i++) {
+      const int cnt = qCnt[i];
+      if (cnt == 0) continue;
+      const int nl = min(cnt, kMtK);
+      unsigned long long key = ~0ull;
+      bool freeSlot = false;
+      if (lane < nl) {
+        key = qList[(size_t)i * kMtK + lane];
+        freeSlot = sBin[(int)(key & 0xfffff)] == -1;
+      }
+      uint32_t bal = __ballot_sync(0xffffffffu, freeSlot);
+      unsigned long long win = ~0ull;
+      if (bal && cnt <= kMtStage) {
+        win = __shfl_sync(0xffffffffu, key, __ffs(bal) - 1);
+      } else if (cnt > kMtK) {
+        // (the staged list was complete only up to kMtStage candidates; beyond that, and whenever
+        //  every kept candidate is taken while more existed, redo the full sweep skipping taken targets)
+        float u, v;
+        int oct;
+        if (A.consecutive) {
+          const pgb_keypoint k = prevK[i];
+          u = k.x + fx; v = k.y + fy; oct = k.octave;
+        } else {
+          u = A.qUV[((size_t)p * cap + i) * 2]; v = A.qUV[((size_t)p * cap + i) * 2 + 1];
+          oct = A.qOct[(size_t)p * cap + i];
+        }
+        const QueryWin q = make_window(A, u, v, oct, true, invW, invH);
+        uint32_t qd[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) qd[w] = reinterpret_cast<const uint32_t*>(qD)[(size_t)i * 8 + w];
+        unsigned long long best = ~0ull;
+        for (int t = lane; t < nCur; t += 32) {
+          const uint32_t m = sMeta[t];
+          const int posX = m & 0xff, posY = (m >> 8) & 0xff, o = (m >> 16) & 0xff;
+          if ((m >> 24) && sBin[t] == -1 && posX >= q.cx0 && posX <= q.cx1 && posY >= q.cy0 && posY <= q.cy1 &&
+              o >= q.o0 && o <= q.o1 && fabsf(sX[t] - q.u) < q.r && fabsf(sY[t] - q.v) < q.r) {
+            const int d = hamming256(qd, sDesc + (size_t)t * 8);
+            const unsigned long long k2 =
+                ((unsigned long long)d << 40) | ((unsigned long long)(posX * kGridRows + posY) << 20) | (unsigned)t;
+            best = min(best, k2);
+          }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, s));
+        win = best;
+      }
+      if (win != ~0ull) {
+        const int dist = (int)(win >> 40), t = (int)(win & 0xfffff);
+        if (dist <= kThHigh) {
+          int bin = kHisto;  // "assigned, no histogram"
+          if (A.checkOri) {
+            const float qa = A.consecutive ? prevK[i].angle : A.qAng[(size_t)p * cap + i];
+            float rot = qa - sAng[t];
+            if (rot < 0.0f) rot += 360.0f;
+            bin = (int)roundf(rot * factor);
+            if (bin == kHisto) bin = 0;
+          }
+          if (lane == 0) {
+            sBin[t] = bin;
+            matchOfCur[t] = i;
+            if (A.checkOri) sHist[bin]++;
+          }
+          nm++;
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      sNm = nm;
+      int ind1 = -1, ind2 = -1, ind3 = -1;
+      if (A.checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0;
+        for (int b = 0; b < kHisto; b++) {
+          const int s = sHist[b];
+          if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+          else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+          else if (s > max3) { max3 = s; ind3 = b; }
+        }
+        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+      }
+      sKeep[0] = ind1; sKeep[1] = ind2; sKeep[2] = ind3;
+    }
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    int removed = 0;
+    for (int t = tid; t < nCur; t += kMtThreads) {
+      const int b = sBin[t];
+      if (b >= 0 && b < kHisto && b != sKeep[0] && b != sKeep[1] && b != sKeep[2]) {
+        matchOfCur[t] = -1;
+        removed++;
+      }
+    }
+    if (removed) atomicSub(&sNm, removed);
+    __syncthreads();
+  }
+  if (tid == 0) A.nMatches[p] = sNm;
+}
+
+size_t match_smem_bytes(int cap) {
+  size_t b = (size_t)cap * 8 * 4 + (size_t)cap * 4 * 4;
+  b += (size_t)kMtWarps * kMtStage * 8;
+  b += (size_t)cap * 4;
+  return b + 16;
+}
+
+__global__ void k_desc_distance(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n,
+                                int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = hamming256(reinterpret_cast<const uint32_t*>(a) + (size_t)i * 8, reinterpret_cast<const uint32_t*>(b) + (size_t)i * 8);
+}
+
+}  // namespace pgb
+
+using namespace pgb;
+
+struct pgb_matcher {
+  int device = 0, checkOri = 1, maxFeats = 0, maxBatch = 0;
+  float nnratio = 0.f;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  DevBuf<unsigned long long> qList;
+  DevBuf<int> qCnt;
+  // staging for host-buffer calls
+  DevBuf<pgb_keypoint> dK;
+  DevBuf<uint8_t> dD, dQD, dQV;
+  DevBuf<float> dUV, dAng, dFlow;
+  DevBuf<int> dN, dQN, dOct, dMatch, dNm;
+  size_t smemConfigured = 0;
+};
+
+namespace {
+
+int launch_match(pgb_matcher* m, MatchArgs& A, int nPairs) {
+  if (A.cap > m->maxFeats) return fail(PGB_ERR_CAPACITY, "cap %d exceeds the matcher's max_feats %d", A.cap, m->maxFeats);
+  if (nPairs > m->maxBatch) return fail(PGB_ERR_CAPACITY, "n_pairs %d exceeds the matcher's max_batch %d", nPairs, m->maxBatch);
+  const size_t smem = match_smem_bytes(A.cap);
+  if (smem > 227 * 1024) return fail(PGB_ERR_CAPACITY, "cap %d needs %zu B of shared memory (max 227 KB)", A.cap, smem);
+  if (smem > 48 * 1024 && smem > m->smemConfigured) {
+    PGB_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    m->smemConfigured = smem;
+  }
+  A.qList = m->qList.p;
+  A.qCnt = m->qCnt.p;
+  k_match<<<nPairs, kMtThreads, smem, m->stream>>>(A);
+  PGB_CHECK_LAUNCH();
+  return PGB_OK;
+}
+
+void fill_common(MatchArgs& A, int cap, float minX, float maxX, float minY, float maxY, float th, const float* sf,
+                 int nlevels, int checkOri) {
+  memset(&A, 0, sizeof A);
+  A.cap = cap; A.nlevels = nlevels; A.checkOri = checkOri;
+  A.minX = minX; A.maxX = maxX; A.minY = minY; A.maxY = maxY; A.th = th;
+  for (int i = 0; i < nlevels && i < 16; i++) A.scale[i] = sf[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+pgb_matcher* pgb_matcher_create(int device, float nnratio, int check_orientation, int max_feats, int max_batch,
+                                void* stream) {
+  if (max_feats <= 0 || max_batch <= 0 || max_feats > (1 << 20) - 1) {
+    fail(PGB_ERR_INVALID, "pgb_matcher_create: invalid argument");
+    return nullptr;
+  }
+  if (use_device(device)) return nullptr;
+  pgb_matcher* m = new pgb_matcher;
+  m->device = device; m->nnratio = nnratio; m->checkOri = check_orientation ? 1 : 0;
+  m->maxFeats = max_feats; m->maxBatch = max_batch;
+  if (stream) m->stream = (cudaStream_t)stream;
+  else {
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      fail(PGB_ERR_CUDA, "cudaStreamCreate failed");
+      delete m;
+      return nullptr;
+    }
+    m->ownStream = true;
+  }
+  const size_t n = (size_t)max_feats * max_batch;
+  if (m->qList.alloc(n * kMtK) || m->qCnt.alloc(n)) {
+    pgb_matcher_destroy(m);
+    return nullptr;
+  }
+  return m;
+}
+
+void pgb_matcher_destroy(pgb_matcher* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->ownStream && m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int pgb_match_by_projection(pgb_matcher* m, int n_pairs, int cap, const pgb_keypoint* cur_kps, const uint8_t* cur_desc,
+                            const int32_t* cur_counts, const float* q_uv, const int32_t* q_octave,
+                            const float* q_angle, const uint8_t* q_desc, const uint8_t* q_valid,
+                            const int32_t* q_counts, float min_x, float max_x, float min_y, float max_y, float th,
+                            const float* scale_factors, int nlevels, int32_t* match_of_cur, int32_t* n_matches,
+                            int is_device) {
+  if (!m) return fail(PGB_ERR_INVALID, "null handle");
+  if (n_pairs < 0 || cap <= 0 || nlevels <= 0 || nlevels > 16 || !scale_factors || !(max_x > min_x) || !(max_y > min_y))
+    return fail(PGB_ERR_INVALID, "pgb_match_by_projection: invalid argument");
+  if (n_pairs == 0) return PGB_OK;
+  if (!cur_kps || !cur_desc || !cur_counts || !q_uv || !q_octave || !q_angle || !q_desc || !q_valid || !q_counts ||
+      !match_of_cur || !n_matches)
+    return fail(PGB_ERR_INVALID, "pgb_match_by_projection: null buffer");
+  PGB_CUDA(cudaSetDevice(m->device));
+  MatchArgs A;
+  fill_common(A, cap, min_x, max_x, min_y, max_y, th, scale_factors, nlevels, m->checkOri);
+  const size_t n = (size_t)n_pairs * cap;
+  if (is_device) {
+    A.curK = cur_kps; A.curD = cur_desc; A.curN = cur_counts; A.qUV = q_uv; A.qOct = q_octave; A.qAng = q_angle;
+    A.qD = q_desc; A.qValid = q_valid; A.qN = q_counts; A.matchOfCur = match_of_cur; A.nMatches = n_matches;
+    return launch_match(m, A, n_pairs);
+  }
+  if (m->dK.n < n) {
+    if (m->dK.alloc(n) || m->dD.alloc(n * 32) || m->dQD.alloc(n * 32) || m->dQV.alloc(n) || m->dUV.alloc(n * 2) ||
+        m->dAng.alloc(n) || m->dOct.alloc(n) || m->dMatch.alloc(n))
+      return PGB_ERR_CUDA;
+  }
+  if (m->dN.n < (size_t)n_pairs) {
+    if (m->dN.alloc(n_pairs) || m->dQN.alloc(n_pairs) || m->dNm.alloc(n_pairs)) return PGB_ERR_CUDA;
+  }
+  cudaStream_t s = m->stream;
+  PGB_CUDA(cudaMemcpyAsync(m->dK.p, cur_kps, n * sizeof(pgb_keypoint), cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dD.p, cur_desc, n * 32, cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dQD.p, q_desc, n * 32, cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dQV.p, q_valid, n, cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dUV.p, q_uv, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dAng.p, q_angle, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dOct.p, q_octave, n * sizeof(int), cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dN.p, cur_counts, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(m->dQN.p, q_counts, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+  A.curK = m->dK.p; A.curD = m->dD.p; A.curN = m->dN.p; A.qUV = m->dUV.p; A.qOct = m->dOct.p; A.qAng = m->dAng.p;
+  A.qD = m->dQD.p; A.qValid = m->dQV.p; A.qN = m->dQN.p; A.matchOfCur = m->dMatch.p; A.nMatches = m->dNm.p;
+  int rc = launch_match(m, A, n_pairs);
+  if (rc) return rc;
+  PGB_CUDA(cudaMemcpyAsync(match_of_cur, m->dMatch.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PGB_CUDA(cudaMemcpyAsync(n_matches, m->dNm.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PGB_CUDA(cudaStreamSynchronize(s));
+  return PGB_OK;
+}
+
+int pgb_match_consecutive(pgb_matcher* m, int n_pairs, int cap, const pgb_keypoint* kps, const uint8_t* desc,
+                          const int32_t* counts, const float* flow, float max_x, float max_y, float th,
+                          const float* scale_factors, int nlevels, int32_t* match_of_cur, int32_t* n_matches) {
+  if (!m) return fail(PGB_ERR_INVALID, "null handle");
+  if (n_pairs < 0 || cap <= 0 || nlevels <= 0 || nlevels > 16 || !scale_factors || !(max_x > 0) || !(max_y > 0))
+    return fail(PGB_ERR_INVALID, "pgb_match_consecutive: invalid argument");
+  if (n_pairs == 0) return PGB_OK;
+  if (!kps || !desc || !counts || !flow || !match_of_cur || !n_matches)
+    return fail(PGB_ERR_INVALID, "pgb_match_consecutive: null buffer");
+  PGB_CUDA(cudaSetDevice(m->device));
+  MatchArgs A;
+  fill_common(A, cap, 0.f, max_x, 0.f, max_y, th, scale_factors, nlevels, m->checkOri);
+  A.consecutive = 1;
+  A.curK = kps; A.curD = desc; A.curN = counts; A.flow = flow;
+  A.matchOfCur = match_of_cur; A.nMatches = n_matches;
+  int rc = launch_match(m, A, n_pairs);
+  if (rc) return rc;
+  // Tracking.cc:879-883: wider window when fewer than 20 matches; pairs that already have >= 20 exit at once.
+  A.th = 2 * th;
+  A.onlyIfBelow20 = 1;
+  return launch_match(m, A, n_pairs);
+}
+
+int pgb_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist, int is_device, void* stream) {
+  if (n < 0 || (n > 0 && (!a || !b || !dist))) return fail(PGB_ERR_INVALID, "pgb_descriptor_distance: invalid argument");
+  if (n == 0) return PGB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (is_device) {
+    k_desc_distance<<<(n + 255) / 256, 256, 0, s>>>(a, b, n, dist);
+    PGB_CHECK_LAUNCH();
+    return PGB_OK;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || use_device(dev)) return PGB_ERR_CUDA;
+  DevBuf<uint8_t> da, db;
+  DevBuf<int> dd;
+  if (da.alloc((size_t)n * 32) || db.alloc((size_t)n * 32) || dd.alloc(n)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemcpyAsync(da.p, a, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(db.p, b, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+  k_desc_distance<<<(n + 255) / 256, 256, 0, s>>>(da.p, db.p, n, dd.p);
+  PGB_CHECK_LAUNCH();
+  PGB_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PGB_CUDA(cudaStreamSynchronize(s));
+  return PGB_OK;
+}
+
+}  // extern "C"

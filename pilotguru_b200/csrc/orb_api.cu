@@ -1,0 +1,455 @@
+// C-ABI of the ORB extractor (include/pgb200.h, "ORB extractor" section): handle, geometry, orchestration.
+// Host-side restatement of the reference's constructor tables (ORBextractor.cc:410-470) and of the per-level
+// grid arithmetic (ORBextractor.cc:769-787, :542-545), which must use the same float expressions.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "orb_kernels.cuh"
+
+namespace pgb {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int use_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(PGB_ERR_CUDA, "no CUDA device available (%s); libpgb200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(PGB_ERR_INVALID, "device %d out of range (have %d)", device, n);
+  PGB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp p;
+  PGB_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return fail(PGB_ERR_CUDA, "device %d is sm_%d%d; libpgb200 is built for sm_100a only", device, p.major, p.minor);
+  return PGB_OK;
+}
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+}  // namespace pgb
+
+using namespace pgb;
+
+struct pgb_orb {
+  int device = 0;
+  int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+  float scaleFactor = 0;
+  std::vector<float> scale, invScale, sigma2, invSigma2;
+  std::vector<int> nPerLevel;
+  int maxW = 0, maxH = 0, maxBatch = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+
+  OrbGeo capGeo{};  // geometry at (maxW, maxH): sizes the buffers
+  OrbGeo geo{};     // geometry of the last call
+  int curW = 0, curH = 0, curFrames = 0;
+
+  DevBuf<uint8_t> pyr, score;
+  DevBuf<uint32_t> slots;
+  DevBuf<int> cellCnt, lvlCnt, err, counts;
+  DevBuf<unsigned long long> cand;
+  DevBuf<StagedKp> staged;
+  DevBuf<ResizeTab> xtab, ytab;
+  std::vector<int> xtabOff, ytabOff;
+  DevBuf<pgb_keypoint> kps;
+  DevBuf<uint8_t> desc;
+  int outCap = 0;
+  DevBuf<uint8_t> tmpLevel;
+};
+
+namespace {
+
+int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
+  memset(g, 0, sizeof *g);
+  g->nlevels = o->nlevels;
+  g->iniTh = o->iniTh;
+  g->minTh = o->minTh;
+  g->qTh = o->minTh >= 2 ? (o->minTh + 1) / 4 : 0;
+  unsigned long long off = 0, slotOff = 0, candOff = 0;
+  int cellBase = 0, tileBase = 0, kpBase = 0, maxNode = 1;
+  for (int l = 0; l < o->nlevels; l++) {
+    LevelGeo& L = g->lv[l];
+    L.w = cv_round_f((float)w * o->invScale[l]);
+    L.h = cv_round_f((float)h * o->invScale[l]);
+    if (L.w < 2 * kEdge + 1 || L.h < 2 * kEdge + 1)
+      return fail(PGB_ERR_INVALID, "level %d of a %dx%d image is %dx%d: too small for the 19-px border", l, w, h, L.w, L.h);
+    L.pitch = round_up(L.w, 64);
+    L.off = off;
+    off += (unsigned long long)L.pitch * L.h;
+    off = (off + 255) & ~255ull;
+    L.maxBX = L.w - kMinBorder;
+    L.maxBY = L.h - kMinBorder;
+    const float width = (float)(L.maxBX - kMinBorder), height = (float)(L.maxBY - kMinBorder);
+    L.nCols = (int)(width / 30.f);
+    L.nRows = (int)(height / 30.f);
+    if (L.nCols <= 0 || L.nRows <= 0)
+      return fail(PGB_ERR_INVALID, "level %d (%dx%d) has no FAST cell (the reference divides by zero here)", l, L.w, L.h);
+    L.wCell = (int)std::ceil(width / L.nCols);
+    L.hCell = (int)std::ceil(height / L.nRows);
+    L.cellBase = cellBase;
+    cellBase += L.nCols * L.nRows;
+    L.slotCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+    L.slotBase = slotOff;
+    slotOff += (unsigned long long)L.nCols * L.nRows * L.slotCap;
+    L.quota = o->nPerLevel[l];
+    L.nIni = (int)std::round((float)(L.maxBX - kMinBorder) / (L.maxBY - kMinBorder));
+    if (L.nIni <= 0)
+      return fail(PGB_ERR_INVALID, "level %d (%dx%d): width/height ratio rounds to 0 root nodes", l, L.w, L.h);
+    L.hX = (float)(L.maxBX - kMinBorder) / L.nIni;
+    L.candCap = L.nCols * L.nRows * L.slotCap;
+    L.candBase = candOff;
+    candOff += (unsigned long long)L.candCap;
+    L.nodeCap = std::max(L.quota + 4, 4 * L.nIni + 1);
+    maxNode = std::max(maxNode, L.nodeCap);
+    L.kpBase = kpBase;
+    kpBase += L.nodeCap;
+    L.tilesX = (L.w + kFtW - 1) / kFtW;
+    L.tilesY = (L.h + kFtH - 1) / kFtH;
+    L.tileBase = tileBase;
+    tileBase += L.tilesX * L.tilesY;
+    L.scale = o->scale[l];
+    L.patchSize = (int)(31 * o->scale[l]);
+    if (L.maxBX - kMinBorder > 4095 || L.maxBY - kMinBorder > 4095)
+      return fail(PGB_ERR_INVALID, "images wider/taller than 4127 px are not supported");
+  }
+  g->totalCells = cellBase;
+  g->totalTiles = tileBase;
+  g->kpCapInternal = kpBase;
+  g->maxNodeCap = maxNode;
+  g->frameStride = off;
+  g->slotsPerFrame = slotOff;
+  g->candPerFrame = candOff;
+  return PGB_OK;
+}
+
+// cv::resize(INTER_LINEAR) coefficient tables (OpenCV imgproc resize.cpp)
+void make_resize_tab(int src, int dst, bool clampCoef, std::vector<ResizeTab>& out) {
+  out.resize(dst);
+  const double scale = 1.0 / ((double)dst / src);
+  for (int d = 0; d < dst; d++) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(f);
+    f -= s;
+    if (clampCoef) {
+      if (s < 0) { f = 0; s = 0; }
+      if (s >= src - 1) { f = 0; s = src - 1; }
+    }
+    out[d].s = (short)s;
+    out[d].a0 = (short)cv_round_f((1.f - f) * 2048);
+    out[d].a1 = (short)cv_round_f(f * 2048);
+    out[d].pad = 0;
+  }
+}
+
+int upload_tabs(pgb_orb* o) {
+  std::vector<ResizeTab> xs, ys, t;
+  o->xtabOff.assign(o->nlevels, 0);
+  o->ytabOff.assign(o->nlevels, 0);
+  for (int l = 1; l < o->nlevels; l++) {
+    o->xtabOff[l] = (int)xs.size();
+    make_resize_tab(o->geo.lv[l - 1].w, o->geo.lv[l].w, true, t);
+    xs.insert(xs.end(), t.begin(), t.end());
+    o->ytabOff[l] = (int)ys.size();
+    make_resize_tab(o->geo.lv[l - 1].h, o->geo.lv[l].h, false, t);
+    ys.insert(ys.end(), t.begin(), t.end());
+  }
+  if (xs.size() > o->xtab.n || ys.size() > o->ytab.n) return fail(PGB_ERR_CAPACITY, "resize tables exceed capacity");
+  if (!xs.empty()) PGB_CUDA(cudaMemcpyAsync(o->xtab.p, xs.data(), xs.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, o->stream));
+  if (!ys.empty()) PGB_CUDA(cudaMemcpyAsync(o->ytab.p, ys.data(), ys.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));  // the host vectors die here
+  return PGB_OK;
+}
+
+int set_geometry(pgb_orb* o, int w, int h) {
+  if (w == o->curW && h == o->curH) return PGB_OK;
+  OrbGeo g;
+  int rc = build_geo(o, w, h, &g);
+  if (rc) return rc;
+  const OrbGeo& c = o->capGeo;
+  if (g.frameStride > c.frameStride || g.slotsPerFrame > c.slotsPerFrame || g.candPerFrame > c.candPerFrame ||
+      g.totalCells > c.totalCells || g.kpCapInternal > c.kpCapInternal || g.maxNodeCap > c.maxNodeCap)
+    return fail(PGB_ERR_CAPACITY, "%dx%d frames need more scratch than the %dx%d the handle was created for", w, h,
+                o->maxW, o->maxH);
+  o->geo = g;
+  o->curW = w;
+  o->curH = h;
+  return upload_tabs(o);
+}
+
+int check_err_flag(pgb_orb* o) {
+  int e = 0;
+  PGB_CUDA(cudaMemcpyAsync(&e, o->err.p, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  if (e) {
+    cudaMemsetAsync(o->err.p, 0, sizeof(int), o->stream);
+    return fail(PGB_ERR_CAPACITY, "device-side capacity flag 0x%x (1=candidates 2=octree nodes 4=output cap 8=cell chunks)", e);
+  }
+  return PGB_OK;
+}
+
+int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap) {
+  const OrbGeo& g = o->geo;
+  const int n = o->curFrames;
+  for (int s = from; s <= to; s++) {
+    switch (s) {
+      case 0:
+        for (int l = 1; l < g.nlevels; l++)
+          launch_pyramid_level(g, l, n, o->pyr.p, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], o->stream);
+        break;
+      case 1: launch_fast_score(g, n, o->pyr.p, o->score.p, o->stream); break;
+      case 2: launch_cells(g, n, o->score.p, o->slots.p, o->cellCnt.p, o->err.p, o->stream); break;
+      case 3: launch_octree(g, n, o->slots.p, o->cellCnt.p, o->cand.p, o->staged.p, o->lvlCnt.p, o->err.p, o->stream); break;
+      case 4: launch_orient_desc(g, n, o->pyr.p, o->staged.p, o->lvlCnt.p, kps, desc, counts, cap, o->err.p, o->stream); break;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PGB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return PGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pgb_last_error(void) { return g_last_error.c_str(); }
+int pgb_version(void) { return 100; }
+uint64_t pgb_launch_count(void) { return g_launches.load(); }
+
+pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+                        int max_width, int max_height, int max_batch, void* stream) {
+  if (nfeatures <= 0 || nlevels <= 0 || nlevels > kMaxLevels || !(scale_factor > 1.0f) || max_width <= 0 ||
+      max_height <= 0 || max_batch <= 0 || ini_th_fast < min_th_fast || min_th_fast < 0 || ini_th_fast > 255) {
+    fail(PGB_ERR_INVALID, "pgb_orb_create: invalid argument");
+    return nullptr;
+  }
+  if (use_device(device)) return nullptr;
+  pgb_orb* o = new pgb_orb;
+  o->device = device;
+  o->nfeatures = nfeatures; o->nlevels = nlevels; o->iniTh = ini_th_fast; o->minTh = min_th_fast;
+  o->scaleFactor = scale_factor;
+  o->maxW = max_width; o->maxH = max_height; o->maxBatch = max_batch;
+  // scale tables and per-level quotas, ORBextractor.cc:415-447 (the fork sizes them nlevels+1; [0,nlevels) is read)
+  o->scale.resize(nlevels + 1); o->sigma2.resize(nlevels + 1);
+  o->invScale.resize(nlevels + 1); o->invSigma2.resize(nlevels + 1);
+  o->scale[0] = 1.0f; o->sigma2[0] = 1.0f;
+  for (int i = 1; i <= nlevels; i++) {
+    o->scale[i] = o->scale[i - 1] * scale_factor;
+    o->sigma2[i] = o->scale[i] * o->scale[i];
+  }
+  for (int i = 0; i <= nlevels; i++) {
+    o->invScale[i] = 1.0f / o->scale[i];
+    o->invSigma2[i] = 1.0f / o->sigma2[i];
+  }
+  o->nPerLevel.resize(nlevels + 1);
+  const float factor = 1.0f / scale_factor;
+  float nDesired = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels));
+  int sum = 0;
+  for (int l = 0; l < nlevels; l++) {
+    o->nPerLevel[l] = cv_round_f(nDesired);
+    sum += o->nPerLevel[l];
+    nDesired *= factor;
+  }
+  o->nPerLevel[nlevels] = std::max(nfeatures - sum, 0);
+
+  auto bail = [&](const char* what) -> pgb_orb* {
+    std::string keep = g_last_error;
+    pgb_orb_destroy(o);
+    g_last_error = keep.empty() ? what : keep;
+    return nullptr;
+  };
+  if (build_geo(o, max_width, max_height, &o->capGeo)) return bail("geometry");
+  if (stream) o->stream = (cudaStream_t)stream;
+  else {
+    if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+    o->ownStream = true;
+  }
+  const OrbGeo& c = o->capGeo;
+  const size_t B = (size_t)max_batch;
+  o->outCap = 0;
+  for (int l = 0; l < nlevels; l++) o->outCap += c.lv[l].nodeCap;
+  int tabX = 0, tabY = 0;
+  for (int l = 1; l < nlevels; l++) { tabX += c.lv[l].w + 8; tabY += c.lv[l].h + 8; }
+  if (o->pyr.alloc(B * c.frameStride) || o->score.alloc(B * c.frameStride) || o->slots.alloc(B * c.slotsPerFrame) ||
+      o->cellCnt.alloc(B * c.totalCells) || o->lvlCnt.alloc(B * nlevels) || o->err.alloc(1) || o->counts.alloc(B) ||
+      o->cand.alloc(B * c.candPerFrame) || o->staged.alloc(B * c.kpCapInternal) || o->xtab.alloc(tabX + 8) ||
+      o->ytab.alloc(tabY + 8) || o->kps.alloc(B * o->outCap) || o->desc.alloc(B * o->outCap * 32) ||
+      o->tmpLevel.alloc((size_t)max_width * max_height))
+    return bail("cudaMalloc failed");
+  if (cudaMemsetAsync(o->err.p, 0, sizeof(int), o->stream) != cudaSuccess ||
+      cudaMemsetAsync(o->pyr.p, 0, B * c.frameStride, o->stream) != cudaSuccess ||
+      cudaMemsetAsync(o->score.p, 0, B * c.frameStride, o->stream) != cudaSuccess ||
+      cudaStreamSynchronize(o->stream) != cudaSuccess)
+    return bail("cudaMemset failed");
+  return o;
+}
+
+void pgb_orb_destroy(pgb_orb* o) {
+  if (!o) return;
+  cudaSetDevice(o->device);
+  if (o->stream) cudaStreamSynchronize(o->stream);
+  if (o->ownStream && o->stream) cudaStreamDestroy(o->stream);
+  delete o;
+}
+
+int pgb_orb_levels(const pgb_orb* o) { return o ? o->nlevels : PGB_ERR_INVALID; }
+float pgb_orb_scale_factor(const pgb_orb* o) { return o ? o->scaleFactor : 0.f; }
+int pgb_orb_scale_factors(const pgb_orb* o, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2) {
+  if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  for (int i = 0; i < o->nlevels; i++) {
+    if (scale) scale[i] = o->scale[i];
+    if (inv_scale) inv_scale[i] = o->invScale[i];
+    if (sigma2) sigma2[i] = o->sigma2[i];
+    if (inv_sigma2) inv_sigma2[i] = o->invSigma2[i];
+  }
+  return PGB_OK;
+}
+int pgb_orb_features_per_level(const pgb_orb* o, int32_t* n) {
+  if (!o || !n) return fail(PGB_ERR_INVALID, "null argument");
+  for (int i = 0; i < o->nlevels; i++) n[i] = o->nPerLevel[i];
+  return PGB_OK;
+}
+int pgb_orb_max_keypoints(const pgb_orb* o) { return o ? o->outCap : PGB_ERR_INVALID; }
+int pgb_orb_level_size(const pgb_orb* o, int width, int height, int level, int* w, int* h) {
+  if (!o || level < 0 || level >= o->nlevels) return fail(PGB_ERR_INVALID, "bad level");
+  *w = cv_round_f((float)width * o->invScale[level]);
+  *h = cv_round_f((float)height * o->invScale[level]);
+  return PGB_OK;
+}
+void* pgb_orb_stream(pgb_orb* o) { return o ? (void*)o->stream : nullptr; }
+
+int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames, int width, int height, size_t pitch,
+                    size_t frame_stride, pgb_keypoint* kps, uint8_t* desc, int32_t* counts, int cap) {
+  if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  if (n_frames < 0 || n_frames > o->maxBatch) return fail(PGB_ERR_INVALID, "n_frames %d outside [0,%d]", n_frames, o->maxBatch);
+  if (!counts || (cap > 0 && (!kps || !desc)) || cap < 0) return fail(PGB_ERR_INVALID, "null output buffer");
+  PGB_CUDA(cudaSetDevice(o->device));
+  if (n_frames == 0) return PGB_OK;
+  if (width == 0 || height == 0) {  // empty image: the reference returns without touching the outputs (:1045)
+    if (is_device) PGB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_frames, o->stream));
+    else memset(counts, 0, sizeof(int32_t) * n_frames);
+    return PGB_OK;
+  }
+  if (!gray || width < 0 || height < 0 || pitch < (size_t)width) return fail(PGB_ERR_INVALID, "bad image arguments");
+  int rc = set_geometry(o, width, height);
+  if (rc) return rc;
+  const OrbGeo& g = o->geo;
+  o->curFrames = n_frames;
+  const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (frame_stride == pitch * (size_t)height && n_frames > 1 && false) {
+    // (a single 3-D copy would go here; the per-frame 2-D copies below are already asynchronous)
+  }
+  for (int f = 0; f < n_frames; f++)
+    PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
+                               gray + (size_t)f * frame_stride, pitch, width, height, kind, o->stream));
+  if (is_device) {
+    if (cap < o->outCap) {
+      // caller-provided capacity smaller than the worst case is allowed; overflow raises the device flag
+    }
+    rc = run_stages(o, 0, 4, kps, desc, counts, cap);
+    return rc;
+  }
+  rc = run_stages(o, 0, 4, o->kps.p, o->desc.p, o->counts.p, o->outCap);
+  if (rc) return rc;
+  std::vector<int32_t> hc(n_frames);
+  PGB_CUDA(cudaMemcpyAsync(hc.data(), o->counts.p, sizeof(int32_t) * n_frames, cudaMemcpyDeviceToHost, o->stream));
+  rc = check_err_flag(o);  // synchronises
+  if (rc) return rc;
+  for (int f = 0; f < n_frames; f++) {
+    if (hc[f] > cap) return fail(PGB_ERR_CAPACITY, "frame %d produced %d keypoints, caller cap is %d", f, hc[f], cap);
+    counts[f] = hc[f];
+    if (hc[f] > 0) {
+      PGB_CUDA(cudaMemcpyAsync(kps + (size_t)f * cap, o->kps.p + (size_t)f * o->outCap, sizeof(pgb_keypoint) * hc[f],
+                               cudaMemcpyDeviceToHost, o->stream));
+      PGB_CUDA(cudaMemcpyAsync(desc + (size_t)f * cap * 32, o->desc.p + (size_t)f * o->outCap * 32, (size_t)32 * hc[f],
+                               cudaMemcpyDeviceToHost, o->stream));
+    }
+  }
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  return PGB_OK;
+}
+
+int pgb_orb_check(pgb_orb* o) {
+  if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  PGB_CUDA(cudaSetDevice(o->device));
+  return check_err_flag(o);
+}
+
+int pgb_orb_run_stage(pgb_orb* o, int which) {
+  if (!o || which < 0 || which > 4) return fail(PGB_ERR_INVALID, "bad stage");
+  if (o->curFrames <= 0) return fail(PGB_ERR_INVALID, "no frames resident: call pgb_orb_extract first");
+  PGB_CUDA(cudaSetDevice(o->device));
+  return run_stages(o, which, which, o->kps.p, o->desc.p, o->counts.p, o->outCap);
+}
+
+static int copy_level_out(pgb_orb* o, const uint8_t* base, int frame, int level, uint8_t* out, int* w, int* h) {
+  if (!o || frame < 0 || frame >= o->curFrames || level < 0 || level >= o->nlevels)
+    return fail(PGB_ERR_INVALID, "bad frame/level");
+  PGB_CUDA(cudaSetDevice(o->device));
+  const LevelGeo& L = o->geo.lv[level];
+  if (w) *w = L.w;
+  if (h) *h = L.h;
+  if (!out) return PGB_OK;
+  PGB_CUDA(cudaMemcpy2DAsync(out, L.w, base + (size_t)frame * o->geo.frameStride + L.off, L.pitch, L.w, L.h,
+                             cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  return PGB_OK;
+}
+
+int pgb_orb_get_level(pgb_orb* o, int frame, int level, uint8_t* out, int* w, int* h) {
+  return copy_level_out(o, o ? o->pyr.p : nullptr, frame, level, out, w, h);
+}
+int pgb_orb_get_score_map(pgb_orb* o, int frame, int level, uint8_t* out, int* w, int* h) {
+  return copy_level_out(o, o ? o->score.p : nullptr, frame, level, out, w, h);
+}
+
+int pgb_orb_get_blurred_level(pgb_orb* o, int frame, int level, uint8_t* out, int* w, int* h) {
+  if (!o || frame < 0 || frame >= o->curFrames || level < 0 || level >= o->nlevels)
+    return fail(PGB_ERR_INVALID, "bad frame/level");
+  PGB_CUDA(cudaSetDevice(o->device));
+  const LevelGeo& L = o->geo.lv[level];
+  if (w) *w = L.w;
+  if (h) *h = L.h;
+  if (!out) return PGB_OK;
+  launch_blur_level(o->geo, level, frame, o->pyr.p, o->tmpLevel.p, o->stream);
+  PGB_CUDA(cudaGetLastError());
+  PGB_CUDA(cudaMemcpyAsync(out, o->tmpLevel.p, (size_t)L.w * L.h, cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  return PGB_OK;
+}
+
+int pgb_orb_get_candidates(pgb_orb* o, int frame, int level, int32_t* xyr, int cap, int32_t* n) {
+  if (!o || frame < 0 || frame >= o->curFrames || level < 0 || level >= o->nlevels || !n)
+    return fail(PGB_ERR_INVALID, "bad frame/level");
+  PGB_CUDA(cudaSetDevice(o->device));
+  const OrbGeo& g = o->geo;
+  const LevelGeo& L = g.lv[level];
+  const int nCells = L.nCols * L.nRows;
+  std::vector<int> cnt(nCells);
+  PGB_CUDA(cudaMemcpyAsync(cnt.data(), o->cellCnt.p + (size_t)frame * g.totalCells + L.cellBase, sizeof(int) * nCells,
+                           cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  long total = 0;
+  for (int c : cnt) total += c;
+  *n = (int32_t)total;
+  if (!xyr) return PGB_OK;
+  if (total > cap) return fail(PGB_ERR_CAPACITY, "%ld candidates, cap %d", total, cap);
+  std::vector<uint32_t> sl((size_t)nCells * L.slotCap);
+  PGB_CUDA(cudaMemcpyAsync(sl.data(), o->slots.p + (size_t)frame * g.slotsPerFrame + L.slotBase,
+                           sizeof(uint32_t) * sl.size(), cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  size_t k = 0;
+  for (int c = 0; c < nCells; c++)
+    for (int q = 0; q < cnt[c]; q++) {
+      const uint32_t p = sl[(size_t)c * L.slotCap + q];
+      xyr[3 * k] = (int)(p & 0xfff);
+      xyr[3 * k + 1] = (int)((p >> 12) & 0xfff);
+      xyr[3 * k + 2] = (int)(p >> 24);
+      k++;
+    }
+  return PGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,756 @@
+// sm_100a kernels of the ORB extraction path.  All arithmetic is integer or fp32 with explicit round-to-nearest
+// intrinsics (no FMA contraction), so results are bit-exact against the CPU oracle.
+//
+// Reference semantics (file:line in waiwnf/pilotguru, thirdparty/orb-slam2/src/ORBextractor.cc):
+//   k_pyramid      ComputePyramid :1106-1131 -> cv::resize(INTER_LINEAR) fixed-point bilinear
+//   k_fast_score   cv::FAST(TYPE_9_16) corner score (call sites :809,:814)
+//   k_cells        per-cell threshold iniThFAST/minThFAST + 3x3 NMS :789-829
+//   k_octree       DistributeOctTree :539-763, DivideNode :481-537
+//   k_orient_desc  IC_Angle :77-104, GaussianBlur :1084-1085, computeOrbDescriptor :108-147, rescale :1094-1100
+#include <cuda_runtime.h>
+
+#include "../../include/pgb200_orb_pattern.h"
+#include "common.cuh"
+#include "orb_kernels.cuh"
+
+namespace pgb {
+
+// =========================================================================================== K1 pyramid
+// One thread produces 4 horizontally adjacent destination pixels (one 32-bit store).
+__global__ void __launch_bounds__(256) k_pyramid(OrbGeo g, int level, uint8_t* __restrict__ pyr,
+                                                 const ResizeTab* __restrict__ xtab,
+                                                 const ResizeTab* __restrict__ ytab) {
+  const LevelGeo& D = g.lv[level];
+  const LevelGeo& S = g.lv[level - 1];
+  const int wq = (D.w + 3) >> 2;
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (xq >= wq) return;
+  uint8_t* frame = pyr + (size_t)blockIdx.z * g.frameStride;
+  const uint8_t* src = frame + S.off;
+  const ResizeTab ty = ytab[y];
+  const int sy0 = min(max((int)ty.s, 0), S.h - 1), sy1 = min(max((int)ty.s + 1, 0), S.h - 1);
+  const uint8_t* S0 = src + (size_t)sy0 * S.pitch;
+  const uint8_t* S1 = src + (size_t)sy1 * S.pitch;
+  uint32_t packed = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int x = xq * 4 + i;
+    if (x < D.w) {
+      const ResizeTab tx = xtab[x];
+      const int sx = tx.s, sx1 = min(sx + 1, S.w - 1);
+      const int r0 = (int)__ldg(S0 + sx) * tx.a0 + (int)__ldg(S0 + sx1) * tx.a1;
+      const int r1 = (int)__ldg(S1 + sx) * tx.a0 + (int)__ldg(S1 + sx1) * tx.a1;
+      const int v = ((((int)ty.a0 * (r0 >> 4)) >> 16) + (((int)ty.a1 * (r1 >> 4)) >> 16) + 2) >> 2;
+      packed |= (uint32_t)(v & 0xff) << (8 * i);
+    }
+  }
+  *reinterpret_cast<uint32_t*>(frame + D.off + (size_t)y * D.pitch + (size_t)xq * 4) = packed;
+}
+
+void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
+                          const ResizeTab* ytab, cudaStream_t st) {
+  const LevelGeo& D = g.lv[level];
+  dim3 grid((((D.w + 3) >> 2) + 255) / 256, D.h, nFrames);
+  k_pyramid<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab);
+  PGB_LAUNCHED();
+}
+
+// =========================================================================================== K2 FAST-9 score
+// Exact "bam" of one pixel from a shared-memory tile: max over the 16 contiguous 9-arcs of
+// max(min(v - p_k), min(p_k - v)).  Both polarities ride in the two s16 halves of one register and the 9-wide
+// sliding minimum is two rounds of the 3-input DPX min (VIMNMX3.S16x2).
+__device__ __forceinline__ int fast_bam_smem(const uint8_t* c, int stride) {
+  const int v = c[0];
+  uint32_t w[16];
+  const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int d = v - (int)c[dy[k] * stride + dx[k]];
+    w[k] = __byte_perm((uint32_t)d, (uint32_t)(-d), 0x5410);  // lo16 = v-p (dark), hi16 = p-v (bright)
+  }
+  uint32_t t3[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) t3[k] = __vimin3_s16x2(w[k], w[(k + 1) & 15], w[(k + 2) & 15]);
+  uint32_t m9[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) m9[k] = __vimin3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
+  uint32_t a = __vimax3_s16x2(m9[0], m9[1], m9[2]);
+  uint32_t b = __vimax3_s16x2(m9[3], m9[4], m9[5]);
+  uint32_t cc = __vimax3_s16x2(m9[6], m9[7], m9[8]);
+  uint32_t d2 = __vimax3_s16x2(m9[9], m9[10], m9[11]);
+  uint32_t e = __vimax3_s16x2(m9[12], m9[13], m9[14]);
+  a = __vimax3_s16x2(a, b, cc);
+  d2 = __vimax3_s16x2(d2, e, m9[15]);
+  a = __vmaxs2(a, d2);
+  const int lo = (int)(short)(a & 0xffff), hi = (int)(short)(a >> 16);
+  return max(lo, hi);
+}
+
+// Tile kernel.  Phase 1: byte-SIMD (4 px per thread) conservative prefilter on pixels quantised to 6 bits: a
+// 9-arc always contains one of every opposite ring pair, so a corner at threshold t needs
+// (p0|p8) and (p4|p12) both darker (or both brighter) than the centre by more than t; on the >>2 grid that is
+// "differs by at least qTh = ceil((t-2)/4)" which can only over-accept.  Survivors are compacted into a
+// shared-memory list.  Phase 2: exact score of each survivor.  Phase 3: coalesced 16-byte stores of the tile.
+__global__ void __launch_bounds__(kFtThreads) k_fast_score(OrbGeo g, const uint8_t* __restrict__ pyr,
+                                                           uint8_t* __restrict__ score) {
+  __shared__ __align__(16) uint8_t s_in[kFtInH * kFtInW];
+  __shared__ __align__(16) uint8_t s_out[kFtH * kFtW];
+  __shared__ uint16_t s_list[kFtH * kFtW];
+  __shared__ int s_count;
+
+  // locate the tile
+  int t = blockIdx.x, level = 0;
+#pragma unroll 1
+  for (int l = 1; l < g.nlevels; l++)
+    if (t >= g.lv[l].tileBase) level = l;
+  const LevelGeo& L = g.lv[level];
+  t -= L.tileBase;
+  const int ty = t / L.tilesX, tx = t - ty * L.tilesX;
+  const int x0 = tx * kFtW, y0 = ty * kFtH;
+  const size_t base = (size_t)blockIdx.y * g.frameStride + L.off;
+  const uint8_t* img = pyr + base;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) s_count = 0;
+  // zero the output tile (2 x 16 B per thread)
+  reinterpret_cast<uint4*>(s_out)[tid] = make_uint4(0, 0, 0, 0);
+  reinterpret_cast<uint4*>(s_out)[tid + kFtThreads] = make_uint4(0, 0, 0, 0);
+  // load the input tile with a 3-row / 4-byte halo as 32-bit words; out-of-image words read as 0
+  constexpr int kWordsPerRow = kFtInW / 4;  // 66
+  for (int i = tid; i < kFtInH * kWordsPerRow; i += kFtThreads) {
+    const int r = i / kWordsPerRow, c = i - r * kWordsPerRow;
+    const int gy = y0 - 3 + r, gx = x0 - 4 + c * 4;
+    uint32_t v = 0;
+    if (gy >= 0 && gy < L.h && gx >= 0 && gx + 3 < L.pitch)
+      v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + gx));
+    reinterpret_cast<uint32_t*>(s_in)[i] = v;
+  }
+  __syncthreads();
+
+  // ---- phase 1
+  {
+    const int wx = tid & 63, rg = tid >> 6;
+    const int gx = x0 + wx * 4;
+    // x-validity of the 4 bytes: tested region is [19, w-19)
+    uint32_t xmask = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      if (gx + b >= kEdge && gx + b < L.w - kEdge) xmask |= 0x80u << (8 * b);
+    const uint32_t qth = (uint32_t)g.qTh * 0x01010101u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_in);
+    if (xmask) {
+#pragma unroll 2
+      for (int r = rg; r < kFtH; r += 4) {
+        const int gy = y0 + r;
+        if (gy < kEdge || gy >= L.h - kEdge) continue;
+        const uint32_t* row = sw + (r + 3) * kWordsPerRow + wx;  // word left of the centre word
+        const uint32_t wm = row[0], w0 = row[1], wp = row[2];
+        const uint32_t up = sw[r * kWordsPerRow + wx + 1], dn = sw[(r + 6) * kWordsPerRow + wx + 1];
+        const uint32_t r4 = __byte_perm(w0, wp, 0x6543);   // x+3 .. x+6
+        const uint32_t r12 = __byte_perm(wm, w0, 0x4321);  // x-3 .. x
+        const uint32_t qc = (w0 >> 2) & 0x3f3f3f3fu;
+        const uint32_t q0 = (dn >> 2) & 0x3f3f3f3fu, q8 = (up >> 2) & 0x3f3f3f3fu;
+        const uint32_t q4 = (r4 >> 2) & 0x3f3f3f3fu, q12 = (r12 >> 2) & 0x3f3f3f3fu;
+        const uint32_t V = (qc | 0x80808080u) - qth;  // bytes in [128-qth, 191-qth], no borrow for qth <= 64
+        // dark: v'' - p'' >= qth  <=>  msb(V - p'')
+        const uint32_t d0 = V - q0, d8 = V - q8, d4 = V - q4, d12 = V - q12;
+        // bright: p'' - v'' >= qth  <=>  msb((p''|0x80) - qth - v'')
+        const uint32_t C = qc + qth;
+        const uint32_t b0 = (q0 | 0x80808080u) - C, b8 = (q8 | 0x80808080u) - C;
+        const uint32_t b4 = (q4 | 0x80808080u) - C, b12 = (q12 | 0x80808080u) - C;
+        uint32_t m = (((d0 | d8) & (d4 | d12)) | ((b0 | b8) & (b4 | b12))) & xmask;
+        if (m) {
+          const int n = __popc(m);
+          int pos = atomicAdd(&s_count, n);
+          const int code = (r << 8) | (wx * 4);
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            if (m & (0x80u << (8 * b))) s_list[pos++] = (uint16_t)(code + b);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2
+  const int n = s_count;
+  for (int i = tid; i < n; i += kFtThreads) {
+    const int code = s_list[i];
+    const int r = code >> 8, xl = code & 255;
+    const int bam = fast_bam_smem(s_in + (r + 3) * kFtInW + 4 + xl, kFtInW);
+    if (bam > g.minTh) s_out[r * kFtW + xl] = (uint8_t)(bam - 1);
+  }
+  __syncthreads();
+
+  // ---- phase 3: 16 vectors per row, 32 rows
+  uint8_t* out = score + base;
+  for (int i = tid; i < kFtH * (kFtW / 16); i += kFtThreads) {
+    const int r = i >> 4, c = i & 15;
+    const int gy = y0 + r, gx = x0 + c * 16;
+    if (gy < L.h && gx < L.pitch)
+      *reinterpret_cast<uint4*>(out + (size_t)gy * L.pitch + gx) = reinterpret_cast<const uint4*>(s_out)[i];
+  }
+}
+
+void launch_fast_score(const OrbGeo& g, int nFrames, const uint8_t* pyr, uint8_t* score, cudaStream_t st) {
+  dim3 grid(g.totalTiles, nFrames);
+  k_fast_score<<<grid, kFtThreads, 0, st>>>(g, pyr, score);
+  PGB_LAUNCHED();
+}
+
+// =========================================================================================== K3 cells
+// One warp per FAST cell.  A pixel survives the cell's 3x3 NMS iff its score is strictly greater than its 8
+// neighbours' scores, neighbours outside the cell's tested rectangle counting 0.  Because non-corners at the
+// cell's threshold also count 0 and a survivor's own score is >= the threshold, the survivors at iniTh are
+// exactly the survivors at minTh with score >= iniTh: one NMS pass serves both thresholds.
+constexpr int kCellWarps = 4;
+constexpr int kCellMaxChunks = 256;
+
+__global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const uint8_t* __restrict__ score,
+                                                           uint32_t* __restrict__ slots, int* __restrict__ cellCnt,
+                                                           int* __restrict__ err) {
+  __shared__ uint32_t s_m7[kCellWarps][kCellMaxChunks];
+  __shared__ uint32_t s_m20[kCellWarps][kCellMaxChunks];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cell = blockIdx.x * kCellWarps + warp;
+  if (cell >= g.totalCells) return;
+  const int f = blockIdx.y;
+  int level = 0;
+#pragma unroll 1
+  for (int l = 1; l < g.nlevels; l++)
+    if (cell >= g.lv[l].cellBase) level = l;
+  const LevelGeo& L = g.lv[level];
+  const int ci = cell - L.cellBase;
+  const int i = ci / L.nCols, j = ci - i * L.nCols;
+  int* cnt = cellCnt + (size_t)f * g.totalCells + cell;
+  const int iniX = kMinBorder + j * L.wCell, iniY = kMinBorder + i * L.hCell;
+  if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6) {
+    if (lane == 0) *cnt = 0;
+    return;
+  }
+  const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
+  const int rx0 = iniX + 3, rx1 = maxX - 3, ry0 = iniY + 3, ry1 = maxY - 3;
+  const int tw = rx1 - rx0, th = ry1 - ry0;
+  if (tw <= 0 || th <= 0) {
+    if (lane == 0) *cnt = 0;
+    return;
+  }
+  const int cpr = (tw + 31) >> 5;
+  const int nChunks = cpr * th;
+  if (nChunks > kCellMaxChunks) {
+    if (lane == 0) { atomicOr(err, kErrCellChunks); *cnt = 0; }
+    return;
+  }
+  const uint8_t* S = score + (size_t)f * g.frameStride + L.off;
+  const int pitch = L.pitch;
+  uint32_t any20 = 0;
+  for (int c = 0; c < nChunks; c++) {
+    const int ry = c / cpr;
+    const int y = ry0 + ry, x = rx0 + (c - ry * cpr) * 32 + lane;
+    bool keep = false;
+    int s = 0;
+    if (x < rx1) {
+      s = __ldg(S + (size_t)y * pitch + x);
+      if (s >= g.minTh) {
+        keep = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++) {
+            if (dx == 0 && dy == 0) continue;
+            const int nx = x + dx, ny = y + dy;
+            int nsc = 0;
+            if (nx >= rx0 && nx < rx1 && ny >= ry0 && ny < ry1) nsc = __ldg(S + (size_t)ny * pitch + nx);
+            keep = keep && (nsc < s);
+          }
+      }
+    }
+    const uint32_t m7 = __ballot_sync(0xffffffffu, keep);
+    const uint32_t m20 = __ballot_sync(0xffffffffu, keep && s >= g.iniTh);
+    if (lane == 0) { s_m7[warp][c] = m7; s_m20[warp][c] = m20; }
+    any20 |= m20;
+  }
+  __syncwarp();
+  const uint32_t* sel = any20 ? s_m20[warp] : s_m7[warp];
+  uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)ci * L.slotCap;
+  int basei = 0;
+  for (int c = 0; c < nChunks; c++) {
+    const uint32_t m = sel[c];
+    if (m >> lane & 1) {
+      const int ry = c / cpr;
+      const int y = ry0 + ry, x = rx0 + (c - ry * cpr) * 32 + lane;
+      const int s = __ldg(S + (size_t)y * pitch + x);
+      const int idx = basei + __popc(m & ((1u << lane) - 1));
+      if (idx < L.slotCap) slot[idx] = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | ((uint32_t)s << 24);
+    }
+    basei += __popc(m);
+  }
+  if (lane == 0) {
+    if (basei > L.slotCap) { atomicOr(err, kErrCandOverflow); basei = L.slotCap; }
+    *cnt = basei;
+  }
+}
+
+void launch_cells(const OrbGeo& g, int nFrames, const uint8_t* score, uint32_t* slots, int* cellCnt, int* err,
+                  cudaStream_t st) {
+  dim3 grid((g.totalCells + kCellWarps - 1) / kCellWarps, nFrames);
+  k_cells<<<grid, kCellWarps * 32, 0, st>>>(g, score, slots, cellCnt, err);
+  PGB_LAUNCHED();
+}
+
+// =========================================================================================== K4 octree
+// One CTA per (level, frame).  The std::list of the reference is an array in list order (index 0 = front);
+// every pass rebuilds it: children of the nodes split in the pass, most recently created first (push_front),
+// then the untouched nodes in their old order.  Points carry their node id; a pass is
+//   (a) choose the nodes to split (all expandable ones front-to-back, or -- in the "careful" phase -- the
+//       previous pass's children sorted by (size, creation seq) descending),
+//   (b) count each chosen node's points per quadrant in parallel,
+//   (c) one thread replays the sequential bookkeeping (list size, stop the instant size >= N),
+//   (d) points of the nodes actually split move to their child.
+constexpr int kOctThreads = 256;
+
+struct OctNode {
+  short x0, y0, x1, y1;
+  int cnt;
+  int seq;
+};
+
+__device__ __forceinline__ int oct_mid(int a, int b) { return a + ((b - a + 1) >> 1); }  // a + ceil((b-a)/2)
+
+__global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t* __restrict__ slots,
+                                                        const int* __restrict__ cellCnt,
+                                                        unsigned long long* __restrict__ candAll,
+                                                        StagedKp* __restrict__ staged, int* __restrict__ lvlCnt,
+                                                        int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const LevelGeo& L = g.lv[level];
+  const int cap = L.nodeCap;
+  // shared arrays (all sized by nodeCap)
+  OctNode* nodeA = reinterpret_cast<OctNode*>(smem_raw);
+  OctNode* nodeB = nodeA + cap;
+  int* E = reinterpret_cast<int*>(nodeB + cap);  // processing order: node indices
+  int* eidx = E + cap;                           // node -> position in E or -1
+  int* cc = eidx + cap;                          // [cap][4] child counts
+  int* childNew = cc + 4 * cap;                  // [cap][4] new index of child
+  int* remap = childNew + 4 * cap;               // node -> new index (survivors)
+  int* vlist = remap + cap;                      // children with >1 points created last pass, creation order
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(vlist + cap);  // [cap], 8-aligned by layout
+  __shared__ int s_scan[kOctThreads];
+  __shared__ int s_n, s_alive, s_nE, s_nV, s_P, s_seq, s_mode, s_finish, s_prevSize, s_nToExpand;
+
+  const int nCells = L.nCols * L.nRows;
+  const int* cnt = cellCnt + (size_t)f * g.totalCells + L.cellBase;
+  const uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase;
+  unsigned long long* cand = candAll + (size_t)f * g.candPerFrame + L.candBase;
+
+  // ---- gather the per-cell candidate lists into one array, cell row-major then in-cell order
+  const int chunk = (nCells + kOctThreads - 1) / kOctThreads;
+  const int c0 = min(tid * chunk, nCells), c1 = min(c0 + chunk, nCells);
+  int mySum = 0;
+  for (int c = c0; c < c1; c++) mySum += cnt[c];
+  s_scan[tid] = mySum;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < kOctThreads; i++) { int v = s_scan[i]; s_scan[i] = run; run += v; }
+    s_n = run;
+    if (run > L.candCap) { atomicOr(err, kErrCandOverflow); s_n = 0; }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > 0) {
+    int o = s_scan[tid];
+    for (int c = c0; c < c1; c++) {
+      const int k = cnt[c];
+      for (int q = 0; q < k; q++) cand[o + q] = (unsigned long long)slot[(size_t)c * L.slotCap + q];
+      o += k;
+    }
+  }
+  int* myCnt = lvlCnt + (size_t)f * g.nlevels + level;
+  if (n == 0) {
+    if (tid == 0) *myCnt = 0;
+    return;
+  }
+  __syncthreads();
+
+  // ---- roots
+  const int N = L.quota;
+  const float hX = L.hX;
+  const int H = L.maxBY - kMinBorder;
+  for (int i = tid; i < L.nIni; i += kOctThreads) {
+    nodeB[i].x0 = (short)(int)(hX * (float)i);
+    nodeB[i].x1 = (short)(int)(hX * (float)(i + 1));
+    nodeB[i].y0 = 0; nodeB[i].y1 = (short)H;
+    nodeB[i].cnt = 0; nodeB[i].seq = i;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kOctThreads) {
+    const uint32_t p = (uint32_t)cand[i];
+    int r = (int)(__fdiv_rn((float)(p & 0xfff), hX));
+    r = min(r, L.nIni - 1);
+    cand[i] = (unsigned long long)p | ((unsigned long long)r << 32);
+    atomicAdd(&nodeB[r].cnt, 1);
+  }
+  __syncthreads();
+  if (tid == 0) {  // erase empty roots
+    int a = 0;
+    for (int i = 0; i < L.nIni; i++)
+      if (nodeB[i].cnt > 0) { nodeA[a] = nodeB[i]; remap[i] = a; a++; } else remap[i] = -1;
+    s_alive = a; s_seq = L.nIni; s_mode = 0; s_finish = 0; s_nV = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kOctThreads) {
+    const unsigned long long v = cand[i];
+    cand[i] = (v & 0xffffffffull) | ((unsigned long long)remap[(int)(v >> 32)] << 32);
+  }
+  OctNode* cur = nodeA;
+  OctNode* nxt = nodeB;
+  __syncthreads();
+
+  // ---- main loop
+  while (true) {
+    const int alive = s_alive, mode = s_mode;
+    // (a) processing order
+    for (int i = tid; i < alive; i += kOctThreads) eidx[i] = -1;
+    __syncthreads();
+    if (mode == 0) {
+      if (tid == 0) {
+        int ne = 0;
+        for (int i = 0; i < alive; i++)
+          if (cur[i].cnt > 1) { E[ne] = i; eidx[i] = ne; ne++; }
+        s_nE = ne; s_prevSize = alive;
+      }
+    } else {
+      const int nV = s_nV;
+      for (int t = tid; t < nV; t += kOctThreads) {
+        const int me = vlist[t];
+        const long long km = ((long long)cur[me].cnt << 32) | (unsigned)cur[me].seq;
+        int rank = 0;
+        for (int u = 0; u < nV; u++) {
+          const int o = vlist[u];
+          const long long ko = ((long long)cur[o].cnt << 32) | (unsigned)cur[o].seq;
+          rank += (ko > km);
+        }
+        E[rank] = me; eidx[me] = rank;
+      }
+      if (tid == 0) { s_nE = nV; s_prevSize = alive; }
+    }
+    __syncthreads();
+    const int nE = s_nE;
+    for (int i = tid; i < nE * 4; i += kOctThreads) cc[i] = 0;
+    __syncthreads();
+    // (b) quadrant counts
+    for (int i = tid; i < n; i += kOctThreads) {
+      const unsigned long long v = cand[i];
+      const int node = (int)((v >> 32) & 0x3fffffff);
+      const int e = eidx[node];
+      if (e >= 0) {
+        const int x = (int)(v & 0xfff), y = (int)((v >> 12) & 0xfff);
+        const OctNode nd = cur[node];
+        const int mx = oct_mid(nd.x0, nd.x1), my = oct_mid(nd.y0, nd.y1);
+        const int q = (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
+        atomicAdd(&cc[e * 4 + q], 1);
+        cand[i] = (v & 0x3fffffffffffffffull) | ((unsigned long long)q << 62);
+      }
+    }
+    __syncthreads();
+    // (c) sequential bookkeeping
+    if (tid == 0) {
+      int size = alive, P = 0, created = 0;
+      for (int p = 0; p < nE; p++) {
+        int k = 0;
+        for (int q = 0; q < 4; q++) k += (cc[p * 4 + q] > 0);
+        size += k - 1;
+        created += k;
+        P++;
+        if (mode == 1 && size >= N) break;
+      }
+      if (size > cap) { atomicOr(err, kErrNodeOverflow); s_finish = 2; }
+      else {
+        int ord = 0, nv = 0, nToExpand = 0;
+        for (int p = 0; p < P; p++) {
+          const OctNode nd = cur[E[p]];
+          const int mx = oct_mid(nd.x0, nd.x1), my = oct_mid(nd.y0, nd.y1);
+          for (int q = 0; q < 4; q++) {
+            const int c = cc[p * 4 + q];
+            if (c <= 0) { childNew[p * 4 + q] = -1; continue; }
+            const int idx = created - 1 - ord;
+            OctNode ch;
+            ch.x0 = (q & 1) ? (short)mx : nd.x0;
+            ch.x1 = (q & 1) ? nd.x1 : (short)mx;
+            ch.y0 = (q & 2) ? (short)my : nd.y0;
+            ch.y1 = (q & 2) ? nd.y1 : (short)my;
+            ch.cnt = c;
+            ch.seq = s_seq + ord;
+            nxt[idx] = ch;
+            childNew[p * 4 + q] = idx;
+            if (c > 1) { vlist[nv++] = idx; nToExpand++; }
+            ord++;
+          }
+        }
+        s_seq += ord;
+        int sidx = created;
+        for (int i = 0; i < alive; i++) {
+          const int e = eidx[i];
+          if (e >= 0 && e < P) { remap[i] = -1; continue; }
+          nxt[sidx] = cur[i];
+          remap[i] = sidx++;
+        }
+        s_alive = size; s_P = P; s_nV = nv; s_nToExpand = nToExpand;
+        // loop control (ORBextractor.cc:663-737)
+        if (size >= N || size == s_prevSize) s_finish = 1;
+        else if (mode == 0 && (size + nToExpand * 3) > N) s_mode = 1;
+      }
+    }
+    __syncthreads();
+    if (s_finish == 2) {
+      if (tid == 0) *myCnt = 0;
+      return;
+    }
+    // (d) move points
+    const int P = s_P;
+    for (int i = tid; i < n; i += kOctThreads) {
+      const unsigned long long v = cand[i];
+      const int node = (int)((v >> 32) & 0x3fffffff);
+      const int e = eidx[node];
+      int nn;
+      if (e >= 0 && e < P) nn = childNew[e * 4 + (int)(v >> 62)];
+      else nn = remap[node];
+      cand[i] = (v & 0xffffffffull) | ((unsigned long long)nn << 32);
+    }
+    OctNode* tmp = cur; cur = nxt; nxt = tmp;
+    __syncthreads();
+    if (s_finish) break;
+  }
+
+  // ---- best point per node: max response, first in candidate order on ties (:743-760)
+  const int alive = s_alive;
+  for (int i = tid; i < alive; i += kOctThreads) best[i] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < n; i += kOctThreads) {
+    const unsigned long long v = cand[i];
+    const int node = (int)((v >> 32) & 0x3fffffff);
+    const unsigned long long key = ((unsigned long long)((uint32_t)v >> 24) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+    atomicMax(&best[node], key);
+  }
+  __syncthreads();
+  StagedKp* out = staged + (size_t)f * g.kpCapInternal + L.kpBase;
+  for (int i = tid; i < alive; i += kOctThreads) {
+    const uint32_t pi = 0xffffffffu - (uint32_t)(best[i] & 0xffffffffull);
+    const uint32_t p = (uint32_t)cand[pi];
+    StagedKp k;
+    k.x = (int)(p & 0xfff) + kMinBorder;
+    k.y = (int)((p >> 12) & 0xfff) + kMinBorder;
+    k.score = (int)(p >> 24);
+    k.level = level;
+    out[i] = k;
+  }
+  if (tid == 0) *myCnt = alive;
+}
+
+static size_t octree_smem_bytes(int cap) {
+  // 2 node arrays (12 B each) + E, eidx, remap, vlist (4 ints) + cc, childNew (8 ints) + best (8 B)
+  size_t b = (size_t)cap * (2 * sizeof(OctNode) + 12 * sizeof(int));
+  b = (b + 7) & ~(size_t)7;
+  return b + (size_t)cap * 8;
+}
+
+void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,
+                   StagedKp* staged, int* lvlCnt, int* err, cudaStream_t st) {
+  const size_t smem = octree_smem_bytes(g.maxNodeCap);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid(g.nlevels, nFrames);
+  k_octree<<<grid, kOctThreads, smem, st>>>(g, slots, cellCnt, cand, staged, lvlCnt, err);
+  PGB_LAUNCHED();
+}
+
+// =========================================================================================== K5-K7 orientation + blur + rBRIEF
+// One warp per keypoint.  The warp stages the 45x45 neighbourhood of the keypoint in shared memory (with the
+// level's BORDER_REFLECT_101 applied), takes the intensity-centroid angle from the unblurred pixels, blurs the
+// inner 39x39 patch with the fixed-point 7x7 kernel and samples the 256 rotated test pairs from it.  The blurred
+// level image of the reference is never materialised: its value at a pixel depends only on the 7x7 neighbourhood.
+constexpr int kOdWarps = 4;
+constexpr int kPR = 22;            // patch radius: 19 (pattern reach) + 3 (blur)
+constexpr int kPW = 2 * kPR + 1;   // 45
+constexpr int kBR = 19;
+constexpr int kBW = 2 * kBR + 1;   // 39
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+__device__ const signed char d_pattern[1024] = PGB200_ORB_PATTERN_INIT;
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+// cv::fastAtan2 (fp32 polynomial, no FMA)
+__device__ __forceinline__ float fast_atan2_dev(float y, float x) {
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = __fmul_rn(0.9997878412794807f, scale), p3 = __fmul_rn(-0.3258083974640975f, scale);
+  const float p5 = __fmul_rn(0.1555786518463281f, scale), p7 = __fmul_rn(-0.04432655554792128f, scale);
+  const float eps = (float)2.2204460492503131e-16;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a;
+  if (ax >= ay) {
+    const float c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    const float c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    const float c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    const float c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+__global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const uint8_t* __restrict__ pyr,
+                                                               const StagedKp* __restrict__ staged,
+                                                               const int* __restrict__ lvlCnt,
+                                                               pgb_keypoint* __restrict__ kps,
+                                                               uint8_t* __restrict__ desc, int* __restrict__ counts,
+                                                               int cap, int* __restrict__ err) {
+  __shared__ uint8_t s_patch[kOdWarps][kPW * kPW + 3];
+  __shared__ uint16_t s_h[kOdWarps][kPW * kBW + 1];
+  __shared__ uint8_t s_blur[kOdWarps][kBW * kBW + 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * kOdWarps + warp;
+  const int f = blockIdx.y;
+  if (slot >= g.kpCapInternal) return;
+  int level = 0;
+#pragma unroll 1
+  for (int l = 1; l < g.nlevels; l++)
+    if (slot >= g.lv[l].kpBase) level = l;
+  const LevelGeo& L = g.lv[level];
+  const int j = slot - L.kpBase;
+  const int* lc = lvlCnt + (size_t)f * g.nlevels;
+  int before = 0, total = 0;
+  for (int l = 0; l < g.nlevels; l++) {
+    const int c = lc[l];
+    if (l < level) before += c;
+    total += c;
+  }
+  if (slot == 0 && lane == 0) {
+    counts[f] = min(total, cap);
+    if (total > cap) atomicOr(err, kErrOutCap);
+  }
+  if (j >= lc[level]) return;
+  const int oi = before + j;
+  if (oi >= cap) return;
+  const StagedKp kp = staged[(size_t)f * g.kpCapInternal + slot];
+  const uint8_t* img = pyr + (size_t)f * g.frameStride + L.off;
+  uint8_t* P = s_patch[warp];
+  // stage the patch
+  for (int i = lane; i < kPW * kPW; i += 32) {
+    const int r = i / kPW, c = i - r * kPW;
+    const int y = reflect101(kp.y - kPR + r, L.h), x = reflect101(kp.x - kPR + c, L.w);
+    P[i] = __ldg(img + (size_t)y * L.pitch + x);
+  }
+  __syncwarp();
+  // intensity centroid over the radius-15 disc (integer sums: order-free)
+  int m10 = 0, m01 = 0;
+  for (int r = lane; r < 2 * kHalfPatch + 1; r += 32) {
+    const int v = r - kHalfPatch;
+    const int d = c_umax[v < 0 ? -v : v];
+    const uint8_t* row = P + (kPR + v) * kPW + kPR;
+    int rs = 0;
+    for (int u = -d; u <= d; u++) { const int px = row[u]; m10 += u * px; rs += px; }
+    m01 += v * rs;
+  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
+  const float angle = fast_atan2_dev((float)m01, (float)m10);
+  // horizontal then vertical pass of the 7x7 sigma=2 fixed-point Gaussian {18,34,48,56,48,34,18}
+  uint16_t* Hh = s_h[warp];
+  for (int i = lane; i < kPW * kBW; i += 32) {
+    const int r = i / kBW, c = i - r * kBW;
+    const uint8_t* p = P + r * kPW + c;  // columns c .. c+6 of the patch <=> blurred column c (offset 3)
+    Hh[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+  }
+  __syncwarp();
+  uint8_t* Bl = s_blur[warp];
+  for (int i = lane; i < kBW * kBW; i += 32) {
+    const int r = i / kBW, c = i - r * kBW;
+    const uint16_t* p = Hh + r * kBW + c;
+    const int acc = 18 * (p[0] + p[6 * kBW]) + 34 * (p[kBW] + p[5 * kBW]) + 48 * (p[2 * kBW] + p[4 * kBW]) + 56 * p[3 * kBW];
+    Bl[i] = (uint8_t)((acc + 32768) >> 16);
+  }
+  __syncwarp();
+  // rBRIEF: lane = descriptor byte
+  const float factorPI = (float)(3.14159265358979323846 / 180.0);
+  const float th = __fmul_rn(angle, factorPI);
+  const float a = (float)cos((double)th), b = (float)sin((double)th);
+  const uint8_t* C = Bl + kBR * kBW + kBR;
+  int val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const signed char* pt = d_pattern + (lane * 16 + 2 * k) * 2;
+    const float x0 = (float)pt[0], y0 = (float)pt[1], x1 = (float)pt[2], y1 = (float)pt[3];
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = C[r0 * kBW + c0], t1 = C[r1 * kBW + c1];
+    val |= (t0 < t1) << k;
+  }
+  desc[((size_t)f * cap + oi) * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    pgb_keypoint o;
+    const float s = L.scale;
+    o.x = (level == 0) ? (float)kp.x : __fmul_rn((float)kp.x, s);
+    o.y = (level == 0) ? (float)kp.y : __fmul_rn((float)kp.y, s);
+    o.size = (float)L.patchSize;
+    o.angle = angle;
+    o.response = (float)kp.score;
+    o.octave = level;
+    o.class_id = -1;
+    kps[(size_t)f * cap + oi] = o;
+  }
+}
+
+void launch_orient_desc(const OrbGeo& g, int nFrames, const uint8_t* pyr, const StagedKp* staged, const int* lvlCnt,
+                        pgb_keypoint* kps, uint8_t* desc, int* counts, int cap, int* err, cudaStream_t st) {
+  dim3 grid((g.kpCapInternal + kOdWarps - 1) / kOdWarps, nFrames);
+  k_orient_desc<<<grid, kOdWarps * 32, 0, st>>>(g, pyr, staged, lvlCnt, kps, desc, counts, cap, err);
+  PGB_LAUNCHED();
+}
+
+// =========================================================================================== full-level blur
+// GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101) of a whole level (ORBextractor.cc:1084-1085), for callers
+// that want the reference's blurred working image; the descriptor path above does not need it.
+__global__ void __launch_bounds__(256) k_blur_level(OrbGeo g, int level, int frame, const uint8_t* __restrict__ pyr,
+                                                    uint8_t* __restrict__ out) {
+  const LevelGeo& L = g.lv[level];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= L.w) return;
+  const uint8_t* img = pyr + (size_t)frame * g.frameStride + L.off;
+  const int k[7] = {18, 34, 48, 56, 48, 34, 18};
+  int acc = 0;
+#pragma unroll
+  for (int dy = -3; dy <= 3; dy++) {
+    const uint8_t* row = img + (size_t)reflect101(y + dy, L.h) * L.pitch;
+    int h = 0;
+#pragma unroll
+    for (int dx = -3; dx <= 3; dx++) h += k[dx + 3] * (int)__ldg(row + reflect101(x + dx, L.w));
+    acc += k[dy + 3] * h;
+  }
+  out[(size_t)y * L.w + x] = (uint8_t)((acc + 32768) >> 16);
+}
+
+void launch_blur_level(const OrbGeo& g, int level, int frame, const uint8_t* pyr, uint8_t* out, cudaStream_t st) {
+  const LevelGeo& L = g.lv[level];
+  dim3 grid((L.w + 255) / 256, L.h);
+  k_blur_level<<<grid, 256, 0, st>>>(g, level, frame, pyr, out);
+  PGB_LAUNCHED();
+}
+
+}  // namespace pgb

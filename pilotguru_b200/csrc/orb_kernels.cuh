@@ -1,0 +1,70 @@
+// Device-side geometry and kernel declarations for the ORB extraction path (K1..K7 of SURVEY.md section 2.1).
+// Data layout in HBM (per extractor handle, B = max_batch):
+//   pyr    [B][frameStride]  u8   level l of frame f at f*frameStride + lv[l].off, rows lv[l].pitch apart
+//   score  same layout as pyr (FAST score map, 0 = not a corner at minTh / outside the tested region)
+//   slots  [B][slotsPerFrame] u32  per FAST cell: up to slotCap packed candidates x:12|y:12|score:8
+//   cellCnt[B][totalCells]   i32
+//   cand   [B][candPerFrame] u64  per level: candidates in reference order; hi32 = octree node id | quadrant<<30
+//   staged [B][kpCapInternal]     per level: octree survivors in list order; lvlCnt[B][nlevels]
+#pragma once
+#include <cstdint>
+
+#include "../../include/pgb200.h"
+
+namespace pgb {
+
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 19;        // EDGE_THRESHOLD (ORBextractor.cc:74)
+constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3 (ORBextractor.cc:773)
+constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
+
+// FAST score kernel tiling
+constexpr int kFtW = 256, kFtH = 32, kFtThreads = 256;
+constexpr int kFtInW = kFtW + 8, kFtInH = kFtH + 6;
+
+struct LevelGeo {
+  int w, h, pitch;
+  unsigned long long off;
+  int maxBX, maxBY;             // w-16, h-16
+  int nCols, nRows, wCell, hCell;
+  int cellBase, slotCap;
+  unsigned long long slotBase;  // in u32 units inside a frame's slot block
+  int quota, nIni;
+  float hX;
+  int candCap;
+  unsigned long long candBase;  // in u64 units inside a frame's cand block
+  int nodeCap, kpBase;
+  int tileBase, tilesX, tilesY;
+  float scale;
+  int patchSize;
+};
+
+struct OrbGeo {
+  int nlevels, iniTh, minTh, qTh;
+  int totalCells, totalTiles, kpCapInternal, maxNodeCap;
+  unsigned long long frameStride, slotsPerFrame, candPerFrame;
+  LevelGeo lv[kMaxLevels];
+};
+
+struct ResizeTab {  // one entry per destination column / row
+  short s, a0, a1, pad;
+};
+
+struct StagedKp {
+  int x, y, score, level;
+};
+
+enum OrbErr { kErrCandOverflow = 1, kErrNodeOverflow = 2, kErrOutCap = 4, kErrCellChunks = 8 };
+
+void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
+                          const ResizeTab* ytab, cudaStream_t st);
+void launch_fast_score(const OrbGeo& g, int nFrames, const uint8_t* pyr, uint8_t* score, cudaStream_t st);
+void launch_cells(const OrbGeo& g, int nFrames, const uint8_t* score, uint32_t* slots, int* cellCnt, int* err,
+                  cudaStream_t st);
+void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,
+                   StagedKp* staged, int* lvlCnt, int* err, cudaStream_t st);
+void launch_orient_desc(const OrbGeo& g, int nFrames, const uint8_t* pyr, const StagedKp* staged, const int* lvlCnt,
+                        pgb_keypoint* kps, uint8_t* desc, int* counts, int cap, int* err, cudaStream_t st);
+void launch_blur_level(const OrbGeo& g, int level, int frame, const uint8_t* pyr, uint8_t* out, cudaStream_t st);
+
+}  // namespace pgb

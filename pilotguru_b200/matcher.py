@@ -1,0 +1,76 @@
+"""Host-side mirror of ORB_SLAM2::ORBmatcher's frame-to-frame path (thirdparty/orb-slam2/include/ORBmatcher.h:41-52)
+over the libpgb200 C-ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, check, lib, np_ptr
+
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # ORBmatcher.cc:38-40
+
+
+class ORBmatcher:
+    """``ORBmatcher(nnratio=0.6, checkOri=True)`` (ORBmatcher.cc:42)."""
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, max_feats: int = 1100, max_batch: int = 1,
+                 device: int = 0, stream=None):
+        self._h = None
+        h = lib().pgb_matcher_create(device, nnratio, int(checkOri), max_feats, max_batch, stream)
+        if not h:
+            raise _lib.PgbError(-1, _lib.last_error())
+        self._h = C.c_void_p(h)
+        self.max_feats, self.max_batch = max_feats, max_batch
+
+    def close(self):
+        if self._h:
+            lib().pgb_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray):
+        """ORBmatcher::DescriptorDistance (ORBmatcher.cc:1651-1667); a, b: (32,) or (n, 32) uint8."""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.empty(len(a), np.int32)
+        check(lib().pgb_descriptor_distance(np_ptr(a), np_ptr(b), len(a), np_ptr(out), 0, None))
+        return int(out[0]) if len(out) == 1 else out
+
+    def SearchByProjection(self, cur_kps, cur_desc, q_uv, q_octave, q_angle, q_desc, q_valid, bounds, th,
+                           scale_factors):
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono=True) (ORBmatcher.cc:1332-1474) on flat arrays.
+
+        Returns (nmatches, match_of_cur) where match_of_cur[i] is the query (last-frame map point) index now held
+        by current keypoint i, or -1 -- the state of CurrentFrame.mvpMapPoints after the call."""
+        n_cur, n_q = len(cur_kps), len(q_octave)
+        cap = max(n_cur, n_q, 1)
+
+        def pad(a, dtype, tail=()):
+            out = np.zeros((cap,) + tail, dtype)
+            a = np.asarray(a)
+            if len(a):
+                out[:len(a)] = a
+            return out
+        K = pad(cur_kps, KP_DTYPE); D = pad(cur_desc, np.uint8, (32,)); UV = pad(q_uv, np.float32, (2,))
+        O = pad(q_octave, np.int32); A = pad(q_angle, np.float32); QD = pad(q_desc, np.uint8, (32,))
+        V = pad(q_valid, np.uint8)
+        nc = np.array([n_cur], np.int32); nq = np.array([n_q], np.int32)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        m = np.full(cap, -1, np.int32); nm = np.zeros(1, np.int32)
+        check(lib().pgb_match_by_projection(self._h, 1, cap, np_ptr(K), np_ptr(D), np_ptr(nc), np_ptr(UV), np_ptr(O),
+                                            np_ptr(A), np_ptr(QD), np_ptr(V), np_ptr(nq), bounds[0], bounds[1],
+                                            bounds[2], bounds[3], th, np_ptr(sf), len(sf), np_ptr(m), np_ptr(nm), 0))
+        return int(nm[0]), m[:n_cur].copy()
+
+    def match_consecutive_ptr(self, n_pairs, cap, kps_ptr, desc_ptr, counts_ptr, flow_ptr, max_x, max_y, th,
+                              scale_factors, match_ptr, nmatch_ptr):
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        check(lib().pgb_match_consecutive(self._h, n_pairs, cap, kps_ptr, desc_ptr, counts_ptr, flow_ptr, max_x, max_y,
+                                          th, np_ptr(sf), len(sf), match_ptr, nmatch_ptr))

@@ -167,3 +167,37 @@ class OrbOracle:
         t = np.zeros(6)
         self.l.pgo_orb_stage_times(self.h, ptr(t, f64p), int(reset))
         return t
+
+
+def descriptor_distance(a: np.ndarray, b: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().pgo_descriptor_distance(ptr(a, u8p), ptr(b, u8p)))
+
+
+def search_by_projection(cur_kps, cur_desc, q_uv, q_octave, q_angle, q_desc, q_valid, bounds, th, scale_factors,
+                         check_ori=True):
+    cur_kps = np.ascontiguousarray(cur_kps, KP_DTYPE); cur_desc = np.ascontiguousarray(cur_desc, np.uint8)
+    q_uv = np.ascontiguousarray(q_uv, np.float32); q_octave = np.ascontiguousarray(q_octave, np.int32)
+    q_angle = np.ascontiguousarray(q_angle, np.float32); q_desc = np.ascontiguousarray(q_desc, np.uint8)
+    q_valid = np.ascontiguousarray(q_valid, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    m = np.full(max(len(cur_kps), 1), -1, np.int32)
+    bd = np.full(max(len(q_octave), 1), -1, np.int32)
+    n = lib().pgo_search_by_projection(cur_kps.ctypes.data_as(C.c_void_p), ptr(cur_desc, u8p), len(cur_kps),
+                                       ptr(q_uv, f32p), ptr(q_octave, i32p), ptr(q_angle, f32p), ptr(q_desc, u8p),
+                                       ptr(q_valid, u8p), len(q_octave), C.c_float(bounds[0]), C.c_float(bounds[1]),
+                                       C.c_float(bounds[2]), C.c_float(bounds[3]), C.c_float(th), ptr(sf, f32p),
+                                       len(sf), int(check_ori), ptr(m, i32p), ptr(bd, i32p))
+    return n, m[:len(cur_kps)], bd[:len(q_octave)]
+
+
+def match_consecutive(prev_kps, prev_desc, cur_kps, cur_desc, flow, max_x, max_y, th, scale_factors):
+    prev_kps = np.ascontiguousarray(prev_kps, KP_DTYPE); prev_desc = np.ascontiguousarray(prev_desc, np.uint8)
+    cur_kps = np.ascontiguousarray(cur_kps, KP_DTYPE); cur_desc = np.ascontiguousarray(cur_desc, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    m = np.full(max(len(cur_kps), 1), -1, np.int32)
+    n = lib().pgo_match_consecutive(prev_kps.ctypes.data_as(C.c_void_p), ptr(prev_desc, u8p), len(prev_kps),
+                                    cur_kps.ctypes.data_as(C.c_void_p), ptr(cur_desc, u8p), len(cur_kps),
+                                    C.c_float(flow[0]), C.c_float(flow[1]), C.c_float(max_x), C.c_float(max_y),
+                                    C.c_float(th), ptr(sf, f32p), len(sf), ptr(m, i32p))
+    return n, m[:len(cur_kps)]
