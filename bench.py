@@ -1,0 +1,296 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of BASELINE.json: synthetic 1080p frames/s through ORB extract + match.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU restatement of the reference on host cores)
+
+One "step" = one pass of the hot path over one batch of B synthetic 1080p frames per GPU: ORBextractor (1000
+features, 8 levels, scale 1.2, FAST 20/7) on every frame, then SearchByProjection of every frame against its
+predecessor (th=15, retry at 30).  Workload = BASELINE.json configs[1] (the single-GPU 1080p extractor config)
+batched so the kernels see inputs larger than L2.
+
+JSON line keys: see the task contract.  `value` = frames/s with the frames already resident in HBM; `e2e` = the
+same through the C-ABI from pinned HOST frames with host<->device copies timed; `roofline` = the FAST-9 score
+kernel against the measured HBM copy peak; `cpu_baseline` = the oracle (CPU port of the reference) on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT = 1920, 1080, 1000
+FAST_ALGO_BYTES_PER_FRAME = 2 * 6_419_321  # 8-level 1080p pyramid read once + u8 score map written once
+STAGES = ["pyramid", "fast_score", "cell_nms", "octree", "orient_desc"]
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                       str(index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_frames(n):
+    from pilotguru_b200 import synth
+    fr = np.stack([synth.frame(t) for t in range(n)])
+    fl = np.array([synth.flow(t) if t > 0 else (0, 0) for t in range(n)], np.float32)
+    return fr, fl
+
+
+def cpu_run(n_frames, threads):
+    """The oracle (CPU port of the reference path) on `threads` host threads over n_frames synthetic frames."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    distinct = min(n_frames, 16)
+    fr, fl = cpu_frames(distinct)
+    if n_frames > distinct:
+        reps = (n_frames + distinct - 1) // distinct
+        fr = np.concatenate([fr] * reps)[:n_frames]; fl = np.concatenate([fl] * reps)[:n_frames]
+    O.bench_extract_match(fr[:min(threads, n_frames)], fl[:min(threads, n_frames)], threads)  # warm: page in, spin threads
+    sec, nk, nm = O.bench_extract_match(fr, fl, threads)
+    return sec, nk, nm
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_step = max(8, min(cores, 64))
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(per_step, cores)
+    tot_s, tot_f = 0.0, 0
+    for _ in range(args.steps):
+        s, _, _ = cpu_run(per_step, cores)
+        tot_s += s; tot_f += per_step
+    v = tot_f / tot_s
+    line = {"impl": "reference", "metric": "1080p frames/sec ORB extract+match", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + "
+                                   "SearchByProjection vs previous frame", "frames_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} frames per step x {args.steps} steps, oracle/liboracle.so on {cores} host threads"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from pilotguru_b200 import launch_count, synth
+    from pilotguru_b200.dist import FeatureExchange
+    from pilotguru_b200.matcher import ORBmatcher
+    from pilotguru_b200.orb import ORBextractor
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+
+    # ---- synthetic input: B distinct frames per rank (rank r holds frames r*B .. r*B+B-1 of the sequence)
+    t0 = rank * B
+    host_frames = torch.from_numpy(np.stack([synth.frame(t0 + i) for i in range(B)])).pin_memory()
+    flows_np = np.array([synth.flow(t0 + i) for i in range(B)], np.float32)  # flow into frame i from frame i-1
+    dev_frames = host_frames.cuda(non_blocking=False)
+
+    ex = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
+    cap = ex.cap
+    stream = torch.cuda.ExternalStream(ex.stream)
+    mt = ORBmatcher(0.9, True, max_feats=cap, max_batch=B, device=local, stream=ex.stream)
+    xch = FeatureExchange(world, rank, B, cap, device=torch.device("cuda", local))
+    flow_dev = torch.from_numpy(flows_np).cuda()
+    match = torch.full((B, cap), -1, dtype=torch.int32, device="cuda")
+    nmatch = torch.zeros(B, dtype=torch.int32, device="cuda")
+    sf = ex.GetScaleFactors()
+    # pinned result buffers for the e2e leg
+    h_counts = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+    h_nmatch = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_kps = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
+    h_desc = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+    h_match = torch.zeros((B, cap), dtype=torch.int32).pin_memory()
+    # slot 0 of the exchange buffer = the block's predecessor frame t0-1 (rank r>0 also receives it every step from
+    # its left neighbour through the all-gather; rank 0 keeps this one)
+    pred = torch.from_numpy(synth.frame(t0 - 1)[None].copy()).cuda()
+    torch.cuda.synchronize()
+    ex.extract_ptr(pred.data_ptr(), 3, 1, W, H, W, W * H, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), cap)
+    ex.check()
+
+    def step(frames_ptr, where):
+        """extract B frames into this rank's slot of the exchange buffer, exchange, match B pairs."""
+        xch.carry_last()                                                   # slot 0 <- previous step's last frame
+        ex.extract_ptr(frames_ptr, where, B, W, H, W, W * H, xch.kps_ptr(1), xch.desc_ptr(1), xch.counts_ptr(1), cap)
+        xch.exchange(stream)                                               # N>1: one NCCL all-gather; slot 0 <- left neighbour's last frame
+        mt.match_consecutive_ptr(B, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), flow_dev.data_ptr(),
+                                 float(W), float(H), 15.0, sf, match.data_ptr(), nmatch.data_ptr())
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.cuda.stream(stream):
+        dev_step = lambda: step(dev_frames.data_ptr(), ORBextractor.IN_DEVICE | ORBextractor.OUT_DEVICE)
+
+        def e2e_step():
+            step(host_frames.data_ptr(), ORBextractor.OUT_DEVICE)          # H2D of the frames inside the call
+            h_counts.copy_(xch.counts_view(), non_blocking=True)           # D2H of the step's results
+            h_kps.copy_(xch.kps_view()[1:], non_blocking=True)
+            h_desc.copy_(xch.desc_view()[1:], non_blocking=True)
+            h_match.copy_(match, non_blocking=True)
+            h_nmatch.copy_(nmatch, non_blocking=True)
+            stream.synchronize()                                           # the caller holds the results here
+
+        for _ in range(Wm):
+            dev_step()
+        ex.check()
+        l0 = launch_count()
+        sampler = ClockSampler(local) if rank == 0 else None
+        ms = timed(dev_step, K)
+        launches = launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        ex.check()
+        nm_dev = nmatch.cpu().numpy().copy(); cnt_dev = xch.counts_view().cpu().numpy().copy()
+
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, K)
+        ex.check()
+        assert np.array_equal(h_nmatch.numpy(), nm_dev) and np.array_equal(h_counts.numpy(), cnt_dev), \
+            "e2e (host frames) and device-resident runs disagree"
+
+        # ---- per-stage times and the FAST kernel roofline (same resident batch, events on the launching stream)
+        stage_us = {}
+        for which, name in enumerate(STAGES):
+            for _ in range(2):
+                ex.run_stage(which)
+            reps = 10
+            t = timed(lambda: ex.run_stage(which), reps)
+            stage_us[name] = 1e3 * t / reps / B
+    frames_total = B * world
+    value = frames_total * K / (ms * 1e-3)
+    e2e = frames_total * K / (ms_e2e * 1e-3)
+    peak, peak_src = measured_peaks()
+    fast_s = stage_us["fast_score"] * 1e-6 * B
+    achieved = FAST_ALGO_BYTES_PER_FRAME * B / fast_s / 1e9
+    h2d = int(host_frames.numel())
+    d2h = int(h_counts.numel() * 4 + h_kps.numel() * 4 + h_desc.numel() + h_match.numel() * 4 + h_nmatch.numel() * 4)
+
+    if rank == 0:
+        line = {"metric": "1080p frames/sec ORB extract+match", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + "
+                                       "SearchByProjection vs previous frame (BASELINE configs[1], batched)",
+                           "frames_per_gpu_per_step": B, "global_frames_per_step": frames_total,
+                           "l2": f"inputs larger than L2: {B * W * H / 1e6:.0f} MB of frames + {B * 6.4:.0f} MB pyramid per step",
+                           "parallelism": f"frames sharded over {world} GPU(s); one NCCL all-gather of per-frame keypoint/descriptor records per step" if world > 1 else "1 GPU"},
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": FAST_ALGO_BYTES_PER_FRAME * B,
+                             "us_per_launch": stage_us["fast_score"] * B},
+                "stage_us_per_frame": stage_us,
+                "keypoints_per_frame": float(cnt_dev[1:].mean()), "matches_per_frame": float(nm_dev.mean())}
+        if not args.no_cpu_baseline and world == 1:
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            n = max(16, min(4 * cores, 256))
+            sec, _, _ = cpu_run(n, cores)
+            line["cpu_baseline"] = {"value": n / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} synthetic 1080p frames, extract+match, oracle on {cores} host threads ({sec:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

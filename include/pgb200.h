@@ -69,13 +69,16 @@ int pgb_orb_max_keypoints(const pgb_orb*);
 int pgb_orb_level_size(const pgb_orb*, int width, int height, int level, int* w, int* h);
 
 /* ORBextractor::operator() over a batch of n_frames gray images of identical size (ORBextractor.cc:1042-1104).
- * gray: host pointer (is_device=0; copied with cudaMemcpy2DAsync inside the call) or device pointer (is_device=1).
+ * where = 0: host input, host outputs (the reference's own calling convention; synchronous).
+ * where = PGB_IN_DEVICE | PGB_OUT_DEVICE: everything device-resident, asynchronous on the handle's stream.
+ * where = PGB_OUT_DEVICE: host (ideally pinned) frames are copied in with cudaMemcpy2DAsync, results stay on the
+ * device for the matcher; asynchronous.
  * frame i starts at gray + i*frame_stride, rows are `pitch` bytes apart.
- * Outputs are HOST buffers when is_device=0 and DEVICE buffers when is_device=1:
- *   kps[n_frames][cap], desc[n_frames][cap][32], counts[n_frames]; level-major then octree list order.
- * width==0 || height==0 => counts zeroed, PGB_OK (the reference returns silently on an empty image, :1045).
- * With is_device=1 the call is asynchronous on the handle's stream. */
-int pgb_orb_extract(pgb_orb*, const uint8_t* gray, int is_device, int n_frames, int width, int height, size_t pitch,
+ * Outputs: kps[n_frames][cap], desc[n_frames][cap][32], counts[n_frames]; level-major then octree list order.
+ * width==0 || height==0 => counts zeroed, PGB_OK (the reference returns silently on an empty image, :1045). */
+#define PGB_IN_DEVICE 1
+#define PGB_OUT_DEVICE 2
+int pgb_orb_extract(pgb_orb*, const uint8_t* gray, int where, int n_frames, int width, int height, size_t pitch,
                     size_t frame_stride, pgb_keypoint* kps, uint8_t* desc, int32_t* counts, int cap);
 
 /* mvImagePyramid[level] of frame `frame` of the last extract call, copied to a tight host buffer (w*h bytes). */

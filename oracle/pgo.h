@@ -39,6 +39,9 @@ int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
                           float maxX, float maxY, float th, const float* scale_factors, int nlevels,
                           int32_t* match_of_cur);
+double pgo_bench_extract_match(const uint8_t* frames, int n, int w, int h, const float* flow_xy, int nfeatures,
+                               float scale, int nlevels, int iniTh, int minTh, float th, int nthreads,
+                               int64_t* total_kps, int64_t* total_matches);
 #ifdef __cplusplus
 }
 #endif

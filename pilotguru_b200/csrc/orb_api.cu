@@ -328,7 +328,7 @@ int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames
   PGB_CUDA(cudaSetDevice(o->device));
   if (n_frames == 0) return PGB_OK;
   if (width == 0 || height == 0) {  // empty image: the reference returns without touching the outputs (:1045)
-    if (is_device) PGB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_frames, o->stream));
+    if (is_device & PGB_OUT_DEVICE) PGB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_frames, o->stream));
     else memset(counts, 0, sizeof(int32_t) * n_frames);
     return PGB_OK;
   }
@@ -337,19 +337,14 @@ int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames
   if (rc) return rc;
   const OrbGeo& g = o->geo;
   o->curFrames = n_frames;
-  const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (frame_stride == pitch * (size_t)height && n_frames > 1 && false) {
-    // (a single 3-D copy would go here; the per-frame 2-D copies below are already asynchronous)
-  }
+  const bool inDev = (is_device & PGB_IN_DEVICE) != 0, outDev = (is_device & PGB_OUT_DEVICE) != 0;
+  const cudaMemcpyKind kind = inDev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   for (int f = 0; f < n_frames; f++)
     PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
                                gray + (size_t)f * frame_stride, pitch, width, height, kind, o->stream));
-  if (is_device) {
-    if (cap < o->outCap) {
-      // caller-provided capacity smaller than the worst case is allowed; overflow raises the device flag
-    }
-    rc = run_stages(o, 0, 4, kps, desc, counts, cap);
-    return rc;
+  if (outDev) {
+    // a caller capacity below pgb_orb_max_keypoints() is allowed; overflow raises the device flag (pgb_orb_check)
+    return run_stages(o, 0, 4, kps, desc, counts, cap);
   }
   rc = run_stages(o, 0, 4, o->kps.p, o->desc.p, o->counts.p, o->outCap);
   if (rc) return rc;

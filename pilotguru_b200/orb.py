@@ -85,10 +85,13 @@ class ORBextractor:
                                     np_ptr(counts), self.cap))
         return kps, desc, counts
 
-    def extract_ptr(self, gray_ptr: int, is_device: bool, n: int, w: int, h: int, pitch: int, frame_stride: int,
+    IN_DEVICE, OUT_DEVICE = 1, 2
+
+    def extract_ptr(self, gray_ptr: int, where: int, n: int, w: int, h: int, pitch: int, frame_stride: int,
                     kps_ptr: int, desc_ptr: int, counts_ptr: int, cap: int):
-        """Raw-pointer form (device or pinned-host buffers owned by the caller, e.g. torch tensors)."""
-        check(lib().pgb_orb_extract(self._h, gray_ptr, int(is_device), n, w, h, pitch, frame_stride, kps_ptr, desc_ptr,
+        """Raw-pointer form (device or pinned-host buffers owned by the caller, e.g. torch tensors).
+        where: 0 host->host, OUT_DEVICE host frames -> device results, IN_DEVICE|OUT_DEVICE all on the device."""
+        check(lib().pgb_orb_extract(self._h, gray_ptr, int(where), n, w, h, pitch, frame_stride, kps_ptr, desc_ptr,
                                     counts_ptr, cap))
 
     def check(self):

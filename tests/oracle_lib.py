@@ -201,3 +201,15 @@ def match_consecutive(prev_kps, prev_desc, cur_kps, cur_desc, flow, max_x, max_y
                                     C.c_float(flow[0]), C.c_float(flow[1]), C.c_float(max_x), C.c_float(max_y),
                                     C.c_float(th), ptr(sf, f32p), len(sf), ptr(m, i32p))
     return n, m[:len(cur_kps)]
+
+
+def bench_extract_match(frames: np.ndarray, flows: np.ndarray, nthreads: int, nfeatures=1000, th=15.0):
+    """Timed CPU baseline: returns (seconds, total_keypoints, total_matches)."""
+    frames = np.ascontiguousarray(frames, np.uint8); flows = np.ascontiguousarray(flows, np.float32)
+    n, h, w = frames.shape
+    l = lib()
+    l.pgo_bench_extract_match.restype = C.c_double
+    tk = C.c_int64(); tm = C.c_int64()
+    s = l.pgo_bench_extract_match(ptr(frames, u8p), n, w, h, ptr(flows, f32p), nfeatures, C.c_float(1.2), 8, 20, 7,
+                                  C.c_float(th), nthreads, C.byref(tk), C.byref(tm))
+    return float(s), tk.value, tm.value

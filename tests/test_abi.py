@@ -1,0 +1,45 @@
+"""CPU test: libpgb200.so loads and exports every symbol include/pgb200.h declares; no compute call is made."""
+import ctypes
+import os
+
+import pytest
+
+from pilotguru_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _lib.declared_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/pgb200.h but not exported: {missing}"
+
+
+def test_binding_table_covers_header():
+    declared = set(_lib.declared_symbols())
+    bound = set(_lib._SIGS)
+    assert bound <= declared, bound - declared
+    assert declared <= bound, declared - bound
+
+
+def test_no_gpu_fails_loudly():
+    """Without a usable sm_100 device the product must raise, never fall back to CPU code."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pilotguru_b200 import PgbError
+    from pilotguru_b200.orb import ORBextractor
+    with pytest.raises(PgbError):
+        ORBextractor(1000, 1.2, 8, 20, 7)
+
+
+def test_product_does_not_reference_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dp, _, files in os.walk(os.path.join(root, "pilotguru_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".hpp")):
+                src = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle" not in src.lower() or f in ("synth.py",), f"{f} mentions the oracle"

@@ -1,0 +1,113 @@
+"""GPU parity tests of the CUDA projection matcher, through the C-ABI, against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pilotguru_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_descriptor_distance():
+    from pilotguru_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 256, (4096, 32), dtype=np.uint8); b = rng.integers(0, 256, (4096, 32), dtype=np.uint8)
+    got = ORBmatcher.DescriptorDistance(a, b)
+    assert np.array_equal(got, np.unpackbits(a ^ b, axis=1).sum(axis=1))
+    assert ORBmatcher.DescriptorDistance(a[0], a[0]) == 0
+    assert ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+def _queries(k0, fl):
+    return np.stack([k0["x"] + np.float32(fl[0]), k0["y"] + np.float32(fl[1])], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("th", [15.0, 30.0, 60.0])
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_by_projection_parity(golden_dir, th, check_ori):
+    from pilotguru_b200.matcher import ORBmatcher
+    P = np.load(os.path.join(golden_dir, "orb_pipeline_640x480.npz"))
+    sf = O.OrbOracle(500, 1.2, 8, 20, 7).tables()["scale"]
+    m = ORBmatcher(0.9, check_ori, max_feats=600)
+    for t in (1, 2):
+        k0, d0, k1, d1 = P[f"kps{t-1}"], P[f"desc{t-1}"], P[f"kps{t}"], P[f"desc{t}"]
+        uv = _queries(k0, synth.flow(t, w=640, h=480))
+        valid = np.ones(len(k0), np.uint8); valid[::7] = 0          # some queries without a map point
+        on, om, _ = O.search_by_projection(k1, d1, uv, k0["octave"], k0["angle"], d0, valid, (0, 640, 0, 480), th, sf,
+                                           check_ori)
+        gn, gm = m.SearchByProjection(k1, d1, uv, k0["octave"], k0["angle"], d0, valid, (0.0, 640.0, 0.0, 480.0), th, sf)
+        assert gn == on and np.array_equal(gm, om)
+    m.close()
+
+
+def test_greedy_exclusion_and_overflow_paths():
+    """Crowded scene: hundreds of identical-position targets inside every window force the sorted-list overflow
+    and the sequential re-sweep; result must still equal the reference's greedy loop."""
+    from pilotguru_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(4)
+    n = 900
+    k = np.zeros(n, O.KP_DTYPE)
+    k["x"] = rng.integers(300, 340, n).astype(np.float32); k["y"] = rng.integers(200, 240, n).astype(np.float32)
+    k["octave"] = rng.integers(0, 3, n); k["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    base = rng.integers(0, 256, 32, dtype=np.uint8)
+    d = np.tile(base, (n, 1)); flip = rng.integers(0, 32, n); d[np.arange(n), flip] ^= rng.integers(0, 256, n).astype(np.uint8)
+    q = 700
+    uv = np.stack([rng.uniform(300, 340, q), rng.uniform(200, 240, q)], axis=1).astype(np.float32)
+    qo = rng.integers(0, 3, q).astype(np.int32); qa = rng.uniform(0, 360, q).astype(np.float32)
+    qd = np.tile(base, (q, 1)); qd[np.arange(q), rng.integers(0, 32, q)] ^= rng.integers(0, 256, q).astype(np.uint8)
+    sf = np.array([1.0, 1.2, 1.44], np.float32)
+    on, om, _ = O.search_by_projection(k, d, uv, qo, qa, qd, np.ones(q, np.uint8), (0, 640, 0, 480), 15.0, sf)
+    m = ORBmatcher(0.9, True, max_feats=1000)
+    gn, gm = m.SearchByProjection(k, d, uv, qo, qa, qd, np.ones(q, np.uint8), (0.0, 640.0, 0.0, 480.0), 15.0, sf)
+    assert gn == on and np.array_equal(gm, om)
+    assert on > 300
+    m.close()
+
+
+def test_empty_inputs():
+    from pilotguru_b200.matcher import ORBmatcher
+    m = ORBmatcher(0.9, True, max_feats=64)
+    sf = np.array([1.0, 1.2], np.float32)
+    kz = np.zeros(0, O.KP_DTYPE); dz = np.zeros((0, 32), np.uint8)
+    n, mm = m.SearchByProjection(kz, dz, np.zeros((0, 2), np.float32), np.zeros(0, np.int32), np.zeros(0, np.float32), dz,
+                                 np.zeros(0, np.uint8), (0.0, 640.0, 0.0, 480.0), 15.0, sf)
+    assert n == 0 and len(mm) == 0
+    m.close()
+
+
+def test_extract_then_match_consecutive_device_resident(golden_dir):
+    """The bench path: frames -> extract (device buffers) -> pgb_match_consecutive, all on the GPU, checked
+    against the golden pipeline fixture."""
+    import torch
+    from pilotguru_b200.matcher import ORBmatcher
+    from pilotguru_b200.orb import ORBextractor
+    P = np.load(os.path.join(golden_dir, "orb_pipeline_640x480.npz"))
+    B = 3
+    frames = torch.from_numpy(np.stack([synth.frame(t, w=640, h=480) for t in range(B)])).cuda()
+    ex = ORBextractor(500, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=B)
+    cap = ex.cap
+    kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+    desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(B, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_ptr(frames.data_ptr(), 3, B, 640, 480, 640, 640 * 480, kps.data_ptr(), desc.data_ptr(),
+                   counts.data_ptr(), cap)
+    ex.check()
+    m = ORBmatcher(0.9, True, max_feats=cap, max_batch=B, stream=ex.stream)
+    flow = torch.tensor([synth.flow(t, w=640, h=480) for t in range(1, B)], dtype=torch.float32, device="cuda")
+    match = torch.full((B - 1, cap), -2, dtype=torch.int32, device="cuda")
+    nm = torch.zeros(B - 1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    m.match_consecutive_ptr(B - 1, cap, kps.data_ptr(), desc.data_ptr(), counts.data_ptr(), flow.data_ptr(), 640.0, 480.0,
+                            15.0, ex.GetScaleFactors(), match.data_ptr(), nm.data_ptr())
+    ex.check()
+    c = counts.cpu().numpy(); mm = match.cpu().numpy(); nmh = nm.cpu().numpy()
+    kh = kps.cpu().numpy().view(np.uint8).reshape(B, cap, 28).copy().view(O.KP_DTYPE).reshape(B, cap)
+    for t in range(B):
+        assert np.array_equal(kh[t, :c[t]], P[f"kps{t}"])
+    for t in (1, 2):
+        assert nmh[t - 1] == int(P[f"nmatch{t}"])
+        assert np.array_equal(mm[t - 1, :c[t]], P[f"match{t}"])
+    m.close(); ex.close()

@@ -1,0 +1,118 @@
+"""GPU parity tests of the CUDA ORB extractor, through the C-ABI, against the oracle and the golden fixtures.
+Bar: bit-exact pyramids, FAST score maps, candidate lists, keypoints (all 7 fields) and descriptors."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pilotguru_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+KPF = ["x", "y", "size", "angle", "response", "octave", "class_id"]
+
+
+def _mk(nf, w, h, batch=1):
+    from pilotguru_b200.orb import ORBextractor
+    return ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=batch)
+
+
+def _assert_same(gk, gd, ok, od):
+    assert len(gk) == len(ok)
+    for f in KPF:
+        assert np.array_equal(gk[f], ok[f]), f
+    assert np.array_equal(gd, od)
+
+
+@pytest.mark.parametrize("case", ["synth1080", "noise", "odd", "lowtexture", "gradient"])
+def test_extract_stage_by_stage(case):
+    rng = np.random.default_rng(9)
+    if case == "synth1080":
+        img, nf = synth.frame(7), 1000
+    elif case == "noise":
+        img, nf = rng.integers(0, 256, (480, 640), dtype=np.uint8), 1000
+    elif case == "odd":
+        img, nf = synth.frame(3, w=701, h=403), 777
+    elif case == "lowtexture":   # almost everything needs the minThFAST retry; many empty cells
+        img = np.clip(synth.frame(2, w=640, h=480).astype(np.int32) // 8 + 100, 0, 255).astype(np.uint8); nf = 500
+    else:                        # smooth ramp with a few saturated blocks: exercises ties and flat regions
+        yy, xx = np.mgrid[0:400, 0:600]
+        img = ((xx + yy) // 4 % 256).astype(np.uint8); img[100:140, 200:260] = 255; img[300:330, 50:90] = 0; nf = 300
+    h, w = img.shape
+    ex = _mk(nf, w, h)
+    orc = O.OrbOracle(nf, 1.2, 8, 20, 7)
+    ok, od = orc.extract(img)
+    gk, gd = ex(img)
+    for l in range(8):
+        lvl = orc.level(l)
+        assert np.array_equal(ex.image_pyramid(l), lvl), f"pyramid level {l}"
+        assert np.array_equal(ex.score_map(l), O.fast_score_map(lvl, 7)), f"score map level {l}"
+        assert np.array_equal(ex.candidates(l), orc.candidates(l)), f"candidates level {l}"
+        assert np.array_equal(ex.blurred_level(l), O.gaussian_blur7(lvl)), f"blur level {l}"
+    _assert_same(gk, gd, ok, od)
+    ex.close()
+
+
+def test_batch_matches_single_and_golden(golden_dir):
+    P = np.load(os.path.join(golden_dir, "orb_pipeline_640x480.npz"))
+    frames = np.stack([synth.frame(t, w=640, h=480) for t in range(3)])
+    ex = _mk(500, 640, 480, batch=3)
+    kps, desc, counts = ex.extract_batch(frames)
+    for t in range(3):
+        n = counts[t]
+        _assert_same(kps[t, :n], desc[t, :n], P[f"kps{t}"], P[f"desc{t}"])
+    # the same frames one at a time through operator()
+    for t in range(3):
+        gk, gd = ex(frames[t])
+        _assert_same(gk, gd, P[f"kps{t}"], P[f"desc{t}"])
+    ex.close()
+
+
+def test_getters_and_levels():
+    ex = _mk(1000, 1920, 1080)
+    t = O.OrbOracle(1000, 1.2, 8, 20, 7).tables()
+    assert ex.GetLevels() == 8 and ex.GetScaleFactor() == pytest.approx(1.2)
+    assert np.array_equal(ex.GetScaleFactors(), t["scale"]) and np.array_equal(ex.GetInverseScaleFactors(), t["inv_scale"])
+    assert np.array_equal(ex.GetScaleSigmaSquares(), t["sigma2"]) and np.array_equal(ex.GetInverseScaleSigmaSquares(), t["inv_sigma2"])
+    assert ex.features_per_level().tolist() == t["n_per_level"].tolist()
+    assert [ex.level_size(1920, 1080, l) for l in range(8)][-1] == (536, 301)
+    ex.close()
+
+
+def test_edge_cases():
+    from pilotguru_b200 import PgbError
+    ex = _mk(300, 320, 240, batch=2)
+    k, d = ex(np.zeros((0, 0), np.uint8))            # empty image: silent return (ORBextractor.cc:1045)
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = ex(np.full((240, 320), 50, np.uint8))     # flat image: no keypoints, descriptors released
+    assert len(k) == 0
+    with pytest.raises(ValueError):
+        ex(np.zeros((240, 320), np.float32))         # CV_8UC1 assert (ORBextractor.cc:1049)
+    with pytest.raises(PgbError):
+        ex(np.zeros((480, 640), np.uint8))           # larger than the handle's capacity: loud failure
+    with pytest.raises(PgbError):
+        ex.extract_batch(np.zeros((3, 240, 320), np.uint8))  # more frames than max_batch
+    # smaller than capacity is fine and still exact
+    img = synth.frame(4, w=300, h=200)
+    gk, gd = ex(img)
+    ok, od = O.OrbOracle(300, 1.2, 8, 20, 7).extract(img)
+    _assert_same(gk, gd, ok, od)
+    ex.close()
+
+
+def test_size_independent_properties_full_size_batch():
+    """At BASELINE size (1080p, 1000 features, batch of 8): idempotence across calls, batch position independence,
+    level-major order and quota bounds -- properties that do not need the oracle."""
+    frames = np.stack([synth.frame(t) for t in range(8)])
+    ex = _mk(1000, 1920, 1080, batch=8)
+    k1, d1, c1 = ex.extract_batch(frames)
+    k2, d2, c2 = ex.extract_batch(frames[::-1].copy())
+    assert np.array_equal(c1, c2[::-1])
+    for t in range(8):
+        n = c1[t]
+        assert np.array_equal(k1[t, :n], k2[7 - t, :n]) and np.array_equal(d1[t, :n], d2[7 - t, :n])
+        assert np.all(np.diff(k1[t, :n]["octave"]) >= 0)
+        assert np.all(np.bincount(k1[t, :n]["octave"], minlength=8) <= ex.features_per_level() + 2)
+        assert 900 < n <= ex.cap
+    ex.close()
