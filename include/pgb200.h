@@ -163,14 +163,12 @@ int pgb_imu_integrate(pgb_imu*, const double x[9], int64_t cap, int64_t* merged_
 /* ComputeAndSaveForwardVelocitiesFromImu's window loop (fit_motion.cc:156-273) for ALL sliding windows at once:
  * windows start at GPS index 0, shift_step, 2*shift_step, ... and hold batch_size samples.  Every window's
  * L-BFGS runs on the device.  first_window/n_windows select a contiguous shard (n_windows<0 = all) so ranks can
- * split the windows; sums are exchanged by the caller.
+ * split the windows; the per-event sums of different shards add up (in window order).
  * Outputs (host): per merged event speed_sum[n_merged], speed_cnt[n_merged] (accumulated in window order);
- * per window x_out[w][9], fx_out[w], iters_out[w]; forward-axis accumulator fwd_sum[3] + fwd_rem[3] (KahanSum,
- * math.hpp:8-26) may be NULL. */
+ * per window of the shard x_out[w][9], fx_out[w], iters_out[w] (any may be NULL). */
 int pgb_imu_fit_windows(pgb_imu*, const double* gps_v, const int64_t* gps_t, int n_gps, int batch_size,
                         int shift_step, int max_iterations, double epsilon, int first_window, int n_windows,
-                        double* speed_sum, int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out,
-                        double min_velocity_m_s, double min_rotation_rad, double* fwd_sum, double* fwd_rem);
+                        double* speed_sum, int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out);
 int pgb_imu_num_windows(int n_gps, int shift_step);
 
 /* SmoothTimeSeries (src/slam/smoothing.cc:56-98): host arrays in/out, device compute. */

@@ -213,6 +213,7 @@ struct WinRec {     /* one GPS interval of a window, in the window's fixed frame
   V3 a; M3 B;              /* D = T*v0 + a + B*h + g*c */
   M3 MW;                   /* sum_k dt_k * W_k  (grad_h += MW^T * dL) */
   M3 RQ;                   /* rotation at the start of the interval (K10) */
+  Q4 Q;                    /* the same as a quaternion (K10 orientation output) */
   V3 Sa; M3 SE; double St; /* velocity at the start of the interval: v0 + Sa + SE*h + g*St (K10) */
 };
 
@@ -229,6 +230,7 @@ PGB_HD void win_init(WinState* w) {
 PGB_HD void win_chain(WinState* w, const GpsLocal& g, double gps_speed, WinRec* r) {
   const M3 RQ = qmat(w->Q);
   r->RQ = RQ;
+  r->Q = w->Q;
   r->T = g.T;
   r->dref = gps_speed * g.T;
   r->T2 = ((double)w->tau * 1e-6) * g.T + g.ct;

@@ -39,6 +39,32 @@ int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
                           float maxX, float maxY, float th, const float* scale_factors, int nlevels,
                           int32_t* match_of_cur);
+typedef struct pgo_calib pgo_calib;
+pgo_calib* pgo_calib_create(const double* gps_v, const int64_t* gps_t, int n_gps, const double* gyro_xyz,
+                            const int64_t* gyro_t, int64_t n_gyro, const double* acc_xyz, const int64_t* acc_t,
+                            int64_t n_acc);
+void pgo_calib_destroy(pgo_calib*);
+int64_t pgo_calib_merged_count(const pgo_calib*);
+void pgo_calib_merged_events(const pgo_calib*, int64_t* t, int64_t* gi, int64_t* ai);
+int64_t pgo_calib_num_intervals(const pgo_calib*);
+void pgo_calib_intervals(const pgo_calib*, int64_t* ref_idx, int64_t* merged_idx, int64_t* start, int64_t* end);
+double pgo_calib_eval(const pgo_calib*, const double* x, double* grad);
+double pgo_calib_eval_core(pgo_calib*, const double* x, double* grad);
+int pgo_calib_minimize(pgo_calib*, double* x, double* fx, int max_iterations, double epsilon, int* n_eval);
+int pgo_calib_minimize_core(pgo_calib*, double* x, double* fx, int max_iterations, double epsilon, int* n_eval);
+int pgo_calib_minimize_literal_driver_core_eval(pgo_calib*, double* x, double* fx, int max_iterations, double epsilon,
+                                                int* n_eval);
+int64_t pgo_calib_integrate(const pgo_calib*, const double* x, int64_t cap, int64_t* idx, double* speed, double* quat,
+                            double* vel, int64_t* dur);
+int64_t pgo_calib_integrate_core(pgo_calib*, const double* x, int64_t cap, int64_t* idx, double* speed, double* vel,
+                                 int64_t* dur);
+void pgo_smooth_time_series(const double* values, const double* times, int64_t n, const double* target, int64_t nt,
+                            double sigma, double* out);
+int64_t pgo_fit_motion(const double* gps_v, const int64_t* gps_t, int n_gps, const double* gyro_xyz, const int64_t* gyro_t,
+                       int64_t n_gyro, const double* acc_xyz, const int64_t* acc_t, int64_t n_acc, int batch_size,
+                       int shift_step, int max_iters, double sigma, int mode, int64_t cap, int64_t* out_idx,
+                       int64_t* out_t_usec, double* out_avg, double* out_smoothed, double* x_out, int32_t* iters_out,
+                       double* fx_out, int64_t* n_evals_total);
 double pgo_bench_extract_match(const uint8_t* frames, int n, int w, int h, const float* flow_xy, int nfeatures,
                                float scale, int nlevels, int iniTh, int minTh, float th, int nthreads,
                                int64_t* total_kps, int64_t* total_matches);

@@ -574,3 +574,5 @@ int64_t pgo_fit_motion(const double* gps_v, const int64_t* gps_t, int n_gps, con
 }
 
 }  // extern "C"
+
+extern "C" void pgo_det_sincos(double x, double* s, double* c) { pgbimu::det_sincos(x, s, c); }

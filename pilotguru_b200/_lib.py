@@ -55,6 +55,19 @@ _SIGS = {
                                           C.c_float, C.c_float, C.c_float, vp, C.c_int, vp, vp, C.c_int]),
     "pgb_match_consecutive": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp,
                                         C.c_int, vp, vp]),
+    "pgb_imu_create": (vp, [C.c_int, vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp]),
+    "pgb_imu_destroy": (None, [vp]),
+    "pgb_imu_merged_count": (C.c_int64, [vp]),
+    "pgb_imu_merged_events": (C.c_int, [vp, vp, vp, vp]),
+    "pgb_imu_set_window": (C.c_int, [vp, vp, vp, C.c_int]),
+    "pgb_imu_window_intervals": (C.c_int64, [vp]),
+    "pgb_imu_eval": (C.c_int, [vp, vp, vp, vp]),
+    "pgb_imu_minimize": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_double]),
+    "pgb_imu_integrate": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
+    "pgb_imu_fit_windows": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                      vp, vp, vp, vp, vp]),
+    "pgb_imu_num_windows": (C.c_int, [C.c_int, C.c_int]),
+    "pgb_smooth_time_series": (C.c_int, [C.c_int, vp, vp, C.c_int64, vp, C.c_int64, C.c_double, vp]),
 }
 
 

@@ -1,0 +1,608 @@
+// K9/K10: IMU+GPS calibration on the device, and its C-ABI ("IMU + GPS calibration" section of pgb200.h).
+//
+// Reference (file:line in waiwnf/pilotguru): AccelerometerCalibrator src/calibration/velocity.cc:29-256,
+// MergeTimeSeries / MakeInterpolationIntervals src/interpolation/align_time_series.cc:29-196, the window loop of
+// src/fit_motion.cc:156-273, LBFGS++ thirdparty/LBFGS/LBFGS.h:79-182, SmoothTimeSeries src/slam/smoothing.cc:49-98.
+//
+// Device pipeline (all fp64, arithmetic from include/pgb200_imu_core.h, compiled with -fmad=false):
+//   k_imu_sweep    one thread per GPS interval: the rotation sweep over its IMU sub-intervals -> GpsLocal
+//   k_imu_chain    one thread per window: chains <= batch_size-1 GpsLocal records -> WinRec coefficients
+//   k_imu_solve    one thread per window: the whole L-BFGS (<= 500 iterations) on the 9 unknowns
+//   k_imu_speeds   one thread per (window, GPS interval): |v| at every IMU sub-interval with the fitted x (K10)
+//   k_imu_average  one thread per merged IMU event: sum over the covering windows, in window order
+// Host side: merged-event table and interpolation intervals are built once per recording / GPS series in O(N)
+// (the reference rebuilds them per window).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../../include/pgb200_imu_core.h"
+#include "common.cuh"
+
+namespace pgb {
+using namespace pgbimu;
+
+struct WinDesc {
+  int s, e;          // GPS index range [s, e) of the window; its GPS intervals are refs s+1 .. e-1
+  long long spOff;   // offset of the window's first sub-interval in the speeds array
+};
+
+__global__ void k_imu_sweep(int nRef, const int* __restrict__ ioff, const int* __restrict__ ivM,
+                            const long long* __restrict__ ivDur, const int* __restrict__ mG, const int* __restrict__ mA,
+                            const double* __restrict__ gyro, const double* __restrict__ acc, GpsLocal* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nRef) return;
+  GpsLocal gl;
+  SweepState ss;
+  sweep_init(&ss, &gl);
+  for (int k = ioff[r]; k < ioff[r + 1]; k++) {
+    const int m = ivM[k];
+    const int gi = mG[m], ai = mA[m];
+    ImuStep st;
+    st.wx = gyro[3 * (size_t)gi]; st.wy = gyro[3 * (size_t)gi + 1]; st.wz = gyro[3 * (size_t)gi + 2];
+    st.ax = acc[3 * (size_t)ai]; st.ay = acc[3 * (size_t)ai + 1]; st.az = acc[3 * (size_t)ai + 2];
+    st.dur_usec = ivDur[k];
+    const double dt = sweep_step(&ss, st);
+    sweep_accumulate(ss, dt, &gl);
+  }
+  sweep_finish(ss, &gl);
+  out[r] = gl;
+}
+
+__global__ void k_imu_chain(int nWin, const WinDesc* __restrict__ win, const GpsLocal* __restrict__ loc,
+                            const double* __restrict__ gpsV, int recStride, WinRec* __restrict__ rec,
+                            long long* __restrict__ totalUsec) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nWin) return;
+  WinState ws;
+  win_init(&ws);
+  long long tot = 0;
+  int j = 0;
+  for (int r = win[w].s + 1; r < win[w].e; r++, j++) {
+    const GpsLocal gl = loc[r];
+    WinRec wr;
+    win_chain(&ws, gl, gpsV[r], &wr);
+    rec[(size_t)w * recStride + j] = wr;
+    tot += gl.dur;
+  }
+  totalUsec[w] = tot;
+}
+
+struct DevEval {
+  const WinRec* rec;
+  int n;
+  long long total;
+  __device__ double operator()(const double* x, double* g) const { return imu_eval(rec, n, total, x, g); }
+};
+
+__global__ void k_imu_eval(const WinRec* __restrict__ rec, int n, long long total, const double* __restrict__ x,
+                           double* __restrict__ out10) {
+  if (blockIdx.x * blockDim.x + threadIdx.x != 0) return;
+  double xx[9], g[9];
+  for (int i = 0; i < 9; i++) xx[i] = x[i];
+  out10[0] = imu_eval(rec, n, total, xx, g);
+  for (int i = 0; i < 9; i++) out10[1 + i] = g[i];
+}
+
+__global__ void __launch_bounds__(32) k_imu_solve(int nWin, const WinDesc* __restrict__ win, int recStride,
+                                                  const WinRec* __restrict__ rec, const long long* __restrict__ totalUsec,
+                                                  int maxIter, double epsilon, int useX0, double* __restrict__ xOut,
+                                                  double* __restrict__ fxOut, int* __restrict__ itOut,
+                                                  int* __restrict__ evalOut) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nWin) return;
+  double x[9];
+  for (int i = 0; i < 9; i++) x[i] = useX0 ? xOut[(size_t)w * 9 + i] : 0.0;
+  const int n = win[w].e - win[w].s - 1;
+  double fx = 0.0;
+  int it = 0, ne = 0;
+  if (n > 0 && totalUsec[w] > 0) {
+    DevEval f{rec + (size_t)w * recStride, n, totalUsec[w]};
+    LbfgsParam P = lbfgs_default();
+    P.epsilon = epsilon;
+    P.max_iterations = maxIter;
+    it = lbfgs_minimize9(f, x, &fx, P, &ne);
+  }
+  for (int i = 0; i < 9; i++) xOut[(size_t)w * 9 + i] = x[i];
+  fxOut[w] = fx;
+  itOut[w] = it;
+  if (evalOut) evalOut[w] = ne;
+}
+
+// K10: per sub-interval speed (and optionally orientation / velocity) with the fitted parameters.
+__global__ void k_imu_speeds(int nWin, int maxRefs, const WinDesc* __restrict__ win, int recStride,
+                             const WinRec* __restrict__ rec, const double* __restrict__ xAll,
+                             const int* __restrict__ ioff, const int* __restrict__ ivM,
+                             const long long* __restrict__ ivDur, const int* __restrict__ mG, const int* __restrict__ mA,
+                             const double* __restrict__ gyro, const double* __restrict__ acc,
+                             double* __restrict__ speeds, double* __restrict__ quat, double* __restrict__ vel) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nWin * maxRefs) return;
+  const int w = t / maxRefs, j = t - w * maxRefs;
+  const int r = win[w].s + 1 + j;
+  if (r >= win[w].e) return;
+  const double* x = xAll + (size_t)w * 9;
+  const V3 g = v3(x[0], x[1], x[2]), h = v3(x[3], x[4], x[5]), v0 = v3(x[6], x[7], x[8]);
+  const WinRec wr = rec[(size_t)w * recStride + j];
+  const V3 Vr = add(add(v0, wr.Sa), add(mv(wr.SE, h), scale(g, wr.St)));
+  GpsLocal gl;
+  SweepState ss;
+  sweep_init(&ss, &gl);
+  const long long base = win[w].spOff - ioff[win[w].s + 1];
+  for (int k = ioff[r]; k < ioff[r + 1]; k++) {
+    const int m = ivM[k];
+    const int gi = mG[m], ai = mA[m];
+    ImuStep st;
+    st.wx = gyro[3 * (size_t)gi]; st.wy = gyro[3 * (size_t)gi + 1]; st.wz = gyro[3 * (size_t)gi + 2];
+    st.ax = acc[3 * (size_t)ai]; st.ay = acc[3 * (size_t)ai + 1]; st.az = acc[3 * (size_t)ai + 2];
+    st.dur_usec = ivDur[k];
+    sweep_step(&ss, st);
+    const V3 loc = add(ss.pa, mv(ss.pR, h));
+    const V3 v = add(add(Vr, mv(wr.RQ, loc)), scale(g, (double)ss.tau * 1e-6));
+    speeds[base + k] = norm3(v);
+    if (vel) { vel[3 * (base + k)] = v.x; vel[3 * (base + k) + 1] = v.y; vel[3 * (base + k) + 2] = v.z; }
+    if (quat) {
+      const Q4 q = qmul(wr.Q, ss.l);
+      quat[4 * (base + k)] = q.w; quat[4 * (base + k) + 1] = q.x; quat[4 * (base + k) + 2] = q.y; quat[4 * (base + k) + 3] = q.z;
+    }
+  }
+}
+
+// Per merged event: the sub-intervals carrying it are a contiguous run [ka, kb] of the global interval list.
+// A window contributes the value of the LAST of them it contains (IntegrateTrajectory overwrites the partial result
+// of an event split by a GPS boundary, velocity.cc:236-250); windows are added in ascending order
+// (std::accumulate over push_back order, fit_motion.cc:218-221, :256-258).
+__global__ void k_imu_average(int mLo, int mCount, const int* __restrict__ firstIv, const int* __restrict__ lastIv,
+                              const int* __restrict__ ivRef, int nWin, int firstWin, int batch, int step, int nGps,
+                              const WinDesc* __restrict__ win, const int* __restrict__ ioff,
+                              const double* __restrict__ speeds, double* __restrict__ sum, int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mCount) return;
+  const int ka = firstIv[i], kb = lastIv[i];
+  double s = 0.0;
+  int c = 0;
+  if (ka >= 0) {
+    const int ra = ivRef[ka], rb = ivRef[kb];
+    int wlo = (ra - batch) / step - 1, whi = rb / step + 1;
+    wlo = max(wlo, firstWin);
+    whi = min(whi, firstWin + nWin - 1);
+    for (int wg = wlo; wg <= whi; wg++) {
+      const WinDesc wd = win[wg - firstWin];
+      const int lo = ioff[wd.s + 1], hi = ioff[wd.e];  // the window's sub-intervals [lo, hi)
+      const int k = min(kb, hi - 1);
+      if (hi > lo && k >= max(ka, lo)) {
+        s = s + speeds[wd.spOff + (k - lo)];
+        c++;
+      }
+    }
+  }
+  sum[mLo + i] = s;
+  cnt[mLo + i] = c;
+}
+
+// SmoothTimeSeries (smoothing.cc:56-98): one thread per target; the reference's moving window bounds are
+// monotone in the target time, so each thread finds its own by bisection over the same predicates.
+__global__ void k_smooth(const double* __restrict__ v, const double* __restrict__ t, long long n,
+                         const double* __restrict__ tt, long long nt, double sigma, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  const double target = tt[i];
+  // left = number of leading indices j (j+1 < n) with target - t[j+1] > 3 sigma  (monotone in j)
+  long long lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) / 2;
+    if ((target - t[mid + 1]) > 3 * sigma) lo = mid + 1; else hi = mid;
+  }
+  const long long left = lo;
+  // right = first index j with !(t[j] - target < 3 sigma) or n-1
+  lo = 0; hi = n - 1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) / 2;
+    if ((t[mid] - target) < 3 * sigma) lo = mid + 1; else hi = mid;
+  }
+  const long long right = lo;
+  const double sqrt2 = sqrt(2.0);
+  double prev = 0.0, acc = 0.0;
+  for (long long k = left; k < right; k++) {
+    const double midp = (t[k] + t[k + 1]) / 2.0;
+    const double cdf = 0.5 * (1.0 + erf((midp - target) / (sqrt2 * sigma)));
+    acc = acc + v[k] * (cdf - prev);
+    prev = cdf;
+  }
+  acc = acc + v[right] * (1.0 - prev);
+  out[i] = acc;
+}
+
+}  // namespace pgb
+
+using namespace pgb;
+
+struct pgb_imu {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  // recording
+  std::vector<int64_t> gyroT, accT, mergedT;
+  std::vector<int> mG, mA;
+  DevBuf<double> dGyro, dAcc;
+  DevBuf<int> dMG, dMA;
+  // prepared GPS series
+  std::vector<int64_t> gpsT;
+  std::vector<int> ioff, ivM, ivRef;
+  std::vector<long long> ivDur;
+  std::vector<WinDesc> win;
+  int firstWin = 0, batch = 0, step = 0, maxRefs = 0;
+  long long spTotal = 0;
+  DevBuf<int> dIoff, dIvM, dIvRef, dFirstIv, dLastIv, dIt, dNe, dCnt;
+  DevBuf<long long> dIvDur, dTotal;
+  DevBuf<double> dGpsV, dX, dFx, dSpeeds, dQuat, dVel, dSum, dOut10;
+  DevBuf<GpsLocal> dLoc;
+  DevBuf<WinRec> dRec;
+  DevBuf<WinDesc> dWin;
+  std::vector<long long> hTotal;
+  bool windowReady = false;
+};
+
+namespace {
+
+// MergeTimeSeries for the two IMU components (align_time_series.cc:29-113): every emitted event holds, per
+// component, the index of its latest sample at or before the event time.
+int merge_two(const std::vector<int64_t>& a, const std::vector<int64_t>& b, std::vector<int>& ia, std::vector<int>& ib,
+              std::vector<int64_t>& t) {
+  ia.clear(); ib.clear(); t.clear();
+  const int64_t start = std::max(a.front(), b.front()), end = std::min(a.back(), b.back());
+  if (end < start) return 0;
+  auto first = [&](const std::vector<int64_t>& c) {
+    size_t i = std::lower_bound(c.begin(), c.end(), start) - c.begin();
+    return c[i] > start ? i - 1 : i;
+  };
+  size_t i = first(a), j = first(b);
+  for (;;) {
+    ia.push_back((int)i); ib.push_back((int)j);
+    t.push_back(std::max(a[i], b[j]));
+    if (i + 1 >= a.size() || j + 1 >= b.size()) break;
+    const int64_t next = std::min(a[i + 1], b[j + 1]);
+    const bool adva = a[i + 1] == next, advb = b[j + 1] == next;
+    if (adva) i++;
+    if (advb) j++;
+  }
+  return (int)t.size();
+}
+
+int check_increasing(const int64_t* t, size_t n, const char* what) {
+  for (size_t i = 0; i + 1 < n; i++)
+    if (!(t[i] < t[i + 1])) return fail(PGB_ERR_INVALID, "%s timestamps must be strictly increasing (index %zu)", what, i);
+  return PGB_OK;
+}
+
+// MakeInterpolationIntervals (align_time_series.cc:155-196) over a GPS series, flattened.
+void make_intervals(const std::vector<int64_t>& ref, const std::vector<int64_t>& interp, std::vector<int>& ioff,
+                    std::vector<int>& ivM, std::vector<int>& ivRef, std::vector<long long>& ivDur) {
+  ioff.assign(ref.size() + 1, 0); ivM.clear(); ivRef.clear(); ivDur.clear();
+  int64_t latest = std::min(interp.front(), ref.front());
+  size_t k = 0;
+  for (size_t r = 0; r < ref.size(); r++) {
+    ioff[r] = (int)ivM.size();
+    const int64_t rts = ref[r];
+    while (k < interp.size() && interp[k] <= rts) {
+      const int64_t ts = interp[k];
+      if (ts > latest && k > 0 && r > 0) { ivM.push_back((int)k); ivRef.push_back((int)r); ivDur.push_back(ts - latest); }
+      latest = ts;
+      k++;
+    }
+    if (k > 0 && r > 0 && k < interp.size() && rts > latest) { ivM.push_back((int)k); ivRef.push_back((int)r); ivDur.push_back(rts - latest); }
+    latest = rts;
+  }
+  ioff[ref.size()] = (int)ivM.size();
+}
+
+template <typename T>
+int upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t s) {
+  if (d.n < h.size() || !d.p) { if (d.alloc(h.size())) return PGB_ERR_CUDA; }
+  if (!h.empty()) PGB_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return PGB_OK;
+}
+template <typename T>
+int ensure(DevBuf<T>& d, size_t n) {
+  if (d.n < n || !d.p) return d.alloc(n);
+  return PGB_OK;
+}
+
+// Builds intervals for the GPS series, the window list, and runs sweep + chain.
+int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, int batch, int step, int first_window,
+            int n_windows) {
+  if (n_gps <= 0 || !gps_v || !gps_t) return fail(PGB_ERR_INVALID, "empty GPS series");
+  int rc = check_increasing(gps_t, n_gps, "GPS");
+  if (rc) return rc;
+  o->windowReady = false;
+  o->gpsT.assign(gps_t, gps_t + n_gps);
+  make_intervals(o->gpsT, o->mergedT, o->ioff, o->ivM, o->ivRef, o->ivDur);
+  const int allWin = (n_gps + step - 1) / step;
+  if (first_window < 0 || first_window > allWin) return fail(PGB_ERR_INVALID, "first_window out of range");
+  if (n_windows < 0 || first_window + n_windows > allWin) n_windows = allWin - first_window;
+  o->win.clear();
+  o->firstWin = first_window; o->batch = batch; o->step = step;
+  long long sp = 0;
+  int maxRefs = 1;
+  for (int w = first_window; w < first_window + n_windows; w++) {
+    WinDesc d;
+    d.s = w * step;
+    d.e = std::min(d.s + batch, n_gps);
+    d.spOff = sp;
+    sp += o->ioff[d.e] - o->ioff[std::min(d.s + 1, n_gps)];
+    maxRefs = std::max(maxRefs, d.e - d.s - 1);
+    o->win.push_back(d);
+  }
+  o->spTotal = sp;
+  o->maxRefs = maxRefs;
+  cudaStream_t s = o->stream;
+  std::vector<double> gv(gps_v, gps_v + n_gps);
+  if (upload(o->dIoff, o->ioff, s) || upload(o->dIvM, o->ivM, s) || upload(o->dIvRef, o->ivRef, s) ||
+      upload(o->dIvDur, o->ivDur, s) || upload(o->dGpsV, gv, s) || upload(o->dWin, o->win, s))
+    return PGB_ERR_CUDA;
+  const size_t nW = o->win.size();
+  if (ensure(o->dLoc, n_gps) || ensure(o->dRec, nW * maxRefs) || ensure(o->dTotal, nW) || ensure(o->dX, nW * 9) ||
+      ensure(o->dFx, nW) || ensure(o->dIt, nW) || ensure(o->dNe, nW) || ensure(o->dOut10, 16))
+    return PGB_ERR_CUDA;
+  if (nW == 0) { PGB_CUDA(cudaStreamSynchronize(s)); return PGB_OK; }
+  k_imu_sweep<<<(n_gps + 63) / 64, 64, 0, s>>>(n_gps, o->dIoff.p, o->dIvM.p, o->dIvDur.p, o->dMG.p, o->dMA.p,
+                                                o->dGyro.p, o->dAcc.p, o->dLoc.p);
+  PGB_CHECK_LAUNCH();
+  k_imu_chain<<<((int)nW + 63) / 64, 64, 0, s>>>((int)nW, o->dWin.p, o->dLoc.p, o->dGpsV.p, maxRefs, o->dRec.p, o->dTotal.p);
+  PGB_CHECK_LAUNCH();
+  o->hTotal.resize(nW);
+  PGB_CUDA(cudaMemcpyAsync(o->hTotal.data(), o->dTotal.p, nW * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  PGB_CUDA(cudaStreamSynchronize(s));  // gv and the host vectors were sources of async copies
+  o->windowReady = true;
+  return PGB_OK;
+}
+
+int solve(pgb_imu* o, int maxIter, double eps, int useX0) {
+  const int nW = (int)o->win.size();
+  if (nW == 0) return PGB_OK;
+  k_imu_solve<<<(nW + 31) / 32, 32, 0, o->stream>>>(nW, o->dWin.p, o->maxRefs, o->dRec.p, o->dTotal.p, maxIter, eps, useX0,
+                                                    o->dX.p, o->dFx.p, o->dIt.p, o->dNe.p);
+  PGB_CHECK_LAUNCH();
+  return PGB_OK;
+}
+
+int speeds(pgb_imu* o, bool full) {
+  const int nW = (int)o->win.size();
+  if (nW == 0 || o->spTotal == 0) return PGB_OK;
+  if (ensure(o->dSpeeds, o->spTotal)) return PGB_ERR_CUDA;
+  if (full && (ensure(o->dQuat, 4 * o->spTotal) || ensure(o->dVel, 3 * o->spTotal))) return PGB_ERR_CUDA;
+  const int n = nW * o->maxRefs;
+  k_imu_speeds<<<(n + 63) / 64, 64, 0, o->stream>>>(nW, o->maxRefs, o->dWin.p, o->maxRefs, o->dRec.p, o->dX.p, o->dIoff.p,
+                                                    o->dIvM.p, o->dIvDur.p, o->dMG.p, o->dMA.p, o->dGyro.p, o->dAcc.p,
+                                                    o->dSpeeds.p, full ? o->dQuat.p : nullptr, full ? o->dVel.p : nullptr);
+  PGB_CHECK_LAUNCH();
+  return PGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+pgb_imu* pgb_imu_create(int device, const double* gyro_xyz, const int64_t* gyro_t, size_t n_gyro, const double* acc_xyz,
+                        const int64_t* acc_t, size_t n_acc, void* stream) {
+  if (!gyro_xyz || !gyro_t || !acc_xyz || !acc_t || n_gyro == 0 || n_acc == 0) {  // CHECK(!component->empty())
+    fail(PGB_ERR_INVALID, "pgb_imu_create: empty sensor series");
+    return nullptr;
+  }
+  if (check_increasing(gyro_t, n_gyro, "gyro") || check_increasing(acc_t, n_acc, "accelerometer")) return nullptr;
+  if (use_device(device)) return nullptr;
+  pgb_imu* o = new pgb_imu;
+  o->device = device;
+  o->gyroT.assign(gyro_t, gyro_t + n_gyro);
+  o->accT.assign(acc_t, acc_t + n_acc);
+  merge_two(o->gyroT, o->accT, o->mG, o->mA, o->mergedT);
+  if (o->mergedT.empty()) {
+    fail(PGB_ERR_INVALID, "gyro and accelerometer series do not overlap in time");
+    delete o;
+    return nullptr;
+  }
+  if (stream) o->stream = (cudaStream_t)stream;
+  else {
+    if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(PGB_ERR_CUDA, "cudaStreamCreate failed"); delete o; return nullptr; }
+    o->ownStream = true;
+  }
+  auto bad = [&]() -> pgb_imu* { pgb_imu_destroy(o); return nullptr; };
+  if (o->dGyro.alloc(3 * n_gyro) || o->dAcc.alloc(3 * n_acc)) return bad();
+  if (cudaMemcpyAsync(o->dGyro.p, gyro_xyz, 3 * n_gyro * sizeof(double), cudaMemcpyHostToDevice, o->stream) != cudaSuccess ||
+      cudaMemcpyAsync(o->dAcc.p, acc_xyz, 3 * n_acc * sizeof(double), cudaMemcpyHostToDevice, o->stream) != cudaSuccess) {
+    fail(PGB_ERR_CUDA, "H2D copy of the sensor series failed");
+    return bad();
+  }
+  if (upload(o->dMG, o->mG, o->stream) || upload(o->dMA, o->mA, o->stream)) return bad();
+  if (cudaStreamSynchronize(o->stream) != cudaSuccess) { fail(PGB_ERR_CUDA, "stream sync failed"); return bad(); }
+  return o;
+}
+
+void pgb_imu_destroy(pgb_imu* o) {
+  if (!o) return;
+  cudaSetDevice(o->device);
+  if (o->stream) cudaStreamSynchronize(o->stream);
+  if (o->ownStream && o->stream) cudaStreamDestroy(o->stream);
+  delete o;
+}
+
+int64_t pgb_imu_merged_count(const pgb_imu* o) { return o ? (int64_t)o->mergedT.size() : PGB_ERR_INVALID; }
+
+int pgb_imu_merged_events(const pgb_imu* o, int64_t* t_usec, int64_t* gyro_idx, int64_t* acc_idx) {
+  if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  for (size_t i = 0; i < o->mergedT.size(); i++) {
+    if (t_usec) t_usec[i] = o->mergedT[i];
+    if (gyro_idx) gyro_idx[i] = o->mG[i];
+    if (acc_idx) acc_idx[i] = o->mA[i];
+  }
+  return PGB_OK;
+}
+
+int pgb_imu_set_window(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps) {
+  if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  PGB_CUDA(cudaSetDevice(o->device));
+  return prepare(o, gps_v, gps_t, n_gps, n_gps, n_gps, 0, 1);
+}
+
+int64_t pgb_imu_window_intervals(const pgb_imu* o) {
+  if (!o || !o->windowReady || o->win.empty()) return 0;
+  return (int64_t)o->spTotal;
+}
+
+int pgb_imu_eval(pgb_imu* o, const double x[9], double* loss, double grad[9]) {
+  if (!o || !x || !loss || !grad) return fail(PGB_ERR_INVALID, "null argument");  // CHECK_NOTNULL(gradient)
+  if (!o->windowReady || o->win.size() != 1) return fail(PGB_ERR_INVALID, "pgb_imu_eval: call pgb_imu_set_window first");
+  PGB_CUDA(cudaSetDevice(o->device));
+  const int n = o->win[0].e - o->win[0].s - 1;
+  PGB_CUDA(cudaMemcpyAsync(o->dX.p, x, 9 * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+  k_imu_eval<<<1, 32, 0, o->stream>>>(o->dRec.p, n, o->hTotal[0], o->dX.p, o->dOut10.p);
+  PGB_CHECK_LAUNCH();
+  double out[10];
+  PGB_CUDA(cudaMemcpyAsync(out, o->dOut10.p, sizeof out, cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  *loss = out[0];
+  for (int i = 0; i < 9; i++) grad[i] = out[1 + i];
+  return PGB_OK;
+}
+
+int pgb_imu_minimize(pgb_imu* o, double x[9], double* fx, int* n_iter, int max_iterations, double epsilon) {
+  if (!o || !x || !fx) return fail(PGB_ERR_INVALID, "null argument");
+  if (!o->windowReady || o->win.size() != 1) return fail(PGB_ERR_INVALID, "pgb_imu_minimize: call pgb_imu_set_window first");
+  if (max_iterations < 0 || !(epsilon > 0)) return fail(PGB_ERR_INVALID, "bad L-BFGS parameters");  // LBFGSParam::check_param
+  PGB_CUDA(cudaSetDevice(o->device));
+  PGB_CUDA(cudaMemcpyAsync(o->dX.p, x, 9 * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+  int rc = solve(o, max_iterations, epsilon, 1);
+  if (rc) return rc;
+  int it = 0;
+  PGB_CUDA(cudaMemcpyAsync(x, o->dX.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaMemcpyAsync(fx, o->dFx.p, sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaMemcpyAsync(&it, o->dIt.p, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  if (it < 0) return fail(PGB_ERR_NUMERIC, "the line search step left [min_step, max_step]");
+  if (n_iter) *n_iter = it;
+  return PGB_OK;
+}
+
+int pgb_imu_integrate(pgb_imu* o, const double x[9], int64_t cap, int64_t* merged_idx, double* speed, double* quat_wxyz,
+                      double* vel_xyz, int64_t* duration_usec, int64_t* n_out) {
+  if (!o || !x || !n_out) return fail(PGB_ERR_INVALID, "null argument");
+  if (!o->windowReady || o->win.size() != 1) return fail(PGB_ERR_INVALID, "pgb_imu_integrate: call pgb_imu_set_window first");
+  PGB_CUDA(cudaSetDevice(o->device));
+  PGB_CUDA(cudaMemcpyAsync(o->dX.p, x, 9 * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+  int rc = speeds(o, true);
+  if (rc) return rc;
+  const long long n = o->spTotal;
+  std::vector<double> sp(n), q(4 * n), v(3 * n);
+  if (n) {
+    PGB_CUDA(cudaMemcpyAsync(sp.data(), o->dSpeeds.p, n * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    PGB_CUDA(cudaMemcpyAsync(q.data(), o->dQuat.p, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    PGB_CUDA(cudaMemcpyAsync(v.data(), o->dVel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+  }
+  PGB_CUDA(cudaStreamSynchronize(o->stream));
+  // fold sub-intervals of the same merged event: later overwrites, durations add (velocity.cc:236-250)
+  const int lo = o->ioff[std::min(o->win[0].s + 1, (int)o->gpsT.size())];
+  int64_t k = 0;
+  for (long long i = 0; i < n; i++) {
+    const int m = o->ivM[lo + i];
+    const bool cont = i > 0 && o->ivM[lo + i - 1] == m;
+    if (!cont) {
+      if (k >= cap) return fail(PGB_ERR_CAPACITY, "trajectory has more than %lld points", (long long)cap);
+      k++;
+      if (duration_usec) duration_usec[k - 1] = 0;
+    }
+    if (merged_idx) merged_idx[k - 1] = m;
+    if (speed) speed[k - 1] = sp[i];
+    if (quat_wxyz) for (int c = 0; c < 4; c++) quat_wxyz[4 * (k - 1) + c] = q[4 * i + c];
+    if (vel_xyz) for (int c = 0; c < 3; c++) vel_xyz[3 * (k - 1) + c] = v[3 * i + c];
+    if (duration_usec) duration_usec[k - 1] += o->ivDur[lo + i];
+  }
+  *n_out = k;
+  return PGB_OK;
+}
+
+int pgb_imu_num_windows(int n_gps, int shift_step) {
+  if (n_gps <= 0 || shift_step <= 0) return 0;
+  return (n_gps + shift_step - 1) / shift_step;
+}
+
+int pgb_imu_fit_windows(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, int batch_size, int shift_step,
+                        int max_iterations, double epsilon, int first_window, int n_windows, double* speed_sum,
+                        int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out) {
+  if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  // the CHECKs of fit_motion.cc:304-309
+  if (batch_size <= 0 || shift_step <= 0 || batch_size < shift_step || max_iterations <= 0 || !(epsilon > 0))
+    return fail(PGB_ERR_INVALID, "pgb_imu_fit_windows: invalid window/optimiser parameters");
+  PGB_CUDA(cudaSetDevice(o->device));
+  int rc = prepare(o, gps_v, gps_t, n_gps, batch_size, shift_step, first_window, n_windows);
+  if (rc) return rc;
+  const int nW = (int)o->win.size();
+  const size_t M = o->mergedT.size();
+  if (speed_sum) memset(speed_sum, 0, M * sizeof(double));
+  if (speed_cnt) memset(speed_cnt, 0, M * sizeof(int32_t));
+  if (nW == 0) return PGB_OK;
+  rc = solve(o, max_iterations, epsilon, 0);
+  if (rc) return rc;
+  rc = speeds(o, false);
+  if (rc) return rc;
+  cudaStream_t s = o->stream;
+  std::vector<int> its(nW);
+  PGB_CUDA(cudaMemcpyAsync(its.data(), o->dIt.p, nW * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (x_out) PGB_CUDA(cudaMemcpyAsync(x_out, o->dX.p, (size_t)nW * 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (fx_out) PGB_CUDA(cudaMemcpyAsync(fx_out, o->dFx.p, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if ((speed_sum || speed_cnt) && o->spTotal > 0) {
+    // merged-event range touched by the shard, and each event's run of sub-intervals
+    const int kLo = o->ioff[std::min(o->win.front().s + 1, n_gps)], kHi = o->ioff[o->win.back().e];
+    if (kHi > kLo) {
+      const int mLo = o->ivM[kLo], mHi = o->ivM[kHi - 1];
+      const int mc = mHi - mLo + 1;
+      std::vector<int> firstIv(mc, -1), lastIv(mc, -1);
+      for (int k = kLo; k < kHi; k++) {
+        const int i = o->ivM[k] - mLo;
+        if (firstIv[i] < 0) firstIv[i] = k;
+        lastIv[i] = k;
+      }
+      if (upload(o->dFirstIv, firstIv, s) || upload(o->dLastIv, lastIv, s) || ensure(o->dSum, M) || ensure(o->dCnt, M))
+        return PGB_ERR_CUDA;
+      k_imu_average<<<(mc + 255) / 256, 256, 0, s>>>(mLo, mc, o->dFirstIv.p, o->dLastIv.p, o->dIvRef.p, nW, o->firstWin,
+                                                     batch_size, shift_step, n_gps, o->dWin.p, o->dIoff.p, o->dSpeeds.p,
+                                                     o->dSum.p, o->dCnt.p);
+      PGB_CHECK_LAUNCH();
+      if (speed_sum) PGB_CUDA(cudaMemcpyAsync(speed_sum + mLo, o->dSum.p + mLo, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (speed_cnt) PGB_CUDA(cudaMemcpyAsync(speed_cnt + mLo, o->dCnt.p + mLo, (size_t)mc * sizeof(int), cudaMemcpyDeviceToHost, s));
+      PGB_CUDA(cudaStreamSynchronize(s));  // firstIv/lastIv are host sources
+    }
+  }
+  PGB_CUDA(cudaStreamSynchronize(s));
+  for (int w = 0; w < nW; w++) {
+    if (iters_out) iters_out[w] = its[w];
+    if (its[w] < 0) return fail(PGB_ERR_NUMERIC, "window %d: the line search step left [min_step, max_step]", o->firstWin + w);
+  }
+  return PGB_OK;
+}
+
+int pgb_smooth_time_series(int device, const double* values, const double* times, int64_t n, const double* target_times,
+                           int64_t n_target, double sigma, double* out) {
+  if (!(sigma > 0)) return fail(PGB_ERR_INVALID, "sigma must be positive");  // CHECK_GT(sigma, 0)
+  if (n < 0 || n_target < 0 || (n_target > 0 && (!values || !times || !target_times || !out || n == 0)))
+    return fail(PGB_ERR_INVALID, "pgb_smooth_time_series: invalid argument");
+  if (n_target == 0) return PGB_OK;
+  // the reference's window bounds only ever move forward (smoothing.cc:70-78): targets and data must be ascending
+  for (int64_t i = 0; i + 1 < n_target; i++)
+    if (target_times[i + 1] < target_times[i]) return fail(PGB_ERR_INVALID, "target timestamps must be non-decreasing");
+  for (int64_t i = 0; i + 1 < n; i++)
+    if (times[i + 1] < times[i]) return fail(PGB_ERR_INVALID, "data timestamps must be non-decreasing");
+  if (use_device(device)) return PGB_ERR_CUDA;
+  DevBuf<double> dv, dt, dtt, dout;
+  if (dv.alloc(n) || dt.alloc(n) || dtt.alloc(n_target) || dout.alloc(n_target)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemcpy(dv.p, values, n * sizeof(double), cudaMemcpyHostToDevice));
+  PGB_CUDA(cudaMemcpy(dt.p, times, n * sizeof(double), cudaMemcpyHostToDevice));
+  PGB_CUDA(cudaMemcpy(dtt.p, target_times, n_target * sizeof(double), cudaMemcpyHostToDevice));
+  k_smooth<<<(unsigned)((n_target + 255) / 256), 256>>>(dv.p, dt.p, n, dtt.p, n_target, sigma, dout.p);
+  PGB_CHECK_LAUNCH();
+  PGB_CUDA(cudaMemcpy(out, dout.p, n_target * sizeof(double), cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}
+
+}  // extern "C"

@@ -213,3 +213,92 @@ def bench_extract_match(frames: np.ndarray, flows: np.ndarray, nthreads: int, nf
     s = l.pgo_bench_extract_match(ptr(frames, u8p), n, w, h, ptr(flows, f32p), nfeatures, C.c_float(1.2), 8, 20, 7,
                                   C.c_float(th), nthreads, C.byref(tk), C.byref(tm))
     return float(s), tk.value, tm.value
+
+
+class CalibOracle:
+    """AccelerometerCalibrator restatement (literal) + the contract-header ("core") evaluation on the host."""
+
+    def __init__(self, gps_v, gps_t, gyro, gyro_t, acc, acc_t):
+        self.l = lib()
+        self.l.pgo_calib_create.restype = C.c_void_p
+        self.l.pgo_calib_eval.restype = C.c_double
+        self.l.pgo_calib_eval_core.restype = C.c_double
+        for f in ("pgo_calib_merged_count", "pgo_calib_num_intervals", "pgo_calib_integrate", "pgo_calib_integrate_core"):
+            getattr(self.l, f).restype = C.c_int64
+        a = lambda x, t: np.ascontiguousarray(x, t)
+        self.gps_v, self.gps_t = a(gps_v, np.float64), a(gps_t, np.int64)
+        self.gyro, self.gyro_t, self.acc, self.acc_t = a(gyro, np.float64), a(gyro_t, np.int64), a(acc, np.float64), a(acc_t, np.int64)
+        self.h = C.c_void_p(self.l.pgo_calib_create(ptr(self.gps_v, f64p), ptr(self.gps_t, i64p), len(self.gps_v),
+                                                    ptr(self.gyro, f64p), ptr(self.gyro_t, i64p), C.c_int64(len(self.gyro_t)),
+                                                    ptr(self.acc, f64p), ptr(self.acc_t, i64p), C.c_int64(len(self.acc_t))))
+        if not self.h:
+            raise ValueError("pgo_calib_create failed (CHECK failure in the reference)")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.pgo_calib_destroy(self.h); self.h = None
+
+    def merged(self):
+        n = self.l.pgo_calib_merged_count(self.h)
+        t = np.empty(n, np.int64); gi = np.empty(n, np.int64); ai = np.empty(n, np.int64)
+        self.l.pgo_calib_merged_events(self.h, ptr(t, i64p), ptr(gi, i64p), ptr(ai, i64p))
+        return t, gi, ai
+
+    def intervals(self):
+        n = self.l.pgo_calib_num_intervals(self.h)
+        r = [np.empty(n, np.int64) for _ in range(4)]
+        self.l.pgo_calib_intervals(self.h, *[ptr(x, i64p) for x in r])
+        return r  # ref_idx, merged_idx, start, end
+
+    def eval(self, x, core=False):
+        x = np.ascontiguousarray(x, np.float64); g = np.zeros(9)
+        f = (self.l.pgo_calib_eval_core if core else self.l.pgo_calib_eval)(self.h, ptr(x, f64p), ptr(g, f64p))
+        return float(f), g
+
+    def minimize(self, x0=None, max_iterations=500, epsilon=1e-5, mode="literal"):
+        x = np.zeros(9) if x0 is None else np.array(x0, np.float64)
+        fx = C.c_double(); ne = C.c_int()
+        fn = {"literal": self.l.pgo_calib_minimize, "core": self.l.pgo_calib_minimize_core,
+              "literal_driver_core_eval": self.l.pgo_calib_minimize_literal_driver_core_eval}[mode]
+        it = fn(self.h, ptr(x, f64p), C.byref(fx), max_iterations, C.c_double(epsilon), C.byref(ne))
+        return it, x, fx.value, ne.value
+
+    def integrate(self, x, core=False):
+        x = np.ascontiguousarray(x, np.float64)
+        cap = self.l.pgo_calib_merged_count(self.h) + 8
+        idx = np.empty(cap, np.int64); sp = np.empty(cap); q = np.empty((cap, 4)); v = np.empty((cap, 3)); d = np.empty(cap, np.int64)
+        if core:
+            n = self.l.pgo_calib_integrate_core(self.h, ptr(x, f64p), C.c_int64(cap), ptr(idx, i64p), ptr(sp, f64p), ptr(v, f64p), ptr(d, i64p))
+        else:
+            n = self.l.pgo_calib_integrate(self.h, ptr(x, f64p), C.c_int64(cap), ptr(idx, i64p), ptr(sp, f64p), ptr(q, f64p), ptr(v, f64p), ptr(d, i64p))
+        assert n >= 0
+        return idx[:n].copy(), sp[:n].copy(), q[:n].copy(), v[:n].copy(), d[:n].copy()
+
+
+def smooth_time_series(values, times, target, sigma):
+    v = np.ascontiguousarray(values, np.float64); t = np.ascontiguousarray(times, np.float64)
+    tt = np.ascontiguousarray(target, np.float64); out = np.empty(len(tt))
+    lib().pgo_smooth_time_series(ptr(v, f64p), ptr(t, f64p), C.c_int64(len(v)), ptr(tt, f64p), C.c_int64(len(tt)),
+                                 C.c_double(sigma), ptr(out, f64p))
+    return out
+
+
+def fit_motion(d, batch_size=40, shift_step=5, max_iters=500, sigma=0.003, mode=0):
+    """The window loop of fit_motion.cc:156-273 on a synth.imu_gps() dict. mode 0 literal, 1 contract/core."""
+    l = lib()
+    l.pgo_fit_motion.restype = C.c_int64
+    gv = np.ascontiguousarray(d["gps_v"], np.float64); gt = np.ascontiguousarray(d["gps_t"], np.int64)
+    gy = np.ascontiguousarray(d["gyro"], np.float64); gyt = np.ascontiguousarray(d["gyro_t"], np.int64)
+    ac = np.ascontiguousarray(d["acc"], np.float64); act = np.ascontiguousarray(d["acc_t"], np.int64)
+    cap = len(gyt) + len(act) + 8
+    nwin = (len(gv) + shift_step - 1) // shift_step
+    idx = np.empty(cap, np.int64); ts = np.empty(cap, np.int64); avg = np.empty(cap); sm = np.empty(cap)
+    xo = np.zeros((nwin, 9)); it = np.zeros(nwin, np.int32); fx = np.zeros(nwin); ne = C.c_int64()
+    n = l.pgo_fit_motion(ptr(gv, f64p), ptr(gt, i64p), len(gv), ptr(gy, f64p), ptr(gyt, i64p), C.c_int64(len(gyt)),
+                         ptr(ac, f64p), ptr(act, i64p), C.c_int64(len(act)), batch_size, shift_step, max_iters,
+                         C.c_double(sigma), mode, C.c_int64(cap), ptr(idx, i64p), ptr(ts, i64p), ptr(avg, f64p),
+                         ptr(sm, f64p), ptr(xo, f64p), ptr(it, i32p), ptr(fx, f64p), C.byref(ne))
+    if n < 0:
+        raise RuntimeError(f"pgo_fit_motion failed: {n}")
+    return dict(idx=idx[:n].copy(), t_usec=ts[:n].copy(), avg=avg[:n].copy(), smoothed=sm[:n].copy(), x=xo, iters=it,
+                fx=fx, n_evals=ne.value)
