@@ -151,17 +151,16 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   // ---------------- phase A
   unsigned long long* stage = sStage + warp * kMtStage;
   for (int i = warp; i < nQ; i += kMtWarps) {
-    float u, v, ang;
+    float u, v;
     int oct;
     bool valid;
     if (A.consecutive) {
       const pgb_keypoint k = prevK[i];
-      u = k.x + fx; v = k.y + fy; oct = k.octave; valid = true; ang = k.angle;
+      u = k.x + fx; v = k.y + fy; oct = k.octave; valid = true;
     } else {
       u = A.qUV[((size_t)p * cap + i) * 2]; v = A.qUV[((size_t)p * cap + i) * 2 + 1];
       oct = A.qOct[(size_t)p * cap + i]; valid = A.qValid[(size_t)p * cap + i] != 0;
     }
-    (void)ang;
     const QueryWin q = make_window(A, u, v, oct, valid, invW, invH);
     int cnt = 0;
     if (q.ok) {

@@ -2,6 +2,7 @@
 // Host-side restatement of the reference's constructor tables (ORBextractor.cc:410-470) and of the per-level
 // grid arithmetic (ORBextractor.cc:769-787, :542-545), which must use the same float expressions.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -58,6 +59,9 @@ struct pgb_orb {
   DevBuf<uint8_t> desc;
   int outCap = 0;
   DevBuf<uint8_t> tmpLevel;
+  TmapPack tmaps{};
+  bool fastV2 = true;  // PGB_FAST_IMPL=v1 selects the first-generation kernel (kept for A/B measurements)
+  int numSMs = 148;
 };
 
 namespace {
@@ -69,13 +73,13 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
   g->minTh = o->minTh;
   g->qTh = o->minTh >= 2 ? (o->minTh + 1) / 4 : 0;
   unsigned long long off = 0, slotOff = 0, candOff = 0;
-  int cellBase = 0, tileBase = 0, kpBase = 0, maxNode = 1;
+  int cellBase = 0, tileBase = 0, tile2Base = 0, kpBase = 0, maxNode = 1;
   for (int l = 0; l < o->nlevels; l++) {
     LevelGeo& L = g->lv[l];
     L.w = cv_round_f((float)w * o->invScale[l]);
     L.h = cv_round_f((float)h * o->invScale[l]);
-    if (L.w < 2 * kEdge + 1 || L.h < 2 * kEdge + 1)
-      return fail(PGB_ERR_INVALID, "level %d of a %dx%d image is %dx%d: too small for the 19-px border", l, w, h, L.w, L.h);
+    if (L.w < 1 || L.h < 1)
+      return fail(PGB_ERR_INVALID, "level %d of a %dx%d image is empty", l, w, h);
     L.pitch = round_up(L.w, 64);
     L.off = off;
     off += (unsigned long long)L.pitch * L.h;
@@ -85,17 +89,21 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
     const float width = (float)(L.maxBX - kMinBorder), height = (float)(L.maxBY - kMinBorder);
     L.nCols = (int)(width / 30.f);
     L.nRows = (int)(height / 30.f);
-    if (L.nCols <= 0 || L.nRows <= 0)
-      return fail(PGB_ERR_INVALID, "level %d (%dx%d) has no FAST cell (the reference divides by zero here)", l, L.w, L.h);
-    L.wCell = (int)std::ceil(width / L.nCols);
-    L.hCell = (int)std::ceil(height / L.nRows);
+    if (L.nCols <= 0 || L.nRows <= 0) {
+      // Level too small for a 30-px cell: the reference's cell loops do not execute (nRows or nCols is 0; the
+      // inf -> int cell size it computes is never used) and the level contributes no keypoints.
+      L.nCols = 0; L.nRows = 0; L.wCell = 1; L.hCell = 1;
+    } else {
+      L.wCell = (int)std::ceil(width / L.nCols);
+      L.hCell = (int)std::ceil(height / L.nRows);
+    }
     L.cellBase = cellBase;
     cellBase += L.nCols * L.nRows;
     L.slotCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
     L.slotBase = slotOff;
     slotOff += (unsigned long long)L.nCols * L.nRows * L.slotCap;
     L.quota = o->nPerLevel[l];
-    L.nIni = (int)std::round((float)(L.maxBX - kMinBorder) / (L.maxBY - kMinBorder));
+    L.nIni = L.nCols > 0 ? (int)std::round((float)(L.maxBX - kMinBorder) / (L.maxBY - kMinBorder)) : 1;
     if (L.nIni <= 0)
       return fail(PGB_ERR_INVALID, "level %d (%dx%d): width/height ratio rounds to 0 root nodes", l, L.w, L.h);
     L.hX = (float)(L.maxBX - kMinBorder) / L.nIni;
@@ -110,6 +118,10 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
     L.tilesY = (L.h + kFtH - 1) / kFtH;
     L.tileBase = tileBase;
     tileBase += L.tilesX * L.tilesY;
+    L.tiles2X = (L.w + kF2W - 1) / kF2W;
+    L.tiles2Y = (L.h + kF2H - 1) / kF2H;
+    L.tile2Base = tile2Base;
+    tile2Base += L.tiles2X * L.tiles2Y;
     L.scale = o->scale[l];
     L.patchSize = (int)(31 * o->scale[l]);
     if (L.maxBX - kMinBorder > 4095 || L.maxBY - kMinBorder > 4095)
@@ -117,6 +129,7 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
   }
   g->totalCells = cellBase;
   g->totalTiles = tileBase;
+  g->totalTiles2 = tile2Base;
   g->kpCapInternal = kpBase;
   g->maxNodeCap = maxNode;
   g->frameStride = off;
@@ -163,6 +176,40 @@ int upload_tabs(pgb_orb* o) {
   return PGB_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// u32 views of every pyramid level (TMA load, 68x70 halo box) and score-map level (TMA store, 64x64 box).
+int build_tmaps(pgb_orb* o) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = (EncodeTiledFn)fn;
+  }
+  const OrbGeo& g = o->geo;
+  for (int l = 0; l < g.nlevels; l++) {
+    const LevelGeo& L = g.lv[l];
+    const cuuint64_t dims[3] = {(cuuint64_t)(L.pitch / 4), (cuuint64_t)L.h, (cuuint64_t)o->maxBatch};
+    const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.frameStride};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const cuuint32_t boxIn[3] = {(cuuint32_t)kF2InWords, (cuuint32_t)kF2InRows, 1};
+    const cuuint32_t boxOut[3] = {(cuuint32_t)(kF2W / 4), (cuuint32_t)kF2H, 1};
+    CUresult r = encode(&o->tmaps.in[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->pyr.p + L.off, dims, strides, boxIn, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(load, level %d) failed: %d", l, (int)r);
+    r = encode(&o->tmaps.out[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->score.p + L.off, dims, strides, boxOut, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(store, level %d) failed: %d", l, (int)r);
+  }
+  return PGB_OK;
+}
+
 int set_geometry(pgb_orb* o, int w, int h) {
   if (w == o->curW && h == o->curH) return PGB_OK;
   OrbGeo g;
@@ -176,6 +223,10 @@ int set_geometry(pgb_orb* o, int w, int h) {
   o->geo = g;
   o->curW = w;
   o->curH = h;
+  if (o->fastV2) {
+    rc = build_tmaps(o);
+    if (rc) return rc;
+  }
   return upload_tabs(o);
 }
 
@@ -199,7 +250,14 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         for (int l = 1; l < g.nlevels; l++)
           launch_pyramid_level(g, l, n, o->pyr.p, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], o->stream);
         break;
-      case 1: launch_fast_score(g, n, o->pyr.p, o->score.p, o->stream); break;
+      case 1:
+        if (o->fastV2) {
+          int rc = launch_fast_score_v2(g, o->tmaps, n, o->numSMs, o->stream);
+          if (rc) return rc;
+        } else {
+          launch_fast_score(g, n, o->pyr.p, o->score.p, o->stream);
+        }
+        break;
       case 2: launch_cells(g, n, o->score.p, o->slots.p, o->cellCnt.p, o->err.p, o->stream); break;
       case 3: launch_octree(g, n, o->slots.p, o->cellCnt.p, o->cand.p, o->staged.p, o->lvlCnt.p, o->err.p, o->stream); break;
       case 4: launch_orient_desc(g, n, o->pyr.p, o->staged.p, o->lvlCnt.p, kps, desc, counts, cap, o->err.p, o->stream); break;
@@ -261,6 +319,12 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
     return nullptr;
   };
   if (build_geo(o, max_width, max_height, &o->capGeo)) return bail("geometry");
+  {
+    const char* impl = getenv("PGB_FAST_IMPL");
+    o->fastV2 = !(impl && strcmp(impl, "v1") == 0);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) o->numSMs = prop.multiProcessorCount;
+  }
   if (stream) o->stream = (cudaStream_t)stream;
   else {
     if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");

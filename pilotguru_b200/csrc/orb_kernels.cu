@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
   int* vlist = remap + cap;                      // children with >1 points created last pass, creation order
   unsigned long long* best = reinterpret_cast<unsigned long long*>(vlist + cap);  // [cap], 8-aligned by layout
   __shared__ int s_scan[kOctThreads];
-  __shared__ int s_n, s_alive, s_nE, s_nV, s_P, s_seq, s_mode, s_finish, s_prevSize, s_nToExpand;
+  __shared__ int s_n, s_alive, s_nE, s_nV, s_P, s_seq, s_mode, s_finish, s_prevSize;
 
   const int nCells = L.nCols * L.nRows;
   const int* cnt = cellCnt + (size_t)f * g.totalCells + L.cellBase;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
           nxt[sidx] = cur[i];
           remap[i] = sidx++;
         }
-        s_alive = size; s_P = P; s_nV = nv; s_nToExpand = nToExpand;
+        s_alive = size; s_P = P; s_nV = nv;
         // loop control (ORBextractor.cc:663-737)
         if (size >= N || size == s_prevSize) s_finish = 1;
         else if (mode == 0 && (size + nToExpand * 3) > N) s_mode = 1;

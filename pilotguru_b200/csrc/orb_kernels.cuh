@@ -7,6 +7,8 @@
 //   cand   [B][candPerFrame] u64  per level: candidates in reference order; hi32 = octree node id | quadrant<<30
 //   staged [B][kpCapInternal]     per level: octree survivors in list order; lvlCnt[B][nlevels]
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include <cstdint>
 
 #include "../../include/pgb200.h"
@@ -22,6 +24,12 @@ constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
 constexpr int kFtW = 256, kFtH = 32, kFtThreads = 256;
 constexpr int kFtInW = kFtW + 8, kFtInH = kFtH + 6;
 
+// FAST score kernel v2 (TMA-staged persistent tiles)
+constexpr int kF2W = 256, kF2H = 64, kF2Threads = 256;
+constexpr int kF2InWords = kF2W / 4 + 4;  // 68 words per row: 8-byte halo left and right
+constexpr int kF2InRows = kF2H + 6;       // 70
+constexpr int kF2InBytes = kF2InWords * 4 * kF2InRows;  // 19040 = TMA transaction size
+
 struct LevelGeo {
   int w, h, pitch;
   unsigned long long off;
@@ -35,15 +43,21 @@ struct LevelGeo {
   unsigned long long candBase;  // in u64 units inside a frame's cand block
   int nodeCap, kpBase;
   int tileBase, tilesX, tilesY;
+  int tile2Base, tiles2X, tiles2Y;
   float scale;
   int patchSize;
 };
 
 struct OrbGeo {
   int nlevels, iniTh, minTh, qTh;
-  int totalCells, totalTiles, kpCapInternal, maxNodeCap;
+  int totalCells, totalTiles, totalTiles2, kpCapInternal, maxNodeCap;
   unsigned long long frameStride, slotsPerFrame, candPerFrame;
   LevelGeo lv[kMaxLevels];
+};
+
+struct alignas(64) TmapPack {  // per level: u32 views of the pyramid (load) and of the score map (store)
+  CUtensorMap in[kMaxLevels];
+  CUtensorMap out[kMaxLevels];
 };
 
 struct ResizeTab {  // one entry per destination column / row
@@ -59,6 +73,7 @@ enum OrbErr { kErrCandOverflow = 1, kErrNodeOverflow = 2, kErrOutCap = 4, kErrCe
 void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
                           const ResizeTab* ytab, cudaStream_t st);
 void launch_fast_score(const OrbGeo& g, int nFrames, const uint8_t* pyr, uint8_t* score, cudaStream_t st);
+int launch_fast_score_v2(const OrbGeo& g, const TmapPack& tm, int nFrames, int numSMs, cudaStream_t st);
 void launch_cells(const OrbGeo& g, int nFrames, const uint8_t* score, uint32_t* slots, int* cellCnt, int* err,
                   cudaStream_t st);
 void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,
