@@ -4,14 +4,15 @@
 // [19, w-19) x [19, h-19), else 0.  Reference: cv::FAST(TYPE_9_16) as called at ORBextractor.cc:809,:814.
 //
 // Per 256x64 tile (one CTA iteration):
-//   * one elected thread issues a 3-D TMA load (cp.async.bulk.tensor) of the 68-word x 70-row halo box of the level
+//   * one elected thread issues a 3-D TMA load (cp.async.bulk.tensor) of the 72-word x 70-row halo box of the level
 //     image into a 2-stage shared-memory ring, signalled through an mbarrier; out-of-image words arrive as zeros.
 //     The load of tile i+1 is in flight while tile i is processed.
 //   * phase 1, per warp (8 rows x 256 px, 8 px per lane): the 14 rows the band touches are loaded once as 64-bit
 //     words and quantised to 6 bits; for every row the compass test "(p0|p8)&(p4|p12) all darker / all brighter than
 //     the centre by more than t" is 8 subtractions per 4 px whose per-byte MSBs are the comparison results.  Lanes
 //     with a surviving pixel append one 32-bit entry (8 flags + row + lane) to the warp's own list via one ballot.
-//   * phase 2, per warp: lanes take entries and score their flagged pixels exactly.  v-p_k and p_k-v ride in the
+//   * phase 2: the tile's entries are split evenly over the warps, expanded into per-pixel candidates (warp scan
+//     + circular queue) and scored exactly 32 at a time.  v-p_k and p_k-v ride in the
 //     two s16 halves of one register, produced by a single IMAD per ring pixel ((v-p)*(1-2^16)); the circular
 //     9-wide sliding minimum is two rounds of 3-input VIMNMX3.S16x2, the maximum a 3-input tree.
 //   * the zero-initialised 256x64 output tile leaves through a TMA store, which also clips it to the image.
@@ -106,11 +107,13 @@ __device__ __forceinline__ int fast_bam_packed(const uint8_t* c) {
 //   [0, 2*kInStage)            input ring, each stage kF2InRows x kF2InWords u32 (stage size rounded up to 128)
 //   [.., +kF2W*kF2H)           output tile
 //   [.., +8 warps * 256 * 4)   warp-private entry lists
-//   [.., +16)                  two mbarriers
+//   [.., +8 warps * 512 * 2)   per-warp circular candidate queues
+//   [.., +16)                  two mbarriers, then the 8 per-warp entry counts
 constexpr int kInStage = (kF2InBytes + 127) / 128 * 128;
 constexpr int kOutBytes = kF2W * kF2H;
 constexpr int kListPerWarp = 8 * 32;
-constexpr int kF2Smem = 2 * kInStage + kOutBytes + 8 * kListPerWarp * 4 + 16;
+constexpr int kQueueCap = 512;  // u16 candidate codes per warp; at most 31 + 256 are ever queued
+constexpr int kF2Smem = 2 * kInStage + kOutBytes + 8 * kListPerWarp * 4 + 8 * kQueueCap * 2 + 16 + 32;
 
 __global__ void __launch_bounds__(kF2Threads, 3) k_fast_score_v2(const __grid_constant__ OrbGeo g,
                                                                  const __grid_constant__ TmapPack tm, int nFrames) {
@@ -118,7 +121,9 @@ __global__ void __launch_bounds__(kF2Threads, 3) k_fast_score_v2(const __grid_co
   uint32_t* sIn0 = reinterpret_cast<uint32_t*>(smem);
   uint8_t* sOut = smem + 2 * kInStage;
   uint32_t* sList = reinterpret_cast<uint32_t*>(sOut + kOutBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sList + 8 * kListPerWarp);
+  uint16_t* sQueue = reinterpret_cast<uint16_t*>(sList + 8 * kListPerWarp);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQueue + 8 * kQueueCap);
+  int* sCnt = reinterpret_cast<int*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = g.totalTiles2 * nFrames;
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(kF2Threads, 3) k_fast_score_v2(const __grid_co
     int level, x0, y0, f;
     decode(t, level, x0, y0, f);
     mbar_expect_tx(&bars[stage], kF2InBytes);
-    tma_load_3d(smem + stage * kInStage, &tm.in[level], x0 / 4 - 2, y0 - 3, f, &bars[stage]);
+    tma_load_3d(smem + stage * kInStage, &tm.in[level], x0 / 4 - 4, y0 - 3, f, &bars[stage]);
   };
 
   int t = blockIdx.x;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(kF2Threads, 3) k_fast_score_v2(const __grid_co
     if (bandLive && __any_sync(0xffffffffu, (xmA | xmB) != 0)) {
       // quantised own words of the 14 smem rows r0 .. r0+13 (global rows y0+r0-3 .. y0+r0+10)
       uint32_t qa[14], qb[14];
-      const uint32_t* col = sIn + r0 * kF2InWords + 2 + 2 * lane;
+      const uint32_t* col = sIn + r0 * kF2InWords + 4 + 2 * lane;
 #pragma unroll
       for (int i = 0; i < 14; i++) {
         const uint2 v = *reinterpret_cast<const uint2*>(col + i * kF2InWords);
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(kF2Threads, 3) k_fast_score_v2(const __grid_co
       for (int j = 0; j < 8; j++) {
         const int gy = y0 + r0 + j;
         if (gy < kEdge || gy >= L.h - kEdge) continue;  // warp-uniform
-        const uint32_t* crow = sIn + (r0 + j + 3) * kF2InWords + 1 + 2 * lane;
+        const uint32_t* crow = sIn + (r0 + j + 3) * kF2InWords + 3 + 2 * lane;
         const uint32_t qL = quant6(crow[0]), qR = quant6(crow[3]);
         const uint32_t cA = qa[j + 3], cB = qb[j + 3];
         const uint32_t a12 = __byte_perm(qL, cA, 0x4321), a4 = __byte_perm(cA, cB, 0x6543);
@@ -221,26 +226,68 @@ __global__ void __launch_bounds__(kF2Threads, 3) k_fast_score_v2(const __grid_co
     }
     __syncwarp();
 
-    // ---------------- phase 2
+    // ---------------- phase 2: the tile's entries (all warps' lists, concatenated) are split evenly over the
+    // warps; each warp expands its share into per-pixel candidates through a small circular queue and scores them
+    // 32 at a time, so lanes stay full no matter how the candidates cluster.
+    if (lane == 0) sCnt[warp] = cnt;
+    __syncthreads();
     {
+      int pre[9];
+      pre[0] = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) pre[w + 1] = pre[w] + sCnt[w];
+      const int tot = pre[8];
+      const int lo = (int)(((long long)tot * warp) >> 3), hi = (int)(((long long)tot * (warp + 1)) >> 3);
+      uint16_t* q = sQueue + warp * kQueueCap;
       const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn);
-      for (int e0 = 0; e0 < cnt; e0 += 32) {
-        const int e = e0 + lane;
-        uint32_t entry = e < cnt ? myList[e] : 0u;
-        uint32_t flags = entry & 0xC0C0C0C0u;
-        const int j = entry & 7, ln = (entry >> 8) & 31;
-        const uint8_t* base = sInB + (r0 + j + 3) * (kF2InWords * 4) + 8 + ln * 8;
-        uint8_t* obase = sOut + (r0 + j) * kF2W + ln * 8;
-        while (__any_sync(0xffffffffu, flags != 0)) {
-          if (flags) {
-            const int bit = __ffs(flags) - 1;
-            flags &= flags - 1;
-            const int xo = (bit >> 3) + (((bit & 7) == 6) ? 4 : 0);
-            const int bam = fast_bam_packed(base + xo);
-            if (bam > g.minTh) obase[xo] = (uint8_t)(bam - 1);
-          }
+      int head = 0, tail = 0;
+      auto score_round = [&](int n) {  // the first n queued candidates, one per lane
+        if (lane < n) {
+          const int code = q[(head + lane) & (kQueueCap - 1)];
+          const int r = code >> 8, x = code & 255;
+          const int bam = fast_bam_packed(sInB + (r + 3) * (kF2InWords * 4) + 16 + x);
+          if (bam > g.minTh) sOut[r * kF2W + x] = (uint8_t)(bam - 1);
         }
+      };
+      for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        uint32_t flags = 0;
+        int rbase = 0, xbase = 0;
+        if (e < hi) {
+          int w = 0, wbase = 0;
+#pragma unroll
+          for (int k = 1; k < 8; k++)
+            if (e >= pre[k]) { w = k; wbase = pre[k]; }
+          const uint32_t entry = sList[w * kListPerWarp + (e - wbase)];
+          flags = entry & 0xC0C0C0C0u;
+          rbase = (w * 8 + (int)(entry & 7)) << 8;
+          xbase = (int)((entry >> 8) & 31) * 8;
+        }
+        // exclusive scan of the per-lane candidate counts
+        const int c = __popc(flags);
+        int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += v;
+        }
+        int pos = tail + inc - c;
+        tail += __shfl_sync(0xffffffffu, inc, 31);
+        while (flags) {
+          const int bit = __ffs(flags) - 1;
+          flags &= flags - 1;
+          const int xo = (bit >> 3) + (((bit & 7) == 6) ? 4 : 0);
+          q[pos & (kQueueCap - 1)] = (uint16_t)(rbase | (xbase + xo));
+          pos++;
+        }
+        __syncwarp();
+        while (tail - head >= 32) {
+          score_round(32);
+          head += 32;
+        }
+        __syncwarp();
       }
+      if (tail > head) score_round(tail - head);
     }
     fence_proxy_async();
     __syncthreads();  // every warp is done with sIn[stage] and with its band of sOut

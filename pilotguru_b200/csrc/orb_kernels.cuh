@@ -26,9 +26,10 @@ constexpr int kFtInW = kFtW + 8, kFtInH = kFtH + 6;
 
 // FAST score kernel v2 (TMA-staged persistent tiles)
 constexpr int kF2W = 256, kF2H = 64, kF2Threads = 256;
-constexpr int kF2InWords = kF2W / 4 + 4;  // 68 words per row: 8-byte halo left and right
+constexpr int kF2InWords = kF2W / 4 + 8;  // 72 words per row: 16-byte halo left and right (a TMA box must start
+                                          // on a 16-byte boundary in the innermost dimension; measured: tools/probe)
 constexpr int kF2InRows = kF2H + 6;       // 70
-constexpr int kF2InBytes = kF2InWords * 4 * kF2InRows;  // 19040 = TMA transaction size
+constexpr int kF2InBytes = kF2InWords * 4 * kF2InRows;  // 20160 = TMA transaction size
 
 struct LevelGeo {
   int w, h, pitch;
