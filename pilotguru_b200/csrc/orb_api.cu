@@ -60,6 +60,7 @@ struct pgb_orb {
   int outCap = 0;
   DevBuf<uint8_t> tmpLevel;
   TmapPack tmaps{};
+  DevBuf<int4> tileTab;
   bool fastV2 = true;  // PGB_FAST_IMPL=v1 selects the first-generation kernel (kept for A/B measurements)
   int numSMs = 148;
 };
@@ -226,6 +227,13 @@ int set_geometry(pgb_orb* o, int w, int h) {
   if (o->fastV2) {
     rc = build_tmaps(o);
     if (rc) return rc;
+    std::vector<int4> tab;
+    for (int l = 0; l < g.nlevels; l++)
+      for (int ty = 0; ty < g.lv[l].tiles2Y; ty++)
+        for (int tx = 0; tx < g.lv[l].tiles2X; tx++) tab.push_back(make_int4(l, tx * kF2W, ty * kF2H, 0));
+    if (o->tileTab.n < tab.size() && o->tileTab.alloc(tab.size())) return PGB_ERR_CUDA;
+    PGB_CUDA(cudaMemcpyAsync(o->tileTab.p, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice, o->stream));
+    PGB_CUDA(cudaStreamSynchronize(o->stream));
   }
   return upload_tabs(o);
 }
@@ -252,7 +260,7 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         break;
       case 1:
         if (o->fastV2) {
-          int rc = launch_fast_score_v2(g, o->tmaps, n, o->numSMs, o->stream);
+          int rc = launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, n, o->stream);
           if (rc) return rc;
         } else {
           launch_fast_score(g, n, o->pyr.p, o->score.p, o->stream);

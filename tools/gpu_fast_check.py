@@ -22,7 +22,7 @@ for name, (img, nf) in cases.items():
     ok, od = orc.extract(img)
     refs[name] = (ok, od, [O.fast_score_map(orc.level(l), 7) for l in range(8)])
 frames = np.stack([synth.frame(t) for t in range(B)])
-for impl in ("v1", "v2"):
+for impl in os.environ.get("CHK_IMPLS", "v1,v2").split(","):
     os.environ["PGB_FAST_IMPL"] = impl
     r = {}
     for name, (img, nf) in cases.items():
