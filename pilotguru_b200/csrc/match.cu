@@ -6,11 +6,8 @@
 // ComputeThreeMaxima :1605-1646; TH_HIGH=100, HISTO_LENGTH=30 (:38-40); retry at 2*th below 20 matches
 // (Tracking.cc:876-883).
 //
-// One CTA per frame pair.  Phase A (all warps): one warp per query; lanes sweep the current frame's keypoints
-// (descriptors staged in shared memory), apply the window/octave/grid tests, take the 256-bit Hamming distance
-// with POPC and keep the query's candidates sorted by (distance, traversal order).  Phase B (one warp): the
-// reference's greedy loop is sequential in the query index -- a target taken by an earlier query is skipped --
-// so the queries are replayed in order, each taking the first candidate of its sorted list that is still free.
+// One CTA per frame pair; the phases are described at k_match.  The reference's greedy loop is sequential in the
+// query index -- a target taken by an earlier query is skipped -- which is why phase B replays the queries in order.
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -20,9 +17,8 @@
 namespace pgb {
 
 constexpr int kMtThreads = 256;
-constexpr int kMtWarps = kMtThreads / 32;
+
 constexpr int kMtK = 32;        // sorted candidates kept per query
-constexpr int kMtStage = 128;   // per-warp staging of unsorted candidates
 constexpr int kThHigh = 100;
 constexpr int kHisto = 30;
 constexpr int kGridCols = 64, kGridRows = 48;
@@ -45,7 +41,7 @@ struct MatchArgs {
   const float* flow;
   int* matchOfCur;   // [pair][cap]
   int* nMatches;     // [pair]
-  unsigned long long* qList;  // scratch [pair][cap][kMtK]
+  uint32_t* qList32;          // scratch [pair][cap][kMtK]: target | distance << 16, in arrival order
   int* qCnt;                  // scratch [pair][cap] (total candidates found, may exceed kMtK)
 };
 
@@ -84,8 +80,36 @@ __device__ __forceinline__ QueryWin make_window(const MatchArgs& A, float u, flo
   return q;
 }
 
-// shared-memory layout per CTA (dynamic): for each current keypoint: 8 x u32 descriptor, x, y (float),
-// meta = posX | posY<<8 | octave<<16 | ingrid<<24, taken/bin byte.
+// shared-memory layout per CTA (dynamic): for each current keypoint 8 x u32 descriptor, x, y, angle (float),
+// meta = posX | posY<<8 | octave<<16 | ingrid<<24, bin/taken word, the grid-cell-sorted index list; then the
+// 64x48 grid's cell start offsets (u16).
+//
+// Phase 0: current keypoints are binned into the Frame grid (counting sort that keeps index order inside a cell,
+//          Frame.cc:234-249).
+// Phase A: one THREAD per query walks its window's cells in the reference's order (ix, iy, index ascending --
+//          Frame.cc:352-381), applies the octave and |dx|,|dy| < r tests, takes the Hamming distance with POPC and
+//          appends (distance, target) to the query's candidate row in arrival order.
+// Phase B: one warp replays the reference's greedy loop in query order: lanes hold the query's candidates, taken
+//          targets are masked out and a single warp-wide min over (distance << 8 | arrival) picks the winner --
+//          strict '<' with first-wins ties, ORBmatcher.cc:1420-1433.  The next query's row is prefetched.
+constexpr int kCells = kGridCols * kGridRows;  // 3072
+
+__device__ __forceinline__ bool query_window(const MatchArgs& A, int p, int i, const pgb_keypoint* prevK, float fx,
+                                             float fy, float invW, float invH, QueryWin* q) {
+  float u, v;
+  int oct;
+  bool valid;
+  if (A.consecutive) {
+    const pgb_keypoint k = prevK[i];
+    u = k.x + fx; v = k.y + fy; oct = k.octave; valid = true;
+  } else {
+    const size_t o = (size_t)p * A.cap + i;
+    u = A.qUV[o * 2]; v = A.qUV[o * 2 + 1]; oct = A.qOct[o]; valid = A.qValid[o] != 0;
+  }
+  *q = make_window(A, u, v, oct, valid, invW, invH);
+  return q->ok;
+}
+
 __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -116,13 +140,15 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   nCur = min(nCur, cap);
   nQ = min(nQ, cap);
 
-  uint32_t* sDesc = reinterpret_cast<uint32_t*>(smem);           // [cap][8]
-  float* sX = reinterpret_cast<float*>(sDesc + (size_t)cap * 8); // [cap]
+  uint32_t* sDesc = reinterpret_cast<uint32_t*>(smem);            // [cap][8]
+  float* sX = reinterpret_cast<float*>(sDesc + (size_t)cap * 8);  // [cap]
   float* sY = sX + cap;
-  uint32_t* sMeta = reinterpret_cast<uint32_t*>(sY + cap);       // [cap]
-  float* sAng = reinterpret_cast<float*>(sMeta + cap);           // [cap]
-  unsigned long long* sStage = reinterpret_cast<unsigned long long*>(sAng + cap);  // [warps][kMtStage]; 48*cap bytes in: 16-aligned
-  int* sBin = reinterpret_cast<int*>(sStage + kMtWarps * kMtStage);  // [cap] -1 free, else histogram bin
+  uint32_t* sMeta = reinterpret_cast<uint32_t*>(sY + cap);        // [cap]
+  float* sAng = reinterpret_cast<float*>(sMeta + cap);            // [cap]
+  int* sBin = reinterpret_cast<int*>(sAng + cap);                 // [cap] -1 free, else histogram bin
+  uint16_t* sOrder = reinterpret_cast<uint16_t*>(sBin + cap);     // [cap] target indices sorted by cell
+  uint16_t* sCell = sOrder + cap + (cap & 1);                     // [kCells + 1] start offsets, then cursors
+  uint16_t* sCur = sCell + kCells + 2;                            // [kCells] running cursors for the scatter
   __shared__ int sHist[kHisto];
   __shared__ int sKeep[3];
   __shared__ int sNm;
@@ -131,6 +157,8 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   const float invH = (float)kGridRows / (A.maxY - A.minY);
 
   int* matchOfCur = A.matchOfCur + (size_t)p * cap;
+  for (int i = tid; i < kCells + 1; i += kMtThreads) sCell[i] = 0;
+  __syncthreads();
   for (int i = tid; i < nCur; i += kMtThreads) {
     const pgb_keypoint k = curK[i];
     sX[i] = k.x; sY[i] = k.y; sAng[i] = k.angle;
@@ -138,70 +166,80 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
     const bool in = !(posX < 0 || posX >= kGridCols || posY < 0 || posY >= kGridRows);
     sMeta[i] = in ? ((uint32_t)posX | ((uint32_t)posY << 8) | ((uint32_t)(k.octave & 0xff) << 16) | (1u << 24)) : 0u;
     sBin[i] = -1;
+    if (in) atomicAdd(reinterpret_cast<unsigned int*>(sCell) + ((posX * kGridRows + posY + 1) >> 1),
+                      ((posX * kGridRows + posY + 1) & 1) ? 0x10000u : 1u);  // u16 histogram, two bins per word
   }
   for (int i = tid; i < cap; i += kMtThreads) matchOfCur[i] = -1;
   for (int i = tid; i < nCur * 8; i += kMtThreads) sDesc[i] = reinterpret_cast<const uint32_t*>(curD)[i];
   if (tid < kHisto) sHist[tid] = 0;
   if (tid == 0) sNm = 0;
   __syncthreads();
+  // exclusive scan of the histogram (sCell[c + 1] holds the count of cell c): warp 0, 96 bins per lane
+  if (warp == 0) {
+    constexpr int per = kCells / 32;  // 96
+    int sum = 0;
+    for (int k = 0; k < per; k++) sum += sCell[1 + lane * per + k];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int run = incl - sum;
+    for (int k = 0; k < per; k++) {
+      const int c = sCell[1 + lane * per + k];
+      sCur[lane * per + k] = (uint16_t)run;
+      run += c;
+      sCell[1 + lane * per + k] = (uint16_t)run;  // becomes the END offset of cell (lane*per + k) = start of the next
+    }
+  }
+  __syncthreads();
+  // scatter in index order (one warp, chunks of 32 in order; lanes of a chunk that share a cell are ranked by lane)
+  if (warp == 0) {
+    for (int t0 = 0; t0 < nCur; t0 += 32) {
+      const int t = t0 + lane;
+      const uint32_t m = t < nCur ? sMeta[t] : 0u;
+      const bool in = (m >> 24) != 0;
+      const int cell = in ? (int)(m & 0xff) * kGridRows + (int)((m >> 8) & 0xff) : -1 - lane;
+      const uint32_t same = __match_any_sync(0xffffffffu, cell);
+      if (in) {
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        sOrder[sCur[cell] + rank] = (uint16_t)t;
+      }
+      __syncwarp();
+      if (in && (same & ((1u << lane) - 1u)) == 0) sCur[cell] = (uint16_t)(sCur[cell] + __popc(same));
+      __syncwarp();
+    }
+  }
+  __syncthreads();
 
-  unsigned long long* qList = A.qList + (size_t)p * cap * kMtK;
+  uint32_t* qRow = A.qList32 + (size_t)p * cap * kMtK;  // [query][kMtK]: target | dist << 16, arrival order
   int* qCnt = A.qCnt + (size_t)p * cap;
 
-  // ---------------- phase A
-  unsigned long long* stage = sStage + warp * kMtStage;
-  for (int i = warp; i < nQ; i += kMtWarps) {
-    float u, v;
-    int oct;
-    bool valid;
-    if (A.consecutive) {
-      const pgb_keypoint k = prevK[i];
-      u = k.x + fx; v = k.y + fy; oct = k.octave; valid = true;
-    } else {
-      u = A.qUV[((size_t)p * cap + i) * 2]; v = A.qUV[((size_t)p * cap + i) * 2 + 1];
-      oct = A.qOct[(size_t)p * cap + i]; valid = A.qValid[(size_t)p * cap + i] != 0;
-    }
-    const QueryWin q = make_window(A, u, v, oct, valid, invW, invH);
+  // ---------------- phase A: thread per query
+  for (int i = tid; i < nQ; i += kMtThreads) {
+    QueryWin q;
     int cnt = 0;
-    if (q.ok) {
+    if (query_window(A, p, i, prevK, fx, fy, invW, invH, &q)) {
       uint32_t qd[8];
 #pragma unroll
       for (int w = 0; w < 8; w++) qd[w] = reinterpret_cast<const uint32_t*>(qD)[(size_t)i * 8 + w];
-      for (int t0 = 0; t0 < nCur; t0 += 32) {
-        const int t = t0 + lane;
-        bool hit = false;
-        unsigned long long key = 0;
-        if (t < nCur) {
-          const uint32_t m = sMeta[t];
-          const int posX = m & 0xff, posY = (m >> 8) & 0xff, o = (m >> 16) & 0xff;
-          if ((m >> 24) && posX >= q.cx0 && posX <= q.cx1 && posY >= q.cy0 && posY <= q.cy1 && o >= q.o0 && o <= q.o1) {
-            const float dx = sX[t] - q.u, dy = sY[t] - q.v;
-            if (fabsf(dx) < q.r && fabsf(dy) < q.r) {
-              const int d = hamming256(qd, sDesc + (size_t)t * 8);
-              key = ((unsigned long long)d << 40) | ((unsigned long long)(posX * kGridRows + posY) << 20) | (unsigned)t;
-              hit = true;
-            }
+      for (int ix = q.cx0; ix <= q.cx1; ix++)
+        for (int iy = q.cy0; iy <= q.cy1; iy++) {
+          const int cell = ix * kGridRows + iy;
+          const int e1 = sCell[cell + 1];
+          for (int e = cell ? sCell[cell] : 0; e < e1; e++) {
+            const int t = sOrder[e];
+            const int o = (sMeta[t] >> 16) & 0xff;
+            if (o < q.o0 || o > q.o1) continue;
+            if (!(fabsf(sX[t] - q.u) < q.r && fabsf(sY[t] - q.v) < q.r)) continue;
+            const int d = hamming256(qd, sDesc + (size_t)t * 8);
+            if (cnt < kMtK) qRow[(size_t)i * kMtK + cnt] = (uint32_t)t | ((uint32_t)d << 16);
+            cnt++;
           }
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-          const int pos = cnt + __popc(bal & ((1u << lane) - 1));
-          if (pos < kMtStage) stage[pos] = key;
-        }
-        cnt += __popc(bal);
-      }
-      __syncwarp();
-      // rank-sort the staged keys (distinct by construction) and keep the kMtK smallest
-      const int ns = min(cnt, kMtStage);
-      for (int a = lane; a < ns; a += 32) {
-        const unsigned long long ka = stage[a];
-        int rank = 0;
-        for (int b = 0; b < ns; b++) rank += (stage[b] < ka);
-        if (rank < kMtK) qList[(size_t)i * kMtK + rank] = ka;
-      }
-      __syncwarp();
     }
-    if (lane == 0) qCnt[i] = cnt;
+    qCnt[i] = cnt;
   }
   __syncthreads();
 
@@ -209,33 +247,29 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   if (warp == 0) {
     const float factor = 1.0f / kHisto;
     int nm = 0;
+    int cntN = nQ > 0 ? qCnt[0] : 0;
+    uint32_t entN = (nQ > 0 && lane < min(cntN, kMtK)) ? qRow[lane] : 0u;
     for (int i = 0; i < nQ; i++) {
-      const int cnt = qCnt[i];
-      if (cnt == 0) continue;
-      const int nl = min(cnt, kMtK);
-      unsigned long long key = ~0ull;
-      bool freeSlot = false;
-      if (lane < nl) {
-        key = qList[(size_t)i * kMtK + lane];
-        freeSlot = sBin[(int)(key & 0xfffff)] == -1;
+      const int cnt = cntN;
+      const uint32_t ent = entN;
+      if (i + 1 < nQ) {  // prefetch the next query's candidate row
+        cntN = qCnt[i + 1];
+        entN = lane < min(cntN, kMtK) ? qRow[(size_t)(i + 1) * kMtK + lane] : 0u;
       }
-      uint32_t bal = __ballot_sync(0xffffffffu, freeSlot);
-      unsigned long long win = ~0ull;
-      if (bal && cnt <= kMtStage) {
-        win = __shfl_sync(0xffffffffu, key, __ffs(bal) - 1);
-      } else if (cnt > kMtK) {
-        // (the staged list was complete only up to kMtStage candidates; beyond that, and whenever
-        //  every kept candidate is taken while more existed, redo the full sweep skipping taken targets)
-        float u, v;
-        int oct;
-        if (A.consecutive) {
-          const pgb_keypoint k = prevK[i];
-          u = k.x + fx; v = k.y + fy; oct = k.octave;
-        } else {
-          u = A.qUV[((size_t)p * cap + i) * 2]; v = A.qUV[((size_t)p * cap + i) * 2 + 1];
-          oct = A.qOct[(size_t)p * cap + i];
+      if (cnt == 0) continue;
+      int winT = -1, winD = 256;
+      if (cnt <= kMtK) {
+        uint32_t key = 0xffffffffu;
+        if (lane < cnt && sBin[ent & 0xffff] == -1) key = ((ent >> 16) << 8) | (uint32_t)lane;
+        const uint32_t best = __reduce_min_sync(0xffffffffu, key);
+        if (best != 0xffffffffu) {
+          winD = (int)(best >> 8);
+          winT = (int)(__shfl_sync(0xffffffffu, ent, best & 31) & 0xffff);
         }
-        const QueryWin q = make_window(A, u, v, oct, true, invW, invH);
+      } else {
+        // more candidates than a row holds: redo the window sweep for this query, skipping taken targets
+        QueryWin q;
+        query_window(A, p, i, prevK, fx, fy, invW, invH, &q);
         uint32_t qd[8];
 #pragma unroll
         for (int w = 0; w < 8; w++) qd[w] = reinterpret_cast<const uint32_t*>(qD)[(size_t)i * 8 + w];
@@ -253,26 +287,23 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
         }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, s));
-        win = best;
+        if (best != ~0ull) { winD = (int)(best >> 40); winT = (int)(best & 0xfffff); }
       }
-      if (win != ~0ull) {
-        const int dist = (int)(win >> 40), t = (int)(win & 0xfffff);
-        if (dist <= kThHigh) {
-          int bin = kHisto;  // "assigned, no histogram"
-          if (A.checkOri) {
-            const float qa = A.consecutive ? prevK[i].angle : A.qAng[(size_t)p * cap + i];
-            float rot = qa - sAng[t];
-            if (rot < 0.0f) rot += 360.0f;
-            bin = (int)roundf(rot * factor);
-            if (bin == kHisto) bin = 0;
-          }
-          if (lane == 0) {
-            sBin[t] = bin;
-            matchOfCur[t] = i;
-            if (A.checkOri) sHist[bin]++;
-          }
-          nm++;
+      if (winT >= 0 && winD <= kThHigh) {
+        int bin = kHisto;  // "assigned, no histogram"
+        if (A.checkOri) {
+          const float qa = A.consecutive ? prevK[i].angle : A.qAng[(size_t)p * cap + i];
+          float rot = qa - sAng[winT];
+          if (rot < 0.0f) rot += 360.0f;
+          bin = (int)roundf(rot * factor);
+          if (bin == kHisto) bin = 0;
         }
+        if (lane == 0) {
+          sBin[winT] = bin;
+          matchOfCur[winT] = i;
+          if (A.checkOri) sHist[bin]++;
+        }
+        nm++;
       }
       __syncwarp();
     }
@@ -310,9 +341,9 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
 }
 
 size_t match_smem_bytes(int cap) {
-  size_t b = (size_t)cap * 8 * 4 + (size_t)cap * 4 * 4;
-  b += (size_t)kMtWarps * kMtStage * 8;
-  b += (size_t)cap * 4;
+  size_t b = (size_t)cap * 8 * 4 + (size_t)cap * 5 * 4;        // desc, x, y, meta, angle, bin
+  b += (size_t)(cap + (cap & 1)) * 2;                           // cell-sorted order
+  b += (size_t)(kCells + 2) * 2 + (size_t)kCells * 2;           // cell offsets + cursors
   return b + 16;
 }
 
@@ -332,7 +363,7 @@ struct pgb_matcher {
   float nnratio = 0.f;
   cudaStream_t stream = nullptr;
   bool ownStream = false;
-  DevBuf<unsigned long long> qList;
+  DevBuf<uint32_t> qList;
   DevBuf<int> qCnt;
   // staging for host-buffer calls
   DevBuf<pgb_keypoint> dK;
@@ -353,7 +384,7 @@ int launch_match(pgb_matcher* m, MatchArgs& A, int nPairs) {
     PGB_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     m->smemConfigured = smem;
   }
-  A.qList = m->qList.p;
+  A.qList32 = m->qList.p;
   A.qCnt = m->qCnt.p;
   k_match<<<nPairs, kMtThreads, smem, m->stream>>>(A);
   PGB_CHECK_LAUNCH();
