@@ -252,6 +252,11 @@ def main():
             reps = 10
             t = timed(lambda: ex.run_stage(which), reps)
             stage_us[name] = 1e3 * t / reps / B
+        match_fn = lambda: mt.match_consecutive_ptr(B, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0),
+                                                    flow_dev.data_ptr(), float(W), float(H), 15.0, sf,
+                                                    match.data_ptr(), nmatch.data_ptr())
+        match_fn()
+        stage_us["match"] = 1e3 * timed(match_fn, 10) / 10 / B
     frames_total = B * world
     value = frames_total * K / (ms * 1e-3)
     e2e = frames_total * K / (ms_e2e * 1e-3)

@@ -109,7 +109,7 @@ template <int kOcc>
 __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v2(const __grid_constant__ OrbGeo g,
                                                                  const __grid_constant__ TmapPack tm,
                                                                  const int4* __restrict__ tileTab,
-                                                                 uint8_t* __restrict__ score) {
+                                                                 uint8_t* __restrict__ score, int frame0) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t* sIn = reinterpret_cast<const uint32_t*>(smem);
   uint32_t* sList = reinterpret_cast<uint32_t*>(smem + kInStage);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v2(const __grid
   int* sCnt = reinterpret_cast<int*>(bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int f = blockIdx.y;
+  const int f = blockIdx.y + frame0;
   const int4 te = __ldg(&tileTab[blockIdx.x]);
   const int level = te.x, x0 = te.y, y0 = te.z;
   const LevelGeo& L = g.lv[level];
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v2(const __grid
   }
 }
 
-int launch_fast_score_v2(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, uint8_t* score, int nFrames,
-                         cudaStream_t st) {
+int launch_fast_score_v2(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, uint8_t* score, int frame0,
+                         int nFrames, cudaStream_t st) {
   static int occ = 0;
   if (!occ) {
     const char* e = getenv("PGB_FAST_OCC");  // resident CTAs per SM the kernel is compiled for (register budget)
@@ -257,8 +257,8 @@ int launch_fast_score_v2(const OrbGeo& g, const TmapPack& tm, const int4* tileTa
   }
   if (g.totalTiles2 <= 0 || nFrames <= 0) return PGB_OK;
   dim3 grid(g.totalTiles2, nFrames);
-  if (occ == 6) k_fast_score_v2<6><<<grid, kF2Threads, kF2Smem, st>>>(g, tm, tileTab, score);
-  else k_fast_score_v2<5><<<grid, kF2Threads, kF2Smem, st>>>(g, tm, tileTab, score);
+  if (occ == 6) k_fast_score_v2<6><<<grid, kF2Threads, kF2Smem, st>>>(g, tm, tileTab, score, frame0);
+  else k_fast_score_v2<5><<<grid, kF2Threads, kF2Smem, st>>>(g, tm, tileTab, score, frame0);
   PGB_LAUNCHED();
   return PGB_OK;
 }

@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   uint16_t* sOrder = reinterpret_cast<uint16_t*>(sBin + cap);     // [cap] target indices sorted by cell
   uint16_t* sCell = sOrder + cap + (cap & 1);                     // [kCells + 1] start offsets, then cursors
   uint16_t* sCur = sCell + kCells + 2;                            // [kCells] running cursors for the scatter
+  float* sQAng = reinterpret_cast<float*>(sCur + kCells);         // [cap] query angles (phase B must not touch HBM)
+  int* sMatch = reinterpret_cast<int*>(sQAng + cap);              // [cap] match_of_cur, written out at the end
   __shared__ int sHist[kHisto];
   __shared__ int sKeep[3];
   __shared__ int sNm;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
     if (in) atomicAdd(reinterpret_cast<unsigned int*>(sCell) + ((posX * kGridRows + posY + 1) >> 1),
                       ((posX * kGridRows + posY + 1) & 1) ? 0x10000u : 1u);  // u16 histogram, two bins per word
   }
-  for (int i = tid; i < cap; i += kMtThreads) matchOfCur[i] = -1;
+  for (int i = tid; i < cap; i += kMtThreads) sMatch[i] = -1;
   for (int i = tid; i < nCur * 8; i += kMtThreads) sDesc[i] = reinterpret_cast<const uint32_t*>(curD)[i];
   if (tid < kHisto) sHist[tid] = 0;
   if (tid == 0) sNm = 0;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   for (int i = tid; i < nQ; i += kMtThreads) {
     QueryWin q;
     int cnt = 0;
+    sQAng[i] = A.consecutive ? prevK[i].angle : A.qAng[(size_t)p * cap + i];
     if (query_window(A, p, i, prevK, fx, fy, invW, invH, &q)) {
       uint32_t qd[8];
 #pragma unroll
@@ -247,15 +250,30 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   if (warp == 0) {
     const float factor = 1.0f / kHisto;
     int nm = 0;
-    int cntN = nQ > 0 ? qCnt[0] : 0;
-    uint32_t entN = (nQ > 0 && lane < min(cntN, kMtK)) ? qRow[lane] : 0u;
+    // candidate rows are streamed through registers in blocks of kPB queries, one block ahead of the replay, so
+    // the global-memory latency of a row is hidden behind the resolution of the previous block
+    constexpr int kPB = 8;
+    uint32_t rowN[kPB], row[kPB];
+    int cN, cC = 0;
+    auto load_block = [&](int i0, uint32_t (&r)[kPB], int& c) {
+      c = (lane < kPB && i0 + lane < nQ) ? qCnt[i0 + lane] : 0;
+#pragma unroll
+      for (int k = 0; k < kPB; k++) r[k] = (i0 + k < nQ) ? qRow[(size_t)(i0 + k) * kMtK + lane] : 0u;
+    };
+    load_block(0, rowN, cN);
     for (int i = 0; i < nQ; i++) {
-      const int cnt = cntN;
-      const uint32_t ent = entN;
-      if (i + 1 < nQ) {  // prefetch the next query's candidate row
-        cntN = qCnt[i + 1];
-        entN = lane < min(cntN, kMtK) ? qRow[(size_t)(i + 1) * kMtK + lane] : 0u;
+      const int k = i & (kPB - 1);
+      if (k == 0) {
+#pragma unroll
+        for (int q = 0; q < kPB; q++) row[q] = rowN[q];
+        cC = cN;
+        load_block(i + kPB, rowN, cN);
       }
+      const int cnt = __shfl_sync(0xffffffffu, cC, k);
+      uint32_t ent = row[0];
+#pragma unroll
+      for (int q = 1; q < kPB; q++)
+        if (k == q) ent = row[q];
       if (cnt == 0) continue;
       int winT = -1, winD = 256;
       if (cnt <= kMtK) {
@@ -292,15 +310,14 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
       if (winT >= 0 && winD <= kThHigh) {
         int bin = kHisto;  // "assigned, no histogram"
         if (A.checkOri) {
-          const float qa = A.consecutive ? prevK[i].angle : A.qAng[(size_t)p * cap + i];
-          float rot = qa - sAng[winT];
+          float rot = sQAng[i] - sAng[winT];
           if (rot < 0.0f) rot += 360.0f;
           bin = (int)roundf(rot * factor);
           if (bin == kHisto) bin = 0;
         }
         if (lane == 0) {
           sBin[winT] = bin;
-          matchOfCur[winT] = i;
+          sMatch[winT] = i;
           if (A.checkOri) sHist[bin]++;
         }
         nm++;
@@ -330,13 +347,14 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
     for (int t = tid; t < nCur; t += kMtThreads) {
       const int b = sBin[t];
       if (b >= 0 && b < kHisto && b != sKeep[0] && b != sKeep[1] && b != sKeep[2]) {
-        matchOfCur[t] = -1;
+        sMatch[t] = -1;
         removed++;
       }
     }
     if (removed) atomicSub(&sNm, removed);
     __syncthreads();
   }
+  for (int i = tid; i < cap; i += kMtThreads) matchOfCur[i] = sMatch[i];
   if (tid == 0) A.nMatches[p] = sNm;
 }
 
@@ -344,6 +362,7 @@ size_t match_smem_bytes(int cap) {
   size_t b = (size_t)cap * 8 * 4 + (size_t)cap * 5 * 4;        // desc, x, y, meta, angle, bin
   b += (size_t)(cap + (cap & 1)) * 2;                           // cell-sorted order
   b += (size_t)(kCells + 2) * 2 + (size_t)kCells * 2;           // cell offsets + cursors
+  b += (size_t)cap * 8;                                         // query angles, match_of_cur
   return b + 16;
 }
 

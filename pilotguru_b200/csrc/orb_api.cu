@@ -61,11 +61,17 @@ struct pgb_orb {
   DevBuf<uint8_t> tmpLevel;
   TmapPack tmaps{};
   DevBuf<int4> tileTab;
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evDone = nullptr;
+  cudaEvent_t evChunk[16] = {};
+  int h2dChunk = 8;  // frames per H2D/compute pipeline chunk (PGB_H2D_CHUNK)
   bool fastV2 = true;  // PGB_FAST_IMPL=v1 selects the first-generation kernel (kept for A/B measurements)
   int numSMs = 148;
 };
 
 namespace {
+
+constexpr int kMaxChunkEvents = 16;
 
 int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
   memset(g, 0, sizeof *g);
@@ -249,30 +255,66 @@ int check_err_flag(pgb_orb* o) {
   return PGB_OK;
 }
 
-int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap) {
+// Stages `from`..`to` over frames [f0, f0+n) of the resident batch; kps/desc/counts are the bases of the WHOLE
+// batch's output arrays (frame f0 writes at f0*cap).
+int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap, int f0, int n) {
   const OrbGeo& g = o->geo;
-  const int n = o->curFrames;
+  if (n <= 0) return PGB_OK;
+  uint8_t* pyr = o->pyr.p + (size_t)f0 * g.frameStride;
+  uint8_t* score = o->score.p + (size_t)f0 * g.frameStride;
+  uint32_t* slots = o->slots.p + (size_t)f0 * g.slotsPerFrame;
+  int* cellCnt = o->cellCnt.p + (size_t)f0 * g.totalCells;
+  unsigned long long* cand = o->cand.p + (size_t)f0 * g.candPerFrame;
+  StagedKp* staged = o->staged.p + (size_t)f0 * g.kpCapInternal;
+  int* lvlCnt = o->lvlCnt.p + (size_t)f0 * g.nlevels;
   for (int s = from; s <= to; s++) {
     switch (s) {
       case 0:
         for (int l = 1; l < g.nlevels; l++)
-          launch_pyramid_level(g, l, n, o->pyr.p, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], o->stream);
+          launch_pyramid_level(g, l, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], o->stream);
         break;
       case 1:
         if (o->fastV2) {
-          int rc = launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, n, o->stream);
+          int rc = launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, f0, n, o->stream);
           if (rc) return rc;
         } else {
-          launch_fast_score(g, n, o->pyr.p, o->score.p, o->stream);
+          launch_fast_score(g, n, pyr, score, o->stream);
         }
         break;
-      case 2: launch_cells(g, n, o->score.p, o->slots.p, o->cellCnt.p, o->err.p, o->stream); break;
-      case 3: launch_octree(g, n, o->slots.p, o->cellCnt.p, o->cand.p, o->staged.p, o->lvlCnt.p, o->err.p, o->stream); break;
-      case 4: launch_orient_desc(g, n, o->pyr.p, o->staged.p, o->lvlCnt.p, kps, desc, counts, cap, o->err.p, o->stream); break;
+      case 2: launch_cells(g, n, score, slots, cellCnt, o->err.p, o->stream); break;
+      case 3: launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, o->stream); break;
+      case 4:
+        launch_orient_desc(g, n, pyr, staged, lvlCnt, kps + (size_t)f0 * cap, desc + (size_t)f0 * cap * 32, counts + f0,
+                           cap, o->err.p, o->stream);
+        break;
     }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PGB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return PGB_OK;
+}
+
+// Host frames -> level 0, pipelined: chunks are copied on a dedicated copy stream while the compute stream works
+// on the previous chunk, so the PCIe transfer hides behind the kernels (or the other way round).
+int extract_host_pipelined(pgb_orb* o, const uint8_t* gray, int n_frames, int width, int height, size_t pitch,
+                           size_t frame_stride, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap) {
+  const OrbGeo& g = o->geo;
+  const int chunk = std::max(1, std::min(o->h2dChunk, n_frames));
+  // the copy stream may not overwrite level 0 before the previous call's kernels are done with it
+  PGB_CUDA(cudaEventRecord(o->evDone, o->stream));
+  PGB_CUDA(cudaStreamWaitEvent(o->copyStream, o->evDone, 0));
+  for (int f0 = 0, k = 0; f0 < n_frames; f0 += chunk, k++) {
+    const int n = std::min(chunk, n_frames - f0);
+    for (int f = f0; f < f0 + n; f++)
+      PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
+                                 gray + (size_t)f * frame_stride, pitch, width, height, cudaMemcpyHostToDevice,
+                                 o->copyStream));
+    cudaEvent_t ev = o->evChunk[k % kMaxChunkEvents];
+    PGB_CUDA(cudaEventRecord(ev, o->copyStream));
+    PGB_CUDA(cudaStreamWaitEvent(o->stream, ev, 0));
+    int rc = run_stages(o, 0, 4, kps, desc, counts, cap, f0, n);
+    if (rc) return rc;
+  }
   return PGB_OK;
 }
 
@@ -338,6 +380,12 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
     if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
     o->ownStream = true;
   }
+  if (cudaStreamCreateWithFlags(&o->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&o->evDone, cudaEventDisableTiming) != cudaSuccess)
+    return bail("cudaStreamCreate/cudaEventCreate failed");
+  for (int k = 0; k < kMaxChunkEvents; k++)
+    if (cudaEventCreateWithFlags(&o->evChunk[k], cudaEventDisableTiming) != cudaSuccess) return bail("cudaEventCreate failed");
+  if (const char* e = getenv("PGB_H2D_CHUNK")) o->h2dChunk = std::max(1, atoi(e));
   const OrbGeo& c = o->capGeo;
   const size_t B = (size_t)max_batch;
   o->outCap = 0;
@@ -362,6 +410,10 @@ void pgb_orb_destroy(pgb_orb* o) {
   if (!o) return;
   cudaSetDevice(o->device);
   if (o->stream) cudaStreamSynchronize(o->stream);
+  if (o->copyStream) { cudaStreamSynchronize(o->copyStream); cudaStreamDestroy(o->copyStream); }
+  if (o->evDone) cudaEventDestroy(o->evDone);
+  for (int k = 0; k < kMaxChunkEvents; k++)
+    if (o->evChunk[k]) cudaEventDestroy(o->evChunk[k]);
   if (o->ownStream && o->stream) cudaStreamDestroy(o->stream);
   delete o;
 }
@@ -410,16 +462,20 @@ int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames
   const OrbGeo& g = o->geo;
   o->curFrames = n_frames;
   const bool inDev = (is_device & PGB_IN_DEVICE) != 0, outDev = (is_device & PGB_OUT_DEVICE) != 0;
-  const cudaMemcpyKind kind = inDev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  for (int f = 0; f < n_frames; f++)
-    PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
-                               gray + (size_t)f * frame_stride, pitch, width, height, kind, o->stream));
-  if (outDev) {
-    // a caller capacity below pgb_orb_max_keypoints() is allowed; overflow raises the device flag (pgb_orb_check)
-    return run_stages(o, 0, 4, kps, desc, counts, cap);
+  pgb_keypoint* dk = outDev ? kps : o->kps.p;
+  uint8_t* dd = outDev ? desc : o->desc.p;
+  int* dc = outDev ? counts : o->counts.p;
+  const int dcap = outDev ? cap : o->outCap;  // a caller capacity below pgb_orb_max_keypoints() raises the device flag
+  if (inDev) {
+    for (int f = 0; f < n_frames; f++)
+      PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
+                                 gray + (size_t)f * frame_stride, pitch, width, height, cudaMemcpyDeviceToDevice,
+                                 o->stream));
+    rc = run_stages(o, 0, 4, dk, dd, dc, dcap, 0, n_frames);
+  } else {
+    rc = extract_host_pipelined(o, gray, n_frames, width, height, pitch, frame_stride, dk, dd, dc, dcap);
   }
-  rc = run_stages(o, 0, 4, o->kps.p, o->desc.p, o->counts.p, o->outCap);
-  if (rc) return rc;
+  if (rc || outDev) return rc;
   std::vector<int32_t> hc(n_frames);
   PGB_CUDA(cudaMemcpyAsync(hc.data(), o->counts.p, sizeof(int32_t) * n_frames, cudaMemcpyDeviceToHost, o->stream));
   rc = check_err_flag(o);  // synchronises
@@ -448,7 +504,7 @@ int pgb_orb_run_stage(pgb_orb* o, int which) {
   if (!o || which < 0 || which > 4) return fail(PGB_ERR_INVALID, "bad stage");
   if (o->curFrames <= 0) return fail(PGB_ERR_INVALID, "no frames resident: call pgb_orb_extract first");
   PGB_CUDA(cudaSetDevice(o->device));
-  return run_stages(o, which, which, o->kps.p, o->desc.p, o->counts.p, o->outCap);
+  return run_stages(o, which, which, o->kps.p, o->desc.p, o->counts.p, o->outCap, 0, o->curFrames);
 }
 
 static int copy_level_out(pgb_orb* o, const uint8_t* base, int frame, int level, uint8_t* out, int* w, int* h) {
