@@ -1,0 +1,274 @@
+// K2 v3: FAST-9 score kernel for sm_100a.  Same contract as v2 (fast_v2.cu): score map = (max arc threshold) where
+// the pixel is a FAST-9 corner at minThFAST inside [19, w-19) x [19, h-19), else 0.
+// Reference: cv::FAST(TYPE_9_16) as called at ORBextractor.cc:809,:814.
+//
+// The round-1 ncu capture of v2 (profiles/r01_fast_score_ncu_full.md) showed 82 % of the issue slots busy at 16 %
+// of DRAM bandwidth: the kernel is bound by instruction issue, and on this part LOP3/PRMT/SHF/VIMNMX/VABSDIFF4 share
+// one half-rate pipe while IMAD runs on the other (profiles/r01_pipe_probe.txt).  v3 therefore minimises
+// instructions on the ALU pipe:
+//   * one CTA per 256x64 tile; one elected thread issues a 3-D TMA load of the 72-word x 70-row halo box; every warp
+//     owns an 8-row band of a shared-memory score tile, zeroes it, and at the end stores it with ONE TMA store
+//     (clipped by the tensor map) -- no per-thread global stores, no bounds arithmetic on the output side.
+//   * phase 1 (prefilter), 8 px per lane per row, no quantisation: VABSDIFF4 gives |c - p| for 4 pixels per
+//     instruction; "(p0 or p8) and (p4 or p12) differ from the centre by more than t'" with t' = 2^k - 1 <= minTh is
+//     a bit test on the OR of two absolute differences.  It ignores polarity, which costs 3.6 % more candidates than
+//     the 6-bit signed test of v2 (measured on the synthetic frames) and saves the whole quantisation pass.
+//     The vertical differences |row r - row r+3| are shared between the two centre rows that use them.
+//     The 64 flags of a lane's 8x8 block stay in two registers; there are no per-row ballots or list stores.
+//   * expansion: one warp scan of the per-lane candidate counts, then every lane appends its own candidates to the
+//     warp's queue (11-bit codes) -- no per-candidate ballots, no CTA barrier, no cross-warp rebalancing.
+//   * phase 2 (exact score), one candidate per lane: ring pixel p becomes (p, -p) in the two s16 halves of a
+//     register with one IMAD (FMA pipe); the circular 9-wide sliding MAX is two rounds of VIMNMX3.S16x2, the MIN
+//     over the 16 arcs a 3-input tree; dark = v - min_arcs(max_arc p), bright = max_arcs(min_arc p) - v.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "orb_kernels.cuh"
+
+namespace pgb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int x, int y, int z, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(x),
+               "r"(y), "r"(z), "r"(smem_u32(src))
+               : "memory");
+}
+
+constexpr int kRowB = kF2InWords * 4;  // 288 bytes per staged input row
+
+// Exact bam of the pixel at byte pointer c inside the staged tile.
+__device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
+  const int v = c[0];
+  const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  uint32_t w[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const uint32_t p = c[dy[k] * kRowB + dx[k]];
+    asm("mul.lo.u32 %0, %1, 0xFFFF0001;" : "=r"(w[k]) : "r"(p));  // lo16 = p, hi16 = -p
+  }
+  uint32_t t3[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) t3[k] = __vimax3_s16x2(w[k], w[(k + 1) & 15], w[(k + 2) & 15]);
+  uint32_t m9[16];  // lo: max of p over the arc starting at k; hi: -(min of p over the arc)
+#pragma unroll
+  for (int k = 0; k < 16; k++) m9[k] = __vimax3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
+  uint32_t a = __vimin3_s16x2(m9[0], m9[1], m9[2]);
+  uint32_t b = __vimin3_s16x2(m9[3], m9[4], m9[5]);
+  uint32_t cc = __vimin3_s16x2(m9[6], m9[7], m9[8]);
+  uint32_t d = __vimin3_s16x2(m9[9], m9[10], m9[11]);
+  uint32_t e = __vimin3_s16x2(m9[12], m9[13], m9[14]);
+  a = __vimin3_s16x2(a, b, cc);
+  d = __vimin3_s16x2(d, e, m9[15]);
+  a = __vmins2(a, d);
+  const int lo = (int)(a & 0xffffu);  // min over arcs of (max p)
+  const int hi = (int)a >> 16;        // -(max over arcs of (min p))
+  return max(v - lo, -hi - v);
+}
+
+}  // namespace
+
+// dynamic shared memory layout (bytes):
+//   [0, kInStage)               input tile, kF2InRows x kF2InWords u32
+//   [kInStage, +16384)          score tile 64 x 256 u8 (8 bands of 2 KB, each the source of one TMA store)
+//   [.., +8 warps * 512 * 2)    per-warp candidate queues (u16 codes: lane<<6 | half<<5 | bit)
+//   [.., +16)                   the mbarrier
+constexpr int kF3InStage = (kF2InBytes + 127) / 128 * 128;
+constexpr int kF3QueueCap = 512;
+constexpr int kF3Smem = kF3InStage + kF2W * kF2H + 8 * kF3QueueCap * 2 + 16;
+
+template <int kOcc>
+__global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid_constant__ OrbGeo g,
+                                                                 const __grid_constant__ TmapPack tm,
+                                                                 const int4* __restrict__ tileTab, int frame0) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t* sIn = reinterpret_cast<const uint32_t*>(smem);
+  uint8_t* sScore = smem + kF3InStage;
+  uint16_t* sQueue = reinterpret_cast<uint16_t*>(sScore + kF2W * kF2H);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sQueue + 8 * kF3QueueCap);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y + frame0;
+  const int4 te = __ldg(&tileTab[blockIdx.x]);
+  const int level = te.x, x0 = te.y, y0 = te.z;
+  const LevelGeo& L = g.lv[level];
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, kF2InBytes);
+    tma_load_3d(smem, &tm.in[level], x0 / 4 - 4, y0 - 3, f, bar);
+  }
+  const int r0 = warp * 8;
+  const bool bandLive = y0 + r0 < L.h;  // else the whole band lies below the level (warp-uniform): nothing to store
+  uint8_t* band = sScore + r0 * kF2W;
+  {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) *reinterpret_cast<uint4*>(band + i * 512 + lane * 16) = z;
+  }
+
+  // validity masks of this lane's 8x8 block in the flag layout: byte b of a half-register holds pixels b (word A,
+  // bits 7,5,3,1 for rows 0..3 of the half) and 4+b (word B, bits 6,4,2,0)
+  const int gx = x0 + lane * 8;
+  uint32_t vmLo, vmHi;
+  {
+    const int a = min(max(kEdge - gx, 0), 8), b = min(max(L.w - kEdge - gx, 0), 8);
+    const uint32_t m8 = b > a ? ((1u << b) - 1u) & ~((1u << a) - 1u) : 0u;  // bit i = pixel i of the lane is testable
+    const uint32_t sa = ((m8 & 15u) * 0x00204081u) & 0x01010101u;          // bit 0 of byte b = pixel b
+    const uint32_t sb = ((m8 >> 4) * 0x00204081u) & 0x01010101u;           // bit 0 of byte b = pixel 4+b
+    const uint32_t xm = sa * 0xAAu + sb * 0x55u;
+    const int gy = y0 + r0;
+    uint32_t rl = 0, rh = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (gy + j >= kEdge && gy + j < L.h - kEdge) rl |= 0xC0C0C0C0u >> (2 * j);
+      if (gy + 4 + j >= kEdge && gy + 4 + j < L.h - kEdge) rh |= 0xC0C0C0C0u >> (2 * j);
+    }
+    vmLo = xm & rl;
+    vmHi = xm & rh;
+  }
+
+  __syncthreads();  // mbarrier initialised before anyone polls it
+  if (!bandLive) return;
+  while (!mbar_try_wait(bar, 0)) {
+  }
+
+  // ---------------- phase 1: 64 prefilter flags per lane
+  uint32_t lo = 0, hi = 0;
+  if (__any_sync(0xffffffffu, (vmLo | vmHi) != 0)) {
+    uint32_t ra[14], rb[14];
+    const uint32_t* col = sIn + r0 * kF2InWords + 4 + 2 * lane;
+#pragma unroll
+    for (int i = 0; i < 14; i++) {
+      const uint2 v = *reinterpret_cast<const uint2*>(col + i * kF2InWords);
+      ra[i] = v.x;
+      rb[i] = v.y;
+    }
+    const uint32_t M = g.absMask;  // bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c = j + 3;
+      const uint32_t* crow = col + c * kF2InWords;
+      const uint32_t wl = crow[-1], wr = crow[2];
+      const uint32_t cA = ra[c], cB = rb[c];
+      const uint32_t vA = __vabsdiffu4(ra[j], cA) | __vabsdiffu4(cA, ra[c + 3]);
+      const uint32_t vB = __vabsdiffu4(rb[j], cB) | __vabsdiffu4(cB, rb[c + 3]);
+      const uint32_t hA = __vabsdiffu4(cA, __byte_perm(wl, cA, 0x4321)) | __vabsdiffu4(cA, __byte_perm(cA, cB, 0x6543));
+      const uint32_t hB = __vabsdiffu4(cB, __byte_perm(cA, cB, 0x4321)) | __vabsdiffu4(cB, __byte_perm(cB, wr, 0x6543));
+      // msb of a byte: the absolute difference has a bit at or above k, i.e. exceeds 2^k - 1
+      const uint32_t fA = (((vA & M) + M) | vA) & (((hA & M) + M) | hA);
+      const uint32_t fB = (((vB & M) + M) | vB) & (((hB & M) + M) | hB);
+      const int s = 2 * (j & 3);
+      const uint32_t bits = ((fA >> s) & (0x80808080u >> s)) | ((fB >> (s + 1)) & (0x80808080u >> (s + 1)));
+      if (j < 4) lo |= bits; else hi |= bits;
+    }
+    lo &= vmLo;
+    hi &= vmHi;
+  }
+
+  // ---------------- expansion + phase 2
+  const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn);
+  uint16_t* q = sQueue + warp * kF3QueueCap;
+  const int cnt = __popc(lo) + __popc(hi);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  // Normally the band's candidates fit the queue in one pass; otherwise (noise images) one pass per row (<= 256).
+  const int nParts = total <= kF3QueueCap ? 1 : 8;
+  for (int part = 0; part < nParts; part++) {
+    uint32_t mlo = lo, mhi = hi;
+    int pos = incl - cnt, T = total;
+    if (nParts > 1) {
+      const uint32_t rm = 0xC0C0C0C0u >> (2 * (part & 3));
+      mlo = part < 4 ? (lo & rm) : 0u;
+      mhi = part < 4 ? 0u : (hi & rm);
+      const int c2 = __popc(mlo) + __popc(mhi);
+      int in2 = c2;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, in2, d);
+        if (lane >= d) in2 += t;
+      }
+      T = __shfl_sync(0xffffffffu, in2, 31);
+      pos = in2 - c2;
+    }
+    const uint32_t lcode = (uint32_t)lane << 6;
+    while (mlo) {
+      const int bit = __ffs(mlo) - 1;
+      mlo &= mlo - 1;
+      q[pos++] = (uint16_t)(lcode | bit);
+    }
+    while (mhi) {
+      const int bit = __ffs(mhi) - 1;
+      mhi &= mhi - 1;
+      q[pos++] = (uint16_t)(lcode | 32u | bit);
+    }
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+      const uint32_t e = q[i];
+      const uint32_t bit = e & 31u, t = ~e & 7u;
+      const int row = (int)((e >> 3) & 4u) + (int)(t >> 1);               // half*4 + row in half
+      const int x = (int)(e >> 6) * 8 + (int)(t & 1u) * 4 + (int)(bit >> 3);  // lane*8 + word*4 + byte
+      const int bam = fast_bam_minmax(sInB + (r0 + row + 3) * kRowB + 16 + x);
+      if (bam > g.minTh) band[row * kF2W + x] = (uint8_t)(bam - 1);
+    }
+    __syncwarp();
+  }
+
+  // ---------------- store the band
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(&tm.out[level], x0 / 4, y0 + r0, f, band);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+int launch_fast_score_v3(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
+                         cudaStream_t st) {
+  static bool init = false;
+  if (!init) {
+    PGB_CUDA(cudaFuncSetAttribute(k_fast_score_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
+    init = true;
+  }
+  if (g.totalTiles2 <= 0 || nFrames <= 0) return PGB_OK;
+  dim3 grid(g.totalTiles2, nFrames);
+  k_fast_score_v3<5><<<grid, kF2Threads, kF3Smem, st>>>(g, tm, tileTab, frame0);
+  PGB_LAUNCHED();
+  return PGB_OK;
+}
+
+}  // namespace pgb

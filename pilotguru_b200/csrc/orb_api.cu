@@ -65,6 +65,7 @@ struct pgb_orb {
   cudaEvent_t evDone = nullptr;
   cudaEvent_t evChunk[16] = {};
   int h2dChunk = 8;  // frames per H2D/compute pipeline chunk (PGB_H2D_CHUNK)
+  bool fastV3 = true;  // PGB_FAST_IMPL=v2: previous TMA kernel (A/B measurements)
   bool fastV2 = true;  // PGB_FAST_IMPL=v1 selects the first-generation kernel (kept for A/B measurements)
   int numSMs = 148;
 };
@@ -79,6 +80,11 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
   g->iniTh = o->iniTh;
   g->minTh = o->minTh;
   g->qTh = o->minTh >= 2 ? (o->minTh + 1) / 4 : 0;
+  {
+    int k = 0;
+    while (k < 7 && (2 << k) - 1 <= o->minTh) k++;  // 2^k - 1 <= minTh < 2^(k+1) - 1 (k = 0 when minTh < 1)
+    g->absMask = (0x7fu & ~((1u << k) - 1u)) * 0x01010101u;
+  }
   unsigned long long off = 0, slotOff = 0, candOff = 0;
   int cellBase = 0, tileBase = 0, tile2Base = 0, kpBase = 0, maxNode = 1;
   for (int l = 0; l < o->nlevels; l++) {
@@ -204,7 +210,7 @@ int build_tmaps(pgb_orb* o) {
     const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.frameStride};
     const cuuint32_t es[3] = {1, 1, 1};
     const cuuint32_t boxIn[3] = {(cuuint32_t)kF2InWords, (cuuint32_t)kF2InRows, 1};
-    const cuuint32_t boxOut[3] = {(cuuint32_t)(kF2W / 4), (cuuint32_t)kF2H, 1};
+    const cuuint32_t boxOut[3] = {(cuuint32_t)(kF2W / 4), 8, 1};  // one warp's band
     CUresult r = encode(&o->tmaps.in[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->pyr.p + L.off, dims, strides, boxIn, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -275,7 +281,8 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         break;
       case 1:
         if (o->fastV2) {
-          int rc = launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, f0, n, o->stream);
+          int rc = o->fastV3 ? launch_fast_score_v3(g, o->tmaps, o->tileTab.p, f0, n, o->stream)
+                             : launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, f0, n, o->stream);
           if (rc) return rc;
         } else {
           launch_fast_score(g, n, pyr, score, o->stream);
@@ -372,6 +379,7 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
   {
     const char* impl = getenv("PGB_FAST_IMPL");
     o->fastV2 = !(impl && strcmp(impl, "v1") == 0);
+    o->fastV3 = !(impl && strcmp(impl, "v2") == 0);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) o->numSMs = prop.multiProcessorCount;
   }

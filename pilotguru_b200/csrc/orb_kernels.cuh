@@ -51,6 +51,7 @@ struct LevelGeo {
 
 struct OrbGeo {
   int nlevels, iniTh, minTh, qTh;
+  unsigned absMask;  // FAST v3 prefilter: bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
   int totalCells, totalTiles, totalTiles2, kpCapInternal, maxNodeCap;
   unsigned long long frameStride, slotsPerFrame, candPerFrame;
   LevelGeo lv[kMaxLevels];
@@ -76,6 +77,8 @@ void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr,
 void launch_fast_score(const OrbGeo& g, int nFrames, const uint8_t* pyr, uint8_t* score, cudaStream_t st);
 int launch_fast_score_v2(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, uint8_t* score, int frame0,
                          int nFrames, cudaStream_t st);
+int launch_fast_score_v3(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
+                         cudaStream_t st);
 void launch_cells(const OrbGeo& g, int nFrames, const uint8_t* score, uint32_t* slots, int* cellCnt, int* err,
                   cudaStream_t st);
 void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,
