@@ -15,8 +15,10 @@
 //     the 6-bit signed test of v2 (measured on the synthetic frames) and saves the whole quantisation pass.
 //     The vertical differences |row r - row r+3| are shared between the two centre rows that use them.
 //     The 64 flags of a lane's 8x8 block stay in two registers; there are no per-row ballots or list stores.
-//   * expansion: one warp scan of the per-lane candidate counts, then every lane appends its own candidates to the
-//     warp's queue (11-bit codes) -- no per-candidate ballots, no CTA barrier, no cross-warp rebalancing.
+//   * expansion: a 4x4 byte transpose inside lane quads evens out the blobs, one warp scan of the per-lane counts,
+//     then every lane appends the isolated flag bits of its candidates to the warp's queue (m & -m: no FLO/BREV in
+//     the divergent loop; the bit index is recovered once per scoring round) -- no per-candidate ballots, no CTA
+//     barrier, no cross-warp rebalancing.
 //   * phase 2 (exact score), one candidate per lane: ring pixel p becomes (p, -p) in the two s16 halves of a
 //     register with one IMAD (FMA pipe); the circular 9-wide sliding MAX is two rounds of VIMNMX3.S16x2, the MIN
 //     over the 16 arcs a 3-input tree; dark = v - min_arcs(max_arc p), bright = max_arcs(min_arc p) - v.
@@ -61,9 +63,17 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int x, int y
                : "memory");
 }
 
+__device__ __forceinline__ uint32_t mad1(uint32_t a, uint32_t one, uint32_t c) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
+  return d;
+}
+
 constexpr int kRowB = kF2InWords * 4;  // 288 bytes per staged input row
 
 // Exact bam of the pixel at byte pointer c inside the staged tile.
+// (Tried: encoding p as fp16-compatible halves so that part of the min/max tree runs as HMNMX2 on the FMA pipes;
+// ptxas fuses the pairs into 3-input VHMNMX on the ALU pipe again, and splitting them costs issue slots -- no gain.)
 __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
   const int v = c[0];
   const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
@@ -98,11 +108,12 @@ __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
 // dynamic shared memory layout (bytes):
 //   [0, kInStage)               input tile, kF2InRows x kF2InWords u32
 //   [kInStage, +16384)          score tile 64 x 256 u8 (8 bands of 2 KB, each the source of one TMA store)
-//   [.., +8 warps * 512 * 2)    per-warp candidate queues (u16 codes: lane<<6 | half<<5 | bit)
+//   [.., +8 warps * 384 * 4)    per-warp candidate queues: one-hot flag bit of the candidate in its register
+//   [.., +8 warps * 384)        ... and the producer's part of the candidate position
 //   [.., +16)                   the mbarrier
 constexpr int kF3InStage = (kF2InBytes + 127) / 128 * 128;
-constexpr int kF3QueueCap = 512;
-constexpr int kF3Smem = kF3InStage + kF2W * kF2H + 8 * kF3QueueCap * 2 + 16;
+constexpr int kF3QueueCap = 384;
+constexpr int kF3Smem = kF3InStage + kF2W * kF2H + 8 * kF3QueueCap * 5 + 16;
 
 template <int kOcc>
 __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid_constant__ OrbGeo g,
@@ -111,8 +122,9 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t* sIn = reinterpret_cast<const uint32_t*>(smem);
   uint8_t* sScore = smem + kF3InStage;
-  uint16_t* sQueue = reinterpret_cast<uint16_t*>(sScore + kF2W * kF2H);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sQueue + 8 * kF3QueueCap);
+  uint32_t* sQueue = reinterpret_cast<uint32_t*>(sScore + kF2W * kF2H);
+  uint8_t* sQCode = reinterpret_cast<uint8_t*>(sQueue + 8 * kF3QueueCap);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sQCode + 8 * kF3QueueCap);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y + frame0;
@@ -136,10 +148,10 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
   }
 
   // validity masks of this lane's 8x8 block in the flag layout: byte b of a half-register holds pixels b (word A,
-  // bits 7,5,3,1 for rows 0..3 of the half) and 4+b (word B, bits 6,4,2,0)
+  // bits 7,5,3,1 for rows 0..3 of the half) and 4+b (word B, bits 6,4,2,0).  Interior bands (warp-uniform) skip it.
   const int gx = x0 + lane * 8;
-  uint32_t vmLo, vmHi;
-  {
+  uint32_t vmLo = 0xffffffffu, vmHi = 0xffffffffu;
+  if (!(x0 >= kEdge && x0 + kF2W <= L.w - kEdge && y0 + r0 >= kEdge && y0 + r0 + 8 <= L.h - kEdge)) {
     const int a = min(max(kEdge - gx, 0), 8), b = min(max(L.w - kEdge - gx, 0), 8);
     const uint32_t m8 = b > a ? ((1u << b) - 1u) & ~((1u << a) - 1u) : 0u;  // bit i = pixel i of the lane is testable
     const uint32_t sa = ((m8 & 15u) * 0x00204081u) & 0x01010101u;          // bit 0 of byte b = pixel b
@@ -172,7 +184,8 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
       ra[i] = v.x;
       rb[i] = v.y;
     }
-    const uint32_t M = g.absMask;  // bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
+    const uint32_t one = g.one;
+    const uint32_t M = g.absMask;  // K = 0x80 - 2^k in every byte, 2^k - 1 = largest such value <= minTh
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int c = j + 3;
@@ -184,8 +197,11 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
       const uint32_t hA = __vabsdiffu4(cA, __byte_perm(wl, cA, 0x4321)) | __vabsdiffu4(cA, __byte_perm(cA, cB, 0x6543));
       const uint32_t hB = __vabsdiffu4(cB, __byte_perm(cA, cB, 0x4321)) | __vabsdiffu4(cB, __byte_perm(cB, wr, 0x6543));
       // msb of a byte: the absolute difference has a bit at or above k, i.e. exceeds 2^k - 1
-      const uint32_t fA = (((vA & M) + M) | vA) & (((hA & M) + M) | hA);
-      const uint32_t fB = (((vB & M) + M) | vB) & (((hB & M) + M) | hB);
+      // (the additions are issued as IMAD x*1+M: the FMA pipe idles while LOP3/PRMT/VABSDIFF4 saturate the ALU pipe)
+      // x + K sets the msb for x in [2^k, 0x7f]; "| x" covers x >= 0x80; a carry out of a byte >= 0x88 can only turn a
+      // neighbour's flag ON (over-accepting is harmless here), never off.
+      const uint32_t fA = (mad1(vA, one, M) | vA) & (mad1(hA, one, M) | hA);
+      const uint32_t fB = (mad1(vB, one, M) | vB) & (mad1(hB, one, M) | hB);
       const int s = 2 * (j & 3);
       const uint32_t bits = ((fA >> s) & (0x80808080u >> s)) | ((fB >> (s + 1)) & (0x80808080u >> (s + 1)));
       if (j < 4) lo |= bits; else hi |= bits;
@@ -195,8 +211,22 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
   }
 
   // ---------------- expansion + phase 2
+  // Candidates come in blobs, so a few lanes hold most of a band's flags.  A 4x4 byte transpose inside every lane
+  // quad (2 SHFL + 2 PRMT per register) hands lane i of the quad column i of all four lanes, which evens the
+  // per-lane counts before the (divergent) append loops.  Byte j of a transposed register = source lane 4q + j.
+  {
+    const uint32_t sel1 = (lane & 1) ? 0x3715u : 0x6240u, sel2 = (lane & 2) ? 0x3276u : 0x5410u;
+    uint32_t x = __shfl_xor_sync(0xffffffffu, lo, 1), y = __shfl_xor_sync(0xffffffffu, hi, 1);
+    lo = __byte_perm(lo, x, sel1);
+    hi = __byte_perm(hi, y, sel1);
+    x = __shfl_xor_sync(0xffffffffu, lo, 2);
+    y = __shfl_xor_sync(0xffffffffu, hi, 2);
+    lo = __byte_perm(lo, x, sel2);
+    hi = __byte_perm(hi, y, sel2);
+  }
   const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn);
-  uint16_t* q = sQueue + warp * kF3QueueCap;
+  uint32_t* q = sQueue + warp * kF3QueueCap;                 // one-hot flag of the candidate inside its register
+  uint8_t* qc = sQCode + warp * kF3QueueCap;                 // (lane & 28) * 8 + (lane & 3) + 4 * half
   const int cnt = __popc(lo) + __popc(hi);
   int incl = cnt;
 #pragma unroll
@@ -224,23 +254,27 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
       T = __shfl_sync(0xffffffffu, in2, 31);
       pos = in2 - c2;
     }
-    const uint32_t lcode = (uint32_t)lane << 6;
+    const uint8_t pcode = (uint8_t)((lane & 28) * 8 + (lane & 3));  // x of (source-lane quad, column); bit 2 = half
+    uint32_t* qp = q + pos;
+    uint8_t* qcp = qc + pos;
     while (mlo) {
-      const int bit = __ffs(mlo) - 1;
-      mlo &= mlo - 1;
-      q[pos++] = (uint16_t)(lcode | bit);
+      const uint32_t low = mlo & (0u - mlo);
+      mlo ^= low;
+      *qp++ = low;
+      *qcp++ = pcode;
     }
     while (mhi) {
-      const int bit = __ffs(mhi) - 1;
-      mhi &= mhi - 1;
-      q[pos++] = (uint16_t)(lcode | 32u | bit);
+      const uint32_t low = mhi & (0u - mhi);
+      mhi ^= low;
+      *qp++ = low;
+      *qcp++ = (uint8_t)(pcode | 4);
     }
     __syncwarp();
     for (int i = lane; i < T; i += 32) {
-      const uint32_t e = q[i];
-      const uint32_t bit = e & 31u, t = ~e & 7u;
-      const int row = (int)((e >> 3) & 4u) + (int)(t >> 1);               // half*4 + row in half
-      const int x = (int)(e >> 6) * 8 + (int)(t & 1u) * 4 + (int)(bit >> 3);  // lane*8 + word*4 + byte
+      const uint32_t low = q[i], c = qc[i];
+      const uint32_t bit = 31u - (uint32_t)__clz(low), u = bit ^ 7u;  // u & 7 = 2 * (row in half) + word
+      const int row = (int)(c & 4u) + (int)((u >> 1) & 3u);
+      const int x = (int)((c & 0xE3u) + (bit & 0x18u) + ((u & 1u) << 2));  // (lane quad)*32 + (source lane)*8 + word*4 + byte
       const int bam = fast_bam_minmax(sInB + (r0 + row + 3) * kRowB + 16 + x);
       if (bam > g.minTh) band[row * kF2W + x] = (uint8_t)(bam - 1);
     }
@@ -261,12 +295,12 @@ int launch_fast_score_v3(const OrbGeo& g, const TmapPack& tm, const int4* tileTa
                          cudaStream_t st) {
   static bool init = false;
   if (!init) {
-    PGB_CUDA(cudaFuncSetAttribute(k_fast_score_v3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
+    PGB_CUDA(cudaFuncSetAttribute(k_fast_score_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
     init = true;
   }
   if (g.totalTiles2 <= 0 || nFrames <= 0) return PGB_OK;
   dim3 grid(g.totalTiles2, nFrames);
-  k_fast_score_v3<5><<<grid, kF2Threads, kF3Smem, st>>>(g, tm, tileTab, frame0);
+  k_fast_score_v3<4><<<grid, kF2Threads, kF3Smem, st>>>(g, tm, tileTab, frame0);
   PGB_LAUNCHED();
   return PGB_OK;
 }

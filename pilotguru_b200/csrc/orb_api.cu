@@ -83,6 +83,7 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
   {
     int k = 0;
     while (k < 7 && (2 << k) - 1 <= o->minTh) k++;  // 2^k - 1 <= minTh < 2^(k+1) - 1 (k = 0 when minTh < 1)
+    g->one = 1u;
     g->absMask = (0x7fu & ~((1u << k) - 1u)) * 0x01010101u;
   }
   unsigned long long off = 0, slotOff = 0, candOff = 0;

@@ -51,6 +51,7 @@ struct LevelGeo {
 
 struct OrbGeo {
   int nlevels, iniTh, minTh, qTh;
+  unsigned one;      // = 1, opaque to the compiler (FAST v3 issues its additions as IMAD on the idle FMA pipe)
   unsigned absMask;  // FAST v3 prefilter: bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
   int totalCells, totalTiles, totalTiles2, kpCapInternal, maxNodeCap;
   unsigned long long frameStride, slotsPerFrame, candPerFrame;

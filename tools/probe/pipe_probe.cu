@@ -26,6 +26,21 @@ __device__ __forceinline__ void step(unsigned (&a)[kAcc], unsigned b, unsigned c
     if (OP == 11) { a[i] = __vimin3_s16x2(a[i], b, c); i++; a[i] = __vabsdiffu4(a[i], b); }
     if (OP == 12) a[i] = __vimax3_u16x2(a[i], b, c);
     if (OP == 13) a[i] = __popc(a[i]) + b;
+    if (OP == 15) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+    if (OP == 16) { asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b)); i++; asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+    if (OP == 17) { asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b)); i++; asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+    if (OP == 18) { asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b)); i++; a[i] = __vimin3_s16x2(a[i], b, c); }
+    if (OP == 19) { float f = __uint_as_float(a[i]); asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__uint_as_float(b)), "f"(__uint_as_float(c))); a[i] = __float_as_uint(f); }
+    if (OP == 20) { float f = __uint_as_float(a[i]); asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__uint_as_float(b)), "f"(__uint_as_float(c))); a[i] = __float_as_uint(f); i++; asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+    if (OP == 21) a[i] = a[i] + a[(i + 1) % kAcc] + b;
+    if (OP == 22) a[i] = __funnelshift_r(a[i], a[(i + 1) % kAcc], 3);
+    if (OP == 23) a[i] = __brev(a[i]) ^ b;
+    if (OP == 24) a[i] = __ffs(a[i]) + b;
+    if (OP == 25) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1);
+    if (OP == 26) { a[i] = a[i] + a[(i + 1) % kAcc] + b; i++; asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+    if (OP == 27) { a[i] = a[i] + a[(i + 1) % kAcc] + b; i++; asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); }
+    if (OP == 28) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+    if (OP == 29) asm volatile("{.reg .b32 t; add.u32 t, %0, %1; max.s32 %0, t, %2;}" : "+r"(a[i]) : "r"(b), "r"(c));
     if (OP == 14) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); i++; asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); }
   }
 }
@@ -86,5 +101,20 @@ int main() {
   run<9>("VIMNMX3 + LOP3", out, cyc, sms);
   run<10>("VABSDIFF4 + LOP3", out, cyc, sms);
   run<11>("VIMNMX3 + VABSDIFF4", out, cyc, sms);
+  run<15>("HMNMX2", out, cyc, sms);
+  run<16>("HMNMX2 + LOP3", out, cyc, sms);
+  run<17>("HMNMX2 + IMAD", out, cyc, sms);
+  run<18>("HMNMX2 + VIMNMX3", out, cyc, sms);
+  run<19>("FMNMX3", out, cyc, sms);
+  run<20>("FMNMX3 + LOP3", out, cyc, sms);
+  run<21>("IADD3 (a+a'+b)", out, cyc, sms);
+  run<26>("IADD3 + IMAD", out, cyc, sms);
+  run<27>("IADD3 + LOP3", out, cyc, sms);
+  run<22>("SHF (funnel)", out, cyc, sms);
+  run<23>("BREV+LOP3", out, cyc, sms);
+  run<24>("FFS(BREV+FLO)+IADD", out, cyc, sms);
+  run<25>("SHFL.BFLY", out, cyc, sms);
+  run<28>("IMAD.HI", out, cyc, sms);
+  run<29>("VIADDMNMX", out, cyc, sms);
   return 0;
 }
