@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 
 W, H, NFEAT = 1920, 1080, 1000
 FAST_ALGO_BYTES_PER_FRAME = 2 * 6_419_321  # 8-level 1080p pyramid read once + u8 score map written once
+# dram__bytes_read.sum + dram__bytes_write.sum of k_fast_score per frame from the committed `ncu --set full` capture
+# (profiles/r01_fast_score_v3_ncu_full.md: 104.5 MB read + 64.2 MB written over a 16-frame launch; part of the score
+# map is still dirty in L2 when the kernel ends, hence below the algorithmic bytes)
+FAST_NCU_TRAFFIC_BYTES_PER_FRAME = (104_522_496 + 64_215_040) / 16
 STAGES = ["pyramid", "fast_score", "cell_nms", "octree", "orient_desc"]
 
 
@@ -107,6 +111,34 @@ def cpu_run(n_frames, threads):
     return sec, nk, nm
 
 
+def calibration_leg(device, seconds, hz):
+    """BASELINE configs[3]: fit_motion's velocity calibration over `seconds` of `hz` IMU + 1 Hz GPS (all sliding
+    windows, 500 L-BFGS iterations each) through the C-ABI, host arrays in, host arrays out (secondary metric)."""
+    import torch
+    from pilotguru_b200 import calibration as cal, synth
+    d = synth.imu_gps(seconds, hz)
+    t0 = time.time()
+    imu = cal.ImuSeries(d["gyro"], d["gyro_t"], d["acc"], d["acc_t"], device=device)
+    t_up = time.time() - t0
+    cal.fit_windows(imu, d["gps_v"][:200], d["gps_t"][:200])                # warm-up (module load, allocations)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(3):
+        t0 = time.time()
+        r = cal.fit_windows(imu, d["gps_v"], d["gps_t"])
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    n_win = len(r["iters"])
+    covered = int((r["speed_cnt"] > 0).sum())
+    per_window = min(40, len(d["gps_v"])) - 1
+    intervals = n_win * per_window * hz                                    # IMU intervals swept per evaluation pass
+    imu.close()
+    return {"workload": f"fit_motion {seconds:.0f} s @ {hz:.0f} Hz IMU + 1 Hz GPS, window 40 / step 5, 500 L-BFGS iterations",
+            "windows": n_win, "windows_per_s": n_win / best, "seconds_per_fit": best, "upload_s": t_up,
+            "imu_events_covered": covered, "lbfgs_iterations_total": int(np.abs(r["iters"]).sum()),
+            "imu_intervals_per_window_pass": intervals, "dtype": "f64"}
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -140,6 +172,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-calibration", action="store_true", help="skip the fit_motion (BASELINE configs[3]) leg")
+    ap.add_argument("--calib-seconds", type=float, default=3600.0)
+    ap.add_argument("--calib-hz", type=float, default=500.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -280,17 +315,20 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": FAST_NCU_TRAFFIC_BYTES_PER_FRAME * B, "peak_source": peak_src,
+                             "traffic_source": "ncu --set full capture, profiles/r01_fast_score_v3_ncu_full.md, scaled to this launch",
                              "algorithmic_bytes_per_launch": FAST_ALGO_BYTES_PER_FRAME * B,
                              "us_per_launch": stage_us["fast_score"] * B},
                 "stage_us_per_frame": stage_us,
                 "keypoints_per_frame": float(cnt_dev[1:].mean()), "matches_per_frame": float(nm_dev.mean())}
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            n = max(16, min(4 * cores, 256))
+            n = max(64, min(16 * cores, 512))                              # ~15-30 s of CPU work (oracle: ~14 frames/s/core)
             sec, _, _ = cpu_run(n, cores)
             line["cpu_baseline"] = {"value": n / sec, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} synthetic 1080p frames, extract+match, oracle on {cores} host threads ({sec:.1f} s)"}
+                                    "sample": f"{n} synthetic 1080p frames, extract+match, oracle on {cores} host threads ({sec:.1f} s wall)"}
+        if not args.no_calibration and world == 1:
+            line["calibration"] = calibration_leg(local, args.calib_seconds, args.calib_hz)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

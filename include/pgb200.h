@@ -170,6 +170,25 @@ int pgb_imu_fit_windows(pgb_imu*, const double* gps_v, const int64_t* gps_t, int
                         int shift_step, int max_iterations, double epsilon, int first_window, int n_windows,
                         double* speed_sum, int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out);
 int pgb_imu_num_windows(int n_gps, int shift_step);
+/* Same, plus the forward-axis evidence of fit_motion.cc:172-173,223-248: the Kahan sum (include/math/math.hpp:8-27) of
+ * the device-frame velocities conj(orientation)*velocity over every trajectory point with |v| >= fwd_min_velocity of
+ * every window whose largest rotation acos(min |q.w|) reaches fwd_min_rotation_rad.  fwd_sum_xyz[3] is the raw sum
+ * (the caller projects out the vertical axis and normalises, fit_motion.cc:281-283); shards add. */
+int pgb_imu_fit_windows_fwd(pgb_imu*, const double* gps_v, const int64_t* gps_t, int n_gps, int batch_size,
+                            int shift_step, int max_iterations, double epsilon, int first_window, int n_windows,
+                            double* speed_sum, int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out,
+                            double fwd_min_velocity, double fwd_min_rotation_rad, double* fwd_sum_xyz,
+                            int32_t* fwd_windows_used);
+
+/* GetPrincipalRotationAxes (src/calibration/rotation.cc:16-57): integrates the gyro over intervals of at least
+ * integration_interval_usec (device), then cv::PCA of the quaternion vector parts: axes_out = 3x3 row-major
+ * eigenvectors, rows by descending eigenvalue, signs as OpenCV's Jacobi solver leaves them.  Fails with
+ * PGB_ERR_INVALID when fewer than 3 intervals result (CHECK_GE, rotation.cc:46). */
+int pgb_principal_rotation_axes(int device, const double* gyro_xyz, const int64_t* gyro_t, size_t n,
+                                int64_t integration_interval_usec, double axes_out[9], int64_t* n_intervals);
+/* GetAngularVelocitiesAroundAxisDirect (rotation.cc:103-119): out[i] = gyro[i] . axis / |axis|; |axis| must be
+ * within 1e-2 of 1 (CHECK_GT/CHECK_LT). */
+int pgb_angular_velocities_around_axis(int device, const double* gyro_xyz, size_t n, const double axis[3], double* out);
 
 /* SmoothTimeSeries (src/slam/smoothing.cc:56-98): host arrays in/out, device compute. */
 int pgb_smooth_time_series(int device, const double* values, const double* times, int64_t n,

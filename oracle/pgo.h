@@ -65,6 +65,14 @@ int64_t pgo_fit_motion(const double* gps_v, const int64_t* gps_t, int n_gps, con
                        int shift_step, int max_iters, double sigma, int mode, int64_t cap, int64_t* out_idx,
                        int64_t* out_t_usec, double* out_avg, double* out_smoothed, double* x_out, int32_t* iters_out,
                        double* fx_out, int64_t* n_evals_total);
+int pgo_forward_axis_sum(const double* gps_v, const int64_t* gps_t, int n_gps, const double* gyro_xyz,
+                         const int64_t* gyro_t, int64_t n_gyro, const double* acc_xyz, const int64_t* acc_t,
+                         int64_t n_acc, int batch_size, int shift_step, const double* x_all, int mode, double min_vel,
+                         double min_rot, double* sum_out, int32_t* windows_used);
+void pgo_pca3(const double* rows, int64_t n, double* eigvec9, double* eigval3, double* mean3);
+int64_t pgo_principal_rotation_axes(const double* gyro_xyz, const int64_t* gyro_t, int64_t n, int64_t interval_usec,
+                                    double* axes9, double* rows_out, int64_t cap);
+void pgo_angular_velocities_around_axis(const double* gyro_xyz, int64_t n, const double* axis, double* out);
 double pgo_bench_extract_match(const uint8_t* frames, int n, int w, int h, const float* flow_xy, int nfeatures,
                                float scale, int nlevels, int iniTh, int minTh, float th, int nthreads,
                                int64_t* total_kps, int64_t* total_matches);

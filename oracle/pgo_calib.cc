@@ -349,12 +349,13 @@ std::map<size_t, TrajPoint> integrate_core(pgo_calib* c, const double* x) {
       const V3 loc = add(ss.pa, mv(ss.pR, h));
       const V3 v = add(add(Vr, mv(wr.RQ, loc)), scale(g, (double)ss.tau * 1e-6));
       TrajPoint tp;
-      tp.q = {1, 0, 0, 0};  // orientation is not part of the core K10 output (speed only)
+      const Q4 qq = pgbimu::qmul(wr.Q, ss.l);  // orientation after the step, as k_imu_speeds forms it
+      tp.q = {qq.w, qq.x, qq.y, qq.z};
       tp.v = {v.x, v.y, v.z};
       tp.dur = st.dur_usec;
       auto it = result.find(iv.interp_idx);
       if (it == result.end()) result.insert({iv.interp_idx, tp});
-      else { it->second.v = tp.v; it->second.dur += tp.dur; }
+      else { it->second.q = tp.q; it->second.v = tp.v; it->second.dur += tp.dur; }
     }
   }
   return result;
@@ -571,6 +572,142 @@ int64_t pgo_fit_motion(const double* gps_v, const int64_t* gps_t, int n_gps, con
   pgo_calib_destroy(all);
   if (k > 0) pgo_smooth_time_series(avg.data(), ts_sec.data(), k, ts_sec.data(), k, sigma, out_smoothed);
   return k;
+}
+
+// total_velocity_local of fit_motion.cc:172-173,223-248 for given per-window solutions x_all[w][9]: Kahan sum
+// (include/math/math.hpp:8-27) of conj(orientation)*velocity over the trajectory points with |v| >= min_vel of the
+// windows whose largest rotation acos(min |q.w|) reaches min_rot.  mode as in pgo_fit_motion.
+int pgo_forward_axis_sum(const double* gps_v, const int64_t* gps_t, int n_gps, const double* gyro_xyz,
+                         const int64_t* gyro_t, int64_t n_gyro, const double* acc_xyz, const int64_t* acc_t,
+                         int64_t n_acc, int batch_size, int shift_step, const double* x_all, int mode, double min_vel,
+                         double min_rot, double* sum_out, int32_t* windows_used) {
+  Vec3 sum{0, 0, 0}, rem{0, 0, 0};
+  int w = 0, used = 0;
+  for (size_t start = 0; start < (size_t)n_gps; start += shift_step, ++w) {
+    const size_t end = std::min(start + (size_t)batch_size, (size_t)n_gps);
+    pgo_calib* c = pgo_calib_create(gps_v + start, gps_t + start, (int)(end - start), gyro_xyz, gyro_t, n_gyro, acc_xyz,
+                                    acc_t, n_acc);
+    if (!c) return -2;
+    const auto traj = mode == 0 ? integrate_literal(c, x_all + 9 * w) : integrate_core(c, x_all + 9 * w);
+    pgo_calib_destroy(c);
+    double min_cos = 1.0;
+    for (const auto& p : traj) min_cos = std::min(min_cos, std::abs(p.second.q.w));
+    if (!(std::acos(min_cos) >= min_rot)) continue;
+    used++;
+    for (const auto& p : traj) {
+      if (norm(p.second.v) >= min_vel) {
+        const Quat qc{p.second.q.w, -p.second.q.x, -p.second.q.y, -p.second.q.z};
+        const Vec3 v = transform_vector(qc, p.second.v);
+        const Vec3 prop = v + rem;                       // KahanSum<Eigen::Vector3d>::add
+        const Vec3 upd = sum + prop;
+        const Vec3 act{upd.x - sum.x, upd.y - sum.y, upd.z - sum.z};
+        rem = Vec3{prop.x - act.x, prop.y - act.y, prop.z - act.z};
+        sum = upd;
+      }
+    }
+  }
+  sum_out[0] = sum.x; sum_out[1] = sum.y; sum_out[2] = sum.z;
+  if (windows_used) *windows_used = used;
+  return 0;
+}
+
+// cv::eigen for a symmetric 3x3 (OpenCV core/src/lapack.cpp JacobiImpl_, un-vendored; restated from the published
+// algorithm): rows of V = eigenvectors by descending eigenvalue, signs as the sweep leaves them.
+static void jacobi_sym(double* A, double* W, double* V, int n) {
+  const double eps = std::numeric_limits<double>::epsilon();
+  std::vector<int> indR(n, 0), indC(n, 0);
+  for (int i = 0; i < n * n; i++) V[i] = 0.0;
+  for (int i = 0; i < n; i++) V[i * n + i] = 1.0;
+  auto scan_row = [&](int k) { int m = k + 1; double mv = std::abs(A[n * k + m]); for (int i = k + 2; i < n; i++) { double v = std::abs(A[n * k + i]); if (mv < v) { mv = v; m = i; } } return m; };
+  auto scan_col = [&](int k) { int m = 0; double mv = std::abs(A[k]); for (int i = 1; i < k; i++) { double v = std::abs(A[n * i + k]); if (mv < v) { mv = v; m = i; } } return m; };
+  for (int k = 0; k < n; k++) {
+    W[k] = A[(n + 1) * k];
+    if (k < n - 1) indR[k] = scan_row(k);
+    if (k > 0) indC[k] = scan_col(k);
+  }
+  if (n > 1)
+    for (int iters = 0; iters < n * n * 30; iters++) {
+      int k = 0;
+      double mv = std::abs(A[indR[0]]);
+      for (int i = 1; i < n - 1; i++) { double v = std::abs(A[n * i + indR[i]]); if (mv < v) { mv = v; k = i; } }
+      int l = indR[k];
+      for (int i = 1; i < n; i++) { double v = std::abs(A[n * indC[i] + i]); if (mv < v) { mv = v; k = indC[i]; l = i; } }
+      const double p = A[n * k + l];
+      if (std::abs(p) <= eps) break;
+      const double y = (W[l] - W[k]) * 0.5;
+      double t = std::abs(y) + std::hypot(p, y);
+      double s = std::hypot(p, t);
+      const double c = t / s;
+      s = p / s; t = (p / t) * p;
+      if (y < 0) { s = -s; t = -t; }
+      A[n * k + l] = 0;
+      W[k] -= t; W[l] += t;
+      auto rot = [&](double& v0, double& v1) { const double a0 = v0, b0 = v1; v0 = a0 * c - b0 * s; v1 = a0 * s + b0 * c; };
+      for (int i = 0; i < k; i++) rot(A[n * i + k], A[n * i + l]);
+      for (int i = k + 1; i < l; i++) rot(A[n * k + i], A[n * i + l]);
+      for (int i = l + 1; i < n; i++) rot(A[n * k + i], A[n * l + i]);
+      for (int i = 0; i < n; i++) rot(V[n * k + i], V[n * l + i]);
+      for (int j = 0; j < 2; j++) {
+        const int idx = j == 0 ? k : l;
+        if (idx < n - 1) indR[idx] = scan_row(idx);
+        if (idx > 0) indC[idx] = scan_col(idx);
+      }
+    }
+  for (int k = 0; k < n - 1; k++) {
+    int m = k;
+    for (int i = k + 1; i < n; i++) if (W[m] < W[i]) m = i;
+    if (k != m) { std::swap(W[m], W[k]); for (int i = 0; i < n; i++) std::swap(V[n * m + i], V[n * k + i]); }
+  }
+}
+
+// cv::PCA(data, noArray(), CV_PCA_DATA_AS_ROW) for an n x 3 matrix: eigenvectors (3x3 row-major) and eigenvalues.
+void pgo_pca3(const double* rows, int64_t n, double* eigvec9, double* eigval3, double* mean3) {
+  double mean[3] = {0, 0, 0};
+  for (int64_t i = 0; i < n; i++) for (int c = 0; c < 3; c++) mean[c] += rows[3 * i + c];
+  for (int c = 0; c < 3; c++) mean[c] /= (double)n;
+  double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = 0; i < n; i++) {
+    double d[3];
+    for (int c = 0; c < 3; c++) d[c] = rows[3 * i + c] - mean[c];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) cov[3 * a + b] += d[a] * d[b];
+  }
+  for (int i = 0; i < 9; i++) cov[i] /= (double)n;
+  double W[3];
+  jacobi_sym(cov, W, eigvec9, 3);
+  if (eigval3) for (int c = 0; c < 3; c++) eigval3[c] = W[c];
+  if (mean3) for (int c = 0; c < 3; c++) mean3[c] = mean[c];
+}
+
+// GetPrincipalRotationAxes (rotation.cc:16-57), literal: returns the number of integration intervals (rows of the PCA
+// input, optionally copied to rows_out[cap][3]) or -1 when fewer than 3 (CHECK_GE).
+int64_t pgo_principal_rotation_axes(const double* gyro_xyz, const int64_t* gyro_t, int64_t n, int64_t interval_usec,
+                                    double* axes9, double* rows_out, int64_t cap) {
+  std::vector<double> rows;
+  Quat cur{1, 0, 0, 0};
+  int64_t cur_usec = 0;
+  for (int64_t i = 1; i < n; i++) {
+    const int64_t dur = gyro_t[i] - gyro_t[i - 1];
+    cur_usec += dur;
+    const Quat rq = rotation_motion_to_quaternion(gyro_xyz[3 * i], gyro_xyz[3 * i + 1], gyro_xyz[3 * i + 2], (double)dur * 1e-6);
+    cur = qmul(cur, rq);
+    if (cur_usec >= interval_usec) {
+      rows.push_back(cur.x); rows.push_back(cur.y); rows.push_back(cur.z);
+      cur = Quat{1, 0, 0, 0};
+      cur_usec = 0;
+    }
+  }
+  const int64_t m = (int64_t)rows.size() / 3;
+  if (m < 3) return -1;
+  if (rows_out) for (int64_t i = 0; i < std::min(m, cap) * 3; i++) rows_out[i] = rows[i];
+  pgo_pca3(rows.data(), m, axes9, nullptr, nullptr);
+  return m;
+}
+
+// GetAngularVelocitiesAroundAxisDirect (rotation.cc:103-119)
+void pgo_angular_velocities_around_axis(const double* gyro_xyz, int64_t n, const double* axis, double* out) {
+  const double nrm = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);  // cv::norm(axis, NORM_L2)
+  for (int64_t i = 0; i < n; i++)
+    out[i] = (gyro_xyz[3 * i] * axis[0] + gyro_xyz[3 * i + 1] * axis[1] + gyro_xyz[3 * i + 2] * axis[2]) / nrm;
 }
 
 }  // extern "C"

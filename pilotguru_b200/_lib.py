@@ -67,6 +67,10 @@ _SIGS = {
     "pgb_imu_fit_windows": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                       vp, vp, vp, vp, vp]),
     "pgb_imu_num_windows": (C.c_int, [C.c_int, C.c_int]),
+    "pgb_imu_fit_windows_fwd": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                          vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp]),
+    "pgb_principal_rotation_axes": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int64, vp, vp]),
+    "pgb_angular_velocities_around_axis": (C.c_int, [C.c_int, vp, C.c_size_t, vp, vp]),
     "pgb_smooth_time_series": (C.c_int, [C.c_int, vp, vp, C.c_int64, vp, C.c_int64, C.c_double, vp]),
 }
 

@@ -103,8 +103,33 @@ def num_windows(n_gps: int, shift_step: int) -> int:
     return int(lib().pgb_imu_num_windows(n_gps, shift_step))
 
 
+def principal_rotation_axes(gyro_xyz, gyro_t, integration_interval_usec: int = 500000, device: int = 0):
+    """GetPrincipalRotationAxes (src/calibration/rotation.cc:16-57): 3x3 eigenvector rows (row 0 = the vehicle's
+    vertical axis as fit_motion.cc:326-333 uses it) and the number of integration intervals."""
+    g, t = _f64(gyro_xyz), _i64(gyro_t)
+    axes = np.zeros(9); n = C.c_int64()
+    check(lib().pgb_principal_rotation_axes(device, np_ptr(g), np_ptr(t), len(t), integration_interval_usec, np_ptr(axes),
+                                            C.byref(n)))
+    return axes.reshape(3, 3), n.value
+
+
+def angular_velocities_around_axis(gyro_xyz, axis, device: int = 0):
+    """GetAngularVelocitiesAroundAxisDirect (rotation.cc:103-119)."""
+    g, a = _f64(gyro_xyz), _f64(axis)
+    out = np.empty(len(g))
+    check(lib().pgb_angular_velocities_around_axis(device, np_ptr(g), len(g), np_ptr(a), np_ptr(out)))
+    return out
+
+
+def forward_axis(fwd_sum, vertical_axis):
+    """fit_motion.cc:281-283: remove the vertical component of the summed device-frame velocities, normalise."""
+    f = _f64(fwd_sum).copy(); v = _f64(vertical_axis)
+    f -= v * v.dot(f)
+    return f / (np.sqrt((f * f).sum()) + 1e-5)
+
+
 def fit_windows(imu: ImuSeries, gps_v, gps_t, batch_size=40, shift_step=5, max_iterations=500, epsilon=1e-5,
-                first_window=0, n_windows=-1):
+                first_window=0, n_windows=-1, fwd_min_velocity=None, fwd_min_rotation_rad=0.2):
     """All sliding windows of fit_motion.cc:179-221 at once, every L-BFGS on the device.  Returns per-merged-event
     (sum of |v| over covering windows, count) plus per-window x / fx / iterations for the selected shard."""
     gv, gt = _f64(gps_v), _i64(gps_t)
@@ -113,10 +138,17 @@ def fit_windows(imu: ImuSeries, gps_v, gps_t, batch_size=40, shift_step=5, max_i
     nw = nw_all - first_window if n_windows < 0 else n_windows
     ssum = np.zeros(M); scnt = np.zeros(M, np.int32)
     x = np.zeros((max(nw, 1), 9)); fx = np.zeros(max(nw, 1)); it = np.zeros(max(nw, 1), np.int32)
-    check(lib().pgb_imu_fit_windows(imu._h, np_ptr(gv), np_ptr(gt), len(gv), batch_size, shift_step, max_iterations,
-                                    epsilon, first_window, n_windows, np_ptr(ssum), np_ptr(scnt), np_ptr(x), np_ptr(fx),
-                                    np_ptr(it)))
-    return dict(speed_sum=ssum, speed_cnt=scnt, x=x[:nw], fx=fx[:nw], iters=it[:nw])
+    if fwd_min_velocity is None:
+        check(lib().pgb_imu_fit_windows(imu._h, np_ptr(gv), np_ptr(gt), len(gv), batch_size, shift_step, max_iterations,
+                                        epsilon, first_window, n_windows, np_ptr(ssum), np_ptr(scnt), np_ptr(x),
+                                        np_ptr(fx), np_ptr(it)))
+        return dict(speed_sum=ssum, speed_cnt=scnt, x=x[:nw], fx=fx[:nw], iters=it[:nw])
+    fwd = np.zeros(3); used = C.c_int32()
+    check(lib().pgb_imu_fit_windows_fwd(imu._h, np_ptr(gv), np_ptr(gt), len(gv), batch_size, shift_step, max_iterations,
+                                        epsilon, first_window, n_windows, np_ptr(ssum), np_ptr(scnt), np_ptr(x),
+                                        np_ptr(fx), np_ptr(it), fwd_min_velocity, fwd_min_rotation_rad, np_ptr(fwd),
+                                        C.byref(used)))
+    return dict(speed_sum=ssum, speed_cnt=scnt, x=x[:nw], fx=fx[:nw], iters=it[:nw], fwd_sum=fwd, fwd_windows=used.value)
 
 
 def forward_velocities(gyro_xyz, gyro_t, acc_xyz, acc_t, gps_v, gps_t, batch_size=40, shift_step=5, max_iterations=500,

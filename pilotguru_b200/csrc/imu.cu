@@ -117,12 +117,17 @@ __global__ void k_imu_speeds(int nWin, int maxRefs, const WinDesc* __restrict__ 
                              const int* __restrict__ ioff, const int* __restrict__ ivM,
                              const long long* __restrict__ ivDur, const int* __restrict__ mG, const int* __restrict__ mA,
                              const double* __restrict__ gyro, const double* __restrict__ acc,
-                             double* __restrict__ speeds, double* __restrict__ quat, double* __restrict__ vel) {
+                             double* __restrict__ speeds, double* __restrict__ quat, double* __restrict__ vel,
+                             double minVel, double* __restrict__ fwdPart) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nWin * maxRefs) return;
   const int w = t / maxRefs, j = t - w * maxRefs;
   const int r = win[w].s + 1 + j;
+  if (fwdPart) { fwdPart[4 * (size_t)t] = 0.0; fwdPart[4 * (size_t)t + 1] = 0.0; fwdPart[4 * (size_t)t + 2] = 0.0; fwdPart[4 * (size_t)t + 3] = 1.0; }
   if (r >= win[w].e) return;
+  V3 fsum = v3(0.0, 0.0, 0.0);
+  double minW = 1.0;
+  const int kEnd = ioff[win[w].e];  // one past the window's last sub-interval
   const double* x = xAll + (size_t)w * 9;
   const V3 g = v3(x[0], x[1], x[2]), h = v3(x[3], x[4], x[5]), v0 = v3(x[6], x[7], x[8]);
   const WinRec wr = rec[(size_t)w * recStride + j];
@@ -147,7 +152,40 @@ __global__ void k_imu_speeds(int nWin, int maxRefs, const WinDesc* __restrict__ 
       const Q4 q = qmul(wr.Q, ss.l);
       quat[4 * (base + k)] = q.w; quat[4 * (base + k) + 1] = q.x; quat[4 * (base + k) + 2] = q.y; quat[4 * (base + k) + 3] = q.z;
     }
+    // forward-axis evidence (fit_motion.cc:223-248): one trajectory point per merged event -- the LAST sub-interval
+    // carrying it inside the window (velocity.cc:236-250)
+    if (fwdPart && (k + 1 >= kEnd || ivM[k + 1] != m)) {
+      const Q4 q = qmul(wr.Q, ss.l);
+      minW = fmin(minW, fabs(q.w));
+      if (norm3(v) >= minVel) {
+        Q4 qc; qc.w = q.w; qc.x = -q.x; qc.y = -q.y; qc.z = -q.z;
+        fsum = add(fsum, qrot(qc, v));
+      }
+    }
   }
+  if (fwdPart) { fwdPart[4 * (size_t)t] = fsum.x; fwdPart[4 * (size_t)t + 1] = fsum.y; fwdPart[4 * (size_t)t + 2] = fsum.z; fwdPart[4 * (size_t)t + 3] = minW; }
+}
+
+// GetPrincipalRotationAxes (rotation.cc:16-57): one thread per integration interval multiplies the rotation
+// quaternions of its gyro samples (the interval boundaries are an integer prefix computed on the host).
+__global__ void k_rot_intervals(int nIv, const int* __restrict__ ivStart, const double* __restrict__ gyro,
+                                const long long* __restrict__ gyroT, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nIv) return;
+  Q4 q; q.w = 1.0; q.x = 0.0; q.y = 0.0; q.z = 0.0;
+  for (int k = ivStart[i]; k < ivStart[i + 1]; k++) {
+    const double dt = (double)(gyroT[k] - gyroT[k - 1]) * 1e-6;
+    q = qmul(q, rotation_motion_to_quaternion(gyro[3 * (size_t)k], gyro[3 * (size_t)k + 1], gyro[3 * (size_t)k + 2], dt));
+  }
+  out[3 * (size_t)i] = q.x; out[3 * (size_t)i + 1] = q.y; out[3 * (size_t)i + 2] = q.z;
+}
+
+// GetAngularVelocitiesAroundAxisDirect (rotation.cc:103-119)
+__global__ void k_axis_project(long long n, const double* __restrict__ gyro, double ax, double ay, double az, double norm,
+                               double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = ((gyro[3 * i] * ax + gyro[3 * i + 1] * ay) + gyro[3 * i + 2] * az) / norm;
 }
 
 // Per merged event: the sub-intervals carrying it are a contiguous run [ka, kb] of the global interval list.
@@ -237,7 +275,7 @@ struct pgb_imu {
   long long spTotal = 0;
   DevBuf<int> dIoff, dIvM, dIvRef, dFirstIv, dLastIv, dIt, dNe, dCnt;
   DevBuf<long long> dIvDur, dTotal;
-  DevBuf<double> dGpsV, dX, dFx, dSpeeds, dQuat, dVel, dSum, dOut10;
+  DevBuf<double> dGpsV, dX, dFx, dSpeeds, dQuat, dVel, dSum, dOut10, dFwd;
   DevBuf<GpsLocal> dLoc;
   DevBuf<WinRec> dRec;
   DevBuf<WinDesc> dWin;
@@ -368,15 +406,17 @@ int solve(pgb_imu* o, int maxIter, double eps, int useX0) {
   return PGB_OK;
 }
 
-int speeds(pgb_imu* o, bool full) {
+int speeds(pgb_imu* o, bool full, bool fwd = false, double minVel = 0.0) {
   const int nW = (int)o->win.size();
   if (nW == 0 || o->spTotal == 0) return PGB_OK;
   if (ensure(o->dSpeeds, o->spTotal)) return PGB_ERR_CUDA;
+  if (fwd && ensure(o->dFwd, 4 * (size_t)nW * o->maxRefs)) return PGB_ERR_CUDA;
   if (full && (ensure(o->dQuat, 4 * o->spTotal) || ensure(o->dVel, 3 * o->spTotal))) return PGB_ERR_CUDA;
   const int n = nW * o->maxRefs;
   k_imu_speeds<<<(n + 63) / 64, 64, 0, o->stream>>>(nW, o->maxRefs, o->dWin.p, o->maxRefs, o->dRec.p, o->dX.p, o->dIoff.p,
                                                     o->dIvM.p, o->dIvDur.p, o->dMG.p, o->dMA.p, o->dGyro.p, o->dAcc.p,
-                                                    o->dSpeeds.p, full ? o->dQuat.p : nullptr, full ? o->dVel.p : nullptr);
+                                                    o->dSpeeds.p, full ? o->dQuat.p : nullptr, full ? o->dVel.p : nullptr,
+                                                    minVel, fwd ? o->dFwd.p : nullptr);
   PGB_CHECK_LAUNCH();
   return PGB_OK;
 }
@@ -530,6 +570,15 @@ int pgb_imu_num_windows(int n_gps, int shift_step) {
 int pgb_imu_fit_windows(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, int batch_size, int shift_step,
                         int max_iterations, double epsilon, int first_window, int n_windows, double* speed_sum,
                         int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out) {
+  return pgb_imu_fit_windows_fwd(o, gps_v, gps_t, n_gps, batch_size, shift_step, max_iterations, epsilon, first_window,
+                                 n_windows, speed_sum, speed_cnt, x_out, fx_out, iters_out, 0.0, 0.0, nullptr, nullptr);
+}
+
+int pgb_imu_fit_windows_fwd(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, int batch_size,
+                            int shift_step, int max_iterations, double epsilon, int first_window, int n_windows,
+                            double* speed_sum, int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out,
+                            double fwd_min_velocity, double fwd_min_rotation_rad, double* fwd_sum_xyz,
+                            int32_t* fwd_windows_used) {
   if (!o) return fail(PGB_ERR_INVALID, "null handle");
   // the CHECKs of fit_motion.cc:304-309
   if (batch_size <= 0 || shift_step <= 0 || batch_size < shift_step || max_iterations <= 0 || !(epsilon > 0))
@@ -544,10 +593,15 @@ int pgb_imu_fit_windows(pgb_imu* o, const double* gps_v, const int64_t* gps_t, i
   if (nW == 0) return PGB_OK;
   rc = solve(o, max_iterations, epsilon, 0);
   if (rc) return rc;
-  rc = speeds(o, false);
+  rc = speeds(o, false, fwd_sum_xyz != nullptr, fwd_min_velocity);
   if (rc) return rc;
   cudaStream_t s = o->stream;
   std::vector<int> its(nW);
+  std::vector<double> fwd;
+  if (fwd_sum_xyz && o->spTotal > 0) {
+    fwd.resize(4 * (size_t)nW * o->maxRefs);
+    PGB_CUDA(cudaMemcpyAsync(fwd.data(), o->dFwd.p, fwd.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
   PGB_CUDA(cudaMemcpyAsync(its.data(), o->dIt.p, nW * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (x_out) PGB_CUDA(cudaMemcpyAsync(x_out, o->dX.p, (size_t)nW * 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (fx_out) PGB_CUDA(cudaMemcpyAsync(fx_out, o->dFx.p, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -575,10 +629,163 @@ int pgb_imu_fit_windows(pgb_imu* o, const double* gps_v, const int64_t* gps_t, i
     }
   }
   PGB_CUDA(cudaStreamSynchronize(s));
+  if (fwd_sum_xyz) {
+    // total_velocity_local (fit_motion.cc:172-173, :232-248): Kahan sum (math.hpp:8-27) over the windows whose largest
+    // rotation reaches the threshold; per (window, GPS interval) partial sums come from k_imu_speeds.
+    double sum[3] = {0, 0, 0}, rem[3] = {0, 0, 0};
+    int used = 0;
+    for (int w = 0; w < nW && !fwd.empty(); w++) {
+      const int nr = o->win[w].e - o->win[w].s - 1;
+      double minCos = 1.0;
+      for (int j = 0; j < nr; j++) minCos = std::min(minCos, fwd[4 * ((size_t)w * o->maxRefs + j) + 3]);
+      if (!(std::acos(minCos) >= fwd_min_rotation_rad)) continue;
+      used++;
+      for (int j = 0; j < nr; j++)
+        for (int c = 0; c < 3; c++) {
+          const double v = fwd[4 * ((size_t)w * o->maxRefs + j) + c];
+          const double prop = v + rem[c], upd = sum[c] + prop, act = upd - sum[c];
+          rem[c] = prop - act;
+          sum[c] = upd;
+        }
+    }
+    for (int c = 0; c < 3; c++) fwd_sum_xyz[c] = sum[c];
+    if (fwd_windows_used) *fwd_windows_used = used;
+  }
   for (int w = 0; w < nW; w++) {
     if (iters_out) iters_out[w] = its[w];
     if (its[w] < 0) return fail(PGB_ERR_NUMERIC, "window %d: the line search step left [min_step, max_step]", o->firstWin + w);
   }
+  return PGB_OK;
+}
+
+// Symmetric 3x3 eigen-decomposition as cv::PCA performs it (cv::eigen -> the cyclic Jacobi sweep of OpenCV's
+// core/src/lapack.cpp JacobiImpl_, un-vendored: restated from the published algorithm so that the eigenvector SIGNS
+// follow OpenCV's; rows sorted by descending eigenvalue).
+static void jacobi3(double A[9], double W[3], double V[9]) {
+  const int n = 3;
+  const double eps = 2.220446049250313e-16;
+  for (int i = 0; i < 9; i++) V[i] = 0.0;
+  for (int i = 0; i < n; i++) V[i * n + i] = 1.0;
+  int indR[3] = {0, 0, 0}, indC[3] = {0, 0, 0};
+  for (int k = 0; k < n; k++) {
+    W[k] = A[(n + 1) * k];
+    if (k < n - 1) {
+      int m = k + 1;
+      double mv = std::fabs(A[n * k + m]);
+      for (int i = k + 2; i < n; i++) { const double val = std::fabs(A[n * k + i]); if (mv < val) { mv = val; m = i; } }
+      indR[k] = m;
+    }
+    if (k > 0) {
+      int m = 0;
+      double mv = std::fabs(A[k]);
+      for (int i = 1; i < k; i++) { const double val = std::fabs(A[n * i + k]); if (mv < val) { mv = val; m = i; } }
+      indC[k] = m;
+    }
+  }
+  for (int iters = 0, maxIters = n * n * 30; iters < maxIters; iters++) {
+    int k = 0;
+    double mv = std::fabs(A[indR[0]]);
+    for (int i = 1; i < n - 1; i++) { const double val = std::fabs(A[n * i + indR[i]]); if (mv < val) { mv = val; k = i; } }
+    int l = indR[k];
+    for (int i = 1; i < n; i++) { const double val = std::fabs(A[n * indC[i] + i]); if (mv < val) { mv = val; k = indC[i]; l = i; } }
+    const double p = A[n * k + l];
+    if (std::fabs(p) <= eps) break;
+    const double y = (W[l] - W[k]) * 0.5;
+    double t = std::fabs(y) + std::hypot(p, y);
+    double s = std::hypot(p, t);
+    const double c = t / s;
+    s = p / s;
+    t = (p / t) * p;
+    if (y < 0) { s = -s; t = -t; }
+    A[n * k + l] = 0;
+    W[k] -= t;
+    W[l] += t;
+    auto rot = [&](double& v0, double& v1) { const double a0 = v0, b0 = v1; v0 = a0 * c - b0 * s; v1 = a0 * s + b0 * c; };
+    for (int i = 0; i < k; i++) rot(A[n * i + k], A[n * i + l]);
+    for (int i = k + 1; i < l; i++) rot(A[n * k + i], A[n * i + l]);
+    for (int i = l + 1; i < n; i++) rot(A[n * k + i], A[n * l + i]);
+    for (int i = 0; i < n; i++) rot(V[n * k + i], V[n * l + i]);
+    for (int j = 0; j < 2; j++) {
+      const int idx = j == 0 ? k : l;
+      if (idx < n - 1) {
+        int m = idx + 1;
+        double mv2 = std::fabs(A[n * idx + m]);
+        for (int i = idx + 2; i < n; i++) { const double val = std::fabs(A[n * idx + i]); if (mv2 < val) { mv2 = val; m = i; } }
+        indR[idx] = m;
+      }
+      if (idx > 0) {
+        int m = 0;
+        double mv2 = std::fabs(A[idx]);
+        for (int i = 1; i < idx; i++) { const double val = std::fabs(A[n * i + idx]); if (mv2 < val) { mv2 = val; m = i; } }
+        indC[idx] = m;
+      }
+    }
+  }
+  for (int k = 0; k < n - 1; k++) {
+    int m = k;
+    for (int i = k + 1; i < n; i++) if (W[m] < W[i]) m = i;
+    if (k != m) {
+      std::swap(W[m], W[k]);
+      for (int i = 0; i < n; i++) std::swap(V[n * m + i], V[n * k + i]);
+    }
+  }
+}
+
+int pgb_principal_rotation_axes(int device, const double* gyro_xyz, const int64_t* gyro_t, size_t n,
+                                int64_t integration_interval_usec, double axes_out[9], int64_t* n_intervals) {
+  if (!gyro_xyz || !gyro_t || !axes_out) return fail(PGB_ERR_INVALID, "null argument");
+  if (integration_interval_usec <= 0) return fail(PGB_ERR_INVALID, "integration interval must be positive");  // CHECK_GT
+  // interval boundaries: the integer running sum of rotation.cc:24-43
+  std::vector<int> start;
+  start.push_back(1);
+  int64_t cur = 0;
+  for (size_t k = 1; k < n; k++) {
+    cur += gyro_t[k] - gyro_t[k - 1];
+    if (cur >= integration_interval_usec) { start.push_back((int)k + 1); cur = 0; }
+  }
+  const int nIv = (int)start.size() - 1;
+  if (n_intervals) *n_intervals = nIv;
+  if (nIv < 3) return fail(PGB_ERR_INVALID, "fewer than 3 rotation integration intervals (%d)", nIv);  // CHECK_GE(.., 3)
+  if (use_device(device)) return PGB_ERR_CUDA;
+  DevBuf<double> dG, dOut;
+  DevBuf<long long> dT;
+  DevBuf<int> dS;
+  if (dG.alloc(3 * n) || dT.alloc(n) || dS.alloc(start.size()) || dOut.alloc(3 * (size_t)nIv)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemcpy(dG.p, gyro_xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+  PGB_CUDA(cudaMemcpy(dT.p, gyro_t, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+  PGB_CUDA(cudaMemcpy(dS.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
+  k_rot_intervals<<<(nIv + 63) / 64, 64>>>(nIv, dS.p, dG.p, dT.p, dOut.p);
+  PGB_CHECK_LAUNCH();
+  std::vector<double> rows(3 * (size_t)nIv);
+  PGB_CUDA(cudaMemcpy(rows.data(), dOut.p, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  // cv::PCA(data, noArray(), DATA_AS_ROW): mean, covariance scaled by 1/nsamples, eigenvectors as rows
+  double mean[3] = {0, 0, 0};
+  for (int i = 0; i < nIv; i++) for (int c = 0; c < 3; c++) mean[c] += rows[3 * (size_t)i + c];
+  for (int c = 0; c < 3; c++) mean[c] /= nIv;
+  double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nIv; i++) {
+    double d[3];
+    for (int c = 0; c < 3; c++) d[c] = rows[3 * (size_t)i + c] - mean[c];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) cov[3 * a + b] += d[a] * d[b];
+  }
+  for (int i = 0; i < 9; i++) cov[i] /= nIv;
+  double W[3];
+  jacobi3(cov, W, axes_out);
+  return PGB_OK;
+}
+
+int pgb_angular_velocities_around_axis(int device, const double* gyro_xyz, size_t n, const double axis[3], double* out) {
+  if (!gyro_xyz || !axis || !out) return fail(PGB_ERR_INVALID, "null argument");
+  const double norm = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  if (!(norm > 1.0 - 1e-2) || !(norm < 1.0 + 1e-2)) return fail(PGB_ERR_INVALID, "axis is not normalised");  // rotation.cc:108-109
+  if (n == 0) return PGB_OK;
+  if (use_device(device)) return PGB_ERR_CUDA;
+  DevBuf<double> dG, dOut;
+  if (dG.alloc(3 * n) || dOut.alloc(n)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemcpy(dG.p, gyro_xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+  k_axis_project<<<(unsigned)((n + 255) / 256), 256>>>((long long)n, dG.p, axis[0], axis[1], axis[2], norm, dOut.p);
+  PGB_CHECK_LAUNCH();
+  PGB_CUDA(cudaMemcpy(out, dOut.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   return PGB_OK;
 }
 

@@ -123,3 +123,18 @@ def imu_gps(duration_s: float, imu_hz: float, seed: int = 11, gps_offset_s: floa
     gps_v = 8 + 4 * np.sin(0.15 * gts) + 2 * np.sin(0.5 * gts) + rng.normal(0, 0.1, size=gts.shape)
     return dict(gyro=np.ascontiguousarray(gyro), gyro_t=t_us, acc=np.ascontiguousarray(acc),
                 acc_t=acc_t, gps_v=np.ascontiguousarray(gps_v), gps_t=gps_t)
+
+
+def write_imu_gps_json(d, out_dir: str):
+    """Writes rotations.json / accelerations.json / locations.json in the PilotGuru Recorder format
+    (mobile/android/README.md:22-98, field names include/io/json_converters.hpp:10-35) for an imu_gps() dict."""
+    import json, os
+    os.makedirs(out_dir, exist_ok=True)
+    paths = {k: os.path.join(out_dir, k + ".json") for k in ("rotations", "accelerations", "locations")}
+    def xyz(a, t):
+        return [{"x": float(r[0]), "y": float(r[1]), "z": float(r[2]), "time_usec": int(u)} for r, u in zip(a, t)]
+    json.dump({"rotations": xyz(d["gyro"], d["gyro_t"])}, open(paths["rotations"], "w"))
+    json.dump({"accelerations": xyz(d["acc"], d["acc_t"])}, open(paths["accelerations"], "w"))
+    json.dump({"locations": [{"lat": 0.0, "lon": 0.0, "accuracy_m": 5.0, "speed_m_s": float(v), "time_usec": int(u)}
+                             for v, u in zip(d["gps_v"], d["gps_t"])]}, open(paths["locations"], "w"), indent=1)
+    return paths

@@ -302,3 +302,44 @@ def fit_motion(d, batch_size=40, shift_step=5, max_iters=500, sigma=0.003, mode=
         raise RuntimeError(f"pgo_fit_motion failed: {n}")
     return dict(idx=idx[:n].copy(), t_usec=ts[:n].copy(), avg=avg[:n].copy(), smoothed=sm[:n].copy(), x=xo, iters=it,
                 fx=fx, n_evals=ne.value)
+
+
+def forward_axis_sum(d, x_all, batch_size=40, shift_step=5, mode=0, min_vel=5.0, min_rot=0.2):
+    """total_velocity_local of fit_motion.cc:172-173,223-248 for per-window solutions x_all; returns (sum[3], windows used)."""
+    l = lib()
+    gv = np.ascontiguousarray(d["gps_v"], np.float64); gt = np.ascontiguousarray(d["gps_t"], np.int64)
+    gy = np.ascontiguousarray(d["gyro"], np.float64); gyt = np.ascontiguousarray(d["gyro_t"], np.int64)
+    ac = np.ascontiguousarray(d["acc"], np.float64); act = np.ascontiguousarray(d["acc_t"], np.int64)
+    xa = np.ascontiguousarray(x_all, np.float64); out = np.zeros(3); used = C.c_int32()
+    rc = l.pgo_forward_axis_sum(ptr(gv, f64p), ptr(gt, i64p), len(gv), ptr(gy, f64p), ptr(gyt, i64p), C.c_int64(len(gyt)),
+                                ptr(ac, f64p), ptr(act, i64p), C.c_int64(len(act)), batch_size, shift_step, ptr(xa, f64p),
+                                mode, C.c_double(min_vel), C.c_double(min_rot), ptr(out, f64p), C.byref(used))
+    if rc:
+        raise RuntimeError(f"pgo_forward_axis_sum failed: {rc}")
+    return out, used.value
+
+
+def pca3(rows):
+    """cv::PCA(rows, noArray(), DATA_AS_ROW) of an n x 3 matrix: (eigenvectors 3x3, eigenvalues, mean)."""
+    r = np.ascontiguousarray(rows, np.float64); ev = np.zeros(9); ew = np.zeros(3); mu = np.zeros(3)
+    lib().pgo_pca3(ptr(r, f64p), C.c_int64(len(r)), ptr(ev, f64p), ptr(ew, f64p), ptr(mu, f64p))
+    return ev.reshape(3, 3), ew, mu
+
+
+def principal_rotation_axes(gyro, gyro_t, interval_usec=500000):
+    """GetPrincipalRotationAxes (rotation.cc:16-57), literal: (axes 3x3, PCA input rows)."""
+    l = lib()
+    l.pgo_principal_rotation_axes.restype = C.c_int64
+    g = np.ascontiguousarray(gyro, np.float64); t = np.ascontiguousarray(gyro_t, np.int64)
+    axes = np.zeros(9); rows = np.zeros((len(t), 3))
+    n = l.pgo_principal_rotation_axes(ptr(g, f64p), ptr(t, i64p), C.c_int64(len(t)), C.c_int64(interval_usec), ptr(axes, f64p),
+                                      ptr(rows, f64p), C.c_int64(len(t)))
+    if n < 0:
+        raise ValueError("fewer than 3 rotation integration intervals")
+    return axes.reshape(3, 3), rows[:n].copy()
+
+
+def angular_velocities_around_axis(gyro, axis):
+    g = np.ascontiguousarray(gyro, np.float64); a = np.ascontiguousarray(axis, np.float64); out = np.empty(len(g))
+    lib().pgo_angular_velocities_around_axis(ptr(g, f64p), C.c_int64(len(g)), ptr(a, f64p), ptr(out, f64p))
+    return out
