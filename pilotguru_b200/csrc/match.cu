@@ -43,6 +43,11 @@ struct MatchArgs {
   int* nMatches;     // [pair]
   uint32_t* qList32;          // scratch [pair][cap][kMtK]: target | distance << 16, in arrival order
   int* qCnt;                  // scratch [pair][cap] (total candidates found, may exceed kMtK)
+  // work split: mode 1 = candidate search only (phases 0 + A) for the queries of split (blockIdx.x % nSplit) of pair
+  // (blockIdx.x / nSplit), followed by k_match_resolve; mode 0 = the whole sequential kernel, run only for pairs
+  // whose overflow flag is set (a query with more than kMtK candidates)
+  int mode, nSplit;
+  int* overflow;              // [pair]
 };
 
 __device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) {
@@ -112,9 +117,11 @@ __device__ __forceinline__ bool query_window(const MatchArgs& A, int p, int i, c
 
 __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p = A.mode == 1 ? blockIdx.x / A.nSplit : blockIdx.x, split = A.mode == 1 ? blockIdx.x % A.nSplit : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cap = A.cap;
   if (A.onlyIfBelow20 && A.nMatches[p] >= 20) return;
+  if (A.mode == 0 && A.overflow && !A.overflow[p]) return;
 
   const pgb_keypoint* curK;
   const uint8_t* curD;
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   int* qCnt = A.qCnt + (size_t)p * cap;
 
   // ---------------- phase A: thread per query
-  for (int i = tid; i < nQ; i += kMtThreads) {
+  for (int i = tid + split * kMtThreads; i < nQ; i += kMtThreads * A.nSplit) {
     QueryWin q;
     int cnt = 0;
     sQAng[i] = A.consecutive ? prevK[i].angle : A.qAng[(size_t)p * cap + i];
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
     }
     qCnt[i] = cnt;
   }
+  if (A.mode == 1) return;  // the greedy assignment is resolved by k_match_resolve
   __syncthreads();
 
   // ---------------- phase B: greedy replay in query order
@@ -358,6 +366,133 @@ __global__ void __launch_bounds__(kMtThreads) k_match(MatchArgs A) {
   if (tid == 0) A.nMatches[p] = sNm;
 }
 
+// Greedy assignment of ORBmatcher.cc:1380-1447 without the sequential replay.  The reference visits the queries in
+// index order and gives each its best still-free target.  Query i's decision is FINAL as soon as no unresolved
+// query with a lower index has i's chosen target among its candidates (then nothing processed before i in the
+// reference's order can still take it); targets taken by finalised queries of higher index can never be candidates of
+// an unresolved lower one by the same rule.  Rounds: (1) every unresolved query atomicMin's its index into each of
+// its free candidate targets, (2) every unresolved query picks its best free candidate (distance, then arrival
+// order: strict '<', first wins) and finalises it if it holds the target's minimum.  The lowest unresolved query
+// always finalises, chains of queries competing for the same targets resolve one link per round (a handful of
+// rounds on real frames instead of ~1000 dependent iterations).  Identical results to the sequential replay.
+__global__ void __launch_bounds__(kMtThreads) k_match_resolve(MatchArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int cap = A.cap;
+  if (A.onlyIfBelow20 && A.nMatches[p] >= 20) return;
+  const pgb_keypoint* curK;
+  const pgb_keypoint* prevK = nullptr;
+  int nCur, nQ;
+  if (A.consecutive) {
+    curK = A.curK + (size_t)(p + 1) * cap;
+    prevK = A.curK + (size_t)p * cap;
+    nCur = A.curN[p + 1];
+    nQ = A.curN[p];
+  } else {
+    curK = A.curK + (size_t)p * cap;
+    nCur = A.curN[p];
+    nQ = A.qN[p];
+  }
+  nCur = min(nCur, cap);
+  nQ = min(nQ, cap);
+  int* sBin = reinterpret_cast<int*>(smem);          // [cap] -1 free, else histogram bin (kHisto: taken, no histogram)
+  int* sMinUn = sBin + cap;                          // [cap] lowest unresolved query listing the target
+  int* sMatch = sMinUn + cap;                        // [cap]
+  unsigned char* sRes = reinterpret_cast<unsigned char*>(sMatch + cap);  // [cap] query resolved
+  __shared__ int sHist[kHisto];
+  __shared__ int sKeep[3];
+  __shared__ int sNm;
+  const uint32_t* qRow = A.qList32 + (size_t)p * cap * kMtK;
+  const int* qCnt = A.qCnt + (size_t)p * cap;
+
+  int over = 0;
+  for (int i = tid; i < cap; i += kMtThreads) {
+    sBin[i] = -1; sMinUn[i] = 0x7fffffff; sMatch[i] = -1;
+    sRes[i] = i < nQ ? 0 : 1;
+    if (i < nQ && qCnt[i] > kMtK) over = 1;
+  }
+  if (tid < kHisto) sHist[tid] = 0;
+  if (tid == 0) sNm = 0;
+  over = __syncthreads_or(over);
+  if (tid == 0) A.overflow[p] = over;
+  if (over) return;  // a query's candidate row was truncated: the sequential kernel redoes this pair
+
+  const float factor = 1.0f / kHisto;
+  for (;;) {
+    for (int i = tid; i < nQ; i += kMtThreads) {
+      if (sRes[i]) continue;
+      const int cnt = qCnt[i];
+      for (int c = 0; c < cnt; c++) {
+        const int t = (int)(qRow[(size_t)i * kMtK + c] & 0xffffu);
+        if (sBin[t] == -1) atomicMin(&sMinUn[t], i);
+      }
+    }
+    __syncthreads();
+    int pending = 0;
+    for (int i = tid; i < nQ; i += kMtThreads) {
+      if (sRes[i]) continue;
+      const int cnt = qCnt[i];
+      uint32_t best = 0xffffffffu;
+      int bestT = -1;
+      for (int c = 0; c < cnt; c++) {
+        const uint32_t e = qRow[(size_t)i * kMtK + c];
+        const int t = (int)(e & 0xffffu);
+        if (*(volatile int*)&sBin[t] != -1) continue;
+        const uint32_t key = ((e >> 16) << 8) | (uint32_t)c;
+        if (key < best) { best = key; bestT = t; }
+      }
+      if (bestT < 0 || (int)(best >> 8) > kThHigh) { sRes[i] = 1; continue; }  // no free candidate / bestDist > TH_HIGH
+      if (sMinUn[bestT] != i) { pending = 1; continue; }
+      int bin = kHisto;
+      if (A.checkOri) {
+        float rot = (A.consecutive ? prevK[i].angle : A.qAng[(size_t)p * cap + i]) - curK[bestT].angle;
+        if (rot < 0.0f) rot += 360.0f;
+        bin = (int)roundf(rot * factor);
+        if (bin == kHisto) bin = 0;
+        atomicAdd(&sHist[bin], 1);
+      }
+      *(volatile int*)&sBin[bestT] = bin;
+      sMatch[bestT] = i;
+      atomicAdd(&sNm, 1);
+      sRes[i] = 1;
+    }
+    if (!__syncthreads_or(pending)) break;
+    for (int t = tid; t < nCur; t += kMtThreads) sMinUn[t] = 0x7fffffff;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    if (A.checkOri) {  // ComputeThreeMaxima, ORBmatcher.cc:1605-1646
+      int max1 = 0, max2 = 0, max3 = 0;
+      for (int b = 0; b < kHisto; b++) {
+        const int s = sHist[b];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+        else if (s > max3) { max3 = s; ind3 = b; }
+      }
+      if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+    }
+    sKeep[0] = ind1; sKeep[1] = ind2; sKeep[2] = ind3;
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    int removed = 0;
+    for (int t = tid; t < nCur; t += kMtThreads) {
+      const int b = sBin[t];
+      if (b >= 0 && b < kHisto && b != sKeep[0] && b != sKeep[1] && b != sKeep[2]) {
+        sMatch[t] = -1;
+        removed++;
+      }
+    }
+    if (removed) atomicSub(&sNm, removed);
+    __syncthreads();
+  }
+  int* matchOfCur = A.matchOfCur + (size_t)p * cap;
+  for (int i = tid; i < cap; i += kMtThreads) matchOfCur[i] = sMatch[i];
+  if (tid == 0) A.nMatches[p] = sNm;
+}
+
 size_t match_smem_bytes(int cap) {
   size_t b = (size_t)cap * 8 * 4 + (size_t)cap * 5 * 4;        // desc, x, y, meta, angle, bin
   b += (size_t)(cap + (cap & 1)) * 2;                           // cell-sorted order
@@ -389,7 +524,8 @@ struct pgb_matcher {
   DevBuf<uint8_t> dD, dQD, dQV;
   DevBuf<float> dUV, dAng, dFlow;
   DevBuf<int> dN, dQN, dOct, dMatch, dNm;
-  size_t smemConfigured = 0;
+  DevBuf<int> overflow;
+  size_t smemConfigured = 0, smem2Configured = 0;
 };
 
 namespace {
@@ -405,6 +541,21 @@ int launch_match(pgb_matcher* m, MatchArgs& A, int nPairs) {
   }
   A.qList32 = m->qList.p;
   A.qCnt = m->qCnt.p;
+  A.overflow = m->overflow.p;
+  // candidate search spread over kSplit CTAs per pair, then the round-based greedy resolution (one CTA per pair)
+  constexpr int kSplit = 4;
+  A.mode = 1; A.nSplit = kSplit;
+  k_match<<<nPairs * kSplit, kMtThreads, smem, m->stream>>>(A);
+  PGB_CHECK_LAUNCH();
+  const size_t smem2 = (size_t)A.cap * 13 + 16;
+  if (smem2 > 48 * 1024 && smem2 > m->smem2Configured) {
+    PGB_CUDA(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    m->smem2Configured = smem2;
+  }
+  k_match_resolve<<<nPairs, kMtThreads, smem2, m->stream>>>(A);
+  PGB_CHECK_LAUNCH();
+  // pairs with a truncated candidate row (flagged by k_match_resolve) are redone by the sequential kernel
+  A.mode = 0; A.nSplit = 1;
   k_match<<<nPairs, kMtThreads, smem, m->stream>>>(A);
   PGB_CHECK_LAUNCH();
   return PGB_OK;
@@ -442,7 +593,7 @@ pgb_matcher* pgb_matcher_create(int device, float nnratio, int check_orientation
     m->ownStream = true;
   }
   const size_t n = (size_t)max_feats * max_batch;
-  if (m->qList.alloc(n * kMtK) || m->qCnt.alloc(n)) {
+  if (m->qList.alloc(n * kMtK) || m->qCnt.alloc(n) || m->overflow.alloc(max_batch)) {
     pgb_matcher_destroy(m);
     return nullptr;
   }

@@ -62,9 +62,11 @@ struct pgb_orb {
   TmapPack tmaps{};
   DevBuf<int4> tileTab;
   cudaStream_t copyStream = nullptr;
+  cudaStream_t auxStream[2] = {nullptr, nullptr};
+  cudaEvent_t evAux[2] = {nullptr, nullptr};
   cudaEvent_t evDone = nullptr;
   cudaEvent_t evChunk[16] = {};
-  int h2dChunk = 8;  // frames per H2D/compute pipeline chunk (PGB_H2D_CHUNK)
+  int h2dChunk = 16;  // largest H2D/compute pipeline chunk in frames (PGB_H2D_CHUNK)
   bool fastV3 = true;  // PGB_FAST_IMPL=v2: previous TMA kernel (A/B measurements)
   bool fastV2 = true;  // PGB_FAST_IMPL=v1 selects the first-generation kernel (kept for A/B measurements)
   int numSMs = 148;
@@ -264,7 +266,9 @@ int check_err_flag(pgb_orb* o) {
 
 // Stages `from`..`to` over frames [f0, f0+n) of the resident batch; kps/desc/counts are the bases of the WHOLE
 // batch's output arrays (frame f0 writes at f0*cap).
-int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap, int f0, int n) {
+int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap, int f0, int n,
+               cudaStream_t st = nullptr) {
+  if (!st) st = o->stream;
   const OrbGeo& g = o->geo;
   if (n <= 0) return PGB_OK;
   uint8_t* pyr = o->pyr.p + (size_t)f0 * g.frameStride;
@@ -278,22 +282,22 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
     switch (s) {
       case 0:
         for (int l = 1; l < g.nlevels; l++)
-          launch_pyramid_level(g, l, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], o->stream);
+          launch_pyramid_level(g, l, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], st);
         break;
       case 1:
         if (o->fastV2) {
-          int rc = o->fastV3 ? launch_fast_score_v3(g, o->tmaps, o->tileTab.p, f0, n, o->stream)
-                             : launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, f0, n, o->stream);
+          int rc = o->fastV3 ? launch_fast_score_v3(g, o->tmaps, o->tileTab.p, f0, n, st)
+                             : launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, f0, n, st);
           if (rc) return rc;
         } else {
-          launch_fast_score(g, n, pyr, score, o->stream);
+          launch_fast_score(g, n, pyr, score, st);
         }
         break;
-      case 2: launch_cells(g, n, score, slots, cellCnt, o->err.p, o->stream); break;
-      case 3: launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, o->stream); break;
+      case 2: launch_cells(g, n, score, slots, cellCnt, o->err.p, st); break;
+      case 3: launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, st); break;
       case 4:
         launch_orient_desc(g, n, pyr, staged, lvlCnt, kps + (size_t)f0 * cap, desc + (size_t)f0 * cap * 32, counts + f0,
-                           cap, o->err.p, o->stream);
+                           cap, o->err.p, st);
         break;
     }
   }
@@ -311,17 +315,32 @@ int extract_host_pipelined(pgb_orb* o, const uint8_t* gray, int n_frames, int wi
   // the copy stream may not overwrite level 0 before the previous call's kernels are done with it
   PGB_CUDA(cudaEventRecord(o->evDone, o->stream));
   PGB_CUDA(cudaStreamWaitEvent(o->copyStream, o->evDone, 0));
-  for (int f0 = 0, k = 0; f0 < n_frames; f0 += chunk, k++) {
-    const int n = std::min(chunk, n_frames - f0);
+  // Chunk schedule (frames): 4, 8, 16, 16, ..., 8, 4, 2, 2.  Small chunks first so the kernels start while the bulk
+  // of the batch is still on the bus; small chunks last so that what the caller waits for after the last byte has
+  // arrived is only the kernels of a 2-frame chunk.
+  // Chunks alternate over three compute streams: the latency-bound kernels of one chunk (octree, small grids) overlap
+  // the throughput-bound ones of its neighbours, so chunking does not cost kernel efficiency.
+  cudaStream_t cs[3] = {o->stream, o->auxStream[0], o->auxStream[1]};
+  for (int a = 1; a < 3; a++) PGB_CUDA(cudaStreamWaitEvent(cs[a], o->evDone, 0));
+  int used = 0;
+  for (int f0 = 0, k = 0, n = 0; f0 < n_frames; f0 += n, k++) {
+    n = std::min(chunk, std::max(std::min(2, n_frames - f0), (n_frames - f0) / 2));
+    if (k < 2) n = std::min(n, std::max(1, chunk >> (2 - k)));
+    cudaStream_t st = cs[k % 3];
+    used = std::max(used, std::min(k, 2));
     for (int f = f0; f < f0 + n; f++)
       PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
                                  gray + (size_t)f * frame_stride, pitch, width, height, cudaMemcpyHostToDevice,
                                  o->copyStream));
     cudaEvent_t ev = o->evChunk[k % kMaxChunkEvents];
     PGB_CUDA(cudaEventRecord(ev, o->copyStream));
-    PGB_CUDA(cudaStreamWaitEvent(o->stream, ev, 0));
-    int rc = run_stages(o, 0, 4, kps, desc, counts, cap, f0, n);
+    PGB_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    int rc = run_stages(o, 0, 4, kps, desc, counts, cap, f0, n, st);
     if (rc) return rc;
+  }
+  for (int a = 1; a <= used; a++) {  // join: everything after this call on the handle's stream sees all chunks
+    PGB_CUDA(cudaEventRecord(o->evAux[a - 1], cs[a]));
+    PGB_CUDA(cudaStreamWaitEvent(o->stream, o->evAux[a - 1], 0));
   }
   return PGB_OK;
 }
@@ -394,6 +413,10 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
     return bail("cudaStreamCreate/cudaEventCreate failed");
   for (int k = 0; k < kMaxChunkEvents; k++)
     if (cudaEventCreateWithFlags(&o->evChunk[k], cudaEventDisableTiming) != cudaSuccess) return bail("cudaEventCreate failed");
+  for (int a = 0; a < 2; a++)
+    if (cudaStreamCreateWithFlags(&o->auxStream[a], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&o->evAux[a], cudaEventDisableTiming) != cudaSuccess)
+      return bail("cudaStreamCreate/cudaEventCreate failed");
   if (const char* e = getenv("PGB_H2D_CHUNK")) o->h2dChunk = std::max(1, atoi(e));
   const OrbGeo& c = o->capGeo;
   const size_t B = (size_t)max_batch;
@@ -421,6 +444,10 @@ void pgb_orb_destroy(pgb_orb* o) {
   if (o->stream) cudaStreamSynchronize(o->stream);
   if (o->copyStream) { cudaStreamSynchronize(o->copyStream); cudaStreamDestroy(o->copyStream); }
   if (o->evDone) cudaEventDestroy(o->evDone);
+  for (int a = 0; a < 2; a++) {
+    if (o->auxStream[a]) { cudaStreamSynchronize(o->auxStream[a]); cudaStreamDestroy(o->auxStream[a]); }
+    if (o->evAux[a]) cudaEventDestroy(o->evAux[a]);
+  }
   for (int k = 0; k < kMaxChunkEvents; k++)
     if (o->evChunk[k]) cudaEventDestroy(o->evChunk[k]);
   if (o->ownStream && o->stream) cudaStreamDestroy(o->stream);
