@@ -1,0 +1,58 @@
+"""GPU end-to-end test of the `optical_trajectories` drop-in binary in flow-tracking mode (pilotguru_b200/host):
+synthetic frames with a known integer flow -> ORB extraction + projection matching on the B200 through the C-ABI
+(host buffers, the reference's calling convention) -> trajectory JSON in the reference's schema
+(src/io/json_converters.cc:37-96).  The per-frame keypoint/match counts the binary reports are checked against the
+oracle's extraction + matching of the same frames."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pilotguru_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_optical_trajectories_binary(tmp_path):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "pilotguru_b200", "host")], check=True, capture_output=True)
+    w, h, n = 640, 480, 21
+    frames = np.stack([synth.frame(t, w=w, h=h) for t in range(n)])
+    raw = tmp_path / "frames.gray"
+    frames.tofile(raw)
+    settings = tmp_path / "settings.yml"
+    settings.write_text("%YAML:1.0\nCamera.fps: 25.0\nORBextractor.nFeatures: 500\nORBextractor.scaleFactor: 1.2\n"
+                        "ORBextractor.nLevels: 8\nORBextractor.iniThFAST: 20\nORBextractor.minThFAST: 7\n")
+    p = subprocess.run([os.path.join(ROOT, "pilotguru_b200", "host", "optical_trajectories"), "--vocabulary_file=unused.txt",
+                        "--camera_settings", str(settings), "--out_dir", str(tmp_path), f"--in_video=raw:{raw}:{w}x{h}",
+                        "--novisualize", "--batch=8", "--logtostderr"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = json.load(open(tmp_path / "trajectory-0.json"))
+    assert not (tmp_path / "trajectory-1.json").exists()                  # tracking never lost on this sequence
+    tr = out["trajectory"]
+    assert len(tr) == n and np.array(out["plane"]).shape == (2, 3)
+    assert [e["frame_id"] for e in tr] == list(range(n)) and [e["time_usec"] for e in tr] == [int(round(i * 1e6 / 25.0)) for i in range(n)]
+    # translation = minus the accumulated image flow (x -> x, y -> z); the synthetic flow is an exact integer shift
+    flow = np.array([synth.flow(t, w=w, h=h) if t else (0, 0) for t in range(n)], float)
+    want = -np.cumsum(flow, axis=0)
+    got = np.array([[e["pose"]["translation"][0], e["pose"]["translation"][2]] for e in tr])
+    assert np.max(np.abs(got - want)) <= 0.51, (got - want)
+    assert all(e["pose"]["translation"][1] == 0 for e in tr) and not any(e["is_lost"] for e in tr)
+    # the counts the binary reports equal the oracle's on the same frames (extraction + zero-velocity-guess matching)
+    orc = O.OrbOracle(500, 1.2, 8, 20, 7)
+    feats = [orc.extract(f) for f in frames]
+    sf = orc.tables()[0]
+    tot_k = sum(len(k) for k, _ in feats); tot_m = 0
+    vflow = np.zeros(2, np.float32)
+    for t in range(1, n):
+        (pk, pd), (ck, cd) = feats[t - 1], feats[t]
+        uv = np.stack([pk["x"] + vflow[0], pk["y"] + vflow[1]], axis=1).astype(np.float32)
+        nm, mo, _ = O.search_by_projection(ck, cd, uv, pk["octave"], pk["angle"], pd, np.ones(len(pk), np.uint8), (0, w, 0, h), 15.0, sf)
+        if nm < 20:
+            nm, mo, _ = O.search_by_projection(ck, cd, uv, pk["octave"], pk["angle"], pd, np.ones(len(pk), np.uint8), (0, w, 0, h), 30.0, sf)
+        tot_m += nm
+    line = [l for l in p.stderr.splitlines() if "keypoints/frame" in l][-1]
+    assert f"{tot_k / n:.1f} keypoints/frame" in line and f"{tot_m / (n - 1):.1f} matches/frame" in line, (line, tot_k / n, tot_m / (n - 1))

@@ -65,3 +65,74 @@ def test_json_round_trip(host_bins, tmp_path):
     fin.write_text(json.dumps({"locations": []}))
     p = run(host_bins, "json_selftest", str(fin), "locations", "speed_m_s", str(fout), "v", "s")
     assert p.returncode == -6 and "is empty" in p.stderr
+
+
+def _np_finish(poses, sigma):
+    """numpy restatement of track_image_sequence.cc:63-109 (+ smoothing.cc:11-46, horizontal_flatten.cc:7-64)"""
+    t = poses[:, 2:5].copy(); q = poses[:, 5:9].copy()
+    if sigma > 0:
+        ks = 4 * sigma + 1
+        x = np.arange(ks) - (ks - 1) / 2
+        k = np.exp(-0.5 * x * x / (sigma * sigma)); k /= k.sum()
+        idx = np.clip(np.arange(len(q))[:, None] + np.arange(ks)[None, :] - ks // 2, 0, len(q) - 1)
+        q = (q[idx] * k[None, :, None]).sum(axis=1)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+    import oracle_lib as O
+    vec, val, _ = O.pca3(t)
+    plane = vec[:2]
+    w, v = q[:, 0], q[:, 1:]
+    z = np.array([0.0, 0.0, 1.0])
+    uv = 2 * np.cross(v, z)
+    d = z + w[:, None] * uv + np.cross(v, uv)
+    dirs = d @ plane.T
+    turn = np.zeros(len(dirs))
+    for i in range(1, len(dirs)):
+        p, c = dirs[i - 1], dirs[i]
+        cs = p.dot(c) / np.linalg.norm(p) / np.linalg.norm(c)
+        turn[i] = np.arccos(cs) * (1.0 if p[0] * c[1] - p[1] * c[0] > 0 else -1.0)
+    return plane, dirs, turn, q, val
+
+
+@pytest.mark.parametrize("sigma", [-1, 2])
+def test_trajectory_postprocessing(host_bins, tmp_path, sigma):
+    rng = np.random.default_rng(7)
+    n = 60
+    s = np.linspace(0, 3, n)
+    yaw = 0.6 * np.sin(s) + 0.02 * rng.normal(size=n)
+    pos = np.stack([np.cumsum(np.sin(yaw)), 1e-4 * rng.normal(size=n), np.cumsum(np.cos(yaw))], axis=1)
+    quat = np.stack([np.cos(yaw / 2), np.zeros(n), np.sin(yaw / 2), np.zeros(n)], axis=1)
+    ts = (np.arange(n) * 33333).astype(np.int64)
+    poses = np.concatenate([ts[:, None].astype(float), np.arange(n)[:, None].astype(float), pos, quat], axis=1)
+    fin, fout = tmp_path / "poses.json", tmp_path / "traj.json"
+    fin.write_text(json.dumps({"poses": [[int(r[0]), int(r[1])] + [float(x) for x in r[2:]] for r in poses]}))
+    p = run(host_bins, "trajectory_selftest", str(fin), str(sigma), str(fout))
+    assert p.returncode == 0, p.stderr
+    out = json.loads(fout.read_text())
+    plane, dirs, turn, q, val = _np_finish(poses, sigma)
+    assert sorted(out.keys()) == ["plane", "trajectory"] and len(out["trajectory"]) == n
+    assert np.max(np.abs(np.array(out["plane"]) - plane)) <= 1e-12
+    e0 = out["trajectory"][0]
+    assert sorted(e0.keys()) == ["angular_velocity", "frame_id", "is_lost", "planar_direction", "pose", "time_usec"]
+    assert e0["angular_velocity"] == 0 and e0["is_lost"] is False
+    for i, e in enumerate(out["trajectory"]):
+        assert e["frame_id"] == i and e["time_usec"] == int(ts[i])
+        assert np.max(np.abs(np.array(e["planar_direction"]) - dirs[i])) <= 1e-12
+        r = e["pose"]["rotation"]
+        assert np.max(np.abs(np.array([r["w"], r["x"], r["y"], r["z"]]) - q[i])) <= 1e-12
+        assert np.array_equal(np.array(e["pose"]["translation"]), pos[i])
+        if i:
+            assert abs(e["angular_velocity"] - turn[i] / ((ts[i] - ts[i - 1]) * 1e-6 + 1e-10)) <= 1e-8 * max(1.0, abs(e["angular_velocity"]))
+    # a trajectory with real vertical motion is dropped (3rd eigenvalue gate) and nothing is written
+    pos[:, 1] = 5.0 * np.sin(3 * s)
+    poses[:, 2:5] = pos
+    fin.write_text(json.dumps({"poses": [[int(r[0]), int(r[1])] + [float(x) for x in r[2:]] for r in poses]}))
+    fout.unlink()
+    p = run(host_bins, "trajectory_selftest", str(fin), str(sigma), str(fout))
+    assert p.returncode == 3 and "3rd eigenvalue was too large" in p.stderr and not fout.exists()
+
+
+def test_optical_trajectories_flags(host_bins):
+    p = run(host_bins, "optical_trajectories")
+    assert p.returncode == -6 and "Check failed: !vocabulary_file.empty()" in p.stderr
+    p = run(host_bins, "optical_trajectories", "--vocabulary_file=v", "--camera_settings=/nonexistent.yml", "--in_video=video.mp4")
+    assert p.returncode == -6 and "raw:<path>:<width>x<height>" in p.stderr
