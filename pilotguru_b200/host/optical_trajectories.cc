@@ -142,8 +142,8 @@ int main(int argc, char** argv) {
       }
     }
     PGB_CALL(pgb_orb_extract(orb, frames.data(), 0, n, width, height, width, frame_bytes, kps.data(), desc.data(), counts.data(), cap));
-    // queries of pair p = keypoints of frame p-1, projected with the constant-velocity guess (TrackWithMotionModel);
-    // the guess is the last resolved flow of the previous batch
+    // queries of pair p = keypoints of frame p-1 projected with the motion guess (TrackWithMotionModel's role); the
+    // guess is zero motion: the th=15 / 30 px windows (times the octave scale) cover ordinary inter-frame flow
     int first = have_prev ? 0 : 1;
     for (int p = first; p < n; p++) {
       const pgb_keypoint* pk = p == 0 ? prev.k.data() : kps.data() + (size_t)(p - 1) * cap;

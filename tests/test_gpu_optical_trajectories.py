@@ -44,7 +44,7 @@ def test_optical_trajectories_binary(tmp_path):
     # the counts the binary reports equal the oracle's on the same frames (extraction + zero-velocity-guess matching)
     orc = O.OrbOracle(500, 1.2, 8, 20, 7)
     feats = [orc.extract(f) for f in frames]
-    sf = orc.tables()[0]
+    sf = orc.tables()["scale"]
     tot_k = sum(len(k) for k, _ in feats); tot_m = 0
     vflow = np.zeros(2, np.float32)
     for t in range(1, n):
