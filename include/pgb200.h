@@ -194,6 +194,15 @@ int pgb_angular_velocities_around_axis(int device, const double* gyro_xyz, size_
 int pgb_smooth_time_series(int device, const double* values, const double* times, int64_t n,
                            const double* target_times, int64_t n_target, double sigma, double* out);
 
+/* annotate_frames' per-frame labels (src/annotate_frames.cc:59-72): TimeSeries<double>::TimeAveragedValue
+ * (include/interpolation/time_series.hpp:129-189) of the series (values, times_usec)[n] over every frame interval
+ * (frame_times_usec[i-1], frame_times_usec[i]], i = 1..n_frames-1.  out_values/out_valid have n_frames-1 entries;
+ * out_valid[i-1] = 0 where the series does not cover the interval (is_valid = false; the value is NaN).  Host arrays,
+ * device compute.  Frame timestamps must be strictly increasing (CHECK_GT(end, start)); an interval ending at or
+ * after the last event fails like the reference's CHECK in LinearInterpolate (PGB_ERR_INVALID). */
+int pgb_time_averaged_values(int device, const double* values, const int64_t* times_usec, int64_t n,
+                             const int64_t* frame_times_usec, int64_t n_frames, double* out_values, uint8_t* out_valid);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,8 @@ void pgo_pca3(const double* rows, int64_t n, double* eigvec9, double* eigval3, d
 int64_t pgo_principal_rotation_axes(const double* gyro_xyz, const int64_t* gyro_t, int64_t n, int64_t interval_usec,
                                     double* axes9, double* rows_out, int64_t cap);
 void pgo_angular_velocities_around_axis(const double* gyro_xyz, int64_t n, const double* axis, double* out);
+int pgo_time_averaged_values(const double* values, const int64_t* times, int64_t n, const int64_t* ft, int64_t n_frames,
+                             double* out, uint8_t* valid);
 double pgo_bench_extract_match(const uint8_t* frames, int n, int w, int h, const float* flow_xy, int nfeatures,
                                float scale, int nlevels, int iniTh, int minTh, float th, int nthreads,
                                int64_t* total_kps, int64_t* total_matches);

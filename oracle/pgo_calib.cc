@@ -710,6 +710,57 @@ void pgo_angular_velocities_around_axis(const double* gyro_xyz, int64_t n, const
     out[i] = (gyro_xyz[3 * i] * axis[0] + gyro_xyz[3 * i + 1] * axis[1] + gyro_xyz[3 * i + 2] * axis[2]) / nrm;
 }
 
+// annotate_frames.cc:59-72 over TimeSeries<double>::TimeAveragedValue / MostRecentPreviousValue / LinearInterpolate
+// (include/interpolation/time_series.hpp:103-225), literal including the forward scans from the hint.  Returns 0,
+// or -1 where the reference would CHECK-fail.  out/valid have n_frames-1 entries.
+int pgo_time_averaged_values(const double* values, const int64_t* times, int64_t n, const int64_t* ft, int64_t n_frames,
+                             double* out, uint8_t* valid) {
+  if (n <= 0) return -1;
+  auto interval_sec = [](int64_t a, int64_t b) { return (double)(b - a) * 1e-6; };
+  struct R { double value; bool ok; int64_t end; };
+  auto most_recent = [&](int64_t q, int64_t hint, bool* fatal) -> R {
+    if (hint >= n) { *fatal = true; return {0, false, 0}; }
+    if (times[0] > q) return {std::numeric_limits<double>::quiet_NaN(), false, 0};
+    if (!(times[hint] <= q)) { *fatal = true; return {0, false, 0}; }
+    int64_t next = hint;
+    while (next < n && times[next] <= q) ++next;
+    return {values[next - 1], true, next - 1};
+  };
+  auto lerp = [&](int64_t l, int64_t r, int64_t q, bool* fatal) -> double {
+    if (!(l < r) || !(r < n) || !(times[l] <= q) || !(q <= times[r])) { *fatal = true; return 0; }
+    const double lt = interval_sec(times[l], q), rt = interval_sec(q, times[r]), tt = interval_sec(times[l], times[r]);
+    return (lt / tt) * values[r] + (rt / tt) * values[l];
+  };
+  R ann{0, false, 0};
+  for (int64_t i = 1; i < n_frames; i++) {
+    const int64_t start = ft[i - 1], end = ft[i];
+    bool fatal = false;
+    if (!(end > start)) return -1;
+    if (start < times[0] || end > times[n - 1]) {
+      ann = {std::numeric_limits<double>::quiet_NaN(), false, 0};
+    } else {
+      const R se = most_recent(start, ann.end, &fatal);
+      if (fatal || !se.ok) return -1;
+      const R ee = most_recent(end, se.end, &fatal);
+      if (fatal || !ee.ok) return -1;
+      double total = 0;
+      for (int64_t k = se.end + 1; k < ee.end; ++k) total += (interval_sec(times[k], times[k + 1]) * 0.5 * (values[k] + values[k + 1]));
+      const double lv = lerp(se.end, se.end + 1, start, &fatal), rv = lerp(ee.end, ee.end + 1, end, &fatal);
+      if (fatal) return -1;
+      if (se.end == ee.end) {
+        total += (lv + rv) * 0.5 * interval_sec(start, end);
+      } else {
+        total += (lv + values[se.end + 1]) * 0.5 * interval_sec(start, times[se.end + 1]);
+        total += (values[ee.end] + rv) * 0.5 * interval_sec(times[ee.end], end);
+      }
+      ann = {total / interval_sec(start, end), true, ee.end};
+    }
+    out[i - 1] = ann.value;
+    valid[i - 1] = ann.ok ? 1 : 0;
+  }
+  return 0;
+}
+
 }  // extern "C"
 
 extern "C" void pgo_det_sincos(double x, double* s, double* c) { pgbimu::det_sincos(x, s, c); }

@@ -71,6 +71,7 @@ _SIGS = {
                                           vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp]),
     "pgb_principal_rotation_axes": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int64, vp, vp]),
     "pgb_angular_velocities_around_axis": (C.c_int, [C.c_int, vp, C.c_size_t, vp, vp]),
+    "pgb_time_averaged_values": (C.c_int, [C.c_int, vp, vp, C.c_int64, vp, C.c_int64, vp, vp]),
     "pgb_smooth_time_series": (C.c_int, [C.c_int, vp, vp, C.c_int64, vp, C.c_int64, C.c_double, vp]),
 }
 

@@ -99,6 +99,15 @@ def smooth_time_series(values, times, target_times, sigma: float, device: int = 
     return out
 
 
+def time_averaged_values(values, times_usec, frame_times_usec, device: int = 0):
+    """annotate_frames.cc:59-72 over TimeSeries::TimeAveragedValue (time_series.hpp:129-189): (values, valid) for
+    frames 1..n-1, each averaged over (t[i-1], t[i]]."""
+    v, t, ft = _f64(values), _i64(times_usec), _i64(frame_times_usec)
+    out = np.full(max(len(ft) - 1, 0), np.nan); ok = np.zeros(max(len(ft) - 1, 0), np.uint8)
+    check(lib().pgb_time_averaged_values(device, np_ptr(v), np_ptr(t), len(v), np_ptr(ft), len(ft), np_ptr(out), np_ptr(ok)))
+    return out, ok.astype(bool)
+
+
 def num_windows(n_gps: int, shift_step: int) -> int:
     return int(lib().pgb_imu_num_windows(n_gps, shift_step))
 

@@ -253,6 +253,47 @@ __global__ void k_smooth(const double* __restrict__ v, const double* __restrict_
   out[i] = acc;
 }
 
+// TimeSeries<double>::TimeAveragedValue (include/interpolation/time_series.hpp:129-189) for every frame interval
+// (t[i-1], t[i]] of annotate_frames.cc:59-72: one thread per frame; the reference's forward linear scans
+// (MostRecentPreviousValue, :103-125) become bisections for the same index (last event with time <= query).
+// status: 0 = not covered by the series (is_valid = false), 1 = valid, 2 = the reference would CHECK-fail
+// (LinearInterpolate needs an event after the query's end: :210-213).
+__device__ __forceinline__ long long last_not_after(const long long* __restrict__ t, long long n, long long q) {
+  long long lo = 0, hi = n;  // first index with t > q
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (t[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+__device__ __forceinline__ double interval_sec(long long a, long long b) { return (double)(b - a) * 1e-6; }
+__device__ __forceinline__ double lerp_at(const double* __restrict__ v, const long long* __restrict__ t, long long l,
+                                          long long r, long long q) {
+  const double left = interval_sec(t[l], q), right = interval_sec(q, t[r]), total = interval_sec(t[l], t[r]);
+  return (left / total) * v[r] + (right / total) * v[l];
+}
+__global__ void k_time_average(const double* __restrict__ v, const long long* __restrict__ t, long long n,
+                               const long long* __restrict__ ft, long long nFrames, double* __restrict__ out,
+                               unsigned char* __restrict__ status) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (i >= nFrames) return;
+  const long long start = ft[i - 1], end = ft[i];
+  if (start < t[0] || end > t[n - 1]) { out[i - 1] = nan(""); status[i - 1] = 0; return; }
+  const long long si = last_not_after(t, n, start), ei = last_not_after(t, n, end);
+  if (ei + 1 >= n || si + 1 >= n) { out[i - 1] = nan(""); status[i - 1] = 2; return; }
+  double total = 0.0;
+  for (long long k = si + 1; k < ei; k++) total += (interval_sec(t[k], t[k + 1]) * 0.5 * (v[k] + v[k + 1]));
+  const double lv = lerp_at(v, t, si, si + 1, start), rv = lerp_at(v, t, ei, ei + 1, end);
+  if (si == ei) {
+    total += (lv + rv) * 0.5 * interval_sec(start, end);
+  } else {
+    total += (lv + v[si + 1]) * 0.5 * interval_sec(start, t[si + 1]);
+    total += (v[ei] + rv) * 0.5 * interval_sec(t[ei], end);
+  }
+  out[i - 1] = total / interval_sec(start, end);
+  status[i - 1] = 1;
+}
+
 }  // namespace pgb
 
 using namespace pgb;
@@ -786,6 +827,36 @@ int pgb_angular_velocities_around_axis(int device, const double* gyro_xyz, size_
   k_axis_project<<<(unsigned)((n + 255) / 256), 256>>>((long long)n, dG.p, axis[0], axis[1], axis[2], norm, dOut.p);
   PGB_CHECK_LAUNCH();
   PGB_CUDA(cudaMemcpy(out, dOut.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}
+
+int pgb_time_averaged_values(int device, const double* values, const int64_t* times_usec, int64_t n,
+                             const int64_t* frame_times_usec, int64_t n_frames, double* out_values, uint8_t* out_valid) {
+  if (n <= 0 || !values || !times_usec) return fail(PGB_ERR_INVALID, "empty time series");  // CHECK_LT(hint, size)
+  if (n_frames < 0 || (n_frames > 0 && (!frame_times_usec || (n_frames > 1 && (!out_values || !out_valid)))))
+    return fail(PGB_ERR_INVALID, "pgb_time_averaged_values: invalid argument");
+  if (n_frames < 2) return PGB_OK;
+  for (int64_t i = 1; i < n_frames; i++)
+    if (!(frame_times_usec[i] > frame_times_usec[i - 1]))
+      return fail(PGB_ERR_INVALID, "frame timestamps must be strictly increasing (frame %lld)", (long long)i);  // CHECK_GT(end, start)
+  for (int64_t i = 1; i < n; i++)
+    if (times_usec[i] < times_usec[i - 1]) return fail(PGB_ERR_INVALID, "series timestamps must be non-decreasing");
+  if (use_device(device)) return PGB_ERR_CUDA;
+  DevBuf<double> dv, dout;
+  DevBuf<long long> dt, dft;
+  DevBuf<unsigned char> dst;
+  if (dv.alloc(n) || dt.alloc(n) || dft.alloc(n_frames) || dout.alloc(n_frames - 1) || dst.alloc(n_frames - 1)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemcpy(dv.p, values, n * sizeof(double), cudaMemcpyHostToDevice));
+  PGB_CUDA(cudaMemcpy(dt.p, times_usec, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+  PGB_CUDA(cudaMemcpy(dft.p, frame_times_usec, n_frames * sizeof(int64_t), cudaMemcpyHostToDevice));
+  k_time_average<<<(unsigned)((n_frames - 1 + 127) / 128), 128>>>(dv.p, dt.p, n, dft.p, n_frames, dout.p, dst.p);
+  PGB_CHECK_LAUNCH();
+  PGB_CUDA(cudaMemcpy(out_values, dout.p, (n_frames - 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  PGB_CUDA(cudaMemcpy(out_valid, dst.p, n_frames - 1, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i + 1 < n_frames; i++)
+    if (out_valid[i] == 2)
+      return fail(PGB_ERR_INVALID, "frame %lld ends at or after the last event of the series: the reference's LinearInterpolate CHECK fails "
+                  "(time_series.hpp:210-213)", (long long)(i + 1));
   return PGB_OK;
 }
 

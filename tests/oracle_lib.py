@@ -343,3 +343,15 @@ def angular_velocities_around_axis(gyro, axis):
     g = np.ascontiguousarray(gyro, np.float64); a = np.ascontiguousarray(axis, np.float64); out = np.empty(len(g))
     lib().pgo_angular_velocities_around_axis(ptr(g, f64p), C.c_int64(len(g)), ptr(a, f64p), ptr(out, f64p))
     return out
+
+
+def time_averaged_values(values, times_usec, frame_times_usec):
+    """annotate_frames.cc:59-72 (TimeAveragedValue per frame interval), literal: (values, valid)."""
+    v = np.ascontiguousarray(values, np.float64); t = np.ascontiguousarray(times_usec, np.int64)
+    ft = np.ascontiguousarray(frame_times_usec, np.int64)
+    out = np.full(max(len(ft) - 1, 0), np.nan); ok = np.zeros(max(len(ft) - 1, 0), np.uint8)
+    rc = lib().pgo_time_averaged_values(ptr(v, f64p), ptr(t, i64p), C.c_int64(len(v)), ptr(ft, i64p), C.c_int64(len(ft)),
+                                        ptr(out, f64p), ptr(ok, u8p))
+    if rc:
+        raise ValueError("the reference would CHECK-fail on this input")
+    return out, ok.astype(bool)

@@ -85,3 +85,33 @@ def test_fit_motion_binary_end_to_end(tmp_path):
     f = s - oaxes[0] * oaxes[0].dot(s); f /= np.sqrt((f * f).sum()) + 1e-5
     assert used > 0 and np.max(np.abs(np.array([fw["x"], fw["y"], fw["z"]]) - f)) <= 1e-6
     assert fw["x"] > 0.9
+
+
+def test_time_averaged_values_and_annotate_frames_binary(tmp_path):
+    from pilotguru_b200 import calibration as cal
+    rng = np.random.default_rng(4)
+    t = np.cumsum(rng.integers(1500, 2500, 20000)).astype(np.int64) + 1_000_000
+    v = np.sin(t * 2e-6) * 5 + rng.normal(0, 0.2, len(t))
+    ft = (np.arange(0, 1300) * 33_333 + 600_000).astype(np.int64)
+    out, ok = cal.time_averaged_values(v, t, ft)
+    oout, ook = O.time_averaged_values(v, t, ft)
+    assert np.array_equal(ok, ook) and ok.any() and (~ok).any()
+    assert np.array_equal(out[ok], oout[ok])                               # same fp64 operations in the same order
+    with pytest.raises(Exception):
+        cal.time_averaged_values(v, t, np.array([t[5], int(t[-1])], np.int64))   # the reference's CHECK
+    # the binary: smoothing + annotation, frame ids and values
+    subprocess.run(["make", "-C", os.path.join(ROOT, "pilotguru_b200", "host")], check=True, capture_output=True)
+    fj, sj, oj = tmp_path / "frames.json", tmp_path / "velocities.json", tmp_path / "out.json"
+    fj.write_text(json.dumps({"frames": [{"frame_id": int(i), "time_usec": int(x)} for i, x in enumerate(ft)]}))
+    sj.write_text(json.dumps({"velocities": [{"speed_m_s": float(a), "time_usec": int(b)} for a, b in zip(v, t)]}))
+    p = subprocess.run([os.path.join(ROOT, "pilotguru_b200", "host", "annotate_frames"), "--frames_json", str(fj), "--in_json", str(sj),
+                        "--json_root_element_name=velocities", "--json_value_name=speed_m_s", "--out_json", str(oj),
+                        "--smoothing_sigma=0.01"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    res = json.load(open(oj))["velocities"]
+    ts = (t - t[0]) * 1e-6
+    sm = O.smooth_time_series(v, ts, ts, 0.01)
+    want, wok = O.time_averaged_values(sm, t, ft)
+    assert [e["frame_id"] for e in res] == (np.nonzero(wok)[0] + 1).tolist()
+    got = np.array([e["speed_m_s"] for e in res])
+    assert np.max(np.abs(got - want[wok])) <= 1e-12 * np.max(np.abs(want[wok]))
