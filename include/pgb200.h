@@ -133,6 +133,30 @@ int pgb_match_consecutive(pgb_matcher*, int n_pairs, int cap, const pgb_keypoint
                           const int32_t* counts, const float* flow, float max_x, float max_y, float th,
                           const float* scale_factors, int nlevels, int32_t* match_of_cur, int32_t* n_matches);
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:407-522) for
+ * n_pairs independent frame pairs: level-0 keypoints of F1 search a +-window_size window around prev_matched_xy in
+ * F2 (level 0 only), TH_LOW = 50, the ratio test with the matcher's nnratio, stealing of already matched targets by
+ * closer queries, and the rotation-histogram filter.  prev_matched_xy[pair][cap][2] is updated in place for matched
+ * keypoints (:517-519); matches12[pair][cap] = index in F2 or -1; n_matches[pair] = the return value.
+ * More than 96 candidates in one window -> PGB_ERR_CAPACITY. */
+int pgb_match_for_initialization(pgb_matcher*, int n_pairs, int cap, const pgb_keypoint* kps1, const uint8_t* desc1,
+                                 const int32_t* counts1, const pgb_keypoint* kps2, const uint8_t* desc2,
+                                 const int32_t* counts2, float* prev_matched_xy, int window_size, float min_x, float max_x,
+                                 float min_y, float max_y, int32_t* matches12, int32_t* n_matches, int is_device);
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:46-131; Tracking::SearchLocalPoints)
+ * for n_frames independent frames.  Per map point (arrays [frame][cap]): projection proj_xy (mTrackProjX/Y), predicted
+ * level (mnTrackScaleLevel), viewing cosine (mTrackViewCos -> RadiusByViewingCos, :133-139), descriptor, in_view
+ * (mbTrackInView && !isBad()), mp_observed (Observations() > 0).  has_map_point[frame][cap]: the feature already holds
+ * a map point with observations (skipped, :85-87).  match_of_feature[frame][cap] = index of the map point this call
+ * assigned to the feature, else -1; n_matches[frame] = the return value.  Mono only (mvuRight < 0). */
+int pgb_match_map_points(pgb_matcher*, int n_frames, int cap, const pgb_keypoint* kps, const uint8_t* desc,
+                         const int32_t* counts, const uint8_t* has_map_point, const float* proj_xy,
+                         const int32_t* track_level, const float* view_cos, const uint8_t* mp_desc, const uint8_t* in_view,
+                         const uint8_t* mp_observed, const int32_t* mp_counts, float min_x, float max_x, float min_y,
+                         float max_y, float th, const float* scale_factors, int nlevels, int32_t* match_of_feature,
+                         int32_t* n_matches, int is_device);
+
 /* ------------------------------------------------------------------ IMU + GPS calibration ------------------ */
 typedef struct pgb_imu pgb_imu;
 

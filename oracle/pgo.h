@@ -35,6 +35,13 @@ int pgo_search_by_projection(const pgb_keypoint* cur_kps, const uint8_t* cur_des
                              const uint8_t* q_valid, int n_q, float minX, float maxX, float minY, float maxY, float th,
                              const float* scale_factors, int nlevels, int check_ori, int32_t* match_of_cur,
                              int32_t* best_dist_of_q);
+int pgo_search_for_initialization(const pgb_keypoint* k1, const uint8_t* d1, int n1, const pgb_keypoint* k2,
+                                  const uint8_t* d2, int n2, float* prev_matched, int windowSize, float minX, float maxX,
+                                  float minY, float maxY, float nnratio, int check_ori, int32_t* vnMatches12);
+int pgo_search_map_points(const pgb_keypoint* kps, const uint8_t* desc, int n, const uint8_t* has_map_point,
+                          const float* proj_xy, const int32_t* track_level, const float* view_cos, const uint8_t* mp_desc,
+                          const uint8_t* in_view, const uint8_t* mp_observed, int n_mp, float minX, float maxX, float minY,
+                          float maxY, float th, const float* scale_factors, float nnratio, int32_t* match_of_feature);
 int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
                           float maxX, float maxY, float th, const float* scale_factors, int nlevels,

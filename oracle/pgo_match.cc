@@ -143,6 +143,139 @@ int pgo_search_by_projection(const pgb_keypoint* cur_kps, const uint8_t* cur_des
 
 // The synthetic benchmark's match stage: previous frame's keypoints are the map points, projected
 // by the known flow; retry at 2*th when fewer than 20 matches (Tracking.cc:876-883).
+namespace {
+// Frame::AssignFeaturesToGrid + GetFeaturesInArea (Frame.cc:234-249, 331-384), shared by the flavours below.
+struct FrameGrid {
+  std::vector<int> cell[GRID_COLS][GRID_ROWS];
+  float minX, minY, invW, invH;
+  const pgb_keypoint* kps;
+  FrameGrid(const pgb_keypoint* k, int n, float mnX, float mxX, float mnY, float mxY) : minX(mnX), minY(mnY), kps(k) {
+    invW = (float)GRID_COLS / (mxX - mnX);
+    invH = (float)GRID_ROWS / (mxY - mnY);
+    for (int i = 0; i < n; i++) {
+      const int posX = (int)std::round((k[i].x - minX) * invW), posY = (int)std::round((k[i].y - minY) * invH);
+      if (posX < 0 || posX >= GRID_COLS || posY < 0 || posY >= GRID_ROWS) continue;
+      cell[posX][posY].push_back(i);
+    }
+  }
+  std::vector<size_t> in_area(float x, float y, float r, int minLevel, int maxLevel) const {
+    std::vector<size_t> out;
+    const int nMinCellX = std::max(0, (int)std::floor((x - minX - r) * invW));
+    if (nMinCellX >= GRID_COLS) return out;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + r) * invW));
+    if (nMaxCellX < 0) return out;
+    const int nMinCellY = std::max(0, (int)std::floor((y - minY - r) * invH));
+    if (nMinCellY >= GRID_ROWS) return out;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+    if (nMaxCellY < 0) return out;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+      for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+        for (int idx : cell[ix][iy]) {
+          const pgb_keypoint& kp = kps[idx];
+          if (bCheckLevels) {
+            if (kp.octave < minLevel) continue;
+            if (maxLevel >= 0)
+              if (kp.octave > maxLevel) continue;
+          }
+          const float distx = kp.x - x, disty = kp.y - y;
+          if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+        }
+    return out;
+  }
+};
+const int TH_LOW = 50;
+}  // namespace
+
+// ORBmatcher::SearchForInitialization (ORBmatcher.cc:407-522), literal.  prev_matched is updated in place.
+int pgo_search_for_initialization(const pgb_keypoint* k1, const uint8_t* d1, int n1, const pgb_keypoint* k2,
+                                  const uint8_t* d2, int n2, float* prev_matched, int windowSize, float minX, float maxX,
+                                  float minY, float maxY, float nnratio, int check_ori, int32_t* vnMatches12) {
+  int nmatches = 0;
+  for (int i = 0; i < n1; i++) vnMatches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  std::vector<int> vMatchedDistance(n2, INT32_MAX), vnMatches21(n2, -1);
+  const FrameGrid F2(k2, n2, minX, maxX, minY, maxY);
+  for (int i1 = 0; i1 < n1; i1++) {
+    const int level1 = k1[i1].octave;
+    if (level1 > 0) continue;
+    const std::vector<size_t> vIndices2 = F2.in_area(prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)windowSize, level1, level1);
+    if (vIndices2.empty()) continue;
+    int bestDist = INT32_MAX, bestDist2 = INT32_MAX, bestIdx2 = -1;
+    for (size_t i2 : vIndices2) {
+      const int dist = descriptor_distance(d1 + (size_t)i1 * 32, d2 + i2 * 32);
+      if (vMatchedDistance[i2] <= dist) continue;
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = (int)i2; }
+      else if (dist < bestDist2) { bestDist2 = dist; }
+    }
+    if (bestDist <= TH_LOW) {
+      if (bestDist < (float)bestDist2 * nnratio) {
+        if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+        vnMatches12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        nmatches++;
+        if (check_ori) {
+          float rot = k1[i1].angle - k2[bestIdx2].angle;
+          if (rot < 0.0) rot += 360.0f;
+          int bin = (int)std::round(rot * factor);
+          if (bin == HISTO_LENGTH) bin = 0;
+          rotHist[bin].push_back(i1);
+        }
+      }
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i])
+        if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+    }
+  }
+  for (int i1 = 0; i1 < n1; i1++)
+    if (vnMatches12[i1] >= 0) { prev_matched[2 * i1] = k2[vnMatches12[i1]].x; prev_matched[2 * i1 + 1] = k2[vnMatches12[i1]].y; }
+  return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:46-131), literal, mono.
+// match_of_feature[idx] = index of the map point this call put into F.mvpMapPoints[idx], else -1.
+int pgo_search_map_points(const pgb_keypoint* kps, const uint8_t* desc, int n, const uint8_t* has_map_point,
+                          const float* proj_xy, const int32_t* track_level, const float* view_cos, const uint8_t* mp_desc,
+                          const uint8_t* in_view, const uint8_t* mp_observed, int n_mp, float minX, float maxX, float minY,
+                          float maxY, float th, const float* scale_factors, float nnratio, int32_t* match_of_feature) {
+  int nmatches = 0;
+  const bool bFactor = th != 1.0;
+  const FrameGrid F(kps, n, minX, maxX, minY, maxY);
+  std::vector<uint8_t> observed(has_map_point, has_map_point + n);  // F.mvpMapPoints[idx] && Observations() > 0
+  for (int i = 0; i < n; i++) match_of_feature[i] = -1;
+  for (int iMP = 0; iMP < n_mp; iMP++) {
+    if (!in_view[iMP]) continue;  // !mbTrackInView || isBad()
+    const int nPredictedLevel = track_level[iMP];
+    float r = view_cos[iMP] > 0.998 ? 2.5f : 4.0f;
+    if (bFactor) r *= th;
+    const std::vector<size_t> vIndices = F.in_area(proj_xy[2 * iMP], proj_xy[2 * iMP + 1], r * scale_factors[nPredictedLevel],
+                                                   nPredictedLevel - 1, nPredictedLevel);
+    if (vIndices.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (size_t idx : vIndices) {
+      if (observed[idx]) continue;
+      const int dist = descriptor_distance(mp_desc + (size_t)iMP * 32, desc + idx * 32);
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kps[idx].octave; bestIdx = (int)idx; }
+      else if (dist < bestDist2) { bestLevel2 = kps[idx].octave; bestDist2 = dist; }
+    }
+    if (bestDist <= TH_HIGH) {
+      if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+      match_of_feature[bestIdx] = iMP;
+      observed[bestIdx] = mp_observed[iMP];
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
+
 int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
                           float maxX, float maxY, float th, const float* scale_factors, int nlevels,

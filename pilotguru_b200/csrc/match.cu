@@ -493,6 +493,201 @@ __global__ void __launch_bounds__(kMtThreads) k_match_resolve(MatchArgs A) {
   if (tid == 0) A.nMatches[p] = sNm;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The other windowed searches of ORBmatcher on the same primitive.  Both are sequential in
+// the query index with state carried between queries, and neither is on the per-frame path of the benchmark, so one
+// CTA per problem does: (A) thread per query: every target inside the query's GetFeaturesInArea window (Frame.cc:331-384:
+// cell range, level range, |dx| < r and |dy| < r) with its Hamming distance, appended to the query's row; (B) thread 0
+// replays the reference's loop over the rows.  A candidate's arrival order in the reference (cell x, cell y, index)
+// only matters for ties of the strict '<' comparisons, so (B) compares (distance, cell, index) keys.
+//   flavour 1: SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)      ORBmatcher.cc:407-522
+//   flavour 2: SearchByProjection(Frame&, const vector<MapPoint*>&, th)                      ORBmatcher.cc:46-131
+constexpr int kWinK = 96;       // candidates kept per query; more raises PGB_ERR_CAPACITY (never truncated silently)
+constexpr int kThLow = 50;
+
+struct WinArgs {
+  int flavour, cap, nlevels, checkOri;
+  float minX, maxX, minY, maxY, th, nnratio;
+  float scale[16];
+  const pgb_keypoint* curK;   // [prob][cap] targets (F2 / the frame)
+  const uint8_t* curD;
+  const int* curN;
+  const uint8_t* curTaken;    // flavour 2: the feature already holds a map point with observations
+  const float* qUV;           // [prob][cap][2]   flavour 1: vbPrevMatched, flavour 2: mTrackProjX/Y
+  const int* qLevel;          // flavour 1: octave of the F1 keypoint, flavour 2: mnTrackScaleLevel
+  const float* qAux;          // flavour 1: angle of the F1 keypoint, flavour 2: mTrackViewCos
+  const uint8_t* qD;
+  const uint8_t* qValid;      // flavour 2: mbTrackInView && !isBad()
+  const uint8_t* qObs;        // flavour 2: Observations() > 0 of the map point
+  const int* qN;
+  int* matchOfQ;              // flavour 1: vnMatches12
+  int* matchOfCur;            // flavour 2: index of the map point assigned to each feature by THIS call, else -1
+  float* qUVOut;              // flavour 1: updated vbPrevMatched
+  int* nMatches;
+  uint32_t* rows;             // scratch [prob][cap][kWinK]: target | dist << 16
+  int* rowCnt;                // scratch [prob][cap]
+  int* err;
+};
+
+__global__ void __launch_bounds__(kMtThreads) k_match_windowed(WinArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int p = blockIdx.x, tid = threadIdx.x, cap = A.cap;
+  const pgb_keypoint* curK = A.curK + (size_t)p * cap;
+  const uint32_t* curD = reinterpret_cast<const uint32_t*>(A.curD + (size_t)p * cap * 32);
+  const uint32_t* qD = reinterpret_cast<const uint32_t*>(A.qD + (size_t)p * cap * 32);
+  const int nCur = min(A.curN[p], cap), nQ = min(A.qN[p], cap);
+  uint16_t* sCellOf = reinterpret_cast<uint16_t*>(smem);       // [cap] cell (x*48+y) of each target, 0xffff = outside
+  int* sState = reinterpret_cast<int*>(sCellOf + cap + (cap & 1));  // [cap] f1: vMatchedDistance; f2: taken flag
+  int* sM21 = sState + cap;                                    // [cap] f1: vnMatches21; f2: match_of_cur
+  int* sM12 = sM21 + cap;                                      // [cap] f1: vnMatches12
+  signed char* sBin = reinterpret_cast<signed char*>(sM12 + cap);  // [cap] f1: histogram bin the query was pushed to
+  const float invW = (float)kGridCols / (A.maxX - A.minX), invH = (float)kGridRows / (A.maxY - A.minY);
+  uint32_t* rows = A.rows + (size_t)p * cap * kWinK;
+  int* rowCnt = A.rowCnt + (size_t)p * cap;
+
+  for (int t = tid; t < cap; t += kMtThreads) {
+    uint16_t cell = 0xffff;
+    if (t < nCur) {
+      const pgb_keypoint k = curK[t];
+      const int posX = (int)roundf((k.x - A.minX) * invW), posY = (int)roundf((k.y - A.minY) * invH);  // Frame::PosInGrid
+      if (!(posX < 0 || posX >= kGridCols || posY < 0 || posY >= kGridRows)) cell = (uint16_t)(posX * kGridRows + posY);
+    }
+    sCellOf[t] = cell;
+    sState[t] = A.flavour == 1 ? 0x7fffffff : (A.curTaken && t < nCur ? A.curTaken[(size_t)p * cap + t] : 0);
+    sM21[t] = -1; sM12[t] = -1; sBin[t] = -1;
+  }
+  __syncthreads();
+
+  // ---- (A) candidate rows
+  for (int i = tid; i < nQ; i += kMtThreads) {
+    const size_t o = (size_t)p * cap + i;
+    int cnt = 0;
+    const int level = A.qLevel[o];
+    bool ok = A.flavour == 1 ? (level <= 0) : (A.qValid[o] != 0);          // "if(level1>0) continue" / mbTrackInView, isBad
+    float r = A.th;                                                        // flavour 1: windowSize
+    int o0 = 0, o1 = 0;
+    if (A.flavour == 2) {
+      if (level < 0 || level >= A.nlevels) ok = false;
+      float rr = A.qAux[o] > 0.998f ? 2.5f : 4.0f;                         // RadiusByViewingCos
+      if (A.th != 1.0f) rr *= A.th;
+      r = ok ? rr * A.scale[level] : 0.f;
+      o0 = level - 1; o1 = level;
+    }
+    if (ok) {
+      const float u = A.qUV[2 * o], v = A.qUV[2 * o + 1];
+      // GetFeaturesInArea's cell range with its four early exits (Frame.cc:336-350)
+      const int cx0 = max(0, (int)floorf((u - A.minX - r) * invW)), cx1 = min(kGridCols - 1, (int)ceilf((u - A.minX + r) * invW));
+      const int cy0 = max(0, (int)floorf((v - A.minY - r) * invH)), cy1 = min(kGridRows - 1, (int)ceilf((v - A.minY + r) * invH));
+      if (!(cx0 >= kGridCols || cx1 < 0 || cy0 >= kGridRows || cy1 < 0)) {
+        uint32_t qd[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) qd[w] = qD[(size_t)i * 8 + w];
+        for (int t = 0; t < nCur; t++) {
+          const int cell = sCellOf[t];
+          if (cell == 0xffff) continue;
+          const int px = cell / kGridRows, py = cell - px * kGridRows;
+          if (px < cx0 || px > cx1 || py < cy0 || py > cy1) continue;
+          const pgb_keypoint k = curK[t];
+          if (k.octave < o0 || k.octave > o1) continue;
+          if (!(fabsf(k.x - u) < r && fabsf(k.y - v) < r)) continue;
+          const int d = hamming256(qd, curD + (size_t)t * 8);
+          if (cnt < kWinK) rows[(size_t)i * kWinK + cnt] = (uint32_t)t | ((uint32_t)d << 16);
+          cnt++;
+        }
+      }
+    }
+    rowCnt[i] = cnt;
+    if (cnt > kWinK) atomicOr(A.err, 1);
+  }
+  __syncthreads();
+  if (tid != 0) return;
+
+  // ---- (B) sequential replay
+  int nm = 0;
+  auto key_of = [&](uint32_t e) -> unsigned long long {  // (distance, arrival order = cell then index)
+    const int t = e & 0xffff;
+    return ((unsigned long long)(e >> 16) << 40) | ((unsigned long long)sCellOf[t] << 20) | (unsigned)t;
+  };
+  if (A.flavour == 1) {
+    int hist[kHisto];
+    for (int b = 0; b < kHisto; b++) hist[b] = 0;
+    const float factor = 1.0f / kHisto;
+    for (int i = 0; i < nQ; i++) {
+      const int cnt = min(rowCnt[i], kWinK);
+      unsigned long long best = ~0ull, best2 = ~0ull;
+      for (int c = 0; c < cnt; c++) {
+        const uint32_t e = rows[(size_t)i * kWinK + c];
+        if (sState[e & 0xffff] <= (int)(e >> 16)) continue;            // vMatchedDistance[i2] <= dist
+        const unsigned long long k = key_of(e);
+        if (k < best) { best2 = best; best = k; } else if (k < best2) best2 = k;
+      }
+      if (best == ~0ull) continue;
+      const int bestDist = (int)(best >> 40), bestIdx2 = (int)(best & 0xfffff);
+      const int bestDist2 = best2 == ~0ull ? 0x7fffffff : (int)(best2 >> 40);
+      if (bestDist <= kThLow && (float)bestDist < (float)bestDist2 * A.nnratio) {
+        if (sM21[bestIdx2] >= 0) { sM12[sM21[bestIdx2]] = -1; nm--; }
+        sM12[i] = bestIdx2; sM21[bestIdx2] = i; sState[bestIdx2] = bestDist; nm++;
+        if (A.checkOri) {
+          float rot = A.qAux[(size_t)p * cap + i] - curK[bestIdx2].angle;
+          if (rot < 0.0f) rot += 360.0f;
+          int bin = (int)roundf(rot * factor);
+          if (bin == kHisto) bin = 0;
+          sBin[i] = (signed char)bin;   // a query is pushed to rotHist at most once
+          hist[bin]++;
+        }
+      }
+    }
+    if (A.checkOri) {
+      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+      for (int b = 0; b < kHisto; b++) {
+        const int s = hist[b];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+        else if (s > max3) { max3 = s; ind3 = b; }
+      }
+      if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+      for (int i = 0; i < nQ; i++) {
+        const int b = sBin[i];
+        if (b < 0 || b == ind1 || b == ind2 || b == ind3) continue;
+        if (sM12[i] >= 0) { sM12[i] = -1; nm--; }
+      }
+    }
+    for (int i = 0; i < cap; i++) {
+      const size_t o = (size_t)p * cap + i;
+      A.matchOfQ[o] = i < nQ ? sM12[i] : -1;
+      if (i < nQ) {  // "Update prev matched"
+        const bool m = sM12[i] >= 0;
+        A.qUVOut[2 * o] = m ? curK[sM12[i]].x : A.qUV[2 * o];
+        A.qUVOut[2 * o + 1] = m ? curK[sM12[i]].y : A.qUV[2 * o + 1];
+      }
+    }
+  } else {
+    for (int i = 0; i < nQ; i++) {
+      const int cnt = min(rowCnt[i], kWinK);
+      unsigned long long best = ~0ull, best2 = ~0ull;
+      for (int c = 0; c < cnt; c++) {
+        const uint32_t e = rows[(size_t)i * kWinK + c];
+        if (sState[e & 0xffff]) continue;                               // F.mvpMapPoints[idx] with Observations() > 0
+        const unsigned long long k = key_of(e);
+        if (k < best) { best2 = best; best = k; } else if (k < best2) best2 = k;
+      }
+      if (best == ~0ull) continue;
+      const int bestDist = (int)(best >> 40), bestIdx = (int)(best & 0xfffff);
+      if (bestDist > kThHigh) continue;
+      if (best2 != ~0ull) {
+        const int bestDist2 = (int)(best2 >> 40), idx2 = (int)(best2 & 0xfffff);
+        if (curK[bestIdx].octave == curK[idx2].octave && (float)bestDist > A.nnratio * (float)bestDist2) continue;
+      }
+      sM21[bestIdx] = i;
+      sState[bestIdx] = A.qObs[(size_t)p * cap + i] ? 1 : 0;
+      nm++;
+    }
+    for (int t = 0; t < cap; t++) A.matchOfCur[(size_t)p * cap + t] = t < nCur ? sM21[t] : -1;
+  }
+  A.nMatches[p] = nm;
+}
+
 size_t match_smem_bytes(int cap) {
   size_t b = (size_t)cap * 8 * 4 + (size_t)cap * 5 * 4;        // desc, x, y, meta, angle, bin
   b += (size_t)(cap + (cap & 1)) * 2;                           // cell-sorted order
@@ -701,6 +896,153 @@ int pgb_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* 
   PGB_CHECK_LAUNCH();
   PGB_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
   PGB_CUDA(cudaStreamSynchronize(s));
+  return PGB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// host->device staging of one input array (or pass-through when the caller's buffers are device-resident)
+template <typename T>
+int stage_in(DevBuf<T>& d, const T*& ptr, size_t n, bool is_device, cudaStream_t s) {
+  if (is_device || !ptr) return PGB_OK;
+  if (d.alloc(n)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemcpyAsync(d.p, ptr, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  ptr = d.p;
+  return PGB_OK;
+}
+
+int run_windowed(pgb_matcher* m, WinArgs& A, int nProb) {
+  DevBuf<uint32_t> rows;
+  DevBuf<int> cnt, err;
+  const size_t n = (size_t)nProb * A.cap;
+  if (rows.alloc(n * kWinK) || cnt.alloc(n) || err.alloc(1)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), m->stream));
+  A.rows = rows.p; A.rowCnt = cnt.p; A.err = err.p;
+  const size_t smem = (size_t)A.cap * 16 + 64;
+  if (smem > 227 * 1024) return fail(PGB_ERR_CAPACITY, "cap %d needs %zu B of shared memory (max 227 KB)", A.cap, smem);
+  if (smem > 48 * 1024) PGB_CUDA(cudaFuncSetAttribute(k_match_windowed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_match_windowed<<<nProb, kMtThreads, smem, m->stream>>>(A);
+  PGB_CHECK_LAUNCH();
+  int e = 0;
+  PGB_CUDA(cudaMemcpyAsync(&e, err.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  PGB_CUDA(cudaStreamSynchronize(m->stream));
+  if (e) return fail(PGB_ERR_CAPACITY, "a search window holds more than %d candidates", kWinK);
+  return PGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgb_match_for_initialization(pgb_matcher* m, int n_pairs, int cap, const pgb_keypoint* kps1, const uint8_t* desc1,
+                                 const int32_t* counts1, const pgb_keypoint* kps2, const uint8_t* desc2,
+                                 const int32_t* counts2, float* prev_matched_xy, int window_size, float min_x, float max_x,
+                                 float min_y, float max_y, int32_t* matches12, int32_t* n_matches, int is_device) {
+  if (!m) return fail(PGB_ERR_INVALID, "null handle");
+  if (n_pairs < 0 || cap <= 0 || cap > 65535 || window_size <= 0 || !(max_x > min_x) || !(max_y > min_y))
+    return fail(PGB_ERR_INVALID, "pgb_match_for_initialization: invalid argument");
+  if (n_pairs == 0) return PGB_OK;
+  if (!kps1 || !desc1 || !counts1 || !kps2 || !desc2 || !counts2 || !prev_matched_xy || !matches12 || !n_matches)
+    return fail(PGB_ERR_INVALID, "pgb_match_for_initialization: null buffer");
+  PGB_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const size_t n = (size_t)n_pairs * cap;
+  // the kernel wants the F1 keypoints as separate level / angle arrays
+  std::vector<pgb_keypoint> hk1;
+  DevBuf<pgb_keypoint> dk1tmp;
+  const pgb_keypoint* k1host = kps1;
+  if (is_device) {
+    hk1.resize(n);
+    PGB_CUDA(cudaMemcpyAsync(hk1.data(), kps1, n * sizeof(pgb_keypoint), cudaMemcpyDeviceToHost, s));
+    PGB_CUDA(cudaStreamSynchronize(s));
+    k1host = hk1.data();
+  }
+  std::vector<int> lvl(n);
+  std::vector<float> ang(n);
+  for (size_t i = 0; i < n; i++) { lvl[i] = k1host[i].octave; ang[i] = k1host[i].angle; }
+  DevBuf<int> dLvl, dN1, dN2, dM12, dNm;
+  DevBuf<float> dAng, dUV, dUVOut;
+  DevBuf<pgb_keypoint> dK2;
+  DevBuf<uint8_t> dD1, dD2;
+  if (dLvl.alloc(n) || dAng.alloc(n) || dUVOut.alloc(2 * n)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemcpyAsync(dLvl.p, lvl.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+  PGB_CUDA(cudaMemcpyAsync(dAng.p, ang.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
+  const float* uv = prev_matched_xy;
+  int rc = stage_in(dK2, kps2, n, is_device, s) | stage_in(dD1, desc1, n * 32, is_device, s) | stage_in(dD2, desc2, n * 32, is_device, s) |
+           stage_in(dN1, counts1, n_pairs, is_device, s) | stage_in(dN2, counts2, n_pairs, is_device, s) | stage_in(dUV, uv, 2 * n, is_device, s);
+  if (rc) return PGB_ERR_CUDA;
+  int* dm12 = matches12;
+  int* dnm = n_matches;
+  if (!is_device) {
+    if (dM12.alloc(n) || dNm.alloc(n_pairs)) return PGB_ERR_CUDA;
+    dm12 = dM12.p; dnm = dNm.p;
+  }
+  WinArgs A;
+  memset(&A, 0, sizeof A);
+  A.flavour = 1; A.cap = cap; A.nlevels = 1; A.checkOri = m->checkOri; A.nnratio = m->nnratio;
+  A.minX = min_x; A.maxX = max_x; A.minY = min_y; A.maxY = max_y; A.th = (float)window_size;
+  A.curK = kps2; A.curD = desc2; A.curN = counts2; A.qUV = uv; A.qLevel = dLvl.p; A.qAux = dAng.p; A.qD = desc1; A.qN = counts1;
+  A.matchOfQ = dm12; A.qUVOut = dUVOut.p; A.nMatches = dnm;
+  rc = run_windowed(m, A, n_pairs);
+  if (rc) return rc;
+  PGB_CUDA(cudaMemcpyAsync(prev_matched_xy, dUVOut.p, 2 * n * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  if (!is_device) {
+    PGB_CUDA(cudaMemcpyAsync(matches12, dM12.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PGB_CUDA(cudaMemcpyAsync(n_matches, dNm.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  PGB_CUDA(cudaStreamSynchronize(s));
+  return PGB_OK;
+}
+
+int pgb_match_map_points(pgb_matcher* m, int n_frames, int cap, const pgb_keypoint* kps, const uint8_t* desc,
+                         const int32_t* counts, const uint8_t* has_map_point, const float* proj_xy,
+                         const int32_t* track_level, const float* view_cos, const uint8_t* mp_desc, const uint8_t* in_view,
+                         const uint8_t* mp_observed, const int32_t* mp_counts, float min_x, float max_x, float min_y,
+                         float max_y, float th, const float* scale_factors, int nlevels, int32_t* match_of_feature,
+                         int32_t* n_matches, int is_device) {
+  if (!m) return fail(PGB_ERR_INVALID, "null handle");
+  if (n_frames < 0 || cap <= 0 || cap > 65535 || nlevels <= 0 || nlevels > 16 || !scale_factors || !(max_x > min_x) || !(max_y > min_y))
+    return fail(PGB_ERR_INVALID, "pgb_match_map_points: invalid argument");
+  if (n_frames == 0) return PGB_OK;
+  if (!kps || !desc || !counts || !proj_xy || !track_level || !view_cos || !mp_desc || !in_view || !mp_observed || !mp_counts ||
+      !match_of_feature || !n_matches)
+    return fail(PGB_ERR_INVALID, "pgb_match_map_points: null buffer");
+  PGB_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const size_t n = (size_t)n_frames * cap;
+  DevBuf<pgb_keypoint> dK;
+  DevBuf<uint8_t> dD, dHas, dQD, dView, dObs;
+  DevBuf<float> dUV, dCos;
+  DevBuf<int> dN, dLvl, dQN, dMatch, dNm;
+  int rc = stage_in(dK, kps, n, is_device, s) | stage_in(dD, desc, n * 32, is_device, s) | stage_in(dN, counts, n_frames, is_device, s) |
+           stage_in(dHas, has_map_point, n, is_device, s) | stage_in(dUV, proj_xy, 2 * n, is_device, s) |
+           stage_in(dLvl, track_level, n, is_device, s) | stage_in(dCos, view_cos, n, is_device, s) |
+           stage_in(dQD, mp_desc, n * 32, is_device, s) | stage_in(dView, in_view, n, is_device, s) |
+           stage_in(dObs, mp_observed, n, is_device, s) | stage_in(dQN, mp_counts, n_frames, is_device, s);
+  if (rc) return PGB_ERR_CUDA;
+  int* dmatch = match_of_feature;
+  int* dnm = n_matches;
+  if (!is_device) {
+    if (dMatch.alloc(n) || dNm.alloc(n_frames)) return PGB_ERR_CUDA;
+    dmatch = dMatch.p; dnm = dNm.p;
+  }
+  WinArgs A;
+  memset(&A, 0, sizeof A);
+  A.flavour = 2; A.cap = cap; A.nlevels = nlevels; A.checkOri = 0; A.nnratio = m->nnratio;
+  A.minX = min_x; A.maxX = max_x; A.minY = min_y; A.maxY = max_y; A.th = th;
+  for (int i = 0; i < nlevels; i++) A.scale[i] = scale_factors[i];
+  A.curK = kps; A.curD = desc; A.curN = counts; A.curTaken = has_map_point; A.qUV = proj_xy; A.qLevel = track_level;
+  A.qAux = view_cos; A.qD = mp_desc; A.qValid = in_view; A.qObs = mp_observed; A.qN = mp_counts;
+  A.matchOfCur = dmatch; A.nMatches = dnm;
+  rc = run_windowed(m, A, n_frames);
+  if (rc) return rc;
+  if (!is_device) {
+    PGB_CUDA(cudaMemcpyAsync(match_of_feature, dMatch.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PGB_CUDA(cudaMemcpyAsync(n_matches, dNm.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PGB_CUDA(cudaStreamSynchronize(s));
+  }
   return PGB_OK;
 }
 

@@ -69,6 +69,51 @@ class ORBmatcher:
                                             bounds[2], bounds[3], th, np_ptr(sf), len(sf), np_ptr(m), np_ptr(nm), 0))
         return int(nm[0]), m[:n_cur].copy()
 
+    def SearchForInitialization(self, kps1, desc1, kps2, desc2, prev_matched, window_size, bounds):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:407-522).
+        Returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+        n1, n2 = len(kps1), len(kps2)
+        cap = max(n1, n2, 1)
+
+        def pad(a, dtype, tail=()):
+            out = np.zeros((cap,) + tail, dtype)
+            a = np.asarray(a)
+            if len(a):
+                out[:len(a)] = a
+            return out
+        K1 = pad(kps1, KP_DTYPE); D1 = pad(desc1, np.uint8, (32,)); K2 = pad(kps2, KP_DTYPE); D2 = pad(desc2, np.uint8, (32,))
+        UV = pad(prev_matched, np.float32, (2,))
+        c1 = np.array([n1], np.int32); c2 = np.array([n2], np.int32)
+        m12 = np.full(cap, -1, np.int32); nm = np.zeros(1, np.int32)
+        check(lib().pgb_match_for_initialization(self._h, 1, cap, np_ptr(K1), np_ptr(D1), np_ptr(c1), np_ptr(K2), np_ptr(D2),
+                                                 np_ptr(c2), np_ptr(UV), int(window_size), bounds[0], bounds[1], bounds[2],
+                                                 bounds[3], np_ptr(m12), np_ptr(nm), 0))
+        return int(nm[0]), m12[:n1].copy(), UV[:n1].copy()
+
+    def SearchByProjectionMapPoints(self, kps, desc, has_map_point, proj_xy, track_level, view_cos, mp_desc, in_view,
+                                    mp_observed, bounds, th, scale_factors):
+        """SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:46-131) on flat arrays.
+        Returns (nmatches, match_of_feature): the map point index this call assigned to each feature, or -1."""
+        n, nq = len(kps), len(track_level)
+        cap = max(n, nq, 1)
+
+        def pad(a, dtype, tail=()):
+            out = np.zeros((cap,) + tail, dtype)
+            a = np.asarray(a)
+            if len(a):
+                out[:len(a)] = a
+            return out
+        K = pad(kps, KP_DTYPE); D = pad(desc, np.uint8, (32,)); H = pad(has_map_point, np.uint8)
+        UV = pad(proj_xy, np.float32, (2,)); L = pad(track_level, np.int32); VC = pad(view_cos, np.float32)
+        QD = pad(mp_desc, np.uint8, (32,)); IV = pad(in_view, np.uint8); OB = pad(mp_observed, np.uint8)
+        c = np.array([n], np.int32); cq = np.array([nq], np.int32)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        mo = np.full(cap, -1, np.int32); nm = np.zeros(1, np.int32)
+        check(lib().pgb_match_map_points(self._h, 1, cap, np_ptr(K), np_ptr(D), np_ptr(c), np_ptr(H), np_ptr(UV), np_ptr(L),
+                                         np_ptr(VC), np_ptr(QD), np_ptr(IV), np_ptr(OB), np_ptr(cq), bounds[0], bounds[1],
+                                         bounds[2], bounds[3], th, np_ptr(sf), len(sf), np_ptr(mo), np_ptr(nm), 0))
+        return int(nm[0]), mo[:n].copy()
+
     def match_consecutive_ptr(self, n_pairs, cap, kps_ptr, desc_ptr, counts_ptr, flow_ptr, max_x, max_y, th,
                               scale_factors, match_ptr, nmatch_ptr):
         sf = np.ascontiguousarray(scale_factors, np.float32)

@@ -355,3 +355,30 @@ def time_averaged_values(values, times_usec, frame_times_usec):
     if rc:
         raise ValueError("the reference would CHECK-fail on this input")
     return out, ok.astype(bool)
+
+
+def search_for_initialization(k1, d1, k2, d2, prev_matched, window_size, bounds, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:407-522), literal: (nmatches, vnMatches12, updated vbPrevMatched)."""
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    pm = np.ascontiguousarray(prev_matched, np.float32).copy(); m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = lib().pgo_search_for_initialization(k1.ctypes.data_as(C.c_void_p), ptr(d1, u8p), len(k1), k2.ctypes.data_as(C.c_void_p),
+                                            ptr(d2, u8p), len(k2), ptr(pm, f32p), int(window_size), C.c_float(bounds[0]),
+                                            C.c_float(bounds[1]), C.c_float(bounds[2]), C.c_float(bounds[3]), C.c_float(nnratio),
+                                            int(check_ori), ptr(m12, i32p))
+    return n, m12[:len(k1)].copy(), pm
+
+
+def search_map_points(kps, desc, has_mp, proj_xy, track_level, view_cos, mp_desc, in_view, mp_observed, bounds, th,
+                      scale_factors, nnratio=0.8):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:46-131), literal."""
+    kps = np.ascontiguousarray(kps); desc = np.ascontiguousarray(desc, np.uint8); has_mp = np.ascontiguousarray(has_mp, np.uint8)
+    uv = np.ascontiguousarray(proj_xy, np.float32); lv = np.ascontiguousarray(track_level, np.int32)
+    vc = np.ascontiguousarray(view_cos, np.float32); qd = np.ascontiguousarray(mp_desc, np.uint8)
+    iv = np.ascontiguousarray(in_view, np.uint8); ob = np.ascontiguousarray(mp_observed, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32); mo = np.full(max(len(kps), 1), -1, np.int32)
+    n = lib().pgo_search_map_points(kps.ctypes.data_as(C.c_void_p), ptr(desc, u8p), len(kps), ptr(has_mp, u8p), ptr(uv, f32p),
+                                    ptr(lv, i32p), ptr(vc, f32p), ptr(qd, u8p), ptr(iv, u8p), ptr(ob, u8p), len(lv),
+                                    C.c_float(bounds[0]), C.c_float(bounds[1]), C.c_float(bounds[2]), C.c_float(bounds[3]),
+                                    C.c_float(th), ptr(sf, f32p), C.c_float(nnratio), ptr(mo, i32p))
+    return n, mo[:len(kps)].copy()

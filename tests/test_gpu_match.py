@@ -111,3 +111,47 @@ def test_extract_then_match_consecutive_device_resident(golden_dir):
         assert nmh[t - 1] == int(P[f"nmatch{t}"])
         assert np.array_equal(mm[t - 1, :c[t]], P[f"match{t}"])
     m.close(); ex.close()
+
+
+def _feats_small(t, w=640, h=480):
+    orc = O.OrbOracle(500, 1.2, 8, 20, 7)
+    return orc.extract(synth.frame(t, w=w, h=h)), orc.tables()["scale"]
+
+
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_for_initialization_matches_oracle(check_ori):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:407-522): vnMatches12, the count and the updated
+    vbPrevMatched are bit-exact against the literal restatement."""
+    from pilotguru_b200.matcher import ORBmatcher
+    (k1, d1), _ = _feats_small(0)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    m = ORBmatcher(0.9, check_ori, max_feats=600)
+    for t2, win in ((1, 100), (4, 100), (2, 20)):
+        (k2, d2), _ = _feats_small(t2)
+        pm = np.stack([k1["x"], k1["y"]], axis=1)
+        on, om, opm = O.search_for_initialization(k1, d1, k2, d2, pm, win, bounds, nnratio=0.9, check_ori=check_ori)
+        gn, gm, gpm = m.SearchForInitialization(k1, d1, k2, d2, pm, win, bounds)
+        assert gn == on and on > 10 and np.array_equal(gm, om) and np.array_equal(gpm, opm)
+    gn, gm, _ = m.SearchForInitialization(k1[:0], d1[:0], k2, d2, np.zeros((0, 2), np.float32), 100, bounds)
+    assert gn == 0 and len(gm) == 0
+
+
+def test_search_map_points_matches_oracle():
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:46-131)."""
+    from pilotguru_b200.matcher import ORBmatcher
+    (k, d), sf = _feats_small(5)
+    rng = np.random.default_rng(8)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    nq = 400
+    sel = rng.integers(0, len(k), nq)
+    uv = (np.stack([k["x"][sel], k["y"][sel]], axis=1) + rng.normal(0, 1.5, (nq, 2))).astype(np.float32)
+    lv = np.clip(k["octave"][sel] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+    vc = rng.uniform(0.99, 1.0, nq).astype(np.float32)
+    qd = d[sel].copy(); qd[np.arange(nq), rng.integers(0, 32, nq)] ^= rng.integers(0, 256, nq).astype(np.uint8)
+    iv = (rng.uniform(size=nq) > 0.1).astype(np.uint8); ob = (rng.uniform(size=nq) > 0.3).astype(np.uint8)
+    has = (rng.uniform(size=len(k)) > 0.9).astype(np.uint8)
+    for th, ratio in ((1.0, 0.8), (3.0, 0.8), (5.0, 0.6)):
+        m = ORBmatcher(ratio, True, max_feats=600)
+        on, om = O.search_map_points(k, d, has, uv, lv, vc, qd, iv, ob, bounds, th, sf, nnratio=ratio)
+        gn, gm = m.SearchByProjectionMapPoints(k, d, has, uv, lv, vc, qd, iv, ob, bounds, th, sf)
+        assert gn == on and on > 50 and np.array_equal(gm, om)
