@@ -1,18 +1,19 @@
-// K2 v3: FAST-9 score kernel for sm_100a.  Same contract as v2 (fast_v2.cu): score map = (max arc threshold) where
+// K2: FAST-9 score kernel for sm_100a.  Score map = (max arc threshold) where
 // the pixel is a FAST-9 corner at minThFAST inside [19, w-19) x [19, h-19), else 0.
 // Reference: cv::FAST(TYPE_9_16) as called at ORBextractor.cc:809,:814.
 //
-// The round-1 ncu capture of v2 (profiles/r01_fast_score_ncu_full.md) showed 82 % of the issue slots busy at 16 %
-// of DRAM bandwidth: the kernel is bound by instruction issue, and on this part LOP3/PRMT/SHF/VIMNMX/VABSDIFF4 share
-// one half-rate pipe while IMAD runs on the other (profiles/r01_pipe_probe.txt).  v3 therefore minimises
-// instructions on the ALU pipe:
+// The round-1 ncu capture of the previous design (profiles/r01_fast_score_ncu_full.md: per-row ballots, quantised
+// signed prefilter, entry lists, direct global stores) showed 82 % of the issue slots busy at 16 % of DRAM bandwidth:
+// the kernel is bound by instruction issue, and on this part LOP3/PRMT/SHF/VIMNMX/VABSDIFF4 share one half-rate pipe
+// while IMAD runs on the other (profiles/r01_pipe_probe.txt).  This design therefore minimises instructions on the
+// ALU pipe:
 //   * one CTA per 256x64 tile; one elected thread issues a 3-D TMA load of the 72-word x 70-row halo box; every warp
 //     owns an 8-row band of a shared-memory score tile, zeroes it, and at the end stores it with ONE TMA store
 //     (clipped by the tensor map) -- no per-thread global stores, no bounds arithmetic on the output side.
 //   * phase 1 (prefilter), 8 px per lane per row, no quantisation: VABSDIFF4 gives |c - p| for 4 pixels per
 //     instruction; "(p0 or p8) and (p4 or p12) differ from the centre by more than t'" with t' = 2^k - 1 <= minTh is
 //     a bit test on the OR of two absolute differences.  It ignores polarity, which costs 3.6 % more candidates than
-//     the 6-bit signed test of v2 (measured on the synthetic frames) and saves the whole quantisation pass.
+//     the 6-bit signed test it replaced (measured on the synthetic frames) and saves the whole quantisation pass.
 //     The vertical differences |row r - row r+3| are shared between the two centre rows that use them.
 //     The 64 flags of a lane's 8x8 block stay in two registers; there are no per-row ballots or list stores.
 //   * expansion: a 4x4 byte transpose inside lane quads evens out the blobs, one warp scan of the per-lane counts,
@@ -111,20 +112,20 @@ __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
 //   [.., +8 warps * 384 * 4)    per-warp candidate queues: one-hot flag bit of the candidate in its register
 //   [.., +8 warps * 384)        ... and the producer's part of the candidate position
 //   [.., +16)                   the mbarrier
-constexpr int kF3InStage = (kF2InBytes + 127) / 128 * 128;
-constexpr int kF3QueueCap = 384;
-constexpr int kF3Smem = kF3InStage + kF2W * kF2H + 8 * kF3QueueCap * 5 + 16;
+constexpr int kFsInStage = (kF2InBytes + 127) / 128 * 128;
+constexpr int kFsQueueCap = 384;
+constexpr int kFsSmem = kFsInStage + kF2W * kF2H + 8 * kFsQueueCap * 5 + 16;
 
 template <int kOcc>
-__global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid_constant__ OrbGeo g,
+__global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_constant__ OrbGeo g,
                                                                  const __grid_constant__ TmapPack tm,
                                                                  const int4* __restrict__ tileTab, int frame0) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t* sIn = reinterpret_cast<const uint32_t*>(smem);
-  uint8_t* sScore = smem + kF3InStage;
+  uint8_t* sScore = smem + kFsInStage;
   uint32_t* sQueue = reinterpret_cast<uint32_t*>(sScore + kF2W * kF2H);
-  uint8_t* sQCode = reinterpret_cast<uint8_t*>(sQueue + 8 * kF3QueueCap);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sQCode + 8 * kF3QueueCap);
+  uint8_t* sQCode = reinterpret_cast<uint8_t*>(sQueue + 8 * kFsQueueCap);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sQCode + 8 * kFsQueueCap);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y + frame0;
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
     hi = __byte_perm(hi, y, sel2);
   }
   const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn);
-  uint32_t* q = sQueue + warp * kF3QueueCap;                 // one-hot flag of the candidate inside its register
-  uint8_t* qc = sQCode + warp * kF3QueueCap;                 // (lane & 28) * 8 + (lane & 3) + 4 * half
+  uint32_t* q = sQueue + warp * kFsQueueCap;                 // one-hot flag of the candidate inside its register
+  uint8_t* qc = sQCode + warp * kFsQueueCap;                 // (lane & 28) * 8 + (lane & 3) + 4 * half
   const int cnt = __popc(lo) + __popc(hi);
   int incl = cnt;
 #pragma unroll
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
   // Normally the band's candidates fit the queue in one pass; otherwise (noise images) one pass per row (<= 256).
-  const int nParts = total <= kF3QueueCap ? 1 : 8;
+  const int nParts = total <= kFsQueueCap ? 1 : 8;
   for (int part = 0; part < nParts; part++) {
     uint32_t mlo = lo, mhi = hi;
     int pos = incl - cnt, T = total;
@@ -291,16 +292,16 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score_v3(const __grid
   }
 }
 
-int launch_fast_score_v3(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
+int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st) {
   static bool init = false;
   if (!init) {
-    PGB_CUDA(cudaFuncSetAttribute(k_fast_score_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
+    PGB_CUDA(cudaFuncSetAttribute(k_fast_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmem));
     init = true;
   }
   if (g.totalTiles2 <= 0 || nFrames <= 0) return PGB_OK;
   dim3 grid(g.totalTiles2, nFrames);
-  k_fast_score_v3<4><<<grid, kF2Threads, kF3Smem, st>>>(g, tm, tileTab, frame0);
+  k_fast_score<4><<<grid, kF2Threads, kFsSmem, st>>>(g, tm, tileTab, frame0);
   PGB_LAUNCHED();
   return PGB_OK;
 }

@@ -67,8 +67,6 @@ struct pgb_orb {
   cudaEvent_t evDone = nullptr;
   cudaEvent_t evChunk[16] = {};
   int h2dChunk = 16;  // largest H2D/compute pipeline chunk in frames (PGB_H2D_CHUNK)
-  bool fastV3 = true;  // PGB_FAST_IMPL=v2: previous TMA kernel (A/B measurements)
-  bool fastV2 = true;  // PGB_FAST_IMPL=v1 selects the first-generation kernel (kept for A/B measurements)
   int numSMs = 148;
 };
 
@@ -81,7 +79,6 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
   g->nlevels = o->nlevels;
   g->iniTh = o->iniTh;
   g->minTh = o->minTh;
-  g->qTh = o->minTh >= 2 ? (o->minTh + 1) / 4 : 0;
   {
     int k = 0;
     while (k < 7 && (2 << k) - 1 <= o->minTh) k++;  // 2^k - 1 <= minTh < 2^(k+1) - 1 (k = 0 when minTh < 1)
@@ -89,7 +86,7 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
     g->absMask = (0x7fu & ~((1u << k) - 1u)) * 0x01010101u;
   }
   unsigned long long off = 0, slotOff = 0, candOff = 0;
-  int cellBase = 0, tileBase = 0, tile2Base = 0, kpBase = 0, maxNode = 1;
+  int cellBase = 0, tile2Base = 0, kpBase = 0, maxNode = 1;
   for (int l = 0; l < o->nlevels; l++) {
     LevelGeo& L = g->lv[l];
     L.w = cv_round_f((float)w * o->invScale[l]);
@@ -130,10 +127,6 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
     maxNode = std::max(maxNode, L.nodeCap);
     L.kpBase = kpBase;
     kpBase += L.nodeCap;
-    L.tilesX = (L.w + kFtW - 1) / kFtW;
-    L.tilesY = (L.h + kFtH - 1) / kFtH;
-    L.tileBase = tileBase;
-    tileBase += L.tilesX * L.tilesY;
     L.tiles2X = (L.w + kF2W - 1) / kF2W;
     L.tiles2Y = (L.h + kF2H - 1) / kF2H;
     L.tile2Base = tile2Base;
@@ -144,7 +137,6 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
       return fail(PGB_ERR_INVALID, "images wider/taller than 4127 px are not supported");
   }
   g->totalCells = cellBase;
-  g->totalTiles = tileBase;
   g->totalTiles2 = tile2Base;
   g->kpCapInternal = kpBase;
   g->maxNodeCap = maxNode;
@@ -239,7 +231,7 @@ int set_geometry(pgb_orb* o, int w, int h) {
   o->geo = g;
   o->curW = w;
   o->curH = h;
-  if (o->fastV2) {
+  {
     rc = build_tmaps(o);
     if (rc) return rc;
     std::vector<int4> tab;
@@ -285,14 +277,11 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
           launch_pyramid_level(g, l, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], st);
         break;
       case 1:
-        if (o->fastV2) {
-          int rc = o->fastV3 ? launch_fast_score_v3(g, o->tmaps, o->tileTab.p, f0, n, st)
-                             : launch_fast_score_v2(g, o->tmaps, o->tileTab.p, o->score.p, f0, n, st);
-          if (rc) return rc;
-        } else {
-          launch_fast_score(g, n, pyr, score, st);
-        }
+      {
+        int rc = launch_fast_score(g, o->tmaps, o->tileTab.p, f0, n, st);
+        if (rc) return rc;
         break;
+      }
       case 2: launch_cells(g, n, score, slots, cellCnt, o->err.p, st); break;
       case 3: launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, st); break;
       case 4:
@@ -397,9 +386,6 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
   };
   if (build_geo(o, max_width, max_height, &o->capGeo)) return bail("geometry");
   {
-    const char* impl = getenv("PGB_FAST_IMPL");
-    o->fastV2 = !(impl && strcmp(impl, "v1") == 0);
-    o->fastV3 = !(impl && strcmp(impl, "v2") == 0);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) o->numSMs = prop.multiProcessorCount;
   }

@@ -133,149 +133,7 @@ void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr,
   PGB_LAUNCHED();
 }
 
-// =========================================================================================== K2 FAST-9 score
-// Exact "bam" of one pixel from a shared-memory tile: max over the 16 contiguous 9-arcs of
-// max(min(v - p_k), min(p_k - v)).  Both polarities ride in the two s16 halves of one register and the 9-wide
-// sliding minimum is two rounds of the 3-input DPX min (VIMNMX3.S16x2).
-__device__ __forceinline__ int fast_bam_smem(const uint8_t* c, int stride) {
-  const int v = c[0];
-  uint32_t w[16];
-  const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-  const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const int d = v - (int)c[dy[k] * stride + dx[k]];
-    w[k] = __byte_perm((uint32_t)d, (uint32_t)(-d), 0x5410);  // lo16 = v-p (dark), hi16 = p-v (bright)
-  }
-  uint32_t t3[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) t3[k] = __vimin3_s16x2(w[k], w[(k + 1) & 15], w[(k + 2) & 15]);
-  uint32_t m9[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) m9[k] = __vimin3_s16x2(t3[k], t3[(k + 3) & 15], t3[(k + 6) & 15]);
-  uint32_t a = __vimax3_s16x2(m9[0], m9[1], m9[2]);
-  uint32_t b = __vimax3_s16x2(m9[3], m9[4], m9[5]);
-  uint32_t cc = __vimax3_s16x2(m9[6], m9[7], m9[8]);
-  uint32_t d2 = __vimax3_s16x2(m9[9], m9[10], m9[11]);
-  uint32_t e = __vimax3_s16x2(m9[12], m9[13], m9[14]);
-  a = __vimax3_s16x2(a, b, cc);
-  d2 = __vimax3_s16x2(d2, e, m9[15]);
-  a = __vmaxs2(a, d2);
-  const int lo = (int)(short)(a & 0xffff), hi = (int)(short)(a >> 16);
-  return max(lo, hi);
-}
-
-// Tile kernel.  Phase 1: byte-SIMD (4 px per thread) conservative prefilter on pixels quantised to 6 bits: a
-// 9-arc always contains one of every opposite ring pair, so a corner at threshold t needs
-// (p0|p8) and (p4|p12) both darker (or both brighter) than the centre by more than t; on the >>2 grid that is
-// "differs by at least qTh = ceil((t-2)/4)" which can only over-accept.  Survivors are compacted into a
-// shared-memory list.  Phase 2: exact score of each survivor.  Phase 3: coalesced 16-byte stores of the tile.
-__global__ void __launch_bounds__(kFtThreads) k_fast_score(OrbGeo g, const uint8_t* __restrict__ pyr,
-                                                           uint8_t* __restrict__ score) {
-  __shared__ __align__(16) uint8_t s_in[kFtInH * kFtInW];
-  __shared__ __align__(16) uint8_t s_out[kFtH * kFtW];
-  __shared__ uint16_t s_list[kFtH * kFtW];
-  __shared__ int s_count;
-
-  // locate the tile
-  int t = blockIdx.x, level = 0;
-#pragma unroll 1
-  for (int l = 1; l < g.nlevels; l++)
-    if (t >= g.lv[l].tileBase) level = l;
-  const LevelGeo& L = g.lv[level];
-  t -= L.tileBase;
-  const int ty = t / L.tilesX, tx = t - ty * L.tilesX;
-  const int x0 = tx * kFtW, y0 = ty * kFtH;
-  const size_t base = (size_t)blockIdx.y * g.frameStride + L.off;
-  const uint8_t* img = pyr + base;
-  const int tid = threadIdx.x;
-
-  if (tid == 0) s_count = 0;
-  // zero the output tile (2 x 16 B per thread)
-  reinterpret_cast<uint4*>(s_out)[tid] = make_uint4(0, 0, 0, 0);
-  reinterpret_cast<uint4*>(s_out)[tid + kFtThreads] = make_uint4(0, 0, 0, 0);
-  // load the input tile with a 3-row / 4-byte halo as 32-bit words; out-of-image words read as 0
-  constexpr int kWordsPerRow = kFtInW / 4;  // 66
-  for (int i = tid; i < kFtInH * kWordsPerRow; i += kFtThreads) {
-    const int r = i / kWordsPerRow, c = i - r * kWordsPerRow;
-    const int gy = y0 - 3 + r, gx = x0 - 4 + c * 4;
-    uint32_t v = 0;
-    if (gy >= 0 && gy < L.h && gx >= 0 && gx + 3 < L.pitch)
-      v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + gx));
-    reinterpret_cast<uint32_t*>(s_in)[i] = v;
-  }
-  __syncthreads();
-
-  // ---- phase 1
-  {
-    const int wx = tid & 63, rg = tid >> 6;
-    const int gx = x0 + wx * 4;
-    // x-validity of the 4 bytes: tested region is [19, w-19)
-    uint32_t xmask = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++)
-      if (gx + b >= kEdge && gx + b < L.w - kEdge) xmask |= 0x80u << (8 * b);
-    const uint32_t qth = (uint32_t)g.qTh * 0x01010101u;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_in);
-    if (xmask) {
-#pragma unroll 2
-      for (int r = rg; r < kFtH; r += 4) {
-        const int gy = y0 + r;
-        if (gy < kEdge || gy >= L.h - kEdge) continue;
-        const uint32_t* row = sw + (r + 3) * kWordsPerRow + wx;  // word left of the centre word
-        const uint32_t wm = row[0], w0 = row[1], wp = row[2];
-        const uint32_t up = sw[r * kWordsPerRow + wx + 1], dn = sw[(r + 6) * kWordsPerRow + wx + 1];
-        const uint32_t r4 = __byte_perm(w0, wp, 0x6543);   // x+3 .. x+6
-        const uint32_t r12 = __byte_perm(wm, w0, 0x4321);  // x-3 .. x
-        const uint32_t qc = (w0 >> 2) & 0x3f3f3f3fu;
-        const uint32_t q0 = (dn >> 2) & 0x3f3f3f3fu, q8 = (up >> 2) & 0x3f3f3f3fu;
-        const uint32_t q4 = (r4 >> 2) & 0x3f3f3f3fu, q12 = (r12 >> 2) & 0x3f3f3f3fu;
-        const uint32_t V = (qc | 0x80808080u) - qth;  // bytes in [128-qth, 191-qth], no borrow for qth <= 64
-        // dark: v'' - p'' >= qth  <=>  msb(V - p'')
-        const uint32_t d0 = V - q0, d8 = V - q8, d4 = V - q4, d12 = V - q12;
-        // bright: p'' - v'' >= qth  <=>  msb((p''|0x80) - qth - v'')
-        const uint32_t C = qc + qth;
-        const uint32_t b0 = (q0 | 0x80808080u) - C, b8 = (q8 | 0x80808080u) - C;
-        const uint32_t b4 = (q4 | 0x80808080u) - C, b12 = (q12 | 0x80808080u) - C;
-        uint32_t m = (((d0 | d8) & (d4 | d12)) | ((b0 | b8) & (b4 | b12))) & xmask;
-        if (m) {
-          const int n = __popc(m);
-          int pos = atomicAdd(&s_count, n);
-          const int code = (r << 8) | (wx * 4);
-#pragma unroll
-          for (int b = 0; b < 4; b++)
-            if (m & (0x80u << (8 * b))) s_list[pos++] = (uint16_t)(code + b);
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2
-  const int n = s_count;
-  for (int i = tid; i < n; i += kFtThreads) {
-    const int code = s_list[i];
-    const int r = code >> 8, xl = code & 255;
-    const int bam = fast_bam_smem(s_in + (r + 3) * kFtInW + 4 + xl, kFtInW);
-    if (bam > g.minTh) s_out[r * kFtW + xl] = (uint8_t)(bam - 1);
-  }
-  __syncthreads();
-
-  // ---- phase 3: 16 vectors per row, 32 rows
-  uint8_t* out = score + base;
-  for (int i = tid; i < kFtH * (kFtW / 16); i += kFtThreads) {
-    const int r = i >> 4, c = i & 15;
-    const int gy = y0 + r, gx = x0 + c * 16;
-    if (gy < L.h && gx < L.pitch)
-      *reinterpret_cast<uint4*>(out + (size_t)gy * L.pitch + gx) = reinterpret_cast<const uint4*>(s_out)[i];
-  }
-}
-
-void launch_fast_score(const OrbGeo& g, int nFrames, const uint8_t* pyr, uint8_t* score, cudaStream_t st) {
-  dim3 grid(g.totalTiles, nFrames);
-  k_fast_score<<<grid, kFtThreads, 0, st>>>(g, pyr, score);
-  PGB_LAUNCHED();
-}
+// K2 (FAST-9 score) lives in fast_score.cu.
 
 // =========================================================================================== K3 cells
 // One warp per FAST cell.  A pixel survives the cell's 3x3 NMS iff its score is strictly greater than its 8

@@ -20,11 +20,7 @@ constexpr int kEdge = 19;        // EDGE_THRESHOLD (ORBextractor.cc:74)
 constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3 (ORBextractor.cc:773)
 constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
 
-// FAST score kernel tiling
-constexpr int kFtW = 256, kFtH = 32, kFtThreads = 256;
-constexpr int kFtInW = kFtW + 8, kFtInH = kFtH + 6;
-
-// FAST score kernel v2 (TMA-staged persistent tiles)
+// FAST score kernel: one CTA per 256x64 tile, TMA-staged with a halo
 constexpr int kF2W = 256, kF2H = 64, kF2Threads = 256;
 constexpr int kF2InWords = kF2W / 4 + 8;  // 72 words per row: 16-byte halo left and right (a TMA box must start
                                           // on a 16-byte boundary in the innermost dimension; measured: tools/probe)
@@ -43,17 +39,16 @@ struct LevelGeo {
   int candCap;
   unsigned long long candBase;  // in u64 units inside a frame's cand block
   int nodeCap, kpBase;
-  int tileBase, tilesX, tilesY;
   int tile2Base, tiles2X, tiles2Y;
   float scale;
   int patchSize;
 };
 
 struct OrbGeo {
-  int nlevels, iniTh, minTh, qTh;
+  int nlevels, iniTh, minTh;
   unsigned one;      // = 1, opaque to the compiler (FAST v3 issues its additions as IMAD on the idle FMA pipe)
   unsigned absMask;  // FAST v3 prefilter: bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
-  int totalCells, totalTiles, totalTiles2, kpCapInternal, maxNodeCap;
+  int totalCells, totalTiles2, kpCapInternal, maxNodeCap;
   unsigned long long frameStride, slotsPerFrame, candPerFrame;
   LevelGeo lv[kMaxLevels];
 };
@@ -75,10 +70,7 @@ enum OrbErr { kErrCandOverflow = 1, kErrNodeOverflow = 2, kErrOutCap = 4, kErrCe
 
 void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
                           const ResizeTab* ytab, cudaStream_t st);
-void launch_fast_score(const OrbGeo& g, int nFrames, const uint8_t* pyr, uint8_t* score, cudaStream_t st);
-int launch_fast_score_v2(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, uint8_t* score, int frame0,
-                         int nFrames, cudaStream_t st);
-int launch_fast_score_v3(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
+int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st);
 void launch_cells(const OrbGeo& g, int nFrames, const uint8_t* score, uint32_t* slots, int* cellCnt, int* err,
                   cudaStream_t st);
