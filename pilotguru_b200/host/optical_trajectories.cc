@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
   pgb_orb* orb = pgb_orb_create((int)device, nfeatures, scale_factor, nlevels, ini_th, min_th, width, height, B, nullptr);
   PGB_CHECK(orb != nullptr) << pgb_last_error();
   const int cap = pgb_orb_max_keypoints(orb);
-  pgb_matcher* matcher = pgb_matcher_create((int)device, 0.9f, 1, cap, B, nullptr);  // ORBmatcher(0.9, true), Tracking.cc:835
+  pgb_matcher* matcher = pgb_matcher_create((int)device, 0.9f, 1, cap, B, nullptr);  // ORBmatcher(0.9, true), Tracking.cc:860
   PGB_CHECK(matcher != nullptr) << pgb_last_error();
   std::vector<float> sf(nlevels), inv(nlevels), s2(nlevels), is2(nlevels);
   PGB_CALL(pgb_orb_scale_factors(orb, sf.data(), inv.data(), s2.data(), is2.data()));
@@ -168,7 +168,7 @@ int main(int argc, char** argv) {
                                          (float)width, 0.f, (float)height, th, sf.data(), nlevels, matchOf.data() + o,
                                          nMatch.data() + p0, 0));
       };
-      run(15.f, first, np);                                        // th = 15 for monocular, Tracking.cc:856-860
+      run(15.f, first, np);                                        // th = 15 for monocular, Tracking.cc:871-876
       for (int p = first; p < n; p++)
         if (nMatch[p] < 20) run(30.f, p, 1);                       // Tracking.cc:876-883
     }
