@@ -61,6 +61,7 @@ struct pgb_orb {
   DevBuf<uint8_t> tmpLevel;
   TmapPack tmaps{};
   DevBuf<int4> tileTab;
+  DevBuf<int> cellTab;  // per FAST cell: level | grid row << 8 | grid column << 20
   cudaStream_t copyStream = nullptr;
   cudaStream_t auxStream[2] = {nullptr, nullptr};
   cudaEvent_t evAux[2] = {nullptr, nullptr};
@@ -238,6 +239,13 @@ int set_geometry(pgb_orb* o, int w, int h) {
     for (int l = 0; l < g.nlevels; l++)
       for (int ty = 0; ty < g.lv[l].tiles2Y; ty++)
         for (int tx = 0; tx < g.lv[l].tiles2X; tx++) tab.push_back(make_int4(l, tx * kF2W, ty * kF2H, 0));
+    std::vector<int> ctab;
+    for (int l = 0; l < g.nlevels; l++)
+      for (int i = 0; i < g.lv[l].nRows; i++)
+        for (int j = 0; j < g.lv[l].nCols; j++) ctab.push_back(l | (i << 8) | (j << 20));
+    if (o->cellTab.n < ctab.size() && o->cellTab.alloc(ctab.size())) return PGB_ERR_CUDA;
+    PGB_CUDA(cudaMemcpyAsync(o->cellTab.p, ctab.data(), ctab.size() * sizeof(int), cudaMemcpyHostToDevice, o->stream));
+    PGB_CUDA(cudaStreamSynchronize(o->stream));  // ctab dies at the end of this block
     if (o->tileTab.n < tab.size() && o->tileTab.alloc(tab.size())) return PGB_ERR_CUDA;
     PGB_CUDA(cudaMemcpyAsync(o->tileTab.p, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice, o->stream));
     PGB_CUDA(cudaStreamSynchronize(o->stream));
@@ -282,7 +290,7 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         if (rc) return rc;
         break;
       }
-      case 2: launch_cells(g, n, score, slots, cellCnt, o->err.p, st); break;
+      case 2: launch_cells(g, n, o->cellTab.p, score, slots, cellCnt, o->err.p, st); break;
       case 3: launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, st); break;
       case 4:
         launch_orient_desc(g, n, pyr, staged, lvlCnt, kps + (size_t)f0 * cap, desc + (size_t)f0 * cap * 32, counts + f0,

@@ -136,33 +136,33 @@ void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr,
 // K2 (FAST-9 score) lives in fast_score.cu.
 
 // =========================================================================================== K3 cells
-// One warp per FAST cell.  A pixel survives the cell's 3x3 NMS iff its score is strictly greater than its 8
-// neighbours' scores, neighbours outside the cell's tested rectangle counting 0.  Because non-corners at the
-// cell's threshold also count 0 and a survivor's own score is >= the threshold, the survivors at iniTh are
-// exactly the survivors at minTh with score >= iniTh: one NMS pass serves both thresholds.
+// One warp per FAST cell (ORBextractor.cc:789-828: cv::FAST at iniThFAST, again at minThFAST if the cell is empty).
+// A pixel survives the cell's 3x3 NMS iff its score is strictly greater than its 8 neighbours' scores, neighbours
+// outside the cell's tested rectangle counting 0.  Because non-corners at the cell's threshold also count 0 and a
+// survivor's own score is >= the threshold, the survivors at iniTh are exactly the survivors at minTh with
+// score >= iniTh: one NMS pass serves both thresholds.
 //
-// The score map is ~98 % zeros, so the cell is scanned as aligned 32-bit words (4 px per lane): pass A keeps only
-// the words holding a score >= minTh inside the rectangle (one ballot per 128 px); pass B runs the neighbour test
-// on those few pixels, one word per lane; pass C emits the survivors in the reference's order (row-major in the
-// cell: word order, then byte order) with a warp scan.
+// Lane = row of the cell's tested rectangle (<= 64 rows: two passes of 32).  A lane reads its row with 16-byte loads,
+// turns the non-zero bytes inside [rx0, rx1) into a 64-bit candidate mask (every non-zero score is >= minTh by
+// construction of the score map), runs the neighbour test on its own candidates (byte loads that hit L1: the rows
+// were just read by the neighbouring lanes) and keeps two 64-bit survivor masks (all / score >= iniTh).  Lane order
+// = row order and bit order = x order, so one warp scan of the per-lane counts places the survivors in the
+// reference's row-major order.  (Round-1 profile of the previous word-scan version: 1120 warp-instructions per cell,
+// a third of them in the candidate scan; this one needs about a third of that.)
 constexpr int kCellWarps = 4;
-constexpr int kCellMaxWords = 1024;  // rows (<= 60) x words per row (<= 17)
 
-__global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const uint8_t* __restrict__ score,
+__global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const int* __restrict__ cellTab,
+                                                           const uint8_t* __restrict__ score,
                                                            uint32_t* __restrict__ slots, int* __restrict__ cellCnt,
                                                            int* __restrict__ err) {
-  __shared__ uint32_t s_ent[kCellWarps][kCellMaxWords];  // row | k<<8 | candidate nibble<<16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x * kCellWarps + warp;
   if (cell >= g.totalCells) return;
   const int f = blockIdx.y;
-  int level = 0;
-#pragma unroll 1
-  for (int l = 1; l < g.nlevels; l++)
-    if (cell >= g.lv[l].cellBase) level = l;
+  const int tv = __ldg(&cellTab[cell]);  // level | row i << 8 | column j << 20 (host table: no search, no division)
+  const int level = tv & 0xff, i = (tv >> 8) & 0xfff, j = (tv >> 20) & 0xfff;
   const LevelGeo& L = g.lv[level];
   const int ci = cell - L.cellBase;
-  const int i = ci / L.nCols, j = ci - i * L.nCols;
   int* cnt = cellCnt + (size_t)f * g.totalCells + cell;
   const int iniX = kMinBorder + j * L.wCell, iniY = kMinBorder + i * L.hCell;
   if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6) {
@@ -176,110 +176,97 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const uint8
     if (lane == 0) *cnt = 0;
     return;
   }
-  const int ax0 = rx0 & ~3;
-  const int wpr = (rx1 - ax0 + 3) >> 2;
-  const int nWords = wpr * th;
-  if (nWords > kCellMaxWords || wpr > 255 || th > 255) {
+  if (tw > 64 || th > 64) {  // cells are W = 30 nominal, so < 60 in each direction (ORBextractor.cc:769-778)
     if (lane == 0) { atomicOr(err, kErrCellChunks); *cnt = 0; }
     return;
   }
   const uint8_t* S = score + (size_t)f * g.frameStride + L.off;
   const int pitch = L.pitch;
-  const uint32_t inv = (65536u + wpr - 1) / wpr;  // exact floor(wi / wpr) for wi < 1024, wpr <= 17
-  const uint32_t lt = (1u << lane) - 1u;
-  const int minTh = g.minTh, iniTh = g.iniTh;
-  uint32_t* ent = s_ent[warp];
+  const int a16 = rx0 & ~15;
+  const int nvec = (rx1 - a16 + 15) >> 4;  // <= 5
+  const int iniTh = g.iniTh;
 
-  // ---- pass A: words with a candidate byte
-  int nEnt = 0;
-  for (int w0 = 0; w0 < nWords; w0 += 32) {
-    const int wi = w0 + lane;
-    uint32_t nib = 0;
-    int row = 0, k = 0;
-    if (wi < nWords) {
-      row = (int)(((uint32_t)wi * inv) >> 16);
-      k = wi - row * wpr;
-      const int x = ax0 + 4 * k;
-      const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(S + (size_t)(ry0 + row) * pitch + x));
-      if (word) {
+  // masks are kept as 32-bit halves [pass][half]: bit = x - rx0 - 32 * half (cells are rarely wider than 32)
+  uint32_t keep[2][2] = {{0u, 0u}, {0u, 0u}}, keep20[2][2] = {{0u, 0u}, {0u, 0u}};
+  const int nHalf = tw > 32 ? 2 : 1;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const int sc = (word >> (8 * b)) & 0xff;
-          if (sc >= minTh && x + b >= rx0 && x + b < rx1) nib |= 1u << b;
+  for (int c = 0; c < 2; c++) {
+    if (32 * c >= th) break;  // warp-uniform
+    const int row = lane + 32 * c;
+    if (row < th) {
+      const int y = ry0 + row;
+      const uint8_t* rowp = S + (size_t)y * pitch;
+      unsigned long long cand = 0ull;
+      for (int v = 0; v < nvec; v++) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rowp + a16 + 16 * v));
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+        uint32_t m16 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t wd = w4[k];
+          // non-zero bytes -> 4 adjacent bits: msb flags, then a multiply gathers them at bits 21..24
+          const uint32_t nz = (((wd & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wd) & 0x80808080u;
+          m16 |= ((((nz >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * k);
         }
+        const int off = a16 + 16 * v - rx0;  // x of the vector's byte 0 relative to the rectangle: -15 .. 63
+        cand |= off >= 0 ? ((unsigned long long)m16 << off) : ((unsigned long long)(m16 >> (-off)));
       }
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, nib != 0);
-    if (nib) ent[nEnt + __popc(bal & lt)] = (uint32_t)row | ((uint32_t)k << 8) | (nib << 16);
-    nEnt += __popc(bal);
-  }
-  __syncwarp();
-
-  // ---- pass B + C, 32 entries at a time
-  uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)ci * L.slotCap;
-  // first find out whether any survivor reaches iniTh (needs all entries), keeping the per-entry results in smem
-  bool any20 = false;
-  for (int e0 = 0; e0 < nEnt; e0 += 32) {
-    const int e = e0 + lane;
-    uint32_t keep = 0, keep20 = 0;
-    if (e < nEnt) {
-      const uint32_t en = ent[e];
-      const int row = en & 0xff, k = (en >> 8) & 0xff;
-      uint32_t nib = en >> 16;
-      const int y = ry0 + row, xw = ax0 + 4 * k;
-      const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(S + (size_t)y * pitch + xw));
-      while (nib) {
-        const int b = __ffs(nib) - 1;
-        nib &= nib - 1;
-        const int x = xw + b;
-        const int sc = (word >> (8 * b)) & 0xff;
-        bool ok = true;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++) {
-            if (dx == 0 && dy == 0) continue;
-            const int nx = x + dx, ny = y + dy;
-            int nsc = 0;
-            if (nx >= rx0 && nx < rx1 && ny >= ry0 && ny < ry1) nsc = __ldg(S + (size_t)ny * pitch + nx);
-            ok = ok && (nsc < sc);
+      if (tw < 64) cand &= (1ull << tw) - 1ull;
+      // neighbours outside the rectangle count 0; the loads themselves are always inside the level (rectangles
+      // start >= 19 px from every image border), so they are issued unconditionally and masked afterwards
+      const bool top = row > 0, bot = row < th - 1;
+      for (int hf = 0; hf < nHalf; hf++) {
+        uint32_t m = hf ? (uint32_t)(cand >> 32) : (uint32_t)cand;
+        uint32_t kp = 0, kp20 = 0;
+        while (m) {
+          const uint32_t low = m & (0u - m);
+          m ^= low;
+          const int bx = 31 - __clz(low) + 32 * hf;
+          const uint8_t* p = rowp + rx0 + bx;
+          const int sc = __ldg(p);
+          int nw = __ldg(p - pitch - 1), n = __ldg(p - pitch), ne = __ldg(p - pitch + 1);
+          const int w = __ldg(p - 1), e = __ldg(p + 1);
+          int sw = __ldg(p + pitch - 1), so = __ldg(p + pitch), se = __ldg(p + pitch + 1);
+          if (!top) { nw = 0; n = 0; ne = 0; }
+          if (!bot) { sw = 0; so = 0; se = 0; }
+          int left = max(max(nw, w), sw), right = max(max(ne, e), se);
+          if (bx == 0) left = 0;
+          if (bx == tw - 1) right = 0;
+          if (max(max(left, right), max(n, so)) < sc) {
+            kp |= low;
+            if (sc >= iniTh) kp20 |= low;
           }
-        if (ok) {
-          keep |= 1u << b;
-          if (sc >= iniTh) keep20 |= 1u << b;
         }
+        keep[c][hf] = kp;
+        keep20[c][hf] = kp20;
       }
-      ent[e] = (en & 0xffffu) | (keep << 16) | (keep20 << 20);
     }
-    any20 = any20 || __any_sync(0xffffffffu, keep20 != 0);
   }
-  __syncwarp();
+  const bool any20 = __any_sync(0xffffffffu, (keep20[0][0] | keep20[0][1] | keep20[1][0] | keep20[1][1]) != 0u);
+  uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)ci * L.slotCap;
   int basei = 0;
-  for (int e0 = 0; e0 < nEnt; e0 += 32) {
-    const int e = e0 + lane;
-    uint32_t sel = 0, en = 0;
-    if (e < nEnt) {
-      en = ent[e];
-      sel = any20 ? ((en >> 20) & 0xf) : ((en >> 16) & 0xf);
-    }
-    const int c = __popc(sel);
-    int incl = c;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    if (32 * c >= th) break;
+    const uint32_t s0 = any20 ? keep20[c][0] : keep[c][0], s1 = any20 ? keep20[c][1] : keep[c][1];
+    const int n = __popc(s0) + __popc(s1);
+    int incl = n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += v;
     }
-    int pos = basei + incl - c;
+    int pos = basei + incl - n;
     basei += __shfl_sync(0xffffffffu, incl, 31);
-    if (sel) {
-      const int row = en & 0xff, k = (en >> 8) & 0xff;
-      const int y = ry0 + row, xw = ax0 + 4 * k;
-      const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(S + (size_t)y * pitch + xw));
-      while (sel) {
-        const int b = __ffs(sel) - 1;
-        sel &= sel - 1;
+    const int y = ry0 + lane + 32 * c;
+    for (int hf = 0; hf < nHalf; hf++) {
+      uint32_t m = hf ? s1 : s0;
+      while (m) {
+        const uint32_t low = m & (0u - m);
+        m ^= low;
+        const int x = rx0 + 31 - __clz(low) + 32 * hf;
         if (pos < L.slotCap)
-          slot[pos] = (uint32_t)(xw + b - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | (((word >> (8 * b)) & 0xffu) << 24);
+          slot[pos] = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | ((uint32_t)__ldg(S + (size_t)y * pitch + x) << 24);
         pos++;
       }
     }
@@ -290,10 +277,10 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const uint8
   }
 }
 
-void launch_cells(const OrbGeo& g, int nFrames, const uint8_t* score, uint32_t* slots, int* cellCnt, int* err,
-                  cudaStream_t st) {
+void launch_cells(const OrbGeo& g, int nFrames, const int* cellTab, const uint8_t* score, uint32_t* slots, int* cellCnt,
+                  int* err, cudaStream_t st) {
   dim3 grid((g.totalCells + kCellWarps - 1) / kCellWarps, nFrames);
-  k_cells<<<grid, kCellWarps * 32, 0, st>>>(g, score, slots, cellCnt, err);
+  k_cells<<<grid, kCellWarps * 32, 0, st>>>(g, cellTab, score, slots, cellCnt, err);
   PGB_LAUNCHED();
 }
 

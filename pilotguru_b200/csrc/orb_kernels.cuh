@@ -72,8 +72,8 @@ void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr,
                           const ResizeTab* ytab, cudaStream_t st);
 int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st);
-void launch_cells(const OrbGeo& g, int nFrames, const uint8_t* score, uint32_t* slots, int* cellCnt, int* err,
-                  cudaStream_t st);
+void launch_cells(const OrbGeo& g, int nFrames, const int* cellTab, const uint8_t* score, uint32_t* slots, int* cellCnt,
+                  int* err, cudaStream_t st);
 void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,
                    StagedKp* staged, int* lvlCnt, int* err, cudaStream_t st);
 void launch_orient_desc(const OrbGeo& g, int nFrames, const uint8_t* pyr, const StagedKp* staged, const int* lvlCnt,
