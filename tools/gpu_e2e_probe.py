@@ -44,6 +44,7 @@ def timed(name, fn, n=10):
 
 with torch.cuda.stream(st):
     timed("H2D only (one 133 MB copy)", lambda: dev.copy_(host, non_blocking=True))
+    timed("H2D only (64 x 2 MB copies)", lambda: [dev[i].copy_(host[i], non_blocking=True) for i in range(B)])
     timed("extract, frames resident", lambda: extract(3, dev.data_ptr()))
     timed("extract from pinned host (pipelined)", lambda: extract(2, host.data_ptr()))
     timed("... + match", lambda: (extract(2, host.data_ptr()), domatch()))
