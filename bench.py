@@ -144,7 +144,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    per_step = max(8, min(cores, 64))
+    per_step = max(32, min(8 * cores, 256))  # ~10-20 s of CPU work per step at ~14 frames/s/core
     for _ in range(min(args.warmup, 1)):
         cpu_run(per_step, cores)
     tot_s, tot_f = 0.0, 0

@@ -54,7 +54,8 @@ struct pgb_orb {
   DevBuf<unsigned long long> cand;
   DevBuf<StagedKp> staged;
   DevBuf<ResizeTab> xtab, ytab;
-  std::vector<int> xtabOff, ytabOff;
+  std::vector<int> xtabOff, ytabOff, tileXOff, tileYOff;
+  DevBuf<int2> tileX, tileY;
   DevBuf<pgb_keypoint> kps;
   DevBuf<uint8_t> desc;
   int outCap = 0;
@@ -168,16 +169,37 @@ void make_resize_tab(int src, int dst, bool clampCoef, std::vector<ResizeTab>& o
 
 int upload_tabs(pgb_orb* o) {
   std::vector<ResizeTab> xs, ys, t;
+  std::vector<int2> tx, ty;  // per tile column {first staged source byte (16-aligned), 16-byte vectors}, per tile row {first source row, rows}
   o->xtabOff.assign(o->nlevels, 0);
   o->ytabOff.assign(o->nlevels, 0);
+  o->tileXOff.assign(o->nlevels, 0);
+  o->tileYOff.assign(o->nlevels, 0);
   for (int l = 1; l < o->nlevels; l++) {
+    const LevelGeo& S = o->geo.lv[l - 1];
+    const LevelGeo& D = o->geo.lv[l];
     o->xtabOff[l] = (int)xs.size();
-    make_resize_tab(o->geo.lv[l - 1].w, o->geo.lv[l].w, true, t);
+    make_resize_tab(S.w, D.w, true, t);
     xs.insert(xs.end(), t.begin(), t.end());
+    o->tileXOff[l] = (int)tx.size();
+    for (int x0 = 0; x0 < D.w; x0 += kPyW) {
+      const int xl = std::min(x0 + kPyW - 1, D.w - 1);
+      const int sxLo = t[x0].s, sxHi = std::min((int)t[xl].s + 1, S.w - 1);
+      const int ax = sxLo & ~15;
+      tx.push_back(make_int2(ax, (sxHi - ax + 16) >> 4));
+    }
     o->ytabOff[l] = (int)ys.size();
-    make_resize_tab(o->geo.lv[l - 1].h, o->geo.lv[l].h, false, t);
+    make_resize_tab(S.h, D.h, false, t);
     ys.insert(ys.end(), t.begin(), t.end());
+    o->tileYOff[l] = (int)ty.size();
+    for (int y0 = 0; y0 < D.h; y0 += kPyH) {
+      const int yl = std::min(y0 + kPyH - 1, D.h - 1);
+      const int syLo = std::min(std::max((int)t[y0].s, 0), S.h - 1), syHi = std::min(std::max((int)t[yl].s + 1, 0), S.h - 1);
+      ty.push_back(make_int2(syLo, syHi - syLo + 1));
+    }
   }
+  if ((o->tileX.n < tx.size() && o->tileX.alloc(tx.size() + 1)) || (o->tileY.n < ty.size() && o->tileY.alloc(ty.size() + 1))) return PGB_ERR_CUDA;
+  if (!tx.empty()) PGB_CUDA(cudaMemcpyAsync(o->tileX.p, tx.data(), tx.size() * sizeof(int2), cudaMemcpyHostToDevice, o->stream));
+  if (!ty.empty()) PGB_CUDA(cudaMemcpyAsync(o->tileY.p, ty.data(), ty.size() * sizeof(int2), cudaMemcpyHostToDevice, o->stream));
   if (xs.size() > o->xtab.n || ys.size() > o->ytab.n) return fail(PGB_ERR_CAPACITY, "resize tables exceed capacity");
   if (!xs.empty()) PGB_CUDA(cudaMemcpyAsync(o->xtab.p, xs.data(), xs.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, o->stream));
   if (!ys.empty()) PGB_CUDA(cudaMemcpyAsync(o->ytab.p, ys.data(), ys.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, o->stream));
@@ -282,7 +304,8 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
     switch (s) {
       case 0:
         for (int l = 1; l < g.nlevels; l++)
-          launch_pyramid_level(g, l, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l], st);
+          launch_pyramid_level(g, l, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l],
+                               o->tileX.p + o->tileXOff[l], o->tileY.p + o->tileYOff[l], st);
         break;
       case 1:
       {

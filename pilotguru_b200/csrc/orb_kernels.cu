@@ -48,14 +48,17 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeo g, int level, uint8_t* _
   *reinterpret_cast<uint32_t*>(frame + D.off + (size_t)y * D.pitch + (size_t)xq * 4) = packed;
 }
 
-// Tiled variant: a CTA produces a 256 x 16 destination tile.  The source rows it needs are staged in shared memory
+// Tiled variant: a CTA produces a 256 x 32 destination tile; the source footprint of every tile column / tile row
+// comes from small host-built tables (one independent load each: the round-1 profile showed 56 % of the kernel's
+// stall samples before the first barrier, on the dependent xtab/ytab -> address -> load chain).  The source rows it needs are staged in shared memory
 // with 16-byte loads, the horizontal pass runs once per source row (not once per destination row, a 1.3x saving at
 // scale 1.2) and the vertical pass reads its two rows from shared memory.  Same integer arithmetic as k_pyramid.
-constexpr int kPyW = 256, kPyH = 16, kPySrcPitch = 416, kPySrcRows = 28;
+constexpr int kPySrcPitch = 416, kPySrcRows = 44;  // kPyW x kPyH = 256 x 32 destination tile (orb_kernels.cuh)
 
 __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint8_t* __restrict__ pyr,
                                                        const ResizeTab* __restrict__ xtab,
-                                                       const ResizeTab* __restrict__ ytab) {
+                                                       const ResizeTab* __restrict__ ytab,
+                                                       const int2* __restrict__ tileX, const int2* __restrict__ tileY) {
   __shared__ __align__(16) uint8_t s_src[kPySrcRows * kPySrcPitch];
   __shared__ uint16_t s_h[kPySrcRows * kPyW];
   __shared__ ResizeTab s_ty[kPyH];
@@ -65,67 +68,80 @@ __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint
   const int x0 = blockIdx.x * kPyW, y0 = blockIdx.y * kPyH;
   uint8_t* frame = pyr + (size_t)blockIdx.z * g.frameStride;
   const uint8_t* src = frame + S.off;
-  const int xl = min(x0 + kPyW - 1, D.w - 1), yl = min(y0 + kPyH - 1, D.h - 1);
-  const int sxLo = xtab[x0].s, sxHi = min((int)xtab[xl].s + 1, S.w - 1);
-  const int syLo = min(max((int)ytab[y0].s, 0), S.h - 1), syHi = min(max((int)ytab[yl].s + 1, 0), S.h - 1);
-  const int ax = sxLo & ~15;
-  const int nvec = (sxHi - ax + 16) >> 4, nrows = syHi - syLo + 1;  // host guarantees nvec*16 <= pitch, nrows <= rows
+  const int2 fx = __ldg(&tileX[blockIdx.x]), fy = __ldg(&tileY[blockIdx.y]);
+  const int ax = fx.x, nvec = fx.y, syLo = fy.x, nrows = fy.y;  // host guarantees nvec*16 <= pitch, nrows <= rows
   if (tid < kPyH) s_ty[tid] = ytab[min(y0 + tid, D.h - 1)];
-  for (int i = tid; i < nvec * nrows; i += 256) {
-    const int r = i / nvec, c = i - r * nvec;
-    const int gx = ax + c * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (gx < S.pitch) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(syLo + r) * S.pitch + gx));
-    *reinterpret_cast<uint4*>(s_src + r * kPySrcPitch + c * 16) = v;
+  {  // staging: warp = source row (stride 8), lane = 16-byte vector (nvec <= 26): no index division
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane < nvec) {
+      const int gx = ax + lane * 16;
+      const bool in = gx < S.pitch;
+      for (int r = warp; r < nrows; r += 8) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (in) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(syLo + r) * S.pitch + gx));
+        *reinterpret_cast<uint4*>(s_src + r * kPySrcPitch + lane * 16) = v;
+      }
+    }
   }
   __syncthreads();
-  // horizontal pass: thread = destination column
+  // horizontal pass: thread = destination column, 4 source rows in flight
   {
     const int x = min(x0 + tid, D.w - 1);
     const ResizeTab tx = xtab[x];
     const int o0 = tx.s - ax, o1 = min((int)tx.s + 1, S.w - 1) - ax;
     const int a0 = tx.a0, a1 = tx.a1;
-    for (int r = 0; r < nrows; r++) {
-      const uint8_t* row = s_src + r * kPySrcPitch;
-      s_h[r * kPyW + tid] = (uint16_t)(((int)row[o0] * a0 + (int)row[o1] * a1) >> 4);
+    const uint8_t* c0 = s_src + o0;
+    const uint8_t* c1 = s_src + o1;
+    uint16_t* hcol = s_h + tid;
+    int r = 0;
+    for (; r + 4 <= nrows; r += 4) {
+      int v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = (int)c0[(r + u) * kPySrcPitch] * a0 + (int)c1[(r + u) * kPySrcPitch] * a1;
+#pragma unroll
+      for (int u = 0; u < 4; u++) hcol[(r + u) * kPyW] = (uint16_t)(v[u] >> 4);
     }
+    for (; r < nrows; r++) hcol[r * kPyW] = (uint16_t)(((int)c0[r * kPySrcPitch] * a0 + (int)c1[r * kPySrcPitch] * a1) >> 4);
   }
   __syncthreads();
-  // vertical pass: thread = 4 adjacent columns x 4 rows, one 32-bit store per row
+  // vertical pass: thread = 4 adjacent columns x 8 rows; the 4 u16 of a row come in one 8-byte load, one 32-bit store
+  // per row.  Columns beyond the level's width land in the pitch padding (pitch is a multiple of 64 >= w), which no
+  // consumer reads, so they are not masked.
   {
     const int q = tid & 63, rr = tid >> 6;
     const int gx = x0 + q * 4;
     if (gx < D.w) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < kPyH / 4; k++) {
         const int ry = rr + 4 * k, gy = y0 + ry;
         if (gy >= D.h) break;
         const ResizeTab ty = s_ty[ry];
         const int r0 = min(max((int)ty.s, 0), S.h - 1) - syLo, r1 = min(max((int)ty.s + 1, 0), S.h - 1) - syLo;
-        const uint16_t* h0 = s_h + r0 * kPyW + q * 4;
-        const uint16_t* h1 = s_h + r1 * kPyW + q * 4;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int v = ((((int)ty.a0 * (int)h0[c]) >> 16) + (((int)ty.a1 * (int)h1[c]) >> 16) + 2) >> 2;
-          if (gx + c < D.w) packed |= (uint32_t)(v & 0xff) << (8 * c);
-        }
-        *reinterpret_cast<uint32_t*>(frame + D.off + (size_t)gy * D.pitch + gx) = packed;
+        const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + r0 * kPyW + q * 4);
+        const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + r1 * kPyW + q * 4);
+        const int b0 = ty.a0, b1 = ty.a1;
+        const int v0 = (((b0 * (int)(h0.x & 0xffffu)) >> 16) + ((b1 * (int)(h1.x & 0xffffu)) >> 16) + 2) >> 2;
+        const int v1 = (((b0 * (int)(h0.x >> 16)) >> 16) + ((b1 * (int)(h1.x >> 16)) >> 16) + 2) >> 2;
+        const int v2 = (((b0 * (int)(h0.y & 0xffffu)) >> 16) + ((b1 * (int)(h1.y & 0xffffu)) >> 16) + 2) >> 2;
+        const int v3 = (((b0 * (int)(h0.y >> 16)) >> 16) + ((b1 * (int)(h1.y >> 16)) >> 16) + 2) >> 2;
+        // every v is in [0, 255] (a convex combination of bytes), so the bytes can be packed without masking
+        *reinterpret_cast<uint32_t*>(frame + D.off + (size_t)gy * D.pitch + gx) =
+            (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
       }
     }
   }
 }
 
 void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
-                          const ResizeTab* ytab, cudaStream_t st) {
+                          const ResizeTab* ytab, const int2* tileX, const int2* tileY, cudaStream_t st) {
   const LevelGeo& D = g.lv[level];
   const LevelGeo& S = g.lv[level - 1];
   // does the source footprint of a 256x16 tile fit the static staging buffers?  (true for scale factors <= ~1.5)
   const double rx = (double)S.w / D.w, ry = (double)S.h / D.h;
-  const bool fits = rx * kPyW + 34 <= kPySrcPitch && ry * kPyH + 3 <= kPySrcRows;
+  const bool fits = pyramid_tile_fits(S.w, S.h, D.w, D.h);
   if (fits) {
     dim3 grid((D.w + kPyW - 1) / kPyW, (D.h + kPyH - 1) / kPyH, nFrames);
-    k_pyramid_tiled<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab);
+    k_pyramid_tiled<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab, tileX, tileY);
   } else {
     dim3 grid((((D.w + 3) >> 2) + 255) / 256, D.h, nFrames);
     k_pyramid<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab);

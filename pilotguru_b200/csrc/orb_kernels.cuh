@@ -20,6 +20,13 @@ constexpr int kEdge = 19;        // EDGE_THRESHOLD (ORBextractor.cc:74)
 constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3 (ORBextractor.cc:773)
 constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
 
+// pyramid kernel: destination tile of k_pyramid_tiled and the capacity of its source staging buffers
+constexpr int kPyW = 256, kPyH = 32;
+inline bool pyramid_tile_fits(int sw, int sh, int dw, int dh) {
+  const double rx = (double)sw / dw, ry = (double)sh / dh;
+  return rx * kPyW + 34 <= 416 && ry * kPyH + 3 <= 44;
+}
+
 // FAST score kernel: one CTA per 256x64 tile, TMA-staged with a halo
 constexpr int kF2W = 256, kF2H = 64, kF2Threads = 256;
 constexpr int kF2InWords = kF2W / 4 + 8;  // 72 words per row: 16-byte halo left and right (a TMA box must start
@@ -69,7 +76,7 @@ struct StagedKp {
 enum OrbErr { kErrCandOverflow = 1, kErrNodeOverflow = 2, kErrOutCap = 4, kErrCellChunks = 8 };
 
 void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
-                          const ResizeTab* ytab, cudaStream_t st);
+                          const ResizeTab* ytab, const int2* tileX, const int2* tileY, cudaStream_t st);
 int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st);
 void launch_cells(const OrbGeo& g, int nFrames, const int* cellTab, const uint8_t* score, uint32_t* slots, int* cellCnt,
