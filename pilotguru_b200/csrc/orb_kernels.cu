@@ -579,7 +579,8 @@ void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const in
 constexpr int kOdWarps = 4;
 constexpr int kPR = 22;            // patch radius: 19 (pattern reach) + 3 (blur)
 constexpr int kPW = 2 * kPR + 1;   // 45
-constexpr int kPP = 52;            // shared-memory row pitch of the patch: 13 aligned words cover 45 px at any phase
+constexpr int kPP = 52;            // shared-memory row pitch of the patch: 13 aligned words cover 45 px at any phase (odd word
+                                   // count: column walks are bank-conflict free)
 constexpr int kBR = 19;
 constexpr int kBW = 2 * kBR + 1;   // 39
 
@@ -655,14 +656,30 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
   const int xs = kp.x - kPR, ys = kp.y - kPR;
   int po = 0;
   if (xs >= 0 && ys >= 0 && xs + 2 * kPR < L.w && ys + 2 * kPR < L.h) {
-    const int a = xs & ~3;
-    po = xs - a;
-    const int nw = ((xs + 2 * kPR) >> 2) - (a >> 2) + 1;  // <= 13
-    for (int i = lane; i < kPW * 13; i += 32) {
-      const int r = (i * 5042) >> 16, k = i - r * 13;  // exact i / 13 for i < 585
-      if (k < nw)
-        reinterpret_cast<uint32_t*>(Pw + r * kPP)[k] =
-            __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(ys + r) * L.pitch + a) + k);
+    // 45 rows x 4 vectors of 16 bytes = 180 loads, 6 per lane, all issued before the first shared-memory store (the
+    // round-1 profile had 39 % of this kernel's stall samples on a word-at-a-time version of this loop); the 13 words
+    // of a row that hold the patch are then stored at the odd 13-word pitch
+    const int a = xs & ~15, a4 = xs & ~3;
+    po = xs - a4;
+    const int woff = (a4 - a) >> 2;  // first useful word of the 16 loaded per row
+    uint4 v[6];
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+      const int i = lane + 32 * u, r = i >> 2, k = i & 3;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (r < kPW && a + 16 * k < L.pitch) v[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)(ys + r) * L.pitch + a) + k);
+    }
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+      const int i = lane + 32 * u, r = i >> 2, k = i & 3;
+      if (r < kPW) {
+        uint32_t* row = reinterpret_cast<uint32_t*>(Pw + r * kPP);
+        const int w0 = 4 * k - woff;  // shared-memory word index of v[u].x
+        if (w0 >= 0 && w0 < 13) row[w0] = v[u].x;
+        if (w0 + 1 >= 0 && w0 + 1 < 13) row[w0 + 1] = v[u].y;
+        if (w0 + 2 >= 0 && w0 + 2 < 13) row[w0 + 2] = v[u].z;
+        if (w0 + 3 >= 0 && w0 + 3 < 13) row[w0 + 3] = v[u].w;
+      }
     }
   } else {
     for (int i = lane; i < kPW * kPW; i += 32) {
