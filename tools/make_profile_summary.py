@@ -1,0 +1,76 @@
+#!/usr/bin/env python3
+"""Turns the raw artefacts of a GPU run into the tracked summaries under profiles/ (run here, no GPU needed):
+    python tools/make_profile_summary.py r01 gpurun_out/launches_r1d.csv gpurun_out/bench_r1d.json gpurun_out/stages_r1d.ncu-rep
+ * <tag>_launches_summary.md : ncu launch list (gpu__time_duration per launch) aggregated per kernel, shares next to the
+                               live CUDA-event stage times of the bench line
+ * <tag>_kernels_ncu_full.md : one row per kernel of the `ncu --set full` capture (tools/gpu_stage_profile.py)
+ * copies of the bench line and the launch list themselves"""
+import collections, csv, io, json, os, shutil, subprocess, sys
+
+tag, launches_csv, bench_json, stages_rep = sys.argv[1:5]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+os.makedirs(P, exist_ok=True)
+shutil.copy(launches_csv, os.path.join(P, f"{tag}_launches_bench_b64.csv"))
+shutil.copy(bench_json, os.path.join(P, f"{tag}_bench_n1.json"))
+
+rows = [r for r in csv.reader(open(launches_csv)) if len(r) > 5]
+for i, r in enumerate(rows):
+    if r[0] == 'ID':
+        hdr = r; rows = rows[i + 1:]; break
+ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
+agg = collections.OrderedDict()
+for r in rows:
+    agg.setdefault(r[ki].split('(')[0].replace('void ', ''), []).append(float(r[vi].replace(',', '')) / 1000)
+tot = sum(sum(v) for v in agg.values())
+b = json.load(open(bench_json))
+st = b['stage_us_per_frame']; s = sum(st.values())
+stage_of = {'pgb::k_pyramid_tiled': 'pyramid', 'pgb::k_fast_score<4>': 'fast_score', 'pgb::k_cells': 'cell_nms', 'pgb::k_octree': 'octree',
+            'pgb::k_orient_desc': 'orient_desc', 'pgb::k_match': 'match', 'pgb::k_match_resolve': 'match'}
+out = [f"# {tag} launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 python bench.py --steps 2 --warmup 1 --batch 64 --no-cpu-baseline --no-calibration`",
+       "Per-launch times under ncu are cold-cache and serialised: compare SHARES with the live CUDA-event stage times, not absolutes.", "",
+       "| kernel | launches | total us | avg us | share (ncu) |", "|---|---|---|---|---|"]
+share_ncu = collections.Counter()
+for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    out.append(f"| `{k}` | {len(v)} | {sum(v):.1f} | {sum(v) / len(v):.1f} | {sum(v) / tot:.3f} |")
+    if k in stage_of: share_ncu[stage_of[k]] += sum(v) / tot
+out += ["", f"Live stage times of the same workload (bench line {os.path.basename(bench_json)}: value {b['value']:.0f} frames/s, e2e {b['e2e']['value']:.0f} frames/s):", "",
+        "| stage | us/frame (CUDA events) | share live | share ncu |", "|---|---|---|---|"]
+for k, v in st.items():
+    out.append(f"| {k} | {v:.2f} | {v / s:.3f} | {share_ncu[k]:.3f} |")
+r = b['roofline']
+out += ["", f"`k_fast_score`: {r['us_per_launch']:.1f} us per 64-frame launch -> {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of {r['peak']:.0f} GB/s ({r['peak_source']})."]
+open(os.path.join(P, f"{tag}_launches_summary.md"), "w").write("\n".join(out) + "\n")
+
+raw = subprocess.run(["ncu", "-i", stages_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(io.StringIO(raw)))
+h, units, data = rr[0], rr[1], rr[2:]
+cols = [('gpu__time_duration.sum', 'us'), ('launch__grid_size', 'grid'), ('launch__registers_per_thread', 'regs'), ('smsp__inst_executed.sum', 'warp-inst'),
+        ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue %'), ('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'ALU pipe %'),
+        ('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'FMA pipe %'), ('l1tex__throughput.avg.pct_of_peak_sustained_active', 'L1/smem %'),
+        ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %'), ('dram__bytes_read.sum', 'DRAM rd MB'), ('dram__bytes_write.sum', 'DRAM wr MB'),
+        ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM %')]
+nb = [l for l in open(os.path.join(ROOT, "gpurun_out", "ncu_stages.log")) if 'profiled stages over' in l]
+out = [f"# {tag} `ncu --profile-from-start off --set full --clock-control none --import-source on python tools/gpu_stage_profile.py`",
+       "One pass of every stage kernel over a resident batch (" + (nb[-1].strip() if nb else "32 frames") + ").", "",
+       "| kernel | " + " | ".join(c[1] for c in cols) + " |", "|---|" + "---|" * len(cols)]
+for d in data:
+    name = d[h.index('Kernel Name')].split('(')[0].replace('void ', '')
+    vals = []
+    for c, _ in cols:
+        v = d[h.index(c)]
+        try:
+            v = f"{float(v):.1f}" if '.' in v else v
+        except ValueError:
+            pass
+        vals.append(v)
+    out.append(f"| `{name}` | " + " | ".join(vals) + " |")
+fs = [d for d in data if 'k_fast_score' in d[h.index('Kernel Name')]]
+if fs:
+    d = fs[0]
+    rd, wr = float(d[h.index('dram__bytes_read.sum')]), float(d[h.index('dram__bytes_write.sum')])
+    n = 32
+    out += ["", f"`k_fast_score`: DRAM traffic {rd + wr:.1f} MB per {n}-frame launch = {(rd + wr) / n:.2f} MB/frame (algorithmic 12.84 MB/frame; part of the score map is still dirty in L2 when the kernel ends).",
+            "Reading: issue slots and the half-rate ALU pipe are busy, DRAM is not: the kernel is bound by ALU-pipe instruction issue (see DESIGN.md section 4 and r01_pipe_probe.txt)."]
+open(os.path.join(P, f"{tag}_kernels_ncu_full.md"), "w").write("\n".join(out) + "\n")
+print("wrote", [f for f in os.listdir(P) if f.startswith(tag)])
