@@ -116,3 +116,31 @@ def test_size_independent_properties_full_size_batch():
         assert np.all(np.bincount(k1[t, :n]["octave"], minlength=8) <= ex.features_per_level() + 2)
         assert 900 < n <= ex.cap
     ex.close()
+
+
+def test_host_frame_pipeline_matches_resident():
+    """PGB_OUT_DEVICE (host frames copied in chunks 4, 8, 16, ..., 2, 2, 1 on a copy stream while three compute
+    streams alternate over the chunks) must give exactly what the device-resident call gives, for an odd batch size,
+    and keep doing so when the call is repeated (the copy stream must not overtake the previous call's kernels)."""
+    import torch
+    from pilotguru_b200.orb import ORBextractor
+    n, w, h = 37, 640, 480
+    frames = np.stack([synth.frame(t, w=w, h=h) for t in range(n)])
+    ex = _mk(500, w, h, batch=n)
+    cap = ex.cap
+    host = torch.from_numpy(frames).pin_memory()
+    dev = host.cuda()
+    outs = []
+    for where, ptr in ((ORBextractor.IN_DEVICE | ORBextractor.OUT_DEVICE, dev.data_ptr()), (ORBextractor.OUT_DEVICE, host.data_ptr()),
+                       (ORBextractor.OUT_DEVICE, host.data_ptr())):
+        kps = torch.zeros((n, cap, 7), dtype=torch.float32, device="cuda"); desc = torch.zeros((n, cap, 32), dtype=torch.uint8, device="cuda")
+        counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ex.extract_ptr(ptr, where, n, w, h, w, w * h, kps.data_ptr(), desc.data_ptr(), counts.data_ptr(), cap)
+        ex.check()
+        outs.append((kps.cpu().numpy().view(np.uint32), desc.cpu().numpy(), counts.cpu().numpy()))
+    for o in outs[1:]:
+        assert np.array_equal(o[2], outs[0][2]) and (outs[0][2] > 300).all()
+        for t in range(n):
+            c = outs[0][2][t]
+            assert np.array_equal(o[0][t, :c], outs[0][0][t, :c]) and np.array_equal(o[1][t, :c], outs[0][1][t, :c])
+    ex.close()
