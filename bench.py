@@ -90,6 +90,29 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and, by first touch, its pinned frame buffers) to the NUMA node the GPU hangs off:
+    with 8 ranks each pulling 133 MB per step over PCIe, remote-socket host memory is the first e2e bottleneck."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def cpu_frames(n):
     from pilotguru_b200 import synth
     fr = np.stack([synth.frame(t) for t in range(n)])
@@ -192,6 +215,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
@@ -312,6 +336,7 @@ def main():
                                        "SearchByProjection vs previous frame (BASELINE configs[1], batched)",
                            "frames_per_gpu_per_step": B, "global_frames_per_step": frames_total,
                            "l2": f"inputs larger than L2: {B * W * H / 1e6:.0f} MB of frames + {B * 6.4:.0f} MB pyramid per step",
+                           "host_numa_node_rank0": numa,
                            "parallelism": f"frames sharded over {world} GPU(s); one NCCL all-gather of per-frame keypoint/descriptor records per step" if world > 1 else "1 GPU"},
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K, "h2d_only_ms_per_step": ms_h2d,

@@ -166,11 +166,14 @@ void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr,
 // reference's row-major order.  (Round-1 profile of the previous word-scan version: 1120 warp-instructions per cell,
 // a third of them in the candidate scan; this one needs about a third of that.)
 constexpr int kCellWarps = 4;
+constexpr int kCellListCap = 256;  // window over a cell's candidate sequence (natural images: one window)
 
 __global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const int* __restrict__ cellTab,
                                                            const uint8_t* __restrict__ score,
                                                            uint32_t* __restrict__ slots, int* __restrict__ cellCnt,
                                                            int* __restrict__ err) {
+  __shared__ uint16_t s_list[kCellWarps][kCellListCap];
+  __shared__ __align__(16) uint32_t s_keep[kCellWarps][64 * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x * kCellWarps + warp;
   if (cell >= g.totalCells) return;
@@ -202,17 +205,15 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const int* 
   const int nvec = (rx1 - a16 + 15) >> 4;  // <= 5
   const int iniTh = g.iniTh;
 
-  // masks are kept as 32-bit halves [pass][half]: bit = x - rx0 - 32 * half (cells are rarely wider than 32)
-  uint32_t keep[2][2] = {{0u, 0u}, {0u, 0u}}, keep20[2][2] = {{0u, 0u}, {0u, 0u}};
-  const int nHalf = tw > 32 ? 2 : 1;
+  // ---- 1. per-lane candidate masks (bit = x - rx0), two passes of 32 rows
+  unsigned long long cand[2] = {0ull, 0ull};
 #pragma unroll
   for (int c = 0; c < 2; c++) {
     if (32 * c >= th) break;  // warp-uniform
     const int row = lane + 32 * c;
     if (row < th) {
-      const int y = ry0 + row;
-      const uint8_t* rowp = S + (size_t)y * pitch;
-      unsigned long long cand = 0ull;
+      const uint8_t* rowp = S + (size_t)(ry0 + row) * pitch;
+      unsigned long long cm = 0ull;
       for (int v = 0; v < nvec; v++) {
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(rowp + a16 + 16 * v));
         const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
@@ -225,55 +226,107 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const int* 
           m16 |= ((((nz >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * k);
         }
         const int off = a16 + 16 * v - rx0;  // x of the vector's byte 0 relative to the rectangle: -15 .. 63
-        cand |= off >= 0 ? ((unsigned long long)m16 << off) : ((unsigned long long)(m16 >> (-off)));
+        cm |= off >= 0 ? ((unsigned long long)m16 << off) : ((unsigned long long)(m16 >> (-off)));
       }
-      if (tw < 64) cand &= (1ull << tw) - 1ull;
-      // neighbours outside the rectangle count 0; the loads themselves are always inside the level (rectangles
-      // start >= 19 px from every image border), so they are issued unconditionally and masked afterwards
-      const bool top = row > 0, bot = row < th - 1;
-      for (int hf = 0; hf < nHalf; hf++) {
-        uint32_t m = hf ? (uint32_t)(cand >> 32) : (uint32_t)cand;
-        uint32_t kp = 0, kp20 = 0;
+      if (tw < 64) cm &= (1ull << tw) - 1ull;
+      cand[c] = cm;
+    }
+  }
+  // ---- 2. compact the candidates into a list so that the neighbour test keeps all 32 lanes busy (the candidates of a
+  //         cell sit in a few rows: per-lane loops ran at 6 of 32 lanes in the round-1 profile).  The list is a
+  //         window of kCellListCap entries over the row-major candidate sequence (one window on natural images);
+  //         survivors are reported back to per-row masks in shared memory.  Shared memory is kept small on purpose:
+  //         the neighbour loads live on L1 hits, and L1 is what the shared-memory carve-out leaves.
+  uint16_t* list = s_list[warp];              // row | bx << 6
+  uint32_t* rowKeep = s_keep[warp];           // [64 rows][4]: keep lo, keep hi, keep20 lo, keep20 hi
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    uint4* rk = reinterpret_cast<uint4*>(rowKeep + 4 * (lane + 32 * c));
+    *rk = make_uint4(0u, 0u, 0u, 0u);
+  }
+  const int cnt0 = __popcll(cand[0]), cnt1 = __popcll(cand[1]);
+  int incl = cnt0;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int tot0 = __shfl_sync(0xffffffffu, incl, 31);
+  int pos0 = incl - cnt0, pos1 = 0, total = tot0;
+  if (th > 32) {
+    int in1 = cnt1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, in1, d);
+      if (lane >= d) in1 += v;
+    }
+    pos1 = tot0 + in1 - cnt1;
+    total = tot0 + __shfl_sync(0xffffffffu, in1, 31);
+  }
+  __syncwarp();
+  for (int base = 0; base < total; base += kCellListCap) {
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      if (32 * c >= th) break;
+      int pos = (c ? pos1 : pos0) - base;
+      const uint32_t rowcode = (uint32_t)(lane + 32 * c);
+      for (int hf = 0; hf < 2; hf++) {
+        uint32_t m = hf ? (uint32_t)(cand[c] >> 32) : (uint32_t)cand[c];
         while (m) {
           const uint32_t low = m & (0u - m);
           m ^= low;
-          const int bx = 31 - __clz(low) + 32 * hf;
-          const uint8_t* p = rowp + rx0 + bx;
-          const int sc = __ldg(p);
-          int nw = __ldg(p - pitch - 1), n = __ldg(p - pitch), ne = __ldg(p - pitch + 1);
-          const int w = __ldg(p - 1), e = __ldg(p + 1);
-          int sw = __ldg(p + pitch - 1), so = __ldg(p + pitch), se = __ldg(p + pitch + 1);
-          if (!top) { nw = 0; n = 0; ne = 0; }
-          if (!bot) { sw = 0; so = 0; se = 0; }
-          int left = max(max(nw, w), sw), right = max(max(ne, e), se);
-          if (bx == 0) left = 0;
-          if (bx == tw - 1) right = 0;
-          if (max(max(left, right), max(n, so)) < sc) {
-            kp |= low;
-            if (sc >= iniTh) kp20 |= low;
-          }
+          if (pos >= 0 && pos < kCellListCap) list[pos] = (uint16_t)(rowcode | ((uint32_t)(31 - __clz(low) + 32 * hf) << 6));
+          pos++;
         }
-        keep[c][hf] = kp;
-        keep20[c][hf] = kp20;
       }
     }
+    __syncwarp();
+    // ---- 3. neighbour test, one candidate per lane.  Neighbours outside the rectangle count 0; the loads themselves
+    //         are always inside the level (rectangles start >= 19 px from every border), so they are issued
+    //         unconditionally and masked afterwards.
+    const int nwin = min(kCellListCap, total - base);
+    for (int i = lane; i < nwin; i += 32) {
+      const uint32_t e = list[i];
+      const int row = e & 63, bx = (e >> 6) & 63;
+      const uint8_t* p = S + (size_t)(ry0 + row) * pitch + rx0 + bx;
+      const int sc = __ldg(p);
+      int nw = __ldg(p - pitch - 1), n = __ldg(p - pitch), ne = __ldg(p - pitch + 1);
+      const int w = __ldg(p - 1), ea = __ldg(p + 1);
+      int sw = __ldg(p + pitch - 1), so = __ldg(p + pitch), se = __ldg(p + pitch + 1);
+      if (row == 0) { nw = 0; n = 0; ne = 0; }
+      if (row == th - 1) { sw = 0; so = 0; se = 0; }
+      int left = max(max(nw, w), sw), right = max(max(ne, ea), se);
+      if (bx == 0) left = 0;
+      if (bx == tw - 1) right = 0;
+      if (max(max(left, right), max(n, so)) < sc) {
+        uint32_t* rk = rowKeep + 4 * row + (bx >> 5);
+        atomicOr(rk, 1u << (bx & 31));
+        if (sc >= iniTh) atomicOr(rk + 2, 1u << (bx & 31));
+      }
+    }
+    __syncwarp();
   }
-  const bool any20 = __any_sync(0xffffffffu, (keep20[0][0] | keep20[0][1] | keep20[1][0] | keep20[1][1]) != 0u);
+  // ---- 4. emit the survivors (at iniTh if there is any, else at minTh): lane order = row order, bit order = x order
+  uint4 rk[2];
+#pragma unroll
+  for (int c = 0; c < 2; c++) rk[c] = *reinterpret_cast<const uint4*>(rowKeep + 4 * (lane + 32 * c));
+  const bool any20 = __any_sync(0xffffffffu, (rk[0].z | rk[0].w | rk[1].z | rk[1].w) != 0u);
   uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)ci * L.slotCap;
+  const int nHalf = tw > 32 ? 2 : 1;
   int basei = 0;
 #pragma unroll
   for (int c = 0; c < 2; c++) {
     if (32 * c >= th) break;
-    const uint32_t s0 = any20 ? keep20[c][0] : keep[c][0], s1 = any20 ? keep20[c][1] : keep[c][1];
+    const uint32_t s0 = any20 ? rk[c].z : rk[c].x, s1 = any20 ? rk[c].w : rk[c].y;
     const int n = __popc(s0) + __popc(s1);
-    int incl = n;
+    int in2 = n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
+      const int v = __shfl_up_sync(0xffffffffu, in2, d);
+      if (lane >= d) in2 += v;
     }
-    int pos = basei + incl - n;
-    basei += __shfl_sync(0xffffffffu, incl, 31);
+    int pos = basei + in2 - n;
+    basei += __shfl_sync(0xffffffffu, in2, 31);
     const int y = ry0 + lane + 32 * c;
     for (int hf = 0; hf < nHalf; hf++) {
       uint32_t m = hf ? s1 : s0;
