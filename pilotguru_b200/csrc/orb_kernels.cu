@@ -636,6 +636,7 @@ constexpr int kPP = 52;            // shared-memory row pitch of the patch: 13 a
                                    // count: column walks are bank-conflict free)
 constexpr int kBR = 19;
 constexpr int kBW = 2 * kBR + 1;   // 39
+constexpr int kHP = 40;            // row pitch of the horizontally blurred patch (u16): even, so two outputs go in one store
 
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 __device__ const signed char d_pattern[1024] = PGB200_ORB_PATTERN_INIT;
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
                                                                uint8_t* __restrict__ desc, int* __restrict__ counts,
                                                                int cap, int* __restrict__ err) {
   __shared__ __align__(4) uint8_t s_patch[kOdWarps][kPW * kPP];
-  __shared__ uint16_t s_h[kOdWarps][kPW * kBW + 1];
+  __shared__ __align__(4) uint16_t s_h[kOdWarps][kPW * kHP];
   __shared__ uint8_t s_blur[kOdWarps][kBW * kBW + 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kOdWarps + warp;
@@ -756,20 +757,50 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
   const float angle = fast_atan2_dev((float)m01, (float)m10);
-  // horizontal then vertical pass of the 7x7 sigma=2 fixed-point Gaussian {18,34,48,56,48,34,18}
+  // horizontal then vertical pass of the 7x7 sigma=2 fixed-point Gaussian {18,34,48,56,48,34,18}, with register
+  // sliding windows instead of 7 shared-memory loads per output (the round-1 profile had this kernel at 91 % of the
+  // shared-memory pipe).  Horizontal: lane = patch row; the row's 13 words are realigned to the patch phase (po is
+  // warp-uniform), adjacent pixels are packed as two 16-bit halves, and one multiply-add chain yields two outputs
+  // (a half never exceeds 256 * 255).  Vertical: lane = (column, third of the rows).
   uint16_t* Hh = s_h[warp];
-  for (int i = lane; i < kPW * kBW; i += 32) {
-    const int r = i / kBW, c = i - r * kBW;
-    const uint8_t* p = P + r * kPP + c;  // columns c .. c+6 of the patch <=> blurred column c (offset 3)
-    Hh[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+  for (int r = lane; r < kPW; r += 32) {
+    const uint32_t* wrow = reinterpret_cast<const uint32_t*>(Pw + r * kPP);
+    uint32_t w[13], al[12];
+#pragma unroll
+    for (int k = 0; k < 13; k++) w[k] = wrow[k];
+#pragma unroll
+    for (int k = 0; k < 12; k++) al[k] = __funnelshift_r(w[k], w[k + 1], 8 * po);  // bytes 4k .. 4k+3 of the patch row
+    uint32_t pr[46];  // pr[j] = pixel j | pixel j+1 << 16
+#pragma unroll
+    for (int j = 0; j < 46; j++) {
+      const int k = j >> 2;
+      switch (j & 3) {
+        case 0: pr[j] = __byte_perm(al[k], 0u, 0x4140); break;
+        case 1: pr[j] = __byte_perm(al[k], 0u, 0x4241); break;
+        case 2: pr[j] = __byte_perm(al[k], 0u, 0x4342); break;
+        default: pr[j] = __byte_perm(al[k], al[k + 1], 0x0403) & 0x00ff00ffu; break;  // j <= 43 here: k + 1 <= 11
+      }
+    }
+    uint32_t* hrow = reinterpret_cast<uint32_t*>(Hh + r * kHP);
+#pragma unroll
+    for (int c = 0; c < kBW + 1; c += 2)  // columns c and c+1 (column 39 is padding)
+      hrow[c >> 1] = 18u * (pr[c] + pr[c + 6]) + 34u * (pr[c + 1] + pr[c + 5]) + 48u * (pr[c + 2] + pr[c + 4]) + 56u * pr[c + 3];
   }
   __syncwarp();
   uint8_t* Bl = s_blur[warp];
-  for (int i = lane; i < kBW * kBW; i += 32) {
-    const int r = i / kBW, c = i - r * kBW;
-    const uint16_t* p = Hh + r * kBW + c;
-    const int acc = 18 * (p[0] + p[6 * kBW]) + 34 * (p[kBW] + p[5 * kBW]) + 48 * (p[2 * kBW] + p[4 * kBW]) + 56 * p[3 * kBW];
-    Bl[i] = (uint8_t)((acc + 32768) >> 16);
+#pragma unroll 1
+  for (int id = lane; id < 3 * kBW; id += 32) {
+    const int t = id / kBW, c = id - t * kBW;
+    const uint16_t* hc = Hh + (13 * t) * kHP + c;
+    int h[19];
+#pragma unroll
+    for (int k = 0; k < 19; k++) h[k] = hc[k * kHP];
+    uint8_t* out = Bl + (13 * t) * kBW + c;
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+      const int acc = 18 * (h[k] + h[k + 6]) + 34 * (h[k + 1] + h[k + 5]) + 48 * (h[k + 2] + h[k + 4]) + 56 * h[k + 3];
+      out[k * kBW] = (uint8_t)((acc + 32768) >> 16);
+    }
   }
   __syncwarp();
   // rBRIEF: lane = descriptor byte
