@@ -277,14 +277,26 @@ def main():
     with torch.cuda.stream(stream):
         dev_step = lambda: step(dev_frames.data_ptr(), ORBextractor.IN_DEVICE | ORBextractor.OUT_DEVICE)
 
+        d2h_stream = torch.cuda.Stream()
+        ev_feat = torch.cuda.Event()
+
         def e2e_step():
-            step(host_frames.data_ptr(), ORBextractor.OUT_DEVICE)          # H2D of the frames inside the call
-            h_counts.copy_(xch.counts_view(), non_blocking=True)           # D2H of the step's results
-            h_kps.copy_(xch.kps_view()[1:], non_blocking=True)
-            h_desc.copy_(xch.desc_view()[1:], non_blocking=True)
-            h_match.copy_(match, non_blocking=True)
+            xch.carry_last()
+            ex.extract_ptr(host_frames.data_ptr(), ORBextractor.OUT_DEVICE, B, W, H, W, W * H, xch.kps_ptr(1), xch.desc_ptr(1),
+                           xch.counts_ptr(1), cap)                         # H2D of the frames inside the call
+            xch.exchange(stream)
+            ev_feat.record(stream)
+            with torch.cuda.stream(d2h_stream):                            # D2H of the features while the matcher runs
+                d2h_stream.wait_event(ev_feat)
+                h_counts.copy_(xch.counts_view(), non_blocking=True)
+                h_kps.copy_(xch.kps_view()[1:], non_blocking=True)
+                h_desc.copy_(xch.desc_view()[1:], non_blocking=True)
+            mt.match_consecutive_ptr(B, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), flow_dev.data_ptr(),
+                                     float(W), float(H), 15.0, sf, match.data_ptr(), nmatch.data_ptr())
+            h_match.copy_(match, non_blocking=True)                        # D2H of the matches
             h_nmatch.copy_(nmatch, non_blocking=True)
-            stream.synchronize()                                           # the caller holds the results here
+            d2h_stream.synchronize()
+            stream.synchronize()                                           # the caller holds every result here
 
         for _ in range(Wm):
             dev_step()
