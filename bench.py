@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 W, H, NFEAT = 1920, 1080, 1000
 FAST_ALGO_BYTES_PER_FRAME = 2 * 6_419_321  # 8-level 1080p pyramid read once + u8 score map written once
 # dram__bytes_read.sum + dram__bytes_write.sum of k_fast_score per frame from the committed `ncu --set full` capture
-# (profiles/r01b_kernels_ncu_full.md: 209.0 MB read + 168.7 MB written over a 32-frame launch; part of the score map
+# (profiles/r01c_kernels_ncu_full.md: 209.0 MB read + 167.8 MB written over a 32-frame launch; part of the score map
 # is still dirty in L2 when the kernel ends, hence slightly below the algorithmic bytes)
-FAST_NCU_TRAFFIC_BYTES_PER_FRAME = (209.0e6 + 168.7e6) / 32
+FAST_NCU_TRAFFIC_BYTES_PER_FRAME = (209.0e6 + 167.8e6) / 32
 STAGES = ["pyramid", "fast_score", "cell_nms", "octree", "orient_desc"]
 
 
@@ -357,7 +357,7 @@ def main():
                 "clocks": clocks,
                 "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": FAST_NCU_TRAFFIC_BYTES_PER_FRAME * B, "peak_source": peak_src,
-                             "traffic_source": "ncu --set full capture, profiles/r01b_kernels_ncu_full.md, scaled to this launch",
+                             "traffic_source": "ncu --set full capture, profiles/r01c_kernels_ncu_full.md, scaled to this launch",
                              "algorithmic_bytes_per_launch": FAST_ALGO_BYTES_PER_FRAME * B,
                              "us_per_launch": stage_us["fast_score"] * B},
                 "stage_us_per_frame": stage_us,

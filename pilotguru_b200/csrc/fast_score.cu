@@ -73,6 +73,8 @@ __device__ __forceinline__ uint32_t mad1(uint32_t a, uint32_t one, uint32_t c) {
 constexpr int kRowB = kF2InWords * 4;  // 288 bytes per staged input row
 
 // Exact bam of the pixel at byte pointer c inside the staged tile.
+// (Tried: 16-row bands per warp to amortise the per-band overhead -- 14 % fewer instructions but half the resident warps;
+// 5.0 -> 5.8 us/frame.)
 // (Tried: encoding p as fp16-compatible halves so that part of the min/max tree runs as HMNMX2 on the FMA pipes;
 // ptxas fuses the pairs into 3-input VHMNMX on the ALU pipe again, and splitting them costs issue slots -- no gain.)
 __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
