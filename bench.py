@@ -34,6 +34,8 @@ FAST_ALGO_BYTES_PER_FRAME = 2 * 6_419_321  # 8-level 1080p pyram
 # (profiles/r01c_kernels_ncu_full.md: 209.0 MB read + 167.8 MB written over a 32-frame launch; part of the score map
 # is still dirty in L2 when the kernel ends, hence slightly below the algorithmic bytes)
 FAST_NCU_TRAFFIC_BYTES_PER_FRAME = (209.0e6 + 167.8e6) / 32
+WORKLOAD = ("ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + SearchByProjection vs previous "
+            "frame (BASELINE configs[1], batched)")
 STAGES = ["pyramid", "fast_score", "cell_nms", "octree", "orient_desc"]
 
 
@@ -178,16 +180,32 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "1080p frames/sec ORB extract+match", "value": v, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + "
-                                   "SearchByProjection vs previous frame", "frames_per_step": per_step},
+            "config": {"workload": WORKLOAD, "frames_per_step": per_step},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{per_step} frames per step x {args.steps} steps, oracle/liboracle.so on {cores} host threads"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the process's original stdout; everything else that writes to fd 1 (NCCL prints its
+    version banner there) was diverted to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -344,8 +362,7 @@ def main():
         line = {"metric": "1080p frames/sec ORB extract+match", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + "
-                                       "SearchByProjection vs previous frame (BASELINE configs[1], batched)",
+                "config": {"workload": WORKLOAD,
                            "frames_per_gpu_per_step": B, "global_frames_per_step": frames_total,
                            "l2": f"inputs larger than L2: {B * W * H / 1e6:.0f} MB of frames + {B * 6.4:.0f} MB pyramid per step",
                            "host_numa_node_rank0": numa,
@@ -370,7 +387,7 @@ def main():
                                     "sample": f"{n} synthetic 1080p frames, extract+match, oracle on {cores} host threads ({sec:.1f} s wall)"}
         if not args.no_calibration and world == 1:
             line["calibration"] = calibration_leg(local, args.calib_seconds, args.calib_hz)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
