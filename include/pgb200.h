@@ -157,6 +157,13 @@ int pgb_match_map_points(pgb_matcher*, int n_frames, int cap, const pgb_keypoint
                          float max_y, float th, const float* scale_factors, int nlevels, int32_t* match_of_feature,
                          int32_t* n_matches, int is_device);
 
+/* MapPoint::ComputeDistinctiveDescriptors (thirdparty/orb-slam2/src/MapPoint.cc:259-324) for n_points map points:
+ * the observing descriptors of point p are rows offsets[p] .. offsets[p+1]-1 of desc[][32]; best_idx[p] = row (relative
+ * to offsets[p]) with the least median Hamming distance to the others, -1 for a point without observations.
+ * More than 256 observations of one point -> PGB_ERR_CAPACITY. */
+int pgb_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, int is_device,
+                                void* stream);
+
 /* ------------------------------------------------------------------ IMU + GPS calibration ------------------ */
 typedef struct pgb_imu pgb_imu;
 

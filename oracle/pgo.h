@@ -42,6 +42,7 @@ int pgo_search_map_points(const pgb_keypoint* kps, const uint8_t* desc, int n, c
                           const float* proj_xy, const int32_t* track_level, const float* view_cos, const uint8_t* mp_desc,
                           const uint8_t* in_view, const uint8_t* mp_observed, int n_mp, float minX, float maxX, float minY,
                           float maxY, float th, const float* scale_factors, float nnratio, int32_t* match_of_feature);
+int pgo_distinctive_descriptor(const uint8_t* desc, int N);
 int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
                           float maxX, float maxY, float th, const float* scale_factors, int nlevels,

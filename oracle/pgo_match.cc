@@ -276,6 +276,29 @@ int pgo_search_map_points(const pgb_keypoint* kps, const uint8_t* desc, int n, c
   return nmatches;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324), literal: index of the descriptor with the least
+// median distance to the rest (float distance matrix, std::sort of each row, vDists[0.5*(N-1)]).
+int pgo_distinctive_descriptor(const uint8_t* desc, int N) {
+  if (N <= 0) return -1;
+  std::vector<std::vector<float>> Distances(N, std::vector<float>(N));
+  for (int i = 0; i < N; i++) {
+    Distances[i][i] = 0;
+    for (int j = i + 1; j < N; j++) {
+      const int distij = descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+      Distances[i][j] = (float)distij;
+      Distances[j][i] = (float)distij;
+    }
+  }
+  int BestMedian = INT32_MAX, BestIdx = 0;
+  for (int i = 0; i < N; i++) {
+    std::vector<int> vDists(Distances[i].begin(), Distances[i].end());
+    std::sort(vDists.begin(), vDists.end());
+    const int median = vDists[(size_t)(0.5 * (N - 1))];
+    if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+  }
+  return BestIdx;
+}
+
 int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
                           float maxX, float maxY, float th, const float* scale_factors, int nlevels,

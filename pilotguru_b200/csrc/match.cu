@@ -688,6 +688,46 @@ __global__ void __launch_bounds__(kMtThreads) k_match_windowed(WinArgs A) {
   A.nMatches[p] = nm;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (thirdparty/orb-slam2/src/MapPoint.cc:259-324): among the N descriptors that
+// observe a map point, the one with the least median Hamming distance to the rest (median = sorted row[(size_t)(0.5 *
+// (N - 1))], the row includes the zero self-distance; first index wins ties).  One warp per map point; for each
+// candidate i the lanes hold the distances to j = lane, lane + 32, ... and the k-th smallest is found by bisection on
+// the value (distances are integers in [0, 256]) with ballot counts -- no sort.
+constexpr int kDistinctMaxN = 256;
+
+__global__ void __launch_bounds__(128) k_distinctive(const uint8_t* __restrict__ desc, const int* __restrict__ offsets,
+                                                     int nPoints, int* __restrict__ bestIdx, int* __restrict__ err) {
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= nPoints) return;
+  const int o = offsets[p], N = offsets[p + 1] - o;
+  if (N <= 0) { if (lane == 0) bestIdx[p] = -1; return; }          // "if(vDescriptors.empty()) return;"
+  if (N > kDistinctMaxN) { if (lane == 0) { bestIdx[p] = -1; atomicOr(err, 1); } return; }
+  const uint32_t* D = reinterpret_cast<const uint32_t*>(desc) + (size_t)o * 8;
+  const int k = (int)(0.5 * (N - 1));
+  int best = 0x7fffffff, bestI = 0;
+  for (int i = 0; i < N; i++) {
+    uint32_t di[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) di[w] = D[(size_t)i * 8 + w];
+    int d[kDistinctMaxN / 32];
+#pragma unroll
+    for (int c = 0; c < kDistinctMaxN / 32; c++) {
+      const int j = lane + 32 * c;
+      d[c] = j < N ? hamming256(di, D + (size_t)j * 8) : 0x7fffffff;
+    }
+    int lo = 0, hi = 256;  // smallest v with #(d <= v) >= k + 1
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < kDistinctMaxN / 32; c++) cnt += __popc(__ballot_sync(0xffffffffu, d[c] <= mid));
+      if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    if (lo < best) { best = lo; bestI = i; }
+  }
+  if (lane == 0) bestIdx[p] = bestI;
+}
+
 size_t match_smem_bytes(int cap) {
   size_t b = (size_t)cap * 8 * 4 + (size_t)cap * 5 * 4;        // desc, x, y, meta, angle, bin
   b += (size_t)(cap + (cap & 1)) * 2;                           // cell-sorted order
@@ -1043,6 +1083,39 @@ int pgb_match_map_points(pgb_matcher* m, int n_frames, int cap, const pgb_keypoi
     PGB_CUDA(cudaMemcpyAsync(n_matches, dNm.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
     PGB_CUDA(cudaStreamSynchronize(s));
   }
+  return PGB_OK;
+}
+
+int pgb_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, int is_device,
+                                void* stream) {
+  if (n_points < 0 || (n_points > 0 && (!desc || !offsets || !best_idx)))
+    return fail(PGB_ERR_INVALID, "pgb_distinctive_descriptors: invalid argument");
+  if (n_points == 0) return PGB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || use_device(dev)) return PGB_ERR_CUDA;
+  DevBuf<uint8_t> dD;
+  DevBuf<int> dO, dB, dE;
+  if (dE.alloc(1)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemsetAsync(dE.p, 0, sizeof(int), s));
+  const uint8_t* pd = desc;
+  const int* po = offsets;
+  int* pb = best_idx;
+  if (!is_device) {
+    const int total = offsets[n_points];
+    if (total < 0) return fail(PGB_ERR_INVALID, "offsets must be non-decreasing");
+    if (dD.alloc((size_t)std::max(total, 1) * 32) || dO.alloc(n_points + 1) || dB.alloc(n_points)) return PGB_ERR_CUDA;
+    PGB_CUDA(cudaMemcpyAsync(dD.p, desc, (size_t)total * 32, cudaMemcpyHostToDevice, s));
+    PGB_CUDA(cudaMemcpyAsync(dO.p, offsets, (n_points + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    pd = dD.p; po = dO.p; pb = dB.p;
+  }
+  k_distinctive<<<(n_points + 3) / 4, 128, 0, s>>>(pd, po, n_points, pb, dE.p);
+  PGB_CHECK_LAUNCH();
+  int e = 0;
+  PGB_CUDA(cudaMemcpyAsync(&e, dE.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (!is_device) PGB_CUDA(cudaMemcpyAsync(best_idx, dB.p, n_points * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PGB_CUDA(cudaStreamSynchronize(s));
+  if (e) return fail(PGB_ERR_CAPACITY, "a map point has more than %d observations", kDistinctMaxN);
   return PGB_OK;
 }
 

@@ -119,3 +119,15 @@ class ORBmatcher:
         sf = np.ascontiguousarray(scale_factors, np.float32)
         check(lib().pgb_match_consecutive(self._h, n_pairs, cap, kps_ptr, desc_ptr, counts_ptr, flow_ptr, max_x, max_y,
                                           th, np_ptr(sf), len(sf), match_ptr, nmatch_ptr))
+
+
+def ComputeDistinctiveDescriptors(descriptor_sets):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324) for a list of (n_i, 32) uint8 arrays: index of the
+    descriptor with the least median distance to the rest, per map point (-1 for an empty set)."""
+    sets = [np.ascontiguousarray(d, np.uint8).reshape(-1, 32) for d in descriptor_sets]
+    off = np.zeros(len(sets) + 1, np.int32)
+    off[1:] = np.cumsum([len(d) for d in sets])
+    flat = np.concatenate(sets) if sets and off[-1] else np.zeros((1, 32), np.uint8)
+    best = np.full(max(len(sets), 1), -1, np.int32)
+    check(lib().pgb_distinctive_descriptors(np_ptr(flat), np_ptr(off), len(sets), np_ptr(best), 0, None))
+    return best[:len(sets)].copy()

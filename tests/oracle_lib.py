@@ -382,3 +382,9 @@ def search_map_points(kps, desc, has_mp, proj_xy, track_level, view_cos, mp_desc
                                     C.c_float(bounds[0]), C.c_float(bounds[1]), C.c_float(bounds[2]), C.c_float(bounds[3]),
                                     C.c_float(th), ptr(sf, f32p), C.c_float(nnratio), ptr(mo, i32p))
     return n, mo[:len(kps)].copy()
+
+
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324), literal; -1 for an empty set."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    return int(lib().pgo_distinctive_descriptor(ptr(d, u8p) if len(d) else None, len(d)))

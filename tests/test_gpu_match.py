@@ -155,3 +155,19 @@ def test_search_map_points_matches_oracle():
         on, om = O.search_map_points(k, d, has, uv, lv, vc, qd, iv, ob, bounds, th, sf, nnratio=ratio)
         gn, gm = m.SearchByProjectionMapPoints(k, d, has, uv, lv, vc, qd, iv, ob, bounds, th, sf)
         assert gn == on and on > 50 and np.array_equal(gm, om)
+
+
+def test_distinctive_descriptors_match_oracle():
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324) for a batch of map points."""
+    from pilotguru_b200.matcher import ComputeDistinctiveDescriptors
+    rng = np.random.default_rng(12)
+    sets = []
+    for n in [1, 2, 3, 5, 0, 8, 31, 32, 33, 64, 100, 256, 4, 17]:
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        sets.append(np.stack([base ^ (rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8))
+                              for _ in range(n)]) if n else np.zeros((0, 32), np.uint8))
+    got = ComputeDistinctiveDescriptors(sets)
+    want = [O.distinctive_descriptor(s) for s in sets]
+    assert got.tolist() == want
+    with pytest.raises(Exception):
+        ComputeDistinctiveDescriptors([rng.integers(0, 256, (257, 32), dtype=np.uint8)])   # capacity: loud, never truncated

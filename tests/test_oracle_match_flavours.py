@@ -85,3 +85,15 @@ def test_search_map_points_against_brute_force():
         want[idx[b]] = i; observed[idx[b]] = bool(ob[i]); nm += 1
     assert n == nm and n > 100 and np.array_equal(mo, want)
     assert (mo[has.astype(bool)] == -1).all()
+
+
+def test_distinctive_descriptor_against_numpy():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 7, 20, 65):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.stack([base ^ (rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8))
+                      for _ in range(n)])
+        dist = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(axis=2)
+        med = np.sort(dist, axis=1)[:, int(0.5 * (n - 1))]
+        assert O.distinctive_descriptor(d) == int(np.argmin(med))          # argmin: first index wins ties
+    assert O.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1
