@@ -294,13 +294,14 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_co
   }
 }
 
+// Function attributes are per device: called once per extractor handle (after its device was made current).
+int configure_fast_score() {
+  PGB_CUDA(cudaFuncSetAttribute(k_fast_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmem));
+  return PGB_OK;
+}
+
 int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
-                         cudaStream_t st) {
-  static bool init = false;
-  if (!init) {
-    PGB_CUDA(cudaFuncSetAttribute(k_fast_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmem));
-    init = true;
-  }
+                      cudaStream_t st) {
   if (g.totalTiles2 <= 0 || nFrames <= 0) return PGB_OK;
   dim3 grid(g.totalTiles2, nFrames);
   k_fast_score<4><<<grid, kF2Threads, kFsSmem, st>>>(g, tm, tileTab, frame0);

@@ -423,6 +423,7 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
     return nullptr;
   };
   if (build_geo(o, max_width, max_height, &o->capGeo)) return bail("geometry");
+  if (configure_fast_score()) return bail("cudaFuncSetAttribute failed");
   {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) o->numSMs = prop.multiProcessorCount;
