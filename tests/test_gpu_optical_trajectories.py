@@ -56,3 +56,46 @@ def test_optical_trajectories_binary(tmp_path):
         tot_m += nm
     line = [l for l in p.stderr.splitlines() if "keypoints/frame" in l][-1]
     assert f"{tot_k / n:.1f} keypoints/frame" in line and f"{tot_m / (n - 1):.1f} matches/frame" in line, (line, tot_k / n, tot_m / (n - 1))
+
+
+def test_annotation_pipeline_binaries(tmp_path):
+    """BASELINE configs[4] in miniature: the three drop-in binaries chained as python/preprocess_all.py chains the
+    reference's -- optical_trajectories (frames -> trajectory JSON), fit_motion (IMU + GPS -> velocities / steering),
+    annotate_frames (velocities and steering -> per-frame labels) -- on synthetic data, checked for consistency."""
+    host = os.path.join(ROOT, "pilotguru_b200", "host")
+    subprocess.run(["make", "-C", host], check=True, capture_output=True)
+    w, h, n, fps = 640, 480, 31, 30.0
+    np.stack([synth.frame(t, w=w, h=h) for t in range(n)]).tofile(tmp_path / "frames.gray")
+    (tmp_path / "settings.yml").write_text("%YAML:1.0\nCamera.fps: 30.0\nORBextractor.nFeatures: 500\nORBextractor.scaleFactor: 1.2\n"
+                                           "ORBextractor.nLevels: 8\nORBextractor.iniThFAST: 20\nORBextractor.minThFAST: 7\n")
+    run = lambda *a: subprocess.run(list(a), capture_output=True, text=True, timeout=600)
+    p = run(os.path.join(host, "optical_trajectories"), "--vocabulary_file=unused", "--camera_settings", str(tmp_path / "settings.yml"),
+            "--out_dir", str(tmp_path), f"--in_video=raw:{tmp_path / 'frames.gray'}:{w}x{h}", "--rotation_smooth_sigma=2")
+    assert p.returncode == 0, p.stderr[-1500:]
+    traj = json.load(open(tmp_path / "trajectory-0.json"))["trajectory"]
+    assert len(traj) == n
+    d = synth.imu_gps(60, 100)
+    paths = synth.write_imu_gps_json(d, str(tmp_path))
+    p = run(os.path.join(host, "fit_motion"), "--rotations_json", paths["rotations"], "--accelerations_json", paths["accelerations"],
+            "--locations_json", paths["locations"], "--velocities_out_json", str(tmp_path / "velocities.json"),
+            "--steering_out_json", str(tmp_path / "steering.json"), "--optimization_iters=100")
+    assert p.returncode == 0, p.stderr[-1500:]
+    vel = json.load(open(tmp_path / "velocities.json"))["velocities"]
+    # frames.json: the trajectory's frames placed inside the IMU recording (frame 0 at t = 10 s)
+    t0 = 10_000_000
+    frames = [{"frame_id": e["frame_id"], "time_usec": t0 + e["time_usec"]} for e in traj]
+    (tmp_path / "frames.json").write_text(json.dumps({"frames": frames}))
+    for root, val, src in (("velocities", "speed_m_s", "velocities.json"), ("steering", "angular_velocity", "steering.json")):
+        p = run(os.path.join(host, "annotate_frames"), "--frames_json", str(tmp_path / "frames.json"), "--in_json", str(tmp_path / src),
+                "--json_root_element_name", root, "--json_value_name", val, "--out_json", str(tmp_path / f"frame_{root}.json"))
+        assert p.returncode == 0, p.stderr[-1500:]
+        lab = json.load(open(tmp_path / f"frame_{root}.json"))[root]
+        assert [e["frame_id"] for e in lab] == list(range(1, n))            # every frame after the first is covered
+    # the per-frame speed is the time average of the velocity series over the frame interval: bounded by its extremes
+    lab = json.load(open(tmp_path / "frame_velocities.json"))["velocities"]
+    vt = np.array([e["time_usec"] for e in vel]); vv = np.array([e["speed_m_s"] for e in vel])
+    for e, fr_prev, fr in zip(lab, frames[:-1], frames[1:]):
+        seg = vv[(vt >= fr_prev["time_usec"] - 20_000) & (vt <= fr["time_usec"] + 20_000)]
+        assert seg.min() - 1e-9 <= e["speed_m_s"] <= seg.max() + 1e-9
+    gps_mean = float(np.mean(d["gps_v"][9:13]))
+    assert abs(np.mean([e["speed_m_s"] for e in lab]) - gps_mean) < 1.5          # m/s: the calibrated speed tracks GPS
