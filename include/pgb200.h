@@ -99,6 +99,17 @@ void* pgb_orb_stream(pgb_orb*);
  * (is_device=1) extract calls. */
 int pgb_orb_check(pgb_orb*);
 
+/* Frame feed: cv::flip (src/io/image_sequence_reader.cc:163-175) + cvtColor to gray (Tracking::GrabImageMonocular,
+ * thirdparty/orb-slam2/src/Tracking.cc:243-258) of n_frames interleaved 8-bit frames in one device pass.
+ * channels 1/3/4; rgb_order = Camera.RGB (1: RGB(A), 0: BGR(A)); formula 0 = OpenCV 2.4 fixed point (the version the
+ * reference pins), 1 = OpenCV >= 3 (bit-exact against cv2 4.13).  src/dst may each be host or device (is_device flags);
+ * with device buffers the call is asynchronous on `stream`.  The gray output can be handed to pgb_orb_extract
+ * (PGB_IN_DEVICE). */
+int pgb_frames_to_gray(int device, const uint8_t* src, int src_is_device, int n_frames, int width, int height, int channels,
+                       int rgb_order, size_t src_pitch, size_t src_frame_stride, int vertical_flip, int horizontal_flip,
+                       int formula, uint8_t* dst_gray, int dst_is_device, size_t dst_pitch, size_t dst_frame_stride,
+                       void* stream);
+
 /* ------------------------------------------------------------------ matcher -------------------------------- */
 /* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1651-1667) for n pairs of 32-byte descriptors (device or host
  * pointers; host pointers are staged). Mostly a test hook for the popcount primitive. */

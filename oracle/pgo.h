@@ -23,6 +23,8 @@ void pgo_resize_linear(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw,
 int pgo_fast(const uint8_t* img, int w, int h, int th, int nms, int32_t* xys, int cap);
 void pgo_fast_score_map(const uint8_t* img, int w, int h, int min_th, uint8_t* out);
 void pgo_gaussian_blur7(const uint8_t* src, int w, int h, uint8_t* dst);
+void pgo_to_gray(const uint8_t* src, int w, int h, int channels, int rgb_order, int vflip, int hflip, int formula,
+                 uint8_t* dst);
 float pgo_fast_atan2(float y, float x);
 void pgo_fast_atan2_many(const float* y, const float* x, float* out, int n);
 float pgo_ic_angle(const uint8_t* img, int w, int h, int cx, int cy);

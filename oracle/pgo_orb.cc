@@ -665,3 +665,19 @@ int pgo_distribute_octree(const int32_t* xyr, int n, int minX, int maxX, int min
 }
 
 }  // extern "C"
+
+// cv::flip + cvtColor(8U, RGB/BGR[A] -> GRAY) (image_sequence_reader.cc:163-175, Tracking.cc:243-258).
+// formula 0: OpenCV 2.4 (yuv_shift 14: R2Y 4899, G2Y 9617, B2Y 1868), formula 1: OpenCV >= 3 (shift 15: 9798, 19235, 3735).
+extern "C" void pgo_to_gray(const uint8_t* src, int w, int h, int channels, int rgb_order, int vflip, int hflip, int formula,
+                            uint8_t* dst) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const uint8_t* p = src + ((size_t)(vflip ? h - 1 - y : y) * w + (hflip ? w - 1 - x : x)) * channels;
+      int v = p[0];
+      if (channels > 1) {
+        const int r = rgb_order ? p[0] : p[2], g = p[1], b = rgb_order ? p[2] : p[0];
+        v = formula ? (r * 9798 + g * 19235 + b * 3735 + 16384) >> 15 : (r * 4899 + g * 9617 + b * 1868 + 8192) >> 14;
+      }
+      dst[(size_t)y * w + x] = (uint8_t)v;
+    }
+}

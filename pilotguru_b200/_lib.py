@@ -48,6 +48,8 @@ _SIGS = {
     "pgb_orb_run_stage": (C.c_int, [vp, C.c_int]),
     "pgb_orb_stream": (vp, [vp]),
     "pgb_orb_check": (C.c_int, [vp]),
+    "pgb_frames_to_gray": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                     C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
     "pgb_descriptor_distance": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
     "pgb_matcher_create": (vp, [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, vp]),
     "pgb_matcher_destroy": (None, [vp]),

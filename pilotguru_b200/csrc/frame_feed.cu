@@ -1,0 +1,90 @@
+// Frame feed: what happens to a decoded frame between the video reader and ORBextractor --
+// cv::flip of the RGB24 frame (src/io/image_sequence_reader.cc:163-175, flags --vertical_flip / --horizontal_flip) and
+// cvtColor to gray in Tracking::GrabImageMonocular (thirdparty/orb-slam2/src/Tracking.cc:243-258: RGB/BGR/RGBA/BGRA by
+// Camera.RGB) -- as one pass over the pixels, so frames can go to the extractor without leaving the device.
+// cvtColor(8U) is fixed point; the reference pins OpenCV 2.4.x, whose RGB2Gray is (R*4899 + G*9617 + B*1868 + 8192) >> 14
+// (formula 0, un-vendored, restated from the published source); OpenCV >= 3 uses (R*9798 + G*19235 + B*3735 + 16384) >> 15
+// (formula 1, pinned bit-exact against cv2 4.13 golden vectors).  They differ on ~0.3 % of random pixels by one level.
+// Video decoding itself (libav in the reference) stays outside the library.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace pgb {
+
+template <int kCh>
+__global__ void __launch_bounds__(256) k_to_gray(const uint8_t* __restrict__ src, size_t srcPitch, size_t srcStride,
+                                                 uint8_t* __restrict__ dst, size_t dstPitch, size_t dstStride, int w, int h,
+                                                 int rgbOrder, int vflip, int hflip, int formula) {
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  if (xq * 4 >= w) return;
+  const uint8_t* srow = src + (size_t)f * srcStride + (size_t)(vflip ? h - 1 - y : y) * srcPitch;
+  const int cr = formula ? 9798 : 4899, cg = formula ? 19235 : 9617, cb = formula ? 3735 : 1868;
+  const int rnd = formula ? 16384 : 8192, sh = formula ? 15 : 14;
+  uint32_t packed = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int x = xq * 4 + i;
+    if (x < w) {
+      const uint8_t* p = srow + (size_t)(hflip ? w - 1 - x : x) * kCh;
+      int v;
+      if (kCh == 1) {
+        v = p[0];
+      } else {
+        const int c0 = p[0], c1 = p[1], c2 = p[2];
+        const int r = rgbOrder ? c0 : c2, b = rgbOrder ? c2 : c0;
+        v = (r * cr + c1 * cg + b * cb + rnd) >> sh;
+      }
+      packed |= (uint32_t)v << (8 * i);
+    }
+  }
+  uint8_t* drow = dst + (size_t)f * dstStride + (size_t)y * dstPitch;
+  if (xq * 4 + 3 < w && (dstPitch & 3) == 0 && ((size_t)dst & 3) == 0 && (dstStride & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(drow + xq * 4) = packed;
+  } else {
+    for (int i = 0; i < 4 && xq * 4 + i < w; i++) drow[xq * 4 + i] = (uint8_t)(packed >> (8 * i));
+  }
+}
+
+}  // namespace pgb
+
+using namespace pgb;
+
+extern "C" int pgb_frames_to_gray(int device, const uint8_t* src, int src_is_device, int n_frames, int width, int height,
+                                  int channels, int rgb_order, size_t src_pitch, size_t src_frame_stride, int vertical_flip,
+                                  int horizontal_flip, int formula, uint8_t* dst_gray, int dst_is_device, size_t dst_pitch,
+                                  size_t dst_frame_stride, void* stream) {
+  if (n_frames < 0 || width < 0 || height < 0 || (channels != 1 && channels != 3 && channels != 4) || (formula != 0 && formula != 1))
+    return fail(PGB_ERR_INVALID, "pgb_frames_to_gray: invalid argument");
+  if (n_frames == 0 || width == 0 || height == 0) return PGB_OK;
+  if (!src || !dst_gray || src_pitch < (size_t)width * channels || dst_pitch < (size_t)width ||
+      src_frame_stride < src_pitch * height || dst_frame_stride < dst_pitch * height)
+    return fail(PGB_ERR_INVALID, "pgb_frames_to_gray: null buffer or pitch/stride smaller than the image");
+  if (use_device(device)) return PGB_ERR_CUDA;
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf<uint8_t> dIn, dOut;
+  const uint8_t* in = src;
+  uint8_t* out = dst_gray;
+  if (!src_is_device) {
+    if (dIn.alloc(src_frame_stride * n_frames)) return PGB_ERR_CUDA;
+    PGB_CUDA(cudaMemcpyAsync(dIn.p, src, src_frame_stride * (n_frames - 1) + src_pitch * height, cudaMemcpyHostToDevice, s));
+    in = dIn.p;
+  }
+  if (!dst_is_device) {
+    if (dOut.alloc(dst_frame_stride * n_frames)) return PGB_ERR_CUDA;
+    out = dOut.p;
+  }
+  dim3 grid(((width + 3) / 4 + 255) / 256, height, n_frames);
+  if (channels == 1) k_to_gray<1><<<grid, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula);
+  else if (channels == 3) k_to_gray<3><<<grid, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula);
+  else k_to_gray<4><<<grid, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula);
+  PGB_CHECK_LAUNCH();
+  if (!dst_is_device) {
+    PGB_CUDA(cudaMemcpy2DAsync(dst_gray, dst_pitch, dOut.p, dst_pitch, width, (size_t)height, cudaMemcpyDeviceToHost, s));
+    for (int f = 1; f < n_frames; f++)
+      PGB_CUDA(cudaMemcpy2DAsync(dst_gray + f * dst_frame_stride, dst_pitch, dOut.p + f * dst_frame_stride, dst_pitch, width,
+                                 (size_t)height, cudaMemcpyDeviceToHost, s));
+  }
+  if (!src_is_device || !dst_is_device) PGB_CUDA(cudaStreamSynchronize(s));
+  return PGB_OK;
+}

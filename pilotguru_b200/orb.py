@@ -128,3 +128,17 @@ class ORBextractor:
         lw = C.c_int(); lh = C.c_int()
         check(lib().pgb_orb_level_size(self._h, w, h, level, C.byref(lw), C.byref(lh)))
         return lw.value, lh.value
+
+
+def frames_to_gray(frames: np.ndarray, rgb_order: bool = True, vertical_flip: bool = False, horizontal_flip: bool = False,
+                   formula: int = 0, device: int = 0) -> np.ndarray:
+    """cv::flip + cvtColor to gray of (n, h, w[, c]) uint8 frames on the device (image_sequence_reader.cc:163-175,
+    Tracking.cc:243-258).  formula 0 = OpenCV 2.4 fixed point (the reference's pinned version), 1 = OpenCV >= 3."""
+    a = np.ascontiguousarray(frames, np.uint8)
+    if a.ndim == 3:
+        a = a[..., None]
+    n, h, w, c = a.shape
+    out = np.empty((n, h, w), np.uint8)
+    check(lib().pgb_frames_to_gray(device, np_ptr(a), 0, n, w, h, c, int(rgb_order), w * c, w * c * h, int(vertical_flip),
+                                   int(horizontal_flip), formula, np_ptr(out), 0, w, w * h, None))
+    return out

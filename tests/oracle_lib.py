@@ -388,3 +388,14 @@ def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324), literal; -1 for an empty set."""
     d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
     return int(lib().pgo_distinctive_descriptor(ptr(d, u8p) if len(d) else None, len(d)))
+
+
+def to_gray(img, rgb_order=True, vflip=False, hflip=False, formula=0):
+    """cv::flip + cvtColor to gray of one (h, w[, c]) uint8 image."""
+    a = np.ascontiguousarray(img, np.uint8)
+    if a.ndim == 2:
+        a = a[..., None]
+    h, w, c = a.shape
+    out = np.empty((h, w), np.uint8)
+    lib().pgo_to_gray(ptr(a, u8p), w, h, c, int(rgb_order), int(vflip), int(hflip), int(formula), ptr(out, u8p))
+    return out

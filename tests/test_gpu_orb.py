@@ -144,3 +144,28 @@ def test_host_frame_pipeline_matches_resident():
             c = outs[0][2][t]
             assert np.array_equal(o[0][t, :c], outs[0][0][t, :c]) and np.array_equal(o[1][t, :c], outs[0][1][t, :c])
     ex.close()
+
+
+def test_frame_feed_matches_oracle_and_feeds_the_extractor(golden_dir):
+    """pgb_frames_to_gray (cv::flip + cvtColor) against the oracle for every layout, and its output through the extractor."""
+    from pilotguru_b200.orb import frames_to_gray
+    rng = np.random.default_rng(9)
+    g = np.load(os.path.join(golden_dir, "cv2_gray.npz"))
+    assert np.array_equal(frames_to_gray(g["rgb"][None], formula=1)[0], g["rgb2gray"])          # the cv2 pin, on the GPU
+    assert np.array_equal(frames_to_gray(g["rgba"][None], rgb_order=False, formula=1)[0], g["bgra2gray"])
+    for c in (1, 3, 4):
+        for w, h in ((64, 48), (61, 37), (1, 1), (5, 3)):
+            fr = rng.integers(0, 256, (3, h, w, c), dtype=np.uint8)
+            for rgbo, vf, hf, fm in ((1, 0, 0, 0), (0, 1, 0, 1), (1, 0, 1, 1), (0, 1, 1, 0)):
+                got = frames_to_gray(fr, bool(rgbo), bool(vf), bool(hf), fm)
+                for i in range(3):
+                    assert np.array_equal(got[i], O.to_gray(fr[i], bool(rgbo), bool(vf), bool(hf), fm)), (c, w, h, rgbo, vf, hf, fm)
+    # colour frame -> gray on the device -> extractor == extractor on the oracle's gray
+    base = synth.frame(2, w=320, h=240)
+    rgb = np.stack([base, np.roll(base, 1, axis=1), np.roll(base, 2, axis=0)], axis=2)
+    gray = frames_to_gray(rgb[None], formula=0)[0]
+    ex = _mk(300, 320, 240)
+    gk, gd = ex(gray)
+    ok, od = O.OrbOracle(300, 1.2, 8, 20, 7).extract(O.to_gray(rgb, formula=0))
+    _assert_same(gk, gd, ok, od)
+    ex.close()
