@@ -5,7 +5,9 @@
 //
 // Scope: the SLAM back end (map initialisation, pose optimisation, local BA, loop
 // closing, DBoW2 relocalisation) and video decoding are out of scope.  So this binary runs in FLOW-TRACKING mode:
-//   * --in_video takes raw 8-bit gray frames:  raw:<path>:<width>x<height>  (frame i at byte i*width*height)
+//   * --in_video takes raw frames:  raw:<path>:<width>x<height> (8-bit gray, frame i at byte i*width*height) or
+//     raw24:<path>:<width>x<height> (interleaved 24-bit colour, the format the reference's reader hands to the tracker;
+//     channel order from Camera.RGB).  Flips and the colour conversion run on the device (pgb_frames_to_gray).
 //   * the tracked quantity is the dominant image translation between consecutive frames (median displacement of the
 //     matched keypoints); the camera is modelled as translating in its x-z plane by minus that flow, heading along
 //     its motion.  Poses are therefore in pixel units, not metres -- monocular SLAM scale is arbitrary as well.
@@ -76,10 +78,14 @@ int main(int argc, char** argv) {
   PGB_CHECK(!in_video.empty());
   PGB_CHECK(batch >= 2);
 
-  int width = 0, height = 0;
+  int width = 0, height = 0, channels = 1;
   char path[4096];
-  PGB_CHECK(sscanf(in_video.c_str(), "raw:%4095[^:]:%dx%d", path, &width, &height) == 3 && width > 0 && height > 0)
-      << "--in_video must be raw:<path>:<width>x<height> (video decoding is out of scope, see the header comment)";
+  if (sscanf(in_video.c_str(), "raw24:%4095[^:]:%dx%d", path, &width, &height) == 3) channels = 3;
+  else
+    PGB_CHECK(sscanf(in_video.c_str(), "raw:%4095[^:]:%dx%d", path, &width, &height) == 3)
+        << "--in_video must be raw:<path>:<width>x<height> or raw24:<path>:<width>x<height> (video decoding is out of "
+           "scope, see the header comment)";
+  PGB_CHECK(width > 0 && height > 0);
   const auto cfg = ReadSettings(camera_settings);
   auto get = [&](const char* k, double dflt) { auto it = cfg.find(k); return it == cfg.end() ? dflt : it->second; };
   const int nfeatures = (int)get("ORBextractor.nFeatures", 1000), nlevels = (int)get("ORBextractor.nLevels", 8);
@@ -90,7 +96,8 @@ int main(int argc, char** argv) {
 
   FILE* in = fopen(path, "rb");
   PGB_CHECK(in != nullptr) << "cannot open " << path;
-  const size_t frame_bytes = (size_t)width * height;
+  const size_t frame_bytes = (size_t)width * height, in_bytes = frame_bytes * channels;
+  const int rgb_order = (int)get("Camera.RGB", 1.0);  // Tracking.cc:90-96
 
   const int B = (int)batch;
   pgb_orb* orb = pgb_orb_create((int)device, nfeatures, scale_factor, nlevels, ini_th, min_th, width, height, B, nullptr);
@@ -101,7 +108,7 @@ int main(int argc, char** argv) {
   std::vector<float> sf(nlevels), inv(nlevels), s2(nlevels), is2(nlevels);
   PGB_CALL(pgb_orb_scale_factors(orb, sf.data(), inv.data(), s2.data(), is2.data()));
 
-  std::vector<uint8_t> frames(frame_bytes * B);
+  std::vector<uint8_t> frames(frame_bytes * B), raw(in_bytes * B);
   std::vector<pgb_keypoint> kps((size_t)B * cap);
   std::vector<uint8_t> desc((size_t)B * cap * 32);
   std::vector<int32_t> counts(B);
@@ -129,18 +136,12 @@ int main(int argc, char** argv) {
   };
 
   for (;;) {
-    const size_t got = fread(frames.data(), frame_bytes, B, in);
+    const size_t got = fread(raw.data(), in_bytes, B, in);
     if (got == 0) break;
     const int n = (int)got;
-    if (vertical_flip || horizontal_flip) {  // image_sequence_reader.cc:163-175
-      for (int f = 0; f < n; f++) {
-        uint8_t* img = frames.data() + (size_t)f * frame_bytes;
-        if (vertical_flip)
-          for (int y = 0; y < height / 2; y++) std::swap_ranges(img + (size_t)y * width, img + (size_t)(y + 1) * width, img + (size_t)(height - 1 - y) * width);
-        if (horizontal_flip)
-          for (int y = 0; y < height; y++) std::reverse(img + (size_t)y * width, img + (size_t)(y + 1) * width);
-      }
-    }
+    // cv::flip (image_sequence_reader.cc:163-175) and cvtColor (Tracking.cc:243-258; OpenCV 2.4 fixed point) on the device
+    PGB_CALL(pgb_frames_to_gray((int)device, raw.data(), 0, n, width, height, channels, rgb_order, (size_t)width * channels, in_bytes,
+                                vertical_flip ? 1 : 0, horizontal_flip ? 1 : 0, 0, frames.data(), 0, width, frame_bytes, nullptr));
     PGB_CALL(pgb_orb_extract(orb, frames.data(), 0, n, width, height, width, frame_bytes, kps.data(), desc.data(), counts.data(), cap));
     // queries of pair p = keypoints of frame p-1 projected with the motion guess (TrackWithMotionModel's role); the
     // guess is zero motion: the th=15 / 30 px windows (times the octave scale) cover ordinary inter-frame flow

@@ -58,6 +58,27 @@ def test_optical_trajectories_binary(tmp_path):
     assert f"{tot_k / n:.1f} keypoints/frame" in line and f"{tot_m / (n - 1):.1f} matches/frame" in line, (line, tot_k / n, tot_m / (n - 1))
 
 
+def test_optical_trajectories_colour_and_flip_input(tmp_path):
+    """raw24 input with --vertical_flip: the device feed (flip + cvtColor) in front of the extractor gives the same
+    trajectory as feeding the equivalent gray frames."""
+    host = os.path.join(ROOT, "pilotguru_b200", "host")
+    subprocess.run(["make", "-C", host], check=True, capture_output=True)
+    w, h, n = 320, 240, 9
+    gray = np.stack([synth.frame(t, w=w, h=h) for t in range(n)])
+    rgb = np.repeat(gray[:, ::-1, :, None], 3, axis=3)                    # R = G = B, stored upside down
+    (tmp_path / "s.yml").write_text("%YAML:1.0\nCamera.fps: 30.0\nCamera.RGB: 1\nORBextractor.nFeatures: 300\n")
+    gray.tofile(tmp_path / "g.raw"); np.ascontiguousarray(rgb).tofile(tmp_path / "c.raw")
+    outs = []
+    for spec, extra, sub in ((f"raw:{tmp_path / 'g.raw'}:{w}x{h}", [], "a"), (f"raw24:{tmp_path / 'c.raw'}:{w}x{h}", ["--vertical_flip"], "b")):
+        os.makedirs(tmp_path / sub)
+        p = subprocess.run([os.path.join(host, "optical_trajectories"), "--vocabulary_file=x", "--camera_settings", str(tmp_path / "s.yml"),
+                            "--out_dir", str(tmp_path / sub), "--in_video=" + spec] + extra, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-1500:]
+        outs.append(json.load(open(tmp_path / sub / "trajectory-0.json")))
+    # (R*4899 + G*9617 + B*1868 + 8192) >> 14 with R = G = B = v is v exactly, so both runs see identical gray frames
+    assert outs[0] == outs[1] and len(outs[0]["trajectory"]) == n
+
+
 def test_annotation_pipeline_binaries(tmp_path):
     """BASELINE configs[4] in miniature: the three drop-in binaries chained as python/preprocess_all.py chains the
     reference's -- optical_trajectories (frames -> trajectory JSON), fit_motion (IMU + GPS -> velocities / steering),
