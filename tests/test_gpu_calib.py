@@ -109,3 +109,24 @@ def test_error_behaviour():
     with pytest.raises(PgbError):                       # CHECK_GT(sigma, 0)
         smooth_time_series(np.ones(4), np.arange(4.0), np.arange(4.0), 0.0)
     imu.close()
+
+
+def test_c4_scale_windows_bit_exact():
+    """BASELINE configs[3] rate (500 Hz IMU, 1 Hz GPS) on a 10-minute recording: a shard of windows in the middle of
+    the recording (large merged-event / interval offsets) equals the host evaluation of the contract bit for bit, and
+    the whole run covers every IMU event between the first and the last GPS sample exactly 8 times in the interior."""
+    from pilotguru_b200 import calibration as cal
+    d = synth.imu_gps(600, 500, interleaved=True)
+    imu = cal.ImuSeries(d["gyro"], d["gyro_t"], d["acc"], d["acc_t"])
+    part = cal.fit_windows(imu, d["gps_v"], d["gps_t"], max_iterations=40, first_window=57, n_windows=3)
+    whole = cal.fit_windows(imu, d["gps_v"], d["gps_t"], max_iterations=40)
+    imu.close()
+    assert np.array_equal(part["x"], whole["x"][57:60]) and np.array_equal(part["iters"], whole["iters"][57:60])
+    for k, w in enumerate(range(57, 60)):                              # the oracle on exactly that window's GPS slice
+        sl = slice(5 * w, 5 * w + 40)
+        orc = O.CalibOracle(d["gps_v"][sl], d["gps_t"][sl], d["gyro"], d["gyro_t"], d["acc"], d["acc_t"])
+        it, x, fx, _ = orc.minimize(max_iterations=40, mode="core")
+        assert it == part["iters"][k] and np.array_equal(x, part["x"][k]) and fx == part["fx"][k]
+    cnt = whole["speed_cnt"]
+    assert cnt.max() == 8 and (cnt[len(cnt) // 4: 3 * len(cnt) // 4] == 8).all()   # window 40 / step 5
+    assert np.isfinite(whole["speed_sum"]).all() and (whole["speed_sum"][cnt > 0] > 0).all()
