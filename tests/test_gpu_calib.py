@@ -114,7 +114,7 @@ def test_error_behaviour():
 def test_c4_scale_windows_bit_exact():
     """BASELINE configs[3] rate (500 Hz IMU, 1 Hz GPS) on a 10-minute recording: a shard of windows in the middle of
     the recording (large merged-event / interval offsets) equals the host evaluation of the contract bit for bit, and
-    the whole run covers every IMU event between the first and the last GPS sample exactly 8 times in the interior."""
+    the whole run covers every interior IMU event 7 or 8 times (a 40-sample window spans 39 GPS intervals, step 5)."""
     from pilotguru_b200 import calibration as cal
     d = synth.imu_gps(600, 500, interleaved=True)
     imu = cal.ImuSeries(d["gyro"], d["gyro_t"], d["acc"], d["acc_t"])
@@ -128,5 +128,6 @@ def test_c4_scale_windows_bit_exact():
         it, x, fx, _ = orc.minimize(max_iterations=40, mode="core")
         assert it == part["iters"][k] and np.array_equal(x, part["x"][k]) and fx == part["fx"][k]
     cnt = whole["speed_cnt"]
-    assert cnt.max() == 8 and (cnt[len(cnt) // 4: 3 * len(cnt) // 4] == 8).all()   # window 40 / step 5
+    mid = cnt[len(cnt) // 4: 3 * len(cnt) // 4]
+    assert cnt.max() == 8 and mid.min() == 7 and 7.7 < mid.mean() < 7.9                # 39 intervals / step 5 = 7.8
     assert np.isfinite(whole["speed_sum"]).all() and (whole["speed_sum"][cnt > 0] > 0).all()
