@@ -528,10 +528,16 @@ int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames
   int* dc = outDev ? counts : o->counts.p;
   const int dcap = outDev ? cap : o->outCap;  // a caller capacity below pgb_orb_max_keypoints() raises the device flag
   if (inDev) {
-    for (int f = 0; f < n_frames; f++)
-      PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
-                                 gray + (size_t)f * frame_stride, pitch, width, height, cudaMemcpyDeviceToDevice,
-                                 o->stream));
+    if (pitch == (size_t)width && g.lv[0].pitch == width) {
+      // contiguous frames: ONE 2-D copy whose "rows" are whole frames (128 separate 2 MB copies cost 0.8 ms of gaps)
+      PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + g.lv[0].off, g.frameStride, gray, frame_stride, (size_t)width * height, n_frames,
+                                 cudaMemcpyDeviceToDevice, o->stream));
+    } else {
+      for (int f = 0; f < n_frames; f++)
+        PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + (size_t)f * g.frameStride + g.lv[0].off, g.lv[0].pitch,
+                                   gray + (size_t)f * frame_stride, pitch, width, height, cudaMemcpyDeviceToDevice,
+                                   o->stream));
+    }
     rc = run_stages(o, 0, 4, dk, dd, dc, dcap, 0, n_frames);
   } else {
     rc = extract_host_pipelined(o, gray, n_frames, width, height, pitch, frame_stride, dk, dd, dc, dcap);
