@@ -69,6 +69,7 @@ struct pgb_orb {
   cudaEvent_t evDone = nullptr;
   cudaEvent_t evChunk[16] = {};
   int h2dChunk = 16;  // largest H2D/compute pipeline chunk in frames (PGB_H2D_CHUNK)
+  int h2dMinChunk = 4;  // smallest chunk of the ramp-down at the end of a batch (PGB_H2D_MIN_CHUNK)
   int numSMs = 148;
 };
 
@@ -335,16 +336,16 @@ int extract_host_pipelined(pgb_orb* o, const uint8_t* gray, int n_frames, int wi
   // the copy stream may not overwrite level 0 before the previous call's kernels are done with it
   PGB_CUDA(cudaEventRecord(o->evDone, o->stream));
   PGB_CUDA(cudaStreamWaitEvent(o->copyStream, o->evDone, 0));
-  // Chunk schedule (frames): 4, 8, 16, 16, ..., 8, 4, 2, 2.  Small chunks first so the kernels start while the bulk
+  // Chunk schedule (frames): 4, 8, 16, 16, ..., 8, 4 (+ remainder).  Small chunks first so the kernels start while the bulk
   // of the batch is still on the bus; small chunks last so that what the caller waits for after the last byte has
-  // arrived is only the kernels of a 2-frame chunk.
+  // arrived is only the kernels of a small chunk (their latency floor, ~0.2 ms, is the same for 1 or 8 frames).
   // Chunks alternate over three compute streams: the latency-bound kernels of one chunk (octree, small grids) overlap
   // the throughput-bound ones of its neighbours, so chunking does not cost kernel efficiency.
   cudaStream_t cs[3] = {o->stream, o->auxStream[0], o->auxStream[1]};
   for (int a = 1; a < 3; a++) PGB_CUDA(cudaStreamWaitEvent(cs[a], o->evDone, 0));
   int used = 0;
   for (int f0 = 0, k = 0, n = 0; f0 < n_frames; f0 += n, k++) {
-    n = std::min(chunk, std::max(std::min(2, n_frames - f0), (n_frames - f0) / 2));
+    n = std::min(chunk, std::max(std::min(o->h2dMinChunk, n_frames - f0), (n_frames - f0) / 2));
     if (k < 2) n = std::min(n, std::max(1, chunk >> (2 - k)));
     cudaStream_t st = cs[k % 3];
     used = std::max(used, std::min(k, 2));
@@ -443,6 +444,7 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
         cudaEventCreateWithFlags(&o->evAux[a], cudaEventDisableTiming) != cudaSuccess)
       return bail("cudaStreamCreate/cudaEventCreate failed");
   if (const char* e = getenv("PGB_H2D_CHUNK")) o->h2dChunk = std::max(1, atoi(e));
+  if (const char* e = getenv("PGB_H2D_MIN_CHUNK")) o->h2dMinChunk = std::max(1, atoi(e));
   const OrbGeo& c = o->capGeo;
   const size_t B = (size_t)max_batch;
   o->outCap = 0;
