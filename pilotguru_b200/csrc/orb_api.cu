@@ -61,6 +61,7 @@ struct pgb_orb {
   int outCap = 0;
   DevBuf<uint8_t> tmpLevel;
   TmapPack tmaps{};
+  TmapPack tmapsCur{};  // = tmaps, with in[0] re-encoded on the caller's buffer while level 0 is read in place
   DevBuf<int4> tileTab;
   DevBuf<int> cellTab;  // per FAST cell: level | grid row << 8 | grid column << 20
   cudaStream_t copyStream = nullptr;
@@ -242,6 +243,32 @@ int build_tmaps(pgb_orb* o) {
   return PGB_OK;
 }
 
+// Level 0 in place (PGB_IN_DEVICE input that is 16-byte aligned): kernels read the caller's frames where they lie.
+int use_external_level0(pgb_orb* o, const uint8_t* gray, size_t pitch, size_t frame_stride, int n_frames) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = (EncodeTiledFn)fn;
+  }
+  const LevelGeo& L = o->geo.lv[0];
+  o->tmapsCur = o->tmaps;
+  const cuuint64_t dims[3] = {(cuuint64_t)(pitch / 4), (cuuint64_t)L.h, (cuuint64_t)n_frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const cuuint32_t boxIn[3] = {(cuuint32_t)kF2InWords, (cuuint32_t)kF2InRows, 1};
+  CUresult r = encode(&o->tmapsCur.in[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(gray), dims, strides, boxIn, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(external level 0) failed: %d", (int)r);
+  o->geo.ext0 = gray;
+  o->geo.ext0Stride = frame_stride;
+  o->geo.ext0Pitch = (int)pitch;
+  return PGB_OK;
+}
+
 int set_geometry(pgb_orb* o, int w, int h) {
   if (w == o->curW && h == o->curH) return PGB_OK;
   OrbGeo g;
@@ -292,8 +319,9 @@ int check_err_flag(pgb_orb* o) {
 int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap, int f0, int n,
                cudaStream_t st = nullptr) {
   if (!st) st = o->stream;
-  const OrbGeo& g = o->geo;
   if (n <= 0) return PGB_OK;
+  OrbGeo g = o->geo;  // kernels index frames relative to f0: advance the in-place level 0 like the other bases
+  if (g.ext0) g.ext0 += (size_t)f0 * g.ext0Stride;
   uint8_t* pyr = o->pyr.p + (size_t)f0 * g.frameStride;
   uint8_t* score = o->score.p + (size_t)f0 * g.frameStride;
   uint32_t* slots = o->slots.p + (size_t)f0 * g.slotsPerFrame;
@@ -310,7 +338,7 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         break;
       case 1:
       {
-        int rc = launch_fast_score(g, o->tmaps, o->tileTab.p, f0, n, st);
+        int rc = launch_fast_score(g, o->tmapsCur, o->tileTab.p, f0, n, st);
         if (rc) return rc;
         break;
       }
@@ -529,7 +557,14 @@ int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames
   uint8_t* dd = outDev ? desc : o->desc.p;
   int* dc = outDev ? counts : o->counts.p;
   const int dcap = outDev ? cap : o->outCap;  // a caller capacity below pgb_orb_max_keypoints() raises the device flag
-  if (inDev) {
+  o->geo.ext0 = nullptr;
+  o->tmapsCur = o->tmaps;
+  if (inDev && ((size_t)gray & 15) == 0 && (pitch & 15) == 0 && (frame_stride & 15) == 0 && frame_stride >= pitch * (size_t)height) {
+    // level 0 is read in place: no copy; the frames must stay valid until the next extract call on this handle
+    rc = use_external_level0(o, gray, pitch, frame_stride, n_frames);
+    if (rc) return rc;
+    rc = run_stages(o, 0, 4, dk, dd, dc, dcap, 0, n_frames);
+  } else if (inDev) {
     if (pitch == (size_t)width && g.lv[0].pitch == width) {
       // contiguous frames: ONE 2-D copy whose "rows" are whole frames (128 separate 2 MB copies cost 0.8 ms of gaps)
       PGB_CUDA(cudaMemcpy2DAsync(o->pyr.p + g.lv[0].off, g.frameStride, gray, frame_stride, (size_t)width * height, n_frames,
@@ -584,8 +619,12 @@ static int copy_level_out(pgb_orb* o, const uint8_t* base, int frame, int level,
   if (w) *w = L.w;
   if (h) *h = L.h;
   if (!out) return PGB_OK;
-  PGB_CUDA(cudaMemcpy2DAsync(out, L.w, base + (size_t)frame * o->geo.frameStride + L.off, L.pitch, L.w, L.h,
-                             cudaMemcpyDeviceToHost, o->stream));
+  if (level == 0 && base == o->pyr.p && o->geo.ext0)  // level 0 read in place from the caller's (still valid) frames
+    PGB_CUDA(cudaMemcpy2DAsync(out, L.w, o->geo.ext0 + (size_t)frame * o->geo.ext0Stride, o->geo.ext0Pitch, L.w, L.h,
+                               cudaMemcpyDeviceToHost, o->stream));
+  else
+    PGB_CUDA(cudaMemcpy2DAsync(out, L.w, base + (size_t)frame * o->geo.frameStride + L.off, L.pitch, L.w, L.h,
+                               cudaMemcpyDeviceToHost, o->stream));
   PGB_CUDA(cudaStreamSynchronize(o->stream));
   return PGB_OK;
 }

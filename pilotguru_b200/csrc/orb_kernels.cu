@@ -27,11 +27,12 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeo g, int level, uint8_t* _
   const int y = blockIdx.y;
   if (xq >= wq) return;
   uint8_t* frame = pyr + (size_t)blockIdx.z * g.frameStride;
-  const uint8_t* src = frame + S.off;
+  int sPitch;
+  const uint8_t* src = level_base(g, pyr, level - 1, blockIdx.z, &sPitch);
   const ResizeTab ty = ytab[y];
   const int sy0 = min(max((int)ty.s, 0), S.h - 1), sy1 = min(max((int)ty.s + 1, 0), S.h - 1);
-  const uint8_t* S0 = src + (size_t)sy0 * S.pitch;
-  const uint8_t* S1 = src + (size_t)sy1 * S.pitch;
+  const uint8_t* S0 = src + (size_t)sy0 * sPitch;
+  const uint8_t* S1 = src + (size_t)sy1 * sPitch;
   uint32_t packed = 0;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * kPyW, y0 = blockIdx.y * kPyH;
   uint8_t* frame = pyr + (size_t)blockIdx.z * g.frameStride;
-  const uint8_t* src = frame + S.off;
+  int sPitch;
+  const uint8_t* src = level_base(g, pyr, level - 1, blockIdx.z, &sPitch);
   const int2 fx = __ldg(&tileX[blockIdx.x]), fy = __ldg(&tileY[blockIdx.y]);
   const int ax = fx.x, nvec = fx.y, syLo = fy.x, nrows = fy.y;  // host guarantees nvec*16 <= pitch, nrows <= rows
   if (tid < kPyH) s_ty[tid] = ytab[min(y0 + tid, D.h - 1)];
@@ -75,10 +77,10 @@ __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint
     const int warp = tid >> 5, lane = tid & 31;
     if (lane < nvec) {
       const int gx = ax + lane * 16;
-      const bool in = gx < S.pitch;
+      const bool in = gx < sPitch;
       for (int r = warp; r < nrows; r += 8) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (in) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(syLo + r) * S.pitch + gx));
+        if (in) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(syLo + r) * sPitch + gx));
         *reinterpret_cast<uint4*>(s_src + r * kPySrcPitch + lane * 16) = v;
       }
     }
@@ -703,7 +705,8 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
   const int oi = before + j;
   if (oi >= cap) return;
   const StagedKp kp = staged[(size_t)f * g.kpCapInternal + slot];
-  const uint8_t* img = pyr + (size_t)f * g.frameStride + L.off;
+  int iPitch;
+  const uint8_t* img = level_base(g, pyr, level, f, &iPitch);
   uint8_t* Pw = s_patch[warp];
   // stage the patch.  Interior keypoints (all 45x45 px inside the level) copy aligned 32-bit words and keep the
   // row's byte phase; keypoints within 22 px of a border take the byte path with BORDER_REFLECT_101.
@@ -721,7 +724,7 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
     for (int u = 0; u < 6; u++) {
       const int i = lane + 32 * u, r = i >> 2, k = i & 3;
       v[u] = make_uint4(0, 0, 0, 0);
-      if (r < kPW && a + 16 * k < L.pitch) v[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)(ys + r) * L.pitch + a) + k);
+      if (r < kPW && a + 16 * k < iPitch) v[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)(ys + r) * iPitch + a) + k);
     }
 #pragma unroll
     for (int u = 0; u < 6; u++) {
@@ -739,7 +742,7 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
     for (int i = lane; i < kPW * kPW; i += 32) {
       const int r = i / kPW, c = i - r * kPW;
       const int y = reflect101(ys + r, L.h), x = reflect101(xs + c, L.w);
-      Pw[r * kPP + c] = __ldg(img + (size_t)y * L.pitch + x);
+      Pw[r * kPP + c] = __ldg(img + (size_t)y * iPitch + x);
     }
   }
   const uint8_t* P = Pw + po;  // P[r * kPP + c] = level pixel (ys + r, xs + c)
@@ -850,12 +853,13 @@ __global__ void __launch_bounds__(256) k_blur_level(OrbGeo g, int level, int fra
   const LevelGeo& L = g.lv[level];
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= L.w) return;
-  const uint8_t* img = pyr + (size_t)frame * g.frameStride + L.off;
+  int iPitch;
+  const uint8_t* img = level_base(g, pyr, level, frame, &iPitch);
   const int k[7] = {18, 34, 48, 56, 48, 34, 18};
   int acc = 0;
 #pragma unroll
   for (int dy = -3; dy <= 3; dy++) {
-    const uint8_t* row = img + (size_t)reflect101(y + dy, L.h) * L.pitch;
+    const uint8_t* row = img + (size_t)reflect101(y + dy, L.h) * iPitch;
     int h = 0;
 #pragma unroll
     for (int dx = -3; dx <= 3; dx++) h += k[dx + 3] * (int)__ldg(row + reflect101(x + dx, L.w));

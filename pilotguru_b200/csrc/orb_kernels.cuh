@@ -57,8 +57,25 @@ struct OrbGeo {
   unsigned absMask;  // FAST v3 prefilter: bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
   int totalCells, totalTiles2, kpCapInternal, maxNodeCap;
   unsigned long long frameStride, slotsPerFrame, candPerFrame;
+  // Level 0 in place: when the caller's frames are device-resident and 16-byte aligned, level 0 is read where it lies
+  // (ext0 + f * ext0Stride, rows ext0Pitch apart) instead of being copied into the pyramid buffer.
+  const uint8_t* ext0;
+  unsigned long long ext0Stride;
+  int ext0Pitch;
   LevelGeo lv[kMaxLevels];
 };
+
+#ifdef __CUDACC__
+// Base address and row pitch of level `level` of frame f (f relative to the pointers the kernel was given).
+__device__ __forceinline__ const uint8_t* level_base(const OrbGeo& g, const uint8_t* pyr, int level, int f, int* pitch) {
+  if (level == 0 && g.ext0) {
+    *pitch = g.ext0Pitch;
+    return g.ext0 + (size_t)f * g.ext0Stride;
+  }
+  *pitch = g.lv[level].pitch;
+  return pyr + (size_t)f * g.frameStride + g.lv[level].off;
+}
+#endif
 
 struct alignas(64) TmapPack {  // per level: u32 views of the pyramid (load) and of the score map (store)
   CUtensorMap in[kMaxLevels];
