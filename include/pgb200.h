@@ -168,6 +168,23 @@ int pgb_match_map_points(pgb_matcher*, int n_frames, int cap, const pgb_keypoint
                          float max_y, float th, const float* scale_factors, int nlevels, int32_t* match_of_feature,
                          int32_t* n_matches, int is_device);
 
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:161-290; Tracking::TrackReferenceKeyFrame,
+ * Tracking::Relocalization) for n_pairs independent (keyframe, frame) problems.  Per problem p: keyframe descriptors
+ * kf_desc[p][cap][32], angles kf_angle[p][cap] (mvKeysUn[i].angle), kf_has_map_point[p][cap] (vpMapPointsKF[i] &&
+ * !isBad()); frame descriptors f_desc, angles f_angle (mvKeys[i].angle), f_counts[p] = F.N.  The DBoW2::FeatureVector
+ * of each side is a CSR: nodes kf_node_off[p] .. kf_node_off[p+1]-1 belong to problem p, node k has id kf_node_id[k]
+ * (strictly increasing inside a problem = std::map order) and lists the features kf_feat_idx[kf_feat_start[k] ..
+ * kf_feat_start[k+1]-1] in their vector order; same for f_*.  A frame feature appears in at most one node (what
+ * DBoW2's transform produces); anything else -> PGB_ERR_INVALID.  match_of_feature[p][cap] = index of the keyframe
+ * feature whose map point the frame feature received (vpMapPointMatches), else -1; n_matches[p] = the return value.
+ * TH_LOW = 50, the matcher's nnratio and checkOrientation apply. */
+int pgb_match_by_bow(pgb_matcher*, int n_pairs, int cap, const uint8_t* kf_desc, const float* kf_angle,
+                     const uint8_t* kf_has_map_point, const int32_t* kf_node_off, const uint32_t* kf_node_id,
+                     const int32_t* kf_feat_start, const uint32_t* kf_feat_idx, int kf_nodes_total, int kf_idx_total,
+                     const uint8_t* f_desc, const float* f_angle, const int32_t* f_counts, const int32_t* f_node_off,
+                     const uint32_t* f_node_id, const int32_t* f_feat_start, const uint32_t* f_feat_idx, int f_nodes_total,
+                     int f_idx_total, int32_t* match_of_feature, int32_t* n_matches, int is_device);
+
 /* MapPoint::ComputeDistinctiveDescriptors (thirdparty/orb-slam2/src/MapPoint.cc:259-324) for n_points map points:
  * the observing descriptors of point p are rows offsets[p] .. offsets[p+1]-1 of desc[][32]; best_idx[p] = row (relative
  * to offsets[p]) with the least median Hamming distance to the others, -1 for a point without observations.

@@ -44,6 +44,11 @@ int pgo_search_map_points(const pgb_keypoint* kps, const uint8_t* desc, int n, c
                           const float* proj_xy, const int32_t* track_level, const float* view_cos, const uint8_t* mp_desc,
                           const uint8_t* in_view, const uint8_t* mp_observed, int n_mp, float minX, float maxX, float minY,
                           float maxY, float th, const float* scale_factors, float nnratio, int32_t* match_of_feature);
+int pgo_search_by_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_map_point,
+                      const uint32_t* kf_node_id, const int32_t* kf_feat_start, const uint32_t* kf_feat_idx, int kf_nodes,
+                      const uint8_t* f_desc, const float* f_angle, int f_n, const uint32_t* f_node_id,
+                      const int32_t* f_feat_start, const uint32_t* f_feat_idx, int f_nodes, float nnratio, int check_ori,
+                      int32_t* match_of_feature);
 int pgo_distinctive_descriptor(const uint8_t* desc, int N);
 int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,

@@ -276,6 +276,66 @@ int pgo_search_map_points(const pgb_keypoint* kps, const uint8_t* desc, int n, c
   return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:161-290), literal.  The two
+// DBoW2::FeatureVector maps (node id -> feature indices, std::map order) arrive as CSR arrays sorted by node id; the
+// merge with lower_bound jumps is restated on them.  kf_has_map_point[i] = vpMapPointsKF[i] && !isBad().
+// match_of_feature[idxF] = index of the keyframe feature whose map point F's feature received, else -1.
+int pgo_search_by_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_map_point,
+                      const uint32_t* kf_node_id, const int32_t* kf_feat_start, const uint32_t* kf_feat_idx, int kf_nodes,
+                      const uint8_t* f_desc, const float* f_angle, int f_n, const uint32_t* f_node_id,
+                      const int32_t* f_feat_start, const uint32_t* f_feat_idx, int f_nodes, float nnratio, int check_ori,
+                      int32_t* match_of_feature) {
+  for (int i = 0; i < f_n; i++) match_of_feature[i] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  int KFit = 0, Fit = 0;
+  while (KFit != kf_nodes && Fit != f_nodes) {
+    if (kf_node_id[KFit] == f_node_id[Fit]) {
+      for (int iKF = kf_feat_start[KFit]; iKF < kf_feat_start[KFit + 1]; iKF++) {
+        const unsigned realIdxKF = kf_feat_idx[iKF];
+        if (!kf_has_map_point[realIdxKF]) continue;
+        const uint8_t* dKF = kf_desc + (size_t)realIdxKF * 32;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int iF = f_feat_start[Fit]; iF < f_feat_start[Fit + 1]; iF++) {
+          const unsigned realIdxF = f_feat_idx[iF];
+          if (match_of_feature[realIdxF] >= 0) continue;
+          const int dist = descriptor_distance(dKF, f_desc + (size_t)realIdxF * 32);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = (int)realIdxF; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            match_of_feature[bestIdxF] = (int)realIdxKF;
+            if (check_ori) {
+              float rot = kf_angle[realIdxKF] - f_angle[bestIdxF];
+              if (rot < 0.0) rot += 360.0f;
+              int bin = (int)roundf(rot * factor);
+              if (bin == HISTO_LENGTH) bin = 0;
+              rotHist[bin].push_back(bestIdxF);
+            }
+            nmatches++;
+          }
+        }
+      }
+      KFit++; Fit++;
+    } else if (kf_node_id[KFit] < f_node_id[Fit]) {
+      KFit = (int)(std::lower_bound(kf_node_id, kf_node_id + kf_nodes, f_node_id[Fit]) - kf_node_id);
+    } else {
+      Fit = (int)(std::lower_bound(f_node_id, f_node_id + f_nodes, kf_node_id[KFit]) - f_node_id);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { match_of_feature[idx] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
 // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324), literal: index of the descriptor with the least
 // median distance to the rest (float distance matrix, std::sort of each row, vDists[0.5*(N-1)]).
 int pgo_distinctive_descriptor(const uint8_t* desc, int N) {

@@ -61,6 +61,8 @@ _SIGS = {
                                                C.c_float, C.c_float, vp, vp, C.c_int]),
     "pgb_match_map_points": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_float, vp, C.c_int, vp, vp, C.c_int]),
+    "pgb_match_by_bow": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                   vp, C.c_int, C.c_int, vp, vp, C.c_int]),
     "pgb_distinctive_descriptors": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
     "pgb_imu_create": (vp, [C.c_int, vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp]),
     "pgb_imu_destroy": (None, [vp]),

@@ -688,6 +688,131 @@ __global__ void __launch_bounds__(kMtThreads) k_match_windowed(WinArgs A) {
   A.nMatches[p] = nm;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:161-290).  The two DBoW2 feature vectors
+// arrive as CSR arrays sorted by node id.  A frame feature belongs to exactly one vocabulary node, so the reference's
+// only sequential dependence ("skip features of F that already got a map point") stays inside a node: one warp per
+// common node replays that node's keyframe features in order, the lanes share the node's frame features, the best and
+// second-best distances are two warp REDUX on (distance, position) keys.  One CTA per (keyframe, frame) problem; the
+// rotation histogram lives in shared memory and is applied after a CTA barrier.
+struct BowArgs {
+  int cap, checkOri;
+  float nnratio;
+  const uint8_t* kfD;        // [prob][cap][32]
+  const float* kfAng;        // [prob][cap]    mvKeysUn[i].angle
+  const uint8_t* kfHas;      // [prob][cap]    vpMapPointsKF[i] && !isBad()
+  const int* kfNodeOff;      // [prob + 1]     node range of each problem
+  const uint32_t* kfNode;    // node ids, strictly increasing inside a problem
+  const int* kfStart;        // [nodes + 1]    CSR over kfIdx
+  const uint32_t* kfIdx;
+  const uint8_t* fD;
+  const float* fAng;
+  const int* fN;             // [prob] F.N
+  const int* fNodeOff;
+  const uint32_t* fNode;
+  const int* fStart;
+  const uint32_t* fIdx;
+  int* matchOfF;             // [prob][cap]
+  int* nMatches;             // [prob]
+  int* err;
+};
+
+__global__ void __launch_bounds__(kMtThreads) k_match_bow(BowArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cap = A.cap;
+  int* sHist = reinterpret_cast<int*>(smem);                       // [32]: 30 bins, [30] = match count
+  uint32_t* sSeen = reinterpret_cast<uint32_t*>(sHist + 32);       // [(cap + 31) / 32] frame feature listed in a node
+  signed char* sBin = reinterpret_cast<signed char*>(sSeen + (cap + 31) / 32);  // [cap] bin the feature was pushed to
+  int* mOf = A.matchOfF + (size_t)p * cap;
+  const int nF = min(A.fN[p], cap);
+  const int k0 = A.kfNodeOff[p], k1 = A.kfNodeOff[p + 1], f0 = A.fNodeOff[p], f1 = A.fNodeOff[p + 1];
+  for (int t = tid; t < cap; t += kMtThreads) { mOf[t] = -1; sBin[t] = -1; }
+  for (int t = tid; t < (cap + 31) / 32; t += kMtThreads) sSeen[t] = 0;
+  if (tid < 32) sHist[tid] = 0;
+  __syncthreads();
+
+  // input contract: node ids strictly increasing, indices in range, a frame feature in at most one node
+  bool bad = false;
+  for (int k = k0 + tid; k + 1 < k1; k += kMtThreads) bad |= A.kfNode[k] >= A.kfNode[k + 1];
+  for (int k = f0 + tid; k + 1 < f1; k += kMtThreads) bad |= A.fNode[k] >= A.fNode[k + 1];
+  if (k1 > k0)
+    for (int i = A.kfStart[k0] + tid; i < A.kfStart[k1]; i += kMtThreads) bad |= A.kfIdx[i] >= (uint32_t)cap;
+  if (f1 > f0)
+    for (int i = A.fStart[f0] + tid; i < A.fStart[f1]; i += kMtThreads) {
+      const uint32_t x = A.fIdx[i];
+      if (x >= (uint32_t)nF) { bad = true; continue; }
+      if (atomicOr(&sSeen[x >> 5], 1u << (x & 31)) & (1u << (x & 31))) bad = true;
+    }
+  if (bad) atomicOr(A.err, 1);
+  __syncthreads();
+
+  const uint32_t* kfD = reinterpret_cast<const uint32_t*>(A.kfD + (size_t)p * cap * 32);
+  const uint32_t* fD = reinterpret_cast<const uint32_t*>(A.fD + (size_t)p * cap * 32);
+  const float factor = 1.0f / kHisto;
+  for (int k = k0 + warp; k < k1; k += kMtThreads / 32) {
+    const uint32_t id = A.kfNode[k];
+    int lo = f0, hi = f1;                                   // lower_bound of id among F's nodes
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (A.fNode[mid] < id) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= f1 || A.fNode[lo] != id) continue;
+    const int fs = A.fStart[lo], fe = A.fStart[lo + 1];
+    for (int iKF = A.kfStart[k]; iKF < A.kfStart[k + 1]; iKF++) {
+      const uint32_t realIdxKF = A.kfIdx[iKF];
+      if (realIdxKF >= (uint32_t)cap || !A.kfHas[(size_t)p * cap + realIdxKF]) continue;
+      uint32_t q[8];
+#pragma unroll
+      for (int w = 0; w < 8; w++) q[w] = kfD[(size_t)realIdxKF * 8 + w];
+      uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu;         // (distance << 16 | position in the node), two smallest
+      for (int iF = fs + lane; iF < fe; iF += 32) {
+        const uint32_t realIdxF = A.fIdx[iF];
+        if (realIdxF >= (uint32_t)nF || mOf[realIdxF] >= 0) continue;
+        const uint32_t key = ((uint32_t)hamming256(q, fD + (size_t)realIdxF * 8) << 16) | (uint32_t)(iF - fs);
+        if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
+      }
+      const uint32_t best = __reduce_min_sync(0xffffffffu, b1);
+      const uint32_t second = __reduce_min_sync(0xffffffffu, b1 == best ? b2 : b1);
+      if (lane == 0 && best != 0xffffffffu) {
+        const int bestDist1 = (int)(best >> 16), bestDist2 = second == 0xffffffffu ? 256 : (int)(second >> 16);
+        if (bestDist1 <= kThLow && (float)bestDist1 < A.nnratio * (float)bestDist2) {
+          const uint32_t bestIdxF = A.fIdx[fs + (int)(best & 0xffffu)];
+          mOf[bestIdxF] = (int)realIdxKF;
+          if (A.checkOri) {
+            float rot = A.kfAng[(size_t)p * cap + realIdxKF] - A.fAng[(size_t)p * cap + bestIdxF];
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == kHisto) bin = 0;
+            sBin[bestIdxF] = (signed char)bin;
+            atomicAdd(&sHist[bin], 1);
+          }
+          atomicAdd(&sHist[30], 1);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (A.checkOri) {
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;   // ComputeThreeMaxima, every thread the same
+    for (int b = 0; b < kHisto; b++) {
+      const int s = sHist[b];
+      if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+      else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+      else if (s > max3) { max3 = s; ind3 = b; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+    for (int t = tid; t < nF; t += kMtThreads) {
+      const int b = sBin[t];
+      if (b < 0 || b == ind1 || b == ind2 || b == ind3) continue;
+      mOf[t] = -1;
+      atomicSub(&sHist[30], 1);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) A.nMatches[p] = sHist[30];
+}
+
 // MapPoint::ComputeDistinctiveDescriptors (thirdparty/orb-slam2/src/MapPoint.cc:259-324): among the N descriptors that
 // observe a map point, the one with the least median Hamming distance to the rest (median = sorted row[(size_t)(0.5 *
 // (N - 1))], the row includes the zero self-distance; first index wins ties).  One warp per map point; for each
@@ -1083,6 +1208,65 @@ int pgb_match_map_points(pgb_matcher* m, int n_frames, int cap, const pgb_keypoi
     PGB_CUDA(cudaMemcpyAsync(n_matches, dNm.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
     PGB_CUDA(cudaStreamSynchronize(s));
   }
+  return PGB_OK;
+}
+
+int pgb_match_by_bow(pgb_matcher* m, int n_pairs, int cap, const uint8_t* kf_desc, const float* kf_angle,
+                     const uint8_t* kf_has_map_point, const int32_t* kf_node_off, const uint32_t* kf_node_id,
+                     const int32_t* kf_feat_start, const uint32_t* kf_feat_idx, int kf_nodes_total, int kf_idx_total,
+                     const uint8_t* f_desc, const float* f_angle, const int32_t* f_counts, const int32_t* f_node_off,
+                     const uint32_t* f_node_id, const int32_t* f_feat_start, const uint32_t* f_feat_idx, int f_nodes_total,
+                     int f_idx_total, int32_t* match_of_feature, int32_t* n_matches, int is_device) {
+  if (!m) return fail(PGB_ERR_INVALID, "null handle");
+  if (n_pairs < 0 || cap <= 0 || cap > 65535 || kf_nodes_total < 0 || kf_idx_total < 0 || f_nodes_total < 0 || f_idx_total < 0)
+    return fail(PGB_ERR_INVALID, "pgb_match_by_bow: invalid argument");
+  if (n_pairs == 0) return PGB_OK;
+  if (!kf_desc || !kf_angle || !kf_has_map_point || !kf_node_off || !kf_feat_start || !f_desc || !f_angle || !f_counts ||
+      !f_node_off || !f_feat_start || !match_of_feature || !n_matches || (kf_nodes_total && !kf_node_id) ||
+      (kf_idx_total && !kf_feat_idx) || (f_nodes_total && !f_node_id) || (f_idx_total && !f_feat_idx))
+    return fail(PGB_ERR_INVALID, "pgb_match_by_bow: null buffer");
+  PGB_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const size_t n = (size_t)n_pairs * cap;
+  DevBuf<uint8_t> dKD, dKH, dFD;
+  DevBuf<float> dKA, dFA;
+  DevBuf<int> dKO, dKS, dFN, dFO, dFS, dMatch, dNm, dErr;
+  DevBuf<uint32_t> dKN, dKI, dFNode, dFI;
+  int rc = stage_in(dKD, kf_desc, n * 32, is_device, s) | stage_in(dKA, kf_angle, n, is_device, s) |
+           stage_in(dKH, kf_has_map_point, n, is_device, s) | stage_in(dKO, kf_node_off, (size_t)n_pairs + 1, is_device, s) |
+           stage_in(dKN, kf_node_id, kf_nodes_total, is_device, s) | stage_in(dKS, kf_feat_start, (size_t)kf_nodes_total + 1, is_device, s) |
+           stage_in(dKI, kf_feat_idx, kf_idx_total, is_device, s) | stage_in(dFD, f_desc, n * 32, is_device, s) |
+           stage_in(dFA, f_angle, n, is_device, s) | stage_in(dFN, f_counts, n_pairs, is_device, s) |
+           stage_in(dFO, f_node_off, (size_t)n_pairs + 1, is_device, s) | stage_in(dFNode, f_node_id, f_nodes_total, is_device, s) |
+           stage_in(dFS, f_feat_start, (size_t)f_nodes_total + 1, is_device, s) | stage_in(dFI, f_feat_idx, f_idx_total, is_device, s);
+  if (rc || dErr.alloc(1)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemsetAsync(dErr.p, 0, sizeof(int), s));
+  int* dmatch = match_of_feature;
+  int* dnm = n_matches;
+  if (!is_device) {
+    if (dMatch.alloc(n) || dNm.alloc(n_pairs)) return PGB_ERR_CUDA;
+    dmatch = dMatch.p; dnm = dNm.p;
+  }
+  BowArgs A;
+  memset(&A, 0, sizeof A);
+  A.cap = cap; A.checkOri = m->checkOri; A.nnratio = m->nnratio;
+  A.kfD = kf_desc; A.kfAng = kf_angle; A.kfHas = kf_has_map_point; A.kfNodeOff = kf_node_off; A.kfNode = kf_node_id;
+  A.kfStart = kf_feat_start; A.kfIdx = kf_feat_idx; A.fD = f_desc; A.fAng = f_angle; A.fN = f_counts; A.fNodeOff = f_node_off;
+  A.fNode = f_node_id; A.fStart = f_feat_start; A.fIdx = f_feat_idx; A.matchOfF = dmatch; A.nMatches = dnm; A.err = dErr.p;
+  const size_t smem = 128 + (size_t)((cap + 31) / 32) * 4 + cap + 16;
+  if (smem > 227 * 1024) return fail(PGB_ERR_CAPACITY, "cap %d needs %zu B of shared memory (max 227 KB)", cap, smem);
+  if (smem > 48 * 1024) PGB_CUDA(cudaFuncSetAttribute(k_match_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_match_bow<<<n_pairs, kMtThreads, smem, s>>>(A);
+  PGB_CHECK_LAUNCH();
+  int e = 0;
+  PGB_CUDA(cudaMemcpyAsync(&e, dErr.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (!is_device) {
+    PGB_CUDA(cudaMemcpyAsync(match_of_feature, dMatch.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PGB_CUDA(cudaMemcpyAsync(n_matches, dNm.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  PGB_CUDA(cudaStreamSynchronize(s));
+  if (e) return fail(PGB_ERR_INVALID, "pgb_match_by_bow: feature vectors must have strictly increasing node ids, in-range indices and "
+                                      "every frame feature in at most one node");
   return PGB_OK;
 }
 

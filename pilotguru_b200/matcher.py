@@ -114,11 +114,50 @@ class ORBmatcher:
                                          bounds[2], bounds[3], th, np_ptr(sf), len(sf), np_ptr(mo), np_ptr(nm), 0))
         return int(nm[0]), mo[:n].copy()
 
+    def SearchByBoW(self, kf_desc, kf_angle, kf_has_map_point, kf_featvec, f_desc, f_angle, f_featvec):
+        """SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:161-290) on flat arrays.  A feature vector
+        (DBoW2::FeatureVector) is a dict {node id: [feature indices]} (iterated in ascending node id, like std::map) or an
+        already flattened (node_ids, starts, indices) triple.  Returns (nmatches, match_of_feature): the keyframe feature
+        index whose map point each frame feature received, or -1."""
+        nk, nf = len(kf_desc), len(f_desc)
+        cap = max(nk, nf, 1)
+
+        def pad(a, dtype, tail=()):
+            out = np.zeros((cap,) + tail, dtype)
+            a = np.asarray(a)
+            if len(a):
+                out[:len(a)] = a
+            return out
+        kn, ks, ki = featvec_csr(kf_featvec)
+        fn, fs, fi = featvec_csr(f_featvec)
+        KD = pad(kf_desc, np.uint8, (32,)); KA = pad(kf_angle, np.float32); KH = pad(kf_has_map_point, np.uint8)
+        FD = pad(f_desc, np.uint8, (32,)); FA = pad(f_angle, np.float32)
+        ko = np.array([0, len(kn)], np.int32); fo = np.array([0, len(fn)], np.int32); c = np.array([nf], np.int32)
+        mo = np.full(cap, -1, np.int32); nm = np.zeros(1, np.int32)
+        check(lib().pgb_match_by_bow(self._h, 1, cap, np_ptr(KD), np_ptr(KA), np_ptr(KH), np_ptr(ko), np_ptr(kn), np_ptr(ks),
+                                     np_ptr(ki), len(kn), len(ki), np_ptr(FD), np_ptr(FA), np_ptr(c), np_ptr(fo), np_ptr(fn),
+                                     np_ptr(fs), np_ptr(fi), len(fn), len(fi), np_ptr(mo), np_ptr(nm), 0))
+        return int(nm[0]), mo[:nf].copy()
+
     def match_consecutive_ptr(self, n_pairs, cap, kps_ptr, desc_ptr, counts_ptr, flow_ptr, max_x, max_y, th,
                               scale_factors, match_ptr, nmatch_ptr):
         sf = np.ascontiguousarray(scale_factors, np.float32)
         check(lib().pgb_match_consecutive(self._h, n_pairs, cap, kps_ptr, desc_ptr, counts_ptr, flow_ptr, max_x, max_y,
                                           th, np_ptr(sf), len(sf), match_ptr, nmatch_ptr))
+
+
+def featvec_csr(fv):
+    """DBoW2::FeatureVector as (node_ids u32 ascending, starts i32 [nodes + 1], indices u32)."""
+    if isinstance(fv, dict):
+        ids = sorted(fv)
+        lists = [np.asarray(fv[k], np.uint32).reshape(-1) for k in ids]
+        starts = np.zeros(len(ids) + 1, np.int32)
+        if ids:
+            starts[1:] = np.cumsum([len(x) for x in lists])
+        idx = np.concatenate(lists).astype(np.uint32) if ids and starts[-1] else np.zeros(0, np.uint32)
+        return np.asarray(ids, np.uint32), starts, idx
+    ids, starts, idx = fv
+    return np.ascontiguousarray(ids, np.uint32), np.ascontiguousarray(starts, np.int32), np.ascontiguousarray(idx, np.uint32)
 
 
 def ComputeDistinctiveDescriptors(descriptor_sets):

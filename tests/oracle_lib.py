@@ -384,6 +384,20 @@ def search_map_points(kps, desc, has_mp, proj_xy, track_level, view_cos, mp_desc
     return n, mo[:len(kps)].copy()
 
 
+def search_by_bow(kf_desc, kf_angle, kf_has_mp, kf_featvec, f_desc, f_angle, f_featvec, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW (ORBmatcher.cc:161-290), literal; feature vectors as (node_ids, starts, indices)."""
+    kd = np.ascontiguousarray(kf_desc, np.uint8); ka = np.ascontiguousarray(kf_angle, np.float32)
+    kh = np.ascontiguousarray(kf_has_mp, np.uint8); fd = np.ascontiguousarray(f_desc, np.uint8)
+    fa = np.ascontiguousarray(f_angle, np.float32)
+    kn, ks, ki = [np.ascontiguousarray(a, t) for a, t in zip(kf_featvec, (np.uint32, np.int32, np.uint32))]
+    fn, fs, fi = [np.ascontiguousarray(a, t) for a, t in zip(f_featvec, (np.uint32, np.int32, np.uint32))]
+    mo = np.full(max(len(fd), 1), -1, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = lib().pgo_search_by_bow(vp(kd), vp(ka), vp(kh), vp(kn), vp(ks), vp(ki), len(kn), vp(fd), vp(fa), len(fd), vp(fn), vp(fs),
+                                vp(fi), len(fn), C.c_float(nnratio), int(check_ori), vp(mo))
+    return n, mo[:len(fd)].copy()
+
+
 def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324), literal; -1 for an empty set."""
     d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)

@@ -171,3 +171,31 @@ def test_distinctive_descriptors_match_oracle():
     assert got.tolist() == want
     with pytest.raises(Exception):
         ComputeDistinctiveDescriptors([rng.integers(0, 256, (257, 32), dtype=np.uint8)])   # capacity: loud, never truncated
+
+
+def test_search_by_bow_matches_oracle():
+    """ORBmatcher::SearchByBoW (ORBmatcher.cc:161-290): vpMapPointMatches and the count, bit-exact against the literal
+    restatement, for small and large vocabulary nodes, shuffled node lists, with and without the orientation filter."""
+    import bow_util as B
+    from pilotguru_b200 import PgbError
+    from pilotguru_b200.matcher import ORBmatcher, featvec_csr
+    total = 0
+    for (t0, t1, seed, cell), (ratio, ori) in zip(((0, 1, 1, 80), (2, 5, 2, 80), (3, 3, 3, 40), (1, 2, 4, 1000)),
+                                                  ((0.7, True), (0.9, True), (0.75, False), (0.8, True))):
+        P = B.problem(t0, t1, seed, cell=cell)
+        m = ORBmatcher(ratio, ori, max_feats=600)
+        on, om = O.search_by_bow(P["kf_desc"], P["kf_angle"], P["kf_has"], featvec_csr(P["kf_fv"]), P["f_desc"], P["f_angle"],
+                                 featvec_csr(P["f_fv"]), nnratio=ratio, check_ori=ori)
+        gn, gm = m.SearchByBoW(P["kf_desc"], P["kf_angle"], P["kf_has"], P["kf_fv"], P["f_desc"], P["f_angle"], P["f_fv"])
+        assert gn == on and np.array_equal(gm, om)
+        total += on
+        m.close()
+    assert total > 200
+    m = ORBmatcher(0.7, True, max_feats=600)
+    P = B.problem(0, 1, 5)
+    gn, gm = m.SearchByBoW(P["kf_desc"], P["kf_angle"], P["kf_has"], {}, P["f_desc"], P["f_angle"], P["f_fv"])   # no common node
+    assert gn == 0 and (gm == -1).all()
+    bad = dict(P["f_fv"]); k0, k1 = sorted(bad)[:2]; bad[k1] = list(bad[k1]) + [bad[k0][0]]                       # a feature in two nodes
+    with pytest.raises(PgbError):
+        m.SearchByBoW(P["kf_desc"], P["kf_angle"], P["kf_has"], P["kf_fv"], P["f_desc"], P["f_angle"], bad)
+    m.close()

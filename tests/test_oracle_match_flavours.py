@@ -97,3 +97,30 @@ def test_distinctive_descriptor_against_numpy():
         med = np.sort(dist, axis=1)[:, int(0.5 * (n - 1))]
         assert O.distinctive_descriptor(d) == int(np.argmin(med))          # argmin: first index wins ties
     assert O.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1
+
+
+def test_search_by_bow_against_python_restatement():
+    """SearchByBoW (ORBmatcher.cc:161-290): the literal merge-loop oracle against an independent dict-based restatement,
+    plus the invariants of the reference's algorithm."""
+    import bow_util as B
+    from pilotguru_b200.matcher import featvec_csr
+    for (t0, t1, seed), (ratio, ori) in zip(((0, 1, 1), (2, 5, 2), (3, 3, 3)), ((0.7, True), (0.9, True), (0.75, False))):
+        P = B.problem(t0, t1, seed)
+        n, mo = O.search_by_bow(P["kf_desc"], P["kf_angle"], P["kf_has"], featvec_csr(P["kf_fv"]), P["f_desc"], P["f_angle"],
+                                featvec_csr(P["f_fv"]), nnratio=ratio, check_ori=ori)
+        pn, pm = B.python_search_by_bow(P, ratio, ori)
+        assert n == pn and np.array_equal(mo, pm) and n > 40
+        sel = np.nonzero(mo >= 0)[0]
+        assert len(sel) == n and P["kf_has"][mo[sel]].all()
+        node_of_f = {i: k for k, v in P["f_fv"].items() for i in v}
+        node_of_k = {i: k for k, v in P["kf_fv"].items() for i in v}
+        for jf in sel:
+            assert node_of_f[jf] == node_of_k[mo[jf]]                            # matches never leave a vocabulary node
+            assert _dist(P["kf_desc"][mo[jf]], P["f_desc"][jf]) <= 50            # TH_LOW
+    # disjoint vocabularies, empty feature vectors
+    P = B.problem(0, 1, 4)
+    kfv = {k + 100000: v for k, v in P["kf_fv"].items()}
+    n, mo = O.search_by_bow(P["kf_desc"], P["kf_angle"], P["kf_has"], featvec_csr(kfv), P["f_desc"], P["f_angle"], featvec_csr(P["f_fv"]))
+    assert n == 0 and (mo == -1).all()
+    n, mo = O.search_by_bow(P["kf_desc"], P["kf_angle"], P["kf_has"], featvec_csr({}), P["f_desc"], P["f_angle"], featvec_csr(P["f_fv"]))
+    assert n == 0 and (mo == -1).all()
