@@ -192,6 +192,21 @@ int pgb_match_by_bow(pgb_matcher*, int n_pairs, int cap, const uint8_t* kf_desc,
 int pgb_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, int is_device,
                                 void* stream);
 
+/* Optimizer::PoseOptimization(Frame*) (thirdparty/orb-slam2/src/Optimizer.cc:239-451; called from
+ * Tracking::TrackWithMotionModel / TrackReferenceKeyFrame / TrackLocalMap / Relocalization) for n_frames independent
+ * frames, monocular observations only (mvuRight < 0): 4 rounds of <= 10 g2o Levenberg-Marquardt iterations over the
+ * 6-DoF pose with Huber(sqrt(5.991)) edges, chi2 > 5.991 classifies outliers after every round, the robust kernel is
+ * dropped for the last round, every round restarts from the input pose.  Per frame f (arrays [frame][cap]): Tcw_in[f][16]
+ * = pFrame->mTcw (4x4 row-major float), kp_xy = mvKeysUn[i].pt, kp_octave, mp_xyz = mvpMapPoints[i]->GetWorldPos(),
+ * has_map_point[i] = mvpMapPoints[i] != NULL, counts[f] = N; inv_level_sigma2[nlevels] = mvInvLevelSigma2; fx, fy, cx, cy.
+ * Outputs: Tcw_out[f][16] (what SetPose receives; the input pose when there are fewer than 3 correspondences),
+ * outlier[f][cap] = mvbOutlier (0 where there is no map point), n_inliers[f] = the return value
+ * (nInitialCorrespondences - nBad).  fp64 inside, like g2o.  An octave outside [0, nlevels) -> PGB_ERR_INVALID. */
+int pgb_pose_optimization(int device, int n_frames, int cap, const float* Tcw_in, const float* kp_xy,
+                          const int32_t* kp_octave, const float* mp_xyz, const uint8_t* has_map_point,
+                          const int32_t* counts, const float* inv_level_sigma2, int nlevels, float fx, float fy, float cx,
+                          float cy, float* Tcw_out, uint8_t* outlier, int32_t* n_inliers, int is_device, void* stream);
+
 /* ------------------------------------------------------------------ IMU + GPS calibration ------------------ */
 typedef struct pgb_imu pgb_imu;
 

@@ -50,6 +50,9 @@ int pgo_search_by_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8
                       const int32_t* f_feat_start, const uint32_t* f_feat_idx, int f_nodes, float nnratio, int check_ori,
                       int32_t* match_of_feature);
 int pgo_distinctive_descriptor(const uint8_t* desc, int N);
+int pgo_pose_optimization(const float* Tcw_in, const float* kp_xy, const int32_t* kp_octave, const float* mp_xyz,
+                          const uint8_t* has_map_point, int n, const float* inv_level_sigma2, float fx, float fy, float cx,
+                          float cy, float* Tcw_out, uint8_t* outlier, uint8_t* round_outliers);
 int pgo_match_consecutive(const pgb_keypoint* prev_kps, const uint8_t* prev_desc, int n_prev,
                           const pgb_keypoint* cur_kps, const uint8_t* cur_desc, int n_cur, float flow_x, float flow_y,
                           float maxX, float maxY, float th, const float* scale_factors, int nlevels,

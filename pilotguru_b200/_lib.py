@@ -64,6 +64,8 @@ _SIGS = {
     "pgb_match_by_bow": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                    vp, C.c_int, C.c_int, vp, vp, C.c_int]),
     "pgb_distinctive_descriptors": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
+    "pgb_pose_optimization": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float,
+                                        C.c_float, C.c_float, vp, vp, vp, C.c_int, vp]),
     "pgb_imu_create": (vp, [C.c_int, vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp]),
     "pgb_imu_destroy": (None, [vp]),
     "pgb_imu_merged_count": (C.c_int64, [vp]),

@@ -398,6 +398,19 @@ def search_by_bow(kf_desc, kf_angle, kf_has_mp, kf_featvec, f_desc, f_angle, f_f
     return n, mo[:len(fd)].copy()
 
 
+def pose_optimization(Tcw, kp_xy, kp_octave, mp_xyz, has_mp, inv_level_sigma2, fx, fy, cx, cy):
+    """Optimizer::PoseOptimization (Optimizer.cc:239-451), mono; returns (n_inliers, Tcw_out, outlier, outlier_after_round[4])."""
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16); xy = np.ascontiguousarray(kp_xy, np.float32)
+    oc = np.ascontiguousarray(kp_octave, np.int32); X = np.ascontiguousarray(mp_xyz, np.float32)
+    hm = np.ascontiguousarray(has_mp, np.uint8); s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    n = len(oc)
+    To = np.zeros(16, np.float32); out = np.zeros(max(n, 1), np.uint8); rounds = np.full((4, max(n, 1)), 255, np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    r = lib().pgo_pose_optimization(vp(T), vp(xy), vp(oc), vp(X), vp(hm), n, vp(s2), C.c_float(fx), C.c_float(fy), C.c_float(cx),
+                                    C.c_float(cy), vp(To), vp(out), vp(rounds))
+    return int(r), To.reshape(4, 4), out[:n].copy(), rounds[:, :n].copy()
+
+
 def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324), literal; -1 for an empty set."""
     d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
