@@ -75,6 +75,8 @@ constexpr int kRowB = kF2InWords * 4;  // 288 bytes per staged input row
 // Exact bam of the pixel at byte pointer c inside the staged tile.
 // (Tried: 16-row bands per warp to amortise the per-band overhead -- 14 % fewer instructions but half the resident warps;
 // 5.0 -> 5.8 us/frame.)
+// (Tried: a 192-entry queue so that 5 CTAs fit an SM, with a two-pass split for bands above 192 candidates: 4.97 -> 5.13
+// us/frame -- the extra resident warps do not pay for the second passes and the smaller L1.)
 // (Tried: encoding p as fp16-compatible halves so that part of the min/max tree runs as HMNMX2 on the FMA pipes;
 // ptxas fuses the pairs into 3-input VHMNMX on the ALU pipe again, and splitting them costs issue slots -- no gain.)
 __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
