@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 W, H, NFEAT = 1920, 1080, 1000
 FAST_ALGO_BYTES_PER_FRAME = 2 * 6_419_321  # 8-level 1080p pyramid read once + u8 score map written once
 # dram__bytes_read.sum + dram__bytes_write.sum of k_fast_score per frame from the committed `ncu --set full` capture
-# (profiles/r01c_kernels_ncu_full.md: 209.0 MB read + 167.8 MB written over a 32-frame launch; part of the score map
+# (profiles/r01e_kernels_ncu_full.md: 209.1 MB read + 168.7 MB written over a 32-frame launch; part of the score map
 # is still dirty in L2 when the kernel ends, hence slightly below the algorithmic bytes)
-FAST_NCU_TRAFFIC_BYTES_PER_FRAME = (209.0e6 + 167.8e6) / 32
+FAST_NCU_TRAFFIC_BYTES_PER_FRAME = (209.1e6 + 168.7e6) / 32
 WORKLOAD = ("ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + SearchByProjection vs previous "
             "frame (BASELINE configs[1], batched)")
 STAGES = ["pyramid", "fast_score", "cell_nms", "octree", "orient_desc"]
@@ -57,13 +57,32 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions (between begin() and end()).  NVML is polled from
+    a thread every 2 ms (what nvidia-smi reads, without its start-up latency: a 10-step timed region lasts ~30 ms);
+    if NVML cannot be loaded, `nvidia-smi -lms 20` is used and the samples are filtered by arrival time."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.p = [], None
+        self.samples, self.windows, self.p, self.nv, self.max_mhz = [], [], None, None, None   # samples: (t, mhz, reasons)
+        self.stop_flag = False
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+            get(self.h); nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.nv, self.source = (nv, get, bits), "nvml, 2 ms poll"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            self.source = "nvidia-smi -lms 20"
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                        str(index), "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -71,25 +90,53 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _poll(self):
+        nv, get, bits = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)); r = int(get(self.h))
+                self.samples.append((time.monotonic(), mhz, [n for b, n in bits if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 6 and c[0].replace(".", "").isdigit():
+                if c[1].replace(".", "").isdigit():
+                    self.max_mhz = max(self.max_mhz or 0.0, float(c[1]))
+                self.samples.append((time.monotonic(), float(c[0]), [n for n, v in zip(self.NAMES, c[2:6]) if v.lower().startswith("active")]))
+
+    def wait_ready(self, timeout=5.0):
+        t0 = time.monotonic()
+        while not self.samples and time.monotonic() - t0 < timeout and (self.nv or self.p):
+            time.sleep(0.01)
+
+    def begin(self):
+        self._t0 = time.monotonic()
+
+    def end(self):
+        self.windows.append((self._t0, time.monotonic()))
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=2)
-        except Exception:
-            pass
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if not self.nv and not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
+        self.stop_flag = True
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                pass
+        slack = 0.0 if self.nv else 0.02                                  # a piped nvidia-smi line arrives up to one period late
+        inside = [s for s in self.samples if any(a <= s[0] <= b + slack for a, b in self.windows)]
+        sm = [s[1] for s in inside]
+        reasons = sorted({n for s in inside for n in s[2]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": self.source,
+                "window_ms": round(1e3 * sum(b - a for a, b in self.windows), 2)}
 
 
 def bind_to_gpu_numa_node(local):
@@ -359,19 +406,28 @@ def main():
                 dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
             return float(ms_.item())
 
+        sampler = ClockSampler(local) if rank == 0 else None              # started before the warm-up: ready when timing starts
         for _ in range(Wm):
             dev_step()
         ex.check()
         l0 = launch_count()
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.wait_ready()
+            sampler.begin()
         ms = timed(dev_step, K)
+        if sampler:
+            sampler.end()
         launches = launch_count() - l0
-        clocks = sampler.stop() if sampler else None
         ex.check()
         nm_dev = nmatch.cpu().numpy().copy(); cnt_dev = xch.counts_view().cpu().numpy().copy()
 
         e2e_run(3)
+        if sampler:
+            sampler.begin()
         ms_e2e = timed_e2e(K)
+        if sampler:
+            sampler.end()
+        clocks = sampler.stop() if sampler else None
         ex.check(); ex2.check()
         # context for the e2e number: the bare host->device transfer of one step's frames (pinned, same stream)
         ms_h2d = timed(lambda: dev_frames.copy_(host_frames, non_blocking=True), 5) / 5
@@ -430,7 +486,7 @@ def main():
                 "clocks": clocks,
                 "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": FAST_NCU_TRAFFIC_BYTES_PER_FRAME * B, "peak_source": peak_src,
-                             "traffic_source": "ncu --set full capture, profiles/r01c_kernels_ncu_full.md, scaled to this launch",
+                             "traffic_source": "ncu --set full capture, profiles/r01e_kernels_ncu_full.md, scaled to this launch",
                              "algorithmic_bytes_per_launch": FAST_ALGO_BYTES_PER_FRAME * B,
                              "us_per_launch": stage_us["fast_score"] * B},
                 "stage_us_per_frame": stage_us,

@@ -7,7 +7,7 @@
 // the kernel is bound by instruction issue, and on this part LOP3/PRMT/SHF/VIMNMX/VABSDIFF4 share one half-rate pipe
 // while IMAD runs on the other (profiles/r01_pipe_probe.txt).  This design therefore minimises instructions on the
 // ALU pipe:
-//   * one CTA per 256x64 tile; one elected thread issues a 3-D TMA load of the 72-word x 70-row halo box; every warp
+//   * one CTA per 256x32 tile (4 warps); one elected thread issues a 3-D TMA load of the 72-word x 38-row halo box; every warp
 //     owns an 8-row band of a shared-memory score tile, zeroes it, and at the end stores it with ONE TMA store
 //     (clipped by the tensor map) -- no per-thread global stores, no bounds arithmetic on the output side.
 //   * phase 1 (prefilter), 8 px per lane per row, no quantisation: VABSDIFF4 gives |c - p| for 4 pixels per
@@ -75,7 +75,9 @@ constexpr int kRowB = kF2InWords * 4;  // 288 bytes per staged input row
 // Exact bam of the pixel at byte pointer c inside the staged tile.
 // (Tried: 16-row bands per warp to amortise the per-band overhead -- 14 % fewer instructions but half the resident warps;
 // 5.0 -> 5.8 us/frame.)
-// (Tried: a 192-entry queue so that 5 CTAs fit an SM, with a two-pass split for bands above 192 candidates: 4.97 -> 5.13
+// (Tile height: 64 rows / 8 warps per CTA 4.97 us/frame, 32 rows / 4 warps 4.59, 16 rows / 2 warps 4.71 -- a CTA lives as
+// long as its slowest band, so smaller CTAs keep more warps resident; below 32 rows the halo and per-CTA set-up win.)
+// (Tried: a 192-entry queue so that 5 CTAs fit an SM, with a two-pass split for bands above 192 candidates (64-row tiles): 4.97 -> 5.13
 // us/frame -- the extra resident warps do not pay for the second passes and the smaller L1.)
 // (Tried: encoding p as fp16-compatible halves so that part of the min/max tree runs as HMNMX2 on the FMA pipes;
 // ptxas fuses the pairs into 3-input VHMNMX on the ALU pipe again, and splitting them costs issue slots -- no gain.)
@@ -118,7 +120,12 @@ __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
 //   [.., +16)                   the mbarrier
 constexpr int kFsInStage = (kF2InBytes + 127) / 128 * 128;
 constexpr int kFsQueueCap = 384;
-constexpr int kFsSmem = kFsInStage + kF2W * kF2H + 8 * kFsQueueCap * 5 + 16;
+constexpr int kFsWarps = kF2Threads / 32;
+#ifndef PGB_FS_OCC
+#define PGB_FS_OCC 8
+#endif
+constexpr int kFsOcc = PGB_FS_OCC;  // resident CTAs per SM the kernel is compiled for
+constexpr int kFsSmem = kFsInStage + kF2W * kF2H + kFsWarps * kFsQueueCap * 5 + 16;
 
 template <int kOcc>
 __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_constant__ OrbGeo g,
@@ -128,8 +135,8 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_co
   const uint32_t* sIn = reinterpret_cast<const uint32_t*>(smem);
   uint8_t* sScore = smem + kFsInStage;
   uint32_t* sQueue = reinterpret_cast<uint32_t*>(sScore + kF2W * kF2H);
-  uint8_t* sQCode = reinterpret_cast<uint8_t*>(sQueue + 8 * kFsQueueCap);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sQCode + 8 * kFsQueueCap);
+  uint8_t* sQCode = reinterpret_cast<uint8_t*>(sQueue + kFsWarps * kFsQueueCap);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sQCode + kFsWarps * kFsQueueCap);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y + frame0;
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_co
 
 // Function attributes are per device: called once per extractor handle (after its device was made current).
 int configure_fast_score() {
-  PGB_CUDA(cudaFuncSetAttribute(k_fast_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmem));
+  PGB_CUDA(cudaFuncSetAttribute(k_fast_score<kFsOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmem));
   return PGB_OK;
 }
 
@@ -306,7 +313,7 @@ int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, 
                       cudaStream_t st) {
   if (g.totalTiles2 <= 0 || nFrames <= 0) return PGB_OK;
   dim3 grid(g.totalTiles2, nFrames);
-  k_fast_score<4><<<grid, kF2Threads, kFsSmem, st>>>(g, tm, tileTab, frame0);
+  k_fast_score<kFsOcc><<<grid, kF2Threads, kFsSmem, st>>>(g, tm, tileTab, frame0);
   PGB_LAUNCHED();
   return PGB_OK;
 }

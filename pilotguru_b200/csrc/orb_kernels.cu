@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeo g, int level, uint8_t* _
 // stall samples before the first barrier, on the dependent xtab/ytab -> address -> load chain).  The source rows it needs are staged in shared memory
 // with 16-byte loads, the horizontal pass runs once per source row (not once per destination row, a 1.3x saving at
 // scale 1.2) and the vertical pass reads its two rows from shared memory.  Same integer arithmetic as k_pyramid.
-constexpr int kPySrcPitch = 416, kPySrcRows = 44;  // kPyW x kPyH = 256 x 32 destination tile (orb_kernels.cuh)
 
 __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint8_t* __restrict__ pyr,
                                                        const ResizeTab* __restrict__ xtab,
@@ -167,7 +166,10 @@ void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr,
 // = row order and bit order = x order, so one warp scan of the per-lane counts places the survivors in the
 // reference's row-major order.  (Round-1 profile of the previous word-scan version: 1120 warp-instructions per cell,
 // a third of them in the candidate scan; this one needs about a third of that.)
-constexpr int kCellWarps = 4;
+#ifndef PGB_CELL_WARPS
+#define PGB_CELL_WARPS 4
+#endif
+constexpr int kCellWarps = PGB_CELL_WARPS;
 constexpr int kCellListCap = 256;  // window over a cell's candidate sequence (natural images: one window)
 
 __global__ void __launch_bounds__(kCellWarps * 32) k_cells(OrbGeo g, const int* __restrict__ cellTab,

@@ -21,14 +21,19 @@ constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3 (ORBextractor.cc:773)
 constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE
 
 // pyramid kernel: destination tile of k_pyramid_tiled and the capacity of its source staging buffers
-constexpr int kPyW = 256, kPyH = 32;
+// (the PGB_* macros exist for A/B builds: tools/build_variants.sh)
+#ifndef PGB_PY_H
+#define PGB_PY_H 32
+#endif
+constexpr int kPyW = 256, kPyH = PGB_PY_H;
+constexpr int kPySrcPitch = 416, kPySrcRows = kPyH * 5 / 4 + 4;  // staged source footprint of a destination tile
 inline bool pyramid_tile_fits(int sw, int sh, int dw, int dh) {
   const double rx = (double)sw / dw, ry = (double)sh / dh;
-  return rx * kPyW + 34 <= 416 && ry * kPyH + 3 <= 44;
+  return rx * kPyW + 34 <= kPySrcPitch && ry * kPyH + 3 <= kPySrcRows;
 }
 
-// FAST score kernel: one CTA per 256x64 tile, TMA-staged with a halo
-constexpr int kF2W = 256, kF2H = 64, kF2Threads = 256;
+// FAST score kernel: one CTA per 256x32 tile (4 warps x 8-row bands), TMA-staged with a halo
+constexpr int kF2W = 256, kF2H = 32, kF2Threads = 128;
 constexpr int kF2InWords = kF2W / 4 + 8;  // 72 words per row: 16-byte halo left and right (a TMA box must start
                                           // on a 16-byte boundary in the innermost dimension; measured: tools/probe)
 constexpr int kF2InRows = kF2H + 6;       // 70

@@ -11,7 +11,7 @@ tag, launches_csv, bench_json, stages_rep = sys.argv[1:5]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
-shutil.copy(launches_csv, os.path.join(P, f"{tag}_launches_bench_b64.csv"))
+shutil.copy(launches_csv, os.path.join(P, f"{tag}_launches_bench.csv"))
 shutil.copy(bench_json, os.path.join(P, f"{tag}_bench_n1.json"))
 
 rows = [r for r in csv.reader(open(launches_csv)) if len(r) > 5]
@@ -27,19 +27,20 @@ b = json.load(open(bench_json))
 st = b['stage_us_per_frame']; s = sum(st.values())
 stage_of = {'pgb::k_pyramid_tiled': 'pyramid', 'pgb::k_fast_score<4>': 'fast_score', 'pgb::k_cells': 'cell_nms', 'pgb::k_octree': 'octree',
             'pgb::k_orient_desc': 'orient_desc', 'pgb::k_match': 'match', 'pgb::k_match_resolve': 'match'}
-out = [f"# {tag} launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 python bench.py --steps 2 --warmup 1 --batch 64 --no-cpu-baseline --no-calibration`",
+out = [f"# {tag} launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-calibration`",
        "Per-launch times under ncu are cold-cache and serialised: compare SHARES with the live CUDA-event stage times, not absolutes.", "",
        "| kernel | launches | total us | avg us | share (ncu) |", "|---|---|---|---|---|"]
 share_ncu = collections.Counter()
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     out.append(f"| `{k}` | {len(v)} | {sum(v):.1f} | {sum(v) / len(v):.1f} | {sum(v) / tot:.3f} |")
-    if k in stage_of: share_ncu[stage_of[k]] += sum(v) / tot
+    kk = 'pgb::k_fast_score<4>' if k.startswith('pgb::k_fast_score') else k
+    if kk in stage_of: share_ncu[stage_of[kk]] += sum(v) / tot
 out += ["", f"Live stage times of the same workload (bench line {os.path.basename(bench_json)}: value {b['value']:.0f} frames/s, e2e {b['e2e']['value']:.0f} frames/s):", "",
         "| stage | us/frame (CUDA events) | share live | share ncu |", "|---|---|---|---|"]
 for k, v in st.items():
     out.append(f"| {k} | {v:.2f} | {v / s:.3f} | {share_ncu[k]:.3f} |")
 r = b['roofline']
-out += ["", f"`k_fast_score`: {r['us_per_launch']:.1f} us per 64-frame launch -> {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of {r['peak']:.0f} GB/s ({r['peak_source']})."]
+out += ["", f"`k_fast_score`: {r['us_per_launch']:.1f} us per {b['config']['frames_per_gpu_per_step']}-frame launch -> {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of {r['peak']:.0f} GB/s ({r['peak_source']})."]
 open(os.path.join(P, f"{tag}_launches_summary.md"), "w").write("\n".join(out) + "\n")
 
 raw = subprocess.run(["ncu", "-i", stages_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
