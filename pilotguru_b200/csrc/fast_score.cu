@@ -114,9 +114,9 @@ __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
 
 // dynamic shared memory layout (bytes):
 //   [0, kInStage)               input tile, kF2InRows x kF2InWords u32
-//   [kInStage, +16384)          score tile 64 x 256 u8 (8 bands of 2 KB, each the source of one TMA store)
-//   [.., +8 warps * 384 * 4)    per-warp candidate queues: one-hot flag bit of the candidate in its register
-//   [.., +8 warps * 384)        ... and the producer's part of the candidate position
+//   [kInStage, +kF2W * kF2H)    score tile 32 x 256 u8 (one 2 KB band per warp, each the source of one TMA store)
+//   [.., +warps * 384 * 4)      per-warp candidate queues: one-hot flag bit of the candidate in its register
+//   [.., +warps * 384)          ... and the producer's part of the candidate position
 //   [.., +16)                   the mbarrier
 constexpr int kFsInStage = (kF2InBytes + 127) / 128 * 128;
 constexpr int kFsQueueCap = 384;
