@@ -169,3 +169,31 @@ def test_frame_feed_matches_oracle_and_feeds_the_extractor(golden_dir):
     ok, od = O.OrbOracle(300, 1.2, 8, 20, 7).extract(O.to_gray(rgb, formula=0))
     _assert_same(gk, gd, ok, od)
     ex.close()
+
+
+def test_resident_batch_chunked_over_streams_matches_single_pass(monkeypatch):
+    """With PGB_RES_CHUNK set, device-resident batches of >= 2 chunks are cut into chunks that alternate over the handle's
+    three compute streams (off by default: it measured slower).  Same keypoints and descriptors as the single-pass
+    schedule, call after call, including a ragged last chunk."""
+    import torch
+    from pilotguru_b200.orb import ORBextractor
+    n, w, h = 23, 640, 480
+    dev = torch.from_numpy(np.stack([synth.frame(t, w=w, h=h) for t in range(n)])).cuda()
+    outs = []
+    for chunk in ("0", "4", "5"):
+        monkeypatch.setenv("PGB_RES_CHUNK", chunk)
+        ex = _mk(500, w, h, batch=n)
+        cap = ex.cap
+        for rep in range(2):
+            kps = torch.zeros((n, cap, 7), dtype=torch.float32, device="cuda"); desc = torch.zeros((n, cap, 32), dtype=torch.uint8, device="cuda")
+            counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+            ex.extract_ptr(dev.data_ptr(), ORBextractor.IN_DEVICE | ORBextractor.OUT_DEVICE, n, w, h, w, w * h, kps.data_ptr(),
+                           desc.data_ptr(), counts.data_ptr(), cap)
+            ex.check()
+            outs.append((kps.cpu().numpy().view(np.uint32), desc.cpu().numpy(), counts.cpu().numpy()))
+        ex.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[2], outs[0][2]) and (outs[0][2] > 300).all()
+        for t in range(n):
+            c = outs[0][2][t]
+            assert np.array_equal(o[0][t, :c], outs[0][0][t, :c]) and np.array_equal(o[1][t, :c], outs[0][1][t, :c])
