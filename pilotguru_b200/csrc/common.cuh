@@ -68,6 +68,39 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
+// Per-call scratch for the entry points that have no handle to keep buffers in: memory from the device's stream-ordered
+// pool (cudaMallocAsync / cudaFreeAsync on the call's stream).  The pool keeps what it is given back (release threshold
+// raised once per device), so steady-state calls do not reach the driver's allocator -- ten cudaMalloc/cudaFree pairs
+// per call cost more than the kernels they serve (pgb_pose_optimization: 9.4 -> 5.0 ms per 256-frame batch).
+// Usage: `TempScope scope(device, stream);` first, then TempBuf<T> objects with DevBuf's interface.
+int keep_pool_memory(int device);
+struct TempScope {
+  static cudaStream_t& current() { static thread_local cudaStream_t s = nullptr; return s; }
+  cudaStream_t prev;
+  int rc;
+  TempScope(int device, cudaStream_t s) : prev(current()), rc(keep_pool_memory(device)) { current() = s; }
+  ~TempScope() { current() = prev; }
+};
+template <typename T>
+struct TempBuf {
+  T* p = nullptr;
+  cudaStream_t s = nullptr;
+  int alloc(size_t count) {
+    release();
+    s = TempScope::current();
+    PGB_CUDA(cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), s));
+    return PGB_OK;
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+  }
+  ~TempBuf() { release(); }
+  TempBuf() {}
+  TempBuf(const TempBuf&) = delete;
+  TempBuf& operator=(const TempBuf&) = delete;
+};
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace pgb

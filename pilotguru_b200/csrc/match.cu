@@ -1069,8 +1069,8 @@ int pgb_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* 
 namespace {
 
 // host->device staging of one input array (or pass-through when the caller's buffers are device-resident)
-template <typename T>
-int stage_in(DevBuf<T>& d, const T*& ptr, size_t n, bool is_device, cudaStream_t s) {
+template <typename B, typename T>
+int stage_in(B& d, const T*& ptr, size_t n, bool is_device, cudaStream_t s) {
   if (is_device || !ptr) return PGB_OK;
   if (d.alloc(n)) return PGB_ERR_CUDA;
   PGB_CUDA(cudaMemcpyAsync(d.p, ptr, n * sizeof(T), cudaMemcpyHostToDevice, s));
@@ -1079,8 +1079,8 @@ int stage_in(DevBuf<T>& d, const T*& ptr, size_t n, bool is_device, cudaStream_t
 }
 
 int run_windowed(pgb_matcher* m, WinArgs& A, int nProb) {
-  DevBuf<uint32_t> rows;
-  DevBuf<int> cnt, err;
+  TempBuf<uint32_t> rows;
+  TempBuf<int> cnt, err;
   const size_t n = (size_t)nProb * A.cap;
   if (rows.alloc(n * kWinK) || cnt.alloc(n) || err.alloc(1)) return PGB_ERR_CUDA;
   PGB_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), m->stream));
@@ -1113,10 +1113,12 @@ int pgb_match_for_initialization(pgb_matcher* m, int n_pairs, int cap, const pgb
     return fail(PGB_ERR_INVALID, "pgb_match_for_initialization: null buffer");
   PGB_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
+  TempScope scope(m->device, s);
+  if (scope.rc) return PGB_ERR_CUDA;
   const size_t n = (size_t)n_pairs * cap;
   // the kernel wants the F1 keypoints as separate level / angle arrays
   std::vector<pgb_keypoint> hk1;
-  DevBuf<pgb_keypoint> dk1tmp;
+  TempBuf<pgb_keypoint> dk1tmp;
   const pgb_keypoint* k1host = kps1;
   if (is_device) {
     hk1.resize(n);
@@ -1127,10 +1129,10 @@ int pgb_match_for_initialization(pgb_matcher* m, int n_pairs, int cap, const pgb
   std::vector<int> lvl(n);
   std::vector<float> ang(n);
   for (size_t i = 0; i < n; i++) { lvl[i] = k1host[i].octave; ang[i] = k1host[i].angle; }
-  DevBuf<int> dLvl, dN1, dN2, dM12, dNm;
-  DevBuf<float> dAng, dUV, dUVOut;
-  DevBuf<pgb_keypoint> dK2;
-  DevBuf<uint8_t> dD1, dD2;
+  TempBuf<int> dLvl, dN1, dN2, dM12, dNm;
+  TempBuf<float> dAng, dUV, dUVOut;
+  TempBuf<pgb_keypoint> dK2;
+  TempBuf<uint8_t> dD1, dD2;
   if (dLvl.alloc(n) || dAng.alloc(n) || dUVOut.alloc(2 * n)) return PGB_ERR_CUDA;
   PGB_CUDA(cudaMemcpyAsync(dLvl.p, lvl.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
   PGB_CUDA(cudaMemcpyAsync(dAng.p, ang.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -1176,11 +1178,13 @@ int pgb_match_map_points(pgb_matcher* m, int n_frames, int cap, const pgb_keypoi
     return fail(PGB_ERR_INVALID, "pgb_match_map_points: null buffer");
   PGB_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
+  TempScope scope(m->device, s);
+  if (scope.rc) return PGB_ERR_CUDA;
   const size_t n = (size_t)n_frames * cap;
-  DevBuf<pgb_keypoint> dK;
-  DevBuf<uint8_t> dD, dHas, dQD, dView, dObs;
-  DevBuf<float> dUV, dCos;
-  DevBuf<int> dN, dLvl, dQN, dMatch, dNm;
+  TempBuf<pgb_keypoint> dK;
+  TempBuf<uint8_t> dD, dHas, dQD, dView, dObs;
+  TempBuf<float> dUV, dCos;
+  TempBuf<int> dN, dLvl, dQN, dMatch, dNm;
   int rc = stage_in(dK, kps, n, is_device, s) | stage_in(dD, desc, n * 32, is_device, s) | stage_in(dN, counts, n_frames, is_device, s) |
            stage_in(dHas, has_map_point, n, is_device, s) | stage_in(dUV, proj_xy, 2 * n, is_device, s) |
            stage_in(dLvl, track_level, n, is_device, s) | stage_in(dCos, view_cos, n, is_device, s) |
@@ -1227,11 +1231,13 @@ int pgb_match_by_bow(pgb_matcher* m, int n_pairs, int cap, const uint8_t* kf_des
     return fail(PGB_ERR_INVALID, "pgb_match_by_bow: null buffer");
   PGB_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
+  TempScope scope(m->device, s);
+  if (scope.rc) return PGB_ERR_CUDA;
   const size_t n = (size_t)n_pairs * cap;
-  DevBuf<uint8_t> dKD, dKH, dFD;
-  DevBuf<float> dKA, dFA;
-  DevBuf<int> dKO, dKS, dFN, dFO, dFS, dMatch, dNm, dErr;
-  DevBuf<uint32_t> dKN, dKI, dFNode, dFI;
+  TempBuf<uint8_t> dKD, dKH, dFD;
+  TempBuf<float> dKA, dFA;
+  TempBuf<int> dKO, dKS, dFN, dFO, dFS, dMatch, dNm, dErr;
+  TempBuf<uint32_t> dKN, dKI, dFNode, dFI;
   int rc = stage_in(dKD, kf_desc, n * 32, is_device, s) | stage_in(dKA, kf_angle, n, is_device, s) |
            stage_in(dKH, kf_has_map_point, n, is_device, s) | stage_in(dKO, kf_node_off, (size_t)n_pairs + 1, is_device, s) |
            stage_in(dKN, kf_node_id, kf_nodes_total, is_device, s) | stage_in(dKS, kf_feat_start, (size_t)kf_nodes_total + 1, is_device, s) |
@@ -1278,8 +1284,10 @@ int pgb_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int
   cudaStream_t s = (cudaStream_t)stream;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || use_device(dev)) return PGB_ERR_CUDA;
-  DevBuf<uint8_t> dD;
-  DevBuf<int> dO, dB, dE;
+  TempScope scope(dev, s);
+  if (scope.rc) return PGB_ERR_CUDA;
+  TempBuf<uint8_t> dD;
+  TempBuf<int> dO, dB, dE;
   if (dE.alloc(1)) return PGB_ERR_CUDA;
   PGB_CUDA(cudaMemsetAsync(dE.p, 0, sizeof(int), s));
   const uint8_t* pd = desc;

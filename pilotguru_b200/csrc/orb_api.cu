@@ -28,6 +28,17 @@ int use_device(int device) {
   return PGB_OK;
 }
 
+int keep_pool_memory(int device) {
+  static std::atomic<unsigned> done{0};
+  if (device >= 0 && device < 32 && (done.load() >> device & 1u)) return PGB_OK;
+  cudaMemPool_t pool;
+  PGB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long keep = ~0ull;
+  PGB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  if (device >= 0 && device < 32) done.fetch_or(1u << device);
+  return PGB_OK;
+}
+
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 
 }  // namespace pgb

@@ -423,39 +423,10 @@ __global__ void __launch_bounds__(kPoThreads) k_pose_optimization(PoseArgs A) {
   }
 }
 
-// Per-call scratch from the device's stream-ordered pool (cudaMallocAsync): this entry point has no handle to keep
-// buffers in, and ten cudaMalloc/cudaFree pairs per call cost more than the kernel.  The pool keeps what it is given back
-// (release threshold raised once per device), so steady-state calls allocate without touching the driver's allocator.
 template <typename T>
-struct PoolBuf {
-  T* p = nullptr;
-  cudaStream_t s = nullptr;
-  int alloc(size_t count, cudaStream_t stream) {
-    s = stream;
-    PGB_CUDA(cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), stream));
-    return PGB_OK;
-  }
-  ~PoolBuf() { if (p) cudaFreeAsync(p, s); }
-  PoolBuf() {}
-  PoolBuf(const PoolBuf&) = delete;
-  PoolBuf& operator=(const PoolBuf&) = delete;
-};
-
-int keep_pool_memory(int device) {
-  static std::atomic<unsigned> done{0};
-  if (device < 32 && (done.load() >> device & 1u)) return PGB_OK;
-  cudaMemPool_t pool;
-  PGB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  unsigned long long keep = ~0ull;
-  PGB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  if (device < 32) done.fetch_or(1u << device);
-  return PGB_OK;
-}
-
-template <typename T>
-int stage_pose_in(PoolBuf<T>& d, const T*& ptr, size_t n, bool is_device, cudaStream_t s) {
+int stage_pose_in(TempBuf<T>& d, const T*& ptr, size_t n, bool is_device, cudaStream_t s) {
   if (is_device) return PGB_OK;
-  if (d.alloc(n, s)) return PGB_ERR_CUDA;
+  if (d.alloc(n)) return PGB_ERR_CUDA;
   PGB_CUDA(cudaMemcpyAsync(d.p, ptr, n * sizeof(T), cudaMemcpyHostToDevice, s));
   ptr = d.p;
   return PGB_OK;
@@ -482,20 +453,21 @@ extern "C" int pgb_pose_optimization(int device, int n_frames, int cap, const fl
   if (use_device(device)) return PGB_ERR_CUDA;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)n_frames * cap;
-  if (keep_pool_memory(device)) return PGB_ERR_CUDA;
-  PoolBuf<float> dT, dXY, dX, dTo;
-  PoolBuf<int> dOct, dCnt, dNi, dErr;
-  PoolBuf<uint8_t> dHas, dOut;
+  TempScope scope(device, s);
+  if (scope.rc) return PGB_ERR_CUDA;
+  TempBuf<float> dT, dXY, dX, dTo;
+  TempBuf<int> dOct, dCnt, dNi, dErr;
+  TempBuf<uint8_t> dHas, dOut;
   int rc = stage_pose_in(dT, Tcw_in, (size_t)n_frames * 16, is_device, s) | stage_pose_in(dXY, kp_xy, n * 2, is_device, s) |
            stage_pose_in(dOct, kp_octave, n, is_device, s) | stage_pose_in(dX, mp_xyz, n * 3, is_device, s) |
            stage_pose_in(dHas, has_map_point, n, is_device, s) | stage_pose_in(dCnt, counts, n_frames, is_device, s);
-  if (rc || dErr.alloc(1, s)) return PGB_ERR_CUDA;
+  if (rc || dErr.alloc(1)) return PGB_ERR_CUDA;
   PGB_CUDA(cudaMemsetAsync(dErr.p, 0, sizeof(int), s));
   float* to = Tcw_out;
   uint8_t* out = outlier;
   int* ni = n_inliers;
   if (!is_device) {
-    if (dTo.alloc((size_t)n_frames * 16, s) || dOut.alloc(n, s) || dNi.alloc(n_frames, s)) return PGB_ERR_CUDA;
+    if (dTo.alloc((size_t)n_frames * 16) || dOut.alloc(n) || dNi.alloc(n_frames)) return PGB_ERR_CUDA;
     to = dTo.p; out = dOut.p; ni = dNi.p;
   }
   PoseArgs A;
