@@ -119,13 +119,22 @@ __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) {
 //   [.., +warps * 384)          ... and the producer's part of the candidate position
 //   [.., +16)                   the mbarrier
 constexpr int kFsInStage = (kF2InBytes + 127) / 128 * 128;
-constexpr int kFsQueueCap = 384;
+// Queue entry formats (A/B build macro PGB_FS_Q64): 0 = u32 one-hot flag + u8 code in two arrays (5 B/entry, cap 384);
+// 1 = one 8-byte {flag, code} entry written with a single STS.64 and read with a single LDS.64 (cap 224, same bytes).
+// Measured: 1 shortens the divergent append loops from 11 to 8 instructions per flag (they are 15 % of the kernel's
+// warp-instructions at 7 of 32 active lanes, profiles/r01e_fast_score_sass_regions.md) but runs 4.77 vs 4.60 us/frame:
+// bands above 224 candidates need a second pass and the 8-byte stores of divergent lanes conflict more.  Default 0.
+#ifndef PGB_FS_Q64
+#define PGB_FS_Q64 0
+#endif
+constexpr int kFsQueueCap = PGB_FS_Q64 ? 224 : 384;
+constexpr int kFsQueueEntryBytes = PGB_FS_Q64 ? 8 : 5;
 constexpr int kFsWarps = kF2Threads / 32;
 #ifndef PGB_FS_OCC
 #define PGB_FS_OCC 8
 #endif
 constexpr int kFsOcc = PGB_FS_OCC;  // resident CTAs per SM the kernel is compiled for
-constexpr int kFsSmem = kFsInStage + kF2W * kF2H + kFsWarps * kFsQueueCap * 5 + 16;
+constexpr int kFsSmem = kFsInStage + kF2W * kF2H + kFsWarps * kFsQueueCap * kFsQueueEntryBytes + 16;
 
 template <int kOcc>
 __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_constant__ OrbGeo g,
@@ -135,8 +144,12 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_co
   const uint32_t* sIn = reinterpret_cast<const uint32_t*>(smem);
   uint8_t* sScore = smem + kFsInStage;
   uint32_t* sQueue = reinterpret_cast<uint32_t*>(sScore + kF2W * kF2H);
+#if PGB_FS_Q64
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sQueue + 2 * kFsWarps * kFsQueueCap);
+#else
   uint8_t* sQCode = reinterpret_cast<uint8_t*>(sQueue + kFsWarps * kFsQueueCap);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sQCode + kFsWarps * kFsQueueCap);
+#endif
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y + frame0;
@@ -237,8 +250,12 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_co
     hi = __byte_perm(hi, y, sel2);
   }
   const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn);
+#if PGB_FS_Q64
+  uint2* q = reinterpret_cast<uint2*>(sQueue) + warp * kFsQueueCap;   // {one-hot flag, code}
+#else
   uint32_t* q = sQueue + warp * kFsQueueCap;                 // one-hot flag of the candidate inside its register
   uint8_t* qc = sQCode + warp * kFsQueueCap;                 // (lane & 28) * 8 + (lane & 3) + 4 * half
+#endif
   const int cnt = __popc(lo) + __popc(hi);
   int incl = cnt;
 #pragma unroll
@@ -247,6 +264,45 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_co
     if (lane >= d) incl += t;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
+#if PGB_FS_Q64
+  // Normally the band's candidates fit the queue in one pass; otherwise one pass per half band (4 rows) if both halves
+  // fit, else (noise images) one pass per (row, word): at most 4 flags per lane = 128 per pass.
+  int nParts = 1;
+  if (total > kFsQueueCap) {
+    const int nLo = __reduce_add_sync(0xffffffffu, __popc(lo));
+    nParts = (nLo <= kFsQueueCap && total - nLo <= kFsQueueCap) ? 2 : 16;
+  }
+  for (int part = 0; part < nParts; part++) {
+    uint32_t mlo = lo, mhi = hi;
+    int pos = incl - cnt, T = total;
+    if (nParts > 1) {
+      const uint32_t rm = nParts == 2 ? 0xffffffffu : (0x80808080u >> (part & 7));
+      const bool first = nParts == 2 ? part == 0 : part < 8;
+      mlo = first ? (lo & rm) : 0u;
+      mhi = first ? 0u : (hi & rm);
+      const int c2 = __popc(mlo) + __popc(mhi);
+      int in2 = c2;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, in2, d);
+        if (lane >= d) in2 += t;
+      }
+      T = __shfl_sync(0xffffffffu, in2, 31);
+      pos = in2 - c2;
+    }
+    const uint32_t pcode = (uint32_t)((lane & 28) * 8 + (lane & 3));  // x of (source-lane quad, column); bit 2 = half
+    uint2* qp = q + pos;
+    while (mlo) {
+      const uint32_t low = mlo & (0u - mlo);
+      mlo ^= low;
+      *qp++ = make_uint2(low, pcode);
+    }
+    while (mhi) {
+      const uint32_t low = mhi & (0u - mhi);
+      mhi ^= low;
+      *qp++ = make_uint2(low, pcode | 4u);
+    }
+#else
   // Normally the band's candidates fit the queue in one pass; otherwise (noise images) one pass per row (<= 256).
   const int nParts = total <= kFsQueueCap ? 1 : 8;
   for (int part = 0; part < nParts; part++) {
@@ -281,9 +337,15 @@ __global__ void __launch_bounds__(kF2Threads, kOcc) k_fast_score(const __grid_co
       *qp++ = low;
       *qcp++ = (uint8_t)(pcode | 4);
     }
+#endif
     __syncwarp();
     for (int i = lane; i < T; i += 32) {
+#if PGB_FS_Q64
+      const uint2 e = q[i];
+      const uint32_t low = e.x, c = e.y;
+#else
       const uint32_t low = q[i], c = qc[i];
+#endif
       const uint32_t bit = 31u - (uint32_t)__clz(low), u = bit ^ 7u;  // u & 7 = 2 * (row in half) + word
       const int row = (int)(c & 4u) + (int)((u >> 1) & 3u);
       const int x = (int)((c & 0xE3u) + (bit & 0x18u) + ((u & 1u) << 2));  // (lane quad)*32 + (source lane)*8 + word*4 + byte
