@@ -63,3 +63,22 @@ def test_edge_cases():
     S2 = dict(S); S2["T0"] = T1
     n2, T2, o2, _ = _run(S2)
     assert np.abs(T2 - T1).max() < 1e-5 and abs(n2 - n1) <= 1
+
+
+def test_degenerate_inputs_terminate():
+    """Points behind the camera, a rank-deficient scene, exact data and z = 0: every loop of the restated LM is bounded, so
+    the call returns; NaN chi2 compares false against the threshold exactly like the reference's `if(chi2>chi2Mono[it])`."""
+    S = U.scene(21, n=300, outlier_frac=0.1)
+    X = S["Xw"].copy(); X[:20] *= -1
+    n_in, T, out, _ = O.pose_optimization(S["T0"], S["xy"], S["octave"], X, S["has"], U.INV_SIGMA2, U.FX, U.FY, U.CX, U.CY)
+    assert np.isfinite(T).all() and out[:20][S["has"][:20] > 0].mean() > 0.8 and n_in > 100
+    S = U.scene(22, n=200, outlier_frac=0.0, noise=0.0, perturb=(0.0, 0.0))      # exact data, start at the truth
+    n_in, T, out, _ = _run(S)
+    assert n_in == int(S["has"].sum()) and np.abs(T - S["T0"]).max() < 1e-6
+    S = U.scene(23, n=50, outlier_frac=0.0)                                       # all correspondences identical
+    X = np.tile(S["Xw"][:1], (50, 1)); xy = np.tile(S["xy"][:1], (50, 1))
+    n_in, T, out, _ = O.pose_optimization(S["T0"], xy, S["octave"], X, S["has"], U.INV_SIGMA2, U.FX, U.FY, U.CX, U.CY)
+    assert np.isfinite(T).all()
+    n_in, T, out, _ = O.pose_optimization(np.eye(4, dtype=np.float32), S["xy"], S["octave"], np.zeros_like(S["Xw"]), S["has"],
+                                          U.INV_SIGMA2, U.FX, U.FY, U.CX, U.CY)   # z = 0: NaN errors
+    assert n_in == int(S["has"].sum()) and (out == 0).all()
