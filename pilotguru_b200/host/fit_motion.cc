@@ -82,9 +82,16 @@ int main(int argc, char** argv) {
   PGB_CHECK(num_gpus >= 1);
 
   // Read input JSONs (fit_motion.cc:315-324; only speed_m_s and time_usec of a location are used, :129-132).
-  const Table gps = pgbhost::ReadTable(locations_json, "locations", {"speed_m_s"}, "time_usec");
-  const Table rot = pgbhost::ReadTable(rotations_json, "rotations", {"x", "y", "z"}, "time_usec");
-  const Table acc = pgbhost::ReadTable(accelerations_json, "accelerations", {"x", "y", "z"}, "time_usec");
+  // The two IMU files of an hour-long recording are ~200 MB each: parse them side by side (a failed CHECK in a reader
+  // thread aborts the process like anywhere else).
+  Table gps, rot, acc;
+  {
+    std::thread tr([&] { rot = pgbhost::ReadTable(rotations_json, "rotations", {"x", "y", "z"}, "time_usec"); });
+    std::thread ta([&] { acc = pgbhost::ReadTable(accelerations_json, "accelerations", {"x", "y", "z"}, "time_usec"); });
+    gps = pgbhost::ReadTable(locations_json, "locations", {"speed_m_s"}, "time_usec");
+    tr.join();
+    ta.join();
+  }
   const std::vector<double> gyro_xyz = Interleave3(rot), acc_xyz = Interleave3(acc);
   const int dev0 = (int)device;
 
@@ -96,10 +103,14 @@ int main(int argc, char** argv) {
   if (flags.verbose)
     fprintf(stderr, "I principal rotation axis (%lld intervals): %.9g %.9g %.9g\n", (long long)n_iv, vertical[0], vertical[1], vertical[2]);
 
+  std::thread steering_writer;  // formatting 1.8 M records takes longer than the whole velocity fit: do it on the side
+  std::vector<double> steering;
   if (!steering_out_json.empty()) {  // ComputeAndSaveSteeringAngles, fit_motion.cc:138-154
-    std::vector<double> steering(rot.rows());
+    steering.resize(rot.rows());
     PGB_CALL(pgb_angular_velocities_around_axis(dev0, gyro_xyz.data(), rot.rows(), vertical, steering.data()));
-    pgbhost::JsonWriteTimestampedRealData(rot.integer, steering, steering_out_json, "steering", "angular_velocity");
+    steering_writer = std::thread([&] {
+      pgbhost::JsonWriteTimestampedRealData(rot.integer, steering, steering_out_json, "steering", "angular_velocity");
+    });
   }
 
   if (!velocities_out_json.empty() || !forward_axis_out_json.empty()) {
@@ -187,5 +198,6 @@ int main(int argc, char** argv) {
       fclose(out);
     }
   }
+  if (steering_writer.joinable()) steering_writer.join();
   return EXIT_SUCCESS;
 }

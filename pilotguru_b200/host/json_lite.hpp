@@ -13,6 +13,9 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <charconv>
+#include <string_view>
+#include <algorithm>
 
 #include "check.hpp"
 
@@ -22,11 +25,20 @@ class JsonReader {
  public:
   explicit JsonReader(const std::string& text) : s_(text), p_(s_.data()), end_(s_.data() + s_.size()) {}
   static std::string Slurp(const std::string& path) {
-    std::ifstream f(path, std::ios::binary);
-    PGB_CHECK(f.good()) << "cannot open JSON file " << path;
-    std::stringstream ss;
-    ss << f.rdbuf();
-    return ss.str();
+    FILE* f = fopen(path.c_str(), "rb");
+    PGB_CHECK(f != nullptr) << "cannot open JSON file " << path;
+    std::string out;
+    if (fseek(f, 0, SEEK_END) == 0) {
+      const long n = ftell(f);
+      if (n > 0) out.resize((size_t)n);
+      rewind(f);
+    }
+    size_t got = out.empty() ? 0 : fread(&out[0], 1, out.size(), f);
+    if (got < out.size()) out.resize(got);
+    char buf[1 << 16];                                  // whatever follows (or everything, for an unseekable stream)
+    while ((got = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, got);
+    fclose(f);
+    return out;
   }
   void SkipWs() { while (p_ < end_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\t' || *p_ == '\r')) ++p_; }
   char Peek() { SkipWs(); PGB_CHECK(p_ < end_) << "unexpected end of JSON"; return *p_; }
@@ -56,6 +68,17 @@ class JsonReader {
     ++p_;
     return out;
   }
+  // An object key as a view into the text (the common case: no escapes); falls back to String() otherwise.
+  std::string_view Key(std::string* scratch) {
+    SkipWs();
+    PGB_CHECK(p_ < end_ && *p_ == '"') << "JSON parse error: expected '\"' at offset " << (p_ - s_.data());
+    const char* b = p_ + 1;
+    const char* q = b;
+    while (q < end_ && *q != '"' && *q != '\\') ++q;
+    if (q < end_ && *q == '"') { p_ = q + 1; return std::string_view(b, (size_t)(q - b)); }
+    *scratch = String();
+    return *scratch;
+  }
   // A number, kept exact when it is an integer literal.
   void Number(double* d, int64_t* i, bool* is_int) {
     SkipWs();
@@ -67,13 +90,19 @@ class JsonReader {
       ++p_;
     }
     PGB_CHECK(p_ > b) << "JSON parse error: number expected at offset " << (b - s_.data());
-    char buf[64];
-    const size_t n = std::min<size_t>(p_ - b, sizeof buf - 1);
-    memcpy(buf, b, n);
-    buf[n] = 0;
-    *d = strtod(buf, nullptr);
+    // std::from_chars: correctly rounded like strtod, no locale, no copy; it does not take a leading '+'
+    const char* nb = (*b == '+') ? b + 1 : b;
     *is_int = integral;
-    *i = integral ? strtoll(buf, nullptr, 10) : (int64_t)*d;
+    if (integral) {
+      const auto r = std::from_chars(nb, p_, *i);
+      if (r.ec == std::errc() && r.ptr == p_) { *d = (double)*i; return; }
+      *is_int = false;                                   // out of the int64 range: keep it as a double
+    }
+    const auto r = std::from_chars(nb, p_, *d);
+    PGB_CHECK(r.ec == std::errc() || r.ec == std::errc::result_out_of_range)
+        << "JSON parse error: malformed number at offset " << (b - s_.data());
+    if (r.ec == std::errc::result_out_of_range) *d = strtod(std::string(nb, p_).c_str(), nullptr);  // +-inf / denormal, like strtod
+    *i = (int64_t)*d;
   }
   double Double() { double d; int64_t i; bool b; Number(&d, &i, &b); return b ? (double)i : d; }
   int64_t Int() { double d; int64_t i; bool b; Number(&d, &i, &b); return i; }
@@ -140,14 +169,16 @@ inline Table ReadTable(const std::string& path, const std::string& table, const 
   PGB_CHECK(r.FindTopLevel(table)) << path << ": no \"" << table << "\" element";
   Table t;
   t.real.resize(real_fields.size());
+  std::string scratch;
+  std::vector<char> seen(real_fields.size() + 1, 0);
   r.Expect('[');
   if (!r.TryConsume(']')) {
     do {
       r.Expect('{');
-      std::vector<char> seen(real_fields.size() + 1, 0);
+      std::fill(seen.begin(), seen.end(), 0);
       if (!r.TryConsume('}')) {
         do {
-          const std::string k = r.String();
+          const std::string_view k = r.Key(&scratch);
           r.Expect(':');
           bool used = false;
           for (size_t f = 0; f < real_fields.size() && !used; f++)

@@ -136,3 +136,25 @@ def test_optical_trajectories_flags(host_bins):
     assert p.returncode == -6 and "Check failed: !vocabulary_file.empty()" in p.stderr
     p = run(host_bins, "optical_trajectories", "--vocabulary_file=v", "--camera_settings=/nonexistent.yml", "--in_video=video.mp4")
     assert p.returncode == -6 and "raw:<path>:<width>x<height>" in p.stderr
+
+
+def test_json_number_forms(host_bins, tmp_path):
+    """The reader's number path (std::from_chars): exponents, negative zero, integer literals for a real field, an int64
+    beyond 2^53 kept exact, a real literal for the integer field, odd whitespace."""
+    text = ('{ "locations" :\t[\n'
+            ' {"speed_m_s": 1E+2, "time_usec": 9007199254740993},\n'
+            ' {"time_usec":2,"speed_m_s":-0.0},\n'
+            ' {"speed_m_s": 3, "time_usec": 3},\n'
+            ' {"speed_m_s": 2.5e-3 , "time_usec": 1.5e3 , "extra": [1, {"a": null}, true, "s\\"q"]},\n'
+            ' {"speed_m_s": 0.1, "time_usec": -7}\n'
+            ']}')
+    fin, fout = tmp_path / "in.json", tmp_path / "out.json"
+    fin.write_text(text)
+    p = run(host_bins, "json_selftest", str(fin), "locations", "speed_m_s", str(fout), "v", "speed_m_s")
+    assert p.returncode == 0, p.stderr
+    out = json.loads(fout.read_text())["v"]
+    assert [e["time_usec"] for e in out] == [9007199254740993, 2, 3, 1500, -7]
+    vals = [e["speed_m_s"] for e in out]
+    assert vals == [100.0, 0.0, 3.0, 0.0025, 0.1] and np.signbit(vals[1])
+    fin.write_text('{"locations": [{"speed_m_s": abc, "time_usec": 1}]}')
+    assert run(host_bins, "json_selftest", str(fin), "locations", "speed_m_s", str(fout), "v", "s").returncode == -6
