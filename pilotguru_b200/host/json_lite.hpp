@@ -5,6 +5,7 @@
 // two-space indent, object keys in alphabetical order (nlohmann's default std::map), integers without a decimal
 // point.  Doubles are printed with 17 significant digits so that parsing the file returns the exact values.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -198,11 +199,22 @@ inline Table ReadTable(const std::string& path, const std::string& table, const 
   return t;
 }
 
+// "%.17g" (std::to_chars with chars_format::general and precision 17 is specified as exactly that), plus ".0" for
+// integral values the way nlohmann prints doubles.  Returns the number of characters written to buf (>= 40 bytes).
+inline size_t FormatDoubleTo(char* buf, double v) {
+  if (!std::isfinite(v)) return (size_t)snprintf(buf, 40, "%.17g", v);
+  char* e = std::to_chars(buf, buf + 32, v, std::chars_format::general, 17).ptr;
+  bool plain = true;
+  for (const char* c = buf; c < e; ++c)
+    if (*c == '.' || *c == 'e' || *c == 'E') { plain = false; break; }
+  if (plain) { *e++ = '.'; *e++ = '0'; }
+  *e = 0;
+  return (size_t)(e - buf);
+}
 inline std::string FormatDouble(double v) {
   char buf[40];
-  snprintf(buf, sizeof buf, "%.17g", v);
-  if (!strpbrk(buf, ".eEni")) strcat(buf, ".0");  // nlohmann prints integral doubles as "1.0"
-  return buf;
+  const size_t n = FormatDoubleTo(buf, v);
+  return std::string(buf, n);
 }
 
 // JsonWriteTimestampedRealData (json_converters.cc:184-202): {root: [{"time_usec": t, value_name: v}, ...]} with
@@ -219,15 +231,23 @@ inline void JsonWriteTimestampedRealData(const std::vector<int64_t>& times_usec,
     fprintf(f, "{\n  \"%s\": null\n}\n", root_element_name.c_str());  // out_json[root] = {} dumps as null
   } else {
     fprintf(f, "{\n  \"%s\": [\n", root_element_name.c_str());
+    std::string out;
+    out.reserve(1 << 20);
+    char num[40];
     for (size_t i = 0; i < values.size(); i++) {
-      const std::string v = FormatDouble(values[i]);
-      if (value_first)
-        fprintf(f, "    {\n      \"%s\": %s,\n      \"time_usec\": %lld\n    }%s\n", value_name.c_str(), v.c_str(),
-                (long long)times_usec[i], i + 1 < values.size() ? "," : "");
-      else
-        fprintf(f, "    {\n      \"time_usec\": %lld,\n      \"%s\": %s\n    }%s\n", (long long)times_usec[i],
-                value_name.c_str(), v.c_str(), i + 1 < values.size() ? "," : "");
+      const size_t nv = FormatDoubleTo(num, values[i]);
+      char tnum[24];
+      const size_t nt = (size_t)(std::to_chars(tnum, tnum + sizeof tnum, (long long)times_usec[i]).ptr - tnum);
+      out += "    {\n      \"";
+      if (value_first) {
+        out += value_name; out += "\": "; out.append(num, nv); out += ",\n      \"time_usec\": "; out.append(tnum, nt);
+      } else {
+        out += "time_usec\": "; out.append(tnum, nt); out += ",\n      \""; out += value_name; out += "\": "; out.append(num, nv);
+      }
+      out += i + 1 < values.size() ? "\n    },\n" : "\n    }\n";
+      if (out.size() > (1 << 20) - 256) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
     }
+    fwrite(out.data(), 1, out.size(), f);
     fprintf(f, "  ]\n}\n");
   }
   fclose(f);

@@ -158,3 +158,23 @@ def test_json_number_forms(host_bins, tmp_path):
     assert vals == [100.0, 0.0, 3.0, 0.0025, 0.1] and np.signbit(vals[1])
     fin.write_text('{"locations": [{"speed_m_s": abc, "time_usec": 1}]}')
     assert run(host_bins, "json_selftest", str(fin), "locations", "speed_m_s", str(fout), "v", "s").returncode == -6
+
+
+def test_json_writer_prints_percent_17g(host_bins, tmp_path):
+    """The writer's number text is exactly printf's %.17g (+ ".0" for integral values, like nlohmann's dump)."""
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([rng.normal(0, 1, 300) * 10.0 ** rng.integers(-300, 300, 300), [0.0, -0.0, 1.0, -3.0, 1e22, 1e-5, 123456.0,
+                           5e-324, 1.7976931348623157e308, 0.1, 1 / 3]])
+    ts = np.arange(len(vals), dtype=np.int64) - 5
+    fin, fout = tmp_path / "in.json", tmp_path / "out.json"
+    fin.write_text(json.dumps({"t": [{"v": float(v), "time_usec": int(t)} for v, t in zip(vals, ts)]}))
+    p = run(host_bins, "json_selftest", str(fin), "t", "v", str(fout), "root", "v")
+    assert p.returncode == 0, p.stderr
+    lines = fout.read_text().splitlines()
+    got = [l.split(": ", 1)[1].rstrip(",") for l in lines if l.strip().startswith('"v"')]
+    want = []
+    for v in vals:
+        s = "%.17g" % v
+        want.append(s if any(c in s for c in ".e") else s + ".0")
+    assert got == want
+    assert [int(l.split(": ", 1)[1].rstrip(",")) for l in lines if l.strip().startswith('"time_usec"')] == ts.tolist()
