@@ -44,3 +44,20 @@ def test_product_does_not_reference_oracle():
                 src = open(os.path.join(dp, f), errors="replace").read()
                 for needle in ("oracle/", "oracle_lib", "liboracle", "pgo_", "pgo.h"):
                     assert needle not in src, f"{f} references the test oracle ({needle})"
+
+
+def test_binding_arity_matches_header():
+    """Every ctypes signature lists exactly as many arguments as include/pgb200.h declares (a wrong count would not fail
+    at load time, it would corrupt the call)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "pgb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    seen = {}
+    for m in re.finditer(r"\b(pgb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        name, params = m.group(1), " ".join(m.group(2).split())
+        seen[name] = 0 if params in ("", "void") else params.count(",") + 1
+    assert set(seen) == set(_lib._SIGS)
+    wrong = {n: (len(_lib._SIGS[n][1]), seen[n]) for n in seen if len(_lib._SIGS[n][1]) != seen[n]}
+    assert not wrong, f"(bound, declared) argument counts differ: {wrong}"
