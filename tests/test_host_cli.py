@@ -178,3 +178,40 @@ def test_json_writer_prints_percent_17g(host_bins, tmp_path):
         want.append(s if any(c in s for c in ".e") else s + ".0")
     assert got == want
     assert [int(l.split(": ", 1)[1].rstrip(",")) for l in lines if l.strip().startswith('"time_usec"')] == ts.tolist()
+
+
+def test_json_reader_differential_fuzz(host_bins, tmp_path):
+    """Random documents (nested junk values, escapes in strings and keys, varying whitespace and separators) through
+    the C++ pull parser and back: same columns as Python's json gives."""
+    import random
+    rnd = random.Random(1234)
+
+    def junk(depth=0):
+        k = rnd.randrange(7 if depth < 3 else 4)
+        if k == 0: return rnd.uniform(-1e6, 1e6)
+        if k == 1: return rnd.randrange(-10**12, 10**12)
+        if k == 2: return rnd.choice([True, False, None])
+        if k == 3: return "".join(rnd.choice('ab"\\/ \t{}[],:é') for _ in range(rnd.randrange(6)))
+        if k == 4: return [junk(depth + 1) for _ in range(rnd.randrange(4))]
+        return {"".join(rnd.choice('xy"\\z') for _ in range(1 + rnd.randrange(4))): junk(depth + 1) for _ in range(rnd.randrange(4))}
+
+    for case in range(40):
+        n = rnd.randrange(1, 30)
+        rows = []
+        for i in range(n):
+            rec = {"junk%d" % j: junk() for j in range(rnd.randrange(3))}
+            rec["val"] = rnd.choice([rnd.uniform(-1, 1) * 10.0 ** rnd.randrange(-20, 20), float(rnd.randrange(-5, 5)), rnd.randrange(-1000, 1000)])
+            rec["time_usec"] = rnd.randrange(-10**15, 10**15)
+            items = list(rec.items()); rnd.shuffle(items)
+            rows.append(dict(items))
+        doc = {"before": junk(), "table": rows, "after": junk()}
+        items = list(doc.items()); rnd.shuffle(items)
+        text = json.dumps(dict(items), indent=rnd.choice([None, 0, 1, 3]), separators=rnd.choice([(",", ":"), (", ", ": "), (" ,\t", " :\n")]),
+                          ensure_ascii=rnd.choice([True, False]))
+        fin, fout = tmp_path / f"in{case}.json", tmp_path / f"out{case}.json"
+        fin.write_text(text, encoding="utf-8")
+        p = run(host_bins, "json_selftest", str(fin), "table", "val", str(fout), "r", "val")
+        assert p.returncode == 0, (case, p.stderr, text[:300])
+        out = json.loads(fout.read_text())["r"]
+        assert [e["time_usec"] for e in out] == [r["time_usec"] for r in rows], case
+        assert [e["val"] for e in out] == [float(r["val"]) for r in rows], case
