@@ -9,9 +9,14 @@
 //   src/fit_motion.cc                       ComputeAndSaveForwardVelocitiesFromImu :156-293
 //   src/calibration/rotation.cc             GetPrincipalRotationAxes :16-57, GetAngularVelocitiesAroundAxisDirect :103-119
 // Eigen (un-vendored) is restated from its standard formulas; libm sin/cos/sqrt/erf are used
-// as the reference does.  PARITY UNPINNED against the reference binary (it cannot be built here and ships no
-// fixtures for this path); pinned instead by the doc-comment example of align_time_series.hpp:17-26, by an
-// independent numpy restatement in tests/test_oracle_calib.py and by finite-difference / invariance properties.
+// as the reference does.  PINNED against the reference's OWN SOURCES where they compile: align_time_series.cc,
+// geometry.cc, velocity.cc:1-256, smoothing.cc:48-end and the vendored LBFGS++ are built where they lie into
+// oracle/_ref (make _ref; Eigen / glog stand-ins in ref_shims/) and tests/test_oracle_reference_pin.py runs this file
+// against them: indices and interval tables equal, loss equal to the bit, gradient within 1 ulp, SmoothTimeSeries
+// bit-exact, L-BFGS iterates equal to 1e-14 through 20 iterations.  PARITY UNPINNED against a reference BINARY (no
+// Eigen in this image, no fixtures): the real Eigen's association of reductions is version dependent.  Further pins:
+// the doc-comment example of align_time_series.hpp:17-26, an independent numpy restatement in
+// tests/test_oracle_calib.py and finite-difference / invariance properties.
 //
 // The "_core" entry points evaluate the SAME quantities through include/pgb200_imu_core.h (the arithmetic
 // contract the CUDA kernels are compiled from) on the host, so GPU results can be compared bit for bit; the

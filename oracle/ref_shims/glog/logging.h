@@ -33,3 +33,11 @@ template <typename T> T&& NotNull(const char* file, int line, const char* what, 
 #define CHECK_GT(a, b) PGO_CHECK_OP(a, >, b)
 #define CHECK_GE(a, b) PGO_CHECK_OP(a, >=, b)
 #define CHECK_NOTNULL(p) ::pgo_glog_shim::NotNull(__FILE__, __LINE__, "'" #p "' Must be non NULL", (p))
+
+// LOG(severity) << ...: swallowed (velocity.cc logs its input, gradient and loss at INFO on every evaluation).
+namespace pgo_glog_shim {
+struct NullStream {
+  template <typename T> NullStream& operator<<(const T&) { return *this; }
+};
+}  // namespace pgo_glog_shim
+#define LOG(severity) ::pgo_glog_shim::NullStream()
