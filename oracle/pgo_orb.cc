@@ -14,7 +14,14 @@
 //
 // Documented deviation: DistributeOctTree sorts (size, node pointer) pairs, i.e. breaks size ties by heap
 // address (:684).  The oracle breaks ties by node creation sequence number (ascending sort, processed from the
-// back => later-created first), SURVEY.md App. A.3.
+// back => later-created first), SURVEY.md App. A.3.  That is what the reference itself does whenever its allocator
+// hands out increasing addresses.
+//
+// PINNED against the reference's own source: `make -C oracle _ref` compiles thirdparty/orb-slam2/src/ORBextractor.cc
+// where it lies (OpenCV stand-in in ref_shims/: the file's own logic runs from source, the OpenCV primitives it calls
+// are this file's cv2-pinned restatements; monotonic allocator in ref_bump_alloc.cc), and
+// tests/test_oracle_reference_pin.py holds this file's pyramids, all 7 keypoint fields and all descriptors identical
+// to it on synthetic, noise, odd-sized and low-texture images.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -187,3 +187,81 @@ def test_oracle_lbfgs_window_fit_equals_the_reference_sources(ref):
             else:
                 assert np.max(np.abs(ox - x)) <= tol * np.max(np.abs(x)) and abs(ofx - fx.value) <= tol * abs(fx.value), (w0, iters)
         rc.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The extractor: the reference's own thirdparty/orb-slam2/src/ORBextractor.cc, compiled against the OpenCV stand-in
+# (oracle/ref_shims/pgo_opencv_shim.h).  Everything that file does itself -- pyramid orchestration through cv::Mat views,
+# the 30-px cell grid with the iniThFAST -> minThFAST retry, ExtractorNode::DivideNode / DistributeOctTree, IC_Angle,
+# computeOrbDescriptor, scale tables, per-level quotas, output order, keypoint rescale -- runs from the reference's source;
+# the OpenCV primitives it calls are the cv2-pinned restatements.
+KPF = ["x", "y", "size", "angle", "response", "octave", "class_id"]
+
+
+class RefOrb:
+    def __init__(self, l, nfeatures, scale, nlevels, ini_th, min_th):
+        self.l = l
+        l.pgr_orb_create.restype = C.c_void_p
+        l.pgr_orb_extract.restype = C.c_int
+        self.nlevels = nlevels
+        self.h = C.c_void_p(l.pgr_orb_create(nfeatures, C.c_float(scale), nlevels, ini_th, min_th))
+
+    def extract(self, img, cap=4096):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        kps = np.zeros((cap, 7), np.float32); desc = np.zeros((cap, 32), np.uint8)
+        n = self.l.pgr_orb_extract(self.h, img.ctypes.data_as(C.c_void_p), w, h, kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap)
+        assert 0 <= n <= cap
+        return kps[:n], desc[:n]
+
+    def level(self, l):
+        w, h = C.c_int(), C.c_int()
+        self.l.pgr_orb_level(self.h, l, None, C.byref(w), C.byref(h))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.l.pgr_orb_level(self.h, l, out.ctypes.data_as(C.c_void_p), C.byref(w), C.byref(h))
+        return out
+
+    def tables(self):
+        t = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        self.l.pgr_orb_tables(self.h, *[x.ctypes.data_as(C.c_void_p) for x in t])
+        return t
+
+    def close(self):
+        self.l.pgr_orb_destroy(self.h)
+
+
+def _compare(ref_kd, orc_kd):
+    (rk, rd), (ok, od) = ref_kd, orc_kd
+    assert len(rk) == len(ok), (len(rk), len(ok))
+    for i, f in enumerate(KPF):
+        a = rk[:, i]; b = ok[f].astype(np.float32)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f
+    assert np.array_equal(rd, od)
+
+
+@pytest.mark.parametrize("case", ["synth640", "synth1080", "noise", "odd", "lowtexture"])
+def test_oracle_extractor_equals_the_reference_source(ref, case):
+    rng = np.random.default_rng(9)
+    if case == "synth640":
+        imgs, nf = [synth.frame(t, w=640, h=480) for t in range(3)], 500
+    elif case == "synth1080":
+        imgs, nf = [synth.frame(7)], 1000
+    elif case == "noise":
+        imgs, nf = [rng.integers(0, 256, (480, 640), dtype=np.uint8)], 1000
+    elif case == "odd":
+        imgs, nf = [synth.frame(3, w=701, h=403)], 777
+    else:
+        imgs, nf = [np.clip(synth.frame(2, w=640, h=480).astype(np.int32) // 8 + 100, 0, 255).astype(np.uint8)], 500
+    rx = RefOrb(ref, nf, 1.2, 8, 20, 7)
+    orc = O.OrbOracle(nf, 1.2, 8, 20, 7)
+    t = orc.tables()
+    for a, b in zip(rx.tables(), (t["scale"], t["inv_scale"], t["sigma2"], t["inv_sigma2"])):
+        assert np.array_equal(a, b[:8])
+    for img in imgs:
+        ref_out = rx.extract(img)
+        orc_out = orc.extract(img)
+        for l in range(8):
+            assert np.array_equal(rx.level(l), orc.level(l)), f"pyramid level {l}"
+        assert len(ref_out[0]) > 100
+        _compare(ref_out, orc_out)
+    rx.close()
