@@ -5,7 +5,8 @@
 // the scale tables and quotas, the level-major output order and the keypoint rescale all execute from the reference's
 // own source.  What lives inside OpenCV itself -- cv::resize(INTER_LINEAR), cv::FAST(TYPE_9_16), cv::GaussianBlur(7x7, 2),
 // cv::fastAtan2, cvRound -- is forwarded to the oracle's restatements of those primitives (oracle/pgo_orb.cc), which are
-// pinned bit-exact against cv2 4.13 by tests/test_oracle_orb.py.  cv::Mat here is 8-bit single-channel only, with
+// pinned bit-exact against cv2 4.13 by tests/test_oracle_orb.py.  cv::Mat here is single-channel 8-bit (images,
+// descriptors) or 32-bit float (the small pose / point matrices ORBmatcher.cc multiplies), with
 // OpenCV's view semantics (rowRange / colRange / operator()(Rect) share the buffer; create() keeps a buffer of the right
 // size, which is what lets resize() and copyMakeBorder() write through the pyramid's views).
 // Not part of the product; nothing under pilotguru_b200/ includes it.
@@ -31,6 +32,8 @@ float pgo_fast_atan2(float y, float x);
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
 #define CV_PI 3.1415926535897932384626433832795
 
 typedef unsigned char uchar;
@@ -76,59 +79,99 @@ struct KeyPoint {
 class Mat {
  public:
   int rows, cols;
-  size_t step;
+  size_t step;   // bytes per row
   uchar* data;
+  int type_;
   std::shared_ptr<std::vector<uchar> > buf;
 
-  Mat() : rows(0), cols(0), step(0), data(nullptr) {}
-  Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(nullptr) { create(r, c, type); }
-  Mat(Size sz, int type) : rows(0), cols(0), step(0), data(nullptr) { create(sz.height, sz.width, type); }
-  Mat(int r, int c, int /*type*/, void* ext, size_t st) : rows(r), cols(c), step(st), data((uchar*)ext) {}
+  Mat() : rows(0), cols(0), step(0), data(nullptr), type_(CV_8UC1) {}
+  Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(nullptr), type_(type) { create(r, c, type); }
+  Mat(Size sz, int type) : rows(0), cols(0), step(0), data(nullptr), type_(type) { create(sz.height, sz.width, type); }
+  Mat(int r, int c, int type, void* ext, size_t st) : rows(r), cols(c), step(st), data((uchar*)ext), type_(type) {}
   // Mat::zeros returns a MatExpr in OpenCV, and assigning a MatExpr evaluates it INTO the destination: create() keeps a
   // destination of the right size, so `descriptors = Mat::zeros(n, 32, CV_8UC1)` inside computeDescriptors() clears the
   // rows of the caller's output matrix that `descriptors` views (ORBextractor.cc:1036, :1088) instead of rebinding it.
   struct ZerosExpr { int r, c, type; };
   static ZerosExpr zeros(int r, int c, int type) { return ZerosExpr{r, c, type}; }
-  Mat(const ZerosExpr& e) : rows(0), cols(0), step(0), data(nullptr) { *this = e; }
+  Mat(const ZerosExpr& e) : rows(0), cols(0), step(0), data(nullptr), type_(e.type) { *this = e; }
   Mat& operator=(const ZerosExpr& e) {
     create(e.r, e.c, e.type);
-    for (int y = 0; y < rows; y++) memset(data + (size_t)y * step, 0, (size_t)cols);
+    for (int y = 0; y < rows; y++) memset(data + (size_t)y * step, 0, (size_t)cols * elemSize());
     return *this;
   }
 
-  void create(int r, int c, int /*type*/) {
-    if (data && rows == r && cols == c) return;   // cv::Mat::create: a matrix of the right size is kept (views included)
-    buf = std::make_shared<std::vector<uchar> >((size_t)r * c + 1);
-    rows = r; cols = c; step = (size_t)c; data = buf->data();
+  size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
+  void create(int r, int c, int type) {
+    if (data && rows == r && cols == c && type_ == type) return;   // cv::Mat::create keeps a matrix of the right size (views included)
+    type_ = type;
+    buf = std::make_shared<std::vector<uchar> >((size_t)r * c * elemSize() + 16);
+    rows = r; cols = c; step = (size_t)c * elemSize(); data = buf->data();
   }
   void release() { buf.reset(); rows = cols = 0; step = 0; data = nullptr; }
-  int type() const { return CV_8UC1; }
+  int type() const { return type_; }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   Size size() const { return Size(cols, rows); }
-  size_t step1() const { return step; }
-  template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step + x); }
-  template <typename T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step + x); }
+  size_t step1() const { return step / elemSize(); }
+  template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
+  template <typename T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
+  template <typename T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
+  template <typename T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
   uchar* ptr(int y = 0) { return data + (size_t)y * step; }
   const uchar* ptr(int y = 0) const { return data + (size_t)y * step; }
+  template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step); }
+  template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step); }
   Mat view(int x, int y, int w, int h) const {
     Mat m;
-    m.rows = h; m.cols = w; m.step = step; m.data = data + (size_t)y * step + x; m.buf = buf;
+    m.rows = h; m.cols = w; m.step = step; m.type_ = type_; m.data = data + (size_t)y * step + (size_t)x * elemSize(); m.buf = buf;
     return m;
   }
   Mat rowRange(int a, int b) const { return view(0, a, cols, b - a); }
   Mat colRange(int a, int b) const { return view(a, 0, b - a, rows); }
+  Mat row(int y) const { return view(0, y, cols, 1); }
+  Mat col(int x) const { return view(x, 0, 1, rows); }
   Mat operator()(const Rect& r) const { return view(r.x, r.y, r.width, r.height); }
   Mat clone() const {
-    Mat m(rows, cols, CV_8UC1);
-    for (int y = 0; y < rows; y++) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols);
+    Mat m(rows, cols, type_);
+    for (int y = 0; y < rows; y++) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols * elemSize());
     return m;
   }
-  std::vector<uchar> tight() const {  // helper of the stand-in: the matrix as a dense rows x cols buffer
+  std::vector<uchar> tight() const {  // helper of the stand-in: an 8-bit matrix as a dense rows x cols buffer
     std::vector<uchar> t((size_t)rows * cols + 1);
     for (int y = 0; y < rows; y++) memcpy(t.data() + (size_t)y * cols, data + (size_t)y * step, (size_t)cols);
     return t;
   }
+  // ---- the float algebra ORBmatcher.cc writes on poses and points.  OpenCV evaluates these MatExpr through gemm();
+  // for the 3x3 / 3x1 operands used here its small-matrix path forms each dot product in float, left to right, then
+  // adds the addend (alpha = beta = 1).  Only the monocular branch consumes the values (see ref_wrap_match.cc).
+  Mat t() const {
+    Mat m(cols, rows, CV_32F);
+    for (int y = 0; y < rows; y++)
+      for (int x = 0; x < cols; x++) m.at<float>(x, y) = at<float>(y, x);
+    return m;
+  }
+  Mat operator-() const {
+    Mat m(rows, cols, CV_32F);
+    for (int y = 0; y < rows; y++)
+      for (int x = 0; x < cols; x++) m.at<float>(y, x) = -at<float>(y, x);
+    return m;
+  }
 };
+inline Mat operator*(const Mat& a, const Mat& b) {
+  Mat m(a.rows, b.cols, CV_32F);
+  for (int y = 0; y < a.rows; y++)
+    for (int x = 0; x < b.cols; x++) {
+      float s = 0.f;
+      for (int k = 0; k < a.cols; k++) s = k == 0 ? a.at<float>(y, 0) * b.at<float>(0, x) : s + a.at<float>(y, k) * b.at<float>(k, x);
+      m.at<float>(y, x) = s;
+    }
+  return m;
+}
+inline Mat operator+(const Mat& a, const Mat& b) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int y = 0; y < a.rows; y++)
+    for (int x = 0; x < a.cols; x++) m.at<float>(y, x) = a.at<float>(y, x) + b.at<float>(y, x);
+  return m;
+}
 
 class _InputArray {
  public:
