@@ -7,8 +7,10 @@
 //   thirdparty/orb-slam2/src/Tracking.cc    retry with 2*th when fewer than 20 matches :876-883
 // The Frame/MapPoint object graph is flattened to arrays: every query is a "last frame map point" already
 // projected to (u,v) with its octave, angle and representative descriptor.  Mono only (bForward/bBackward are
-// false, mvuRight = -1).  The reference has no tests for this path; parity is pinned by construction against
-// this restatement and by the brute-force property tests in tests/test_oracle_match.py.
+// false, mvuRight = -1).  The reference has no tests for this path.  PINNED against the reference's own source: `make -C
+// oracle _ref` compiles the bodies of these functions from ORBmatcher.cc / Frame.cc (stand-in class declarations in
+// ref_shims/pgo_orbslam_shim.h) and tests/test_oracle_reference_pin.py holds every flavour restated here identical to them
+// (match vectors, counts, updated vbPrevMatched); further: the brute-force property tests in tests/test_oracle_match.py.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -265,3 +265,104 @@ def test_oracle_extractor_equals_the_reference_source(ref, case):
         assert len(ref_out[0]) > 100
         _compare(ref_out, orc_out)
     rx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The matcher: bodies of ORBmatcher::SearchByProjection (both overloads), SearchForInitialization, SearchByBoW,
+# ComputeThreeMaxima, DescriptorDistance and Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid, compiled from
+# the reference's files behind stand-in class declarations (oracle/ref_shims/pgo_orbslam_shim.h).
+KP = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+u8p = C.POINTER(C.c_uint8)
+
+
+def _v(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _feats(t, w=640, h=480, nf=500):
+    orc = O.OrbOracle(nf, 1.2, 8, 20, 7)
+    return orc.extract(synth.frame(t, w=w, h=h)), orc.tables()["scale"]
+
+
+def test_descriptor_distance_equals_the_reference_source(ref):
+    rng = np.random.default_rng(2)
+    d = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    for i in range(0, 200, 2):
+        assert ref.pgr_descriptor_distance(_v(d[i]), _v(d[i + 1])) == O.descriptor_distance(d[i], d[i + 1]) == int(np.unpackbits(d[i] ^ d[i + 1]).sum())
+
+
+@pytest.mark.parametrize("th,check_ori", [(15.0, True), (30.0, True), (7.0, False), (60.0, True)])
+def test_search_by_projection_equals_the_reference_source(ref, th, check_ori):
+    """SearchByProjection(CurrentFrame, LastFrame, th, bMono=true): grid walk order, strict-< ties, greedy skip of taken
+    features, TH_HIGH, the 30-bin histogram with factor 1/30 (only bins 0..12 fill), ComputeThreeMaxima."""
+    ref.pgr_search_by_projection.restype = C.c_int
+    total = 0
+    for t0 in (0, 1, 4):
+        (k0, d0), sf = _feats(t0)
+        (k1, d1), _ = _feats(t0 + 1)
+        fl = np.array(synth.flow(t0 + 1, w=640, h=480), np.float32)
+        uv = np.ascontiguousarray(np.stack([k0["x"], k0["y"]], axis=1) + fl, np.float32)
+        oc = np.ascontiguousarray(k0["octave"], np.int32); an = np.ascontiguousarray(k0["angle"], np.float32)
+        valid = (np.arange(len(k0)) % 7 != 3).astype(np.uint8)
+        on, om, _ = O.search_by_projection(k1, d1, uv, oc, an, d0, valid, (0.0, 640.0, 0.0, 480.0), th, sf, check_ori=check_ori)
+        k1c = np.ascontiguousarray(k1.astype(KP)); rm = np.full(len(k1), -9, np.int32)
+        rn = ref.pgr_search_by_projection(_v(k1c), _v(d1), len(k1), _v(uv), _v(oc), _v(an), _v(np.ascontiguousarray(d0)), _v(valid), len(k0),
+                                          C.c_float(0.0), C.c_float(640.0), C.c_float(0.0), C.c_float(480.0), C.c_float(th),
+                                          _v(np.ascontiguousarray(sf, np.float32)), 8, int(check_ori), _v(rm))
+        assert rn == on and np.array_equal(rm, om), (t0, rn, on)
+        total += rn
+    assert total > 300
+
+
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_for_initialization_equals_the_reference_source(ref, check_ori):
+    ref.pgr_search_for_initialization.restype = C.c_int
+    (k1, d1), _ = _feats(0)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    for t2, win in ((1, 100), (4, 100), (2, 20)):
+        (k2, d2), _ = _feats(t2)
+        pm = np.ascontiguousarray(np.stack([k1["x"], k1["y"]], axis=1), np.float32)
+        on, om, opm = O.search_for_initialization(k1, d1, k2, d2, pm, win, bounds, nnratio=0.9, check_ori=check_ori)
+        rpm = pm.copy(); rm = np.full(len(k1), -9, np.int32)
+        rn = ref.pgr_search_for_initialization(_v(np.ascontiguousarray(k1.astype(KP))), _v(d1), len(k1), _v(np.ascontiguousarray(k2.astype(KP))), _v(d2),
+                                               len(k2), _v(rpm), win, C.c_float(0.0), C.c_float(640.0), C.c_float(0.0), C.c_float(480.0),
+                                               C.c_float(0.9), int(check_ori), _v(rm))
+        assert rn == on and on > 10 and np.array_equal(rm, om) and np.array_equal(rpm, opm)
+
+
+def test_search_map_points_equals_the_reference_source(ref):
+    ref.pgr_search_map_points.restype = C.c_int
+    (k, d), sf = _feats(5)
+    rng = np.random.default_rng(8)
+    nq = 400
+    sel = rng.integers(0, len(k), nq)
+    uv = (np.stack([k["x"][sel], k["y"][sel]], axis=1) + rng.normal(0, 1.5, (nq, 2))).astype(np.float32)
+    lv = np.clip(k["octave"][sel] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+    vc = rng.uniform(0.99, 1.0, nq).astype(np.float32)
+    qd = d[sel].copy(); qd[np.arange(nq), rng.integers(0, 32, nq)] ^= rng.integers(0, 256, nq).astype(np.uint8)
+    iv = (rng.uniform(size=nq) > 0.1).astype(np.uint8); ob = (rng.uniform(size=nq) > 0.3).astype(np.uint8)
+    has = (rng.uniform(size=len(k)) > 0.9).astype(np.uint8)
+    for th, ratio in ((1.0, 0.8), (3.0, 0.8), (5.0, 0.6)):
+        on, om = O.search_map_points(k, d, has, uv, lv, vc, qd, iv, ob, (0.0, 640.0, 0.0, 480.0), th, sf, nnratio=ratio)
+        rm = np.full(len(k), -9, np.int32)
+        rn = ref.pgr_search_map_points(_v(np.ascontiguousarray(k.astype(KP))), _v(d), len(k), _v(has), _v(uv), _v(lv), _v(vc), _v(np.ascontiguousarray(qd)),
+                                       _v(iv), _v(ob), nq, C.c_float(0.0), C.c_float(640.0), C.c_float(0.0), C.c_float(480.0), C.c_float(th),
+                                       _v(np.ascontiguousarray(sf, np.float32)), 8, C.c_float(ratio), _v(rm))
+        assert rn == on and on > 50 and np.array_equal(rm, om)
+
+
+def test_search_by_bow_equals_the_reference_source(ref):
+    import bow_util as B
+    from pilotguru_b200.matcher import featvec_csr
+    ref.pgr_search_by_bow.restype = C.c_int
+    for (t0, t1, seed, cell), (ratio, ori) in zip(((0, 1, 1, 80), (2, 5, 2, 80), (3, 3, 3, 40), (1, 2, 4, 1000)),
+                                                  ((0.7, True), (0.9, True), (0.75, False), (0.8, True))):
+        P = B.problem(t0, t1, seed, cell=cell)
+        kf, ff = featvec_csr(P["kf_fv"]), featvec_csr(P["f_fv"])
+        on, om = O.search_by_bow(P["kf_desc"], P["kf_angle"], P["kf_has"], kf, P["f_desc"], P["f_angle"], ff, nnratio=ratio, check_ori=ori)
+        rm = np.full(len(P["f_desc"]), -9, np.int32)
+        c = lambda a, t: np.ascontiguousarray(a, t)
+        rn = ref.pgr_search_by_bow(_v(c(P["kf_desc"], np.uint8)), _v(c(P["kf_angle"], np.float32)), _v(c(P["kf_has"], np.uint8)), len(P["kf_desc"]),
+                                   _v(kf[0]), _v(kf[1]), _v(kf[2]), len(kf[0]), _v(c(P["f_desc"], np.uint8)), _v(c(P["f_angle"], np.float32)),
+                                   len(P["f_desc"]), _v(ff[0]), _v(ff[1]), _v(ff[2]), len(ff[0]), C.c_float(ratio), int(ori), _v(rm))
+        assert rn == on and on > 40 and np.array_equal(rm, om)
