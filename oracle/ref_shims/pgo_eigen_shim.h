@@ -33,6 +33,16 @@ template <int O> class Matrix<double, 3, 1, O> {
     for (int i = 0; i < 3; i++) v[i] += o.v[i];
     return *this;
   }
+  template <int O2> Matrix& operator-=(const Matrix<double, 3, 1, O2>& o) {
+    for (int i = 0; i < 3; i++) v[i] -= o.v[i];
+    return *this;
+  }
+  Matrix& operator/=(double s) {
+    for (int i = 0; i < 3; i++) v[i] /= s;
+    return *this;
+  }
+  template <int O2> double dot(const Matrix<double, 3, 1, O2>& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+  double operator()(int i) const { return v[i]; }
 };
 typedef Matrix<double, 3, 1, 0> Vector3d;
 
@@ -90,6 +100,7 @@ template <int O> class Quaternion<double, O> {
   Quaternion() : qx(0), qy(0), qz(0), qw(1) {}
   Quaternion(double w, double x, double y, double z) : qx(x), qy(y), qz(z), qw(w) {}
   template <int O2> Quaternion(const Quaternion<double, O2>& o) : qx(o.qx), qy(o.qy), qz(o.qz), qw(o.qw) {}
+  Quaternion<double, 0> conjugate() const { return Quaternion<double, 0>(qw, -qx, -qy, -qz); }
   double w() const { return qw; }
   double x() const { return qx; }
   double y() const { return qy; }

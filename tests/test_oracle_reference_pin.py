@@ -366,3 +366,31 @@ def test_search_by_bow_equals_the_reference_source(ref):
                                    _v(kf[0]), _v(kf[1]), _v(kf[2]), len(kf[0]), _v(c(P["f_desc"], np.uint8)), _v(c(P["f_angle"], np.float32)),
                                    len(P["f_desc"]), _v(ff[0]), _v(ff[1]), _v(ff[2]), len(ff[0]), C.c_float(ratio), int(ori), _v(rm))
         assert rn == on and on > 40 and np.array_equal(rm, om)
+
+
+@pytest.mark.parametrize("hz,max_iters,tol", [(100.0, 5, 1e-11), (100.0, 15, 1e-9), (500.0, 8, 1e-10)])
+def test_fit_motion_window_loop_equals_the_reference_source(ref, hz, max_iters, tol):
+    """ComputeAndSaveForwardVelocitiesFromImu (src/fit_motion.cc:156-293) compiled from the reference's file: window sliding,
+    per-window LBFGS++ fit and IntegrateTrajectory, per-event averaging over the overlapping windows, the timestamps,
+    SmoothTimeSeries, and the forward axis (KahanSum of the rotated velocities, projection off the vertical, normalisation).
+    Few L-BFGS iterations per window, so that the comparison stays below the objective's chaos horizon (see the L-BFGS pin)."""
+    ref.pgr_fit_motion.restype = C.c_int64
+    d = synth.imu_gps(100.0, hz, seed=21)
+    vertical = np.array([0.05, -0.02, 1.0]); vertical /= np.linalg.norm(vertical)
+    min_vel, min_rot = 2.0, 0.05
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    gv, gt, gy, gyt, ac, act = a(d["gps_v"], np.float64), a(d["gps_t"], np.int64), a(d["gyro"], np.float64), a(d["gyro_t"], np.int64), a(d["acc"], np.float64), a(d["acc_t"], np.int64)
+    cap = len(gyt) + len(act) + 8
+    rt = np.empty(cap, np.int64); rs = np.empty(cap); rf = np.zeros(3)
+    n = ref.pgr_fit_motion(gv.ctypes.data_as(f64p), _p(gt), C.c_int64(len(gt)), gy.ctypes.data_as(f64p), _p(gyt), C.c_int64(len(gyt)),
+                           ac.ctypes.data_as(f64p), _p(act), C.c_int64(len(act)), vertical.ctypes.data_as(f64p), C.c_int64(40), C.c_int64(5),
+                           C.c_int64(max_iters), C.c_double(0.003), C.c_double(min_vel), C.c_double(min_rot), _p(rt), rs.ctypes.data_as(f64p),
+                           C.c_int64(cap), rf.ctypes.data_as(f64p))
+    o = O.fit_motion(d, 40, 5, max_iters, 0.003, mode=0)
+    assert n == len(o["t_usec"]) and n > 5000
+    assert np.array_equal(rt[:n], o["t_usec"])
+    assert np.max(np.abs(rs[:n] - o["smoothed"])) <= tol * np.max(np.abs(rs[:n]))
+    fsum, used = O.forward_axis_sum(d, o["x"], 40, 5, mode=0, min_vel=min_vel, min_rot=min_rot)
+    f = fsum - vertical * np.dot(vertical, fsum)
+    f = f / (np.linalg.norm(f) + 1e-5)
+    assert used > 0 and np.max(np.abs(f - rf)) <= max(tol, 1e-9)
