@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "pgo_opencv_shim.h"
@@ -23,9 +24,14 @@ class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
 
 namespace ORB_SLAM2 {
 
+class KeyFrame;
+
 class MapPoint {
  public:
   cv::Mat mWorldPos, mDescriptor;
+  std::mutex mMutexFeatures;
+  std::map<KeyFrame*, size_t> mObservations;   // MapPoint.h: keyframe -> index of the observing feature
+  void ComputeDistinctiveDescriptors();
   int nObs = 1;
   bool mbBad = false;
   // Tracking::SearchLocalPoints fills these through Frame::isInFrustum (MapPoint.h)
@@ -66,6 +72,8 @@ class KeyFrame {
   cv::Mat mDescriptors;
   std::vector<cv::KeyPoint> mvKeysUn;
   std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  bool mbBad = false;
+  bool isBad() { return mbBad; }
 };
 
 class ORBmatcher {   // thirdparty/orb-slam2/include/ORBmatcher.h:38-103, the members the compiled functions use

@@ -167,4 +167,21 @@ int pgr_search_by_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8
   return n;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324) for one map point observed by n keyframes (observation i =
+// row 0 of keyframe i; the keyframes sit in one array, so the std::map<KeyFrame*, size_t> iterates them in input order).
+// Writes the chosen descriptor; returns 0 if the reference left mDescriptor untouched (no observations).
+int pgr_distinctive_descriptor(const uint8_t* desc, int n, uint8_t* chosen32) {
+  std::vector<KeyFrame> kfs(n > 0 ? n : 1);
+  MapPoint mp;
+  for (int i = 0; i < n; i++) {
+    kfs[i].mDescriptors = cv::Mat(1, 32, CV_8UC1);
+    memcpy(kfs[i].mDescriptors.data, desc + (size_t)i * 32, 32);
+    mp.mObservations[&kfs[i]] = 0;
+  }
+  mp.ComputeDistinctiveDescriptors();
+  if (mp.mDescriptor.empty()) return 0;
+  memcpy(chosen32, mp.mDescriptor.data, 32);
+  return 1;
+}
+
 }  // extern "C"

@@ -394,3 +394,16 @@ def test_fit_motion_window_loop_equals_the_reference_source(ref, hz, max_iters, 
     f = fsum - vertical * np.dot(vertical, fsum)
     f = f / (np.linalg.norm(f) + 1e-5)
     assert used > 0 and np.max(np.abs(f - rf)) <= max(tol, 1e-9)
+
+
+def test_distinctive_descriptor_equals_the_reference_source(ref):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:259-324): float distance matrix, sorted rows, median at
+    0.5 * (N - 1), first least median wins."""
+    rng = np.random.default_rng(12)
+    for n in [1, 2, 3, 4, 5, 8, 17, 31, 32, 33, 64, 100]:
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.stack([base ^ (rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8)) for _ in range(n)])
+        out = np.zeros(32, np.uint8)
+        assert ref.pgr_distinctive_descriptor(_v(np.ascontiguousarray(d)), n, _v(out)) == 1
+        assert np.array_equal(out, d[O.distinctive_descriptor(d)]), n
+    assert ref.pgr_distinctive_descriptor(None, 0, _v(np.zeros(32, np.uint8))) == 0 and O.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1
