@@ -24,6 +24,7 @@
 #include <vector>
 
 extern "C" {
+void pgo_pca3(const double* rows, int64_t n, double* eigvec9, double* eigval3, double* mean3);
 void pgo_resize_linear(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
 int pgo_fast(const uint8_t* img, int w, int h, int th, int nms, int32_t* xys, int cap);
 void pgo_gaussian_blur7(const uint8_t* src, int w, int h, uint8_t* dst);
@@ -34,6 +35,9 @@ float pgo_fast_atan2(float y, float x);
 #define CV_8UC1 0
 #define CV_32F 5
 #define CV_32FC1 5
+#define CV_64F 6
+#define CV_64FC1 6
+#define CV_PCA_DATA_AS_ROW 0
 #define CV_PI 3.1415926535897932384626433832795
 
 typedef unsigned char uchar;
@@ -100,7 +104,7 @@ class Mat {
     return *this;
   }
 
-  size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
+  size_t elemSize() const { return type_ == CV_32F ? 4 : type_ == CV_64F ? 8 : 1; }
   void create(int r, int c, int type) {
     if (data && rows == r && cols == c && type_ == type) return;   // cv::Mat::create keeps a matrix of the right size (views included)
     type_ = type;
@@ -242,6 +246,41 @@ inline void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sx, double
   dst.create(src.rows, src.cols, CV_8UC1);
   for (int y = 0; y < dst.rows; y++) memcpy(dst.data + (size_t)y * dst.step, d.data() + (size_t)y * dst.cols, (size_t)dst.cols);
 }
+
+// ---- what src/calibration/rotation.cc uses: Vec3d, norm, and cv::PCA over an n x 3 CV_64F matrix with the samples as
+// rows.  The PCA itself (covariance + OpenCV's cyclic Jacobi sweep, eigenvectors as rows, descending eigenvalues) is the
+// oracle's restatement, pinned against cv2.PCACompute2 including the eigenvector signs (tests/golden/cv2_pca.npz).
+struct Vec3d {
+  double val[3];
+  Vec3d() : val{0, 0, 0} {}
+  Vec3d(double a, double b, double c) : val{a, b, c} {}
+  double& operator[](int i) { return val[i]; }
+  const double& operator[](int i) const { return val[i]; }
+  double dot(const Vec3d& o) const { return val[0] * o.val[0] + val[1] * o.val[1] + val[2] * o.val[2]; }
+};
+inline Vec3d operator*(const Vec3d& a, double s) { return Vec3d(a.val[0] * s, a.val[1] * s, a.val[2] * s); }
+inline Vec3d operator/(const Vec3d& a, double s) { return Vec3d(a.val[0] / s, a.val[1] / s, a.val[2] / s); }
+enum { NORM_L2 = 4 };
+inline double norm(const Vec3d& v, int /*normType*/) { return std::sqrt(v.val[0] * v.val[0] + v.val[1] * v.val[1] + v.val[2] * v.val[2]); }
+
+class PCA {
+ public:
+  Mat eigenvectors, eigenvalues, mean;
+  PCA(const Mat& data, const _InputArray& /*mean*/, int /*flags*/) {
+    assert(data.type() == CV_64F && data.cols == 3);
+    std::vector<double> rows((size_t)data.rows * 3);
+    for (int y = 0; y < data.rows; y++)
+      for (int x = 0; x < 3; x++) rows[(size_t)y * 3 + x] = data.at<double>(y, x);
+    double ev[9], ew[3], mu[3];
+    pgo_pca3(rows.data(), data.rows, ev, ew, mu);
+    eigenvectors = Mat(3, 3, CV_64F); eigenvalues = Mat(3, 1, CV_64F); mean = Mat(1, 3, CV_64F);
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) eigenvectors.at<double>(i, j) = ev[3 * i + j];
+      eigenvalues.at<double>(i, 0) = ew[i];
+      mean.at<double>(0, i) = mu[i];
+    }
+  }
+};
 
 struct KeyPointsFilter {  // only named by ComputeKeyPointsOld, which operator() does not call
   static void retainBest(std::vector<KeyPoint>& keypoints, int npoints) {

@@ -36,3 +36,23 @@ extern "C" int64_t pgr_fit_motion(const double* gps_v, const int64_t* gps_t, int
   for (int k = 0; k < 3; k++) forward_axis3[k] = c.forward_axis[k];
   return (int64_t)c.values.size();
 }
+
+// ---- src/calibration/rotation.cc:16-57 and :103-119, compiled from the reference's file (cv::PCA: see pgo_opencv_shim.h)
+#include <opencv2/core/core.hpp>
+namespace pilotguru {
+cv::Mat GetPrincipalRotationAxes(const std::vector<TimestampedRotationVelocity>& raw_rotations, long integration_interval_usec);
+std::vector<double> GetAngularVelocitiesAroundAxisDirect(const std::vector<TimestampedRotationVelocity>& raw_rotations, const cv::Vec3d& axis);
+}
+extern "C" void pgr_principal_rotation_axes(const double* gyro_xyz, const int64_t* gyro_t, int64_t n, int64_t interval_usec, double* axes9) {
+  std::vector<pilotguru::TimestampedRotationVelocity> rot;
+  for (int64_t i = 0; i < n; i++) rot.push_back({gyro_xyz[3 * i], gyro_xyz[3 * i + 1], gyro_xyz[3 * i + 2], (long)gyro_t[i]});
+  const cv::Mat ev = pilotguru::GetPrincipalRotationAxes(rot, (long)interval_usec);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) axes9[3 * i + j] = ev.at<double>(i, j);
+}
+extern "C" void pgr_angular_velocities_around_axis(const double* gyro_xyz, int64_t n, const double* axis, double* out) {
+  std::vector<pilotguru::TimestampedRotationVelocity> rot;
+  for (int64_t i = 0; i < n; i++) rot.push_back({gyro_xyz[3 * i], gyro_xyz[3 * i + 1], gyro_xyz[3 * i + 2], 0});
+  const std::vector<double> r = pilotguru::GetAngularVelocitiesAroundAxisDirect(rot, cv::Vec3d(axis[0], axis[1], axis[2]));
+  for (int64_t i = 0; i < n; i++) out[i] = r[(size_t)i];
+}

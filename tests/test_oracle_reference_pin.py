@@ -407,3 +407,21 @@ def test_distinctive_descriptor_equals_the_reference_source(ref):
         assert ref.pgr_distinctive_descriptor(_v(np.ascontiguousarray(d)), n, _v(out)) == 1
         assert np.array_equal(out, d[O.distinctive_descriptor(d)]), n
     assert ref.pgr_distinctive_descriptor(None, 0, _v(np.zeros(32, np.uint8))) == 0 and O.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1
+
+
+def test_rotation_axes_and_steering_equal_the_reference_source(ref):
+    """GetPrincipalRotationAxes (rotation.cc:16-57: gyro integration over >= 0.5 s intervals, quaternion vector parts, cv::PCA)
+    and GetAngularVelocitiesAroundAxisDirect (:103-119), compiled from the reference's file.  cv::PCA itself is the cv2-pinned
+    restatement on both sides, so this pins the interval integration feeding it: bit-exact."""
+    rng = np.random.default_rng(4)
+    for hz, interleaved, interval in ((100.0, False, 500000), (500.0, False, 500000), (100.0, True, 120000)):
+        d = synth.imu_gps(60.0, hz, seed=13, interleaved=interleaved)
+        g = np.ascontiguousarray(d["gyro"], np.float64); t = np.ascontiguousarray(d["gyro_t"], np.int64)
+        axes, rows = O.principal_rotation_axes(g, t, interval)
+        ra = np.zeros(9)
+        ref.pgr_principal_rotation_axes(g.ctypes.data_as(f64p), _p(t), C.c_int64(len(t)), C.c_int64(interval), ra.ctypes.data_as(f64p))
+        assert np.array_equal(ra.reshape(3, 3), axes) and len(rows) >= 3
+        axis = axes[0] * (1 + 0.004 * rng.normal())                       # within the 1e-2 normalisation tolerance
+        out = np.empty(len(g))
+        ref.pgr_angular_velocities_around_axis(g.ctypes.data_as(f64p), C.c_int64(len(g)), np.ascontiguousarray(axis).ctypes.data_as(f64p), out.ctypes.data_as(f64p))
+        assert np.array_equal(out, O.angular_velocities_around_axis(g, axis))
