@@ -21,15 +21,7 @@
 #include <geometry/geometry.hpp>
 #include <math/math.hpp>
 
-namespace nlohmann {
-class json {
- public:
-  std::map<std::string, json> kids;
-  double value = 0;
-  json& operator[](const std::string& k) { return kids[k]; }
-  json& operator=(double v) { value = v; return *this; }
-};
-}  // namespace nlohmann
+#include <json.hpp>
 
 namespace pilotguru {
 std::vector<double> SmoothTimeSeries(const std::vector<double>& data_values, const std::vector<double>& data_timestamps,
@@ -57,9 +49,9 @@ inline void JsonWriteTimestampedRealData(const std::vector<long>& times_usec, co
 }
 inline void WriteJsonFile(nlohmann::json& root, const std::string& /*filename*/) {
   nlohmann::json& a = root[kForwardAxis];
-  g_pgr_fit_capture.forward_axis[0] = a[kX].value;
-  g_pgr_fit_capture.forward_axis[1] = a[kY].value;
-  g_pgr_fit_capture.forward_axis[2] = a[kZ].value;
+  g_pgr_fit_capture.forward_axis[0] = a[kX].num;
+  g_pgr_fit_capture.forward_axis[1] = a[kY].num;
+  g_pgr_fit_capture.forward_axis[2] = a[kZ].num;
   g_pgr_fit_capture.have_axis = true;
 }
 }  // namespace pilotguru

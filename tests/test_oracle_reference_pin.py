@@ -425,3 +425,29 @@ def test_rotation_axes_and_steering_equal_the_reference_source(ref):
         out = np.empty(len(g))
         ref.pgr_angular_velocities_around_axis(g.ctypes.data_as(f64p), C.c_int64(len(g)), np.ascontiguousarray(axis).ctypes.data_as(f64p), out.ctypes.data_as(f64p))
         assert np.array_equal(out, O.angular_velocities_around_axis(g, axis))
+
+
+@pytest.mark.parametrize("sigma", [-1.0, 0.05])
+def test_annotate_frames_equals_the_reference_source(ref, sigma):
+    """The reference's own include/interpolation/time_series.hpp (TimeAveragedValue, MostRecentPreviousValue,
+    LinearInterpolate, GaussianSmooth) and the frame loop of src/annotate_frames.cc:56-69, compiled from the reference's
+    files: the same frames get a label and the labels are bit-identical."""
+    ref.pgr_annotate_frames.restype = C.c_int64
+    rng = np.random.default_rng(6)
+    n = 4000
+    t = np.cumsum(rng.integers(1500, 2600, n)).astype(np.int64) + 1_000_000
+    v = np.cumsum(rng.normal(0, 0.05, n)) + 10
+    ft = np.sort(np.concatenate([np.arange(t[0] - 200_000, t[-1] + 200_000, 33_333), t[[5, 100, 101, 2000]]])).astype(np.int64)
+    ft = np.unique(ft)
+    vv = v
+    if sigma > 0:
+        ts = (t - t[0]).astype(np.float64) * 1e-6
+        vv = O.smooth_time_series(v, ts, ts, sigma)
+    ov, ovalid = O.time_averaged_values(vv, t, ft)
+    ids = np.empty(len(ft), np.int64); vals = np.empty(len(ft))
+    k = ref.pgr_annotate_frames(np.ascontiguousarray(v).ctypes.data_as(f64p), _p(t), C.c_int64(n), _p(ft), C.c_int64(len(ft)), C.c_double(sigma),
+                                _p(ids), vals.ctypes.data_as(f64p), C.c_int64(len(ft)))
+    want_ids = np.nonzero(ovalid)[0] + 1 if len(ovalid) == len(ft) - 1 else np.nonzero(ovalid)[0]
+    assert k == len(want_ids) and k > 100
+    assert np.array_equal(ids[:k], want_ids)
+    assert np.array_equal(vals[:k], ov[ovalid.astype(bool)])
