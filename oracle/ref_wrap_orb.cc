@@ -8,6 +8,8 @@
 
 #include "ORBextractor.h"
 
+extern "C" void pgr_set_monotonic_alloc(int on);   // ref_bump_alloc.cc
+
 extern "C" {
 
 void* pgr_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th) {
@@ -22,7 +24,9 @@ int pgr_orb_extract(void* h, const uint8_t* gray, int w, int h_px, float* kps, u
   cv::Mat image(h_px, w, CV_8UC1, const_cast<uint8_t*>(gray), (size_t)w);
   std::vector<cv::KeyPoint> keypoints;
   cv::Mat descriptors;
+  pgr_set_monotonic_alloc(1);   // DistributeOctTree's heap-address tie-break needs increasing addresses (ref_bump_alloc.cc)
   ex(image, cv::noArray(), keypoints, descriptors);
+  pgr_set_monotonic_alloc(0);
   for (size_t i = 0; i < keypoints.size() && (int)i < cap; i++) {
     const cv::KeyPoint& k = keypoints[i];
     float* o = kps + 7 * i;
