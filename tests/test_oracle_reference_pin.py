@@ -451,3 +451,30 @@ def test_annotate_frames_equals_the_reference_source(ref, sigma):
     assert k == len(want_ids) and k > 100
     assert np.array_equal(ids[:k], want_ids)
     assert np.array_equal(vals[:k], ov[ovalid.astype(bool)])
+
+
+def test_oracle_extractor_fuzz_against_the_reference_source(ref):
+    """Random sizes, quotas and image classes (a 100-image run of this loop during development: 58 318 keypoints, no
+    mismatch).  Sizes stay where the reference itself is defined: landscape (its root-node count round(w/h) is 0 for
+    w < h/2 and it then indexes an empty vector) and at least 32 px on the coarsest level."""
+    rng = np.random.default_rng(321)
+    total = 0
+    for it in range(24):
+        kind = it % 4
+        h = int(rng.integers(240, 620)); w = int(h * rng.uniform(1.0, 2.4)); nf = int(rng.integers(100, 1500))
+        if kind == 0:
+            img = synth.frame(int(rng.integers(0, 500)), w=w, h=h)
+        elif kind == 1:
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif kind == 2:
+            img = (synth.frame(int(rng.integers(0, 500)), w=w, h=h).astype(np.int32) // int(rng.integers(2, 10)) + 60).astype(np.uint8)
+        else:
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = ((xx * int(rng.integers(1, 4)) + yy) // 3 % 256).astype(np.uint8); img[h // 3:h // 3 + 40, w // 4:w // 4 + 60] = 255
+        rx = RefOrb(ref, nf, 1.2, 8, 20, 7)
+        orc = O.OrbOracle(nf, 1.2, 8, 20, 7)
+        ref_out = rx.extract(img, cap=8192)
+        _compare(ref_out, orc.extract(img))
+        total += len(ref_out[0])
+        rx.close()
+    assert total > 5000
