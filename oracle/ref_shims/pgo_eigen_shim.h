@@ -105,6 +105,10 @@ template <int O> class Quaternion<double, O> {
   double x() const { return qx; }
   double y() const { return qy; }
   double z() const { return qz; }
+  double& w() { return qw; }
+  double& x() { return qx; }
+  double& y() { return qy; }
+  double& z() { return qz; }
   template <int O2> Quaternion<double, 0> operator*(const Quaternion<double, O2>& b) const {  // Eigen quat_product
     return Quaternion<double, 0>(qw * b.qw - qx * b.qx - qy * b.qy - qz * b.qz, qw * b.qx + qx * b.qw + qy * b.qz - qz * b.qy,
                                  qw * b.qy + qy * b.qw + qz * b.qx - qx * b.qz, qw * b.qz + qz * b.qw + qx * b.qy - qy * b.qx);

@@ -49,7 +49,7 @@ inline int cvCeil(double v) { const int i = (int)v; return i + (i < v); }
 namespace cv {
 
 using ::uchar;
-enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+enum { BORDER_REPLICATE = 1, BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
 enum { INTER_LINEAR = 1 };
 
 struct Size {
@@ -80,6 +80,8 @@ struct KeyPoint {
       : pt(x, y), size(size_), angle(angle_), response(response_), octave(octave_), class_id(class_id_) {}
 };
 
+struct Vec3d;
+
 class Mat {
  public:
   int rows, cols;
@@ -92,6 +94,7 @@ class Mat {
   Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(nullptr), type_(type) { create(r, c, type); }
   Mat(Size sz, int type) : rows(0), cols(0), step(0), data(nullptr), type_(type) { create(sz.height, sz.width, type); }
   Mat(int r, int c, int type, void* ext, size_t st) : rows(r), cols(c), step(st), data((uchar*)ext), type_(type) {}
+  explicit Mat(const Vec3d& v);   // 3 x 1 CV_64F, like cv::Mat(const Vec<T, n>&)
   // Mat::zeros returns a MatExpr in OpenCV, and assigning a MatExpr evaluates it INTO the destination: create() keeps a
   // destination of the right size, so `descriptors = Mat::zeros(n, 32, CV_8UC1)` inside computeDescriptors() clears the
   // rows of the caller's output matrix that `descriptors` views (ORBextractor.cc:1036, :1088) instead of rebinding it.
@@ -147,33 +150,44 @@ class Mat {
   // ---- the float algebra ORBmatcher.cc writes on poses and points.  OpenCV evaluates these MatExpr through gemm();
   // for the 3x3 / 3x1 operands used here its small-matrix path forms each dot product in float, left to right, then
   // adds the addend (alpha = beta = 1).  Only the monocular branch consumes the values (see ref_wrap_match.cc).
+  double getd(int y, int x) const { return type_ == CV_64F ? at<double>(y, x) : (double)at<float>(y, x); }
+  void setd(int y, int x, double v) { if (type_ == CV_64F) at<double>(y, x) = v; else at<float>(y, x) = (float)v; }
   Mat t() const {
-    Mat m(cols, rows, CV_32F);
+    Mat m(cols, rows, type_);
     for (int y = 0; y < rows; y++)
-      for (int x = 0; x < cols; x++) m.at<float>(x, y) = at<float>(y, x);
+      for (int x = 0; x < cols; x++) m.setd(x, y, getd(y, x));
     return m;
   }
   Mat operator-() const {
-    Mat m(rows, cols, CV_32F);
+    Mat m(rows, cols, type_);
     for (int y = 0; y < rows; y++)
-      for (int x = 0; x < cols; x++) m.at<float>(y, x) = -at<float>(y, x);
+      for (int x = 0; x < cols; x++) m.setd(y, x, -getd(y, x));
     return m;
   }
 };
-inline Mat operator*(const Mat& a, const Mat& b) {
-  Mat m(a.rows, b.cols, CV_32F);
+inline Mat operator*(const Mat& a, const Mat& b) {   // dot products left to right, in the matrices' own precision
+  Mat m(a.rows, b.cols, a.type());
   for (int y = 0; y < a.rows; y++)
     for (int x = 0; x < b.cols; x++) {
-      float s = 0.f;
-      for (int k = 0; k < a.cols; k++) s = k == 0 ? a.at<float>(y, 0) * b.at<float>(0, x) : s + a.at<float>(y, k) * b.at<float>(k, x);
-      m.at<float>(y, x) = s;
+      if (a.type() == CV_64F) {
+        double s = 0;
+        for (int k = 0; k < a.cols; k++) s = k == 0 ? a.at<double>(y, 0) * b.at<double>(0, x) : s + a.at<double>(y, k) * b.at<double>(k, x);
+        m.at<double>(y, x) = s;
+      } else {
+        float s = 0.f;
+        for (int k = 0; k < a.cols; k++) s = k == 0 ? a.at<float>(y, 0) * b.at<float>(0, x) : s + a.at<float>(y, k) * b.at<float>(k, x);
+        m.at<float>(y, x) = s;
+      }
     }
   return m;
 }
 inline Mat operator+(const Mat& a, const Mat& b) {
-  Mat m(a.rows, a.cols, CV_32F);
+  Mat m(a.rows, a.cols, a.type());
   for (int y = 0; y < a.rows; y++)
-    for (int x = 0; x < a.cols; x++) m.at<float>(y, x) = a.at<float>(y, x) + b.at<float>(y, x);
+    for (int x = 0; x < a.cols; x++) {
+      if (a.type() == CV_64F) m.at<double>(y, x) = a.at<double>(y, x) + b.at<double>(y, x);
+      else m.at<float>(y, x) = a.at<float>(y, x) + b.at<float>(y, x);
+    }
   return m;
 }
 
@@ -257,11 +271,64 @@ struct Vec3d {
   double& operator[](int i) { return val[i]; }
   const double& operator[](int i) const { return val[i]; }
   double dot(const Vec3d& o) const { return val[0] * o.val[0] + val[1] * o.val[1] + val[2] * o.val[2]; }
+  double operator()(int i) const { return val[i]; }
+  Vec3d cross(const Vec3d& o) const {
+    return Vec3d(val[1] * o.val[2] - val[2] * o.val[1], val[2] * o.val[0] - val[0] * o.val[2], val[0] * o.val[1] - val[1] * o.val[0]);
+  }
 };
+inline Mat::Mat(const Vec3d& v) : rows(0), cols(0), step(0), data(nullptr), type_(CV_64F) {
+  create(3, 1, CV_64F);
+  for (int i = 0; i < 3; i++) at<double>(i, 0) = v.val[i];
+}
 inline Vec3d operator*(const Vec3d& a, double s) { return Vec3d(a.val[0] * s, a.val[1] * s, a.val[2] * s); }
 inline Vec3d operator/(const Vec3d& a, double s) { return Vec3d(a.val[0] / s, a.val[1] / s, a.val[2] / s); }
 enum { NORM_L2 = 4 };
 inline double norm(const Vec3d& v, int /*normType*/) { return std::sqrt(v.val[0] * v.val[0] + v.val[1] * v.val[1] + v.val[2] * v.val[2]); }
+
+inline double norm(const Mat& m, int /*normType*/) {   // NORM_L2 of a CV_64F matrix
+  double s = 0;
+  for (int y = 0; y < m.rows; y++)
+    for (int x = 0; x < m.cols; x++) s += m.at<double>(y, x) * m.at<double>(y, x);
+  return std::sqrt(s);
+}
+// cv::getGaussianKernel (imgproc/smooth.cpp, OpenCV 2.4): the sigma > 0 branch; CV_64F, n x 1.
+inline Mat getGaussianKernel(int n, double sigma, int ktype = CV_64F) {
+  assert(sigma > 0 && ktype == CV_64F);
+  Mat kernel(n, 1, CV_64F);
+  const double scale2X = -0.5 / (sigma * sigma);
+  double sum = 0;
+  for (int i = 0; i < n; i++) {
+    const double x = i - (n - 1) * 0.5;
+    const double t = std::exp(scale2X * x * x);
+    kernel.at<double>(i, 0) = t;
+    sum += t;
+  }
+  sum = 1. / sum;
+  for (int i = 0; i < n; i++) kernel.at<double>(i, 0) *= sum;
+  return kernel;
+}
+// cv::sepFilter2D for CV_64F with a 1-tap kernelY (what SmoothHeadingDirections asks for): the generic RowFilter sums
+// kx[k] * src[x + k - anchor] for k = 0 .. ksize-1 with replicated borders; the column pass multiplies by kernelY[0].
+inline void sepFilter2D(const Mat& src, Mat& dst, int /*ddepth*/, const Mat& kernelX, const Mat& kernelY, Point /*anchor*/, double delta,
+                        int borderType) {
+  assert(src.type() == CV_64F && kernelY.rows * kernelY.cols == 1 && borderType == BORDER_REPLICATE);
+  (void)borderType;
+  const int ks = kernelX.rows * kernelX.cols, anchor = ks / 2;
+  Mat out(src.rows, src.cols, CV_64F);
+  for (int y = 0; y < src.rows; y++)
+    for (int x = 0; x < src.cols; x++) {
+      double s = 0;
+      for (int k = 0; k < ks; k++) {
+        int j = x + k - anchor;
+        j = j < 0 ? 0 : (j >= src.cols ? src.cols - 1 : j);
+        const double term = kernelX.at<double>(k) * src.at<double>(y, j);
+        s = k == 0 ? term : s + term;
+      }
+      out.at<double>(y, x) = kernelY.at<double>(0) * s + delta;
+    }
+  dst.create(src.rows, src.cols, CV_64F);
+  for (int y = 0; y < src.rows; y++) memcpy(dst.data + (size_t)y * dst.step, out.data + (size_t)y * out.step, (size_t)src.cols * 8);
+}
 
 class PCA {
  public:

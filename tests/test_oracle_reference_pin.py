@@ -478,3 +478,43 @@ def test_oracle_extractor_fuzz_against_the_reference_source(ref):
         total += len(ref_out[0])
         rx.close()
     assert total > 5000
+
+
+@pytest.mark.parametrize("sigma", [-1, 2, 5])
+def test_host_trajectory_postprocessing_equals_the_reference_source(ref, sigma, tmp_path):
+    """The tail of TrackImageSequence as the product's host code does it (pilotguru_b200/host/trajectory.hpp, through its
+    trajectory_selftest binary) against the reference's own SmoothHeadingDirections (src/slam/smoothing.cc:11-46),
+    ProjectDirections and Projected2DDirectionsToTurnAngles (src/slam/horizontal_flatten.cc), compiled from the reference's
+    files: smoothed quaternions, planar directions and turn angles agree to 1e-12 (both sides are fp64; the JSON text carries
+    17 significant digits)."""
+    import json
+    host = os.path.join(ROOT, "pilotguru_b200", "host")
+    subprocess.run(["make", "-C", host], check=True, capture_output=True)
+    rng = np.random.default_rng(7)
+    n = 80
+    s = np.linspace(0, 3, n)
+    yaw = 0.6 * np.sin(s) + 0.02 * rng.normal(size=n)
+    pos = np.stack([np.cumsum(np.sin(yaw)), 1e-4 * rng.normal(size=n), np.cumsum(np.cos(yaw))], axis=1)
+    pitch = 0.05 * rng.normal(size=n)
+    quat = np.stack([np.cos(yaw / 2) * np.cos(pitch / 2), np.sin(pitch / 2) * np.cos(yaw / 2), np.sin(yaw / 2) * np.cos(pitch / 2),
+                     -np.sin(yaw / 2) * np.sin(pitch / 2)], axis=1)
+    ts = (np.arange(n) * 33333).astype(np.int64)
+    fin, fout = tmp_path / "poses.json", tmp_path / "traj.json"
+    fin.write_text(json.dumps({"poses": [[int(t), i] + [float(x) for x in np.r_[pos[i], quat[i]]] for i, t in enumerate(ts)]}))
+    p = subprocess.run([os.path.join(host, "trajectory_selftest"), str(fin), str(sigma), str(fout)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    out = json.loads(fout.read_text())
+    plane = np.ascontiguousarray(np.array(out["plane"], np.float64).reshape(-1)[:6])
+    poses = np.ascontiguousarray(np.concatenate([pos, quat], axis=1), np.float64)
+    rq = np.zeros((n, 4)); rd = np.zeros((n, 2)); rt = np.zeros(n)
+    ref.pgr_finish_trajectory(poses.ctypes.data_as(f64p), C.c_int64(n), int(sigma), plane.ctypes.data_as(f64p), rq.ctypes.data_as(f64p),
+                              rd.ctypes.data_as(f64p), rt.ctypes.data_as(f64p))
+    tr = out["trajectory"]
+    hq = np.array([[e["pose"]["rotation"][k] for k in "wxyz"] for e in tr])
+    hd = np.array([e["planar_direction"] for e in tr]); ht = np.array([e["angular_velocity"] for e in tr])
+    assert np.max(np.abs(hq - rq)) <= 1e-12 and np.max(np.abs(hd - rd)) <= 1e-12
+    # the JSON carries angular_velocity = turn_angle / (dt + 1e-10) (SetTrajectory, src/io/json_converters.cc:81-91)
+    dt = np.r_[1.0, np.diff(ts).astype(np.float64) * 1e-6]
+    want = np.r_[0.0, rt[1:] / (dt[1:] + 1e-10)]
+    assert np.max(np.abs(ht - want)) <= 1e-9 * max(1.0, np.abs(want).max())     # acos near 1 amplifies the last bits of the cosine
+    assert np.abs(rt).max() > 1e-3
