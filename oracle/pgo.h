@@ -50,6 +50,10 @@ int pgo_search_by_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8
                       const int32_t* f_feat_start, const uint32_t* f_feat_idx, int f_nodes, float nnratio, int check_ori,
                       int32_t* match_of_feature);
 int pgo_distinctive_descriptor(const uint8_t* desc, int N);
+void pgo_pose_se3_oplus(const double* update6, const double* pose7, double* out7);
+void pgo_pose_edge(const double* pose7, const double* Xw, const double* obs, double fx, double fy, double cx, double cy, double* err2,
+                   double* J12);
+void pgo_pose_huber(double delta, double e, double* rho3);
 int pgo_pose_optimization(const float* Tcw_in, const float* kp_xy, const int32_t* kp_octave, const float* mp_xyz,
                           const uint8_t* has_map_point, int n, const float* inv_level_sigma2, float fx, float fy, float cx,
                           float cy, float* Tcw_out, uint8_t* outlier, uint8_t* round_outliers);

@@ -11,8 +11,11 @@
 //   thirdparty/g2o/g2o/types/types_six_dof_expmap.{h:59-77,143-171; cpp:266-296}, types/se3quat.h (exp, operator*)
 //   thirdparty/orb-slam2/src/Converter.cc:39-55                           float cv::Mat <-> SE3Quat
 // Eigen's Quaterniond(Matrix3d), quaternion product, _transformVector, toRotationMatrix and LDLT (diagonal pivoting)
-// are restated from their published algorithms.  PARITY UNPINNED against the real g2o/Eigen: the reference holds no
-// test or golden vector for this function; tests pin it by (a) recovery of the true pose on synthetic scenes and (b)
+// are restated from their published algorithms.  PARITY UNPINNED against the real g2o/Eigen as a whole: the reference
+// holds no test or golden vector for this function.  Pins: (a) the per-edge arithmetic -- SE3Quat::exp * estimate, the
+// reprojection error and its 2x6 Jacobian, the Huber kernel -- is bit-identical to the g2o sources compiled in place
+// (oracle/_ref, tests/test_oracle_reference_pin.py); the LM driver, the quadratic form and the 6x6 LDLT stay restatements
+// (they need g2o's optimizer graph on the real Eigen), held by (b) recovery of the true pose on synthetic scenes and (c)
 // an independent scipy least-squares fit on the same inlier set (tests/test_oracle_pose.py).
 #include <cfloat>
 #include <cmath>
@@ -234,6 +237,14 @@ struct Problem {
     }
     return chi;
   }
+  // EdgeSE3ProjectXYZOnlyPose::linearizeOplus (types_six_dof_expmap.cpp:266-288) at the camera-frame point p
+  void jacobian(const double p[3], double J[2][6]) const {
+    const double x = p[0], y = p[1], invz = 1.0 / p[2], invz_2 = invz * invz;
+    J[0][0] = x * y * invz_2 * fx; J[0][1] = -(1 + (x * x * invz_2)) * fx; J[0][2] = y * invz * fx;
+    J[0][3] = -invz * fx; J[0][4] = 0; J[0][5] = x * invz_2 * fx;
+    J[1][0] = (1 + y * y * invz_2) * fy; J[1][1] = -x * y * invz_2 * fy; J[1][2] = -x * invz * fy;
+    J[1][3] = 0; J[1][4] = -invz * fy; J[1][5] = y * invz_2 * fy;
+  }
   void build_system(double H[6][6], double b[6]) const {
     memset(H, 0, 36 * sizeof(double));
     memset(b, 0, 6 * sizeof(double));
@@ -242,12 +253,8 @@ struct Problem {
       double p[3], r[3];
       quat_rotate(est.r, e.Xw, r);
       for (int i = 0; i < 3; i++) p[i] = r[i] + est.t[i];
-      const double x = p[0], y = p[1], invz = 1.0 / p[2], invz_2 = invz * invz;
       double J[2][6];
-      J[0][0] = x * y * invz_2 * fx; J[0][1] = -(1 + (x * x * invz_2)) * fx; J[0][2] = y * invz * fx;
-      J[0][3] = -invz * fx; J[0][4] = 0; J[0][5] = x * invz_2 * fx;
-      J[1][0] = (1 + y * y * invz_2) * fy; J[1][1] = -x * y * invz_2 * fy; J[1][2] = -x * invz * fy;
-      J[1][3] = 0; J[1][4] = -invz * fy; J[1][5] = y * invz_2 * fy;
+      jacobian(p, J);
       double w = 1.0;
       if (e.robust) { double rho[3]; robustify(chi2(e), rho); w = rho[1]; }
       for (int i = 0; i < 6; i++) {
@@ -365,6 +372,44 @@ int pgo_pose_optimization(const float* Tcw_in, const float* kp_xy, const int32_t
   }
   se3_to_cv(P.est, Tcw_out);
   return nInitialCorrespondences - nBad;
+}
+
+// ---- the per-edge pieces, exposed so that tests/test_oracle_reference_pin.py can hold them to the g2o sources compiled in
+// place (oracle/_ref).  pose7 = quaternion w, x, y, z + translation.
+void pgo_pose_se3_oplus(const double* update6, const double* pose7, double* out7) {   // VertexSE3Expmap::oplusImpl
+  SE3 est;
+  est.r = Quat{pose7[1], pose7[2], pose7[3], pose7[0]};
+  normalize_rotation(est.r);                                                            // SE3Quat(q, t) normalises
+  for (int i = 0; i < 3; i++) est.t[i] = pose7[4 + i];
+  const SE3 r = se3_mul(se3_exp(update6), est);
+  out7[0] = r.r.w; out7[1] = r.r.x; out7[2] = r.r.y; out7[3] = r.r.z;
+  for (int i = 0; i < 3; i++) out7[4 + i] = r.t[i];
+}
+
+void pgo_pose_edge(const double* pose7, const double* Xw, const double* obs, double fx, double fy, double cx, double cy, double* err2,
+                   double* J12) {
+  Problem P;
+  P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy; P.delta = 1; P.dsqr = 1;
+  P.est.r = Quat{pose7[1], pose7[2], pose7[3], pose7[0]};
+  normalize_rotation(P.est.r);
+  for (int i = 0; i < 3; i++) P.est.t[i] = pose7[4 + i];
+  Edge e;
+  e.obs[0] = obs[0]; e.obs[1] = obs[1]; e.info = 1; e.level = 0; e.robust = false; e.idx = 0;
+  for (int i = 0; i < 3; i++) e.Xw[i] = Xw[i];
+  P.compute_error(e);
+  err2[0] = e.err[0]; err2[1] = e.err[1];
+  double r[3], p[3], J[2][6];
+  quat_rotate(P.est.r, e.Xw, r);
+  for (int i = 0; i < 3; i++) p[i] = r[i] + P.est.t[i];
+  P.jacobian(p, J);
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 6; j++) J12[6 * i + j] = J[i][j];
+}
+
+void pgo_pose_huber(double delta, double e, double* rho3) {
+  Problem P;
+  P.delta = delta; P.dsqr = delta * delta;
+  P.robustify(e, rho3);
 }
 
 }  // extern "C"

@@ -43,6 +43,10 @@ template <int O> class Matrix<double, 3, 1, O> {
   }
   template <int O2> double dot(const Matrix<double, 3, 1, O2>& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
   double operator()(int i) const { return v[i]; }
+  double& operator()(int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  double& operator[](int i) { return v[i]; }
+  void setZero() { v[0] = v[1] = v[2] = 0; }
 };
 typedef Matrix<double, 3, 1, 0> Vector3d;
 
@@ -61,6 +65,10 @@ template <int O> class Matrix<double, 3, 3, O> {
   double m[3][3];
   Matrix() : m{{0, 0, 0}, {0, 0, 0}, {0, 0, 0}} {}
   static Matrix Zero() { return Matrix(); }
+  static Matrix Identity() { Matrix r; r.m[0][0] = r.m[1][1] = r.m[2][2] = 1; return r; }
+  void fill(double x) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[i][j] = x; }
+  double& operator()(int i, int j) { return m[i][j]; }
+  double operator()(int i, int j) const { return m[i][j]; }
   Matrix transpose() const {
     Matrix t;
     for (int i = 0; i < 3; i++)
@@ -87,11 +95,50 @@ inline Matrix3d operator*(double s, const Matrix3d& a) {
     for (int j = 0; j < 3; j++) r.m[i][j] = s * a.m[i][j];
   return r;
 }
+inline Matrix3d operator+(const Matrix3d& a, const Matrix3d& b) {
+  Matrix3d r;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][j] + b.m[i][j];
+  return r;
+}
+inline Matrix3d operator*(const Matrix3d& a, const Matrix3d& b) {
+  Matrix3d r;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+  return r;
+}
 template <int A> Vector3d operator*(const Matrix3d& a, const Matrix<double, 3, 1, A>& x) {  // lazy coefficient-based product
   Vector3d r;
   for (int i = 0; i < 3; i++) r.v[i] = a.m[i][0] * x.v[0] + a.m[i][1] * x.v[1] + a.m[i][2] * x.v[2];
   return r;
 }
+
+template <int O> class Matrix<double, 2, 1, O> {
+ public:
+  double v[2];
+  Matrix() : v{0, 0} {}
+  Matrix(double x, double y) : v{x, y} {}
+  double operator()(int i) const { return v[i]; }
+  double& operator()(int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  double& operator[](int i) { return v[i]; }
+};
+typedef Matrix<double, 2, 1, 0> Vector2d;
+inline Vector2d operator-(const Vector2d& a, const Vector2d& b) { return Vector2d(a.v[0] - b.v[0], a.v[1] - b.v[1]); }
+template <int O> class Matrix<double, 6, 1, O> {
+ public:
+  double v[6];
+  Matrix() : v{0, 0, 0, 0, 0, 0} {}
+  double operator[](int i) const { return v[i]; }
+  double& operator[](int i) { return v[i]; }
+};
+template <int O> class Matrix<double, 2, 6, O> {
+ public:
+  double m[2][6];
+  Matrix() : m{{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}} {}
+  double& operator()(int i, int j) { return m[i][j]; }
+  double operator()(int i, int j) const { return m[i][j]; }
+};
 
 template <typename S, int O = 0> class Quaternion;
 template <int O> class Quaternion<double, O> {
@@ -100,6 +147,42 @@ template <int O> class Quaternion<double, O> {
   Quaternion() : qx(0), qy(0), qz(0), qw(1) {}
   Quaternion(double w, double x, double y, double z) : qx(x), qy(y), qz(z), qw(w) {}
   template <int O2> Quaternion(const Quaternion<double, O2>& o) : qx(o.qx), qy(o.qy), qz(o.qz), qw(o.qw) {}
+  explicit Quaternion(const Matrix<double, 3, 3, 0>& mat) {   // Eigen quaternionbase_assign_impl<Matrix3>: trace-based conversion
+    const double (*m)[3] = mat.m;
+    double t = m[0][0] + m[1][1] + m[2][2];
+    if (t > 0) {
+      t = std::sqrt(t + 1.0);
+      qw = 0.5 * t;
+      t = 0.5 / t;
+      qx = (m[2][1] - m[1][2]) * t;
+      qy = (m[0][2] - m[2][0]) * t;
+      qz = (m[1][0] - m[0][1]) * t;
+    } else {
+      int i = 0;
+      if (m[1][1] > m[0][0]) i = 1;
+      if (m[2][2] > m[i][i]) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+      double q[3];
+      q[i] = 0.5 * t;
+      t = 0.5 / t;
+      qw = (m[k][j] - m[j][k]) * t;
+      q[j] = (m[j][i] + m[i][j]) * t;
+      q[k] = (m[k][i] + m[i][k]) * t;
+      qx = q[0]; qy = q[1]; qz = q[2];
+    }
+  }
+  void setIdentity() { qx = qy = qz = 0; qw = 1; }
+  double squaredNorm() const { return qx * qx + qy * qy + qz * qz + qw * qw; }
+  double norm() const { return std::sqrt(squaredNorm()); }
+  void normalize() { const double n = norm(); qx /= n; qy /= n; qz /= n; qw /= n; }
+  struct Coeffs {   // coeffs() in Eigen's storage order x, y, z, w
+    Quaternion* q;
+    Coeffs& operator*=(double s) { q->qx *= s; q->qy *= s; q->qz *= s; q->qw *= s; return *this; }
+  };
+  Coeffs coeffs() { return Coeffs{this}; }
+  template <int O2> Quaternion& operator*=(const Quaternion<double, O2>& b) { *this = Quaternion(*this * b); return *this; }
+  template <int A> Matrix<double, 3, 1, 0> operator*(const Matrix<double, 3, 1, A>& v) const { return _transformVector(v); }
   Quaternion<double, 0> conjugate() const { return Quaternion<double, 0>(qw, -qx, -qy, -qz); }
   double w() const { return qw; }
   double x() const { return qx; }

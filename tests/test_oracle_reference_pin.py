@@ -518,3 +518,33 @@ def test_host_trajectory_postprocessing_equals_the_reference_source(ref, sigma, 
     want = np.r_[0.0, rt[1:] / (dt[1:] + 1e-10)]
     assert np.max(np.abs(ht - want)) <= 1e-9 * max(1.0, np.abs(want).max())     # acos near 1 amplifies the last bits of the cosine
     assert np.abs(rt).max() > 1e-3
+
+
+def test_pose_optimization_edge_arithmetic_equals_the_g2o_source(ref):
+    """The per-edge arithmetic Optimizer::PoseOptimization relies on, compiled from the reference's vendored g2o:
+    VertexSE3Expmap::oplusImpl (SE3Quat::exp * estimate: se3quat.h:223-257, 104-110, 280-285), the reprojection error and its
+    2 x 6 Jacobian (types_six_dof_expmap.h:153-157, .cpp:266-296), the Huber kernel (robust_kernel_impl.cpp:78-91), against
+    the corresponding pieces of oracle/pgo_pose.cc.  (The LM driver and the 6 x 6 solve stay restatements: they need g2o's
+    optimizer graph and the real Eigen -- PoseOptimization as a whole remains 'parity unpinned'.)"""
+    l = O.lib()
+    rng = np.random.default_rng(10)
+    worst = 0.0
+    for it in range(300):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        if it % 3 == 0: q = -q
+        pose = np.r_[q, rng.normal(0, 2, 3)]
+        upd = rng.normal(0, 1, 6) * 10.0 ** rng.integers(-9, 1)
+        if it % 10 == 0: upd[:3] *= 1e-7                                    # the small-angle branch (theta < 1e-5)
+        ro = np.zeros(7); oo = np.zeros(7)
+        ref.pgr_se3_oplus(upd.ctypes.data_as(f64p), pose.ctypes.data_as(f64p), ro.ctypes.data_as(f64p))
+        l.pgo_pose_se3_oplus(upd.ctypes.data_as(f64p), pose.ctypes.data_as(f64p), oo.ctypes.data_as(f64p))
+        assert np.array_equal(ro, oo), (it, ro, oo)
+        X = rng.normal(0, 3, 3) + np.array([0, 0, 8.0]); obs = rng.uniform(0, 1000, 2)
+        re_, rj = np.zeros(2), np.zeros(12); oe, oj = np.zeros(2), np.zeros(12)
+        args = (pose.ctypes.data_as(f64p), X.ctypes.data_as(f64p), obs.ctypes.data_as(f64p), C.c_double(718.0), C.c_double(716.5), C.c_double(607.0), C.c_double(185.0))
+        ref.pgr_pose_edge(*args, re_.ctypes.data_as(f64p), rj.ctypes.data_as(f64p))
+        l.pgo_pose_edge(*args, oe.ctypes.data_as(f64p), oj.ctypes.data_as(f64p))
+        assert np.array_equal(re_, oe) and np.array_equal(rj, oj), it
+        e = float(10.0 ** rng.uniform(-3, 3)); rr, orr = np.zeros(3), np.zeros(3)
+        ref.pgr_huber(C.c_double(2.4477), C.c_double(e), rr.ctypes.data_as(f64p)); l.pgo_pose_huber(C.c_double(2.4477), C.c_double(e), orr.ctypes.data_as(f64p))
+        assert np.array_equal(rr, orr)
