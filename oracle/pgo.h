@@ -54,6 +54,19 @@ void pgo_pose_se3_oplus(const double* update6, const double* pose7, double* out7
 void pgo_pose_edge(const double* pose7, const double* Xw, const double* obs, double fx, double fy, double cx, double cy, double* err2,
                    double* J12);
 void pgo_pose_huber(double delta, double e, double* rho3);
+void* pgo_pose_problem_create(const float* Tcw, const float* kp_xy, const int32_t* kp_octave, const float* mp_xyz,
+                              const uint8_t* has_map_point, int n, const float* inv_level_sigma2, float fx, float fy, float cx,
+                              float cy, int robust);
+void pgo_pose_problem_destroy(void* h);
+void pgo_pose_problem_reset(void* h, const float* Tcw);
+void pgo_pose_problem_get_estimate(void* h, double* pose7);
+void pgo_pose_problem_set_estimate(void* h, const double* pose7);
+void pgo_pose_problem_compute_active_errors(void* h);
+double pgo_pose_problem_active_robust_chi2(void* h);
+void pgo_pose_problem_build_system(void* h, double* H36, double* b6);
+int pgo_pose_ldlt6_solve(const double* H36, const double* b6, double* x6);
+void pgo_pose_problem_oplus(void* h, const double* x6);
+void pgo_pose_problem_optimize(void* h, int iterations);
 int pgo_pose_optimization(const float* Tcw_in, const float* kp_xy, const int32_t* kp_octave, const float* mp_xyz,
                           const uint8_t* has_map_point, int n, const float* inv_level_sigma2, float fx, float fy, float cx,
                           float cy, float* Tcw_out, uint8_t* outlier, uint8_t* round_outliers);

@@ -14,8 +14,9 @@
 // are restated from their published algorithms.  PARITY UNPINNED against the real g2o/Eigen as a whole: the reference
 // holds no test or golden vector for this function.  Pins: (a) the per-edge arithmetic -- SE3Quat::exp * estimate, the
 // reprojection error and its 2x6 Jacobian, the Huber kernel -- is bit-identical to the g2o sources compiled in place
-// (oracle/_ref, tests/test_oracle_reference_pin.py); the LM driver, the quadratic form and the 6x6 LDLT stay restatements
-// (they need g2o's optimizer graph on the real Eigen), held by (b) recovery of the true pose on synthetic scenes and (c)
+// (oracle/_ref, tests/test_oracle_reference_pin.py), and lm_solve() gives bit-identical poses to g2o's own
+// OptimizationAlgorithmLevenberg::solve compiled from source and run on these primitives; the quadratic form, the 6x6 LDLT
+// and the outer four-round loop stay restatements (they need g2o's optimizer graph on the real Eigen), held by (b) recovery of the true pose on synthetic scenes and (c)
 // an independent scipy least-squares fit on the same inlier set (tests/test_oracle_pose.py).
 #include <cfloat>
 #include <cmath>
@@ -411,5 +412,63 @@ void pgo_pose_huber(double delta, double e, double* rho3) {
   P.delta = delta; P.dsqr = delta * delta;
   P.robustify(e, rho3);
 }
+
+// ---- a Problem as a handle, one primitive per call: lets the g2o Levenberg-Marquardt driver compiled from source
+// (oracle/_ref, ref_wrap_g2o_lm.cc) run on exactly the arithmetic lm_solve() uses, so that a difference between the two
+// can only come from the driver's control flow.
+void* pgo_pose_problem_create(const float* Tcw, const float* kp_xy, const int32_t* kp_octave, const float* mp_xyz,
+                              const uint8_t* has_map_point, int n, const float* inv_level_sigma2, float fx, float fy, float cx,
+                              float cy, int robust) {
+  Problem* P = new Problem;
+  P->fx = fx; P->fy = fy; P->cx = cx; P->cy = cy;
+  P->delta = (float)std::sqrt(5.991);
+  P->dsqr = P->delta * P->delta;
+  for (int i = 0; i < n; i++) {
+    if (!has_map_point[i]) continue;
+    Edge e;
+    e.obs[0] = kp_xy[2 * i]; e.obs[1] = kp_xy[2 * i + 1];
+    e.info = inv_level_sigma2[kp_octave[i]];
+    for (int k = 0; k < 3; k++) e.Xw[k] = mp_xyz[3 * i + k];
+    e.err[0] = e.err[1] = 0;
+    e.level = 0; e.robust = robust != 0; e.idx = i;
+    P->edges.push_back(e);
+  }
+  P->est = se3_from_cv(Tcw);
+  return P;
+}
+void pgo_pose_problem_destroy(void* h) { delete static_cast<Problem*>(h); }
+void pgo_pose_problem_reset(void* h, const float* Tcw) {
+  Problem* P = static_cast<Problem*>(h);
+  P->est = se3_from_cv(Tcw);
+  P->lambda = -1; P->ni = 2; P->nBad = 0;
+  for (int i = 0; i < 6; i++) P->x[i] = 0;
+}
+void pgo_pose_problem_get_estimate(void* h, double* pose7) {
+  const Problem* P = static_cast<Problem*>(h);
+  pose7[0] = P->est.r.w; pose7[1] = P->est.r.x; pose7[2] = P->est.r.y; pose7[3] = P->est.r.z;
+  for (int i = 0; i < 3; i++) pose7[4 + i] = P->est.t[i];
+}
+void pgo_pose_problem_set_estimate(void* h, const double* pose7) {
+  Problem* P = static_cast<Problem*>(h);
+  P->est.r = Quat{pose7[1], pose7[2], pose7[3], pose7[0]};
+  for (int i = 0; i < 3; i++) P->est.t[i] = pose7[4 + i];
+}
+void pgo_pose_problem_compute_active_errors(void* h) { static_cast<Problem*>(h)->compute_active_errors(); }
+double pgo_pose_problem_active_robust_chi2(void* h) { return static_cast<Problem*>(h)->active_robust_chi2(); }
+void pgo_pose_problem_build_system(void* h, double* H36, double* b6) {
+  double H[6][6];
+  static_cast<Problem*>(h)->build_system(H, b6);
+  memcpy(H36, H, sizeof H);
+}
+int pgo_pose_ldlt6_solve(const double* H36, const double* b6, double* x6) {
+  double H[6][6];
+  memcpy(H, H36, sizeof H);
+  return ldlt6_solve(H, b6, x6) ? 1 : 0;
+}
+void pgo_pose_problem_oplus(void* h, const double* x6) {   // VertexSE3Expmap::oplusImpl on the current estimate
+  Problem* P = static_cast<Problem*>(h);
+  P->est = se3_mul(se3_exp(x6), P->est);
+}
+void pgo_pose_problem_optimize(void* h, int iterations) { static_cast<Problem*>(h)->optimize(iterations); }   // the restated driver
 
 }  // extern "C"
