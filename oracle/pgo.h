@@ -67,6 +67,15 @@ void pgo_pose_problem_build_system(void* h, double* H36, double* b6);
 int pgo_pose_ldlt6_solve(const double* H36, const double* b6, double* x6);
 void pgo_pose_problem_oplus(void* h, const double* x6);
 void pgo_pose_problem_optimize(void* h, int iterations);
+void* pgo_pose_problem_create_raw(int n, const double* obs2, const double* Xw3, const double* info, double fx, double fy, double cx,
+                                  double cy, double delta);
+void pgo_pose_problem_edge_set_level(void* h, int k, int level);
+void pgo_pose_problem_edge_set_robust(void* h, int k, int robust);
+void pgo_pose_problem_edge_compute_error(void* h, int k);
+double pgo_pose_problem_edge_chi2(void* h, int k);
+int pgo_pose_problem_num_active(void* h);
+void pgo_pose_T_to_pose7(const float* T, double* pose7);
+void pgo_pose_pose7_to_T(const double* pose7, float* T);
 int pgo_pose_optimization(const float* Tcw_in, const float* kp_xy, const int32_t* kp_octave, const float* mp_xyz,
                           const uint8_t* has_map_point, int n, const float* inv_level_sigma2, float fx, float fy, float cx,
                           float cy, float* Tcw_out, uint8_t* outlier, uint8_t* round_outliers);

@@ -15,8 +15,10 @@
 // holds no test or golden vector for this function.  Pins: (a) the per-edge arithmetic -- SE3Quat::exp * estimate, the
 // reprojection error and its 2x6 Jacobian, the Huber kernel -- is bit-identical to the g2o sources compiled in place
 // (oracle/_ref, tests/test_oracle_reference_pin.py), and lm_solve() gives bit-identical poses to g2o's own
-// OptimizationAlgorithmLevenberg::solve compiled from source and run on these primitives; the quadratic form, the 6x6 LDLT
-// and the outer four-round loop stay restatements (they need g2o's optimizer graph on the real Eigen), held by (b) recovery of the true pose on synthetic scenes and (c)
+// OptimizationAlgorithmLevenberg::solve compiled from source and run on these primitives, and pgo_pose_optimization() gives
+// identical inlier counts, outlier flags and pose bit patterns to the body of Optimizer::PoseOptimization compiled from
+// Optimizer.cc:239-451; the quadratic form, the robust-chi2 sum and the 6x6 LDLT stay restatements (they need g2o's
+// optimizer graph on the real Eigen), held by (b) recovery of the true pose on synthetic scenes and (c)
 // an independent scipy least-squares fit on the same inlier set (tests/test_oracle_pose.py).
 #include <cfloat>
 #include <cmath>
@@ -470,5 +472,43 @@ void pgo_pose_problem_oplus(void* h, const double* x6) {   // VertexSE3Expmap::o
   P->est = se3_mul(se3_exp(x6), P->est);
 }
 void pgo_pose_problem_optimize(void* h, int iterations) { static_cast<Problem*>(h)->optimize(iterations); }   // the restated driver
+
+// ---- more handle primitives, for the outer four-round loop of Optimizer.cc:239-451 compiled from source (ref_wrap_poseopt.cc)
+void* pgo_pose_problem_create_raw(int n, const double* obs2, const double* Xw3, const double* info, double fx, double fy, double cx,
+                                  double cy, double delta) {
+  Problem* P = new Problem;
+  P->fx = fx; P->fy = fy; P->cx = cx; P->cy = cy; P->delta = delta; P->dsqr = delta * delta;
+  for (int i = 0; i < n; i++) {
+    Edge e;
+    e.obs[0] = obs2[2 * i]; e.obs[1] = obs2[2 * i + 1];
+    for (int k = 0; k < 3; k++) e.Xw[k] = Xw3[3 * i + k];
+    e.info = info[i];
+    e.err[0] = e.err[1] = 0; e.level = 0; e.robust = true; e.idx = i;
+    P->edges.push_back(e);
+  }
+  P->est.r = Quat{0, 0, 0, 1};
+  P->est.t[0] = P->est.t[1] = P->est.t[2] = 0;
+  return P;
+}
+void pgo_pose_problem_edge_set_level(void* h, int k, int level) { static_cast<Problem*>(h)->edges[k].level = level; }
+void pgo_pose_problem_edge_set_robust(void* h, int k, int robust) { static_cast<Problem*>(h)->edges[k].robust = robust != 0; }
+void pgo_pose_problem_edge_compute_error(void* h, int k) { Problem* P = static_cast<Problem*>(h); P->compute_error(P->edges[k]); }
+double pgo_pose_problem_edge_chi2(void* h, int k) { return Problem::chi2(static_cast<Problem*>(h)->edges[k]); }
+int pgo_pose_problem_num_active(void* h) {
+  int n = 0;
+  for (const Edge& e : static_cast<Problem*>(h)->edges) n += e.level == 0;
+  return n;
+}
+void pgo_pose_T_to_pose7(const float* T, double* pose7) {   // Converter::toSE3Quat
+  const SE3 s = se3_from_cv(T);
+  pose7[0] = s.r.w; pose7[1] = s.r.x; pose7[2] = s.r.y; pose7[3] = s.r.z;
+  for (int i = 0; i < 3; i++) pose7[4 + i] = s.t[i];
+}
+void pgo_pose_pose7_to_T(const double* pose7, float* T) {   // Converter::toCvMat(SE3Quat)
+  SE3 s;
+  s.r = Quat{pose7[1], pose7[2], pose7[3], pose7[0]};
+  for (int i = 0; i < 3; i++) s.t[i] = pose7[4 + i];
+  se3_to_cv(s, T);
+}
 
 }  // extern "C"

@@ -140,6 +140,24 @@ template <int O> class Matrix<double, 2, 6, O> {
   double operator()(int i, int j) const { return m[i][j]; }
 };
 
+// `v << a, b, c;` (Eigen's comma initialiser) for the fixed vectors Optimizer.cc fills that way
+template <typename V> struct CommaInit {
+  V* v;
+  int i;
+  CommaInit& operator,(double x) { (*v)[i++] = x; return *this; }
+};
+template <int O> CommaInit<Matrix<double, 2, 1, O> > operator<<(Matrix<double, 2, 1, O>& v, double x) { v[0] = x; return CommaInit<Matrix<double, 2, 1, O> >{&v, 1}; }
+template <int O> CommaInit<Matrix<double, 3, 1, O> > operator<<(Matrix<double, 3, 1, O>& v, double x) { v[0] = x; return CommaInit<Matrix<double, 3, 1, O> >{&v, 1}; }
+template <int O> class Matrix<double, 2, 2, O> {
+ public:
+  double m[2][2];
+  Matrix() : m{{0, 0}, {0, 0}} {}
+  static Matrix Identity() { Matrix r; r.m[0][0] = r.m[1][1] = 1; return r; }
+  double operator()(int i, int j) const { return m[i][j]; }
+};
+typedef Matrix<double, 2, 2, 0> Matrix2d;
+inline Matrix2d operator*(const Matrix2d& a, double s) { Matrix2d r; for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) r.m[i][j] = a.m[i][j] * s; return r; }
+
 template <typename S, int O = 0> class Quaternion;
 template <int O> class Quaternion<double, O> {
  public:

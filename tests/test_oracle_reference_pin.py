@@ -574,3 +574,28 @@ def test_levenberg_marquardt_driver_equals_the_g2o_source(ref, robust):
             assert np.array_equal(eo, er), (seed, iters, eo, er)
             assert iters < 3 or np.abs(eo - np.r_[1, 0, 0, 0, 0, 0, 0]).max() > 1e-3
             l.pgo_pose_problem_destroy(po); l.pgo_pose_problem_destroy(pr)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(n=1000, outlier_frac=0.3), dict(n=150, noise=2.0), dict(n=700, perturb=(0.05, 0.4)),
+                                dict(n=60, n_mp=8, outlier_frac=0.0), dict(n=50, n_mp=2), dict(n=40, n_mp=3, outlier_frac=0.0),
+                                dict(n=200, outlier_frac=0.9)])
+def test_pose_optimization_body_equals_the_reference_source(ref, kw):
+    """The body of Optimizer::PoseOptimization (thirdparty/orb-slam2/src/Optimizer.cc:239-451), compiled from the reference's
+    file behind class shells whose optimize() runs g2o's own LM driver from source: same inlier count, same mvbOutlier,
+    same pose (float bit patterns) as the oracle's restatement -- which observations become edges, the four rounds
+    restarting from mTcw, chi2 classification with re-evaluated outliers, levels, the robust kernel dropped after round
+    three, the < 3 and < 10 exits."""
+    import pose_util as U
+    ref.pgr_pose_optimization.restype = C.c_int
+    for seed in range(5):
+        S = U.scene(500 + seed, **kw)
+        a = lambda x, t: np.ascontiguousarray(x, t)
+        T0, xy, oc, X, has = a(S["T0"], np.float32), a(S["xy"], np.float32), a(S["octave"], np.int32), a(S["Xw"], np.float32), a(S["has"], np.uint8)
+        n = len(oc)
+        on, oT, oout, _ = O.pose_optimization(T0, xy, oc, X, has, U.INV_SIGMA2, U.FX, U.FY, U.CX, U.CY)
+        rT = np.zeros(16, np.float32); rout = np.zeros(max(n, 1), np.uint8)
+        rn = ref.pgr_pose_optimization(_v(T0), _v(xy), _v(oc), _v(X), _v(has), n, _v(U.INV_SIGMA2), 8, C.c_float(U.FX), C.c_float(U.FY),
+                                       C.c_float(U.CX), C.c_float(U.CY), _v(rT), _v(rout))
+        assert rn == on, (seed, rn, on)
+        assert np.array_equal(rout[:n], oout)
+        assert np.array_equal(rT.reshape(4, 4).view(np.uint32), np.ascontiguousarray(oT, np.float32).view(np.uint32)), (seed, rT.reshape(4, 4), oT)
