@@ -141,6 +141,8 @@ def test_oracle_objective_equals_the_reference_source(ref, hz, interleaved):
             assert np.isfinite(fr) and fr > 0
             assert abs(fo - fr) <= 1e-12 * abs(fr), (fo, fr)
             assert np.max(np.abs(go - gr)) <= 1e-12 * np.max(np.abs(gr)), (go, gr)
+            fc, gc = orc.eval(x, core=True)      # the arithmetic contract the CUDA kernels are compiled from (include/pgb200_imu_core.h)
+            assert abs(fc - fr) <= 1e-12 * abs(fr) and np.max(np.abs(gc - gr)) <= 1e-12 * np.max(np.abs(gr))
             io, so, qo, vo, do = orc.integrate(x)
             ir, qr, vr, dr = rc.integrate(x)
             assert np.array_equal(io, ir) and np.array_equal(do, dr) and len(ir) > 1000
