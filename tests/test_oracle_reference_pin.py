@@ -1,8 +1,13 @@
-"""The one piece of the path whose REAL reference source compiles here -- src/interpolation/align_time_series.cc
-(MergedTimeSeries, MakeInterpolationIntervals; its only external dependency is glog's CHECK macros, supplied by
-oracle/ref_shims) -- built where it lies into oracle/_ref/ (`make -C oracle _ref`) and run against the oracle's
-restatement on the same inputs.  Everything downstream of these indices (the calibration objective, the GPU kernels)
-is tested against the oracle, so this pins row a20 of SURVEY section 8 to the reference itself."""
+"""The REFERENCE'S OWN SOURCE against the oracle (and, for the trajectory post-processing, against the product's host code).
+
+`make -C oracle _ref` compiles, where they lie under /root/reference, every piece of the path that can be built without the
+absent third-party packages -- whole files where possible, checked line ranges streamed to the compiler otherwise, behind
+small stand-ins for OpenCV / Eigen / glog / nlohmann and shells of the ORB-SLAM2 / g2o classes (oracle/README.md, DESIGN.md
+section 2) -- into oracle/_ref/libpilotguru_ref.so.  The tests below feed both sides the same inputs:
+time-series alignment, the calibration objective, SmoothTimeSeries, LBFGS++, the ORB extractor (incl. a fuzz), every matcher
+flavour, the frame grid, ComputeDistinctiveDescriptors, the fit_motion window loop, the rotation-axis functions,
+time_series.hpp + the annotate loop, the trajectory post-processing, g2o's edge arithmetic and LM driver, and the body of
+Optimizer::PoseOptimization.  Skipped when neither /root/reference nor a prebuilt oracle/_ref is present."""
 import ctypes as C
 import os
 import subprocess
