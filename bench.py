@@ -29,14 +29,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H, NFEAT = 1920, 1080, 1000
-FAST_ALGO_BYTES_PER_FRAME = 2 * 6_419_321  # 8-level 1080p pyramid read once + u8 score map written once
-# dram__bytes_read.sum + dram__bytes_write.sum of k_fast_score per frame from the committed `ncu --set full` capture
-# (profiles/r01e_kernels_ncu_full.md: 209.1 MB read + 168.7 MB written over a 32-frame launch; part of the score map
-# is still dirty in L2 when the kernel ends, hence slightly below the algorithmic bytes)
-FAST_NCU_TRAFFIC_BYTES_PER_FRAME = (209.1e6 + 168.7e6) / 32
+PYRAMID_PX = 6_419_321                      # sum of the 8 level sizes of a 1080p frame
+# SURVEY.md 8(d), K2 unfused: pyramid read once + u8 score map written once -- the HBM work the fused kernel replaces
+# (and the denominator round 1's k_fast_score was quoted on)
+FAST_K2_BYTES_PER_FRAME = 2 * PYRAMID_PX
+# SURVEY.md 8(d), K2+K3 fused ("6,419,321 B read + 8 B x candidates written"; here 4 B per candidate slot + 4 B per cell count)
+N_CELLS = 6257
 WORKLOAD = ("ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + SearchByProjection vs previous "
             "frame (BASELINE configs[1], batched)")
-STAGES = ["pyramid", "fast_score", "cell_nms", "octree", "orient_desc"]
+# pgb_orb_run_stage ids: 0 pyramid, 1 FAST score + cell NMS (fused k_fast_cells), 3 octree, 4 orientation + descriptor;
+# 2 = the round-1 unfused pair (k_fast_score -> k_cells) recomputing the same candidates, timed for the A/B only
+STAGES = {"pyramid": 0, "fast_cells": 1, "octree": 3, "orient_desc": 4}
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_fast_cells_traffic.json")
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per FRAME of the dominant kernel, read from the summary that
+    tools/ncu_traffic.py wrote from the committed `ncu --set full` capture (None when there is no capture)."""
+    try:
+        t = json.load(open(TRAFFIC_JSON))
+        return (float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])) / float(t["frames_per_launch"]), t.get("source")
+    except Exception:
+        return None, None
 
 
 def env_int(name, default):
@@ -169,18 +183,38 @@ def cpu_frames(n):
     return fr, fl
 
 
-def cpu_run(n_frames, threads):
-    """The oracle (CPU port of the reference path) on `threads` host threads over n_frames synthetic frames."""
+def cpu_run(n_frames, threads, frames=None, flows=None):
+    """The oracle (CPU port of the reference path, `-O3 -march=native` build made on this host) on `threads` host threads
+    over n_frames synthetic frames: extraction of every frame, then the match of EVERY consecutive pair.  Returns
+    (seconds, keypoints per frame, matches per frame [entry 0 = -1], build description)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    distinct = min(n_frames, 16)
-    fr, fl = cpu_frames(distinct)
+    build = O.native_lib()[1]
+    if frames is None:
+        frames, flows = cpu_frames(min(n_frames, 16))
+    distinct = len(frames)
+    fr, fl = frames, flows
     if n_frames > distinct:
-        reps = (n_frames + distinct - 1) // distinct
-        fr = np.concatenate([fr] * reps)[:n_frames]; fl = np.concatenate([fl] * reps)[:n_frames]
-    O.bench_extract_match(fr[:min(threads, n_frames)], fl[:min(threads, n_frames)], threads)  # warm: page in, spin threads
-    sec, nk, nm = O.bench_extract_match(fr, fl, threads)
-    return sec, nk, nm
+        # ping-pong over the distinct frames (0..d-1, d-2..0, 1..): consecutive frames stay consecutive, so every pair is
+        # an ordinary small-flow pair; going backwards the flow is minus the forward flow of the later frame
+        idx, sign = [], []
+        i, step = 0, 1
+        for _ in range(n_frames):
+            idx.append(i); sign.append(step)
+            if i + step < 0 or i + step >= distinct:
+                step = -step
+            i += step
+        idx = np.array(idx)
+        fr = frames[idx]
+        fl = np.zeros((n_frames, 2), np.float32)
+        for k in range(1, n_frames):
+            a, b = idx[k - 1], idx[k]
+            fl[k] = flows[b] if b > a else (-flows[a] if b < a else 0)
+    else:
+        fr, fl = frames[:n_frames], flows[:n_frames]
+    O.bench_extract_match(fr[:min(threads, n_frames)], fl[:min(threads, n_frames)], threads, native=True)  # warm: page in, spin threads
+    sec, _, _, nk, nm = O.bench_extract_match(fr, fl, threads, per_frame=True, native=True)
+    return sec, nk, nm, build
 
 
 def calibration_leg(device, seconds, hz):
@@ -217,19 +251,21 @@ def run_reference(args):
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_step = max(32, min(8 * cores, 256))  # ~10-20 s of CPU work per step at ~14 frames/s/core
+    frames, flows = cpu_frames(16)
+    build = ""
     for _ in range(min(args.warmup, 1)):
-        cpu_run(per_step, cores)
+        cpu_run(per_step, cores, frames, flows)
     tot_s, tot_f = 0.0, 0
     for _ in range(args.steps):
-        s, _, _ = cpu_run(per_step, cores)
+        s, _, _, build = cpu_run(per_step, cores, frames, flows)
         tot_s += s; tot_f += per_step
     v = tot_f / tot_s
     line = {"impl": "reference", "metric": "1080p frames/sec ORB extract+match", "value": v, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": per_step},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} frames per step x {args.steps} steps, oracle/liboracle.so on {cores} host threads"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "build": build,
+                             "sample": f"{per_step} frames per step x {args.steps} steps (extract every frame + match every consecutive pair), oracle on {cores} host threads"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -289,7 +325,8 @@ def main():
 
     # ---- synthetic input: B distinct frames per rank (rank r holds frames r*B .. r*B+B-1 of the sequence)
     t0 = rank * B
-    host_frames = torch.from_numpy(np.stack([synth.frame(t0 + i) for i in range(B)])).pin_memory()
+    frames_np = np.stack([synth.frame(t0 + i) for i in range(B)])
+    host_frames = torch.from_numpy(frames_np).pin_memory()
     flows_np = np.array([synth.flow(t0 + i) for i in range(B)], np.float32)  # flow into frame i from frame i-1
     dev_frames = host_frames.cuda(non_blocking=False)
 
@@ -420,6 +457,23 @@ def main():
         launches = launch_count() - l0
         ex.check()
         nm_dev = nmatch.cpu().numpy().copy(); cnt_dev = xch.counts_view().cpu().numpy().copy()
+        cand_total = sum(len(ex.candidates(l, frame=0)) for l in range(8)) * B   # candidates handed to the octree (frame 0 x B)
+        # ---- N > 1: rank r's pair 0 (its first frame against the LEFT NEIGHBOUR's last frame, received through the
+        # exchange) must equal a local recomputation with the true predecessor frame t0 - 1 extracted here
+        parity = {"checked": False}
+        if world > 1:
+            got_m = match[0].clone(); got_n = nmatch[0:1].clone()
+            ex.extract_ptr(pred.data_ptr(), 3, 1, W, H, W, W * H, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), cap)
+            m1 = torch.full((1, cap), -1, dtype=torch.int32, device="cuda"); n1 = torch.zeros(1, dtype=torch.int32, device="cuda")
+            mt.match_consecutive_ptr(1, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), flow_dev.data_ptr(),
+                                     float(W), float(H), 15.0, sf, m1.data_ptr(), n1.data_ptr())
+            ex.check()
+            ok = torch.tensor([int(torch.equal(m1[0], got_m) and torch.equal(n1, got_n) and int(n1.item()) >= 20)], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            parity = {"checked": True, "cross_rank_pair0_equals_local_recompute": bool(ok.item())}
+            if not ok.item():
+                raise SystemExit("bench.py: a rank's boundary pair differs from the local recomputation with the true predecessor")
+            dev_step()                                                      # restore the exchanged state
 
         e2e_run(3)
         if sampler:
@@ -437,12 +491,14 @@ def main():
 
         # ---- per-stage times and the FAST kernel roofline (same resident batch, events on the launching stream)
         stage_us = {}
-        for which, name in enumerate(STAGES):
+        for name, which in list(STAGES.items()) + [("unfused_fast_score_plus_cell_nms", 2)]:
             for _ in range(2):
                 ex.run_stage(which)
             reps = 10
             t = timed(lambda: ex.run_stage(which), reps)
             stage_us[name] = 1e3 * t / reps / B
+        ex.check()
+        unfused_us = stage_us.pop("unfused_fast_score_plus_cell_nms")
         match_fn = lambda: mt.match_consecutive_ptr(B, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0),
                                                     flow_dev.data_ptr(), float(W), float(H), 15.0, sf,
                                                     match.data_ptr(), nmatch.data_ptr())
@@ -452,8 +508,11 @@ def main():
     value = frames_total * K / (ms * 1e-3)
     e2e = frames_total * K / (ms_e2e * 1e-3)
     peak, peak_src = measured_peaks()
-    fast_s = stage_us["fast_score"] * 1e-6 * B
-    achieved = FAST_ALGO_BYTES_PER_FRAME * B / fast_s / 1e9
+    fast_s = stage_us["fast_cells"] * 1e-6 * B
+    achieved = FAST_K2_BYTES_PER_FRAME * B / fast_s / 1e9
+    cand_per_frame = float(cand_total) / B
+    fused_bytes = PYRAMID_PX + 4 * (N_CELLS + cand_per_frame)
+    traffic_pf, traffic_src = ncu_traffic()
     h2d = int(host_frames.numel())
     s0 = sets[0]
     d2h = int(s0.h_counts.numel() * 4 + s0.h_kps.numel() * 4 + s0.h_desc.numel() + s0.h_match.numel() * 4 + s0.h_nmatch.numel() * 4)
@@ -484,19 +543,39 @@ def main():
                         "h2d_only_gbs": h2d / (ms_h2d * 1e-3) / 1e9},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
-                "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": FAST_NCU_TRAFFIC_BYTES_PER_FRAME * B, "peak_source": peak_src,
-                             "traffic_source": "ncu --set full capture, profiles/r01e_kernels_ncu_full.md, scaled to this launch",
-                             "algorithmic_bytes_per_launch": FAST_ALGO_BYTES_PER_FRAME * B,
-                             "us_per_launch": stage_us["fast_score"] * B},
+                "roofline": {"kernel": "k_fast_cells (FAST-9 score + per-cell NMS + threshold decision, fused)", "bound": "hbm",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic_pf * B if traffic_pf else None, "peak_source": peak_src,
+                             "traffic_source": traffic_src,
+                             "algorithmic_bytes_per_launch": FAST_K2_BYTES_PER_FRAME * B,
+                             "algorithmic_bytes_note": "SURVEY 8(d) K2 figure (pyramid read + u8 score map written = 12,838,642 B/frame): "
+                                                       "the HBM work of the unfused score kernel this launch replaces; round 1 was quoted on it",
+                             "fused_formulation": {"algorithmic_bytes_per_launch": fused_bytes * B,
+                                                   "achieved": fused_bytes * B / fast_s / 1e9,
+                                                   "frac": fused_bytes * B / fast_s / 1e9 / peak,
+                                                   "note": "SURVEY 8(d) fused figure: pyramid read once + 4 B per candidate slot and per cell count; "
+                                                           "the score map is never written"},
+                             "us_per_launch": stage_us["fast_cells"] * B,
+                             "unfused_pair_us_per_frame": unfused_us},
                 "stage_us_per_frame": stage_us,
                 "keypoints_per_frame": float(cnt_dev[1:].mean()), "matches_per_frame": float(nm_dev.mean())}
+        line["parity_checked"] = parity["checked"]
+        line["parity"] = parity
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             n = max(64, min(16 * cores, 512))                              # ~15-30 s of CPU work (oracle: ~14 frames/s/core)
-            sec, _, _ = cpu_run(n, cores)
-            line["cpu_baseline"] = {"value": n / sec, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} synthetic 1080p frames, extract+match, oracle on {cores} host threads ({sec:.1f} s wall)"}
+            # the CPU leg runs the SAME frames the GPU leg held (frames 0..B-1, then ping-pong): per-frame keypoint counts
+            # and per-pair match counts of the first B frames are asserted against the GPU's, outside the timed regions
+            sec, nk, nm, build = cpu_run(n, cores, frames_np, flows_np)
+            m = min(n, B)
+            same = bool(np.array_equal(nk[:m], cnt_dev[1:m + 1]) and np.array_equal(nm[1:m], nm_dev[1:m]))
+            line["parity"].update({"checked": True, "frames_compared_with_cpu_leg": m, "keypoint_counts_equal": bool(np.array_equal(nk[:m], cnt_dev[1:m + 1])),
+                                   "match_counts_equal": bool(np.array_equal(nm[1:m], nm_dev[1:m]))})
+            line["parity_checked"] = True
+            if not same:
+                raise SystemExit(f"bench.py: GPU and CPU legs disagree: keypoints {cnt_dev[1:m + 1][:8]} vs {nk[:8]}, matches {nm_dev[1:m][:8]} vs {nm[1:m][:8]}")
+            line["cpu_baseline"] = {"value": n / sec, "unit": "frames/s", "cores": cores, "kind": "port", "build": build,
+                                    "sample": f"{n} synthetic 1080p frames (extract every frame + match every consecutive pair), oracle on {cores} host threads ({sec:.1f} s wall)"}
         if not args.no_calibration and world == 1:
             line["calibration"] = calibration_leg(local, args.calib_seconds, args.calib_hz)
         emit(line)

@@ -121,7 +121,8 @@ int pgo_time_averaged_values(const double* values, const int64_t* times, int64_t
                              double* out, uint8_t* valid);
 double pgo_bench_extract_match(const uint8_t* frames, int n, int w, int h, const float* flow_xy, int nfeatures,
                                float scale, int nlevels, int iniTh, int minTh, float th, int nthreads,
-                               int64_t* total_kps, int64_t* total_matches);
+                               int64_t* total_kps, int64_t* total_matches, int32_t* kps_per_frame,
+                               int32_t* matches_per_frame);
 #ifdef __cplusplus
 }
 #endif

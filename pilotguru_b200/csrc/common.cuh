@@ -103,4 +103,25 @@ struct TempBuf {
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair, not to a handle: one limit object
+// per kernel keeps the process-wide maximum ever requested on each device and only ever raises the attribute, so a
+// handle with a smaller capacity can never lower it under another handle (or thread) that relies on the larger value.
+struct DynSmemLimit {
+  std::atomic<size_t> perDevice[64];
+  DynSmemLimit() { for (auto& v : perDevice) v.store(0); }
+  template <typename F>
+  int ensure(F fn, size_t bytes) {
+    if (bytes <= 48 * 1024) return PGB_OK;
+    int dev = 0;
+    PGB_CUDA(cudaGetDevice(&dev));
+    std::atomic<size_t>& cur = perDevice[dev & 63];
+    size_t seen = cur.load();
+    while (bytes > seen) {
+      PGB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      if (cur.compare_exchange_weak(seen, bytes)) break;
+    }
+    return PGB_OK;
+  }
+};
+
 }  // namespace pgb

@@ -1,0 +1,392 @@
+// K2+K3 fused: FAST-9 score, per-cell 3x3 non-maximum suppression and the per-cell iniThFAST / minThFAST decision in
+// ONE kernel for sm_100a -- the score map never reaches HBM.
+// Reference: ORBextractor::ComputeKeyPointsOctTree, thirdparty/orb-slam2/src/ORBextractor.cc:765-829 (30-px cell grid,
+// cv::FAST(cell view, iniThFAST, nms=true), again with minThFAST when the cell came back empty) over cv::FAST(TYPE_9_16).
+//
+// Why this shape.  The round-1 pair k_fast_score -> k_cells wrote a 6.4 MB/frame score map (96.5 % zeros) and read it
+// back: 12.8 MB/frame of HBM traffic and 4.9 us/frame in k_cells, most of it spent finding the non-zero bytes again
+// (profiles/r01e_other_kernels_sass_regions.md).  What makes the fusion clean is the reference's own cell semantics:
+// cv::FAST runs on a cell VIEW, so a neighbour outside the cell's tested rectangle counts as score 0 in the 3x3 NMS,
+// and the tested rectangles of the cells tile the level exactly (pitch wCell x hCell from (19, 19)).
+// A tile made of WHOLE cells therefore needs no score halo at all:
+//   * one CTA (4 warps) = one row of up to 8 FAST cells: <= 249 x hCell tested pixels.  The input box (72 words x
+//     (8 * bands + 6) rows, 3-px ring halo) comes in with one 3-D TMA load; the box must start on a 16-byte boundary,
+//     the tile does not, so the 256-px "lane frame" (8 px per lane) starts at the 8-byte boundary at or below the
+//     tile's first pixel and per-lane validity masks cut the frame down to the tested rectangle;
+//   * prefilter / candidate expansion / exact score per 8-row band are the round-1 kernel's (fast_score.cu); the
+//     score goes into a shared-memory tile with a zero guard ring, and the scoring round also compacts the true
+//     corners (52 % of the scored candidates) IN PLACE into the warp's queue as (x, row, score) entries;
+//   * barrier; NMS over the corner lists, one corner per lane: 8 neighbour bytes from the shared tile, neighbours
+//     across a cell boundary masked to 0, survivors set a bit in a per-row bitmap (in the dead code bytes of the queue);
+//   * barrier; emission, warp = cell, lane = tested row: the row's survivor bits inside the cell's x-range, the
+//     subset with score >= iniThFAST, one warp vote for the cell's threshold (survivors at iniTh are exactly the
+//     survivors at minTh with score >= iniTh: one NMS pass serves both thresholds), one warp scan for the reference's
+//     row-major order, then the packed candidates go to the cell's slots -- the same slots / cellCnt layout k_cells
+//     produced, so the octree kernel is unchanged.
+// Algorithmic bytes per 1080p frame: 6,419,321 B read + 4 B x (cells + candidates) written (SURVEY.md 8d's fused figure).
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "fast_common.cuh"
+#include "orb_kernels.cuh"
+
+namespace pgb {
+
+namespace {
+
+using namespace fastk;
+
+constexpr int kRowB = kFcInWords * 4;  // 288 bytes per staged input row
+constexpr int kSP = kFcTilePitch;      // score tile: 16 pad bytes (x = -16 .. -1) + 256 px per row
+constexpr int kQCap = kFcQueueCap;
+
+__device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) { return fastk::fast_bam_minmax<kRowB>(c); }
+
+// One corner against its 8 neighbours in the shared score tile; p points at the corner's byte.  Rows above / below the
+// tile are zero guard rows; `first` / `last`: the corner sits in the first / last column of its cell.
+__device__ __forceinline__ bool nms_keep(const uint8_t* p, int s, bool first, bool last) {
+  const int nw = p[-kSP - 1], n = p[-kSP], ne = p[-kSP + 1];
+  const int w = p[-1], e = p[1];
+  const int sw = p[kSP - 1], so = p[kSP], se = p[kSP + 1];
+  int left = max(max(nw, w), sw), right = max(max(ne, e), se);
+  if (first) left = 0;
+  if (last) right = 0;
+  return max(max(left, right), max(n, so)) < s;
+}
+
+}  // namespace
+
+// kA = true: class A levels (wCell <= 32, hCell <= 32): 4 bands per tile, one per warp, 32-bit cell windows.
+// kA = false: any cell size (bands looped over the warps, 64-bit cell windows); used by the small levels whose cells
+// are larger (1080p: level 7 only) at a lower occupancy.
+template <bool kA, int kOcc>
+__global__ void __launch_bounds__(kFcThreads, kOcc) k_fast_cells(const __grid_constant__ OrbGeo g,
+                                                                 const __grid_constant__ TmapIn tm,
+                                                                 const int4* __restrict__ tileTab, int nbTile, int frame0,
+                                                                 uint32_t* __restrict__ slots, int* __restrict__ cellCnt,
+                                                                 int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nb = kA ? 4 : nbTile;  // bands the shared-memory layout holds
+  const FcSmem lay = fc_smem_layout(nb);
+  const uint8_t* sInB = smem;
+  uint8_t* sTile = smem + lay.tile + kSP + 16;  // (row 0, x 0) of the score tile
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.misc);
+  int* sCorner = reinterpret_cast<int*>(smem + lay.misc + 16);  // per band: corners in the list, or -1 = use the slow NMS
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y;
+  const int4 te = __ldg(&tileTab[blockIdx.x]);
+  const int level = te.x, X0 = te.y, Y0 = te.z, ci0 = te.w & 0xffff, cj0 = te.w >> 16;
+  const LevelGeo& L = g.lv[level];
+  const int wCell = L.wCell, hCell = L.hCell;
+  const int kc = min(L.fcKc, L.nCols - cj0);
+  const int X1 = min(X0 + kc * wCell, L.w - kEdge), Y1 = min(Y0 + hCell, L.h - kEdge);
+  int* cnt = cellCnt + (size_t)f * g.totalCells + L.cellBase + ci0 * L.nCols + cj0;
+  if (X1 <= X0 || Y1 <= Y0) {  // cells the reference skips (ORBextractor.cc:796-805) or whose view is too small for FAST
+    if (tid < kc) cnt[tid] = 0;
+    return;
+  }
+  const int xa = (X0 - 3) & ~15;           // first byte of the TMA box (level x), 16-byte aligned, <= X0 - 3
+  const int o = (X0 - xa) & ~7;            // lane frame: staged bytes [o, o + 256) of every row, 8-byte aligned
+  const int xoff = X0 - xa - o;            // tile's first tested pixel inside the lane frame: 0 .. 7
+  const int tw = X1 - X0, th = Y1 - Y0;    // tested pixels of the tile
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, (uint32_t)(kRowB * (nb * 8 + 6)));
+    tma_load_3d(smem, &tm.in[level], xa >> 2, Y0 - 3, f + frame0, bar);  // the maps index frames from the batch's base
+  }
+  // every warp zeroes the score rows of its bands (+ the guard row above the first / below the last band)
+  for (int b = warp; b < nb; b += kFcWarps) {
+    uint4* z = reinterpret_cast<uint4*>(smem + lay.tile + (8 * b + 1) * kSP);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = lane; i < 8 * kSP / 16; i += 32) z[i] = zero;
+    if (b == 0 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile)[lane] = zero;
+    if (b == nb - 1 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile + (8 * nb + 1) * kSP)[lane] = zero;
+  }
+  __syncthreads();  // mbarrier initialised before anyone polls it
+  while (!mbar_try_wait(bar, 0)) {
+  }
+
+  // ================================================================ score: per 8-row band (fast_score.cu's phases)
+  for (int b = warp; b < nb; b += kFcWarps) {
+    const int r0 = 8 * b;
+    uint32_t* q = reinterpret_cast<uint32_t*>(smem + lay.queue + b * kFcQueueBytes);  // one-hot flag, later corner entries
+    uint8_t* qc = reinterpret_cast<uint8_t*>(q + kQCap);                              // position code, later the band's bitmap
+    int nCorner = 0;
+    if (r0 < th) {
+      // validity masks of this lane's 8x8 block in the flag layout: byte b of a half-register holds pixels b (word A,
+      // bits 7,5,3,1 for rows 0..3 of the half) and 4+b (word B, bits 6,4,2,0)
+      uint32_t vmLo, vmHi;
+      {
+        const int a = min(max(xoff - 8 * lane, 0), 8), e = min(max(xoff + tw - 8 * lane, 0), 8);
+        const uint32_t m8 = e > a ? ((1u << e) - 1u) & ~((1u << a) - 1u) : 0u;  // bit i = pixel i of the lane is tested
+        const uint32_t sa = ((m8 & 15u) * 0x00204081u) & 0x01010101u;          // bit 0 of byte b = pixel b
+        const uint32_t sb = ((m8 >> 4) * 0x00204081u) & 0x01010101u;           // bit 0 of byte b = pixel 4+b
+        const uint32_t xm = sa * 0xAAu + sb * 0x55u;
+        uint32_t rl = 0, rh = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (r0 + j < th) rl |= 0xC0C0C0C0u >> (2 * j);
+          if (r0 + 4 + j < th) rh |= 0xC0C0C0C0u >> (2 * j);
+        }
+        vmLo = xm & rl;
+        vmHi = xm & rh;
+      }
+      // ---------------- phase 1: 64 prefilter flags per lane
+      uint32_t lo = 0, hi = 0;
+      if (__any_sync(0xffffffffu, (vmLo | vmHi) != 0)) {
+        uint32_t ra[14], rb[14];
+        const uint32_t* col = reinterpret_cast<const uint32_t*>(sInB + r0 * kRowB + o) + 2 * lane;
+#pragma unroll
+        for (int i = 0; i < 14; i++) {
+          const uint2 v = *reinterpret_cast<const uint2*>(col + i * kFcInWords);
+          ra[i] = v.x;
+          rb[i] = v.y;
+        }
+        const uint32_t one = g.one;
+        const uint32_t M = g.absMask;  // 0x80 - (minTh + 1) in every byte: x + M has its msb set iff x > minTh (x < 0x80)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int c = j + 3;
+          const uint32_t* crow = col + c * kFcInWords;
+          const uint32_t wl = crow[-1], wr = crow[2];  // lane 0 / o = 0: the word before the row -- only feeds untested pixels
+          const uint32_t cA = ra[c], cB = rb[c];
+          const uint32_t vA = __vabsdiffu4(ra[j], cA) | __vabsdiffu4(cA, ra[c + 3]);
+          const uint32_t vB = __vabsdiffu4(rb[j], cB) | __vabsdiffu4(cB, rb[c + 3]);
+          const uint32_t hA = __vabsdiffu4(cA, __byte_perm(wl, cA, 0x4321)) | __vabsdiffu4(cA, __byte_perm(cA, cB, 0x6543));
+          const uint32_t hB = __vabsdiffu4(cB, __byte_perm(cA, cB, 0x4321)) | __vabsdiffu4(cB, __byte_perm(cB, wr, 0x6543));
+          // msb of a byte: the absolute difference exceeds minTh.  x + M sets the msb for x in (minTh, 0x7f]; "| x"
+          // covers x >= 0x80; a carry out of a byte can only turn a neighbour's flag ON (over-accepting is harmless)
+          const uint32_t fA = (mad1(vA, one, M) | vA) & (mad1(hA, one, M) | hA);
+          const uint32_t fB = (mad1(vB, one, M) | vB) & (mad1(hB, one, M) | hB);
+          const int s = 2 * (j & 3);
+          const uint32_t bits = ((fA >> s) & (0x80808080u >> s)) | ((fB >> (s + 1)) & (0x80808080u >> (s + 1)));
+          if (j < 4) lo |= bits; else hi |= bits;
+        }
+        lo &= vmLo;
+        hi &= vmHi;
+      }
+      // ---------------- expansion: 4x4 byte transpose inside lane quads evens out the per-lane counts
+      {
+        const uint32_t sel1 = (lane & 1) ? 0x3715u : 0x6240u, sel2 = (lane & 2) ? 0x3276u : 0x5410u;
+        uint32_t x = __shfl_xor_sync(0xffffffffu, lo, 1), y = __shfl_xor_sync(0xffffffffu, hi, 1);
+        lo = __byte_perm(lo, x, sel1);
+        hi = __byte_perm(hi, y, sel1);
+        x = __shfl_xor_sync(0xffffffffu, lo, 2);
+        y = __shfl_xor_sync(0xffffffffu, hi, 2);
+        lo = __byte_perm(lo, x, sel2);
+        hi = __byte_perm(hi, y, sel2);
+      }
+      const int cntL = __popc(lo) + __popc(hi);
+      int incl = cntL;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      // Normally the band's candidates fit the queue in one pass; otherwise (noise images) one pass per row (<= 256) and
+      // the NMS of this band takes the slow path (the corner list cannot live in a queue that is refilled)
+      const int nParts = total <= kQCap ? 1 : 8;
+      uint8_t* band = sTile + r0 * kSP;
+      for (int part = 0; part < nParts; part++) {
+        uint32_t mlo = lo, mhi = hi;
+        int pos = incl - cntL, T = total;
+        if (nParts > 1) {
+          const uint32_t rm = 0xC0C0C0C0u >> (2 * (part & 3));
+          mlo = part < 4 ? (lo & rm) : 0u;
+          mhi = part < 4 ? 0u : (hi & rm);
+          const int c2 = __popc(mlo) + __popc(mhi);
+          int in2 = c2;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, in2, d);
+            if (lane >= d) in2 += t;
+          }
+          T = __shfl_sync(0xffffffffu, in2, 31);
+          pos = in2 - c2;
+        }
+        const uint8_t pcode = (uint8_t)((lane & 28) * 8 + (lane & 3));  // x of (source-lane quad, column); bit 2 = half
+        uint32_t* qp = q + pos;
+        uint8_t* qcp = qc + pos;
+        while (mlo) {
+          const uint32_t low = mlo & (0u - mlo);
+          mlo ^= low;
+          *qp++ = low;
+          *qcp++ = pcode;
+        }
+        while (mhi) {
+          const uint32_t low = mhi & (0u - mhi);
+          mhi ^= low;
+          *qp++ = low;
+          *qcp++ = (uint8_t)(pcode | 4);
+        }
+        __syncwarp();
+        // ---------------- phase 2: exact score, one candidate per lane; true corners are compacted in place
+        for (int base = 0; base < T; base += 32) {
+          const int i = base + lane;
+          bool corner = false;
+          uint32_t entry = 0;
+          if (i < T) {
+            const uint32_t low = q[i], c = qc[i];
+            const uint32_t bit = 31u - (uint32_t)__clz(low), u = bit ^ 7u;  // u & 7 = 2 * (row in half) + word
+            const int row = (int)(c & 4u) + (int)((u >> 1) & 3u);
+            const int x = (int)((c & 0xE3u) + (bit & 0x18u) + ((u & 1u) << 2));  // (lane quad)*32 + (source lane)*8 + word*4 + byte
+            const int bam = fast_bam_minmax(sInB + (r0 + row + 3) * kRowB + o + x);
+            if (bam > g.minTh) {
+              band[row * kSP + x] = (uint8_t)(bam - 1);
+              corner = true;
+              entry = (uint32_t)x | ((uint32_t)(r0 + row) << 8) | ((uint32_t)(bam - 1) << 16);
+            }
+          }
+          if (nParts == 1) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, corner);  // (also orders this round's queue reads before the writes)
+            if (corner) q[nCorner + __popc(bal & ((1u << lane) - 1u))] = entry;
+            nCorner += __popc(bal);
+          }
+        }
+        __syncwarp();
+      }
+      if (nParts > 1) nCorner = -1;
+    }
+    // the band's survivor bitmap (8 rows x 256 bits) lives in the queue's code bytes, dead from here on
+    __syncwarp();
+    reinterpret_cast<uint2*>(qc)[lane] = make_uint2(0u, 0u);
+    if (lane == 0) sCorner[b] = nCorner;
+  }
+  __syncthreads();  // every score of the tile is in shared memory
+
+  // ================================================================ NMS: 3x3 inside the corner's own cell
+  const uint32_t recip = L.fcRecip;  // (x * recip) >> 16 = x / wCell for x < 1024
+  for (int b = warp; b < nb; b += kFcWarps) {
+    const int nC = sCorner[b];
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(smem + lay.queue + b * kFcQueueBytes);
+    uint32_t* bm = reinterpret_cast<uint32_t*>(smem + lay.queue + b * kFcQueueBytes + kQCap * 4);  // [8 rows][8 words]
+    if (nC >= 0) {
+      for (int i = lane; i < nC; i += 32) {
+        const uint32_t e = q[i];
+        const int x = e & 0xff, row = (e >> 8) & 0xff, s = e >> 16;
+        const int rel = x - xoff;
+        const int c0 = (int)(((uint32_t)rel * recip) >> 16) * wCell;
+        const bool first = rel == c0, last = rel == c0 + wCell - 1;
+        if (nms_keep(sTile + row * kSP + x, s, first, last)) atomicOr(bm + (row & 7) * 8 + (x >> 5), 1u << (x & 31));
+      }
+    } else {  // slow path: every non-zero score of the band
+#pragma unroll 1
+      for (int j = 0; j < 8; j++) {
+        const uint8_t* rowp = sTile + (8 * b + j) * kSP;
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+          const int x = 8 * lane + k, s = rowp[x];
+          if (s == 0) continue;
+          const int rel = x - xoff;
+          const int c0 = (int)(((uint32_t)rel * recip) >> 16) * wCell;
+          if (nms_keep(rowp + x, s, rel == c0, rel == c0 + wCell - 1)) atomicOr(bm + j * 8 + (x >> 5), 1u << (x & 31));
+        }
+      }
+    }
+  }
+  __syncthreads();  // every survivor bit is set
+
+  // ================================================================ emission: warp = cell, lane = tested row
+  const int iniTh = g.iniTh;
+  for (int c = warp; c < kc; c += kFcWarps) {
+    const int cx0 = xoff + c * wCell, cw = min(wCell, xoff + tw - cx0);  // the cell's columns in the lane frame
+    uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)(ci0 * L.nCols + cj0 + c) * L.slotCap;
+    if (cw <= 0) {
+      if (lane == 0) cnt[c] = 0;
+      continue;
+    }
+    const int wi = cx0 >> 5, sh = cx0 & 31;
+    int basei = 0;
+    // pass 1 decides the threshold (any survivor with score >= iniTh in the whole cell), pass 2 emits.  Class A: cells
+    // are at most 32 x 32, one 32-bit window per row; otherwise up to 59 x 59: 64-bit windows, two passes of 32 rows.
+    typedef typename std::conditional<kA, uint32_t, uint64_t>::type mask_t;
+    constexpr int kPasses = kA ? 1 : 2;
+    mask_t keep[kPasses], keep20[kPasses];
+    bool any20 = false;
+    const int nPass = kA ? 1 : (th + 31) >> 5;  // warp-uniform
+#pragma unroll
+    for (int p = 0; p < kPasses; p++) {
+      keep[p] = 0; keep20[p] = 0;
+      if (p >= nPass) continue;
+      const int r = lane + 32 * p;
+      if (r < th) {
+        // bits [cx0, cx0 + cw) of the row's 256-bit survivor bitmap; words past the row's end are clamped re-reads whose
+        // bits land at or above cw (cx0 + cw <= 256) and fall to the width mask
+        const uint32_t* rowBm = reinterpret_cast<const uint32_t*>(smem + lay.queue + (r >> 3) * kFcQueueBytes + kQCap * 4) + (r & 7) * 8;
+        const uint32_t w0 = rowBm[wi], w1 = rowBm[min(wi + 1, 7)];
+        mask_t m = __funnelshift_r(w0, w1, sh);
+        if (!kA) m |= (mask_t)((uint64_t)__funnelshift_r(w1, rowBm[min(wi + 2, 7)], sh) << 32);
+        m &= cw >= (int)(8 * sizeof(mask_t)) ? ~(mask_t)0 : (((mask_t)1 << cw) - (mask_t)1);
+        keep[p] = m;
+        mask_t m20 = 0;
+        const uint8_t* rowp = sTile + r * kSP + cx0;
+        for (mask_t t = m; t; t &= t - 1) {
+          const int bx = kA ? __ffs((int)t) - 1 : __ffsll((long long)t) - 1;
+          if (rowp[bx] >= iniTh) m20 |= (mask_t)1 << bx;
+        }
+        keep20[p] = m20;
+      }
+      any20 = __any_sync(0xffffffffu, keep20[p] != 0) || any20;
+    }
+    const int xbase = X0 - xoff + cx0 - kMinBorder;  // level x of the cell's first column, relative to the 16-px border
+#pragma unroll
+    for (int p = 0; p < kPasses; p++) {
+      if (p >= nPass) continue;
+      const mask_t sel = any20 ? keep20[p] : keep[p];
+      const int n = kA ? __popc((uint32_t)sel) : __popcll((uint64_t)sel);
+      int in2 = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, in2, d);
+        if (lane >= d) in2 += v;
+      }
+      int pos = basei + in2 - n;
+      basei += __shfl_sync(0xffffffffu, in2, 31);
+      const int r = lane + 32 * p;
+      const uint8_t* rowp = sTile + r * kSP + cx0;
+      const uint32_t ybits = (uint32_t)(Y0 + r - kMinBorder) << 12;
+      for (mask_t t = sel; t; t &= t - 1) {  // lane order = row order, bit order = x order: the reference's row-major order
+        const int bx = kA ? __ffs((int)t) - 1 : __ffsll((long long)t) - 1;
+        if (pos < L.slotCap) slot[pos] = (uint32_t)(xbase + bx) | ybits | ((uint32_t)rowp[bx] << 24);
+        pos++;
+      }
+    }
+    if (lane == 0) {
+      if (basei > L.slotCap) { atomicOr(err, kErrCandOverflow); basei = L.slotCap; }
+      cnt[c] = basei;
+    }
+  }
+}
+
+int configure_fast_cells(int nbGeneric) {
+  static DynSmemLimit limA, limB;
+  if (int rc = limA.ensure(k_fast_cells<true, kFcOccA>, fc_smem_layout(4).total)) return rc;
+  if (nbGeneric > 0)
+    if (int rc = limB.ensure(k_fast_cells<false, 1>, fc_smem_layout(nbGeneric).total)) return rc;
+  return PGB_OK;
+}
+
+int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, int nFrames,
+                      uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0) {
+  if (nFrames <= 0) return PGB_OK;
+  if (int rc = configure_fast_cells(g.fcTilesB > 0 ? g.fcNbB : 0)) return rc;
+  if (g.fcTilesA > 0) {
+    dim3 grid(g.fcTilesA, nFrames);
+    k_fast_cells<true, kFcOccA><<<grid, kFcThreads, fc_smem_layout(4).total, st>>>(g, tm, tileTabA, 4, frame0, slots, cellCnt, err);
+    PGB_LAUNCHED();
+  }
+  if (g.fcTilesB > 0) {
+    dim3 grid(g.fcTilesB, nFrames);
+    k_fast_cells<false, 1><<<grid, kFcThreads, fc_smem_layout(g.fcNbB).total, st>>>(g, tm, tileTabB, g.fcNbB, frame0, slots, cellCnt, err);
+    PGB_LAUNCHED();
+  }
+  return PGB_OK;
+}
+
+}  // namespace pgb

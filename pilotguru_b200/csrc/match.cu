@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kMtThreads) k_match_windowed(WinArgs A) {
     int o0 = 0, o1 = 0;
     if (A.flavour == 2) {
       if (level < 0 || level >= A.nlevels) ok = false;
-      float rr = A.qAux[o] > 0.998f ? 2.5f : 4.0f;                         // RadiusByViewingCos
+      float rr = (double)A.qAux[o] > 0.998 ? 2.5f : 4.0f;                   // RadiusByViewingCos: float vs the DOUBLE literal (ORBmatcher.cc:133-139)
       if (A.th != 1.0f) rr *= A.th;
       r = ok ? rr * A.scale[level] : 0.f;
       o0 = level - 1; o1 = level;
@@ -885,7 +885,6 @@ struct pgb_matcher {
   DevBuf<float> dUV, dAng, dFlow;
   DevBuf<int> dN, dQN, dOct, dMatch, dNm;
   DevBuf<int> overflow;
-  size_t smemConfigured = 0, smem2Configured = 0;
 };
 
 namespace {
@@ -895,10 +894,8 @@ int launch_match(pgb_matcher* m, MatchArgs& A, int nPairs) {
   if (nPairs > m->maxBatch) return fail(PGB_ERR_CAPACITY, "n_pairs %d exceeds the matcher's max_batch %d", nPairs, m->maxBatch);
   const size_t smem = match_smem_bytes(A.cap);
   if (smem > 227 * 1024) return fail(PGB_ERR_CAPACITY, "cap %d needs %zu B of shared memory (max 227 KB)", A.cap, smem);
-  if (smem > 48 * 1024 && smem > m->smemConfigured) {
-    PGB_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    m->smemConfigured = smem;
-  }
+  static DynSmemLimit limMatch, limResolve;
+  if (int rc = limMatch.ensure(k_match, smem)) return rc;
   A.qList32 = m->qList.p;
   A.qCnt = m->qCnt.p;
   A.overflow = m->overflow.p;
@@ -908,10 +905,7 @@ int launch_match(pgb_matcher* m, MatchArgs& A, int nPairs) {
   k_match<<<nPairs * kSplit, kMtThreads, smem, m->stream>>>(A);
   PGB_CHECK_LAUNCH();
   const size_t smem2 = (size_t)A.cap * 13 + 16;
-  if (smem2 > 48 * 1024 && smem2 > m->smem2Configured) {
-    PGB_CUDA(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    m->smem2Configured = smem2;
-  }
+  if (int rc = limResolve.ensure(k_match_resolve, smem2)) return rc;
   k_match_resolve<<<nPairs, kMtThreads, smem2, m->stream>>>(A);
   PGB_CHECK_LAUNCH();
   // pairs with a truncated candidate row (flagged by k_match_resolve) are redone by the sequential kernel
@@ -1087,7 +1081,8 @@ int run_windowed(pgb_matcher* m, WinArgs& A, int nProb) {
   A.rows = rows.p; A.rowCnt = cnt.p; A.err = err.p;
   const size_t smem = (size_t)A.cap * 16 + 64;
   if (smem > 227 * 1024) return fail(PGB_ERR_CAPACITY, "cap %d needs %zu B of shared memory (max 227 KB)", A.cap, smem);
-  if (smem > 48 * 1024) PGB_CUDA(cudaFuncSetAttribute(k_match_windowed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static DynSmemLimit limWindowed;
+  if (int rc = limWindowed.ensure(k_match_windowed, smem)) return rc;
   k_match_windowed<<<nProb, kMtThreads, smem, m->stream>>>(A);
   PGB_CHECK_LAUNCH();
   int e = 0;
@@ -1261,7 +1256,8 @@ int pgb_match_by_bow(pgb_matcher* m, int n_pairs, int cap, const uint8_t* kf_des
   A.fNode = f_node_id; A.fStart = f_feat_start; A.fIdx = f_feat_idx; A.matchOfF = dmatch; A.nMatches = dnm; A.err = dErr.p;
   const size_t smem = 128 + (size_t)((cap + 31) / 32) * 4 + cap + 16;
   if (smem > 227 * 1024) return fail(PGB_ERR_CAPACITY, "cap %d needs %zu B of shared memory (max 227 KB)", cap, smem);
-  if (smem > 48 * 1024) PGB_CUDA(cudaFuncSetAttribute(k_match_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static DynSmemLimit limBow;
+  if (int rc = limBow.ensure(k_match_bow, smem)) return rc;
   k_match_bow<<<n_pairs, kMtThreads, smem, s>>>(A);
   PGB_CHECK_LAUNCH();
   int e = 0;

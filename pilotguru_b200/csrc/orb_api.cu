@@ -74,6 +74,11 @@ struct pgb_orb {
   TmapPack tmaps{};
   TmapPack tmapsCur{};  // = tmaps, with in[0] re-encoded on the caller's buffer while level 0 is read in place
   DevBuf<int4> tileTab;
+  TmapIn tmapsFc{};     // fused kernel: per level, box height of the level's class
+  TmapIn tmapsFcCur{};  // = tmapsFc, with in[0] on the caller's buffer while level 0 is read in place
+  DevBuf<int4> fcTabA, fcTabB;  // fused kernel tile tables: level, first tested x, first tested y, cell row | first cell column << 16
+  bool unfused = false;  // PGB_UNFUSED=1: the round-1 pair k_fast_score -> k_cells instead of k_fast_cells (A/B, stage debugging)
+  bool scoreValid = false;  // the score map of the resident batch has been produced (only the unfused path writes it)
   DevBuf<int> cellTab;  // per FAST cell: level | grid row << 8 | grid column << 20
   cudaStream_t copyStream = nullptr;
   cudaStream_t auxStream[2] = {nullptr, nullptr};
@@ -96,13 +101,14 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
   g->iniTh = o->iniTh;
   g->minTh = o->minTh;
   {
-    int k = 0;
-    while (k < 7 && (2 << k) - 1 <= o->minTh) k++;  // 2^k - 1 <= minTh < 2^(k+1) - 1 (k = 0 when minTh < 1)
+    // prefilter constant K = 0x80 - (minTh + 1) per byte: x + K has its msb set iff x > minTh, for x < 0x80 (x >= 0x80
+    // is caught by "| x"); thresholds >= 0x7f degrade to the weaker but still necessary test x >= 0x80
     g->one = 1u;
-    g->absMask = (0x7fu & ~((1u << k) - 1u)) * 0x01010101u;
+    g->absMask = (uint32_t)std::max(0, 0x80 - (o->minTh + 1)) * 0x01010101u;
   }
   unsigned long long off = 0, slotOff = 0, candOff = 0;
   int cellBase = 0, tile2Base = 0, kpBase = 0, maxNode = 1;
+  g->fcTilesA = g->fcTilesB = g->fcNbB = 0;
   for (int l = 0; l < o->nlevels; l++) {
     LevelGeo& L = g->lv[l];
     L.w = cv_round_f((float)w * o->invScale[l]);
@@ -147,6 +153,18 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
     L.tiles2Y = (L.h + kF2H - 1) / kF2H;
     L.tile2Base = tile2Base;
     tile2Base += L.tiles2X * L.tiles2Y;
+    // fused FAST + cell NMS kernel: a tile is one row of fcKc whole cells
+    L.fcKc = std::max(1, kFcMaxFrame / L.wCell);
+    L.fcNb = (L.hCell + 7) / 8;
+    L.fcClassB = (L.wCell > 32 || L.hCell > 32) ? 1 : 0;
+    L.fcRecip = (65536u + (unsigned)L.wCell - 1u) / (unsigned)L.wCell;
+    if (L.wCell > kFcMaxFrame || L.fcNb > 8)
+      return fail(PGB_ERR_INVALID, "level %d: FAST cell %dx%d exceeds the kernel's tile", l, L.wCell, L.hCell);
+    {
+      const int tiles = L.nRows * ((L.nCols + L.fcKc - 1) / L.fcKc);
+      if (L.fcClassB) { g->fcTilesB += tiles; g->fcNbB = std::max(g->fcNbB, L.fcNb); }
+      else g->fcTilesA += tiles;
+    }
     L.scale = o->scale[l];
     L.patchSize = (int)(31 * o->scale[l]);
     if (L.maxBX - kMinBorder > 4095 || L.maxBY - kMinBorder > 4095)
@@ -247,10 +265,17 @@ int build_tmaps(pgb_orb* o) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(load, level %d) failed: %d", l, (int)r);
-    r = encode(&o->tmaps.out[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->score.p + L.off, dims, strides, boxOut, es,
+    if (o->score.p) {  // the score map exists only on the unfused / stage-debugging path (ensure_score)
+      r = encode(&o->tmaps.out[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->score.p + L.off, dims, strides, boxOut, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(store, level %d) failed: %d", l, (int)r);
+    }
+    const cuuint32_t boxFc[3] = {(cuuint32_t)kFcInWords, (cuuint32_t)(8 * (L.fcClassB ? g.fcNbB : 4) + 6), 1};
+    r = encode(&o->tmapsFc.in[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->pyr.p + L.off, dims, strides, boxFc, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(store, level %d) failed: %d", l, (int)r);
+    if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(fused load, level %d) failed: %d", l, (int)r);
   }
   return PGB_OK;
 }
@@ -275,6 +300,12 @@ int use_external_level0(pgb_orb* o, const uint8_t* gray, size_t pitch, size_t fr
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(external level 0) failed: %d", (int)r);
+  o->tmapsFcCur = o->tmapsFc;
+  const cuuint32_t boxFc[3] = {(cuuint32_t)kFcInWords, (cuuint32_t)(8 * (L.fcClassB ? o->geo.fcNbB : 4) + 6), 1};
+  r = encode(&o->tmapsFcCur.in[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(gray), dims, strides, boxFc, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(external level 0, fused) failed: %d", (int)r);
   o->geo.ext0 = gray;
   o->geo.ext0Stride = frame_stride;
   o->geo.ext0Pitch = (int)pitch;
@@ -311,6 +342,21 @@ int set_geometry(pgb_orb* o, int w, int h) {
     if (o->tileTab.n < tab.size() && o->tileTab.alloc(tab.size())) return PGB_ERR_CUDA;
     PGB_CUDA(cudaMemcpyAsync(o->tileTab.p, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice, o->stream));
     PGB_CUDA(cudaStreamSynchronize(o->stream));
+    // fused kernel: one tile per (cell row, group of fcKc cell columns); first tested pixel of cell (i, j) is
+    // (19 + j * wCell, 19 + i * hCell) (ORBextractor.cc:789-806: iniX + 3, iniY + 3)
+    std::vector<int4> fa, fb;
+    for (int l = 0; l < g.nlevels; l++) {
+      const LevelGeo& L = g.lv[l];
+      for (int i = 0; i < L.nRows; i++)
+        for (int j0 = 0; j0 < L.nCols; j0 += L.fcKc)
+          (L.fcClassB ? fb : fa).push_back(make_int4(l, kEdge + j0 * L.wCell, kEdge + i * L.hCell, i | (j0 << 16)));
+    }
+    if ((int)fa.size() != g.fcTilesA || (int)fb.size() != g.fcTilesB) return fail(PGB_ERR_INVALID, "internal: fused tile count");
+    if (o->fcTabA.n < fa.size() + 1 && o->fcTabA.alloc(fa.size() + 1)) return PGB_ERR_CUDA;
+    if (o->fcTabB.n < fb.size() + 1 && o->fcTabB.alloc(fb.size() + 1)) return PGB_ERR_CUDA;
+    if (!fa.empty()) PGB_CUDA(cudaMemcpyAsync(o->fcTabA.p, fa.data(), fa.size() * sizeof(int4), cudaMemcpyHostToDevice, o->stream));
+    if (!fb.empty()) PGB_CUDA(cudaMemcpyAsync(o->fcTabB.p, fb.data(), fb.size() * sizeof(int4), cudaMemcpyHostToDevice, o->stream));
+    PGB_CUDA(cudaStreamSynchronize(o->stream));
   }
   return upload_tabs(o);
 }
@@ -326,6 +372,27 @@ int check_err_flag(pgb_orb* o) {
   return PGB_OK;
 }
 
+// The FAST score map in HBM (same layout as the pyramid) is only needed by the unfused kernel pair (PGB_UNFUSED=1,
+// pgb_orb_run_stage(2), pgb_orb_get_score_map): allocated on first use, then the TMA store maps are encoded on it.
+int ensure_score(pgb_orb* o) {
+  if (o->score.p) return PGB_OK;
+  const size_t bytes = (size_t)o->maxBatch * o->capGeo.frameStride;
+  if (o->score.alloc(bytes)) return PGB_ERR_CUDA;
+  PGB_CUDA(cudaMemsetAsync(o->score.p, 0, bytes, o->stream));
+  if (o->curW > 0) {
+    int rc = build_tmaps(o);
+    if (rc) return rc;
+    if (o->geo.ext0) {
+      rc = use_external_level0(o, o->geo.ext0, (size_t)o->geo.ext0Pitch, (size_t)o->geo.ext0Stride, o->curFrames);
+      if (rc) return rc;
+    } else {
+      o->tmapsCur = o->tmaps;
+      o->tmapsFcCur = o->tmapsFc;
+    }
+  }
+  return PGB_OK;
+}
+
 // Stages `from`..`to` over frames [f0, f0+n) of the resident batch; kps/desc/counts are the bases of the WHOLE
 // batch's output arrays (frame f0 writes at f0*cap).
 int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, int* counts, int cap, int f0, int n,
@@ -335,7 +402,7 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
   OrbGeo g = o->geo;  // kernels index frames relative to f0: advance the in-place level 0 like the other bases
   if (g.ext0) g.ext0 += (size_t)f0 * g.ext0Stride;
   uint8_t* pyr = o->pyr.p + (size_t)f0 * g.frameStride;
-  uint8_t* score = o->score.p + (size_t)f0 * g.frameStride;
+  uint8_t* score = o->score.p ? o->score.p + (size_t)f0 * g.frameStride : nullptr;
   uint32_t* slots = o->slots.p + (size_t)f0 * g.slotsPerFrame;
   int* cellCnt = o->cellCnt.p + (size_t)f0 * g.totalCells;
   unsigned long long* cand = o->cand.p + (size_t)f0 * g.candPerFrame;
@@ -350,11 +417,29 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         break;
       case 1:
       {
-        int rc = launch_fast_score(g, o->tmapsCur, o->tileTab.p, f0, n, st);
+        // hot path: the fused kernel (score -> per-cell NMS -> candidates, no score map); PGB_UNFUSED=1: the score map kernel
+        int rc;
+        if (o->unfused) {
+          rc = launch_fast_score(g, o->tmapsCur, o->tileTab.p, f0, n, st);
+          if (f0 == 0 && n == o->curFrames) o->scoreValid = true;
+        } else {
+          rc = launch_fast_cells(g, o->tmapsFcCur, o->fcTabA.p, o->fcTabB.p, n, slots, cellCnt, o->err.p, st, f0);
+        }
         if (rc) return rc;
         break;
       }
-      case 2: launch_cells(g, n, o->cellTab.p, score, slots, cellCnt, o->err.p, st); break;
+      case 2:  // the round-1 pair, kept for A/B timing and stage-by-stage parity: on the fused path it recomputes the same slots
+        if (!o->unfused && !(from == 2 && to == 2)) break;  // ... only when asked for by itself (pgb_orb_run_stage(2))
+        if (!o->unfused) {
+          int rc = ensure_score(o);
+          if (rc) return rc;
+          score = o->score.p + (size_t)f0 * g.frameStride;
+          rc = launch_fast_score(g, o->tmapsCur, o->tileTab.p, f0, n, st);
+          if (rc) return rc;
+        }
+        launch_cells(g, n, o->cellTab.p, score, slots, cellCnt, o->err.p, st);
+        if (f0 == 0 && n == o->curFrames) o->scoreValid = true;
+        break;
       case 3: launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, st); break;
       case 4:
         launch_orient_desc(g, n, pyr, staged, lvlCnt, kps + (size_t)f0 * cap, desc + (size_t)f0 * cap * 32, counts + f0,
@@ -519,7 +604,8 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
   for (int l = 0; l < nlevels; l++) o->outCap += c.lv[l].nodeCap;
   int tabX = 0, tabY = 0;
   for (int l = 1; l < nlevels; l++) { tabX += c.lv[l].w + 8; tabY += c.lv[l].h + 8; }
-  if (o->pyr.alloc(B * c.frameStride) || o->score.alloc(B * c.frameStride) || o->slots.alloc(B * c.slotsPerFrame) ||
+  if (const char* e = getenv("PGB_UNFUSED")) o->unfused = atoi(e) != 0;
+  if (o->pyr.alloc(B * c.frameStride) || (o->unfused && o->score.alloc(B * c.frameStride)) || o->slots.alloc(B * c.slotsPerFrame) ||
       o->cellCnt.alloc(B * c.totalCells) || o->lvlCnt.alloc(B * nlevels) || o->err.alloc(1) || o->counts.alloc(B) ||
       o->cand.alloc(B * c.candPerFrame) || o->staged.alloc(B * c.kpCapInternal) || o->xtab.alloc(tabX + 8) ||
       o->ytab.alloc(tabY + 8) || o->kps.alloc(B * o->outCap) || o->desc.alloc(B * o->outCap * 32) ||
@@ -527,7 +613,7 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
     return bail("cudaMalloc failed");
   if (cudaMemsetAsync(o->err.p, 0, sizeof(int), o->stream) != cudaSuccess ||
       cudaMemsetAsync(o->pyr.p, 0, B * c.frameStride, o->stream) != cudaSuccess ||
-      cudaMemsetAsync(o->score.p, 0, B * c.frameStride, o->stream) != cudaSuccess ||
+      (o->score.p && cudaMemsetAsync(o->score.p, 0, B * c.frameStride, o->stream) != cudaSuccess) ||
       cudaStreamSynchronize(o->stream) != cudaSuccess)
     return bail("cudaMemset failed");
   return o;
@@ -599,6 +685,8 @@ int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames
   const int dcap = outDev ? cap : o->outCap;  // a caller capacity below pgb_orb_max_keypoints() raises the device flag
   o->geo.ext0 = nullptr;
   o->tmapsCur = o->tmaps;
+  o->tmapsFcCur = o->tmapsFc;
+  o->scoreValid = false;
   if (inDev && ((size_t)gray & 15) == 0 && (pitch & 15) == 0 && (frame_stride & 15) == 0 && frame_stride >= pitch * (size_t)height) {
     // level 0 is read in place: no copy; the frames must stay valid until the next extract call on this handle
     rc = use_external_level0(o, gray, pitch, frame_stride, n_frames);
@@ -673,7 +761,16 @@ int pgb_orb_get_level(pgb_orb* o, int frame, int level, uint8_t* out, int* w, in
   return copy_level_out(o, o ? o->pyr.p : nullptr, frame, level, out, w, h);
 }
 int pgb_orb_get_score_map(pgb_orb* o, int frame, int level, uint8_t* out, int* w, int* h) {
-  return copy_level_out(o, o ? o->score.p : nullptr, frame, level, out, w, h);
+  if (!o || frame < 0 || frame >= o->curFrames || level < 0 || level >= o->nlevels) return fail(PGB_ERR_INVALID, "bad frame/level");
+  PGB_CUDA(cudaSetDevice(o->device));
+  if (out && !o->scoreValid) {  // the hot path never materialises the score map: produce it now with the score kernel
+    int rc = ensure_score(o);
+    if (rc) return rc;
+    rc = launch_fast_score(o->geo, o->tmapsCur, o->tileTab.p, 0, o->curFrames, o->stream);
+    if (rc) return rc;
+    o->scoreValid = true;
+  }
+  return copy_level_out(o, o->score.p, frame, level, out, w, h);
 }
 
 int pgb_orb_get_blurred_level(pgb_orb* o, int frame, int level, uint8_t* out, int* w, int* h) {

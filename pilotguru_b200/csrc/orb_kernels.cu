@@ -618,11 +618,8 @@ static size_t octree_smem_bytes(int cap) {
 void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,
                    StagedKp* staged, int* lvlCnt, int* err, cudaStream_t st) {
   const size_t smem = octree_smem_bytes(g.maxNodeCap);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static DynSmemLimit lim;
+  lim.ensure(k_octree, smem);  // a failure surfaces as the launch error run_stages() checks
   dim3 grid(g.nlevels, nFrames);
   k_octree<<<grid, kOctThreads, smem, st>>>(g, slots, cellCnt, cand, staged, lvlCnt, err);
   PGB_LAUNCHED();

@@ -39,6 +39,30 @@ constexpr int kF2InWords = kF2W / 4 + 8;  // 72 words per row: 16-byte halo left
 constexpr int kF2InRows = kF2H + 6;       // 70
 constexpr int kF2InBytes = kF2InWords * 4 * kF2InRows;  // 20160 = TMA transaction size
 
+// fused FAST + cell NMS kernel (fast_cells.cu): one CTA per row of up to fcKc FAST cells; the TMA box of a tile is
+// 72 words x (8 * bands + 6) rows, the score tile (8 * bands + 2) rows of 272 bytes, one candidate queue per band
+constexpr int kFcThreads = 128, kFcWarps = 4;
+constexpr int kFcInWords = 72;       // 288-byte staged input rows: <= 18 bytes of alignment slack + 249 px + 3-px halos
+constexpr int kFcTilePitch = 272;    // score tile row: 16 pad bytes + 256 px
+constexpr int kFcQueueCap = 384;     // candidates per band queue (u32 flag + u8 code each)
+constexpr int kFcQueueBytes = kFcQueueCap * 5;
+constexpr int kFcMaxFrame = 249;     // widest tested tile inside the 256-px lane frame (first pixel at offset 0..7)
+#ifndef PGB_FC_OCC
+#define PGB_FC_OCC 8
+#endif
+constexpr int kFcOccA = PGB_FC_OCC;  // resident CTAs per SM the class-A instantiation is compiled for
+struct FcSmem {
+  int tile, queue, misc, total;  // byte offsets inside the dynamic shared memory (input stage at 0)
+};
+__host__ __device__ inline FcSmem fc_smem_layout(int nb) {
+  FcSmem s;
+  s.tile = (kFcInWords * 4 * (8 * nb + 6) + 127) & ~127;
+  s.queue = s.tile + (8 * nb + 2) * kFcTilePitch;
+  s.misc = s.queue + nb * kFcQueueBytes;
+  s.total = s.misc + 64;  // mbarrier + per-band corner counts
+  return s;
+}
+
 struct LevelGeo {
   int w, h, pitch;
   unsigned long long off;
@@ -52,6 +76,8 @@ struct LevelGeo {
   unsigned long long candBase;  // in u64 units inside a frame's cand block
   int nodeCap, kpBase;
   int tile2Base, tiles2X, tiles2Y;
+  int fcKc, fcNb, fcClassB;     // fused kernel: cells per tile, bands per tile, 1 = cells larger than 32 px (generic instantiation)
+  unsigned fcRecip;             // ceil(65536 / wCell): (x * fcRecip) >> 16 == x / wCell for x < 1024
   float scale;
   int patchSize;
 };
@@ -61,6 +87,7 @@ struct OrbGeo {
   unsigned one;      // = 1, opaque to the compiler (FAST v3 issues its additions as IMAD on the idle FMA pipe)
   unsigned absMask;  // FAST v3 prefilter: bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
   int totalCells, totalTiles2, kpCapInternal, maxNodeCap;
+  int fcTilesA, fcTilesB, fcNbB;  // fused kernel: tiles of class A / class B levels, bands per class-B tile
   unsigned long long frameStride, slotsPerFrame, candPerFrame;
   // Level 0 in place: when the caller's frames are device-resident and 16-byte aligned, level 0 is read where it lies
   // (ext0 + f * ext0Stride, rows ext0Pitch apart) instead of being copied into the pyramid buffer.
@@ -87,6 +114,10 @@ struct alignas(64) TmapPack {  // per level: u32 views of the pyramid (load) and
   CUtensorMap out[kMaxLevels];
 };
 
+struct alignas(64) TmapIn {  // fused kernel: per level the u32 view of the pyramid with that level's box height
+  CUtensorMap in[kMaxLevels];
+};
+
 struct ResizeTab {  // one entry per destination column / row
   short s, a0, a1, pad;
 };
@@ -102,6 +133,8 @@ void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr,
 int configure_fast_score();
 int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st);
+int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, int nFrames,
+                      uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0);
 void launch_cells(const OrbGeo& g, int nFrames, const int* cellTab, const uint8_t* score, uint32_t* slots, int* cellCnt,
                   int* err, cudaStream_t st);
 void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,

@@ -480,8 +480,8 @@ extern "C" int pgb_pose_optimization(int device, int n_frames, int cap, const fl
   for (int i = 0; i < nlevels; i++) A.invSigma2[i] = inv_level_sigma2[i];
   A.TcwIn = Tcw_in; A.kpXY = kp_xy; A.kpOctave = kp_octave; A.mpXYZ = mp_xyz; A.hasMp = has_map_point; A.counts = counts;
   A.TcwOut = to; A.outlier = out; A.nInliers = ni; A.err = dErr.p;
-  if (smem > 48 * 1024)
-    PGB_CUDA(cudaFuncSetAttribute(k_pose_optimization, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static DynSmemLimit lim;
+  if (int rc = lim.ensure(k_pose_optimization, smem)) return rc;
   k_pose_optimization<<<n_frames, kPoThreads, smem, s>>>(A);
   PGB_CHECK_LAUNCH();
   int e = 0;

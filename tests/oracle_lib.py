@@ -47,6 +47,24 @@ def lib():
     return _LIB
 
 
+_NATIVE = None
+
+
+def native_lib():
+    """(CDLL, build description) of the `-O3 -march=native` build of the same sources, compiled on THIS host (bench.py's
+    CPU legs: SURVEY.md 8d's flags).  Falls back to the portable build when the host has no compiler."""
+    global _NATIVE
+    if _NATIVE is None:
+        so = os.path.join(ORACLE_DIR, "_native", "liboracle.so")
+        try:
+            subprocess.run(["make", "-C", ORACLE_DIR, "native"], check=True, capture_output=True, timeout=300)
+            l = C.CDLL(so)
+            _NATIVE = (l, "g++ -O3 -march=native -ffp-contract=off, built on this host")
+        except Exception as e:  # noqa: BLE001
+            _NATIVE = (lib(), f"g++ -O3 -march=x86-64-v3 -ffp-contract=off (portable build; native build failed: {type(e).__name__})")
+    return _NATIVE
+
+
 def ptr(a, t):
     return a.ctypes.data_as(t)
 
@@ -203,15 +221,20 @@ def match_consecutive(prev_kps, prev_desc, cur_kps, cur_desc, flow, max_x, max_y
     return n, m[:len(cur_kps)]
 
 
-def bench_extract_match(frames: np.ndarray, flows: np.ndarray, nthreads: int, nfeatures=1000, th=15.0):
-    """Timed CPU baseline: returns (seconds, total_keypoints, total_matches)."""
+def bench_extract_match(frames: np.ndarray, flows: np.ndarray, nthreads: int, nfeatures=1000, th=15.0, per_frame=False,
+                        native=False):
+    """Timed CPU baseline: returns (seconds, total_keypoints, total_matches[, keypoints per frame, matches per frame]).
+    Every consecutive pair (t-1, t) is matched; matches_per_frame[0] = -1."""
     frames = np.ascontiguousarray(frames, np.uint8); flows = np.ascontiguousarray(flows, np.float32)
     n, h, w = frames.shape
-    l = lib()
+    l = native_lib()[0] if native else lib()
     l.pgo_bench_extract_match.restype = C.c_double
     tk = C.c_int64(); tm = C.c_int64()
+    nk = np.zeros(n, np.int32); nm = np.zeros(n, np.int32)
     s = l.pgo_bench_extract_match(ptr(frames, u8p), n, w, h, ptr(flows, f32p), nfeatures, C.c_float(1.2), 8, 20, 7,
-                                  C.c_float(th), nthreads, C.byref(tk), C.byref(tm))
+                                  C.c_float(th), nthreads, C.byref(tk), C.byref(tm), ptr(nk, i32p), ptr(nm, i32p))
+    if per_frame:
+        return float(s), tk.value, tm.value, nk, nm
     return float(s), tk.value, tm.value
 
 
@@ -302,6 +325,45 @@ def fit_motion(d, batch_size=40, shift_step=5, max_iters=500, sigma=0.003, mode=
         raise RuntimeError(f"pgo_fit_motion failed: {n}")
     return dict(idx=idx[:n].copy(), t_usec=ts[:n].copy(), avg=avg[:n].copy(), smoothed=sm[:n].copy(), x=xo, iters=it,
                 fx=fx, n_evals=ne.value)
+
+
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libpilotguru_ref.so")
+_REF = None
+
+
+def ref_lib():
+    """oracle/_ref/libpilotguru_ref.so -- the reference's own sources compiled where they lie (oracle/Makefile `_ref`) --
+    or None when it is neither built nor buildable (no /root/reference, e.g. a GPU box that got no prebuilt copy)."""
+    global _REF
+    if _REF is None:
+        if os.path.isdir("/root/reference"):
+            try:
+                subprocess.run(["make", "-C", ORACLE_DIR, "_ref"], check=True, capture_output=True)
+            except Exception:
+                pass
+        _REF = C.CDLL(REF_SO) if os.path.exists(REF_SO) else False
+    return _REF or None
+
+
+def ref_fit_motion(d, batch_size=40, shift_step=5, max_iters=500, sigma=0.003):
+    """ComputeAndSaveForwardVelocitiesFromImu (src/fit_motion.cc:156-293) compiled from the REFERENCE'S file (oracle/_ref):
+    (event timestamps, smoothed velocities).  None when oracle/_ref is unavailable."""
+    l = ref_lib()
+    if l is None:
+        return None
+    l.pgr_fit_motion.restype = C.c_int64
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    gv, gt, gy, gyt, ac, act = a(d["gps_v"], np.float64), a(d["gps_t"], np.int64), a(d["gyro"], np.float64), a(d["gyro_t"], np.int64), a(d["acc"], np.float64), a(d["acc_t"], np.int64)
+    cap = len(gyt) + len(act) + 8
+    vertical = np.array([0.0, 0.0, 1.0])
+    rt = np.empty(cap, np.int64); rs = np.empty(cap); rf = np.zeros(3)
+    n = l.pgr_fit_motion(ptr(gv, f64p), ptr(gt, i64p), C.c_int64(len(gt)), ptr(gy, f64p), ptr(gyt, i64p), C.c_int64(len(gyt)),
+                         ptr(ac, f64p), ptr(act, i64p), C.c_int64(len(act)), ptr(vertical, f64p), C.c_int64(batch_size),
+                         C.c_int64(shift_step), C.c_int64(max_iters), C.c_double(sigma), C.c_double(5.0), C.c_double(0.2),
+                         ptr(rt, i64p), ptr(rs, f64p), C.c_int64(cap), ptr(rf, f64p))
+    if n < 0:
+        raise RuntimeError(f"pgr_fit_motion failed: {n}")
+    return rt[:n].copy(), rs[:n].copy()
 
 
 def forward_axis_sum(d, x_all, batch_size=40, shift_step=5, mode=0, min_vel=5.0, min_rot=0.2):

@@ -113,6 +113,61 @@ def test_extract_then_match_consecutive_device_resident(golden_dir):
     m.close(); ex.close()
 
 
+def test_match_consecutive_at_the_baseline_config_with_retry_branches():
+    """The BENCHMARKED matcher path at the BASELINE size: pgb_match_consecutive over a batch of 1080p frames with 1000
+    features (cap = the extractor's), every pair compared with the oracle (= SearchByProjection at th, Tracking.cc:876-883's
+    retry at 2*th when fewer than 20 matches, both pinned to the reference's own function bodies).  The batch contains the
+    three outcomes of that retry: pairs that pass at th = 15; pairs that have < 20 matches at 15 and recover at 30 (only
+    low-octave features + a flow that is 24 px off: windows of 15 / 18 px miss, 30 / 36 px hit); pairs that fail at both
+    thresholds (descriptors replaced by noise)."""
+    import torch
+    from pilotguru_b200.matcher import ORBmatcher
+    from pilotguru_b200.orb import ORBextractor
+    W, H, NF, B = 1920, 1080, 1000, 16
+    orc = O.OrbOracle(NF, 1.2, 8, 20, 7)
+    sf = orc.tables()["scale"]
+    feats = [orc.extract(synth.frame(t)) for t in range(B + 1)]
+    flows = np.array([synth.flow(t) for t in range(1, B + 1)], np.float32)
+    rng = np.random.default_rng(77)
+    low = lambda kd: (kd[0][kd[0]["octave"] <= 1], kd[1][kd[0]["octave"] <= 1])
+    for t in (5, 6, 7):                                  # pairs 4..7 touch a frame reduced to octaves 0 and 1
+        feats[t] = low(feats[t])
+    flows[5] += np.float32([24, 0]); flows[6] += np.float32([0, -24])      # pairs 5, 6: low octaves only AND a 24 px flow error
+    feats[11] = (feats[11][0], rng.integers(0, 256, feats[11][1].shape, dtype=np.uint8))   # pairs 10, 11: noise descriptors
+    flows[13] += np.float32([500, 300])                                     # pair 13: windows land nowhere near
+    ex = ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=1)
+    cap = ex.cap
+    ex.close()
+    kps = np.zeros((B + 1, cap), O.KP_DTYPE); desc = np.zeros((B + 1, cap, 32), np.uint8); cnt = np.zeros(B + 1, np.int32)
+    for t, (k, d) in enumerate(feats):
+        kps[t, :len(k)] = k; desc[t, :len(k)] = d; cnt[t] = len(k)
+    want_n, want_m, n15 = [], [], []
+    for p in range(B):
+        (k0, d0), (k1, d1) = feats[p], feats[p + 1]
+        n, m = O.match_consecutive(k0, d0, k1, d1, flows[p], float(W), float(H), 15.0, sf)
+        want_n.append(n); want_m.append(m)
+        uv = _queries(k0, flows[p])
+        n15.append(O.search_by_projection(k1, d1, uv, k0["octave"], k0["angle"], d0, np.ones(len(k0), np.uint8), (0, W, 0, H), 15.0, sf)[0])
+    n15 = np.array(n15); want_n = np.array(want_n)
+    assert ((n15 >= 20)).sum() >= 8                                         # ordinary pairs
+    assert ((n15 < 20) & (want_n >= 20)).sum() >= 2, (n15, want_n)          # recovered by the 2*th retry
+    assert ((n15 < 20) & (want_n < 20)).sum() >= 2, (n15, want_n)           # fail at both thresholds
+    tk = torch.from_numpy(kps.view(np.uint8).reshape(B + 1, cap, 28).copy()).cuda()
+    td = torch.from_numpy(desc).cuda(); tc = torch.from_numpy(cnt).cuda(); tf = torch.from_numpy(flows).cuda()
+    match = torch.full((B, cap), -2, dtype=torch.int32, device="cuda"); nm = torch.zeros(B, dtype=torch.int32, device="cuda")
+    m = ORBmatcher(0.9, True, max_feats=cap, max_batch=B)
+    torch.cuda.synchronize()
+    for _ in range(2):                                                      # second call: scratch state left by the first must not matter
+        m.match_consecutive_ptr(B, cap, tk.data_ptr(), td.data_ptr(), tc.data_ptr(), tf.data_ptr(), float(W), float(H), 15.0, sf,
+                                match.data_ptr(), nm.data_ptr())
+        torch.cuda.synchronize()
+        gm = match.cpu().numpy(); gn = nm.cpu().numpy()
+        assert np.array_equal(gn, want_n), (gn, want_n)
+        for p in range(B):
+            assert np.array_equal(gm[p, :cnt[p + 1]], want_m[p]), p
+    m.close()
+
+
 def _feats_small(t, w=640, h=480):
     orc = O.OrbOracle(500, 1.2, 8, 20, 7)
     return orc.extract(synth.frame(t, w=w, h=h)), orc.tables()["scale"]
@@ -147,6 +202,7 @@ def test_search_map_points_matches_oracle():
     uv = (np.stack([k["x"][sel], k["y"][sel]], axis=1) + rng.normal(0, 1.5, (nq, 2))).astype(np.float32)
     lv = np.clip(k["octave"][sel] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
     vc = rng.uniform(0.99, 1.0, nq).astype(np.float32)
+    vc[::9] = np.float32(0.998)   # float32(0.998) > the double literal 0.998 the reference compares with: r = 2.5
     qd = d[sel].copy(); qd[np.arange(nq), rng.integers(0, 32, nq)] ^= rng.integers(0, 256, nq).astype(np.uint8)
     iv = (rng.uniform(size=nq) > 0.1).astype(np.uint8); ob = (rng.uniform(size=nq) > 0.3).astype(np.uint8)
     has = (rng.uniform(size=len(k)) > 0.9).astype(np.uint8)

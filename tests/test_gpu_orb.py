@@ -197,3 +197,30 @@ def test_resident_batch_chunked_over_streams_matches_single_pass(monkeypatch):
         for t in range(n):
             c = outs[0][2][t]
             assert np.array_equal(o[0][t, :c], outs[0][0][t, :c]) and np.array_equal(o[1][t, :c], outs[0][1][t, :c])
+
+
+@pytest.mark.parametrize("size", [(1920, 1080, 1000), (701, 403, 777), (330, 250, 200)])
+def test_fused_fast_cells_equals_the_unfused_pair(monkeypatch, size):
+    """The hot path's fused kernel (k_fast_cells: score -> per-cell NMS -> candidates, no score map in HBM) against the
+    round-1 pair k_fast_score -> k_cells on the same resident frames: identical per-cell candidate lists on every level
+    (class A tiles: cells <= 32 px; class B: the small levels with larger cells), then identical keypoints / descriptors
+    from an extractor that runs the unfused pair end to end (PGB_UNFUSED=1)."""
+    w, h, nf = size
+    frames = np.stack([synth.frame(t, w=w, h=h) for t in range(2)] +
+                      [np.random.default_rng(5).integers(0, 256, (h, w), dtype=np.uint8)])     # + a noise frame (slow NMS path)
+    ex = _mk(nf, w, h, batch=3)
+    k1, d1, c1 = ex.extract_batch(frames)
+    fused = [[ex.candidates(l, frame=f) for l in range(8)] for f in range(3)]
+    ex.run_stage(2); ex.check()                                                              # recompute the slots with the unfused pair
+    for f in range(3):
+        for l in range(8):
+            assert np.array_equal(ex.candidates(l, frame=f), fused[f][l]), (f, l)
+    assert sum(len(c) for c in fused[0]) > 100
+    ex.close()
+    monkeypatch.setenv("PGB_UNFUSED", "1")
+    ex2 = _mk(nf, w, h, batch=3)
+    k2, d2, c2 = ex2.extract_batch(frames)
+    ex2.close()
+    assert np.array_equal(c1, c2)
+    for f in range(3):
+        assert np.array_equal(k1[f, :c1[f]], k2[f, :c1[f]]) and np.array_equal(d1[f, :c1[f]], d2[f, :c1[f]])

@@ -54,6 +54,7 @@ def test_search_map_points_against_brute_force():
     uv = np.stack([k["x"][sel], k["y"][sel]], axis=1) + rng.normal(0, 1.5, (300, 2)).astype(np.float32)
     lv = np.clip(k["octave"][sel] + rng.integers(0, 2, 300), 0, 7).astype(np.int32)
     vc = rng.uniform(0.99, 1.0, 300).astype(np.float32)
+    vc[::9] = np.float32(0.998)   # float32(0.998) > the double literal 0.998 the reference compares with: r = 2.5
     qd = d[sel].copy(); flip = rng.integers(0, 32, 300); qd[np.arange(300), flip] ^= rng.integers(0, 256, 300).astype(np.uint8)
     iv = (rng.uniform(size=300) > 0.1).astype(np.uint8); ob = (rng.uniform(size=300) > 0.3).astype(np.uint8)
     has = (rng.uniform(size=len(k)) > 0.9).astype(np.uint8)
@@ -67,7 +68,7 @@ def test_search_map_points_against_brute_force():
     for i in range(300):
         if not iv[i]:
             continue
-        r = np.float32(2.5 if vc[i] > 0.998 else 4.0) * np.float32(th) * sf[lv[i]]
+        r = np.float32(2.5 if float(vc[i]) > 0.998 else 4.0) * np.float32(th) * sf[lv[i]]
         ok = ingrid & (np.abs(k["x"] - uv[i, 0]) < r) & (np.abs(k["y"] - uv[i, 1]) < r) & (k["octave"] >= lv[i] - 1) & (k["octave"] <= lv[i])
         # GetFeaturesInArea's cell clipping can only drop keypoints outside the +-r box, never inside: no extra test
         idx = np.nonzero(ok & ~observed)[0]

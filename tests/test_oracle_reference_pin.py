@@ -346,6 +346,7 @@ def test_search_map_points_equals_the_reference_source(ref):
     uv = (np.stack([k["x"][sel], k["y"][sel]], axis=1) + rng.normal(0, 1.5, (nq, 2))).astype(np.float32)
     lv = np.clip(k["octave"][sel] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
     vc = rng.uniform(0.99, 1.0, nq).astype(np.float32)
+    vc[::9] = np.float32(0.998)   # float32(0.998) > the double literal 0.998 the reference compares with: r = 2.5
     qd = d[sel].copy(); qd[np.arange(nq), rng.integers(0, 32, nq)] ^= rng.integers(0, 256, nq).astype(np.uint8)
     iv = (rng.uniform(size=nq) > 0.1).astype(np.uint8); ob = (rng.uniform(size=nq) > 0.3).astype(np.uint8)
     has = (rng.uniform(size=len(k)) > 0.9).astype(np.uint8)
