@@ -15,7 +15,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/pgb200_imu_core.h"
@@ -377,6 +379,22 @@ void make_intervals(const std::vector<int64_t>& ref, const std::vector<int64_t>&
   ioff[ref.size()] = (int)ivM.size();
 }
 
+// PGB_IMU_TIMING=1: wall time of every phase of a fit (stream synchronised at the marks) on stderr -- the breakdown
+// profiles/r02_calibration_phases.txt was taken with it.
+struct PhaseTimer {
+  bool on;
+  cudaStream_t s;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(cudaStream_t st) : on(getenv("PGB_IMU_TIMING") != nullptr), s(st), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pgb_imu] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 template <typename T>
 int upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t s) {
   if (d.n < h.size() || !d.p) { if (d.alloc(h.size())) return PGB_ERR_CUDA; }
@@ -396,8 +414,10 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
   int rc = check_increasing(gps_t, n_gps, "GPS");
   if (rc) return rc;
   o->windowReady = false;
+  PhaseTimer pt(o->stream);
   o->gpsT.assign(gps_t, gps_t + n_gps);
   make_intervals(o->gpsT, o->mergedT, o->ioff, o->ivM, o->ivRef, o->ivDur);
+  pt.mark("host: make_intervals");
   const int allWin = (n_gps + step - 1) / step;
   if (first_window < 0 || first_window > allWin) return fail(PGB_ERR_INVALID, "first_window out of range");
   if (n_windows < 0 || first_window + n_windows > allWin) n_windows = allWin - first_window;
@@ -426,14 +446,17 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
       ensure(o->dFx, nW) || ensure(o->dIt, nW) || ensure(o->dNe, nW) || ensure(o->dOut10, 16))
     return PGB_ERR_CUDA;
   if (nW == 0) { PGB_CUDA(cudaStreamSynchronize(s)); return PGB_OK; }
+  pt.mark("uploads + allocations");
   k_imu_sweep<<<(n_gps + 63) / 64, 64, 0, s>>>(n_gps, o->dIoff.p, o->dIvM.p, o->dIvDur.p, o->dMG.p, o->dMA.p,
                                                 o->dGyro.p, o->dAcc.p, o->dLoc.p);
   PGB_CHECK_LAUNCH();
+  pt.mark("k_imu_sweep");
   k_imu_chain<<<((int)nW + 63) / 64, 64, 0, s>>>((int)nW, o->dWin.p, o->dLoc.p, o->dGpsV.p, maxRefs, o->dRec.p, o->dTotal.p);
   PGB_CHECK_LAUNCH();
   o->hTotal.resize(nW);
   PGB_CUDA(cudaMemcpyAsync(o->hTotal.data(), o->dTotal.p, nW * sizeof(long long), cudaMemcpyDeviceToHost, s));
   PGB_CUDA(cudaStreamSynchronize(s));  // gv and the host vectors were sources of async copies
+  pt.mark("k_imu_chain");
   o->windowReady = true;
   return PGB_OK;
 }
@@ -632,10 +655,13 @@ int pgb_imu_fit_windows_fwd(pgb_imu* o, const double* gps_v, const int64_t* gps_
   if (speed_sum) memset(speed_sum, 0, M * sizeof(double));
   if (speed_cnt) memset(speed_cnt, 0, M * sizeof(int32_t));
   if (nW == 0) return PGB_OK;
+  PhaseTimer pt(o->stream);
   rc = solve(o, max_iterations, epsilon, 0);
   if (rc) return rc;
+  pt.mark("k_imu_solve");
   rc = speeds(o, false, fwd_sum_xyz != nullptr, fwd_min_velocity);
   if (rc) return rc;
+  pt.mark("k_imu_speeds");
   cudaStream_t s = o->stream;
   std::vector<int> its(nW);
   std::vector<double> fwd;
@@ -658,6 +684,7 @@ int pgb_imu_fit_windows_fwd(pgb_imu* o, const double* gps_v, const int64_t* gps_
         if (firstIv[i] < 0) firstIv[i] = k;
         lastIv[i] = k;
       }
+      pt.mark("host: event runs");
       if (upload(o->dFirstIv, firstIv, s) || upload(o->dLastIv, lastIv, s) || ensure(o->dSum, M) || ensure(o->dCnt, M))
         return PGB_ERR_CUDA;
       k_imu_average<<<(mc + 255) / 256, 256, 0, s>>>(mLo, mc, o->dFirstIv.p, o->dLastIv.p, o->dIvRef.p, nW, o->firstWin,
@@ -667,6 +694,7 @@ int pgb_imu_fit_windows_fwd(pgb_imu* o, const double* gps_v, const int64_t* gps_
       if (speed_sum) PGB_CUDA(cudaMemcpyAsync(speed_sum + mLo, o->dSum.p + mLo, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, s));
       if (speed_cnt) PGB_CUDA(cudaMemcpyAsync(speed_cnt + mLo, o->dCnt.p + mLo, (size_t)mc * sizeof(int), cudaMemcpyDeviceToHost, s));
       PGB_CUDA(cudaStreamSynchronize(s));  // firstIv/lastIv are host sources
+      pt.mark("k_imu_average + D2H");
     }
   }
   PGB_CUDA(cudaStreamSynchronize(s));
