@@ -248,12 +248,24 @@ PGB_HD void win_chain(WinState* w, const GpsLocal& g, double gps_speed, WinRec* 
   w->tau += g.dur;
 }
 
-/* AccelerometerCalibrator::eval (velocity.cc:41-180) on a chained window. x = (g, h, v0). */
-PGB_HD double imu_eval(const WinRec* rec, int n, long long total_usec, const double* x, double* grad) {
+/* AccelerometerCalibrator::eval (velocity.cc:41-180) on a chained window. x = (g, h, v0).
+ *
+ * Summation shape (part of the contract).  The reference adds the per-GPS-interval terms of the loss and of the
+ * gradient sequentially; here the sum over the window's n records has the shape of ONE WARP:
+ *   lane l (0..31) adds the terms of records l, l+32, l+64, ... in ascending order onto +0.0   (imu_eval_lane);
+ *   then five butterfly steps k = 16, 8, 4, 2, 1: every lane replaces its partial P_l by P_l + P_(l xor k);
+ *   the result is lane 0's value (IEEE addition is commutative, so all 32 lanes end with identical bits).
+ * The device runs one warp per window and does the butterfly with __shfl_xor_sync (csrc/imu.cu: k_imu_solve); the host
+ * emulation below walks the same 32 partials.  Per evaluation this differs from the sequential order by rounding only
+ * (<= 1e-15 relative on loss and gradient, asserted against the literal restatement in tests/test_oracle_calib.py). */
+enum { PGB_EVAL_LANES = 32 };
+
+/* Partial sums of lane `lane`: acc[0] = sum e^2, acc[1..3] = grad_g, acc[4..6] = grad_h, acc[7..9] = grad_v0 terms. */
+PGB_HD void imu_eval_lane(const WinRec* rec, int n, int lane, const double* x, double* acc) {
   const V3 g = v3(x[0], x[1], x[2]), h = v3(x[3], x[4], x[5]), v0 = v3(x[6], x[7], x[8]);
   double loss = 0.0;
   V3 gg = v3(0, 0, 0), gh = v3(0, 0, 0), gv = v3(0, 0, 0);
-  for (int j = 0; j < n; j++) {
+  for (int j = lane; j < n; j += PGB_EVAL_LANES) {
     const WinRec& r = rec[j];
     V3 D = add(add(scale(v0, r.T), r.a), add(mv(r.B, h), scale(g, r.c)));
     const double dn = norm3(D);
@@ -265,11 +277,31 @@ PGB_HD double imu_eval(const WinRec* rec, int n, long long total_usec, const dou
     gh = add(gh, mtv(r.MW, dL));
     gv = add(gv, scale(dL, r.T));
   }
+  acc[0] = loss;
+  acc[1] = gg.x; acc[2] = gg.y; acc[3] = gg.z;
+  acc[4] = gh.x; acc[5] = gh.y; acc[6] = gh.z;
+  acc[7] = gv.x; acc[8] = gv.y; acc[9] = gv.z;
+}
+
+/* Normalisation by the window's total time (velocity.cc:176-179); returns the loss. */
+PGB_HD double imu_eval_finish(const double* acc, long long total_usec, double* grad) {
   const double total = (double)total_usec * 1e-6;
-  grad[0] = gg.x / total; grad[1] = gg.y / total; grad[2] = gg.z / total;
-  grad[3] = gh.x / total; grad[4] = gh.y / total; grad[5] = gh.z / total;
-  grad[6] = gv.x / total; grad[7] = gv.y / total; grad[8] = gv.z / total;
-  return loss / total;
+  for (int i = 0; i < 9; i++) grad[i] = acc[1 + i] / total;
+  return acc[0] / total;
+}
+
+/* The whole evaluation by ONE thread (host side of the contract, and the single-thread device paths): emulates the 32
+ * lanes and the butterfly. */
+PGB_HD double imu_eval(const WinRec* rec, int n, long long total_usec, const double* x, double* grad) {
+  double P[PGB_EVAL_LANES][10], T[PGB_EVAL_LANES][10];
+  for (int l = 0; l < PGB_EVAL_LANES; l++) imu_eval_lane(rec, n, l, x, P[l]);
+  for (int k = PGB_EVAL_LANES / 2; k >= 1; k >>= 1) {
+    for (int l = 0; l < PGB_EVAL_LANES; l++)
+      for (int i = 0; i < 10; i++) T[l][i] = P[l][i] + P[l ^ k][i];
+    for (int l = 0; l < PGB_EVAL_LANES; l++)
+      for (int i = 0; i < 10; i++) P[l][i] = T[l][i];
+  }
+  return imu_eval_finish(P[0], total_usec, grad);
 }
 
 /* ---------------------------------------------------------------- L-BFGS (LBFGS.h:79-182, LineSearch.h:41-111) */
@@ -295,10 +327,15 @@ PGB_HD double dot9(const double* a, const double* b) {
 
 /* Returns the iteration count (as LBFGSSolver::minimize) or a negative status: -4 when the line-search step
  * leaves [min_step, max_step] (the reference throws std::runtime_error there). n is fixed at 9, m at 6. */
+/* ws: storage for the m = 6 correction pairs, 2 * 6 * 9 doubles (the device keeps it in shared memory, one block per
+ * window: every lane of the window's warp runs this function redundantly on identical values). */
+enum { PGB_LBFGS_WS_DOUBLES = 2 * 6 * 9 };
 template <typename F>
-PGB_HD int lbfgs_minimize9(F& f, double* x, double* fx_out, const LbfgsParam& P, int* n_eval) {
+PGB_HD int lbfgs_minimize9(F& f, double* x, double* fx_out, const LbfgsParam& P, int* n_eval, double* ws) {
   const int n = 9, m = 6;
-  double S[6][9], Y[6][9], ys_h[6], alpha[6];
+  double (*S)[9] = reinterpret_cast<double (*)[9]>(ws);
+  double (*Y)[9] = reinterpret_cast<double (*)[9]>(ws + 6 * 9);
+  double ys_h[6], alpha[6];
   double xp[9], grad[9], gradp[9], drt[9];
   int evals = 0;
   double fx = f(x, grad);

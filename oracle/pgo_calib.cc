@@ -465,7 +465,8 @@ int pgo_calib_minimize_core(pgo_calib* c, double* x, double* fx, int max_iterati
   } f{c};
   pgbimu::LbfgsParam P = pgbimu::lbfgs_default();
   P.epsilon = epsilon; P.max_iterations = max_iterations;
-  return pgbimu::lbfgs_minimize9(f, x, fx, P, n_eval);
+  double ws[pgbimu::PGB_LBFGS_WS_DOUBLES];
+  return pgbimu::lbfgs_minimize9(f, x, fx, P, n_eval, ws);
 }
 
 static int64_t dump_traj(const std::map<size_t, TrajPoint>& tr, int64_t cap, int64_t* idx, double* speed, double* quat,

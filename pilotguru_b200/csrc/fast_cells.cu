@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kFcThreads, kOcc) k_fast_cells(const __grid_co
     if (b == 0 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile)[lane] = zero;
     if (b == nb - 1 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile + (8 * nb + 1) * kSP)[lane] = zero;
   }
+  if (tid < kc) cnt[tid] = 0;  // cells without survivors; the others are overwritten after the NMS (ordered by the barriers)
+  if (tid == 0) sCorner[8] = 0;  // survivor count of the tile
   __syncthreads();  // mbarrier initialised before anyone polls it
   while (!mbar_try_wait(bar, 0)) {
   }
@@ -261,39 +263,105 @@ __global__ void __launch_bounds__(kFcThreads, kOcc) k_fast_cells(const __grid_co
   __syncthreads();  // every score of the tile is in shared memory
 
   // ================================================================ NMS: 3x3 inside the corner's own cell
+  // Survivors go to ONE list per tile (in the input stage, dead since the barrier): cell | row | x | score.  A tile has
+  // ~20 of them on natural images; the list holds kFcListCap.  If it overflows (noise), the NMS is repeated into per-row
+  // bitmaps and the cells are emitted from those (the general, slower path below).
   const uint32_t recip = L.fcRecip;  // (x * recip) >> 16 = x / wCell for x < 1024
-  for (int b = warp; b < nb; b += kFcWarps) {
-    const int nC = sCorner[b];
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(smem + lay.queue + b * kFcQueueBytes);
-    uint32_t* bm = reinterpret_cast<uint32_t*>(smem + lay.queue + b * kFcQueueBytes + kQCap * 4);  // [8 rows][8 words]
-    if (nC >= 0) {
-      for (int i = lane; i < nC; i += 32) {
-        const uint32_t e = q[i];
-        const int x = e & 0xff, row = (e >> 8) & 0xff, s = e >> 16;
+  uint32_t* sList = reinterpret_cast<uint32_t*>(smem);  // [kFcListCap] survivors, then [kFcListCap] packed rank counters
+  uint32_t* sRank = sList + kFcListCap;                 // (four 8-bit counts: the list holds <= 128 survivors)
+  int* sN = sCorner + 8;
+  if (tid < kFcListCap) sRank[tid] = 0u;
+  auto nms_pass = [&](const bool toBitmap) {
+    for (int b = warp; b < nb; b += kFcWarps) {
+      const int nC = sCorner[b];
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(smem + lay.queue + b * kFcQueueBytes);
+      uint32_t* bm = reinterpret_cast<uint32_t*>(smem + lay.queue + b * kFcQueueBytes + kQCap * 4);  // [8 rows][8 words]
+      auto test = [&](int x, int row, int sc) {
         const int rel = x - xoff;
-        const int c0 = (int)(((uint32_t)rel * recip) >> 16) * wCell;
-        const bool first = rel == c0, last = rel == c0 + wCell - 1;
-        if (nms_keep(sTile + row * kSP + x, s, first, last)) atomicOr(bm + (row & 7) * 8 + (x >> 5), 1u << (x & 31));
-      }
-    } else {  // slow path: every non-zero score of the band
+        const int c = (int)(((uint32_t)rel * recip) >> 16), c0 = c * wCell;
+        if (nms_keep(sTile + row * kSP + x, sc, rel == c0, rel == c0 + wCell - 1)) {
+          if (toBitmap) atomicOr(bm + (row & 7) * 8 + (x >> 5), 1u << (x & 31));
+          else {
+            const int pos = atomicAdd(sN, 1);
+            if (pos < kFcListCap) sList[pos] = ((uint32_t)c << 24) | ((uint32_t)row << 16) | ((uint32_t)x << 8) | (uint32_t)sc;
+          }
+        }
+      };
+      if (nC >= 0) {
+        for (int i = lane; i < nC; i += 32) {
+          const uint32_t e = q[i];
+          test((int)(e & 0xff), (int)((e >> 8) & 0xff), (int)(e >> 16));
+        }
+      } else {  // the band's queue was refilled per row (> kQCap candidates): every non-zero score of the band
 #pragma unroll 1
-      for (int j = 0; j < 8; j++) {
-        const uint8_t* rowp = sTile + (8 * b + j) * kSP;
-#pragma unroll 1
-        for (int k = 0; k < 8; k++) {
-          const int x = 8 * lane + k, s = rowp[x];
-          if (s == 0) continue;
-          const int rel = x - xoff;
-          const int c0 = (int)(((uint32_t)rel * recip) >> 16) * wCell;
-          if (nms_keep(rowp + x, s, rel == c0, rel == c0 + wCell - 1)) atomicOr(bm + j * 8 + (x >> 5), 1u << (x & 31));
+        for (int j = 0; j < 8; j++) {
+          const uint8_t* rowp = sTile + (8 * b + j) * kSP;
+          const uint2 v = *reinterpret_cast<const uint2*>(rowp + 8 * lane);
+          uint32_t nzLo = (((v.x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v.x) & 0x80808080u;
+          uint32_t nzHi = (((v.y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v.y) & 0x80808080u;
+          while (nzLo | nzHi) {
+            const bool inLo = nzLo != 0;
+            uint32_t& m = inLo ? nzLo : nzHi;
+            const int k = (31 - __clz(m & (0u - m))) >> 3;
+            m &= m - 1;
+            const int x = 8 * lane + k + (inLo ? 0 : 4);
+            test(x, 8 * b + j, (int)rowp[x]);
+          }
         }
       }
     }
+  };
+  nms_pass(false);
+  __syncthreads();  // every survivor is in the list (or the list overflowed)
+
+  const int iniTh = g.iniTh;
+  const int nSurv = *sN;
+  if (nSurv <= kFcListCap) {
+    // ================================================================ emission from the list
+    // A survivor's slot in its cell = number of survivors of the same cell that precede it in the reference's row-major
+    // order, counted among those with score >= iniTh if the cell has any such (then the others are dropped: the cell was
+    // detected at iniThFAST), among all otherwise (the cell went to the minThFAST retry).  The n x n comparison is split
+    // over the CTA: lane = survivor i (chunks of 32), warp = a quarter of the partners j (shared-memory broadcasts);
+    // the four partial counts meet in shared-memory atomics.  (One warp doing all of it was a serial tail: the other
+    // three had exited but the CTA's shared memory stayed allocated.)
+    const int jq = (nSurv + kFcWarps - 1) / kFcWarps, j0 = warp * jq, j1 = min(j0 + jq, nSurv);
+    for (int base = 0; base < nSurv; base += 32) {
+      const int i = base + lane;
+      const uint32_t ai = (i < nSurv ? sList[i] : 0xffffffffu) >> 8;  // cell | row | x
+      int cntAll = 0, cnt20 = 0, lessAll = 0, less20 = 0;
+      for (int j = j0; j < j1; j++) {
+        const uint32_t e = sList[j], a = e >> 8;
+        const bool same = (a ^ ai) < 0x10000u, hi = (int)(e & 0xffu) >= iniTh, less = a < ai;
+        cntAll += same;
+        cnt20 += same && hi;
+        lessAll += same && less;
+        less20 += same && hi && less;
+      }
+      if (i < nSurv && j1 > j0) atomicAdd(&sRank[i], (uint32_t)cntAll | ((uint32_t)cnt20 << 8) | ((uint32_t)lessAll << 16) | ((uint32_t)less20 << 24));
+    }
+    __syncthreads();
+    for (int i = tid; i < nSurv; i += kFcThreads) {
+      const uint32_t ei = sList[i], rk = sRank[i];
+      const int c = (int)(ei >> 24), row = (int)((ei >> 16) & 0xffu), x = (int)((ei >> 8) & 0xffu), sc = (int)(ei & 0xffu);
+      const int cntAll = rk & 0xff, cnt20 = (rk >> 8) & 0xff, lessAll = (rk >> 16) & 0xff, less20 = rk >> 24;
+      const bool any20 = cnt20 > 0;
+      if (!any20 || sc >= iniTh) {
+        const int pos = any20 ? less20 : lessAll, total = any20 ? cnt20 : cntAll;
+        uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)(ci0 * L.nCols + cj0 + c) * L.slotCap;
+        if (pos < L.slotCap)
+          slot[pos] = (uint32_t)(X0 - xoff + x - kMinBorder) | ((uint32_t)(Y0 + row - kMinBorder) << 12) | ((uint32_t)sc << 24);
+        if (pos == 0) {  // the cell's first candidate also reports the cell's count (cells without survivors keep the 0 written at the start)
+          if (total > L.slotCap) atomicOr(err, kErrCandOverflow);
+          cnt[c] = min(total, L.slotCap);
+        }
+      }
+    }
+    return;
   }
+  nms_pass(true);
   __syncthreads();  // every survivor bit is set
 
-  // ================================================================ emission: warp = cell, lane = tested row
-  const int iniTh = g.iniTh;
+  // ================================================================ emission from the bitmaps: warp = cell, lane = tested row
   for (int c = warp; c < kc; c += kFcWarps) {
     const int cx0 = xoff + c * wCell, cw = min(wCell, xoff + tw - cx0);  // the cell's columns in the lane frame
     uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)(ci0 * L.nCols + cj0 + c) * L.slotCap;

@@ -72,45 +72,69 @@ __global__ void k_imu_chain(int nWin, const WinDesc* __restrict__ win, const Gps
   totalUsec[w] = tot;
 }
 
-struct DevEval {
+// One warp per window: lane l holds the partial sums of records l, l + 32, ...; the butterfly is the contract's
+// (pgb200_imu_core.h: imu_eval).  Every lane ends with identical bits, so every lane can run the L-BFGS bookkeeping
+// redundantly -- no broadcasts, no divergence.
+struct WarpEval {
   const WinRec* rec;
-  int n;
+  int n, lane;
   long long total;
-  __device__ double operator()(const double* x, double* g) const { return imu_eval(rec, n, total, x, g); }
+  __device__ double operator()(const double* x, double* g) const {
+    double acc[10];
+    imu_eval_lane(rec, n, lane, x, acc);
+#pragma unroll
+    for (int k = PGB_EVAL_LANES / 2; k >= 1; k >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 10; i++) acc[i] = acc[i] + __shfl_xor_sync(0xffffffffu, acc[i], k);
+    }
+    return imu_eval_finish(acc, total, g);
+  }
 };
 
-__global__ void k_imu_eval(const WinRec* __restrict__ rec, int n, long long total, const double* __restrict__ x,
-                           double* __restrict__ out10) {
-  if (blockIdx.x * blockDim.x + threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_imu_eval(const WinRec* __restrict__ rec, int n, long long total,
+                                                 const double* __restrict__ x, double* __restrict__ out10) {
   double xx[9], g[9];
   for (int i = 0; i < 9; i++) xx[i] = x[i];
-  out10[0] = imu_eval(rec, n, total, xx, g);
-  for (int i = 0; i < 9; i++) out10[1 + i] = g[i];
+  WarpEval f{rec, n, (int)threadIdx.x, total};
+  const double loss = f(xx, g);
+  if (threadIdx.x == 0) {
+    out10[0] = loss;
+    for (int i = 0; i < 9; i++) out10[1 + i] = g[i];
+  }
 }
 
-__global__ void __launch_bounds__(32) k_imu_solve(int nWin, const WinDesc* __restrict__ win, int recStride,
-                                                  const WinRec* __restrict__ rec, const long long* __restrict__ totalUsec,
-                                                  int maxIter, double epsilon, int useX0, double* __restrict__ xOut,
-                                                  double* __restrict__ fxOut, int* __restrict__ itOut,
-                                                  int* __restrict__ evalOut) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nWin) return;
+// The whole L-BFGS of a window (<= 500 iterations, ~1.2 evaluations each) by one warp; kSolveWarps windows per CTA.  The
+// round-1 kernel ran one THREAD per window (720 threads on 148 SMs for BASELINE configs[3]): 60 of the fit's 80 ms
+// (profiles/r02_calibration_phases.txt); per evaluation it walked the window's 39 records sequentially.
+constexpr int kSolveWarps = 4;
+__global__ void __launch_bounds__(kSolveWarps * 32) k_imu_solve(int nWin, const WinDesc* __restrict__ win, int recStride,
+                                                               const WinRec* __restrict__ rec,
+                                                               const long long* __restrict__ totalUsec, int maxIter,
+                                                               double epsilon, int useX0, double* __restrict__ xOut,
+                                                               double* __restrict__ fxOut, int* __restrict__ itOut,
+                                                               int* __restrict__ evalOut) {
+  __shared__ double sWs[kSolveWarps][PGB_LBFGS_WS_DOUBLES];  // the correction pairs S, Y of each window
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * kSolveWarps + warp;
+  if (w >= nWin) return;  // warp-uniform
   double x[9];
   for (int i = 0; i < 9; i++) x[i] = useX0 ? xOut[(size_t)w * 9 + i] : 0.0;
   const int n = win[w].e - win[w].s - 1;
   double fx = 0.0;
   int it = 0, ne = 0;
   if (n > 0 && totalUsec[w] > 0) {
-    DevEval f{rec + (size_t)w * recStride, n, totalUsec[w]};
+    WarpEval f{rec + (size_t)w * recStride, n, lane, totalUsec[w]};
     LbfgsParam P = lbfgs_default();
     P.epsilon = epsilon;
     P.max_iterations = maxIter;
-    it = lbfgs_minimize9(f, x, &fx, P, &ne);
+    it = lbfgs_minimize9(f, x, &fx, P, &ne, sWs[warp]);
   }
-  for (int i = 0; i < 9; i++) xOut[(size_t)w * 9 + i] = x[i];
-  fxOut[w] = fx;
-  itOut[w] = it;
-  if (evalOut) evalOut[w] = ne;
+  if (lane == 0) {
+    for (int i = 0; i < 9; i++) xOut[(size_t)w * 9 + i] = x[i];
+    fxOut[w] = fx;
+    itOut[w] = it;
+    if (evalOut) evalOut[w] = ne;
+  }
 }
 
 // K10: per sub-interval speed (and optionally orientation / velocity) with the fitted parameters.
@@ -464,7 +488,7 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
 int solve(pgb_imu* o, int maxIter, double eps, int useX0) {
   const int nW = (int)o->win.size();
   if (nW == 0) return PGB_OK;
-  k_imu_solve<<<(nW + 31) / 32, 32, 0, o->stream>>>(nW, o->dWin.p, o->maxRefs, o->dRec.p, o->dTotal.p, maxIter, eps, useX0,
+  k_imu_solve<<<(nW + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, 0, o->stream>>>(nW, o->dWin.p, o->maxRefs, o->dRec.p, o->dTotal.p, maxIter, eps, useX0,
                                                     o->dX.p, o->dFx.p, o->dIt.p, o->dNe.p);
   PGB_CHECK_LAUNCH();
   return PGB_OK;

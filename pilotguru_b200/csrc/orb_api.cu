@@ -76,6 +76,7 @@ struct pgb_orb {
   DevBuf<int4> tileTab;
   TmapIn tmapsFc{};     // fused kernel: per level, box height of the level's class
   TmapIn tmapsFcCur{};  // = tmapsFc, with in[0] on the caller's buffer while level 0 is read in place
+  TmapIn tmapsPy{}, tmapsPyCur{};  // pyramid kernel: source-footprint boxes (kPySrcPitch x kPySrcRows) of every level
   DevBuf<int4> fcTabA, fcTabB;  // fused kernel tile tables: level, first tested x, first tested y, cell row | first cell column << 16
   bool unfused = false;  // PGB_UNFUSED=1: the round-1 pair k_fast_score -> k_cells instead of k_fast_cells (A/B, stage debugging)
   bool scoreValid = false;  // the score map of the resident batch has been produced (only the unfused path writes it)
@@ -276,6 +277,11 @@ int build_tmaps(pgb_orb* o) {
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(fused load, level %d) failed: %d", l, (int)r);
+    const cuuint32_t boxPy[3] = {(cuuint32_t)(kPySrcPitch / 4), (cuuint32_t)kPySrcRows, 1};
+    r = encode(&o->tmapsPy.in[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->pyr.p + L.off, dims, strides, boxPy, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(pyramid source, level %d) failed: %d", l, (int)r);
   }
   return PGB_OK;
 }
@@ -306,6 +312,12 @@ int use_external_level0(pgb_orb* o, const uint8_t* gray, size_t pitch, size_t fr
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(external level 0, fused) failed: %d", (int)r);
+  o->tmapsPyCur = o->tmapsPy;
+  const cuuint32_t boxPy[3] = {(cuuint32_t)(kPySrcPitch / 4), (cuuint32_t)kPySrcRows, 1};
+  r = encode(&o->tmapsPyCur.in[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(gray), dims, strides, boxPy, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(external level 0, pyramid) failed: %d", (int)r);
   o->geo.ext0 = gray;
   o->geo.ext0Stride = frame_stride;
   o->geo.ext0Pitch = (int)pitch;
@@ -388,6 +400,7 @@ int ensure_score(pgb_orb* o) {
     } else {
       o->tmapsCur = o->tmaps;
       o->tmapsFcCur = o->tmapsFc;
+      o->tmapsPyCur = o->tmapsPy;
     }
   }
   return PGB_OK;
@@ -412,7 +425,7 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
     switch (s) {
       case 0:
         for (int l = 1; l < g.nlevels; l++)
-          launch_pyramid_level(g, l, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l],
+          launch_pyramid_level(g, o->tmapsPyCur, l, f0, n, pyr, o->xtab.p + o->xtabOff[l], o->ytab.p + o->ytabOff[l],
                                o->tileX.p + o->tileXOff[l], o->tileY.p + o->tileYOff[l], st);
         break;
       case 1:
@@ -686,6 +699,7 @@ int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames
   o->geo.ext0 = nullptr;
   o->tmapsCur = o->tmaps;
   o->tmapsFcCur = o->tmapsFc;
+  o->tmapsPyCur = o->tmapsPy;
   o->scoreValid = false;
   if (inDev && ((size_t)gray & 15) == 0 && (pitch & 15) == 0 && (frame_stride & 15) == 0 && frame_stride >= pitch * (size_t)height) {
     // level 0 is read in place: no copy; the frames must stay valid until the next extract call on this handle

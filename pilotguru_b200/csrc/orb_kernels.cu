@@ -10,7 +10,10 @@
 #include <cuda_runtime.h>
 
 #include "../../include/pgb200_orb_pattern.h"
+#include <cstdlib>
+
 #include "common.cuh"
+#include "fast_common.cuh"
 #include "orb_kernels.cuh"
 
 namespace pgb {
@@ -133,16 +136,96 @@ __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint
   }
 }
 
-void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
-                          const ResizeTab* ytab, const int2* tileX, const int2* tileY, cudaStream_t st) {
+// Column-walk variant (round 2, the default): the round-1 profile of k_pyramid_tiled (profiles/r01e_other_kernels_sass_regions.md)
+// showed 4.7 M warp-instructions per frame, 42 % of them in a horizontal pass that went through shared memory as u16
+// (8.1 instructions per value) and 40 % in a vertical pass that read it back.  Here a thread owns ONE destination column
+// and walks down the tile: the horizontal interpolation of a source row is computed once (2 byte loads, 2 IMAD on the
+// FMA pipe, one shift), lives in a register, and is reused by the two destination rows that touch it -- the u16
+// intermediate never exists in shared memory.  Which source rows a destination row needs is warp-uniform (the row
+// table of the tile is in shared memory), so the walk has no divergence.  The source footprint comes in with one TMA
+// load (no staging instructions), the 256 x 32 result goes through an 8 KB shared tile so that global stores are
+// 16-byte vectors.  Same integer arithmetic as k_pyramid, bit for bit.
+__global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ OrbGeo g, const __grid_constant__ TmapIn tm,
+                                                      int level, int frame0, uint8_t* __restrict__ pyr,
+                                                      const ResizeTab* __restrict__ xtab, const ResizeTab* __restrict__ ytab,
+                                                      const int2* __restrict__ tileX, const int2* __restrict__ tileY) {
+  __shared__ __align__(128) uint8_t s_src[kPySrcRows * kPySrcPitch];
+  __shared__ __align__(16) uint8_t s_out[kPyH * kPyW];
+  __shared__ uint4 s_row[kPyH];
+  __shared__ __align__(8) uint64_t s_bar;
+  using namespace fastk;
   const LevelGeo& D = g.lv[level];
   const LevelGeo& S = g.lv[level - 1];
-  // does the source footprint of a 256x16 tile fit the static staging buffers?  (true for scale factors <= ~1.5)
-  const double rx = (double)S.w / D.w, ry = (double)S.h / D.h;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kPyW, y0 = blockIdx.y * kPyH;
+  const int2 fx = __ldg(&tileX[blockIdx.x]), fy = __ldg(&tileY[blockIdx.y]);
+  const int ax = fx.x, syLo = fy.x;  // first staged source byte (16-aligned) / row; the box is kPySrcPitch x kPySrcRows
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&s_bar, kPySrcRows * kPySrcPitch);
+    tma_load_3d(s_src, &tm.in[level - 1], ax >> 2, syLo, blockIdx.z + frame0, &s_bar);
+  }
+  if (tid < kPyH) {  // per destination row: byte offsets of its two source rows inside the staged box + the two coefficients
+    const ResizeTab ty = ytab[min(y0 + tid, D.h - 1)];
+    const int r0 = min(max((int)ty.s, 0), S.h - 1) - syLo, r1 = min(max((int)ty.s + 1, 0), S.h - 1) - syLo;
+    s_row[tid] = make_uint4((uint32_t)(r0 * kPySrcPitch), (uint32_t)(r1 * kPySrcPitch), (uint32_t)ty.a0, (uint32_t)ty.a1);
+  }
+  const int x = min(x0 + tid, D.w - 1);
+  const ResizeTab tx = xtab[x];
+  // the right neighbour is always read at +1: where cv::resize clamps it to the last column its coefficient a1 is 0
+  // (make_resize_tab, clampCoef), and the byte read instead is still inside the staged box
+  const uint8_t* c0 = s_src + (tx.s - ax);
+  const uint32_t a0 = (uint32_t)tx.a0, a1 = (uint32_t)tx.a1;
+  __syncthreads();
+  while (!mbar_try_wait(&s_bar, 0)) {
+  }
+  // Straight-line body, no reuse between rows (a version that kept the interpolated source rows in registers needed
+  // warp-uniform branches the compiler could not prove uniform: ~60 instructions per pixel instead of ~19, 7.7 us/frame).
+  // All coefficients are in [0, 2048] and the interpolated values below 2^15: unsigned arithmetic is exact.
+  const int rows = min(kPyH, D.h - y0);
+#pragma unroll 8
+  for (int ry = 0; ry < kPyH; ry++) {
+    const uint4 rw = s_row[ry];  // warp-uniform: one broadcast load
+    const uint8_t* p0 = c0 + rw.x;
+    const uint8_t* p1 = c0 + rw.y;
+    uint32_t h0, h1, t0, t1;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(h0) : "r"((uint32_t)p0[0]), "r"(a0));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h0) : "r"((uint32_t)p0[1]), "r"(a1));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(h1) : "r"((uint32_t)p1[0]), "r"(a0));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h1) : "r"((uint32_t)p1[1]), "r"(a1));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t0) : "r"(h0 >> 4), "r"(rw.z));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t1) : "r"(h1 >> 4), "r"(rw.w));
+    s_out[ry * kPyW + tid] = (uint8_t)(((t0 >> 16) + (t1 >> 16) + 2) >> 2);
+  }
+  __syncthreads();
+  // 256 x 32 bytes out as 16-byte vectors: thread = (row, 32-byte segment).  Segments start inside the level's pitch
+  // (a multiple of 64); bytes beyond the level's width land in the pitch padding, which no consumer reads.
+  {
+    const int ry = tid >> 3, seg = (tid & 7) * 32;
+    const int gx = x0 + seg;
+    if (ry < rows && gx < D.pitch) {
+      uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameStride + D.off + (size_t)(y0 + ry) * D.pitch + gx;
+      const uint4* src = reinterpret_cast<const uint4*>(s_out + ry * kPyW + seg);
+      reinterpret_cast<uint4*>(dst)[0] = src[0];
+      if (gx + 16 < D.pitch) reinterpret_cast<uint4*>(dst)[1] = src[1];
+    }
+  }
+}
+
+static bool g_pyrOld = getenv("PGB_PYR_OLD") != nullptr;  // A/B: the round-1 kernel
+
+void launch_pyramid_level(const OrbGeo& g, const TmapIn& tm, int level, int frame0, int nFrames, uint8_t* pyr,
+                          const ResizeTab* xtab, const ResizeTab* ytab, const int2* tileX, const int2* tileY,
+                          cudaStream_t st) {
+  const LevelGeo& D = g.lv[level];
+  const LevelGeo& S = g.lv[level - 1];
+  // does the source footprint of a 256x32 tile fit the static staging buffers?  (true for scale factors <= ~1.5)
   const bool fits = pyramid_tile_fits(S.w, S.h, D.w, D.h);
   if (fits) {
     dim3 grid((D.w + kPyW - 1) / kPyW, (D.h + kPyH - 1) / kPyH, nFrames);
-    k_pyramid_tiled<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab, tileX, tileY);
+    if (g_pyrOld) k_pyramid_tiled<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab, tileX, tileY);
+    else k_pyramid_walk<<<grid, 256, 0, st>>>(g, tm, level, frame0, pyr, xtab, ytab, tileX, tileY);
   } else {
     dim3 grid((((D.w + 3) >> 2) + 255) / 256, D.h, nFrames);
     k_pyramid<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab);

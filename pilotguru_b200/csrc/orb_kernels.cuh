@@ -46,6 +46,7 @@ constexpr int kFcInWords = 72;       // 288-byte staged input rows: <= 18 bytes 
 constexpr int kFcTilePitch = 272;    // score tile row: 16 pad bytes + 256 px
 constexpr int kFcQueueCap = 384;     // candidates per band queue (u32 flag + u8 code each)
 constexpr int kFcQueueBytes = kFcQueueCap * 5;
+constexpr int kFcListCap = 128;     // NMS survivors per tile kept in the list (natural images: ~20); more -> bitmap emission
 constexpr int kFcMaxFrame = 249;     // widest tested tile inside the 256-px lane frame (first pixel at offset 0..7)
 #ifndef PGB_FC_OCC
 #define PGB_FC_OCC 8
@@ -59,7 +60,7 @@ __host__ __device__ inline FcSmem fc_smem_layout(int nb) {
   s.tile = (kFcInWords * 4 * (8 * nb + 6) + 127) & ~127;
   s.queue = s.tile + (8 * nb + 2) * kFcTilePitch;
   s.misc = s.queue + nb * kFcQueueBytes;
-  s.total = s.misc + 64;  // mbarrier + per-band corner counts
+  s.total = s.misc + 64;  // mbarrier (16 B) + per-band corner counts (8 ints) + the tile's survivor count
   return s;
 }
 
@@ -128,8 +129,9 @@ struct StagedKp {
 
 enum OrbErr { kErrCandOverflow = 1, kErrNodeOverflow = 2, kErrOutCap = 4, kErrCellChunks = 8 };
 
-void launch_pyramid_level(const OrbGeo& g, int level, int nFrames, uint8_t* pyr, const ResizeTab* xtab,
-                          const ResizeTab* ytab, const int2* tileX, const int2* tileY, cudaStream_t st);
+void launch_pyramid_level(const OrbGeo& g, const TmapIn& tm, int level, int frame0, int nFrames, uint8_t* pyr,
+                          const ResizeTab* xtab, const ResizeTab* ytab, const int2* tileX, const int2* tileY,
+                          cudaStream_t st);
 int configure_fast_score();
 int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st);
