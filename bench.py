@@ -306,7 +306,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pilotguru_b200 import launch_count, synth
-    from pilotguru_b200.dist import FeatureExchange
+    from pilotguru_b200.dist import BoundaryExchange, FeatureExchange, PgbComm
     from pilotguru_b200.matcher import ORBmatcher
     from pilotguru_b200.orb import ORBextractor
 
@@ -334,7 +334,14 @@ def main():
     cap = ex.cap
     stream = torch.cuda.ExternalStream(ex.stream)
     mt = ORBmatcher(0.9, True, max_feats=cap, max_batch=B, device=local, stream=ex.stream)
-    xch = FeatureExchange(world, rank, B, cap, device=torch.device("cuda", local))
+    xch = FeatureExchange(1, 0, B, cap, device=torch.device("cuda", local))       # the rank's feature region (slot 0 = predecessor)
+    # N > 1: the C-ABI communicator (NCCL inside libpgb200.so) and a side stream on which the boundary exchange and the
+    # one pair that depends on it run while the main stream matches the other B-1 pairs
+    comm = PgbComm(local, rank, world) if world > 1 else None
+    side = torch.cuda.Stream() if world > 1 else None
+    mt_side = ORBmatcher(0.9, True, max_feats=cap, max_batch=1, device=local, stream=side.cuda_stream) if world > 1 else None
+    bx = BoundaryExchange(comm, xch) if world > 1 else None
+    ev_feat, ev_x = torch.cuda.Event(), torch.cuda.Event()
     flow_dev = torch.from_numpy(flows_np).cuda()
     match = torch.full((B, cap), -1, dtype=torch.int32, device="cuda")
     nmatch = torch.zeros(B, dtype=torch.int32, device="cuda")
@@ -347,12 +354,23 @@ def main():
     ex.check()
 
     def step(frames_ptr, where):
-        """extract B frames into this rank's slot of the exchange buffer, exchange, match B pairs."""
-        xch.carry_last()                                                   # slot 0 <- previous step's last frame
+        """extract B frames into slots 1..B of the rank's feature region, exchange the block boundary, match B pairs."""
         ex.extract_ptr(frames_ptr, where, B, W, H, W, W * H, xch.kps_ptr(1), xch.desc_ptr(1), xch.counts_ptr(1), cap)
-        xch.exchange(stream)                                               # N>1: one NCCL all-gather; slot 0 <- left neighbour's last frame
-        mt.match_consecutive_ptr(B, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), flow_dev.data_ptr(),
-                                 float(W), float(H), 15.0, sf, match.data_ptr(), nmatch.data_ptr())
+        if world == 1:
+            mt.match_consecutive_ptr(B, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), flow_dev.data_ptr(),
+                                     float(W), float(H), 15.0, sf, match.data_ptr(), nmatch.data_ptr())
+            return
+        # side stream: pack my last frame -> ONE NCCL all-gather of the boundary records (pgb_allgather_feats) -> unpack the
+        # left neighbour's into slot 0 -> match pair 0 (the only pair that needs it).  Main stream: pairs 1..B-1 meanwhile.
+        ev_feat.record(stream)
+        side.wait_event(ev_feat)
+        bx.issue(side.cuda_stream)
+        mt_side.match_consecutive_ptr(1, cap, xch.kps_ptr(0), xch.desc_ptr(0), xch.counts_ptr(0), flow_dev.data_ptr(),
+                                      float(W), float(H), 15.0, sf, match.data_ptr(), nmatch.data_ptr())
+        ev_x.record(side)
+        mt.match_consecutive_ptr(B - 1, cap, xch.kps_ptr(1), xch.desc_ptr(1), xch.counts_ptr(1), flow_dev.data_ptr() + 8,
+                                 float(W), float(H), 15.0, sf, match.data_ptr() + 4 * cap, nmatch.data_ptr() + 4)
+        stream.wait_event(ev_x)
 
     def timed(fn, n):
         if world > 1:
@@ -378,8 +396,9 @@ def main():
             region, pinned result buffers.  Two sets alternate so that the tail of step k (last chunk's kernels,
             matcher, D2H) overlaps the H2D of step k+1 -- the double buffering any streaming caller would use."""
 
-            def __init__(self, ex_, mt_, xch_):
+            def __init__(self, ex_, mt_, xch_, comm_):
                 self.ex, self.mt, self.xch = ex_, mt_, xch_
+                self.bx = BoundaryExchange(comm_, xch_) if world > 1 else None   # each in-flight set has its own communicator
                 self.stream = torch.cuda.ExternalStream(ex_.stream)
                 self.d2h = torch.cuda.Stream()
                 self.ev_feat = torch.cuda.Event()
@@ -394,10 +413,10 @@ def main():
             def issue(self):
                 x = self.xch
                 with torch.cuda.stream(self.stream):
-                    x.carry_last()
                     self.ex.extract_ptr(host_frames.data_ptr(), ORBextractor.OUT_DEVICE, B, W, H, W, W * H, x.kps_ptr(1),
                                         x.desc_ptr(1), x.counts_ptr(1), cap)   # H2D of the frames inside the call
-                    x.exchange(self.stream)
+                    if self.bx:
+                        self.bx.issue(self.stream.cuda_stream)                 # boundary record all-gather (C-ABI, NCCL)
                     self.ev_feat.record(self.stream)
                     with torch.cuda.stream(self.d2h):                          # D2H of the features while the matcher runs
                         self.d2h.wait_event(self.ev_feat)
@@ -415,10 +434,11 @@ def main():
 
         ex2 = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B, device=local)
         mt2 = ORBmatcher(0.9, True, max_feats=cap, max_batch=B, device=local, stream=ex2.stream)
-        xch2 = FeatureExchange(world, rank, B, cap, device=torch.device("cuda", local))
+        xch2 = FeatureExchange(1, 0, B, cap, device=torch.device("cuda", local))
         ex2.extract_ptr(pred.data_ptr(), 3, 1, W, H, W, W * H, xch2.kps_ptr(0), xch2.desc_ptr(0), xch2.counts_ptr(0), cap)
         ex2.check()
-        sets = [E2ESet(ex, mt, xch), E2ESet(ex2, mt2, xch2)]
+        comm2 = PgbComm(local, rank, world) if world > 1 else None
+        sets = [E2ESet(ex, mt, xch, comm), E2ESet(ex2, mt2, xch2, comm2)]
 
         def e2e_run(n):
             """n e2e steps, two in flight; returns after the results of all of them are on the host."""
@@ -474,6 +494,7 @@ def main():
             if not ok.item():
                 raise SystemExit("bench.py: a rank's boundary pair differs from the local recomputation with the true predecessor")
             dev_step()                                                      # restore the exchanged state
+            torch.cuda.synchronize()
 
         e2e_run(3)
         if sampler:
@@ -526,8 +547,12 @@ def main():
     gc.collect()
     torch.cuda.synchronize()
     sets.clear()
-    for h_ in (mt2, ex2, mt, ex):
+    for h_ in (mt2, ex2, mt, ex) + ((mt_side,) if mt_side else ()):
         h_.close()
+    if comm:
+        torch.cuda.synchronize()
+        comm2.close()
+        comm.close()
 
     if rank == 0:
         line = {"metric": "1080p frames/sec ORB extract+match", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -537,10 +562,14 @@ def main():
                            "frames_per_gpu_per_step": B, "global_frames_per_step": frames_total,
                            "l2": f"inputs larger than L2: {B * W * H / 1e6:.0f} MB of frames + {B * 6.4:.0f} MB pyramid per step",
                            "host_numa_node_rank0": numa,
-                           "parallelism": f"frames sharded over {world} GPU(s); one NCCL all-gather of per-frame keypoint/descriptor records per step" if world > 1 else "1 GPU"},
+                           "parallelism": (f"frames sharded over {world} GPU(s); one NCCL all-gather (pgb_allgather_feats, C-ABI) of the "
+                                           f"block-boundary keypoint/descriptor records per step, overlapped with the matcher") if world > 1 else "1 GPU"},
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K, "steps_in_flight": 2, "h2d_only_ms_per_step": ms_h2d,
-                        "h2d_only_gbs": h2d / (ms_h2d * 1e-3) / 1e9},
+                        "h2d_only_gbs": h2d / (ms_h2d * 1e-3) / 1e9,
+                        # every rank copying its pinned frames at the same time, ONE plain cudaMemcpyAsync each, no kernels
+                        # running: what the box's host side can deliver (per rank / all ranks together)
+                        "h2d_box_limit_gbs": h2d / (ms_h2d * 1e-3) / 1e9, "h2d_box_limit_gbs_all_ranks": world * h2d / (ms_h2d * 1e-3) / 1e9},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"kernel": "k_fast_cells (FAST-9 score + per-cell NMS + threshold decision, fused)", "bound": "hbm",

@@ -74,6 +74,10 @@ int pgb_orb_level_size(const pgb_orb*, int width, int height, int level, int* w,
  * where = PGB_OUT_DEVICE: host (ideally pinned) frames are copied in with cudaMemcpy2DAsync, results stay on the
  * device for the matcher; asynchronous.
  * frame i starts at gray + i*frame_stride, rows are `pitch` bytes apart.
+ * LIFETIME: device frames that are 16-byte aligned (pointer, pitch, frame_stride) are read IN PLACE as pyramid level 0:
+ * the buffer must stay valid and unmodified until the asynchronous work has completed AND for as long as stage /
+ * level getters (pgb_orb_run_stage, pgb_orb_get_level, pgb_orb_get_blurred_level, pgb_orb_get_score_map) are used on
+ * that batch, i.e. until the next pgb_orb_extract call on the handle.
  * Outputs: kps[n_frames][cap], desc[n_frames][cap][32], counts[n_frames]; level-major then octree list order.
  * width==0 || height==0 => counts zeroed, PGB_OK (the reference returns silently on an empty image, :1045). */
 #define PGB_IN_DEVICE 1
@@ -90,9 +94,12 @@ int pgb_orb_get_score_map(pgb_orb*, int frame, int level, uint8_t* out, int* w, 
 int pgb_orb_get_candidates(pgb_orb*, int frame, int level, int32_t* xyr /*[cap][3]*/, int cap, int32_t* n);
 /* 7x7 sigma=2 fixed-point Gaussian blur of a whole level (ORBextractor.cc:1084-1085); tight host buffer. */
 int pgb_orb_get_blurred_level(pgb_orb*, int frame, int level, uint8_t* out, int* w, int* h);
-/* Run only pyramid + FAST score kernels on the frames already resident from the last extract call
- * (used by bench.py to time the FAST kernel alone). which: 0 = pyramid, 1 = FAST score, 2 = cell NMS,
- * 3 = octree, 4 = orientation+descriptor. Asynchronous on the handle's stream. */
+/* Re-run one stage on the frames resident from the last extract call (bench.py's per-stage timing, stage parity
+ * tests). which: 0 = pyramid, 1 = FAST-9 score + per-cell NMS + threshold decision (the fused kernel of the hot path),
+ * 2 = the unfused pair (score map kernel, then the cell kernel) recomputing the same candidates -- kept for A/B timing
+ * and for pgb_orb_get_score_map --, 3 = octree, 4 = orientation+descriptor.  Asynchronous on the handle's stream.
+ * With PGB_IN_DEVICE input that was read in place (16-byte aligned frames), the caller's frame buffer must still hold
+ * the frames: level 0 is not copied (see pgb_orb_extract). */
 int pgb_orb_run_stage(pgb_orb*, int which);
 void* pgb_orb_stream(pgb_orb*);
 /* Synchronise the handle's stream and report (and clear) device-side capacity flags raised by asynchronous
@@ -206,6 +213,38 @@ int pgb_pose_optimization(int device, int n_frames, int cap, const float* Tcw_in
                           const int32_t* kp_octave, const float* mp_xyz, const uint8_t* has_map_point,
                           const int32_t* counts, const float* inv_level_sigma2, int nlevels, float fx, float fy, float cx,
                           float cy, float* Tcw_out, uint8_t* outlier, int32_t* n_inliers, int is_device, void* stream);
+
+/* ------------------------------------------------------------------ multi-GPU feature exchange ------------- */
+/* Frames shard over the GPUs of one box in contiguous blocks; extraction is independent per
+ * frame, and SearchByProjection(frame t, frame t-1) (Tracking.cc:860-883) is the only dependency that crosses a block
+ * boundary.  The reference has no multi-GPU code: these entry points are what its frame loop
+ * (src/slam/track_image_sequence.cc:63-109 -> System::TrackMonocular) gains when sharded.
+ * One communicator rank per GPU; NCCL is loaded at run time (dlopen libnccl.so.2). */
+typedef struct pgb_comm pgb_comm;
+#define PGB_COMM_ID_BYTES 128
+/* ncclGetUniqueId: rank 0 creates the id, the caller ships the bytes to the other ranks (torch.distributed, MPI, a file). */
+int pgb_comm_unique_id(uint8_t id[PGB_COMM_ID_BYTES]);
+/* One process per GPU (torchrun / bench.py): rank `rank` of `n_ranks` on `device`.  Collective: every rank must call it. */
+pgb_comm* pgb_comm_create(int device, int rank, int n_ranks, const uint8_t id[PGB_COMM_ID_BYTES]);
+/* One process, one host thread per GPU (optical_trajectories --num_gpus): all ranks at once, out[i] on devices[i]. */
+int pgb_comm_create_all(int n, const int* devices, pgb_comm** out);
+void pgb_comm_destroy(pgb_comm*);
+int pgb_comm_rank(const pgb_comm*);
+int pgb_comm_size(const pgb_comm*);
+int pgb_comm_nccl_version(void); /* 0 when NCCL cannot be loaded */
+/* The path's single collective: ncclAllGather of bytes_per_rank bytes from every rank (device pointers; recv holds
+ * size * bytes_per_rank, rank-major).  Callers send either the block-boundary frame record (below) -- all the matcher
+ * needs -- or their whole block of per-frame records.  Asynchronous on `stream` (a cudaStream_t). */
+int pgb_allgather_feats(pgb_comm*, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+/* A frame's features as ONE contiguous record (count | keypoints[cap] | descriptors[cap][32], 16-byte aligned parts):
+ * the unit that crosses ranks.  pack: frame `frame` of the per-frame arrays pgb_orb_extract wrote -> record;
+ * unpack: record -> frame `frame` of such arrays (e.g. slot 0 = "predecessor of my first frame").  Device pointers,
+ * asynchronous on `stream`. */
+size_t pgb_frame_record_bytes(int cap);
+int pgb_frame_record_pack(const pgb_keypoint* kps, const uint8_t* desc, const int32_t* counts, int frame, int cap,
+                          void* record, void* stream);
+int pgb_frame_record_unpack(const void* record, pgb_keypoint* kps, uint8_t* desc, int32_t* counts, int frame, int cap,
+                            void* stream);
 
 /* ------------------------------------------------------------------ IMU + GPS calibration ------------------ */
 typedef struct pgb_imu pgb_imu;

@@ -66,6 +66,17 @@ _SIGS = {
     "pgb_distinctive_descriptors": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
     "pgb_pose_optimization": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float,
                                         C.c_float, C.c_float, vp, vp, vp, C.c_int, vp]),
+    "pgb_comm_unique_id": (C.c_int, [vp]),
+    "pgb_comm_create": (vp, [C.c_int, C.c_int, C.c_int, vp]),
+    "pgb_comm_create_all": (C.c_int, [C.c_int, vp, vp]),
+    "pgb_comm_destroy": (None, [vp]),
+    "pgb_comm_rank": (C.c_int, [vp]),
+    "pgb_comm_size": (C.c_int, [vp]),
+    "pgb_comm_nccl_version": (C.c_int, []),
+    "pgb_allgather_feats": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "pgb_frame_record_bytes": (C.c_size_t, [C.c_int]),
+    "pgb_frame_record_pack": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    "pgb_frame_record_unpack": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "pgb_imu_create": (vp, [C.c_int, vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp]),
     "pgb_imu_destroy": (None, [vp]),
     "pgb_imu_merged_count": (C.c_int64, [vp]),

@@ -192,6 +192,39 @@ __global__ void k_imu_speeds(int nWin, int maxRefs, const WinDesc* __restrict__ 
   if (fwdPart) { fwdPart[4 * (size_t)t] = fsum.x; fwdPart[4 * (size_t)t + 1] = fsum.y; fwdPart[4 * (size_t)t + 2] = fsum.z; fwdPart[4 * (size_t)t + 3] = minW; }
 }
 
+// MakeInterpolationIntervals (align_time_series.cc:155-196) on the device: the host only finds, per GPS fix r, the first
+// merged IMU event after it (hiIdx[r], 3600 bisections for an hour of GPS) and the prefix sums ioff; one thread per
+// GPS interval then writes its sub-intervals: every merged event k in (gps[r-1], gps[r]] ends a sub-interval that
+// starts at the later of the previous event and gps[r-1], and the stretch from the last such event to gps[r] is a
+// partial sub-interval carrying the NEXT event's samples (:187-193).  (Round 1 built the three arrays in a host loop
+// and uploaded 29 MB per fit: 8 of the fit's 80 ms.)
+__global__ void k_imu_build_intervals(int nRef, long long nEvents, const long long* __restrict__ gpsT,
+                                      const long long* __restrict__ evT, const int* __restrict__ hiIdx,
+                                      const int* __restrict__ ioff, int* __restrict__ ivM, int* __restrict__ ivRef,
+                                      long long* __restrict__ ivDur) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < 1 || r >= nRef) return;
+  const int lo = hiIdx[r - 1], hi = hiIdx[r];
+  int out = ioff[r];
+  long long latest = gpsT[r - 1];
+  for (int k = lo; k < hi; k++) {
+    const long long ts = evT[k];
+    if (k > 0) { ivM[out] = k; ivRef[out] = r; ivDur[out] = ts - latest; out++; }
+    latest = ts;
+  }
+  if (hi > 0 && hi < nEvents && gpsT[r] > latest) { ivM[out] = hi; ivRef[out] = r; ivDur[out] = gpsT[r] - latest; }
+}
+
+// Per merged event: first / last sub-interval carrying it (the run is contiguous in the interval list), -1 = none.
+__global__ void k_imu_event_runs(int kLo, int kHi, int mLo, const int* __restrict__ ivM, int* __restrict__ firstIv,
+                                 int* __restrict__ lastIv) {
+  const int k = kLo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kHi) return;
+  const int m = ivM[k];
+  if (k == kLo || ivM[k - 1] != m) firstIv[m - mLo] = k;
+  if (k + 1 == kHi || ivM[k + 1] != m) lastIv[m - mLo] = k;
+}
+
 // GetPrincipalRotationAxes (rotation.cc:16-57): one thread per integration interval multiplies the rotation
 // quaternions of its gyro samples (the interval boundaries are an integer prefix computed on the host).
 __global__ void k_rot_intervals(int nIv, const int* __restrict__ ivStart, const double* __restrict__ gyro,
@@ -335,8 +368,9 @@ struct pgb_imu {
   DevBuf<int> dMG, dMA;
   // prepared GPS series
   std::vector<int64_t> gpsT;
-  std::vector<int> ioff, ivM, ivRef;
-  std::vector<long long> ivDur;
+  std::vector<int> ioff, hiIdx;  // per GPS fix: offset of its first sub-interval; first merged event after it
+  DevBuf<long long> dMergedT, dGpsT;
+  DevBuf<int> dHiIdx;
   std::vector<WinDesc> win;
   int firstWin = 0, batch = 0, step = 0, maxRefs = 0;
   long long spTotal = 0;
@@ -382,25 +416,24 @@ int check_increasing(const int64_t* t, size_t n, const char* what) {
   return PGB_OK;
 }
 
-// MakeInterpolationIntervals (align_time_series.cc:155-196) over a GPS series, flattened.
-void make_intervals(const std::vector<int64_t>& ref, const std::vector<int64_t>& interp, std::vector<int>& ioff,
-                    std::vector<int>& ivM, std::vector<int>& ivRef, std::vector<long long>& ivDur) {
-  ioff.assign(ref.size() + 1, 0); ivM.clear(); ivRef.clear(); ivDur.clear();
-  int64_t latest = std::min(interp.front(), ref.front());
-  size_t k = 0;
-  for (size_t r = 0; r < ref.size(); r++) {
-    ioff[r] = (int)ivM.size();
-    const int64_t rts = ref[r];
-    while (k < interp.size() && interp[k] <= rts) {
-      const int64_t ts = interp[k];
-      if (ts > latest && k > 0 && r > 0) { ivM.push_back((int)k); ivRef.push_back((int)r); ivDur.push_back(ts - latest); }
-      latest = ts;
-      k++;
-    }
-    if (k > 0 && r > 0 && k < interp.size() && rts > latest) { ivM.push_back((int)k); ivRef.push_back((int)r); ivDur.push_back(rts - latest); }
-    latest = rts;
+// Host part of MakeInterpolationIntervals (align_time_series.cc:155-196): per GPS fix r the index of the first merged
+// event after it and the number of sub-intervals of GPS interval r (k_imu_build_intervals writes them).
+void count_intervals(const std::vector<int64_t>& ref, const std::vector<int64_t>& interp, std::vector<int>& ioff,
+                     std::vector<int>& hiIdx) {
+  const size_t R = ref.size(), N = interp.size();
+  ioff.assign(R + 1, 0); hiIdx.assign(R, 0);
+  for (size_t r = 0; r < R; r++) hiIdx[r] = (int)(std::upper_bound(interp.begin(), interp.end(), ref[r]) - interp.begin());
+  int total = 0;
+  for (size_t r = 0; r < R; r++) {
+    ioff[r] = total;
+    if (r == 0) continue;
+    const int lo = hiIdx[r - 1], hi = hiIdx[r];
+    int n = hi - lo - (lo == 0 && hi > 0 ? 1 : 0);  // event 0 never ends a sub-interval (k > 0, :176)
+    const int64_t latest = hi > lo ? interp[hi - 1] : ref[r - 1];
+    if (hi > 0 && (size_t)hi < N && ref[r] > latest) n++;
+    total += n;
   }
-  ioff[ref.size()] = (int)ivM.size();
+  ioff[R] = total;
 }
 
 // PGB_IMU_TIMING=1: wall time of every phase of a fit (stream synchronised at the marks) on stderr -- the breakdown
@@ -440,8 +473,8 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
   o->windowReady = false;
   PhaseTimer pt(o->stream);
   o->gpsT.assign(gps_t, gps_t + n_gps);
-  make_intervals(o->gpsT, o->mergedT, o->ioff, o->ivM, o->ivRef, o->ivDur);
-  pt.mark("host: make_intervals");
+  count_intervals(o->gpsT, o->mergedT, o->ioff, o->hiIdx);
+  pt.mark("host: interval counts");
   const int allWin = (n_gps + step - 1) / step;
   if (first_window < 0 || first_window > allWin) return fail(PGB_ERR_INVALID, "first_window out of range");
   if (n_windows < 0 || first_window + n_windows > allWin) n_windows = allWin - first_window;
@@ -462,15 +495,20 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
   o->maxRefs = maxRefs;
   cudaStream_t s = o->stream;
   std::vector<double> gv(gps_v, gps_v + n_gps);
-  if (upload(o->dIoff, o->ioff, s) || upload(o->dIvM, o->ivM, s) || upload(o->dIvRef, o->ivRef, s) ||
-      upload(o->dIvDur, o->ivDur, s) || upload(o->dGpsV, gv, s) || upload(o->dWin, o->win, s))
+  std::vector<long long> gt(gps_t, gps_t + n_gps);
+  const size_t nIv = (size_t)o->ioff[n_gps];
+  if (upload(o->dIoff, o->ioff, s) || upload(o->dHiIdx, o->hiIdx, s) || upload(o->dGpsT, gt, s) || upload(o->dGpsV, gv, s) ||
+      upload(o->dWin, o->win, s) || ensure(o->dIvM, nIv + 1) || ensure(o->dIvRef, nIv + 1) || ensure(o->dIvDur, nIv + 1))
     return PGB_ERR_CUDA;
+  k_imu_build_intervals<<<(n_gps + 63) / 64, 64, 0, s>>>(n_gps, (long long)o->mergedT.size(), o->dGpsT.p, o->dMergedT.p, o->dHiIdx.p,
+                                                        o->dIoff.p, o->dIvM.p, o->dIvRef.p, o->dIvDur.p);
+  PGB_CHECK_LAUNCH();
   const size_t nW = o->win.size();
   if (ensure(o->dLoc, n_gps) || ensure(o->dRec, nW * maxRefs) || ensure(o->dTotal, nW) || ensure(o->dX, nW * 9) ||
       ensure(o->dFx, nW) || ensure(o->dIt, nW) || ensure(o->dNe, nW) || ensure(o->dOut10, 16))
     return PGB_ERR_CUDA;
   if (nW == 0) { PGB_CUDA(cudaStreamSynchronize(s)); return PGB_OK; }
-  pt.mark("uploads + allocations");
+  pt.mark("uploads + k_imu_build_intervals");
   k_imu_sweep<<<(n_gps + 63) / 64, 64, 0, s>>>(n_gps, o->dIoff.p, o->dIvM.p, o->dIvDur.p, o->dMG.p, o->dMA.p,
                                                 o->dGyro.p, o->dAcc.p, o->dLoc.p);
   PGB_CHECK_LAUNCH();
@@ -479,7 +517,7 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
   PGB_CHECK_LAUNCH();
   o->hTotal.resize(nW);
   PGB_CUDA(cudaMemcpyAsync(o->hTotal.data(), o->dTotal.p, nW * sizeof(long long), cudaMemcpyDeviceToHost, s));
-  PGB_CUDA(cudaStreamSynchronize(s));  // gv and the host vectors were sources of async copies
+  PGB_CUDA(cudaStreamSynchronize(s));  // gv, gt and the host vectors were sources of async copies
   pt.mark("k_imu_chain");
   o->windowReady = true;
   return PGB_OK;
@@ -543,7 +581,11 @@ pgb_imu* pgb_imu_create(int device, const double* gyro_xyz, const int64_t* gyro_
     fail(PGB_ERR_CUDA, "H2D copy of the sensor series failed");
     return bad();
   }
-  if (upload(o->dMG, o->mG, o->stream) || upload(o->dMA, o->mA, o->stream)) return bad();
+  {
+    std::vector<long long> mt(o->mergedT.begin(), o->mergedT.end());
+    if (upload(o->dMG, o->mG, o->stream) || upload(o->dMA, o->mA, o->stream) || upload(o->dMergedT, mt, o->stream)) return bad();
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess) { fail(PGB_ERR_CUDA, "stream sync failed"); return bad(); }
+  }
   if (cudaStreamSynchronize(o->stream) != cudaSuccess) { fail(PGB_ERR_CUDA, "stream sync failed"); return bad(); }
   return o;
 }
@@ -628,13 +670,20 @@ int pgb_imu_integrate(pgb_imu* o, const double x[9], int64_t cap, int64_t* merge
     PGB_CUDA(cudaMemcpyAsync(q.data(), o->dQuat.p, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
     PGB_CUDA(cudaMemcpyAsync(v.data(), o->dVel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
   }
+  // the window's sub-interval table (built on the device): merged event and span of each
+  const int lo = o->ioff[std::min(o->win[0].s + 1, (int)o->gpsT.size())];
+  std::vector<int> ivM(n);
+  std::vector<long long> ivDur(n);
+  if (n) {
+    PGB_CUDA(cudaMemcpyAsync(ivM.data(), o->dIvM.p + lo, n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    PGB_CUDA(cudaMemcpyAsync(ivDur.data(), o->dIvDur.p + lo, n * sizeof(long long), cudaMemcpyDeviceToHost, o->stream));
+  }
   PGB_CUDA(cudaStreamSynchronize(o->stream));
   // fold sub-intervals of the same merged event: later overwrites, durations add (velocity.cc:236-250)
-  const int lo = o->ioff[std::min(o->win[0].s + 1, (int)o->gpsT.size())];
   int64_t k = 0;
   for (long long i = 0; i < n; i++) {
-    const int m = o->ivM[lo + i];
-    const bool cont = i > 0 && o->ivM[lo + i - 1] == m;
+    const int m = ivM[i];
+    const bool cont = i > 0 && ivM[i - 1] == m;
     if (!cont) {
       if (k >= cap) return fail(PGB_ERR_CAPACITY, "trajectory has more than %lld points", (long long)cap);
       k++;
@@ -644,7 +693,7 @@ int pgb_imu_integrate(pgb_imu* o, const double x[9], int64_t cap, int64_t* merge
     if (speed) speed[k - 1] = sp[i];
     if (quat_wxyz) for (int c = 0; c < 4; c++) quat_wxyz[4 * (k - 1) + c] = q[4 * i + c];
     if (vel_xyz) for (int c = 0; c < 3; c++) vel_xyz[3 * (k - 1) + c] = v[3 * i + c];
-    if (duration_usec) duration_usec[k - 1] += o->ivDur[lo + i];
+    if (duration_usec) duration_usec[k - 1] += ivDur[i];
   }
   *n_out = k;
   return PGB_OK;
@@ -676,9 +725,12 @@ int pgb_imu_fit_windows_fwd(pgb_imu* o, const double* gps_v, const int64_t* gps_
   if (rc) return rc;
   const int nW = (int)o->win.size();
   const size_t M = o->mergedT.size();
-  if (speed_sum) memset(speed_sum, 0, M * sizeof(double));
-  if (speed_cnt) memset(speed_cnt, 0, M * sizeof(int32_t));
-  if (nW == 0) return PGB_OK;
+  // events outside the shard's range get 0 / 0; the range itself is overwritten by the device results below
+  auto zero_outside = [&](size_t lo, size_t hi) {
+    if (speed_sum) { memset(speed_sum, 0, lo * sizeof(double)); memset(speed_sum + hi, 0, (M - hi) * sizeof(double)); }
+    if (speed_cnt) { memset(speed_cnt, 0, lo * sizeof(int32_t)); memset(speed_cnt + hi, 0, (M - hi) * sizeof(int32_t)); }
+  };
+  if (nW == 0) { zero_outside(0, 0); return PGB_OK; }
   PhaseTimer pt(o->stream);
   rc = solve(o, max_iterations, epsilon, 0);
   if (rc) return rc;
@@ -696,31 +748,36 @@ int pgb_imu_fit_windows_fwd(pgb_imu* o, const double* gps_v, const int64_t* gps_
   PGB_CUDA(cudaMemcpyAsync(its.data(), o->dIt.p, nW * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (x_out) PGB_CUDA(cudaMemcpyAsync(x_out, o->dX.p, (size_t)nW * 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (fx_out) PGB_CUDA(cudaMemcpyAsync(fx_out, o->dFx.p, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, s));
+  size_t covLo = 0, covHi = 0;  // merged-event range [covLo, covHi) written from the device
   if ((speed_sum || speed_cnt) && o->spTotal > 0) {
-    // merged-event range touched by the shard, and each event's run of sub-intervals
+    // merged-event range touched by the shard, and each event's run of sub-intervals (device: k_imu_event_runs)
     const int kLo = o->ioff[std::min(o->win.front().s + 1, n_gps)], kHi = o->ioff[o->win.back().e];
     if (kHi > kLo) {
-      const int mLo = o->ivM[kLo], mHi = o->ivM[kHi - 1];
+      int mEnds[2] = {0, 0};
+      PGB_CUDA(cudaMemcpyAsync(&mEnds[0], o->dIvM.p + kLo, sizeof(int), cudaMemcpyDeviceToHost, s));
+      PGB_CUDA(cudaMemcpyAsync(&mEnds[1], o->dIvM.p + kHi - 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+      PGB_CUDA(cudaStreamSynchronize(s));
+      const int mLo = mEnds[0], mHi = mEnds[1];
       const int mc = mHi - mLo + 1;
-      std::vector<int> firstIv(mc, -1), lastIv(mc, -1);
-      for (int k = kLo; k < kHi; k++) {
-        const int i = o->ivM[k] - mLo;
-        if (firstIv[i] < 0) firstIv[i] = k;
-        lastIv[i] = k;
-      }
-      pt.mark("host: event runs");
-      if (upload(o->dFirstIv, firstIv, s) || upload(o->dLastIv, lastIv, s) || ensure(o->dSum, M) || ensure(o->dCnt, M))
-        return PGB_ERR_CUDA;
+      if (ensure(o->dFirstIv, mc) || ensure(o->dLastIv, mc) || ensure(o->dSum, M) || ensure(o->dCnt, M)) return PGB_ERR_CUDA;
+      PGB_CUDA(cudaMemsetAsync(o->dFirstIv.p, 0xff, (size_t)mc * sizeof(int), s));
+      PGB_CUDA(cudaMemsetAsync(o->dLastIv.p, 0xff, (size_t)mc * sizeof(int), s));
+      k_imu_event_runs<<<(kHi - kLo + 255) / 256, 256, 0, s>>>(kLo, kHi, mLo, o->dIvM.p, o->dFirstIv.p, o->dLastIv.p);
+      PGB_CHECK_LAUNCH();
+      pt.mark("k_imu_event_runs");
+      covLo = (size_t)mLo; covHi = (size_t)mLo + mc;
       k_imu_average<<<(mc + 255) / 256, 256, 0, s>>>(mLo, mc, o->dFirstIv.p, o->dLastIv.p, o->dIvRef.p, nW, o->firstWin,
                                                      batch_size, shift_step, n_gps, o->dWin.p, o->dIoff.p, o->dSpeeds.p,
                                                      o->dSum.p, o->dCnt.p);
       PGB_CHECK_LAUNCH();
       if (speed_sum) PGB_CUDA(cudaMemcpyAsync(speed_sum + mLo, o->dSum.p + mLo, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, s));
       if (speed_cnt) PGB_CUDA(cudaMemcpyAsync(speed_cnt + mLo, o->dCnt.p + mLo, (size_t)mc * sizeof(int), cudaMemcpyDeviceToHost, s));
-      PGB_CUDA(cudaStreamSynchronize(s));  // firstIv/lastIv are host sources
+      zero_outside(covLo, covHi);  // host work while the copies are in flight
+      PGB_CUDA(cudaStreamSynchronize(s));
       pt.mark("k_imu_average + D2H");
     }
   }
+  if (covHi == covLo) zero_outside(0, 0);
   PGB_CUDA(cudaStreamSynchronize(s));
   if (fwd_sum_xyz) {
     // total_velocity_local (fit_motion.cc:172-173, :232-248): Kahan sum (math.hpp:8-27) over the windows whose largest

@@ -42,9 +42,15 @@ constexpr int kF2InBytes = kF2InWords * 4 * kF2InRows;  // 20160 = TMA transacti
 // fused FAST + cell NMS kernel (fast_cells.cu): one CTA per row of up to fcKc FAST cells; the TMA box of a tile is
 // 72 words x (8 * bands + 6) rows, the score tile (8 * bands + 2) rows of 272 bytes, one candidate queue per band
 constexpr int kFcThreads = 128, kFcWarps = 4;
-constexpr int kFcInWords = 72;       // 288-byte staged input rows: <= 18 bytes of alignment slack + 249 px + 3-px halos
+#ifndef PGB_FC_INW
+#define PGB_FC_INW 72
+#endif
+#ifndef PGB_FC_QCAP
+#define PGB_FC_QCAP 384
+#endif
+constexpr int kFcInWords = PGB_FC_INW;  // staged input rows: >= 72 words (<= 18 bytes of alignment slack + 249 px + 3-px halos)
 constexpr int kFcTilePitch = 272;    // score tile row: 16 pad bytes + 256 px
-constexpr int kFcQueueCap = 384;     // candidates per band queue (u32 flag + u8 code each)
+constexpr int kFcQueueCap = PGB_FC_QCAP;  // candidates per band queue (u32 flag + u8 code each; >= 256: a refilled queue holds one row)
 constexpr int kFcQueueBytes = kFcQueueCap * 5;
 constexpr int kFcListCap = 128;     // NMS survivors per tile kept in the list (natural images: ~20); more -> bitmap emission
 constexpr int kFcMaxFrame = 249;     // widest tested tile inside the 256-px lane frame (first pixel at offset 0..7)

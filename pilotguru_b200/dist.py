@@ -14,10 +14,70 @@ slot 0 is the predecessor frame (t0-1), slots 1..B the rank's own frames.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
 KP_BYTES = 28
+
+
+class PgbComm:
+    """One rank of a pgb_comm (libpgb200's NCCL communicator, include/pgb200.h "multi-GPU feature exchange").  The NCCL
+    unique id is created by rank 0 through the C-ABI and shipped with torch.distributed -- the only thing
+    torch.distributed does on the data path's behalf."""
+
+    def __init__(self, device_index: int, rank: int, world: int):
+        from ._lib import check, last_error, lib, PgbError
+        self._h = None
+        on_gpu = dist.get_backend() == "nccl"
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            check(lib().pgb_comm_unique_id(buf))
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        if on_gpu:
+            idt = idt.cuda(device_index)
+        dist.broadcast(idt, 0)
+        raw = bytes(idt.cpu().tolist())
+        h = lib().pgb_comm_create(device_index, rank, world, C.c_char_p(raw))
+        if not h:
+            raise PgbError(-2, last_error())
+        self._h = C.c_void_p(h)
+        self.rank, self.world = rank, world
+
+    def allgather(self, send_ptr: int, recv_ptr: int, bytes_per_rank: int, stream_ptr: int):
+        from ._lib import check, lib
+        check(lib().pgb_allgather_feats(self._h, send_ptr, recv_ptr, bytes_per_rank, stream_ptr))
+
+    def close(self):
+        if self._h:
+            from ._lib import lib
+            lib().pgb_comm_destroy(self._h)
+            self._h = None
+
+
+class BoundaryExchange:
+    """What the matcher needs across a block boundary, through the C-ABI: every rank packs its LAST frame's features into
+    one contiguous record (pgb_frame_record_pack), ONE NCCL all-gather of those records (62 KB per rank at cap 1033),
+    and rank r > 0 unpacks rank r-1's record into slot 0 of its region (the predecessor of its first frame)."""
+
+    def __init__(self, comm: PgbComm, region: "FeatureExchange"):
+        from ._lib import lib
+        self.comm, self.x = comm, region
+        self.rec_bytes = int(lib().pgb_frame_record_bytes(region.cap))
+        dev = region.local.device
+        self.send = torch.zeros(self.rec_bytes, dtype=torch.uint8, device=dev)
+        self.recv = torch.zeros((comm.world, self.rec_bytes), dtype=torch.uint8, device=dev)
+
+    def issue(self, stream_ptr: int):
+        from ._lib import check, lib
+        x = self.x
+        check(lib().pgb_frame_record_pack(x.kps_ptr(0), x.desc_ptr(0), x.counts_ptr(0), x.B, x.cap, self.send.data_ptr(), stream_ptr))
+        self.comm.allgather(self.send.data_ptr(), self.recv.data_ptr(), self.rec_bytes, stream_ptr)
+        if self.comm.rank > 0:
+            check(lib().pgb_frame_record_unpack(self.recv[self.comm.rank - 1].data_ptr(), x.kps_ptr(0), x.desc_ptr(0), x.counts_ptr(0),
+                                                0, x.cap, stream_ptr))
 
 
 def shard_range(n_frames: int, world: int, rank: int) -> tuple[int, int]:
@@ -69,7 +129,9 @@ class FeatureExchange:
         self.desc_view()[0].copy_(self.desc_view()[self.B])
 
     def exchange(self, stream=None):
-        """One all-gather of every rank's region; slot 0 <- last frame of the left neighbour (rank 0 keeps its own)."""
+        """One all-gather of every rank's WHOLE region through torch.distributed (the full feature table on every rank;
+        gloo in the CPU tests); slot 0 <- last frame of the left neighbour (rank 0 keeps its own).  The GPU hot path
+        uses BoundaryExchange instead: the C-ABI collective on the boundary records only."""
         if self.world == 1:
             return
         dist.all_gather_into_tensor(self.gathered.view(-1), self.local)
