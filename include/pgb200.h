@@ -117,6 +117,23 @@ int pgb_frames_to_gray(int device, const uint8_t* src, int src_is_device, int n_
                        int formula, uint8_t* dst_gray, int dst_is_device, size_t dst_pitch, size_t dst_frame_stride,
                        void* stream);
 
+/* Synthetic frame source for the long BASELINE configs (SURVEY.md 8d's generator rendered on the device: canvas crop at
+ * the ping-pong origin of frame first_t + i, plus deterministic per-frame noise).  Stands where a hardware video decoder
+ * would: n_frames tight width x height gray frames appear in device memory (out_dev), ready for pgb_orb_extract
+ * (PGB_IN_DEVICE).  canvas_dev: canvas_w x canvas_h gray bytes on the device.  Asynchronous on `stream`. */
+int pgb_synth_frames(int device, const uint8_t* canvas_dev, int canvas_w, int canvas_h, int first_t, int n_frames,
+                     int width, int height, uint8_t* out_dev, void* stream);
+
+/* Device / pinned memory for host programs that keep frames and features on the device between calls and link only this
+ * library (its CUDA runtime is private).  kind: 0 host->device, 1 device->host, 2 device->device. */
+int pgb_device_count(void);
+void* pgb_device_malloc(int device, size_t bytes); /* zero-filled; NULL on failure */
+void pgb_device_free(int device, void* p);
+void* pgb_host_malloc_pinned(size_t bytes);
+void pgb_host_free_pinned(void* p);
+int pgb_memcpy_async(int device, void* dst, const void* src, size_t bytes, int kind, void* stream);
+int pgb_stream_synchronize(int device, void* stream);
+
 /* ------------------------------------------------------------------ matcher -------------------------------- */
 /* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1651-1667) for n pairs of 32-byte descriptors (device or host
  * pointers; host pointers are staged). Mostly a test hook for the popcount primitive. */
@@ -283,6 +300,10 @@ int pgb_imu_fit_windows(pgb_imu*, const double* gps_v, const int64_t* gps_t, int
                         int shift_step, int max_iterations, double epsilon, int first_window, int n_windows,
                         double* speed_sum, int32_t* speed_cnt, double* x_out, double* fx_out, int32_t* iters_out);
 int pgb_imu_num_windows(int n_gps, int shift_step);
+/* Device time (CUDA events on the handle's stream) of the three kernels of the last pgb_imu_fit_windows[_fwd] call -- the
+ * rotation sweep over every IMU sub-interval (K9), the per-window L-BFGS, the per-sub-interval speeds (K10) -- and the
+ * number of IMU sub-intervals the sweep covered (64 algorithmic bytes each).  For bench.py's roofline. */
+int pgb_imu_last_kernel_ms(pgb_imu*, float* sweep_ms, float* solve_ms, float* speeds_ms, int64_t* n_intervals);
 /* Same, plus the forward-axis evidence of fit_motion.cc:172-173,223-248: the Kahan sum (include/math/math.hpp:8-27) of
  * the device-frame velocities conj(orientation)*velocity over every trajectory point with |v| >= fwd_min_velocity of
  * every window whose largest rotation acos(min |q.w|) reaches fwd_min_rotation_rad.  fwd_sum_xyz[3] is the raw sum

@@ -50,6 +50,14 @@ _SIGS = {
     "pgb_orb_check": (C.c_int, [vp]),
     "pgb_frames_to_gray": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                      C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
+    "pgb_synth_frames": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "pgb_device_count": (C.c_int, []),
+    "pgb_device_malloc": (vp, [C.c_int, C.c_size_t]),
+    "pgb_device_free": (None, [C.c_int, vp]),
+    "pgb_host_malloc_pinned": (vp, [C.c_size_t]),
+    "pgb_host_free_pinned": (None, [vp]),
+    "pgb_memcpy_async": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, vp]),
+    "pgb_stream_synchronize": (C.c_int, [C.c_int, vp]),
     "pgb_descriptor_distance": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
     "pgb_matcher_create": (vp, [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, vp]),
     "pgb_matcher_destroy": (None, [vp]),
@@ -89,6 +97,7 @@ _SIGS = {
     "pgb_imu_fit_windows": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                       vp, vp, vp, vp, vp]),
     "pgb_imu_num_windows": (C.c_int, [C.c_int, C.c_int]),
+    "pgb_imu_last_kernel_ms": (C.c_int, [vp, vp, vp, vp, vp]),
     "pgb_imu_fit_windows_fwd": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                           vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp]),
     "pgb_principal_rotation_axes": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int64, vp, vp]),

@@ -163,9 +163,19 @@ int pgb_comm_nccl_version(void) {
 
 size_t pgb_frame_record_bytes(int cap) { return cap > 0 ? record_desc_off(cap) + (size_t)cap * 32 : 0; }
 
+// the launch must happen with the buffers' device current (host threads that drive several GPUs call these too)
+static int select_device_of(const void* p) {
+  cudaPointerAttributes a;
+  PGB_CUDA(cudaPointerGetAttributes(&a, p));
+  if (a.type != cudaMemoryTypeDevice) return fail(PGB_ERR_INVALID, "frame record buffers must be device memory");
+  PGB_CUDA(cudaSetDevice(a.device));
+  return PGB_OK;
+}
+
 int pgb_frame_record_pack(const pgb_keypoint* kps, const uint8_t* desc, const int32_t* counts, int frame, int cap, void* record,
                           void* stream) {
   if (!kps || !desc || !counts || !record || frame < 0 || cap <= 0) return fail(PGB_ERR_INVALID, "pgb_frame_record_pack: invalid argument");
+  if (int rc = select_device_of(record)) return rc;
   k_record_copy<<<8, 256, 0, (cudaStream_t)stream>>>(cap, 1, (uint32_t*)(kps + (size_t)frame * cap), (uint32_t*)(desc + (size_t)frame * cap * 32),
                                                       (int*)(counts + frame), (uint32_t*)record);
   PGB_CHECK_LAUNCH();
@@ -174,6 +184,7 @@ int pgb_frame_record_pack(const pgb_keypoint* kps, const uint8_t* desc, const in
 
 int pgb_frame_record_unpack(const void* record, pgb_keypoint* kps, uint8_t* desc, int32_t* counts, int frame, int cap, void* stream) {
   if (!kps || !desc || !counts || !record || frame < 0 || cap <= 0) return fail(PGB_ERR_INVALID, "pgb_frame_record_unpack: invalid argument");
+  if (int rc = select_device_of(record)) return rc;
   k_record_copy<<<8, 256, 0, (cudaStream_t)stream>>>(cap, 0, (uint32_t*)(kps + (size_t)frame * cap), (uint32_t*)(desc + (size_t)frame * cap * 32),
                                                       (int*)(counts + frame), (uint32_t*)const_cast<void*>(record));
   PGB_CHECK_LAUNCH();

@@ -88,3 +88,91 @@ extern "C" int pgb_frames_to_gray(int device, const uint8_t* src, int src_is_dev
   if (!src_is_device || !dst_is_device) PGB_CUDA(cudaStreamSynchronize(s));
   return PGB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ synthetic frame source
+// The SURVEY.md 8(d) frame generator rendered on the device, for the long BASELINE configs (10 000 and 54 000 frames: 21 and
+// 112 GB as raw files): frame t = w x h crop of a canvas at the ping-pong origin of pilotguru_b200/synth.py, plus per-frame
+// noise.  It stands where a hardware video decoder would stand: frames appear in device memory.  The noise is a counter
+// hash (sum of four uniform bytes, sigma 1 like the numpy generator's N(0, 1)), so the frames are deterministic functions
+// of (t, x, y) but NOT bit-identical to synth.frame(t): parity tests use the numpy frames, timing runs use these.
+namespace pgb {
+__device__ __forceinline__ uint32_t hash3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+__global__ void __launch_bounds__(256) k_synth_frames(const uint8_t* __restrict__ canvas, int cw, int ch, int firstT, int w, int h,
+                                                      uint8_t* __restrict__ out) {
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  if (xq * 4 >= w) return;
+  const int t = firstT + f;
+  const int px = cw - w - 32, py = ch - h - 32;  // synth.frame_origin: 16 + pp(2t, px), 16 + pp(t, py)
+  auto pp = [](int a, int p) { const int m = a % (2 * p); return p - abs(m - p); };
+  const int x0 = 16 + pp(2 * t, px), y0 = 16 + pp(t, py);
+  uint32_t packed = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int x = xq * 4 + i;
+    if (x < w) {
+      const uint32_t r = hash3((uint32_t)t, (uint32_t)y, (uint32_t)x);
+      const int s4 = (int)(r & 0xff) + (int)((r >> 8) & 0xff) + (int)((r >> 16) & 0xff) + (int)(r >> 24);
+      const float v = (float)canvas[(size_t)(y0 + y) * cw + x0 + x] + (float)(s4 - 510) * (1.0f / 147.8f);
+      packed |= (uint32_t)min(max(__float2int_rn(v), 0), 255) << (8 * i);
+    }
+  }
+  uint8_t* drow = out + (size_t)f * w * h + (size_t)y * w;
+  if ((w & 3) == 0) *reinterpret_cast<uint32_t*>(drow + xq * 4) = packed;
+  else for (int i = 0; i < 4 && xq * 4 + i < w; i++) drow[xq * 4 + i] = (uint8_t)(packed >> (8 * i));
+}
+}  // namespace pgb
+
+extern "C" int pgb_synth_frames(int device, const uint8_t* canvas_dev, int canvas_w, int canvas_h, int first_t, int n_frames,
+                                int width, int height, uint8_t* out_dev, void* stream) {
+  if (!canvas_dev || !out_dev || n_frames < 0 || width <= 0 || height <= 0 || canvas_w < width + 33 || canvas_h < height + 33 || first_t < 0)
+    return fail(PGB_ERR_INVALID, "pgb_synth_frames: invalid argument (the canvas must exceed the frame by at least 33 px)");
+  if (n_frames == 0) return PGB_OK;
+  if (use_device(device)) return PGB_ERR_CUDA;
+  dim3 grid(((width + 3) / 4 + 255) / 256, height, n_frames);
+  k_synth_frames<<<grid, 256, 0, (cudaStream_t)stream>>>(canvas_dev, canvas_w, canvas_h, first_t, width, height, out_dev);
+  PGB_CHECK_LAUNCH();
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device memory for hosts
+// Host programs that keep frames and features on the device between calls (optical_trajectories) link only libpgb200.so; the
+// CUDA runtime inside it is private, so the few memory operations such a host needs are part of the C-ABI.
+extern "C" void* pgb_device_malloc(int device, size_t bytes) {
+  if (use_device(device)) return nullptr;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { fail(PGB_ERR_CUDA, "cudaMalloc(%zu) failed", bytes); return nullptr; }
+  cudaMemset(p, 0, bytes);
+  return p;
+}
+extern "C" void pgb_device_free(int device, void* p) {
+  if (!p) return;
+  cudaSetDevice(device);
+  cudaFree(p);
+}
+extern "C" void* pgb_host_malloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { fail(PGB_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+extern "C" void pgb_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+extern "C" int pgb_memcpy_async(int device, void* dst, const void* src, size_t bytes, int kind, void* stream) {
+  if (bytes == 0) return PGB_OK;
+  if (!dst || !src || kind < 0 || kind > 2) return fail(PGB_ERR_INVALID, "pgb_memcpy_async: invalid argument");
+  PGB_CUDA(cudaSetDevice(device));
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  PGB_CUDA(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
+  return PGB_OK;
+}
+extern "C" int pgb_stream_synchronize(int device, void* stream) {
+  PGB_CUDA(cudaSetDevice(device));
+  PGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return PGB_OK;
+}
+extern "C" int pgb_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}

@@ -382,6 +382,9 @@ struct pgb_imu {
   DevBuf<WinDesc> dWin;
   std::vector<long long> hTotal;
   bool windowReady = false;
+  // CUDA events around the kernels of the last fit (pgb_imu_last_kernel_ms): 0/1 sweep, 2/3 solve, 4/5 speeds
+  cudaEvent_t ev[6] = {};
+  bool evValid = false;
 };
 
 namespace {
@@ -509,9 +512,14 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
     return PGB_ERR_CUDA;
   if (nW == 0) { PGB_CUDA(cudaStreamSynchronize(s)); return PGB_OK; }
   pt.mark("uploads + k_imu_build_intervals");
+  o->evValid = false;
+  for (auto& e : o->ev)
+    if (!e) PGB_CUDA(cudaEventCreate(&e));
+  PGB_CUDA(cudaEventRecord(o->ev[0], s));
   k_imu_sweep<<<(n_gps + 63) / 64, 64, 0, s>>>(n_gps, o->dIoff.p, o->dIvM.p, o->dIvDur.p, o->dMG.p, o->dMA.p,
                                                 o->dGyro.p, o->dAcc.p, o->dLoc.p);
   PGB_CHECK_LAUNCH();
+  PGB_CUDA(cudaEventRecord(o->ev[1], s));
   pt.mark("k_imu_sweep");
   k_imu_chain<<<((int)nW + 63) / 64, 64, 0, s>>>((int)nW, o->dWin.p, o->dLoc.p, o->dGpsV.p, maxRefs, o->dRec.p, o->dTotal.p);
   PGB_CHECK_LAUNCH();
@@ -590,10 +598,28 @@ pgb_imu* pgb_imu_create(int device, const double* gyro_xyz, const int64_t* gyro_
   return o;
 }
 
+int pgb_imu_last_kernel_ms(pgb_imu* o, float* sweep_ms, float* solve_ms, float* speeds_ms, int64_t* n_intervals) {
+  if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  if (!o->evValid) return fail(PGB_ERR_INVALID, "pgb_imu_last_kernel_ms: no completed pgb_imu_fit_windows call");
+  PGB_CUDA(cudaSetDevice(o->device));
+  PGB_CUDA(cudaEventSynchronize(o->ev[5]));
+  float a = 0, b = 0, c = 0;
+  PGB_CUDA(cudaEventElapsedTime(&a, o->ev[0], o->ev[1]));
+  PGB_CUDA(cudaEventElapsedTime(&b, o->ev[2], o->ev[3]));
+  PGB_CUDA(cudaEventElapsedTime(&c, o->ev[4], o->ev[5]));
+  if (sweep_ms) *sweep_ms = a;
+  if (solve_ms) *solve_ms = b;
+  if (speeds_ms) *speeds_ms = c;
+  if (n_intervals) *n_intervals = o->ioff.empty() ? 0 : (int64_t)o->ioff.back();
+  return PGB_OK;
+}
+
 void pgb_imu_destroy(pgb_imu* o) {
   if (!o) return;
   cudaSetDevice(o->device);
   if (o->stream) cudaStreamSynchronize(o->stream);
+  for (auto& e : o->ev)
+    if (e) cudaEventDestroy(e);
   if (o->ownStream && o->stream) cudaStreamDestroy(o->stream);
   delete o;
 }
@@ -732,11 +758,16 @@ int pgb_imu_fit_windows_fwd(pgb_imu* o, const double* gps_v, const int64_t* gps_
   };
   if (nW == 0) { zero_outside(0, 0); return PGB_OK; }
   PhaseTimer pt(o->stream);
+  PGB_CUDA(cudaEventRecord(o->ev[2], o->stream));
   rc = solve(o, max_iterations, epsilon, 0);
   if (rc) return rc;
+  PGB_CUDA(cudaEventRecord(o->ev[3], o->stream));
   pt.mark("k_imu_solve");
+  PGB_CUDA(cudaEventRecord(o->ev[4], o->stream));
   rc = speeds(o, false, fwd_sum_xyz != nullptr, fwd_min_velocity);
   if (rc) return rc;
+  PGB_CUDA(cudaEventRecord(o->ev[5], o->stream));
+  o->evValid = true;
   pt.mark("k_imu_speeds");
   cudaStream_t s = o->stream;
   std::vector<int> its(nW);

@@ -201,8 +201,12 @@ inline Table ReadTable(const std::string& path, const std::string& table, const 
 
 // "%.17g" (std::to_chars with chars_format::general and precision 17 is specified as exactly that), plus ".0" for
 // integral values the way nlohmann prints doubles.  Returns the number of characters written to buf (>= 40 bytes).
+// Non-finite values become `null`, as nlohmann::json::dump writes them (the reference produces them: the acos of a
+// rotation cosine that rounds above 1 in Projected2DDirectionsToTurnAngles, horizontal_flatten.cc:56-61, is NaN).
+// Digits: the reference pins nlohmann/json 2.1.1 (docker/Dockerfile:34), which prints 15 significant digits; this writer
+// prints 17 so that a value survives the round trip -- compare numerically, not textually.
 inline size_t FormatDoubleTo(char* buf, double v) {
-  if (!std::isfinite(v)) return (size_t)snprintf(buf, 40, "%.17g", v);
+  if (!std::isfinite(v)) { memcpy(buf, "null", 5); return 4; }
   char* e = std::to_chars(buf, buf + 32, v, std::chars_format::general, 17).ptr;
   bool plain = true;
   for (const char* c = buf; c < e; ++c)

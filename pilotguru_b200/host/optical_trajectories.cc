@@ -1,27 +1,44 @@
-// optical_trajectories -- the reference CLI (src/optical_trajectories.cc:36-62) with its per-frame hot path on the
-// B200: ORB extraction of every frame (ORBextractor::operator(), Frame.cc:251-257) and Hamming projection matching
-// against the previous frame (ORBmatcher::SearchByProjection, Tracking.cc:860-883) through libpgb200's C-ABI, and
-// the reference's trajectory post-processing + JSON writer (track_image_sequence.cc:63-109) restated in trajectory.hpp.
+// optical_trajectories -- the reference CLI (src/optical_trajectories.cc:36-62) with its per-frame hot path on B200s:
+// ORB extraction of every frame (ORBextractor::operator(), Frame.cc:251-257) and Hamming projection matching against the
+// previous frame (ORBmatcher::SearchByProjection with the th -> 2*th retry, Tracking.cc:860-883) through libpgb200's
+// C-ABI, frames and features resident on the device, and the reference's trajectory post-processing + JSON writer
+// (track_image_sequence.cc:63-109) restated in trajectory.hpp.
 //
-// Scope: the SLAM back end (map initialisation, pose optimisation, local BA, loop
-// closing, DBoW2 relocalisation) and video decoding are out of scope.  So this binary runs in FLOW-TRACKING mode:
-//   * --in_video takes raw frames:  raw:<path>:<width>x<height> (8-bit gray, frame i at byte i*width*height) or
+// --num_gpus N (extension; BASELINE configs[2]: 10 000 frames over 8 B200s): the frame sequence is cut into N contiguous
+// blocks, one host thread + one GPU per block.  Extraction is independent per frame; the only dependency that crosses a
+// block boundary is the match of a block's FIRST frame against the previous block's LAST frame: every rank packs that
+// frame's features into a record, ONE NCCL all-gather (pgb_allgather_feats) hands each rank its left neighbour's, and
+// the N-1 boundary pairs are matched.  The result is the same trajectory, byte for byte, as --num_gpus 1.
+//
+// Scope: the SLAM back end (map initialisation, local BA, loop closing, DBoW2
+// relocalisation) and video decoding are out of scope.  So this binary runs in FLOW-TRACKING mode:
+//   * --in_video takes raw frames:  raw:<path>:<width>x<height> (8-bit gray, frame i at byte i*width*height),
 //     raw24:<path>:<width>x<height> (interleaved 24-bit colour, the format the reference's reader hands to the tracker;
-//     channel order from Camera.RGB).  Flips and the colour conversion run on the device (pgb_frames_to_gray).
+//     channel order from Camera_RGB; flips and the colour conversion run on the device, pgb_frames_to_gray), or
+//     synth:<canvas path>:<canvas width>x<canvas height>:<frames>:<width>x<height> -- the SURVEY 8(d) synthetic sequence
+//     rendered on the device from a canvas file (pgb_synth_frames; stands where a hardware decoder would);
 //   * the tracked quantity is the dominant image translation between consecutive frames (median displacement of the
 //     matched keypoints); the camera is modelled as translating in its x-z plane by minus that flow, heading along
 //     its motion.  Poses are therefore in pixel units, not metres -- monocular SLAM scale is arbitrary as well.
 //   * tracking is "lost" (segment closed, new trajectory-<k>.json started, as the reference's outer loop does) when
 //     fewer than 20 matches survive the 2*th retry.
-// --vocabulary_file and --camera_settings keep the reference's CHECKs; the settings file supplies ORBextractor.* and
-// Camera.fps (Tracking.cc:52-135).  --visualize and --output_per_segment_videos are accepted and ignored.
+// --vocabulary_file and --camera_settings keep the reference's CHECKs.  The settings file is the fork's format
+// (written by src/calibrate.cc:504-544, read by Tracking.cc:52-135): underscore keys -- Camera_fps, Camera_RGB,
+// ORBextractor_nFeatures / _scaleFactor / _nLevels / _iniThFAST / _minThFAST.  A file with none of the ORBextractor_*
+// keys is rejected (upstream ORB-SLAM2's dotted keys are accepted with a warning).  --visualize and
+// --output_per_segment_videos are accepted and ignored.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pgb200.h"
@@ -49,9 +66,203 @@ std::map<std::string, double> ReadSettings(const std::string& path) {
   return kv;
 }
 
-struct FrameFeats {
-  std::vector<pgb_keypoint> k;
-  std::vector<uint8_t> d;
+struct Source {
+  enum Kind { kRawGray, kRaw24, kSynth } kind = kRawGray;
+  std::string path;
+  int width = 0, height = 0, channels = 1;
+  int canvasW = 0, canvasH = 0;
+  int64_t frames = 0;
+};
+
+Source ParseSource(const std::string& spec) {
+  Source s;
+  char path[4096];
+  long long n = 0;
+  if (sscanf(spec.c_str(), "synth:%4095[^:]:%dx%d:%lld:%dx%d", path, &s.canvasW, &s.canvasH, &n, &s.width, &s.height) == 6) {
+    s.kind = Source::kSynth; s.frames = n;
+  } else if (sscanf(spec.c_str(), "raw24:%4095[^:]:%dx%d", path, &s.width, &s.height) == 3) {
+    s.kind = Source::kRaw24; s.channels = 3;
+  } else {
+    PGB_CHECK(sscanf(spec.c_str(), "raw:%4095[^:]:%dx%d", path, &s.width, &s.height) == 3)
+        << "--in_video must be raw:<path>:<w>x<h>, raw24:<path>:<w>x<h> or synth:<canvas>:<cw>x<ch>:<frames>:<w>x<h> (video "
+           "decoding is out of scope, see the header comment)";
+  }
+  s.path = path;
+  PGB_CHECK(s.width > 0 && s.height > 0);
+  if (s.kind != Source::kSynth) {
+    FILE* f = fopen(path, "rb");
+    PGB_CHECK(f != nullptr) << "cannot open " << path;
+    fseeko(f, 0, SEEK_END);
+    s.frames = (int64_t)(ftello(f) / ((off_t)s.width * s.height * s.channels));
+    fclose(f);
+  }
+  return s;
+}
+
+struct Config {
+  int nfeatures, nlevels, ini_th, min_th, rgb_order;
+  float scale_factor;
+  double fps;
+  bool vertical_flip, horizontal_flip;
+  int batch;
+};
+
+// What the trajectory builder needs from one frame.
+struct FrameResult {
+  int32_t n_kps = 0, n_matches = -1;  // n_matches = -1: the frame has no predecessor (first frame of the sequence)
+  float dx = 0, dy = 0;               // median displacement of the matched keypoints (valid when n_matches >= 20)
+  bool tracked = false;
+};
+
+// One rank: frames [t0, t1) on `device`.  Features live in a device region of batch+1 slots (slot 0 = predecessor).
+struct Rank {
+  int device = 0, rank = 0;
+  int64_t t0 = 0, t1 = 0;
+  pgb_comm* comm = nullptr;
+  const Source* src = nullptr;
+  const Config* cfg = nullptr;
+  FrameResult* out = nullptr;  // out[t - 0], the whole sequence's array
+  double seconds = 0;
+
+  void Run() {
+    const int B = cfg->batch, W = src->width, H = src->height;
+    const size_t frameBytes = (size_t)W * H, inBytes = frameBytes * src->channels;
+    pgb_orb* orb = pgb_orb_create(device, cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th, cfg->min_th, W, H, B, nullptr);
+    PGB_CHECK(orb != nullptr) << pgb_last_error();
+    void* st = pgb_orb_stream(orb);
+    const int cap = pgb_orb_max_keypoints(orb);
+    pgb_matcher* matcher = pgb_matcher_create(device, 0.9f, 1, cap, B, st);  // ORBmatcher(0.9, true), Tracking.cc:860
+    PGB_CHECK(matcher != nullptr) << pgb_last_error();
+    std::vector<float> sf(cfg->nlevels), inv(cfg->nlevels), s2(cfg->nlevels), is2(cfg->nlevels);
+    PGB_CALL(pgb_orb_scale_factors(orb, sf.data(), inv.data(), s2.data(), is2.data()));
+
+    auto dalloc = [&](size_t bytes) { void* p = pgb_device_malloc(device, bytes); PGB_CHECK(p != nullptr) << pgb_last_error(); return p; };
+    pgb_keypoint* dK = (pgb_keypoint*)dalloc((size_t)(B + 1) * cap * sizeof(pgb_keypoint));
+    uint8_t* dD = (uint8_t*)dalloc((size_t)(B + 1) * cap * 32);
+    int32_t* dN = (int32_t*)dalloc((size_t)(B + 1) * sizeof(int32_t));
+    int32_t* dMatch = (int32_t*)dalloc((size_t)B * cap * sizeof(int32_t));
+    int32_t* dNm = (int32_t*)dalloc((size_t)B * sizeof(int32_t));
+    float* dFlow = (float*)dalloc((size_t)B * 2 * sizeof(float));  // zero motion guess (TrackWithMotionModel's role)
+    uint8_t* dGray = (uint8_t*)dalloc(frameBytes * B);
+    const size_t recBytes = pgb_frame_record_bytes(cap);
+    uint8_t* dFirstRec = (uint8_t*)dalloc(recBytes);   // this block's first frame, kept for the boundary pair
+    uint8_t* dLastRec = (uint8_t*)dalloc(recBytes);
+    uint8_t* dAllRec = comm ? (uint8_t*)dalloc(recBytes * pgb_comm_size(comm)) : nullptr;
+    uint8_t* dCanvas = nullptr;
+    uint8_t* hRaw = nullptr;
+    int fd = -1;
+    if (src->kind == Source::kSynth) {
+      std::vector<uint8_t> canvas((size_t)src->canvasW * src->canvasH);
+      FILE* f = fopen(src->path.c_str(), "rb");
+      PGB_CHECK(f != nullptr) << "cannot open canvas " << src->path;
+      PGB_CHECK(fread(canvas.data(), 1, canvas.size(), f) == canvas.size()) << "canvas file is smaller than " << src->canvasW << "x" << src->canvasH;
+      fclose(f);
+      dCanvas = (uint8_t*)dalloc(canvas.size());
+      PGB_CALL(pgb_memcpy_async(device, dCanvas, canvas.data(), canvas.size(), 0, st));
+      PGB_CALL(pgb_stream_synchronize(device, st));
+    } else {
+      hRaw = (uint8_t*)pgb_host_malloc_pinned(inBytes * B);
+      PGB_CHECK(hRaw != nullptr) << pgb_last_error();
+      fd = open(src->path.c_str(), O_RDONLY);
+      PGB_CHECK(fd >= 0) << "cannot open " << src->path;
+    }
+    // pinned result buffers
+    pgb_keypoint* hK = (pgb_keypoint*)pgb_host_malloc_pinned((size_t)(B + 1) * cap * sizeof(pgb_keypoint));
+    int32_t* hN = (int32_t*)pgb_host_malloc_pinned((size_t)(B + 1) * sizeof(int32_t));
+    int32_t* hMatch = (int32_t*)pgb_host_malloc_pinned((size_t)B * cap * sizeof(int32_t));
+    int32_t* hNm = (int32_t*)pgb_host_malloc_pinned((size_t)B * sizeof(int32_t));
+    PGB_CHECK(hK && hN && hMatch && hNm) << pgb_last_error();
+
+    // median displacement of pair (prev slot p, cur slot p + 1) from host copies of keypoints and matches
+    std::vector<float> fx, fy;
+    auto finish_pair = [&](FrameResult& r, const pgb_keypoint* prevK, const pgb_keypoint* curK, int nCur, const int32_t* matchOf, int nMatch) {
+      r.n_matches = nMatch;
+      fx.clear(); fy.clear();
+      for (int t = 0; t < nCur; t++) {
+        const int q = matchOf[t];
+        if (q < 0) continue;
+        fx.push_back(curK[t].x - prevK[q].x);
+        fy.push_back(curK[t].y - prevK[q].y);
+      }
+      r.tracked = nMatch >= 20 && !fx.empty();
+      if (r.tracked) {
+        std::nth_element(fx.begin(), fx.begin() + fx.size() / 2, fx.end());
+        std::nth_element(fy.begin(), fy.begin() + fy.size() / 2, fy.end());
+        r.dx = fx[fx.size() / 2]; r.dy = fy[fy.size() / 2];
+      }
+    };
+
+    const auto wall0 = std::chrono::steady_clock::now();
+    bool have_prev = false;
+    for (int64_t b0 = t0; b0 < t1; b0 += B) {
+      const int n = (int)std::min<int64_t>(B, t1 - b0);
+      // ---- frames -> gray on the device -> features in slots 1..n
+      if (src->kind == Source::kSynth) {
+        PGB_CALL(pgb_synth_frames(device, dCanvas, src->canvasW, src->canvasH, (int)b0, n, W, H, dGray, st));
+        PGB_CALL(pgb_orb_extract(orb, dGray, PGB_IN_DEVICE | PGB_OUT_DEVICE, n, W, H, W, frameBytes, dK + cap, dD + (size_t)cap * 32, dN + 1, cap));
+      } else {
+        const ssize_t want = (ssize_t)(inBytes * n);
+        PGB_CHECK(pread(fd, hRaw, want, (off_t)(b0 * (int64_t)inBytes)) == want) << "short read from " << src->path;
+        if (src->kind == Source::kRaw24 || cfg->vertical_flip || cfg->horizontal_flip) {
+          // cv::flip (image_sequence_reader.cc:163-175) and cvtColor (Tracking.cc:243-258; OpenCV 2.4 fixed point) on the device
+          PGB_CALL(pgb_frames_to_gray(device, hRaw, 0, n, W, H, src->channels, cfg->rgb_order, (size_t)W * src->channels, inBytes,
+                                      cfg->vertical_flip ? 1 : 0, cfg->horizontal_flip ? 1 : 0, 0, dGray, 1, W, frameBytes, st));
+          PGB_CALL(pgb_orb_extract(orb, dGray, PGB_IN_DEVICE | PGB_OUT_DEVICE, n, W, H, W, frameBytes, dK + cap, dD + (size_t)cap * 32, dN + 1, cap));
+        } else {
+          PGB_CALL(pgb_orb_extract(orb, hRaw, PGB_OUT_DEVICE, n, W, H, W, frameBytes, dK + cap, dD + (size_t)cap * 32, dN + 1, cap));
+        }
+      }
+      if (b0 == t0 && rank > 0) PGB_CALL(pgb_frame_record_pack(dK, dD, dN, 1, cap, dFirstRec, st));
+      // ---- pairs (slot p, slot p + 1): all n when slot 0 holds the predecessor, else n - 1 starting at slot 1
+      const int first = have_prev ? 0 : 1, np = n - first;
+      if (np > 0)
+        PGB_CALL(pgb_match_consecutive(matcher, np, cap, dK + (size_t)first * cap, dD + (size_t)first * cap * 32, dN + first, dFlow,
+                                       (float)W, (float)H, 15.f, sf.data(), cfg->nlevels, dMatch, dNm));
+      PGB_CALL(pgb_memcpy_async(device, hN, dN, (size_t)(n + 1) * sizeof(int32_t), 1, st));
+      PGB_CALL(pgb_memcpy_async(device, hK, dK, (size_t)(n + 1) * cap * sizeof(pgb_keypoint), 1, st));
+      if (np > 0) {
+        PGB_CALL(pgb_memcpy_async(device, hMatch, dMatch, (size_t)np * cap * sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, hNm, dNm, (size_t)np * sizeof(int32_t), 1, st));
+      }
+      // slot 0 <- this batch's last frame, for the next batch (stream-ordered after the copies above)
+      PGB_CALL(pgb_frame_record_pack(dK, dD, dN, n, cap, dLastRec, st));
+      PGB_CALL(pgb_frame_record_unpack(dLastRec, dK, dD, dN, 0, cap, st));
+      PGB_CALL(pgb_orb_check(orb));  // synchronises the stream, surfaces device-side capacity flags
+      for (int i = 0; i < n; i++) {  // frame i of the batch sits in slot i + 1; its pair (slot i, slot i + 1) is matched pair i - first
+        FrameResult& r = out[b0 + i];
+        r.n_kps = hN[i + 1];
+        if (i >= first) finish_pair(r, hK + (size_t)i * cap, hK + (size_t)(i + 1) * cap, hN[i + 1], hMatch + (size_t)(i - first) * cap, hNm[i - first]);
+      }
+      have_prev = true;
+    }
+    // ---- block boundary: ONE all-gather of every rank's last-frame record; rank r > 0 matches its first frame against
+    //      the left neighbour's last frame
+    if (comm) {
+      PGB_CALL(pgb_allgather_feats(comm, dLastRec, dAllRec, recBytes, st));
+      if (rank > 0 && t1 > t0) {
+        // (every rank owns frames: main() refuses --num_gpus beyond what the frame count can use)
+        PGB_CALL(pgb_frame_record_unpack(dAllRec + (size_t)(rank - 1) * recBytes, dK, dD, dN, 0, cap, st));
+        PGB_CALL(pgb_frame_record_unpack(dFirstRec, dK, dD, dN, 1, cap, st));
+        PGB_CALL(pgb_match_consecutive(matcher, 1, cap, dK, dD, dN, dFlow, (float)W, (float)H, 15.f, sf.data(), cfg->nlevels, dMatch, dNm));
+        PGB_CALL(pgb_memcpy_async(device, hN, dN, 2 * sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, hK, dK, (size_t)2 * cap * sizeof(pgb_keypoint), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, hMatch, dMatch, (size_t)cap * sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, hNm, dNm, sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_orb_check(orb));
+        finish_pair(out[t0], hK, hK + cap, hN[1], hMatch, hNm[0]);
+      } else {
+        PGB_CALL(pgb_stream_synchronize(device, st));
+      }
+    }
+    seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    if (fd >= 0) close(fd);
+    pgb_host_free_pinned(hRaw); pgb_host_free_pinned(hK); pgb_host_free_pinned(hN); pgb_host_free_pinned(hMatch); pgb_host_free_pinned(hNm);
+    for (void* p : {(void*)dK, (void*)dD, (void*)dN, (void*)dMatch, (void*)dNm, (void*)dFlow, (void*)dGray, (void*)dFirstRec, (void*)dLastRec,
+                    (void*)dAllRec, (void*)dCanvas})
+      pgb_device_free(device, p);
+    pgb_matcher_destroy(matcher);
+    pgb_orb_destroy(orb);
+  }
 };
 
 }  // namespace
@@ -59,71 +270,90 @@ struct FrameFeats {
 int main(int argc, char** argv) {
   std::string vocabulary_file, camera_settings, out_dir, in_video;
   bool visualize = true, vertical_flip = false, horizontal_flip = false, output_per_segment_videos = false;
-  int64_t rotation_smooth_sigma = -1, device = 0, batch = 32;
+  int64_t rotation_smooth_sigma = -1, device = 0, batch = 64, num_gpus = 1;
   pgbhost::Flags flags;
   flags.String("vocabulary_file", &vocabulary_file, "ORB vocabulary file.");
   flags.String("camera_settings", &camera_settings, ".yml file with the camera calibration and ORB parameters.");
   flags.String("out_dir", &out_dir, "Directory to write trajectory-<segment>.json files to.");
-  flags.String("in_video", &in_video, "Input frames: raw:<path>:<width>x<height> (8-bit gray).");
+  flags.String("in_video", &in_video, "Input frames: raw:<path>:<w>x<h>, raw24:<path>:<w>x<h> or synth:<canvas>:<cw>x<ch>:<frames>:<w>x<h>.");
   flags.Bool("visualize", &visualize, "accepted, ignored");
   flags.Bool("vertical_flip", &vertical_flip, "Whether to flip input frames vertically.");
   flags.Bool("horizontal_flip", &horizontal_flip, "Whether to flip input frames horizontally.");
   flags.Bool("output_per_segment_videos", &output_per_segment_videos, "accepted, ignored");
   flags.Int64("rotation_smooth_sigma", &rotation_smooth_sigma, "Gaussian sigma (frames) for smoothing rotations; <0: none");
-  flags.Int64("device", &device, "(extension) CUDA device");
+  flags.Int64("device", &device, "(extension) first CUDA device");
+  flags.Int64("num_gpus", &num_gpus, "(extension) GPUs to shard the frames over (devices device .. device+num_gpus-1)");
   flags.Int64("batch", &batch, "(extension) frames per extraction batch");
   flags.Parse(argc, argv);
   PGB_CHECK(!vocabulary_file.empty());
   PGB_CHECK(!camera_settings.empty());
   PGB_CHECK(!in_video.empty());
   PGB_CHECK(batch >= 2);
+  PGB_CHECK(num_gpus >= 1);
 
-  int width = 0, height = 0, channels = 1;
-  char path[4096];
-  if (sscanf(in_video.c_str(), "raw24:%4095[^:]:%dx%d", path, &width, &height) == 3) channels = 3;
-  else
-    PGB_CHECK(sscanf(in_video.c_str(), "raw:%4095[^:]:%dx%d", path, &width, &height) == 3)
-        << "--in_video must be raw:<path>:<width>x<height> or raw24:<path>:<width>x<height> (video decoding is out of "
-           "scope, see the header comment)";
-  PGB_CHECK(width > 0 && height > 0);
-  const auto cfg = ReadSettings(camera_settings);
-  auto get = [&](const char* k, double dflt) { auto it = cfg.find(k); return it == cfg.end() ? dflt : it->second; };
-  const int nfeatures = (int)get("ORBextractor.nFeatures", 1000), nlevels = (int)get("ORBextractor.nLevels", 8);
-  const int ini_th = (int)get("ORBextractor.iniThFAST", 20), min_th = (int)get("ORBextractor.minThFAST", 7);
-  const float scale_factor = (float)get("ORBextractor.scaleFactor", 1.2);
-  double fps = get("Camera.fps", 30.0);
-  if (fps == 0) fps = 30;  // Tracking.cc:86-88
+  const Source src = ParseSource(in_video);
+  const auto kv = ReadSettings(camera_settings);
+  // The fork's keys (Tracking.cc:80,102,131-135; written by src/calibrate.cc:504-544).  Upstream ORB-SLAM2 spells them
+  // with a dot: accepted, with a warning, so that stock example files still work.
+  bool dotted = false;
+  auto get = [&](const char* stem, const char* field, double dflt) {
+    auto it = kv.find(std::string(stem) + "_" + field);
+    if (it != kv.end()) return it->second;
+    it = kv.find(std::string(stem) + "." + field);
+    if (it != kv.end()) { dotted = true; return it->second; }
+    return dflt;
+  };
+  const bool any_orb = kv.count("ORBextractor_nFeatures") || kv.count("ORBextractor_scaleFactor") || kv.count("ORBextractor_nLevels") ||
+                       kv.count("ORBextractor_iniThFAST") || kv.count("ORBextractor_minThFAST") || kv.count("ORBextractor.nFeatures") ||
+                       kv.count("ORBextractor.scaleFactor") || kv.count("ORBextractor.nLevels") || kv.count("ORBextractor.iniThFAST") ||
+                       kv.count("ORBextractor.minThFAST");
+  PGB_CHECK(any_orb) << "the settings file " << camera_settings << " has none of the ORBextractor_* keys (nFeatures, scaleFactor, nLevels, "
+                        "iniThFAST, minThFAST) that Tracking.cc:131-135 reads; refusing to run on defaults";
+  Config cfg;
+  cfg.nfeatures = (int)get("ORBextractor", "nFeatures", 1000);
+  cfg.nlevels = (int)get("ORBextractor", "nLevels", 8);
+  cfg.ini_th = (int)get("ORBextractor", "iniThFAST", 20);
+  cfg.min_th = (int)get("ORBextractor", "minThFAST", 7);
+  cfg.scale_factor = (float)get("ORBextractor", "scaleFactor", 1.2);
+  cfg.fps = get("Camera", "fps", 30.0);
+  if (cfg.fps == 0) cfg.fps = 30;  // Tracking.cc:103-104
+  cfg.rgb_order = (int)get("Camera", "RGB", 1.0);  // Tracking.cc:114-120
+  cfg.vertical_flip = vertical_flip; cfg.horizontal_flip = horizontal_flip;
+  cfg.batch = (int)batch;
+  if (dotted) fprintf(stderr, "W settings file uses upstream ORB-SLAM2's dotted keys (Camera.fps ...); this fork writes Camera_fps ...\n");
 
-  FILE* in = fopen(path, "rb");
-  PGB_CHECK(in != nullptr) << "cannot open " << path;
-  const size_t frame_bytes = (size_t)width * height, in_bytes = frame_bytes * channels;
-  const int rgb_order = (int)get("Camera.RGB", 1.0);  // Tracking.cc:90-96
+  const int N = (int)num_gpus;
+  PGB_CHECK(pgb_device_count() >= (int)device + N) << "--num_gpus " << N << " from device " << device << ": only " << pgb_device_count() << " CUDA device(s)";
+  std::vector<FrameResult> results((size_t)std::max<int64_t>(src.frames, 1));
+  std::vector<pgb_comm*> comms(N, nullptr);
+  if (N > 1) {
+    std::vector<int> devs(N);
+    for (int i = 0; i < N; i++) devs[i] = (int)device + i;
+    PGB_CALL(pgb_comm_create_all(N, devs.data(), comms.data()));
+  }
+  std::vector<Rank> ranks(N);
+  const int64_t per = (src.frames + N - 1) / N;  // contiguous blocks (pilotguru_b200/dist.py: shard_range)
+  for (int r = 0; r < N; r++) {
+    ranks[r].device = (int)device + r; ranks[r].rank = r; ranks[r].comm = comms[r];
+    ranks[r].t0 = std::min<int64_t>(r * per, src.frames); ranks[r].t1 = std::min<int64_t>(ranks[r].t0 + per, src.frames);
+    ranks[r].src = &src; ranks[r].cfg = &cfg; ranks[r].out = results.data();
+  }
+  if (N > 1) PGB_CHECK(ranks[N - 1].t1 > ranks[N - 1].t0) << "--num_gpus " << N << " exceeds what " << src.frames << " frames can use";
+  const auto wall0 = std::chrono::steady_clock::now();
+  {
+    std::vector<std::thread> th;
+    for (int r = 1; r < N; r++) th.emplace_back([&ranks, r] { ranks[r].Run(); });
+    ranks[0].Run();
+    for (auto& t : th) t.join();
+  }
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+  for (pgb_comm* c : comms) pgb_comm_destroy(c);
 
-  const int B = (int)batch;
-  pgb_orb* orb = pgb_orb_create((int)device, nfeatures, scale_factor, nlevels, ini_th, min_th, width, height, B, nullptr);
-  PGB_CHECK(orb != nullptr) << pgb_last_error();
-  const int cap = pgb_orb_max_keypoints(orb);
-  pgb_matcher* matcher = pgb_matcher_create((int)device, 0.9f, 1, cap, B, nullptr);  // ORBmatcher(0.9, true), Tracking.cc:860
-  PGB_CHECK(matcher != nullptr) << pgb_last_error();
-  std::vector<float> sf(nlevels), inv(nlevels), s2(nlevels), is2(nlevels);
-  PGB_CALL(pgb_orb_scale_factors(orb, sf.data(), inv.data(), s2.data(), is2.data()));
-
-  std::vector<uint8_t> frames(frame_bytes * B), raw(in_bytes * B);
-  std::vector<pgb_keypoint> kps((size_t)B * cap);
-  std::vector<uint8_t> desc((size_t)B * cap * 32);
-  std::vector<int32_t> counts(B);
-  // matcher staging (pair p: current = frame p of the batch, queries = its predecessor)
-  std::vector<pgb_keypoint> curK((size_t)B * cap);
-  std::vector<uint8_t> curD((size_t)B * cap * 32), qD((size_t)B * cap * 32), qValid((size_t)B * cap);
-  std::vector<float> qUV((size_t)B * cap * 2), qAng((size_t)B * cap);
-  std::vector<int32_t> qOct((size_t)B * cap), curN(B), qN(B), matchOf((size_t)B * cap), nMatch(B);
-
-  FrameFeats prev;  // last frame of the previous batch (empty before the first frame / after a lost segment)
-  bool have_prev = false;
-  double pos[3] = {0, 0, 0}, heading = 0.0, vflow[2] = {0, 0};
+  // ---- the sequential part: accumulate the per-pair flows into poses, cut segments where tracking was lost
+  double pos[3] = {0, 0, 0}, heading = 0.0;
   std::vector<pgbhost::PoseWithTimestamp> trajectory;
   int segment_id = 0;
-  int64_t frame_id = 0, total_matches = 0, total_kps = 0;
+  int64_t total_matches = 0, total_kps = 0;
   auto close_segment = [&]() {
     if (trajectory.empty()) return;
     char name[64];
@@ -132,91 +362,34 @@ int main(int argc, char** argv) {
     if (flags.verbose) fprintf(stderr, "I segment %d: %zu poses%s\n", segment_id, trajectory.size(), ok ? "" : " (dropped)");
     trajectory.clear();
     segment_id++;
-    pos[0] = pos[1] = pos[2] = 0; heading = 0; vflow[0] = vflow[1] = 0;
+    pos[0] = pos[1] = pos[2] = 0; heading = 0;
   };
-
-  for (;;) {
-    const size_t got = fread(raw.data(), in_bytes, B, in);
-    if (got == 0) break;
-    const int n = (int)got;
-    // cv::flip (image_sequence_reader.cc:163-175) and cvtColor (Tracking.cc:243-258; OpenCV 2.4 fixed point) on the device
-    PGB_CALL(pgb_frames_to_gray((int)device, raw.data(), 0, n, width, height, channels, rgb_order, (size_t)width * channels, in_bytes,
-                                vertical_flip ? 1 : 0, horizontal_flip ? 1 : 0, 0, frames.data(), 0, width, frame_bytes, nullptr));
-    PGB_CALL(pgb_orb_extract(orb, frames.data(), 0, n, width, height, width, frame_bytes, kps.data(), desc.data(), counts.data(), cap));
-    // queries of pair p = keypoints of frame p-1 projected with the motion guess (TrackWithMotionModel's role); the
-    // guess is zero motion: the th=15 / 30 px windows (times the octave scale) cover ordinary inter-frame flow
-    int first = have_prev ? 0 : 1;
-    for (int p = first; p < n; p++) {
-      const pgb_keypoint* pk = p == 0 ? prev.k.data() : kps.data() + (size_t)(p - 1) * cap;
-      const uint8_t* pd = p == 0 ? prev.d.data() : desc.data() + (size_t)(p - 1) * cap * 32;
-      const int np = p == 0 ? (int)prev.k.size() : counts[p - 1];
-      qN[p] = np; curN[p] = counts[p];
-      for (int i = 0; i < np; i++) {
-        const size_t o = (size_t)p * cap + i;
-        qUV[2 * o] = pk[i].x + (float)vflow[0]; qUV[2 * o + 1] = pk[i].y + (float)vflow[1];
-        qOct[o] = pk[i].octave; qAng[o] = pk[i].angle; qValid[o] = 1;
-      }
-      std::copy(pd, pd + (size_t)np * 32, qD.begin() + (size_t)p * cap * 32);
-      std::copy(kps.begin() + (size_t)p * cap, kps.begin() + (size_t)p * cap + counts[p], curK.begin() + (size_t)p * cap);
-      std::copy(desc.begin() + (size_t)p * cap * 32, desc.begin() + ((size_t)p * cap + counts[p]) * 32, curD.begin() + (size_t)p * cap * 32);
+  for (int64_t t = 0; t < src.frames; t++) {
+    const FrameResult& r = results[t];
+    total_kps += r.n_kps;
+    double dx = 0, dy = 0;
+    if (r.n_matches >= 0) {
+      total_matches += r.n_matches;
+      if (r.tracked) { dx = r.dx; dy = r.dy; }
+      else close_segment();  // LOST: this frame starts the next segment
     }
-    const int np = n - first;
-    if (np > 0) {
-      auto run = [&](float th, int p0, int cnt) {
-        const size_t o = (size_t)p0 * cap;
-        PGB_CALL(pgb_match_by_projection(matcher, cnt, cap, curK.data() + o, curD.data() + o * 32, curN.data() + p0, qUV.data() + 2 * o,
-                                         qOct.data() + o, qAng.data() + o, qD.data() + o * 32, qValid.data() + o, qN.data() + p0, 0.f,
-                                         (float)width, 0.f, (float)height, th, sf.data(), nlevels, matchOf.data() + o,
-                                         nMatch.data() + p0, 0));
-      };
-      run(15.f, first, np);                                        // th = 15 for monocular, Tracking.cc:871-876
-      for (int p = first; p < n; p++)
-        if (nMatch[p] < 20) run(30.f, p, 1);                       // Tracking.cc:876-883
-    }
-    for (int p = 0; p < n; p++, frame_id++) {
-      total_kps += counts[p];
-      bool tracked = true;
-      double dx = 0, dy = 0;
-      if (p >= first) {
-        const pgb_keypoint* pk = p == 0 ? prev.k.data() : kps.data() + (size_t)(p - 1) * cap;
-        std::vector<float> fx, fy;
-        for (int t = 0; t < counts[p]; t++) {
-          const int q = matchOf[(size_t)p * cap + t];
-          if (q < 0) continue;
-          fx.push_back(kps[(size_t)p * cap + t].x - pk[q].x);
-          fy.push_back(kps[(size_t)p * cap + t].y - pk[q].y);
-        }
-        total_matches += nMatch[p];
-        tracked = nMatch[p] >= 20 && !fx.empty();
-        if (tracked) {
-          std::nth_element(fx.begin(), fx.begin() + fx.size() / 2, fx.end());
-          std::nth_element(fy.begin(), fy.begin() + fy.size() / 2, fy.end());
-          dx = fx[fx.size() / 2]; dy = fy[fy.size() / 2];
-        }
-      }
-      if (!tracked) {  // LOST: close the segment; this frame starts the next one
-        close_segment();
-      }
-      pos[0] -= dx; pos[2] -= dy;
-      if (dx != 0 || dy != 0) heading = std::atan2(-dx, -dy);
-      pgbhost::PoseWithTimestamp pw;
-      pw.pose.t[0] = pos[0]; pw.pose.t[1] = pos[1]; pw.pose.t[2] = pos[2];
-      pw.pose.qw = std::cos(heading * 0.5); pw.pose.qx = 0; pw.pose.qy = std::sin(heading * 0.5); pw.pose.qz = 0;
-      pw.time_usec = (int64_t)std::llround((double)frame_id * 1e6 / fps);
-      pw.is_lost = false;
-      pw.frame_id = frame_id;
-      trajectory.push_back(pw);
-    }
-    prev.k.assign(kps.begin() + (size_t)(n - 1) * cap, kps.begin() + (size_t)(n - 1) * cap + counts[n - 1]);
-    prev.d.assign(desc.begin() + (size_t)(n - 1) * cap * 32, desc.begin() + ((size_t)(n - 1) * cap + counts[n - 1]) * 32);
-    have_prev = true;
+    pos[0] -= dx; pos[2] -= dy;
+    if (dx != 0 || dy != 0) heading = std::atan2(-dx, -dy);
+    pgbhost::PoseWithTimestamp pw;
+    pw.pose.t[0] = pos[0]; pw.pose.t[1] = pos[1]; pw.pose.t[2] = pos[2];
+    pw.pose.qw = std::cos(heading * 0.5); pw.pose.qx = 0; pw.pose.qy = std::sin(heading * 0.5); pw.pose.qz = 0;
+    pw.time_usec = (int64_t)std::llround((double)t * 1e6 / cfg.fps);
+    pw.is_lost = false;
+    pw.frame_id = t;
+    trajectory.push_back(pw);
   }
-  fclose(in);
   close_segment();
-  if (flags.verbose)
-    fprintf(stderr, "I %lld frames, %.1f keypoints/frame, %.1f matches/frame, %d segment(s)\n", (long long)frame_id,
-            frame_id ? (double)total_kps / frame_id : 0.0, frame_id > 1 ? (double)total_matches / (frame_id - 1) : 0.0, segment_id);
-  pgb_matcher_destroy(matcher);
-  pgb_orb_destroy(orb);
+  if (flags.verbose) {
+    fprintf(stderr, "I %lld frames, %.1f keypoints/frame, %.1f matches/frame, %d segment(s)\n", (long long)src.frames,
+            src.frames ? (double)total_kps / src.frames : 0.0, src.frames > 1 ? (double)total_matches / (src.frames - 1) : 0.0, segment_id);
+    fprintf(stderr, "I extract+match: %.3f s on %d GPU(s) = %.0f frames/s (per-rank seconds:", wall, N, src.frames / std::max(wall, 1e-9));
+    for (int r = 0; r < N; r++) fprintf(stderr, " %.3f", ranks[r].seconds);
+    fprintf(stderr, "); totals: %lld keypoints, %lld matches\n", (long long)total_kps, (long long)total_matches);
+  }
   return EXIT_SUCCESS;
 }

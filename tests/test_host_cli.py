@@ -135,7 +135,7 @@ def test_optical_trajectories_flags(host_bins):
     p = run(host_bins, "optical_trajectories")
     assert p.returncode == -6 and "Check failed: !vocabulary_file.empty()" in p.stderr
     p = run(host_bins, "optical_trajectories", "--vocabulary_file=v", "--camera_settings=/nonexistent.yml", "--in_video=video.mp4")
-    assert p.returncode == -6 and "raw:<path>:<width>x<height>" in p.stderr
+    assert p.returncode == -6 and "raw:<path>:<w>x<h>" in p.stderr and "synth:<canvas>" in p.stderr
 
 
 def test_json_number_forms(host_bins, tmp_path):
