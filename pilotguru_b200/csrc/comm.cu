@@ -194,6 +194,7 @@ int pgb_frame_record_unpack(const void* record, pgb_keypoint* kps, uint8_t* desc
 int pgb_allgather_feats(pgb_comm* c, const void* send, void* recv, size_t bytes_per_rank, void* stream) {
   if (!c || !send || !recv) return fail(PGB_ERR_INVALID, "pgb_allgather_feats: null argument");
   if (bytes_per_rank == 0) return PGB_OK;
+  NvtxRange range("pgb_allgather_feats");
   PGB_CUDA(cudaSetDevice(c->device));
   ncclResult_t r = nccl()->AllGather(send, recv, bytes_per_rank, kNcclUint8, c->comm, (cudaStream_t)stream);
   if (r) return nccl_fail("ncclAllGather", r);

@@ -1,6 +1,7 @@
 // Shared host-side plumbing for libpgb200.so: error reporting, launch accounting, small RAII helpers.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: no-ops unless a profiler is attached
 
 #include <atomic>
 #include <cstdarg>
@@ -102,6 +103,15 @@ struct TempBuf {
 };
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// NVTX range around a host-side phase (kernel launches of a stage, a collective, a solver call): shows up as a named span in
+// Nsight Systems / ncu --nvtx captures (tracing hooks).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair, not to a handle: one limit object
 // per kernel keeps the process-wide maximum ever requested on each device and only ever raises the attribute, so a

@@ -470,6 +470,7 @@ int ensure(DevBuf<T>& d, size_t n) {
 // Builds intervals for the GPS series, the window list, and runs sweep + chain.
 int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, int batch, int step, int first_window,
             int n_windows) {
+  NvtxRange range("pgb:imu:intervals+sweep+chain");
   if (n_gps <= 0 || !gps_v || !gps_t) return fail(PGB_ERR_INVALID, "empty GPS series");
   int rc = check_increasing(gps_t, n_gps, "GPS");
   if (rc) return rc;
@@ -534,6 +535,7 @@ int prepare(pgb_imu* o, const double* gps_v, const int64_t* gps_t, int n_gps, in
 int solve(pgb_imu* o, int maxIter, double eps, int useX0) {
   const int nW = (int)o->win.size();
   if (nW == 0) return PGB_OK;
+  NvtxRange range("pgb:imu:lbfgs_solve");
   k_imu_solve<<<(nW + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, 0, o->stream>>>(nW, o->dWin.p, o->maxRefs, o->dRec.p, o->dTotal.p, maxIter, eps, useX0,
                                                     o->dX.p, o->dFx.p, o->dIt.p, o->dNe.p);
   PGB_CHECK_LAUNCH();
@@ -543,6 +545,7 @@ int solve(pgb_imu* o, int maxIter, double eps, int useX0) {
 int speeds(pgb_imu* o, bool full, bool fwd = false, double minVel = 0.0) {
   const int nW = (int)o->win.size();
   if (nW == 0 || o->spTotal == 0) return PGB_OK;
+  NvtxRange range("pgb:imu:speeds");
   if (ensure(o->dSpeeds, o->spTotal)) return PGB_ERR_CUDA;
   if (fwd && ensure(o->dFwd, 4 * (size_t)nW * o->maxRefs)) return PGB_ERR_CUDA;
   if (full && (ensure(o->dQuat, 4 * o->spTotal) || ensure(o->dVel, 3 * o->spTotal))) return PGB_ERR_CUDA;

@@ -890,6 +890,7 @@ struct pgb_matcher {
 namespace {
 
 int launch_match(pgb_matcher* m, MatchArgs& A, int nPairs) {
+  NvtxRange range(A.onlyIfBelow20 ? "pgb:match:retry_2th" : "pgb:match:search_by_projection");
   if (A.cap > m->maxFeats) return fail(PGB_ERR_CAPACITY, "cap %d exceeds the matcher's max_feats %d", A.cap, m->maxFeats);
   if (nPairs > m->maxBatch) return fail(PGB_ERR_CAPACITY, "n_pairs %d exceeds the matcher's max_batch %d", nPairs, m->maxBatch);
   const size_t smem = match_smem_bytes(A.cap);

@@ -421,7 +421,9 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
   unsigned long long* cand = o->cand.p + (size_t)f0 * g.candPerFrame;
   StagedKp* staged = o->staged.p + (size_t)f0 * g.kpCapInternal;
   int* lvlCnt = o->lvlCnt.p + (size_t)f0 * g.nlevels;
+  static const char* kStageName[5] = {"pgb:orb:pyramid", "pgb:orb:fast_cells", "pgb:orb:unfused_fast+cells", "pgb:orb:octree", "pgb:orb:orient_desc"};
   for (int s = from; s <= to; s++) {
+    NvtxRange range(kStageName[s]);
     switch (s) {
       case 0:
         for (int l = 1; l < g.nlevels; l++)
@@ -677,6 +679,7 @@ void* pgb_orb_stream(pgb_orb* o) { return o ? (void*)o->stream : nullptr; }
 int pgb_orb_extract(pgb_orb* o, const uint8_t* gray, int is_device, int n_frames, int width, int height, size_t pitch,
                     size_t frame_stride, pgb_keypoint* kps, uint8_t* desc, int32_t* counts, int cap) {
   if (!o) return fail(PGB_ERR_INVALID, "null handle");
+  NvtxRange range("pgb_orb_extract");
   if (n_frames < 0 || n_frames > o->maxBatch) return fail(PGB_ERR_INVALID, "n_frames %d outside [0,%d]", n_frames, o->maxBatch);
   if (!counts || (cap > 0 && (!kps || !desc)) || cap < 0) return fail(PGB_ERR_INVALID, "null output buffer");
   PGB_CUDA(cudaSetDevice(o->device));

@@ -104,7 +104,9 @@ if not args.only_frames:
     d = synth.imu_gps(secs, args.imu_hz)
     paths = synth.write_imu_gps_json(d, args.work)
     frames_json = os.path.join(args.work, "frames.json")
-    json.dump({"frames": [{"frame_id": i, "time_usec": int(round(i * 1e6 / args.fps))} for i in range(n_frames)]}, open(frames_json, "w"))
+    # (+137 us: a frame timestamp EXACTLY equal to the last velocity timestamp trips the reference's own CHECK in
+    # TimeSeries::LinearInterpolate, time_series.hpp:210-213, which annotate_frames reproduces; recorded data never ties)
+    json.dump({"frames": [{"frame_id": i, "time_usec": int(round(i * 1e6 / args.fps)) + 137} for i in range(n_frames)]}, open(frames_json, "w"))
     summary["stages_s"]["generate IMU/GPS/frames JSON (python)"] = round(time.time() - t0, 3)
     vel, steer, fwd = (os.path.join(args.work, n) for n in ("velocities.json", "steering.json", "forward.json"))
     run(f"fit_motion ({args.gpus} GPU)", [os.path.join(HOST, "fit_motion"), "--rotations_json", paths["rotations"], "--accelerations_json", paths["accelerations"],
