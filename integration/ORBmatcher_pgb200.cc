@@ -27,21 +27,24 @@ namespace ORB_SLAM2 {
 
 namespace {
 std::mutex g_mu;
-std::map<const ORBmatcher*, std::pair<pgb_matcher*, int>> g_handles;  // handle and the feature capacity it was created for
+struct Entry { pgb_matcher* h = nullptr; int cap = 0; float nnratio = 0; bool checkOri = false; };
+std::map<const ORBmatcher*, Entry> g_handles;  // keyed by object address: the parameters are re-checked on every call
 [[noreturn]] void die(const char* what) {
   fprintf(stderr, "F ORBmatcher(pgb200): %s: %s\n", what, pgb_last_error());
   abort();
 }
 pgb_matcher* handle_for(const ORBmatcher* m, float nnratio, bool checkOri, int cap) {
   std::lock_guard<std::mutex> l(g_mu);
-  auto& e = g_handles[m];
-  if (!e.first || e.second < cap) {
-    if (e.first) pgb_matcher_destroy(e.first);
-    e.second = std::max(cap, 2048);
-    e.first = pgb_matcher_create(/*device*/ 0, nnratio, checkOri ? 1 : 0, e.second, /*max_batch*/ 1, nullptr);
-    if (!e.first) die("pgb_matcher_create");
+  Entry& e = g_handles[m];
+  // (a matcher object that died and another one constructed at the same address look alike to this registry: the handle is
+  // only reused when it was made for the same parameters)
+  if (!e.h || e.cap < cap || e.nnratio != nnratio || e.checkOri != checkOri) {
+    if (e.h) pgb_matcher_destroy(e.h);
+    e.cap = std::max(cap, 2048); e.nnratio = nnratio; e.checkOri = checkOri;
+    e.h = pgb_matcher_create(/*device*/ 0, nnratio, checkOri ? 1 : 0, e.cap, /*max_batch*/ 1, nullptr);
+    if (!e.h) die("pgb_matcher_create");
   }
-  return e.first;
+  return e.h;
 }
 }  // namespace
 

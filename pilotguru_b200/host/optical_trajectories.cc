@@ -36,7 +36,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -166,12 +168,20 @@ struct Rank {
       fd = open(src->path.c_str(), O_RDONLY);
       PGB_CHECK(fd >= 0) << "cannot open " << src->path;
     }
-    // pinned result buffers
-    pgb_keypoint* hK = (pgb_keypoint*)pgb_host_malloc_pinned((size_t)(B + 1) * cap * sizeof(pgb_keypoint));
-    int32_t* hN = (int32_t*)pgb_host_malloc_pinned((size_t)(B + 1) * sizeof(int32_t));
-    int32_t* hMatch = (int32_t*)pgb_host_malloc_pinned((size_t)B * cap * sizeof(int32_t));
-    int32_t* hNm = (int32_t*)pgb_host_malloc_pinned((size_t)B * sizeof(int32_t));
-    PGB_CHECK(hK && hN && hMatch && hNm) << pgb_last_error();
+    // Two sets of pinned result buffers: while the GPU works on batch k + 1, a worker thread turns batch k's keypoints and
+    // matches into per-frame results (the median displacement of ~750 matches per pair costs the host ~40 us, as much as the
+    // GPU needs for the frame; done inline it held the GPU at a third of its rate).
+    struct HostSet {
+      pgb_keypoint* K; int32_t* N; int32_t* Match; int32_t* Nm;
+      int n = 0, first = 0; int64_t b0 = 0; bool busy = false;
+    } hs[2];
+    for (HostSet& h : hs) {
+      h.K = (pgb_keypoint*)pgb_host_malloc_pinned((size_t)(B + 1) * cap * sizeof(pgb_keypoint));
+      h.N = (int32_t*)pgb_host_malloc_pinned((size_t)(B + 1) * sizeof(int32_t));
+      h.Match = (int32_t*)pgb_host_malloc_pinned((size_t)B * cap * sizeof(int32_t));
+      h.Nm = (int32_t*)pgb_host_malloc_pinned((size_t)B * sizeof(int32_t));
+      PGB_CHECK(h.K && h.N && h.Match && h.Nm) << pgb_last_error();
+    }
 
     // median displacement of pair (prev slot p, cur slot p + 1) from host copies of keypoints and matches
     std::vector<float> fx, fy;
@@ -191,11 +201,41 @@ struct Rank {
         r.dx = fx[fx.size() / 2]; r.dy = fy[fy.size() / 2];
       }
     };
+    auto finish_set = [&](HostSet& h) {
+      for (int i = 0; i < h.n; i++) {  // frame i of the batch sits in slot i + 1; its pair (slot i, slot i + 1) is matched pair i - first
+        FrameResult& r = out[h.b0 + i];
+        r.n_kps = h.N[i + 1];
+        if (i >= h.first) finish_pair(r, h.K + (size_t)i * cap, h.K + (size_t)(i + 1) * cap, h.N[i + 1], h.Match + (size_t)(i - h.first) * cap, h.Nm[i - h.first]);
+      }
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    int pending = -1;  // set handed to the worker, -1 = none, -2 = quit
+    std::thread worker([&] {
+      for (;;) {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return pending != -1; });
+        if (pending == -2) return;
+        HostSet& h = hs[pending];
+        pending = -1;
+        l.unlock();
+        finish_set(h);
+        l.lock();
+        h.busy = false;
+        cv.notify_all();
+      }
+    });
 
     const auto wall0 = std::chrono::steady_clock::now();
     bool have_prev = false;
-    for (int64_t b0 = t0; b0 < t1; b0 += B) {
+    int k = 0;
+    for (int64_t b0 = t0; b0 < t1; b0 += B, k++) {
       const int n = (int)std::min<int64_t>(B, t1 - b0);
+      HostSet& h = hs[k & 1];
+      {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return !h.busy; });  // the worker is done with this set (two batches ago)
+      }
       // ---- frames -> gray on the device -> features in slots 1..n
       if (src->kind == Source::kSynth) {
         PGB_CALL(pgb_synth_frames(device, dCanvas, src->canvasW, src->canvasH, (int)b0, n, W, H, dGray, st));
@@ -218,23 +258,34 @@ struct Rank {
       if (np > 0)
         PGB_CALL(pgb_match_consecutive(matcher, np, cap, dK + (size_t)first * cap, dD + (size_t)first * cap * 32, dN + first, dFlow,
                                        (float)W, (float)H, 15.f, sf.data(), cfg->nlevels, dMatch, dNm));
-      PGB_CALL(pgb_memcpy_async(device, hN, dN, (size_t)(n + 1) * sizeof(int32_t), 1, st));
-      PGB_CALL(pgb_memcpy_async(device, hK, dK, (size_t)(n + 1) * cap * sizeof(pgb_keypoint), 1, st));
+      PGB_CALL(pgb_memcpy_async(device, h.N, dN, (size_t)(n + 1) * sizeof(int32_t), 1, st));
+      PGB_CALL(pgb_memcpy_async(device, h.K, dK, (size_t)(n + 1) * cap * sizeof(pgb_keypoint), 1, st));
       if (np > 0) {
-        PGB_CALL(pgb_memcpy_async(device, hMatch, dMatch, (size_t)np * cap * sizeof(int32_t), 1, st));
-        PGB_CALL(pgb_memcpy_async(device, hNm, dNm, (size_t)np * sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, h.Match, dMatch, (size_t)np * cap * sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, h.Nm, dNm, (size_t)np * sizeof(int32_t), 1, st));
       }
       // slot 0 <- this batch's last frame, for the next batch (stream-ordered after the copies above)
       PGB_CALL(pgb_frame_record_pack(dK, dD, dN, n, cap, dLastRec, st));
       PGB_CALL(pgb_frame_record_unpack(dLastRec, dK, dD, dN, 0, cap, st));
       PGB_CALL(pgb_orb_check(orb));  // synchronises the stream, surfaces device-side capacity flags
-      for (int i = 0; i < n; i++) {  // frame i of the batch sits in slot i + 1; its pair (slot i, slot i + 1) is matched pair i - first
-        FrameResult& r = out[b0 + i];
-        r.n_kps = hN[i + 1];
-        if (i >= first) finish_pair(r, hK + (size_t)i * cap, hK + (size_t)(i + 1) * cap, hN[i + 1], hMatch + (size_t)(i - first) * cap, hNm[i - first]);
+      h.n = n; h.first = first; h.b0 = b0;
+      {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return pending == -1; });
+        h.busy = true;
+        pending = k & 1;
+        cv.notify_all();
       }
       have_prev = true;
     }
+    {
+      std::unique_lock<std::mutex> l(mu);
+      cv.wait(l, [&] { return pending == -1 && !hs[0].busy && !hs[1].busy; });
+      pending = -2;
+      cv.notify_all();
+    }
+    worker.join();
+    pgb_keypoint* hK = hs[0].K; int32_t* hN = hs[0].N; int32_t* hMatch = hs[0].Match; int32_t* hNm = hs[0].Nm;
     // ---- block boundary: ONE all-gather of every rank's last-frame record; rank r > 0 matches its first frame against
     //      the left neighbour's last frame
     if (comm) {
@@ -256,7 +307,8 @@ struct Rank {
     }
     seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
     if (fd >= 0) close(fd);
-    pgb_host_free_pinned(hRaw); pgb_host_free_pinned(hK); pgb_host_free_pinned(hN); pgb_host_free_pinned(hMatch); pgb_host_free_pinned(hNm);
+    pgb_host_free_pinned(hRaw);
+    for (HostSet& h : hs) { pgb_host_free_pinned(h.K); pgb_host_free_pinned(h.N); pgb_host_free_pinned(h.Match); pgb_host_free_pinned(h.Nm); }
     for (void* p : {(void*)dK, (void*)dD, (void*)dN, (void*)dMatch, (void*)dNm, (void*)dFlow, (void*)dGray, (void*)dFirstRec, (void*)dLastRec,
                     (void*)dAllRec, (void*)dCanvas})
       pgb_device_free(device, p);
