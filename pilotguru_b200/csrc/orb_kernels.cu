@@ -136,21 +136,25 @@ __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint
   }
 }
 
-// Column-walk variant (round 2, the default): the round-1 profile of k_pyramid_tiled (profiles/r01e_other_kernels_sass_regions.md)
-// showed 4.7 M warp-instructions per frame, 42 % of them in a horizontal pass that went through shared memory as u16
-// (8.1 instructions per value) and 40 % in a vertical pass that read it back.  Here a thread owns ONE destination column
-// and walks down the tile: the horizontal interpolation of a source row is computed once (2 byte loads, 2 IMAD on the
-// FMA pipe, one shift), lives in a register, and is reused by the two destination rows that touch it -- the u16
-// intermediate never exists in shared memory.  Which source rows a destination row needs is warp-uniform (the row
-// table of the tile is in shared memory), so the walk has no divergence.  The source footprint comes in with one TMA
-// load (no staging instructions), the 256 x 32 result goes through an 8 KB shared tile so that global stores are
-// 16-byte vectors.  Same integer arithmetic as k_pyramid, bit for bit.
+// Round-2 kernel (the default).  The round-1 profile of k_pyramid_tiled (profiles/r01e_other_kernels_sass_regions.md) showed
+// 4.7 M warp-instructions per frame, 42 % of them in a horizontal pass that went through shared memory as u16 and 40 % in
+// a vertical pass that read it back; a first rewrite with one byte load per source pixel (thread = one destination column)
+// cut the instructions by 18 % but saturated the shared-memory pipe instead (l1tex 94 %, profiles/r02_kernels_ncu_full.md).
+// This one is built around LOAD count:
+//   * the source footprint of a 256 x 32 tile comes in with ONE TMA load (no staging instructions);
+//   * a thread owns FOUR adjacent destination columns and 8 destination rows.  At scale <= 1.25 the 8 source bytes its four
+//     columns need from a source row lie inside a 12-byte aligned window: three 32-bit shared loads per source row (instead
+//     of 8 byte loads), two funnel shifts align the window to the first column's left pixel, and two PRMT with per-thread
+//     selectors (constant down the tile) produce (left, right) byte pairs, one pair per 16-bit half;
+//   * IDP.2A (dp2a) multiplies a pair by the column's (a0, a1) coefficient pair: one instruction per horizontal
+//     interpolation; the vertical interpolation is two IMAD + shifts; the four results leave as one 32-bit global store
+//     (a warp writes 128 contiguous bytes).
+// Same integer arithmetic as k_pyramid, bit for bit (all values are non-negative and below 2^27).
 __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ OrbGeo g, const __grid_constant__ TmapIn tm,
                                                       int level, int frame0, uint8_t* __restrict__ pyr,
                                                       const ResizeTab* __restrict__ xtab, const ResizeTab* __restrict__ ytab,
                                                       const int2* __restrict__ tileX, const int2* __restrict__ tileY) {
   __shared__ __align__(128) uint8_t s_src[kPySrcRows * kPySrcPitch];
-  __shared__ __align__(16) uint8_t s_out[kPyH * kPyW];
   __shared__ uint4 s_row[kPyH];
   __shared__ __align__(8) uint64_t s_bar;
   using namespace fastk;
@@ -171,45 +175,66 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
     const int r0 = min(max((int)ty.s, 0), S.h - 1) - syLo, r1 = min(max((int)ty.s + 1, 0), S.h - 1) - syLo;
     s_row[tid] = make_uint4((uint32_t)(r0 * kPySrcPitch), (uint32_t)(r1 * kPySrcPitch), (uint32_t)ty.a0, (uint32_t)ty.a1);
   }
-  const int x = min(x0 + tid, D.w - 1);
-  const ResizeTab tx = xtab[x];
-  // the right neighbour is always read at +1: where cv::resize clamps it to the last column its coefficient a1 is 0
-  // (make_resize_tab, clampCoef), and the byte read instead is still inside the staged box
-  const uint8_t* c0 = s_src + (tx.s - ax);
-  const uint32_t a0 = (uint32_t)tx.a0, a1 = (uint32_t)tx.a1;
+  // this thread's four columns: coefficient pairs (a0 | a1 << 16) and the byte offsets of their left pixels inside the
+  // 8-byte window that starts at the first column's left pixel.  The right neighbour is always the next byte: where
+  // cv::resize clamps it to the last column its coefficient a1 is 0 (make_resize_tab, clampCoef) and the byte read instead
+  // is still inside the staged box.
+  const int cg = tid & 63, rg = tid >> 6;
+  const int gx = x0 + 4 * cg;
+  uint32_t coef[4];
+  int off[4];
+  int s0 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const ResizeTab tx = xtab[min(gx + k, D.w - 1)];
+    if (k == 0) s0 = tx.s;
+    coef[k] = (uint32_t)(uint16_t)tx.a0 | ((uint32_t)(uint16_t)tx.a1 << 16);
+    off[k] = tx.s - s0;  // 0 <= off <= 6 for scale factors the tiled path accepts (pyramid_tile_fits: <= 1.5)
+  }
+  const int rel = s0 - ax;                       // first needed byte inside a staged row
+  const uint8_t* wbase = s_src + (rel & ~3);     // its aligned word
+  const uint32_t shift = 8u * (uint32_t)(rel & 3);
+  // PRMT selectors on the aligned 8-byte window (v0 = bytes 0..3, v1 = bytes 4..7): [l_k, r_k, l_k+1, r_k+1]
+  const uint32_t selAB = (uint32_t)off[0] | ((uint32_t)(off[0] + 1) << 4) | ((uint32_t)off[1] << 8) | ((uint32_t)(off[1] + 1) << 12);
+  const uint32_t selCD = (uint32_t)off[2] | ((uint32_t)(off[2] + 1) << 4) | ((uint32_t)off[3] << 8) | ((uint32_t)(off[3] + 1) << 12);
   __syncthreads();
   while (!mbar_try_wait(&s_bar, 0)) {
   }
-  // Straight-line body, no reuse between rows (a version that kept the interpolated source rows in registers needed
-  // warp-uniform branches the compiler could not prove uniform: ~60 instructions per pixel instead of ~19, 7.7 us/frame).
-  // All coefficients are in [0, 2048] and the interpolated values below 2^15: unsigned arithmetic is exact.
-  const int rows = min(kPyH, D.h - y0);
-#pragma unroll 8
-  for (int ry = 0; ry < kPyH; ry++) {
+  // horizontal interpolation (>> 4, cv::resize's intermediate) of this thread's four columns on the staged row at byte offset ro
+  auto hrow = [&](uint32_t ro, uint32_t h[4]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(wbase + ro);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    const uint32_t v0 = __funnelshift_r(w0, w1, shift), v1 = __funnelshift_r(w1, w2, shift);
+    const uint32_t ab = __byte_perm(v0, v1, selAB), cd = __byte_perm(v0, v1, selCD);
+    h[0] = __dp2a_lo(coef[0], ab, 0u) >> 4;
+    h[1] = __dp2a_hi(coef[1], ab, 0u) >> 4;
+    h[2] = __dp2a_lo(coef[2], cd, 0u) >> 4;
+    h[3] = __dp2a_hi(coef[3], cd, 0u) >> 4;
+  };
+  uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameStride + D.off + (size_t)(y0 + rg * 8) * D.pitch + gx;
+  const bool colOk = gx < D.pitch;  // columns beyond the level's width land in the pitch padding (a multiple of 64 >= w)
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int ry = rg * 8 + j;
     const uint4 rw = s_row[ry];  // warp-uniform: one broadcast load
-    const uint8_t* p0 = c0 + rw.x;
-    const uint8_t* p1 = c0 + rw.y;
-    uint32_t h0, h1, t0, t1;
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(h0) : "r"((uint32_t)p0[0]), "r"(a0));
-    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h0) : "r"((uint32_t)p0[1]), "r"(a1));
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(h1) : "r"((uint32_t)p1[0]), "r"(a0));
-    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h1) : "r"((uint32_t)p1[1]), "r"(a1));
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t0) : "r"(h0 >> 4), "r"(rw.z));
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t1) : "r"(h1 >> 4), "r"(rw.w));
-    s_out[ry * kPyW + tid] = (uint8_t)(((t0 >> 16) + (t1 >> 16) + 2) >> 2);
-  }
-  __syncthreads();
-  // 256 x 32 bytes out as 16-byte vectors: thread = (row, 32-byte segment).  Segments start inside the level's pitch
-  // (a multiple of 64); bytes beyond the level's width land in the pitch padding, which no consumer reads.
-  {
-    const int ry = tid >> 3, seg = (tid & 7) * 32;
-    const int gx = x0 + seg;
-    if (ry < rows && gx < D.pitch) {
-      uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameStride + D.off + (size_t)(y0 + ry) * D.pitch + gx;
-      const uint4* src = reinterpret_cast<const uint4*>(s_out + ry * kPyW + seg);
-      reinterpret_cast<uint4*>(dst)[0] = src[0];
-      if (gx + 16 < D.pitch) reinterpret_cast<uint4*>(dst)[1] = src[1];
+    uint32_t ha[4], hb[4];
+    hrow(rw.x, ha);
+    hrow(rw.y, hb);
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      // (tried: masking the low 4 bits instead of shifting and taking ((h >> 4) * b) >> 16 as mul.hi(h & ~15, b << 12), which
+      // moves 8 shifts per row from the ALU pipe to the FMA pipe: IMAD.HI issues at a quarter rate, 4.52 -> 4.90 us/frame)
+      uint32_t t0, t1;
+      asm("mul.lo.u32 %0, %1, %2;" : "=r"(t0) : "r"(ha[k]), "r"(rw.z));
+      asm("mul.lo.u32 %0, %1, %2;" : "=r"(t1) : "r"(hb[k]), "r"(rw.w));
+      v[k] = ((t0 >> 16) + (t1 >> 16) + 2) >> 2;  // in [0, 255]: a convex combination of bytes
     }
+    uint32_t out;  // v0 | v1 << 8 | v2 << 16 | v3 << 24 by Horner on the FMA pipe (the ALU pipe carries the shifts)
+    asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(out) : "r"(v[3]), "r"(v[2]));
+    asm("mad.lo.u32 %0, %0, 256, %1;" : "+r"(out) : "r"(v[1]));
+    asm("mad.lo.u32 %0, %0, 256, %1;" : "+r"(out) : "r"(v[0]));
+    if (colOk && y0 + ry < D.h) *reinterpret_cast<uint32_t*>(dst + (size_t)j * D.pitch) = out;
   }
 }
 
