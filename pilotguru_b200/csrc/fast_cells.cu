@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(kFcThreads, kOcc) k_fast_cells(const __grid_co
             }
           }
           if (nParts == 1) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, corner);  // (also orders this round's queue reads before the writes)
+            const uint32_t bal = __ballot_sync(0xffffffffu, corner);
+            __syncwarp();  // this round's queue reads (all lanes) are ordered before the in-place writes below
             if (corner) q[nCorner + __popc(bal & ((1u << lane) - 1u))] = entry;
             nCorner += __popc(bal);
           }
