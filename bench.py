@@ -217,6 +217,41 @@ def cpu_run(n_frames, threads, frames=None, flows=None):
     return sec, nk, nm, build
 
 
+def cv2_orb_baseline(frames, threads):
+    """A second CPU data point: OpenCV's OWN optimised ORB + brute-force Hamming matcher on the same frames --
+    cv2.ORB_create(1000, 1.2, 8).detectAndCompute per frame, cv2.BFMatcher(NORM_HAMMING).match per consecutive pair, one
+    frame per host thread (cv2.setNumThreads(1)).  NOT the reference's algorithm (no 30-px cell grid with threshold retry,
+    no octree distribution, no projection windows): it bounds from above what a SIMD implementation of a comparable
+    pipeline does on these cores, so the GPU/CPU ratio against the scalar port has an honest companion.  None if cv2 is absent."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    import concurrent.futures as cf
+    cv2.setNumThreads(1)
+    n = len(frames)
+
+    def work(rng):
+        orb = cv2.ORB_create(nfeatures=NFEAT, scaleFactor=1.2, nlevels=8)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        prev = None
+        for i in rng:
+            k, d = orb.detectAndCompute(frames[i], None)
+            if prev is not None and d is not None and prev is not None:
+                bf.match(prev, d)
+            prev = d
+        return len(rng)
+
+    chunks = [range(a, min(a + (n + threads - 1) // threads, n)) for a in range(0, n, (n + threads - 1) // threads)]
+    work(range(0, min(2, n)))                                             # warm
+    t0 = time.time()
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, chunks))
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": "cv2.ORB + BFMatcher (OpenCV %s), a different, SIMD-optimised pipeline" % cv2.__version__,
+            "sample": f"{n} synthetic 1080p frames, {dt:.1f} s wall"}
+
+
 def calibration_cpu_baseline(d, hz, cores, budget_s=20.0):
     """CPU baseline of the calibration leg: the oracle's window loop (fit_motion.cc:156-293) on all host cores -- one
     independent 60-s slice of the recording per thread (12 windows of 500 L-BFGS iterations each) -- in the LITERAL
@@ -727,6 +762,7 @@ def main():
             line["parity_checked"] = True
             if not same:
                 raise SystemExit(f"bench.py: GPU and CPU legs disagree: keypoints {cnt_dev[1:m + 1][:8]} vs {nk[:8]}, matches {nm_dev[1:m][:8]} vs {nm[1:m][:8]}")
+            line["cpu_baseline_cv2_orb"] = cv2_orb_baseline(frames_np[:min(len(frames_np), 8 * cores)], cores)
             line["cpu_baseline"] = {"value": n / sec, "unit": "frames/s", "cores": cores, "kind": "port", "build": build,
                                     "sample": f"{n} synthetic 1080p frames (extract every frame + match every consecutive pair), oracle on {cores} host threads ({sec:.1f} s wall)"}
         if not args.no_calibration and world == 1:

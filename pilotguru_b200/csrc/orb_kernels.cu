@@ -173,7 +173,14 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
   if (tid < kPyH) {  // per destination row: byte offsets of its two source rows inside the staged box + the two coefficients
     const ResizeTab ty = ytab[min(y0 + tid, D.h - 1)];
     const int r0 = min(max((int)ty.s, 0), S.h - 1) - syLo, r1 = min(max((int)ty.s + 1, 0), S.h - 1) - syLo;
-    s_row[tid] = make_uint4((uint32_t)(r0 * kPySrcPitch), (uint32_t)(r1 * kPySrcPitch), (uint32_t)ty.a0, (uint32_t)ty.a1);
+    // bit 31 of .y: the row's upper source row is the previous destination row's lower one (the common case at scale 1.2:
+    // consecutive destination rows advance by one source row), so its interpolation is already in registers -- except for
+    // the first row of a thread's group of 8
+    const ResizeTab tp = ytab[min(max(y0 + tid - 1, 0), D.h - 1)];
+    const int p1 = min(max((int)tp.s + 1, 0), S.h - 1) - syLo;
+    const bool reuse = (tid & 7) != 0 && y0 + tid < D.h && p1 == r0;
+    s_row[tid] = make_uint4((uint32_t)(r0 * kPySrcPitch), (uint32_t)(r1 * kPySrcPitch) | (reuse ? 0x80000000u : 0u), (uint32_t)ty.a0,
+                            (uint32_t)ty.a1);
   }
   // this thread's four columns: coefficient pairs (a0 | a1 << 16) and the byte offsets of their left pixels inside the
   // 8-byte window that starts at the first column's left pixel.  The right neighbour is always the next byte: where
@@ -213,13 +220,18 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
   };
   uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameStride + D.off + (size_t)(y0 + rg * 8) * D.pitch + gx;
   const bool colOk = gx < D.pitch;  // columns beyond the level's width land in the pitch padding (a multiple of 64 >= w)
+  uint32_t ha[4], hb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const int ry = rg * 8 + j;
     const uint4 rw = s_row[ry];  // warp-uniform: one broadcast load
-    uint32_t ha[4], hb[4];
-    hrow(rw.x, ha);
-    hrow(rw.y, hb);
+    if (rw.y & 0x80000000u) {    // warp-uniform branch
+#pragma unroll
+      for (int k = 0; k < 4; k++) ha[k] = hb[k];
+    } else {
+      hrow(rw.x, ha);
+    }
+    hrow(rw.y & 0x7fffffffu, hb);
     uint32_t v[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
