@@ -433,21 +433,575 @@ __global__ void __launch_bounds__(kFcThreads, kOcc) k_fast_cells(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-tier variant (the hot path for levels whose cells are at most 32 px wide and 8 * kNb px high: every level of a
+// 1080p pyramid).  One warp per 8-row band, kNb warps.  Same tile / lane-frame geometry as above; what changes is the
+// ORDER of the work, which now follows the reference's own (ORBextractor.cc:807-829: cv::FAST at iniThFAST, and only for
+// a cell that came back empty again at minThFAST):
+//   * the prefilter produces the flags of BOTH thresholds from the same absolute differences (four more IMAD + LOP3 per
+//     word and row);
+//   * pass 0 scores the iniThFAST candidates only (natural images: ~45 % fewer than at minThFAST), NMS, survivors to the
+//     tile's list, cells with a survivor are marked;
+//   * pass 1 (only if the tile has a cell without survivors; warp-uniform): the minThFAST flags restricted to the
+//     columns of those cells are scored (few: such cells are the texture-poor ones), NMS among them, survivors appended
+//     to the same list.  A cell that was empty at iniThFAST has no survivor with score >= iniThFAST at minThFAST either
+//     (a higher-scored corner is suppressed by the same neighbour in both runs), so the emission below is unchanged;
+//   * overflow (noise images: > kFcListCap survivors): every cell is rescored at minThFAST and the NMS goes to per-row
+//     bitmaps, emitted by the general path (one NMS serves both thresholds there, as in the kernel above).
+// Results are identical to the single-pass kernel's (tests/test_gpu_orb.py::test_fused_fast_cells_equals_the_unfused_pair).
+template <int kNb>
+__global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells2(const __grid_constant__ OrbGeo g,
+                                                                                 const __grid_constant__ TmapIn tm,
+                                                                                 const int4* __restrict__ tileTab, int frame0,
+                                                                                 uint32_t* __restrict__ slots,
+                                                                                 int* __restrict__ cellCnt, int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kT = 32 * kNb, kQ2 = kFc2QueueCap, kQ2Bytes = kFc2QueueCap * 5;
+  constexpr FcSmem lay = fc2_smem_layout(kNb);
+  const uint8_t* sInB = smem;
+  uint8_t* sTile = smem + lay.tile + kSP + 16;  // (row 0, x 0) of the score tile
+  uint32_t* sList = reinterpret_cast<uint32_t*>(smem + lay.misc);  // [kFcListCap] survivors, then [kFcListCap] packed rank counters
+  uint32_t* sRank = sList + kFcListCap;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.misc + kFcListCap * 8);
+  int* sCorner = reinterpret_cast<int*>(smem + lay.misc + kFcListCap * 8 + 16);  // per band: corners in the list, or -1 = use the slow NMS
+  int* sN = sCorner + 8;                                                        // survivors of the tile
+  uint32_t* sCells = reinterpret_cast<uint32_t*>(sCorner + 9);                  // bit c: cell c of the tile has a survivor
+  int* sQn = sCorner + 10;                                                      // [2] candidates in the tile's pooled queue, per pass
+  uint8_t* sCnt = reinterpret_cast<uint8_t*>(sCorner + 12);                     // [kTileQ / 32] corners of each 32-candidate round
+  // pooled queue of the tile (fast path): one-hot flag (later corner entries) + 16-bit position code per candidate
+  constexpr int kTileQ = kFc2QueueCap * kNb;
+  uint32_t* tq = reinterpret_cast<uint32_t*>(smem + lay.queue);
+  uint16_t* tqc = reinterpret_cast<uint16_t*>(tq + kTileQ);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y;
+  const int4 te = __ldg(&tileTab[blockIdx.x]);
+  const int level = te.x, X0 = te.y, Y0 = te.z, ci0 = te.w & 0xffff, cj0 = te.w >> 16;
+  const LevelGeo& L = g.lv[level];
+  const int wCell = L.wCell, hCell = L.hCell;
+  const int kc = min(L.fcKc, L.nCols - cj0);
+  const int X1 = min(X0 + kc * wCell, L.w - kEdge), Y1 = min(Y0 + hCell, L.h - kEdge);
+  int* cnt = cellCnt + (size_t)f * g.totalCells + L.cellBase + ci0 * L.nCols + cj0;
+  if (X1 <= X0 || Y1 <= Y0) {  // cells the reference skips (ORBextractor.cc:796-805) or whose view is too small for FAST
+    if (tid < kc) cnt[tid] = 0;
+    return;
+  }
+  const int xa = (X0 - 3) & ~15;           // first byte of the TMA box (level x), 16-byte aligned, <= X0 - 3
+  const int o = (X0 - xa) & ~7;            // lane frame: staged bytes [o, o + 256) of every row, 8-byte aligned
+  const int xoff = X0 - xa - o;            // tile's first tested pixel inside the lane frame: 0 .. 7
+  const int tw = X1 - X0, th = Y1 - Y0;    // tested pixels of the tile
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, (uint32_t)(kRowB * (kNb * 8 + 6)));
+    tma_load_3d(smem, &tm.in[level], xa >> 2, Y0 - 3, f + frame0, bar);  // the maps index frames from the batch's base
+  }
+  {  // every warp zeroes the score rows of its band (+ the guard row above the first / below the last band)
+    uint4* z = reinterpret_cast<uint4*>(smem + lay.tile + (8 * warp + 1) * kSP);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = lane; i < 8 * kSP / 16; i += 32) z[i] = zero;
+    if (warp == 0 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile)[lane] = zero;
+    if (warp == kNb - 1 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile + (8 * kNb + 1) * kSP)[lane] = zero;
+  }
+  if (tid < kc) cnt[tid] = 0;  // cells without survivors; the others are overwritten by the emission
+  if (tid == 0) { *sN = 0; *sCells = 0u; sQn[0] = 0; sQn[1] = 0; }
+  if (tid < kFcListCap) sRank[tid] = 0u;
+  __syncthreads();  // mbarrier initialised before anyone polls it
+  while (!mbar_try_wait(bar, 0)) {
+  }
+
+  const int b = warp, r0 = 8 * warp;
+  const bool bandOn = r0 < th;  // warp-uniform
+  uint32_t* q = reinterpret_cast<uint32_t*>(smem + lay.queue + b * kQ2Bytes);  // one-hot flag, later corner entries
+  uint8_t* qc = reinterpret_cast<uint8_t*>(q + kQ2);                           // position code, later the band's bitmap
+  uint8_t* band = sTile + r0 * kSP;
+  // column masks in the flag layout: byte k of a half-register holds pixels k (word A, bits 7,5,3,1 for rows 0..3 of
+  // the half) and 4+k (word B, bits 6,4,2,0)
+  auto expand_cols = [](uint32_t m8) {  // bit i of m8 = pixel i of the lane
+    const uint32_t sa = ((m8 & 15u) * 0x00204081u) & 0x01010101u;  // bit 0 of byte k = pixel k
+    const uint32_t sb = ((m8 >> 4) * 0x00204081u) & 0x01010101u;   // bit 0 of byte k = pixel 4+k
+    return sa * 0xAAu + sb * 0x55u;
+  };
+  // ================================================================ prefilter: 64 flags per lane and threshold
+  uint32_t f7lo = 0, f7hi = 0, f20lo = 0, f20hi = 0;
+  if (bandOn) {
+    uint32_t vmLo, vmHi;
+    {
+      const int a = min(max(xoff - 8 * lane, 0), 8), e = min(max(xoff + tw - 8 * lane, 0), 8);
+      const uint32_t xm = expand_cols(e > a ? ((1u << e) - 1u) & ~((1u << a) - 1u) : 0u);
+      uint32_t rl = 0, rh = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (r0 + j < th) rl |= 0xC0C0C0C0u >> (2 * j);
+        if (r0 + 4 + j < th) rh |= 0xC0C0C0C0u >> (2 * j);
+      }
+      vmLo = xm & rl;
+      vmHi = xm & rh;
+    }
+    if (__any_sync(0xffffffffu, (vmLo | vmHi) != 0)) {
+      uint32_t ra[14], rb[14];
+      const uint32_t* col = reinterpret_cast<const uint32_t*>(sInB + r0 * kRowB + o) + 2 * lane;
+#pragma unroll
+      for (int i = 0; i < 14; i++) {
+        const uint2 v = *reinterpret_cast<const uint2*>(col + i * kFcInWords);
+        ra[i] = v.x;
+        rb[i] = v.y;
+      }
+      const uint32_t one = g.one;
+      const uint32_t M7 = g.absMask, M20 = g.absMaskIni;  // 0x80 - (th + 1) in every byte: x + M has its msb set iff x > th (x < 0x80)
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int c = j + 3;
+        const uint32_t* crow = col + c * kFcInWords;
+        const uint32_t wl = crow[-1], wr = crow[2];  // lane 0 / o = 0: the word before the row -- only feeds untested pixels
+        const uint32_t cA = ra[c], cB = rb[c];
+        const uint32_t vA = __vabsdiffu4(ra[j], cA) | __vabsdiffu4(cA, ra[c + 3]);
+        const uint32_t vB = __vabsdiffu4(rb[j], cB) | __vabsdiffu4(cB, rb[c + 3]);
+        const uint32_t hA = __vabsdiffu4(cA, __byte_perm(wl, cA, 0x4321)) | __vabsdiffu4(cA, __byte_perm(cA, cB, 0x6543));
+        const uint32_t hB = __vabsdiffu4(cB, __byte_perm(cA, cB, 0x4321)) | __vabsdiffu4(cB, __byte_perm(cB, wr, 0x6543));
+        // msb of a byte: the (OR of the two) absolute differences exceeds the threshold -- a necessary condition for a
+        // 9-arc, which contains one pixel of every opposite pair.  x + M sets the msb for x in (th, 0x7f]; "| x" covers
+        // x >= 0x80; a carry out of a byte can only turn a neighbour's flag ON (over-accepting is harmless)
+        const uint32_t fA = (mad1(vA, one, M7) | vA) & (mad1(hA, one, M7) | hA);
+        const uint32_t fB = (mad1(vB, one, M7) | vB) & (mad1(hB, one, M7) | hB);
+        const uint32_t gA = (mad1(vA, one, M20) | vA) & (mad1(hA, one, M20) | hA);
+        const uint32_t gB = (mad1(vB, one, M20) | vB) & (mad1(hB, one, M20) | hB);
+        const int s = 2 * (j & 3);
+        const uint32_t b7 = ((fA >> s) & (0x80808080u >> s)) | ((fB >> (s + 1)) & (0x80808080u >> (s + 1)));
+        const uint32_t b20 = ((gA >> s) & (0x80808080u >> s)) | ((gB >> (s + 1)) & (0x80808080u >> (s + 1)));
+        if (j < 4) { f7lo |= b7; f20lo |= b20; } else { f7hi |= b7; f20hi |= b20; }
+      }
+      f7lo &= vmLo; f7hi &= vmHi;
+      f20lo &= f7lo; f20hi &= f7hi;  // (a carry may have switched an iniTh flag on where the minTh flag is off: keep the sets nested)
+    }
+  }
+
+  const int iniTh = g.iniTh;
+  const uint32_t recip = L.fcRecip;  // (x * recip) >> 16 = x / wCell for x < 1024
+  const uint32_t allCells = (1u << kc) - 1u;
+  int pass = 0;
+  uint32_t cellSel = allCells;  // cells whose corners this pass scores
+  bool toBitmap = false;
+  int nSurv = 0;
+  uint32_t myCells = 0u;
+  // One corner against its cell-local 3x3 neighbourhood; survivors go to the tile's list (or, general path after a list
+  // overflow, to the per-row bitmaps in the band queues' code bytes)
+  auto test = [&](int x, int row, int sc) {
+    const int rel = x - xoff;
+    const int c = (int)(((uint32_t)rel * recip) >> 16), c0 = c * wCell;
+    if (!((cellSel >> c) & 1u)) return;  // (slow path of a later pass: scores of the cells already decided)
+    if (nms_keep(sTile + row * kSP + x, sc, rel == c0, rel == c0 + wCell - 1)) {
+      if (toBitmap) {
+        uint32_t* bm = reinterpret_cast<uint32_t*>(smem + lay.queue + (row >> 3) * kQ2Bytes + kQ2 * 4);  // [8 rows][8 words]
+        atomicOr(bm + (row & 7) * 8 + (x >> 5), 1u << (x & 31));
+      } else {
+        const int pos = atomicAdd(sN, 1);
+        if (pos < kFcListCap) sList[pos] = ((uint32_t)c << 24) | ((uint32_t)row << 16) | ((uint32_t)x << 8) | (uint32_t)sc;
+        myCells |= 1u << c;
+      }
+    }
+  };
+  // this lane's pixels inside the selected cells, in the flag layout (a lane's 8 pixels touch at most two cells: wCell >= 30)
+  auto cell_cols = [&]() {
+    const int relFirst = 8 * lane - xoff;
+    const int c0 = (int)(((uint32_t)max(relFirst, 0) * recip) >> 16);
+    const int bnd = min(max((c0 + 1) * wCell - relFirst, 0), 8);
+    const uint32_t lowm = (1u << bnd) - 1u;
+    return expand_cols((((cellSel >> c0) & 1u) ? lowm : 0u) | (((cellSel >> (c0 + 1)) & 1u) ? (0xffu & ~lowm) : 0u));
+  };
+
+  // ================================================================ fast path: the tile's candidates in ONE pooled queue
+  // Every warp appends its band's candidates (one atomicAdd per warp for the base), then the 32-candidate rounds are
+  // dealt round-robin to the warps -- bands with many candidates no longer keep the others waiting at the barrier --
+  // and each round's corners are compacted into the round's own 32 slots.  Leaves for the general per-band loop below
+  // when the pooled queue or the survivor list overflows (noise).
+  bool general = false;
+  for (;;) {
+    uint32_t lo = 0, hi = 0;
+    const int thr = pass == 0 ? iniTh : g.minTh;  // (every warp scores rounds of the pooled queue, also one whose own band is empty)
+    if (bandOn) {
+      if (pass == 0) {
+        lo = f20lo; hi = f20hi;
+      } else {
+        const uint32_t xm = cell_cols();
+        lo = f7lo & xm; hi = f7hi & xm;
+      }
+    }
+    if (__any_sync(0xffffffffu, (lo | hi) != 0)) {
+      {  // 4x4 byte transpose inside lane quads evens out the per-lane counts
+        const uint32_t sel1 = (lane & 1) ? 0x3715u : 0x6240u, sel2 = (lane & 2) ? 0x3276u : 0x5410u;
+        uint32_t x = __shfl_xor_sync(0xffffffffu, lo, 1), y = __shfl_xor_sync(0xffffffffu, hi, 1);
+        lo = __byte_perm(lo, x, sel1);
+        hi = __byte_perm(hi, y, sel1);
+        x = __shfl_xor_sync(0xffffffffu, lo, 2);
+        y = __shfl_xor_sync(0xffffffffu, hi, 2);
+        lo = __byte_perm(lo, x, sel2);
+        hi = __byte_perm(hi, y, sel2);
+      }
+      const int cntL = __popc(lo) + __popc(hi);
+      int incl = cntL;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&sQn[pass], incl);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      if (base + __shfl_sync(0xffffffffu, incl, 31) <= kTileQ) {
+        const uint16_t pcode = (uint16_t)((lane & 28) * 8 + (lane & 3) + (warp << 8));  // x of (source-lane quad, column); bit 2 = half; band
+        uint32_t* qp = tq + base + incl - cntL;
+        uint16_t* qcp = tqc + base + incl - cntL;
+        while (lo) {
+          const uint32_t low = lo & (0u - lo);
+          lo ^= low;
+          *qp++ = low;
+          *qcp++ = pcode;
+        }
+        while (hi) {
+          const uint32_t low = hi & (0u - hi);
+          hi ^= low;
+          *qp++ = low;
+          *qcp++ = (uint16_t)(pcode | 4);
+        }
+      }
+    }
+    __syncthreads();  // the pooled queue is complete
+    const int nQ = sQn[pass];
+    if (nQ > kTileQ) {  // does not fit: this pass (and what follows) per band
+      general = true;
+      break;
+    }
+    for (int rbase = 32 * warp; rbase < nQ; rbase += 32 * kNb) {
+      const int i = rbase + lane;
+      bool corner = false;
+      uint32_t entry = 0;
+      if (i < nQ) {
+        const uint32_t low = tq[i], c = tqc[i];
+        const uint32_t bit = 31u - (uint32_t)__clz(low), u = bit ^ 7u;  // u & 7 = 2 * (row in half) + word
+        const int row = (int)((c >> 8) << 3) + (int)(c & 4u) + (int)((u >> 1) & 3u);
+        const int x = (int)((c & 0xE3u) + (bit & 0x18u) + ((u & 1u) << 2));  // (lane quad)*32 + (source lane)*8 + word*4 + byte
+        const int bam = fast_bam_minmax(sInB + (row + 3) * kRowB + o + x);
+        if (bam > thr) {
+          sTile[row * kSP + x] = (uint8_t)(bam - 1);
+          corner = true;
+          entry = (uint32_t)x | ((uint32_t)row << 8) | ((uint32_t)(bam - 1) << 16);
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, corner);
+      __syncwarp();  // this round's queue reads (all lanes) are ordered before the in-place writes below
+      if (corner) tq[rbase + __popc(bal & ((1u << lane) - 1u))] = entry;
+      if (lane == 0) sCnt[rbase >> 5] = (uint8_t)__popc(bal);
+    }
+    __syncthreads();  // every score of the pass is in shared memory
+    for (int i = tid; i < nQ; i += kT)
+      if ((i & 31) < (int)sCnt[i >> 5]) {
+        const uint32_t e = tq[i];
+        test((int)(e & 0xff), (int)((e >> 8) & 0xff), (int)(e >> 16));
+      }
+    if (pass == 0) {
+      myCells = __reduce_or_sync(0xffffffffu, myCells);
+      if (lane == 0 && myCells) atomicOr(sCells, myCells);
+    }
+    __syncthreads();  // every survivor of the pass is in the list (or the list overflowed)
+    nSurv = *sN;
+    if (nSurv > kFcListCap) {  // noise: rescore every cell at minThFAST, NMS into the bitmaps, general emission
+      toBitmap = true;
+      cellSel = allCells;
+      pass = 1;
+      general = true;
+      break;
+    }
+    if (pass == 0) {
+      const uint32_t empty = allCells & ~*sCells;
+      if (empty) {
+        cellSel = empty;
+        pass = 1;
+        continue;
+      }
+    }
+    break;
+  }
+
+  // ================================================================ general path: per band, queues refilled row by row
+  while (general) {
+    // ================================================================ score this band's candidates of the pass
+    int nCorner = 0;
+    if (bandOn) {
+      uint32_t lo, hi;
+      int thr;
+      if (pass == 0) {
+        lo = f20lo; hi = f20hi; thr = iniTh;
+      } else {
+        const uint32_t xm = cell_cols();
+        lo = f7lo & xm; hi = f7hi & xm; thr = g.minTh;
+      }
+      if (__any_sync(0xffffffffu, (lo | hi) != 0)) {
+        // ---------------- expansion: 4x4 byte transpose inside lane quads evens out the per-lane counts
+        {
+          const uint32_t sel1 = (lane & 1) ? 0x3715u : 0x6240u, sel2 = (lane & 2) ? 0x3276u : 0x5410u;
+          uint32_t x = __shfl_xor_sync(0xffffffffu, lo, 1), y = __shfl_xor_sync(0xffffffffu, hi, 1);
+          lo = __byte_perm(lo, x, sel1);
+          hi = __byte_perm(hi, y, sel1);
+          x = __shfl_xor_sync(0xffffffffu, lo, 2);
+          y = __shfl_xor_sync(0xffffffffu, hi, 2);
+          lo = __byte_perm(lo, x, sel2);
+          hi = __byte_perm(hi, y, sel2);
+        }
+        const int cntL = __popc(lo) + __popc(hi);
+        int incl = cntL;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        // Normally the band's candidates fit the queue in one pass; otherwise (noise images) one pass per row (<= 256) and
+        // the NMS of this band takes the slow path (the corner list cannot live in a queue that is refilled)
+        const int nParts = total <= kQ2 ? 1 : 8;
+        for (int part = 0; part < nParts; part++) {
+          uint32_t mlo = lo, mhi = hi;
+          int pos = incl - cntL, T = total;
+          if (nParts > 1) {
+            const uint32_t rm = 0xC0C0C0C0u >> (2 * (part & 3));
+            mlo = part < 4 ? (lo & rm) : 0u;
+            mhi = part < 4 ? 0u : (hi & rm);
+            const int c2 = __popc(mlo) + __popc(mhi);
+            int in2 = c2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, in2, d);
+              if (lane >= d) in2 += t;
+            }
+            T = __shfl_sync(0xffffffffu, in2, 31);
+            pos = in2 - c2;
+          }
+          const uint8_t pcode = (uint8_t)((lane & 28) * 8 + (lane & 3));  // x of (source-lane quad, column); bit 2 = half
+          uint32_t* qp = q + pos;
+          uint8_t* qcp = qc + pos;
+          while (mlo) {
+            const uint32_t low = mlo & (0u - mlo);
+            mlo ^= low;
+            *qp++ = low;
+            *qcp++ = pcode;
+          }
+          while (mhi) {
+            const uint32_t low = mhi & (0u - mhi);
+            mhi ^= low;
+            *qp++ = low;
+            *qcp++ = (uint8_t)(pcode | 4);
+          }
+          __syncwarp();
+          // ---------------- exact score, one candidate per lane; true corners are compacted in place
+          for (int base = 0; base < T; base += 32) {
+            const int i = base + lane;
+            bool corner = false;
+            uint32_t entry = 0;
+            if (i < T) {
+              const uint32_t low = q[i], c = qc[i];
+              const uint32_t bit = 31u - (uint32_t)__clz(low), u = bit ^ 7u;  // u & 7 = 2 * (row in half) + word
+              const int row = (int)(c & 4u) + (int)((u >> 1) & 3u);
+              const int x = (int)((c & 0xE3u) + (bit & 0x18u) + ((u & 1u) << 2));  // (lane quad)*32 + (source lane)*8 + word*4 + byte
+              const int bam = fast_bam_minmax(sInB + (r0 + row + 3) * kRowB + o + x);
+              if (bam > thr) {
+                band[row * kSP + x] = (uint8_t)(bam - 1);
+                corner = true;
+                entry = (uint32_t)x | ((uint32_t)(r0 + row) << 8) | ((uint32_t)(bam - 1) << 16);
+              }
+            }
+            if (nParts == 1) {
+              const uint32_t bal = __ballot_sync(0xffffffffu, corner);
+              __syncwarp();  // this round's queue reads (all lanes) are ordered before the in-place writes below
+              if (corner) q[nCorner + __popc(bal & ((1u << lane) - 1u))] = entry;
+              nCorner += __popc(bal);
+            }
+          }
+          __syncwarp();
+        }
+        if (nParts > 1) nCorner = -1;
+      }
+    }
+    // the band's survivor bitmap (8 rows x 256 bits) lives in the queue's code bytes, dead from here on
+    __syncwarp();
+    reinterpret_cast<uint2*>(qc)[lane] = make_uint2(0u, 0u);
+    if (lane == 0) sCorner[b] = nCorner;
+    __syncthreads();  // every score of the pass is in shared memory
+
+    // ================================================================ NMS: 3x3 inside the corner's own cell
+    {
+      myCells = 0u;
+      if (nCorner >= 0) {
+        for (int i = lane; i < nCorner; i += 32) {
+          const uint32_t e = q[i];
+          test((int)(e & 0xff), (int)((e >> 8) & 0xff), (int)(e >> 16));
+        }
+      } else {  // the band's queue was refilled per row (> kQ2 candidates): every non-zero score of the band
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+          const uint8_t* rowp = sTile + (r0 + j) * kSP;
+          const uint2 v = *reinterpret_cast<const uint2*>(rowp + 8 * lane);
+          uint32_t nzLo = (((v.x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v.x) & 0x80808080u;
+          uint32_t nzHi = (((v.y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v.y) & 0x80808080u;
+          while (nzLo | nzHi) {
+            const bool inLo = nzLo != 0;
+            uint32_t& m = inLo ? nzLo : nzHi;
+            const int k = (31 - __clz(m & (0u - m))) >> 3;
+            m &= m - 1;
+            const int x = 8 * lane + k + (inLo ? 0 : 4);
+            if (x >= xoff && x < xoff + tw) test(x, r0 + j, (int)rowp[x]);
+          }
+        }
+      }
+      if (pass == 0) {
+        myCells = __reduce_or_sync(0xffffffffu, myCells);
+        if (lane == 0 && myCells) atomicOr(sCells, myCells);
+      }
+    }
+    __syncthreads();  // every survivor of the pass is in the list / the bitmaps (or the list overflowed)
+    if (toBitmap) break;
+    nSurv = *sN;
+    if (nSurv > kFcListCap) {  // noise: rescore every cell at minThFAST, NMS into the bitmaps, general emission
+      toBitmap = true;
+      cellSel = allCells;
+      pass = 1;
+      continue;
+    }
+    if (pass == 0) {
+      const uint32_t empty = allCells & ~*sCells;
+      if (empty) {
+        cellSel = empty;
+        pass = 1;
+        continue;
+      }
+    }
+    break;
+  }
+
+  if (!toBitmap) {
+    // ================================================================ emission from the list
+    // A survivor's slot in its cell = number of survivors of the same cell that precede it in the reference's row-major
+    // order.  (No threshold logic here: a cell's survivors are either all from the iniThFAST pass or all from the
+    // minThFAST pass of a cell that was empty at iniThFAST.)  The n x n comparison is split over the CTA: lane =
+    // survivor i, warp = a share of the partners j; the partial counts meet in shared-memory atomics.
+    const int jq = (nSurv + kNb - 1) / kNb, j0 = warp * jq, j1 = min(j0 + jq, nSurv);
+    for (int base = 0; base < nSurv; base += 32) {
+      const int i = base + lane;
+      const uint32_t ai = (i < nSurv ? sList[i] : 0xffffffffu) >> 8;  // cell | row | x
+      int cntAll = 0, lessAll = 0;
+      for (int j = j0; j < j1; j++) {
+        const uint32_t a = sList[j] >> 8;
+        const bool same = (a ^ ai) < 0x10000u;
+        cntAll += same;
+        lessAll += same && a < ai;
+      }
+      if (i < nSurv && j1 > j0) atomicAdd(&sRank[i], (uint32_t)cntAll | ((uint32_t)lessAll << 16));
+    }
+    __syncthreads();
+    for (int i = tid; i < nSurv; i += kT) {
+      const uint32_t ei = sList[i], rk = sRank[i];
+      const int c = (int)(ei >> 24), row = (int)((ei >> 16) & 0xffu), x = (int)((ei >> 8) & 0xffu), sc = (int)(ei & 0xffu);
+      const int total = rk & 0xffff, pos = rk >> 16;
+      uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)(ci0 * L.nCols + cj0 + c) * L.slotCap;
+      if (pos < L.slotCap)
+        slot[pos] = (uint32_t)(X0 - xoff + x - kMinBorder) | ((uint32_t)(Y0 + row - kMinBorder) << 12) | ((uint32_t)sc << 24);
+      if (pos == 0) {  // the cell's first candidate also reports the cell's count (cells without survivors keep the 0 written at the start)
+        if (total > L.slotCap) atomicOr(err, kErrCandOverflow);
+        cnt[c] = min(total, L.slotCap);
+      }
+    }
+    return;
+  }
+
+  // ================================================================ emission from the bitmaps: warp = cell, lane = tested row
+  for (int c = warp; c < kc; c += kNb) {
+    const int cx0 = xoff + c * wCell, cw = min(wCell, xoff + tw - cx0);  // the cell's columns in the lane frame
+    uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)(ci0 * L.nCols + cj0 + c) * L.slotCap;
+    if (cw <= 0) {
+      if (lane == 0) cnt[c] = 0;
+      continue;
+    }
+    const int wi = cx0 >> 5, sh = cx0 & 31;
+    int basei = 0;
+    // pass 1 decides the threshold (any survivor with score >= iniTh in the whole cell), pass 2 emits; cells are at most
+    // 32 px wide (one 32-bit window per row) and 8 * kNb rows high
+    constexpr int kPasses = (8 * kNb + 31) / 32;
+    uint32_t keep[kPasses], keep20[kPasses];
+    bool any20 = false;
+    const int nPass = (th + 31) >> 5;  // warp-uniform
+#pragma unroll
+    for (int p = 0; p < kPasses; p++) {
+      keep[p] = 0; keep20[p] = 0;
+      if (p >= nPass) continue;
+      const int r = lane + 32 * p;
+      if (r < th) {
+        const uint32_t* rowBm = reinterpret_cast<const uint32_t*>(smem + lay.queue + (r >> 3) * kQ2Bytes + kQ2 * 4) + (r & 7) * 8;
+        const uint32_t w0 = rowBm[wi], w1 = rowBm[min(wi + 1, 7)];
+        uint32_t m = __funnelshift_r(w0, w1, sh);
+        m &= cw >= 32 ? ~0u : ((1u << cw) - 1u);
+        keep[p] = m;
+        uint32_t m20 = 0;
+        const uint8_t* rowp = sTile + r * kSP + cx0;
+        for (uint32_t t = m; t; t &= t - 1) {
+          const int bx = __ffs((int)t) - 1;
+          if (rowp[bx] >= iniTh) m20 |= 1u << bx;
+        }
+        keep20[p] = m20;
+      }
+      any20 = __any_sync(0xffffffffu, keep20[p] != 0) || any20;
+    }
+    const int xbase = X0 - xoff + cx0 - kMinBorder;  // level x of the cell's first column, relative to the 16-px border
+#pragma unroll
+    for (int p = 0; p < kPasses; p++) {
+      if (p >= nPass) continue;
+      const uint32_t sel = any20 ? keep20[p] : keep[p];
+      const int n = __popc(sel);
+      int in2 = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, in2, d);
+        if (lane >= d) in2 += v;
+      }
+      int pos = basei + in2 - n;
+      basei += __shfl_sync(0xffffffffu, in2, 31);
+      const int r = lane + 32 * p;
+      const uint8_t* rowp = sTile + r * kSP + cx0;
+      const uint32_t ybits = (uint32_t)(Y0 + r - kMinBorder) << 12;
+      for (uint32_t t = sel; t; t &= t - 1) {  // lane order = row order, bit order = x order: the reference's row-major order
+        const int bx = __ffs((int)t) - 1;
+        if (pos < L.slotCap) slot[pos] = (uint32_t)(xbase + bx) | ybits | ((uint32_t)rowp[bx] << 24);
+        pos++;
+      }
+    }
+    if (lane == 0) {
+      if (basei > L.slotCap) { atomicOr(err, kErrCandOverflow); basei = L.slotCap; }
+      cnt[c] = basei;
+    }
+  }
+}
+
+
 int configure_fast_cells(int nbGeneric) {
-  static DynSmemLimit limA, limB;
-  if (int rc = limA.ensure(k_fast_cells<true, kFcOccA>, fc_smem_layout(4).total)) return rc;
+  static DynSmemLimit limA, limA5, limB;
+  if (int rc = limA.ensure(k_fast_cells2<4>, fc2_smem_layout(4).total)) return rc;
+  if (int rc = limA5.ensure(k_fast_cells2<5>, fc2_smem_layout(5).total)) return rc;
   if (nbGeneric > 0)
     if (int rc = limB.ensure(k_fast_cells<false, 1>, fc_smem_layout(nbGeneric).total)) return rc;
   return PGB_OK;
 }
 
-int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, int nFrames,
-                      uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0) {
+int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, const int4* tileTabA5,
+                      int nFrames, uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0) {
   if (nFrames <= 0) return PGB_OK;
   if (int rc = configure_fast_cells(g.fcTilesB > 0 ? g.fcNbB : 0)) return rc;
   if (g.fcTilesA > 0) {
     dim3 grid(g.fcTilesA, nFrames);
-    k_fast_cells<true, kFcOccA><<<grid, kFcThreads, fc_smem_layout(4).total, st>>>(g, tm, tileTabA, 4, frame0, slots, cellCnt, err);
+    k_fast_cells2<4><<<grid, 128, fc2_smem_layout(4).total, st>>>(g, tm, tileTabA, frame0, slots, cellCnt, err);
+    PGB_LAUNCHED();
+  }
+  if (g.fcTilesA5 > 0) {
+    dim3 grid(g.fcTilesA5, nFrames);
+    k_fast_cells2<5><<<grid, 160, fc2_smem_layout(5).total, st>>>(g, tm, tileTabA5, frame0, slots, cellCnt, err);
     PGB_LAUNCHED();
   }
   if (g.fcTilesB > 0) {

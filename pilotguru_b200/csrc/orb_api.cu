@@ -77,7 +77,7 @@ struct pgb_orb {
   TmapIn tmapsFc{};     // fused kernel: per level, box height of the level's class
   TmapIn tmapsFcCur{};  // = tmapsFc, with in[0] on the caller's buffer while level 0 is read in place
   TmapIn tmapsPy{}, tmapsPyCur{};  // pyramid kernel: source-footprint boxes (kPySrcPitch x kPySrcRows) of every level
-  DevBuf<int4> fcTabA, fcTabB;  // fused kernel tile tables: level, first tested x, first tested y, cell row | first cell column << 16
+  DevBuf<int4> fcTabA, fcTabB, fcTabA5;  // fused kernel tile tables: level, first tested x, first tested y, cell row | first cell column << 16
   bool unfused = false;  // PGB_UNFUSED=1: the round-1 pair k_fast_score -> k_cells instead of k_fast_cells (A/B, stage debugging)
   bool scoreValid = false;  // the score map of the resident batch has been produced (only the unfused path writes it)
   DevBuf<int> cellTab;  // per FAST cell: level | grid row << 8 | grid column << 20
@@ -106,10 +106,11 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
     // is caught by "| x"); thresholds >= 0x7f degrade to the weaker but still necessary test x >= 0x80
     g->one = 1u;
     g->absMask = (uint32_t)std::max(0, 0x80 - (o->minTh + 1)) * 0x01010101u;
+    g->absMaskIni = (uint32_t)std::max(0, 0x80 - (o->iniTh + 1)) * 0x01010101u;
   }
   unsigned long long off = 0, slotOff = 0, candOff = 0;
   int cellBase = 0, tile2Base = 0, kpBase = 0, maxNode = 1;
-  g->fcTilesA = g->fcTilesB = g->fcNbB = 0;
+  g->fcTilesA = g->fcTilesB = g->fcNbB = g->fcTilesA5 = 0;
   for (int l = 0; l < o->nlevels; l++) {
     LevelGeo& L = g->lv[l];
     L.w = cv_round_f((float)w * o->invScale[l]);
@@ -157,13 +158,14 @@ int build_geo(const pgb_orb* o, int w, int h, OrbGeo* g) {
     // fused FAST + cell NMS kernel: a tile is one row of fcKc whole cells
     L.fcKc = std::max(1, kFcMaxFrame / L.wCell);
     L.fcNb = (L.hCell + 7) / 8;
-    L.fcClassB = (L.wCell > 32 || L.hCell > 32) ? 1 : 0;
+    L.fcClassB = (L.wCell > 32 || L.hCell > 40) ? 1 : (L.hCell > 32 ? 2 : 0);
     L.fcRecip = (65536u + (unsigned)L.wCell - 1u) / (unsigned)L.wCell;
     if (L.wCell > kFcMaxFrame || L.fcNb > 8)
       return fail(PGB_ERR_INVALID, "level %d: FAST cell %dx%d exceeds the kernel's tile", l, L.wCell, L.hCell);
     {
       const int tiles = L.nRows * ((L.nCols + L.fcKc - 1) / L.fcKc);
-      if (L.fcClassB) { g->fcTilesB += tiles; g->fcNbB = std::max(g->fcNbB, L.fcNb); }
+      if (L.fcClassB == 1) { g->fcTilesB += tiles; g->fcNbB = std::max(g->fcNbB, L.fcNb); }
+      else if (L.fcClassB == 2) g->fcTilesA5 += tiles;
       else g->fcTilesA += tiles;
     }
     L.scale = o->scale[l];
@@ -272,7 +274,7 @@ int build_tmaps(pgb_orb* o) {
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(store, level %d) failed: %d", l, (int)r);
     }
-    const cuuint32_t boxFc[3] = {(cuuint32_t)kFcInWords, (cuuint32_t)(8 * (L.fcClassB ? g.fcNbB : 4) + 6), 1};
+    const cuuint32_t boxFc[3] = {(cuuint32_t)kFcInWords, (cuuint32_t)(8 * (L.fcClassB == 1 ? g.fcNbB : L.fcClassB == 2 ? 5 : 4) + 6), 1};
     r = encode(&o->tmapsFc.in[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, o->pyr.p + L.off, dims, strides, boxFc, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -307,7 +309,7 @@ int use_external_level0(pgb_orb* o, const uint8_t* gray, size_t pitch, size_t fr
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PGB_ERR_CUDA, "cuTensorMapEncodeTiled(external level 0) failed: %d", (int)r);
   o->tmapsFcCur = o->tmapsFc;
-  const cuuint32_t boxFc[3] = {(cuuint32_t)kFcInWords, (cuuint32_t)(8 * (L.fcClassB ? o->geo.fcNbB : 4) + 6), 1};
+  const cuuint32_t boxFc[3] = {(cuuint32_t)kFcInWords, (cuuint32_t)(8 * (L.fcClassB == 1 ? o->geo.fcNbB : L.fcClassB == 2 ? 5 : 4) + 6), 1};
   r = encode(&o->tmapsFcCur.in[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(gray), dims, strides, boxFc, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -356,14 +358,17 @@ int set_geometry(pgb_orb* o, int w, int h) {
     PGB_CUDA(cudaStreamSynchronize(o->stream));
     // fused kernel: one tile per (cell row, group of fcKc cell columns); first tested pixel of cell (i, j) is
     // (19 + j * wCell, 19 + i * hCell) (ORBextractor.cc:789-806: iniX + 3, iniY + 3)
-    std::vector<int4> fa, fb;
+    std::vector<int4> fa, fb, fa5;
     for (int l = 0; l < g.nlevels; l++) {
       const LevelGeo& L = g.lv[l];
       for (int i = 0; i < L.nRows; i++)
         for (int j0 = 0; j0 < L.nCols; j0 += L.fcKc)
-          (L.fcClassB ? fb : fa).push_back(make_int4(l, kEdge + j0 * L.wCell, kEdge + i * L.hCell, i | (j0 << 16)));
+          (L.fcClassB == 1 ? fb : L.fcClassB == 2 ? fa5 : fa).push_back(make_int4(l, kEdge + j0 * L.wCell, kEdge + i * L.hCell, i | (j0 << 16)));
     }
-    if ((int)fa.size() != g.fcTilesA || (int)fb.size() != g.fcTilesB) return fail(PGB_ERR_INVALID, "internal: fused tile count");
+    if ((int)fa.size() != g.fcTilesA || (int)fb.size() != g.fcTilesB || (int)fa5.size() != g.fcTilesA5)
+      return fail(PGB_ERR_INVALID, "internal: fused tile count");
+    if (o->fcTabA5.n < fa5.size() + 1 && o->fcTabA5.alloc(fa5.size() + 1)) return PGB_ERR_CUDA;
+    if (!fa5.empty()) PGB_CUDA(cudaMemcpyAsync(o->fcTabA5.p, fa5.data(), fa5.size() * sizeof(int4), cudaMemcpyHostToDevice, o->stream));
     if (o->fcTabA.n < fa.size() + 1 && o->fcTabA.alloc(fa.size() + 1)) return PGB_ERR_CUDA;
     if (o->fcTabB.n < fb.size() + 1 && o->fcTabB.alloc(fb.size() + 1)) return PGB_ERR_CUDA;
     if (!fa.empty()) PGB_CUDA(cudaMemcpyAsync(o->fcTabA.p, fa.data(), fa.size() * sizeof(int4), cudaMemcpyHostToDevice, o->stream));
@@ -438,7 +443,7 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
           rc = launch_fast_score(g, o->tmapsCur, o->tileTab.p, f0, n, st);
           if (f0 == 0 && n == o->curFrames) o->scoreValid = true;
         } else {
-          rc = launch_fast_cells(g, o->tmapsFcCur, o->fcTabA.p, o->fcTabB.p, n, slots, cellCnt, o->err.p, st, f0);
+          rc = launch_fast_cells(g, o->tmapsFcCur, o->fcTabA.p, o->fcTabB.p, o->fcTabA5.p, n, slots, cellCnt, o->err.p, st, f0);
         }
         if (rc) return rc;
         break;

@@ -69,6 +69,18 @@ __host__ __device__ inline FcSmem fc_smem_layout(int nb) {
   s.total = s.misc + 64;  // mbarrier (16 B) + per-band corner counts (8 ints) + the tile's survivor count
   return s;
 }
+// two-tier kernel (k_fast_cells2<nb>, one warp per band): smaller queues (the iniThFAST pass has about half the
+// candidates), the survivor list in its own region (the input stage stays live for the minThFAST pass)
+constexpr int kFc2QueueCap = 256;  // >= 256: a refilled queue holds one row
+__host__ __device__ constexpr FcSmem fc2_smem_layout(int nb) {
+  FcSmem s{};
+  s.tile = (kFcInWords * 4 * (8 * nb + 6) + 127) & ~127;
+  s.queue = s.tile + (8 * nb + 2) * kFcTilePitch;
+  s.misc = s.queue + nb * kFc2QueueCap * 6;  // pooled queue: u32 flag + u16 code per candidate (general path: nb queues of 5 B entries)
+  s.total = s.misc + kFcListCap * 8 + 128;   // survivor list + rank counters, mbarrier (16 B), corner counts (8 ints), survivor count,
+                                             // cell mask, pooled queue counts (2 ints), per-round corner counts (<= 64 B)
+  return s;
+}
 
 struct LevelGeo {
   int w, h, pitch;
@@ -83,7 +95,8 @@ struct LevelGeo {
   unsigned long long candBase;  // in u64 units inside a frame's cand block
   int nodeCap, kpBase;
   int tile2Base, tiles2X, tiles2Y;
-  int fcKc, fcNb, fcClassB;     // fused kernel: cells per tile, bands per tile, 1 = cells larger than 32 px (generic instantiation)
+  int fcKc, fcNb, fcClassB;     // fused kernel: cells per tile, bands per tile; class 0 = two-tier kernel with 4 bands (cells <= 32 x 32),
+                                // 2 = two-tier with 5 bands (<= 32 x 40), 1 = generic single-pass instantiation (anything larger)
   unsigned fcRecip;             // ceil(65536 / wCell): (x * fcRecip) >> 16 == x / wCell for x < 1024
   float scale;
   int patchSize;
@@ -92,9 +105,11 @@ struct LevelGeo {
 struct OrbGeo {
   int nlevels, iniTh, minTh;
   unsigned one;      // = 1, opaque to the compiler (FAST v3 issues its additions as IMAD on the idle FMA pipe)
-  unsigned absMask;  // FAST v3 prefilter: bits k..6 of every byte, 2^k - 1 = largest such value <= minTh
+  unsigned absMask;  // FAST prefilter: 0x80 - (minTh + 1) in every byte
+  unsigned absMaskIni;  // the same for iniTh (two-tier kernel)
   int totalCells, totalTiles2, kpCapInternal, maxNodeCap;
-  int fcTilesA, fcTilesB, fcNbB;  // fused kernel: tiles of class A / class B levels, bands per class-B tile
+  int fcTilesA, fcTilesB, fcNbB;  // fused kernel: tiles of class 0 / class 1 levels, bands per class-1 tile
+  int fcTilesA5;                  // tiles of class 2 levels
   unsigned long long frameStride, slotsPerFrame, candPerFrame;
   // Level 0 in place: when the caller's frames are device-resident and 16-byte aligned, level 0 is read where it lies
   // (ext0 + f * ext0Stride, rows ext0Pitch apart) instead of being copied into the pyramid buffer.
@@ -141,8 +156,8 @@ void launch_pyramid_level(const OrbGeo& g, const TmapIn& tm, int level, int fram
 int configure_fast_score();
 int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st);
-int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, int nFrames,
-                      uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0);
+int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, const int4* tileTabA5,
+                      int nFrames, uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0);
 void launch_cells(const OrbGeo& g, int nFrames, const int* cellTab, const uint8_t* score, uint32_t* slots, int* cellCnt,
                   int* err, cudaStream_t st);
 void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,

@@ -206,21 +206,29 @@ def test_fused_fast_cells_equals_the_unfused_pair(monkeypatch, size):
     (class A tiles: cells <= 32 px; class B: the small levels with larger cells), then identical keypoints / descriptors
     from an extractor that runs the unfused pair end to end (PGB_UNFUSED=1)."""
     w, h, nf = size
-    frames = np.stack([synth.frame(t, w=w, h=h) for t in range(2)] +
-                      [np.random.default_rng(5).integers(0, 256, (h, w), dtype=np.uint8)])     # + a noise frame (slow NMS path)
-    ex = _mk(nf, w, h, batch=3)
+    rng = np.random.default_rng(5)
+    f0 = synth.frame(0, w=w, h=h)
+    low = (f0.astype(np.float32) * 0.3 + 90).astype(np.uint8)                                  # most corners between minTh and iniTh: the second tier
+    mixed = f0.copy()                                                                          # textured | weak noise | strong noise, cell by cell
+    mixed[:, w // 3:2 * w // 3] = 128 + rng.integers(-9, 10, (h, 2 * w // 3 - w // 3))
+    mixed[:, 2 * w // 3:] = rng.integers(0, 256, (h, w - 2 * w // 3), dtype=np.uint8)
+    frames = np.stack([f0, synth.frame(1, w=w, h=h),
+                       rng.integers(0, 256, (h, w), dtype=np.uint8),                           # a noise frame (list overflow: bitmap path)
+                       low, mixed])
+    nfr = len(frames)
+    ex = _mk(nf, w, h, batch=nfr)
     k1, d1, c1 = ex.extract_batch(frames)
-    fused = [[ex.candidates(l, frame=f) for l in range(8)] for f in range(3)]
+    fused = [[ex.candidates(l, frame=f) for l in range(8)] for f in range(nfr)]
     ex.run_stage(2); ex.check()                                                              # recompute the slots with the unfused pair
-    for f in range(3):
+    for f in range(nfr):
         for l in range(8):
             assert np.array_equal(ex.candidates(l, frame=f), fused[f][l]), (f, l)
     assert sum(len(c) for c in fused[0]) > 100
     ex.close()
     monkeypatch.setenv("PGB_UNFUSED", "1")
-    ex2 = _mk(nf, w, h, batch=3)
+    ex2 = _mk(nf, w, h, batch=nfr)
     k2, d2, c2 = ex2.extract_batch(frames)
     ex2.close()
     assert np.array_equal(c1, c2)
-    for f in range(3):
+    for f in range(nfr):
         assert np.array_equal(k1[f, :c1[f]], k2[f, :c1[f]]) and np.array_equal(d1[f, :c1[f]], d2[f, :c1[f]])
