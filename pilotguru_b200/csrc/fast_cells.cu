@@ -467,11 +467,10 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
   int* sN = sCorner + 8;                                                        // survivors of the tile
   uint32_t* sCells = reinterpret_cast<uint32_t*>(sCorner + 9);                  // bit c: cell c of the tile has a survivor
   int* sQn = sCorner + 10;                                                      // [2] candidates in the tile's pooled queue, per pass
-  uint8_t* sCnt = reinterpret_cast<uint8_t*>(sCorner + 12);                     // [kTileQ / 32] corners of each 32-candidate round
-  // pooled queue of the tile (fast path): one-hot flag (later corner entries) + 16-bit position code per candidate
-  constexpr int kTileQ = kFc2QueueCap * kNb;
-  uint32_t* tq = reinterpret_cast<uint32_t*>(smem + lay.queue);
-  uint16_t* tqc = reinterpret_cast<uint16_t*>(tq + kTileQ);
+  uint16_t* sLut = reinterpret_cast<uint16_t*>(sCorner + 12);                   // [32] flag bit -> x | row << 8 inside a transposed flag word
+  // pooled queue of the tile (fast path): one 16-bit entry x | row << 8 per candidate, later per corner
+  constexpr int kTileQ = kFc2QueueCap * kNb * 3;
+  uint16_t* tq = reinterpret_cast<uint16_t*>(smem + lay.queue);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y;
@@ -507,6 +506,10 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
   if (tid < kc) cnt[tid] = 0;  // cells without survivors; the others are overwritten by the emission
   if (tid == 0) { *sN = 0; *sCells = 0u; sQn[0] = 0; sQn[1] = 0; }
   if (tid < kFcListCap) sRank[tid] = 0u;
+  if (tid < 32) {  // bit b of a transposed flag word: byte (b >> 3) = source lane inside the quad, bit 7 - b % 8 = 2 * row + word
+    const uint32_t u = (uint32_t)tid ^ 7u;
+    sLut[tid] = (uint16_t)((tid & 0x18) + ((u & 1u) << 2) + (((u >> 1) & 3u) << 8));
+  }
   __syncthreads();  // mbarrier initialised before anyone polls it
   while (!mbar_try_wait(bar, 0)) {
   }
@@ -650,20 +653,29 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
       if (lane == 31) base = atomicAdd(&sQn[pass], incl);
       base = __shfl_sync(0xffffffffu, base, 31);
       if (base + __shfl_sync(0xffffffffu, incl, 31) <= kTileQ) {
-        const uint16_t pcode = (uint16_t)((lane & 28) * 8 + (lane & 3) + (warp << 8));  // x of (source-lane quad, column); bit 2 = half; band
-        uint32_t* qp = tq + base + incl - cntL;
-        uint16_t* qcp = tqc + base + incl - cntL;
-        while (lo) {
-          const uint32_t low = lo & (0u - lo);
-          lo ^= low;
-          *qp++ = low;
-          *qcp++ = pcode;
+        // x of (source-lane quad, column) | first row of the band << 8; the hi word holds rows 4..7
+        uint32_t b16 = (uint32_t)((lane & 28) * 8 + (lane & 3) + (warp << 11));
+        uint32_t qa = smem_u32(tq + base + incl - cntL);
+        const uint32_t lutA = smem_u32(sLut);
+        asm volatile("" : "+r"(b16), "+r"(qa));  // (keeps the loop-invariant values in registers)
+#pragma unroll 1
+        while (lo) {  // highest flag first (one FLO); the order inside the queue does not matter
+          uint32_t fb, v;
+          asm("bfind.u32 %0, %1;" : "=r"(fb) : "r"(lo));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lutA + 2u * fb));
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "r"(v + b16) : "memory");
+          qa += 2;
+          lo ^= 1u << fb;
         }
+        b16 += 0x400u;
+#pragma unroll 1
         while (hi) {
-          const uint32_t low = hi & (0u - hi);
-          hi ^= low;
-          *qp++ = low;
-          *qcp++ = (uint16_t)(pcode | 4);
+          uint32_t fb, v;
+          asm("bfind.u32 %0, %1;" : "=r"(fb) : "r"(hi));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lutA + 2u * fb));
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "r"(v + b16) : "memory");
+          qa += 2;
+          hi ^= 1u << fb;
         }
       }
     }
@@ -673,33 +685,36 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
       general = true;
       break;
     }
+    // scoring rounds, dealt round-robin; a warp compacts the corners it finds into the slots of its own rounds, in
+    // order (its k-th corner -> slot k % 32 of its (k / 32)-th round: never ahead of the round being read)
+    int nCw = 0;
     for (int rbase = 32 * warp; rbase < nQ; rbase += 32 * kNb) {
       const int i = rbase + lane;
       bool corner = false;
-      uint32_t entry = 0;
+      uint32_t e = 0;
       if (i < nQ) {
-        const uint32_t low = tq[i], c = tqc[i];
-        const uint32_t bit = 31u - (uint32_t)__clz(low), u = bit ^ 7u;  // u & 7 = 2 * (row in half) + word
-        const int row = (int)((c >> 8) << 3) + (int)(c & 4u) + (int)((u >> 1) & 3u);
-        const int x = (int)((c & 0xE3u) + (bit & 0x18u) + ((u & 1u) << 2));  // (lane quad)*32 + (source lane)*8 + word*4 + byte
+        e = tq[i];
+        const int x = (int)(e & 0xffu), row = (int)(e >> 8);
         const int bam = fast_bam_minmax(sInB + (row + 3) * kRowB + o + x);
         if (bam > thr) {
           sTile[row * kSP + x] = (uint8_t)(bam - 1);
           corner = true;
-          entry = (uint32_t)x | ((uint32_t)row << 8) | ((uint32_t)(bam - 1) << 16);
         }
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, corner);
       __syncwarp();  // this round's queue reads (all lanes) are ordered before the in-place writes below
-      if (corner) tq[rbase + __popc(bal & ((1u << lane) - 1u))] = entry;
-      if (lane == 0) sCnt[rbase >> 5] = (uint8_t)__popc(bal);
+      if (corner) {
+        const int k = nCw + __popc(bal & ((1u << lane) - 1u));
+        tq[32 * (warp + kNb * (k >> 5)) + (k & 31)] = (uint16_t)e;
+      }
+      nCw += __popc(bal);
     }
     __syncthreads();  // every score of the pass is in shared memory
-    for (int i = tid; i < nQ; i += kT)
-      if ((i & 31) < (int)sCnt[i >> 5]) {
-        const uint32_t e = tq[i];
-        test((int)(e & 0xff), (int)((e >> 8) & 0xff), (int)(e >> 16));
-      }
+    for (int k = lane; k < nCw; k += 32) {
+      const uint32_t e = tq[32 * (warp + kNb * (k >> 5)) + (k & 31)];
+      const int x = (int)(e & 0xffu), row = (int)(e >> 8);
+      test(x, row, (int)sTile[row * kSP + x]);
+    }
     if (pass == 0) {
       myCells = __reduce_or_sync(0xffffffffu, myCells);
       if (lane == 0 && myCells) atomicOr(sCells, myCells);
