@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
     h[3] = __dp2a_hi(coef[3], cd, 0u) >> 4;
   };
   uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameStride + D.off + (size_t)(y0 + rg * 8) * D.pitch + gx;
+  size_t dpitch = (size_t)D.pitch;
+  asm volatile("" : "+l"(dst), "+l"(dpitch));  // (keeps both in registers: the compiler otherwise rebuilds the address per row)
   const bool colOk = gx < D.pitch;  // columns beyond the level's width land in the pitch padding (a multiple of 64 >= w)
   uint32_t ha[4], hb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -237,16 +239,18 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
     for (int k = 0; k < 4; k++) {
       // (tried: masking the low 4 bits instead of shifting and taking ((h >> 4) * b) >> 16 as mul.hi(h & ~15, b << 12), which
       // moves 8 shifts per row from the ALU pipe to the FMA pipe: IMAD.HI issues at a quarter rate, 4.52 -> 4.90 us/frame)
+      // the rounding constant rides on the second product (2 << 16 does not touch its low 16 bits): one add less per pixel
       uint32_t t0, t1;
       asm("mul.lo.u32 %0, %1, %2;" : "=r"(t0) : "r"(ha[k]), "r"(rw.z));
-      asm("mul.lo.u32 %0, %1, %2;" : "=r"(t1) : "r"(hb[k]), "r"(rw.w));
-      v[k] = ((t0 >> 16) + (t1 >> 16) + 2) >> 2;  // in [0, 255]: a convex combination of bytes
+      asm("mad.lo.u32 %0, %1, %2, 0x20000;" : "=r"(t1) : "r"(hb[k]), "r"(rw.w));
+      v[k] = ((t0 >> 16) + (t1 >> 16)) >> 2;  // in [0, 255]: a convex combination of bytes
     }
     uint32_t out;  // v0 | v1 << 8 | v2 << 16 | v3 << 24 by Horner on the FMA pipe (the ALU pipe carries the shifts)
     asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(out) : "r"(v[3]), "r"(v[2]));
     asm("mad.lo.u32 %0, %0, 256, %1;" : "+r"(out) : "r"(v[1]));
     asm("mad.lo.u32 %0, %0, 256, %1;" : "+r"(out) : "r"(v[0]));
-    if (colOk && y0 + ry < D.h) *reinterpret_cast<uint32_t*>(dst + (size_t)j * D.pitch) = out;
+    if (colOk && y0 + ry < D.h) *reinterpret_cast<uint32_t*>(dst) = out;
+    dst += dpitch;  // a running pointer: two adds per row instead of a 64-bit multiply-add chain
   }
 }
 
@@ -790,6 +794,29 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
   return a;
 }
 
+// (float)cos((double)th), (float)sin((double)th) of computeOrbDescriptor (ORBextractor.cc:113; the reference's `float angle`
+// promotes to the double overloads) for th in [0, 2 pi]: one quadrant reduction (k <= 4, two-piece pi/2: exact first
+// product) and the fdlibm kernel polynomials on [-pi/4, pi/4], ~30 DFMA instead of the 330 instructions of libdevice's
+// full-range cos() + sin().  Max error 1.1e-16 = 1 ulp of double; the FLOAT results equal glibc's on every 7th float
+// angle in [0, 360) (162 M values, checked on the host with the same expression: tools/probe/sincos_check.c).
+__device__ __forceinline__ void sincos_rbrief(double x, float* s, float* c) {
+  const double k = rint(__dmul_rn(x, 0.63661977236758134308));
+  double r = __fma_rn(-k, 1.57079632673412561417e+00, x);
+  r = __fma_rn(-k, 6.07710050650619224932e-11, r);
+  const double z = __dmul_rn(r, r);
+  const double ps = __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08),
+                                                     2.75573137070700676789e-06), -1.98412698298579493134e-04), 8.33333333332248946124e-03);
+  const double sr = __fma_rn(__dmul_rn(z, r), __fma_rn(z, ps, -1.66666666666666324348e-01), r);
+  const double pc = __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09),
+                                                                -2.75573143513906633035e-07), 2.48015872894767294178e-05),
+                                         -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+  const double cr = __dsub_rn(1.0, __fma_rn(0.5, z, -__dmul_rn(__dmul_rn(z, z), pc)));
+  const int q = (int)k & 3;
+  const double sv = (q & 1) ? cr : sr, cv = (q & 1) ? sr : cr;
+  *s = (float)((q & 2) ? -sv : sv);
+  *c = (float)((q == 1 || q == 2) ? -cv : cv);
+}
+
 __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const uint8_t* __restrict__ pyr,
                                                                const StagedKp* __restrict__ staged,
                                                                const int* __restrict__ lvlCnt,
@@ -928,7 +955,8 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
   // rBRIEF: lane = descriptor byte
   const float factorPI = (float)(3.14159265358979323846 / 180.0);
   const float th = __fmul_rn(angle, factorPI);
-  const float a = (float)cos((double)th), b = (float)sin((double)th);
+  float a, b;
+  sincos_rbrief((double)th, &b, &a);
   const uint8_t* C = Bl + kBR * kBW + kBR;
   int val = 0;
 #pragma unroll
