@@ -46,10 +46,11 @@ __device__ __forceinline__ int fast_bam_minmax(const uint8_t* c) { return fastk:
 
 // One corner against its 8 neighbours in the shared score tile; p points at the corner's byte.  Rows above / below the
 // tile are zero guard rows; `first` / `last`: the corner sits in the first / last column of its cell.
+template <int kPitch = kSP>
 __device__ __forceinline__ bool nms_keep(const uint8_t* p, int s, bool first, bool last) {
-  const int nw = p[-kSP - 1], n = p[-kSP], ne = p[-kSP + 1];
+  const int nw = p[-kPitch - 1], n = p[-kPitch], ne = p[-kPitch + 1];
   const int w = p[-1], e = p[1];
-  const int sw = p[kSP - 1], so = p[kSP], se = p[kSP + 1];
+  const int sw = p[kPitch - 1], so = p[kPitch], se = p[kPitch + 1];
   int left = max(max(nw, w), sw), right = max(max(ne, e), se);
   if (first) left = 0;
   if (last) right = 0;
@@ -457,19 +458,19 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
                                                                                  int* __restrict__ cellCnt, int* __restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kT = 32 * kNb, kQ2 = kFc2QueueCap, kQ2Bytes = kFc2QueueCap * 5;
+  constexpr int kSP = kFc2TilePitch;  // (shadows the single-pass kernel's pitch)
   constexpr FcSmem lay = fc2_smem_layout(kNb);
   const uint8_t* sInB = smem;
-  uint8_t* sTile = smem + lay.tile + kSP + 16;  // (row 0, x 0) of the score tile
-  uint32_t* sList = reinterpret_cast<uint32_t*>(smem + lay.misc);  // [kFcListCap] survivors, then [kFcListCap] packed rank counters
-  uint32_t* sRank = sList + kFcListCap;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.misc + kFcListCap * 8);
-  int* sCorner = reinterpret_cast<int*>(smem + lay.misc + kFcListCap * 8 + 16);  // per band: corners in the list, or -1 = use the slow NMS
+  uint8_t* sTile = smem + lay.tile + kSP + 8;  // (row 0, x 0) of the score tile: 8 pad bytes in front of every row
+  uint32_t* sList = reinterpret_cast<uint32_t*>(smem + lay.misc);  // [kFcListCap] survivors
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.misc + kFcListCap * 4);
+  int* sCorner = reinterpret_cast<int*>(smem + lay.misc + kFcListCap * 4 + 16);  // per band: corners in the list, or -1 = use the slow NMS
   int* sN = sCorner + 8;                                                        // survivors of the tile
   uint32_t* sCells = reinterpret_cast<uint32_t*>(sCorner + 9);                  // bit c: cell c of the tile has a survivor
   int* sQn = sCorner + 10;                                                      // [2] candidates in the tile's pooled queue, per pass
   uint16_t* sLut = reinterpret_cast<uint16_t*>(sCorner + 12);                   // [32] flag bit -> x | row << 8 inside a transposed flag word
   // pooled queue of the tile (fast path): one 16-bit entry x | row << 8 per candidate, later per corner
-  constexpr int kTileQ = kFc2QueueCap * kNb * 3;
+  constexpr int kTileQ = kFc2QueueCap * kNb * 5 / 2;
   uint16_t* tq = reinterpret_cast<uint16_t*>(smem + lay.queue);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -496,16 +497,13 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
     mbar_expect_tx(bar, (uint32_t)(kRowB * (kNb * 8 + 6)));
     tma_load_3d(smem, &tm.in[level], xa >> 2, Y0 - 3, f + frame0, bar);  // the maps index frames from the batch's base
   }
-  {  // every warp zeroes the score rows of its band (+ the guard row above the first / below the last band)
-    uint4* z = reinterpret_cast<uint4*>(smem + lay.tile + (8 * warp + 1) * kSP);
+  {  // zero the score tile (guard rows included)
+    uint4* z = reinterpret_cast<uint4*>(smem + lay.tile);
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = lane; i < 8 * kSP / 16; i += 32) z[i] = zero;
-    if (warp == 0 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile)[lane] = zero;
-    if (warp == kNb - 1 && lane < kSP / 16) reinterpret_cast<uint4*>(smem + lay.tile + (8 * kNb + 1) * kSP)[lane] = zero;
+    for (int i = tid; i < (8 * kNb + 2) * kSP / 16; i += kT) z[i] = zero;
   }
   if (tid < kc) cnt[tid] = 0;  // cells without survivors; the others are overwritten by the emission
   if (tid == 0) { *sN = 0; *sCells = 0u; sQn[0] = 0; sQn[1] = 0; }
-  if (tid < kFcListCap) sRank[tid] = 0u;
   if (tid < 32) {  // bit b of a transposed flag word: byte (b >> 3) = source lane inside the quad, bit 7 - b % 8 = 2 * row + word
     const uint32_t u = (uint32_t)tid ^ 7u;
     sLut[tid] = (uint16_t)((tid & 0x18) + ((u & 1u) << 2) + (((u >> 1) & 3u) << 8));
@@ -594,7 +592,7 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
     const int rel = x - xoff;
     const int c = (int)(((uint32_t)rel * recip) >> 16), c0 = c * wCell;
     if (!((cellSel >> c) & 1u)) return;  // (slow path of a later pass: scores of the cells already decided)
-    if (nms_keep(sTile + row * kSP + x, sc, rel == c0, rel == c0 + wCell - 1)) {
+    if (nms_keep<kSP>(sTile + row * kSP + x, sc, rel == c0, rel == c0 + wCell - 1)) {
       if (toBitmap) {
         uint32_t* bm = reinterpret_cast<uint32_t*>(smem + lay.queue + (row >> 3) * kQ2Bytes + kQ2 * 4);  // [8 rows][8 words]
         atomicOr(bm + (row & 7) * 8 + (x >> 5), 1u << (x & 31));
@@ -897,26 +895,19 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
     // ================================================================ emission from the list
     // A survivor's slot in its cell = number of survivors of the same cell that precede it in the reference's row-major
     // order.  (No threshold logic here: a cell's survivors are either all from the iniThFAST pass or all from the
-    // minThFAST pass of a cell that was empty at iniThFAST.)  The n x n comparison is split over the CTA: lane =
-    // survivor i, warp = a share of the partners j; the partial counts meet in shared-memory atomics.
-    const int jq = (nSurv + kNb - 1) / kNb, j0 = warp * jq, j1 = min(j0 + jq, nSurv);
-    for (int base = 0; base < nSurv; base += 32) {
-      const int i = base + lane;
-      const uint32_t ai = (i < nSurv ? sList[i] : 0xffffffffu) >> 8;  // cell | row | x
-      int cntAll = 0, lessAll = 0;
-      for (int j = j0; j < j1; j++) {
+    // minThFAST pass of a cell that was empty at iniThFAST.)  One thread per survivor (the list holds <= kFcListCap <= the
+    // CTA's threads), the partners are shared-memory broadcasts.
+    static_assert(kFcListCap <= kT, "one thread per list entry");
+    if (tid < nSurv) {
+      const uint32_t ei = sList[tid], ai = ei >> 8;  // cell | row | x
+      int total = 0, pos = 0;
+      for (int j = 0; j < nSurv; j++) {
         const uint32_t a = sList[j] >> 8;
         const bool same = (a ^ ai) < 0x10000u;
-        cntAll += same;
-        lessAll += same && a < ai;
+        total += same;
+        pos += same && a < ai;
       }
-      if (i < nSurv && j1 > j0) atomicAdd(&sRank[i], (uint32_t)cntAll | ((uint32_t)lessAll << 16));
-    }
-    __syncthreads();
-    for (int i = tid; i < nSurv; i += kT) {
-      const uint32_t ei = sList[i], rk = sRank[i];
       const int c = (int)(ei >> 24), row = (int)((ei >> 16) & 0xffu), x = (int)((ei >> 8) & 0xffu), sc = (int)(ei & 0xffu);
-      const int total = rk & 0xffff, pos = rk >> 16;
       uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase + (size_t)(ci0 * L.nCols + cj0 + c) * L.slotCap;
       if (pos < L.slotCap)
         slot[pos] = (uint32_t)(X0 - xoff + x - kMinBorder) | ((uint32_t)(Y0 + row - kMinBorder) << 12) | ((uint32_t)sc << 24);

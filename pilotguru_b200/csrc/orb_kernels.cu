@@ -755,6 +755,9 @@ void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const in
 // inner 39x39 patch with the fixed-point 7x7 kernel and samples the 256 rotated test pairs from it.  The blurred
 // level image of the reference is never materialised: its value at a pixel depends only on the 7x7 neighbourhood.
 constexpr int kOdWarps = 4;
+#ifndef PGB_OD_OCC
+#define PGB_OD_OCC 8
+#endif
 constexpr int kPR = 22;            // patch radius: 19 (pattern reach) + 3 (blur)
 constexpr int kPW = 2 * kPR + 1;   // 45
 constexpr int kPP = 52;            // shared-memory row pitch of the patch: 13 aligned words cover 45 px at any phase (odd word
@@ -817,7 +820,7 @@ __device__ __forceinline__ void sincos_rbrief(double x, float* s, float* c) {
   *c = (float)((q == 1 || q == 2) ? -cv : cv);
 }
 
-__global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const uint8_t* __restrict__ pyr,
+__global__ void __launch_bounds__(kOdWarps * 32, PGB_OD_OCC) k_orient_desc(OrbGeo g, const uint8_t* __restrict__ pyr,
                                                                const StagedKp* __restrict__ staged,
                                                                const int* __restrict__ lvlCnt,
                                                                pgb_keypoint* __restrict__ kps,
@@ -825,7 +828,6 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
                                                                int cap, int* __restrict__ err) {
   __shared__ __align__(4) uint8_t s_patch[kOdWarps][kPW * kPP];
   __shared__ __align__(4) uint16_t s_h[kOdWarps][kPW * kHP];
-  __shared__ uint8_t s_blur[kOdWarps][kBW * kBW + 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kOdWarps + warp;
   const int f = blockIdx.y;
@@ -936,7 +938,7 @@ __global__ void __launch_bounds__(kOdWarps * 32) k_orient_desc(OrbGeo g, const u
       hrow[c >> 1] = 18u * (pr[c] + pr[c + 6]) + 34u * (pr[c + 1] + pr[c + 5]) + 48u * (pr[c + 2] + pr[c + 4]) + 56u * pr[c + 3];
   }
   __syncwarp();
-  uint8_t* Bl = s_blur[warp];
+  uint8_t* Bl = Pw;  // the blurred 39 x 39 patch takes the place of the staged pixels (dead after the horizontal pass): 9 CTAs per SM
 #pragma unroll 1
   for (int id = lane; id < 3 * kBW; id += 32) {
     const int t = id / kBW, c = id - t * kBW;

@@ -71,14 +71,19 @@ __host__ __device__ inline FcSmem fc_smem_layout(int nb) {
 }
 // two-tier kernel (k_fast_cells2<nb>, one warp per band): smaller queues (the iniThFAST pass has about half the
 // candidates), the survivor list in its own region (the input stage stays live for the minThFAST pass)
-constexpr int kFc2QueueCap = 256;  // >= 256: a refilled queue holds one row
+#ifndef PGB_FC2_QCAP
+#define PGB_FC2_QCAP 256
+#endif
+constexpr int kFc2QueueCap = PGB_FC2_QCAP;  // per band, general path (>= 256: a refilled queue holds one row); the pooled queue of the
+                                   // fast path holds kFc2QueueCap * nb * 2 16-bit entries in the same bytes
+constexpr int kFc2TilePitch = 264;  // score tile row: 8 pad bytes + 256 px
 __host__ __device__ constexpr FcSmem fc2_smem_layout(int nb) {
   FcSmem s{};
-  s.tile = (kFcInWords * 4 * (8 * nb + 6) + 127) & ~127;
-  s.queue = s.tile + (8 * nb + 2) * kFcTilePitch;
-  s.misc = s.queue + nb * kFc2QueueCap * 6;  // pooled queue: u32 flag + u16 code per candidate (general path: nb queues of 5 B entries)
-  s.total = s.misc + kFcListCap * 8 + 128;   // survivor list + rank counters, mbarrier (16 B), corner counts (8 ints), survivor count,
-                                             // cell mask, pooled queue counts (2 ints), per-round corner counts (<= 64 B)
+  s.tile = kFcInWords * 4 * (8 * nb + 6);  // (a multiple of 16)
+  s.queue = s.tile + (8 * nb + 2) * kFc2TilePitch;
+  s.misc = s.queue + nb * kFc2QueueCap * 5;
+  s.total = s.misc + kFcListCap * 4 + 128;   // survivor list, mbarrier (16 B), corner counts (8 ints), survivor count, cell mask,
+                                             // pooled queue counts (2 ints), bit -> (x, row) table (64 B)
   return s;
 }
 
