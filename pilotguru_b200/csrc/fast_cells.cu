@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
                                                                                  uint32_t* __restrict__ slots,
                                                                                  int* __restrict__ cellCnt, int* __restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int kT = 32 * kNb, kQ2 = kFc2QueueCap, kQ2Bytes = kFc2QueueCap * 5;
+  constexpr int kT = 32 * kNb, kQ2 = kFc2QueueCap, kQ2Bytes = kFc2QueueCap * 3;
   constexpr int kSP = kFc2TilePitch;  // (shadows the single-pass kernel's pitch)
   constexpr FcSmem lay = fc2_smem_layout(kNb);
   const uint8_t* sInB = smem;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
   int* sQn = sCorner + 10;                                                      // [2] candidates in the tile's pooled queue, per pass
   uint16_t* sLut = reinterpret_cast<uint16_t*>(sCorner + 12);                   // [32] flag bit -> x | row << 8 inside a transposed flag word
   // pooled queue of the tile (fast path): one 16-bit entry x | row << 8 per candidate, later per corner
-  constexpr int kTileQ = kFc2QueueCap * kNb * 5 / 2;
+  constexpr int kTileQ = kFc2QueueCap * kNb * 3 / 2;
   uint16_t* tq = reinterpret_cast<uint16_t*>(smem + lay.queue);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -514,9 +514,8 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
 
   const int b = warp, r0 = 8 * warp;
   const bool bandOn = r0 < th;  // warp-uniform
-  uint32_t* q = reinterpret_cast<uint32_t*>(smem + lay.queue + b * kQ2Bytes);  // one-hot flag, later corner entries
-  uint8_t* qc = reinterpret_cast<uint8_t*>(q + kQ2);                           // position code, later the band's bitmap
-  uint8_t* band = sTile + r0 * kSP;
+  uint16_t* q = reinterpret_cast<uint16_t*>(smem + lay.queue + b * kQ2Bytes);  // general path: this band's queue (candidates, later
+                                                                               // corners), followed by its survivor bitmap
   // column masks in the flag layout: byte k of a half-register holds pixels k (word A, bits 7,5,3,1 for rows 0..3 of
   // the half) and 4+k (word B, bits 6,4,2,0)
   auto expand_cols = [](uint32_t m8) {  // bit i of m8 = pixel i of the lane
@@ -594,7 +593,7 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
     if (!((cellSel >> c) & 1u)) return;  // (slow path of a later pass: scores of the cells already decided)
     if (nms_keep<kSP>(sTile + row * kSP + x, sc, rel == c0, rel == c0 + wCell - 1)) {
       if (toBitmap) {
-        uint32_t* bm = reinterpret_cast<uint32_t*>(smem + lay.queue + (row >> 3) * kQ2Bytes + kQ2 * 4);  // [8 rows][8 words]
+        uint32_t* bm = reinterpret_cast<uint32_t*>(smem + lay.queue + (row >> 3) * kQ2Bytes + kQ2 * 2);  // [8 rows][8 words]
         atomicOr(bm + (row & 7) * 8 + (x >> 5), 1u << (x & 31));
       } else {
         const int pos = atomicAdd(sN, 1);
@@ -790,43 +789,39 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
             T = __shfl_sync(0xffffffffu, in2, 31);
             pos = in2 - c2;
           }
-          const uint8_t pcode = (uint8_t)((lane & 28) * 8 + (lane & 3));  // x of (source-lane quad, column); bit 2 = half
-          uint32_t* qp = q + pos;
-          uint8_t* qcp = qc + pos;
+          // 16-bit entries x | row << 8 through the bit -> (x, row) table, as in the pooled queue
+          uint32_t b16 = (uint32_t)((lane & 28) * 8 + (lane & 3) + (warp << 11));
+          uint16_t* qp = q + pos;
           while (mlo) {
-            const uint32_t low = mlo & (0u - mlo);
-            mlo ^= low;
-            *qp++ = low;
-            *qcp++ = pcode;
+            const uint32_t fb = 31u - (uint32_t)__clz(mlo);
+            mlo ^= 1u << fb;
+            *qp++ = (uint16_t)(b16 + sLut[fb]);
           }
+          b16 += 0x400u;
           while (mhi) {
-            const uint32_t low = mhi & (0u - mhi);
-            mhi ^= low;
-            *qp++ = low;
-            *qcp++ = (uint8_t)(pcode | 4);
+            const uint32_t fb = 31u - (uint32_t)__clz(mhi);
+            mhi ^= 1u << fb;
+            *qp++ = (uint16_t)(b16 + sLut[fb]);
           }
           __syncwarp();
           // ---------------- exact score, one candidate per lane; true corners are compacted in place
           for (int base = 0; base < T; base += 32) {
             const int i = base + lane;
             bool corner = false;
-            uint32_t entry = 0;
+            uint32_t e = 0;
             if (i < T) {
-              const uint32_t low = q[i], c = qc[i];
-              const uint32_t bit = 31u - (uint32_t)__clz(low), u = bit ^ 7u;  // u & 7 = 2 * (row in half) + word
-              const int row = (int)(c & 4u) + (int)((u >> 1) & 3u);
-              const int x = (int)((c & 0xE3u) + (bit & 0x18u) + ((u & 1u) << 2));  // (lane quad)*32 + (source lane)*8 + word*4 + byte
-              const int bam = fast_bam_minmax(sInB + (r0 + row + 3) * kRowB + o + x);
+              e = q[i];
+              const int x = (int)(e & 0xffu), row = (int)(e >> 8);
+              const int bam = fast_bam_minmax(sInB + (row + 3) * kRowB + o + x);
               if (bam > thr) {
-                band[row * kSP + x] = (uint8_t)(bam - 1);
+                sTile[row * kSP + x] = (uint8_t)(bam - 1);
                 corner = true;
-                entry = (uint32_t)x | ((uint32_t)(r0 + row) << 8) | ((uint32_t)(bam - 1) << 16);
               }
             }
             if (nParts == 1) {
               const uint32_t bal = __ballot_sync(0xffffffffu, corner);
               __syncwarp();  // this round's queue reads (all lanes) are ordered before the in-place writes below
-              if (corner) q[nCorner + __popc(bal & ((1u << lane) - 1u))] = entry;
+              if (corner) q[nCorner + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
               nCorner += __popc(bal);
             }
           }
@@ -835,9 +830,9 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
         if (nParts > 1) nCorner = -1;
       }
     }
-    // the band's survivor bitmap (8 rows x 256 bits) lives in the queue's code bytes, dead from here on
+    // the band's survivor bitmap (8 rows x 256 bits) follows its queue
     __syncwarp();
-    reinterpret_cast<uint2*>(qc)[lane] = make_uint2(0u, 0u);
+    reinterpret_cast<uint2*>(q + kQ2)[lane] = make_uint2(0u, 0u);
     if (lane == 0) sCorner[b] = nCorner;
     __syncthreads();  // every score of the pass is in shared memory
 
@@ -847,7 +842,8 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
       if (nCorner >= 0) {
         for (int i = lane; i < nCorner; i += 32) {
           const uint32_t e = q[i];
-          test((int)(e & 0xff), (int)((e >> 8) & 0xff), (int)(e >> 16));
+          const int x = (int)(e & 0xffu), row = (int)(e >> 8);
+          test(x, row, (int)sTile[row * kSP + x]);
         }
       } else {  // the band's queue was refilled per row (> kQ2 candidates): every non-zero score of the band
 #pragma unroll 1
@@ -941,7 +937,7 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
       if (p >= nPass) continue;
       const int r = lane + 32 * p;
       if (r < th) {
-        const uint32_t* rowBm = reinterpret_cast<const uint32_t*>(smem + lay.queue + (r >> 3) * kQ2Bytes + kQ2 * 4) + (r & 7) * 8;
+        const uint32_t* rowBm = reinterpret_cast<const uint32_t*>(smem + lay.queue + (r >> 3) * kQ2Bytes + kQ2 * 2) + (r & 7) * 8;
         const uint32_t w0 = rowBm[wi], w1 = rowBm[min(wi + 1, 7)];
         uint32_t m = __funnelshift_r(w0, w1, sh);
         m &= cw >= 32 ? ~0u : ((1u << cw) - 1u);

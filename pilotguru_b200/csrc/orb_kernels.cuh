@@ -55,7 +55,7 @@ constexpr int kFcQueueBytes = kFcQueueCap * 5;
 constexpr int kFcListCap = 128;     // NMS survivors per tile kept in the list (natural images: ~20); more -> bitmap emission
 constexpr int kFcMaxFrame = 249;     // widest tested tile inside the 256-px lane frame (first pixel at offset 0..7)
 #ifndef PGB_FC_OCC
-#define PGB_FC_OCC 8
+#define PGB_FC_OCC 9
 #endif
 constexpr int kFcOccA = PGB_FC_OCC;  // resident CTAs per SM the class-A instantiation is compiled for
 struct FcSmem {
@@ -75,13 +75,13 @@ __host__ __device__ inline FcSmem fc_smem_layout(int nb) {
 #define PGB_FC2_QCAP 256
 #endif
 constexpr int kFc2QueueCap = PGB_FC2_QCAP;  // per band, general path (>= 256: a refilled queue holds one row); the pooled queue of the
-                                   // fast path holds kFc2QueueCap * nb * 2 16-bit entries in the same bytes
+                                   // fast path holds kFc2QueueCap * nb * 3 / 2 16-bit entries in the same bytes
 constexpr int kFc2TilePitch = 264;  // score tile row: 8 pad bytes + 256 px
 __host__ __device__ constexpr FcSmem fc2_smem_layout(int nb) {
   FcSmem s{};
   s.tile = kFcInWords * 4 * (8 * nb + 6);  // (a multiple of 16)
   s.queue = s.tile + (8 * nb + 2) * kFc2TilePitch;
-  s.misc = s.queue + nb * kFc2QueueCap * 5;
+  s.misc = s.queue + nb * kFc2QueueCap * 3;  // general path, per band: 16-bit queue entries + the 256-byte survivor bitmap
   s.total = s.misc + kFcListCap * 4 + 128;   // survivor list, mbarrier (16 B), corner counts (8 ints), survivor count, cell mask,
                                              // pooled queue counts (2 ints), bit -> (x, row) table (64 B)
   return s;
