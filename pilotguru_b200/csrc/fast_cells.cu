@@ -993,24 +993,35 @@ int configure_fast_cells(int nbGeneric) {
 }
 
 int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, const int4* tileTabA5,
-                      int nFrames, uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0) {
+                      int nFrames, uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0, cudaStream_t side,
+                      cudaEvent_t evFork, cudaEvent_t evJoin) {
   if (nFrames <= 0) return PGB_OK;
   if (int rc = configure_fast_cells(g.fcTilesB > 0 ? g.fcNbB : 0)) return rc;
+  // The 4-band launch holds ~97 % of a 1080p pyramid's tiles; the small ones (level 7's 34-px cell rows, levels with
+  // cells wider than 32 px) go to a side stream so that their partial waves fill in next to it instead of running alone.
+  const bool fork = side && g.fcTilesA > 0 && (g.fcTilesA5 > 0 || g.fcTilesB > 0);
+  cudaStream_t s2 = fork ? side : st;
+  if (fork) {
+    PGB_CUDA(cudaEventRecord(evFork, st));
+    PGB_CUDA(cudaStreamWaitEvent(side, evFork, 0));
+  }
+  if (g.fcTilesA5 > 0) {
+    dim3 grid(g.fcTilesA5, nFrames);
+    k_fast_cells2<5><<<grid, 160, fc2_smem_layout(5).total, s2>>>(g, tm, tileTabA5, frame0, slots, cellCnt, err);
+    PGB_LAUNCHED();
+  }
+  if (g.fcTilesB > 0) {
+    dim3 grid(g.fcTilesB, nFrames);
+    k_fast_cells<false, 1><<<grid, kFcThreads, fc_smem_layout(g.fcNbB).total, s2>>>(g, tm, tileTabB, g.fcNbB, frame0, slots, cellCnt, err);
+    PGB_LAUNCHED();
+  }
+  if (fork) PGB_CUDA(cudaEventRecord(evJoin, side));
   if (g.fcTilesA > 0) {
     dim3 grid(g.fcTilesA, nFrames);
     k_fast_cells2<4><<<grid, 128, fc2_smem_layout(4).total, st>>>(g, tm, tileTabA, frame0, slots, cellCnt, err);
     PGB_LAUNCHED();
   }
-  if (g.fcTilesA5 > 0) {
-    dim3 grid(g.fcTilesA5, nFrames);
-    k_fast_cells2<5><<<grid, 160, fc2_smem_layout(5).total, st>>>(g, tm, tileTabA5, frame0, slots, cellCnt, err);
-    PGB_LAUNCHED();
-  }
-  if (g.fcTilesB > 0) {
-    dim3 grid(g.fcTilesB, nFrames);
-    k_fast_cells<false, 1><<<grid, kFcThreads, fc_smem_layout(g.fcNbB).total, st>>>(g, tm, tileTabB, g.fcNbB, frame0, slots, cellCnt, err);
-    PGB_LAUNCHED();
-  }
+  if (fork) PGB_CUDA(cudaStreamWaitEvent(st, evJoin, 0));
   return PGB_OK;
 }
 

@@ -85,6 +85,9 @@ struct pgb_orb {
   cudaStream_t auxStream[2] = {nullptr, nullptr};
   cudaEvent_t evAux[2] = {nullptr, nullptr};
   cudaEvent_t evDone = nullptr;
+  // fused FAST kernel: the small launches (5-band and generic tiles) run on a side stream next to the main one
+  cudaStream_t fcSide = nullptr;
+  cudaEvent_t evFcFork = nullptr, evFcJoin = nullptr;
   cudaEvent_t evChunk[16] = {};
   int h2dChunk = 16;  // largest H2D/compute pipeline chunk in frames (PGB_H2D_CHUNK)
   int h2dMinChunk = 4;  // smallest chunk of the ramp-down at the end of a batch (PGB_H2D_MIN_CHUNK)
@@ -443,7 +446,8 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
           rc = launch_fast_score(g, o->tmapsCur, o->tileTab.p, f0, n, st);
           if (f0 == 0 && n == o->curFrames) o->scoreValid = true;
         } else {
-          rc = launch_fast_cells(g, o->tmapsFcCur, o->fcTabA.p, o->fcTabB.p, o->fcTabA5.p, n, slots, cellCnt, o->err.p, st, f0);
+          rc = launch_fast_cells(g, o->tmapsFcCur, o->fcTabA.p, o->fcTabB.p, o->fcTabA5.p, n, slots, cellCnt, o->err.p, st, f0, o->fcSide,
+                                 o->evFcFork, o->evFcJoin);
         }
         if (rc) return rc;
         break;
@@ -615,6 +619,11 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
     if (cudaStreamCreateWithFlags(&o->auxStream[a], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&o->evAux[a], cudaEventDisableTiming) != cudaSuccess)
       return bail("cudaStreamCreate/cudaEventCreate failed");
+  if (!getenv("PGB_FC_NO_SIDE") &&
+      (cudaStreamCreateWithFlags(&o->fcSide, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaEventCreateWithFlags(&o->evFcFork, cudaEventDisableTiming) != cudaSuccess ||
+       cudaEventCreateWithFlags(&o->evFcJoin, cudaEventDisableTiming) != cudaSuccess))
+    return bail("cudaStreamCreate/cudaEventCreate failed");
   if (const char* e = getenv("PGB_H2D_CHUNK")) o->h2dChunk = std::max(1, atoi(e));
   if (const char* e = getenv("PGB_H2D_MIN_CHUNK")) o->h2dMinChunk = std::max(1, atoi(e));
   if (const char* e = getenv("PGB_RES_CHUNK")) o->resChunk = std::max(0, atoi(e));
@@ -648,6 +657,11 @@ void pgb_orb_destroy(pgb_orb* o) {
   for (int a = 0; a < 2; a++) {
     if (o->auxStream[a]) { cudaStreamSynchronize(o->auxStream[a]); cudaStreamDestroy(o->auxStream[a]); }
     if (o->evAux[a]) cudaEventDestroy(o->evAux[a]);
+    if (a == 0) {
+      if (o->fcSide) { cudaStreamSynchronize(o->fcSide); cudaStreamDestroy(o->fcSide); }
+      if (o->evFcFork) cudaEventDestroy(o->evFcFork);
+      if (o->evFcJoin) cudaEventDestroy(o->evFcJoin);
+    }
   }
   for (int k = 0; k < kMaxChunkEvents; k++)
     if (o->evChunk[k]) cudaEventDestroy(o->evChunk[k]);

@@ -162,7 +162,8 @@ int configure_fast_score();
 int launch_fast_score(const OrbGeo& g, const TmapPack& tm, const int4* tileTab, int frame0, int nFrames,
                          cudaStream_t st);
 int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, const int4* tileTabB, const int4* tileTabA5,
-                      int nFrames, uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0);
+                      int nFrames, uint32_t* slots, int* cellCnt, int* err, cudaStream_t st, int frame0,
+                      cudaStream_t side = nullptr, cudaEvent_t evFork = nullptr, cudaEvent_t evJoin = nullptr);
 void launch_cells(const OrbGeo& g, int nFrames, const int* cellTab, const uint8_t* score, uint32_t* slots, int* cellCnt,
                   int* err, cudaStream_t st);
 void launch_octree(const OrbGeo& g, int nFrames, const uint32_t* slots, const int* cellCnt, unsigned long long* cand,

@@ -157,7 +157,10 @@ int main(int argc, char** argv) {
           fprintf(stderr, "I Sliding window optimization: %d iterations, result value: %.9g\n", shard[d].iters[w], shard[d].fx[w]);
 
     // Average the velocities among the sliding windows falling on every IMU measurement (fit_motion.cc:250-262);
-    // shards hold disjoint window ranges in ascending order, so adding them in order keeps std::accumulate's order.
+    // shards hold disjoint window ranges in ascending order.  With ONE shard this is std::accumulate's order exactly; with
+    // --num_gpus > 1 an event covered by windows of two shards is summed as (v1 + v2) + (v3 + v4) instead of
+    // ((v1 + v2) + v3) + v4 -- floating-point addition is not associative, so such boundary events (and the forward-axis
+    // sum below) can differ from the single-GPU / reference result in the last ulp.
     const size_t m = merged_t.size();
     std::vector<double> averaged, timestamps_sec;
     std::vector<int64_t> timestamps_usec;
