@@ -548,6 +548,12 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
         ra[i] = v.x;
         rb[i] = v.y;
       }
+      uint32_t dvA[11], dvB[11];
+#pragma unroll
+      for (int i = 0; i < 11; i++) {
+        dvA[i] = __vabsdiffu4(ra[i], ra[i + 3]);
+        dvB[i] = __vabsdiffu4(rb[i], rb[i + 3]);
+      }
       const uint32_t one = g.one;
       const uint32_t M7 = g.absMask, M20 = g.absMaskIni;  // 0x80 - (th + 1) in every byte: x + M has its msb set iff x > th (x < 0x80)
 #pragma unroll
@@ -556,8 +562,9 @@ __global__ void __launch_bounds__(32 * kNb, kNb == 4 ? kFcOccA : 6) k_fast_cells
         const uint32_t* crow = col + c * kFcInWords;
         const uint32_t wl = crow[-1], wr = crow[2];  // lane 0 / o = 0: the word before the row -- only feeds untested pixels
         const uint32_t cA = ra[c], cB = rb[c];
-        const uint32_t vA = __vabsdiffu4(ra[j], cA) | __vabsdiffu4(cA, ra[c + 3]);
-        const uint32_t vB = __vabsdiffu4(rb[j], cB) | __vabsdiffu4(cB, rb[c + 3]);
+        // |row y - row y-3| serves row y (its upper ring pixel) and row y-3 (its lower one): 22 differences per band, not 32
+        const uint32_t vA = dvA[j] | dvA[j + 3];
+        const uint32_t vB = dvB[j] | dvB[j + 3];
         const uint32_t hA = __vabsdiffu4(cA, __byte_perm(wl, cA, 0x4321)) | __vabsdiffu4(cA, __byte_perm(cA, cB, 0x6543));
         const uint32_t hB = __vabsdiffu4(cB, __byte_perm(cA, cB, 0x4321)) | __vabsdiffu4(cB, __byte_perm(cB, wr, 0x6543));
         // msb of a byte: the (OR of the two) absolute differences exceeds the threshold -- a necessary condition for a

@@ -25,7 +25,7 @@ for r in rows:
 tot = sum(sum(v) for v in agg.values())
 b = json.load(open(bench_json))
 st = b['stage_us_per_frame']; s = sum(st.values())
-stage_of = {'pgb::k_pyramid_tiled': 'pyramid', 'pgb::k_fast_score<4>': 'fast_score', 'pgb::k_cells': 'cell_nms', 'pgb::k_octree': 'octree',
+stage_of = {'pgb::k_pyramid_tiled': 'pyramid', 'pgb::k_pyramid_walk': 'pyramid', 'pgb::k_fast_cells': 'fast_cells', 'pgb::k_octree': 'octree',
             'pgb::k_orient_desc': 'orient_desc', 'pgb::k_match': 'match', 'pgb::k_match_resolve': 'match'}
 out = [f"# {tag} launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-calibration`",
        "Per-launch times under ncu are cold-cache and serialised: compare SHARES with the live CUDA-event stage times, not absolutes.", "",
@@ -33,14 +33,14 @@ out = [f"# {tag} launch list: `ncu --metrics gpu__time_duration.sum --clock-cont
 share_ncu = collections.Counter()
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     out.append(f"| `{k}` | {len(v)} | {sum(v):.1f} | {sum(v) / len(v):.1f} | {sum(v) / tot:.3f} |")
-    kk = 'pgb::k_fast_score<4>' if k.startswith('pgb::k_fast_score') else k
+    kk = 'pgb::k_fast_cells' if k.startswith('pgb::k_fast_cells') else k
     if kk in stage_of: share_ncu[stage_of[kk]] += sum(v) / tot
 out += ["", f"Live stage times of the same workload (bench line {os.path.basename(bench_json)}: value {b['value']:.0f} frames/s, e2e {b['e2e']['value']:.0f} frames/s):", "",
         "| stage | us/frame (CUDA events) | share live | share ncu |", "|---|---|---|---|"]
 for k, v in st.items():
     out.append(f"| {k} | {v:.2f} | {v / s:.3f} | {share_ncu[k]:.3f} |")
 r = b['roofline']
-out += ["", f"`k_fast_score`: {r['us_per_launch']:.1f} us per {b['config']['frames_per_gpu_per_step']}-frame launch -> {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of {r['peak']:.0f} GB/s ({r['peak_source']})."]
+out += ["", f"`{r['kernel'].split(' ')[0]}`: {r['us_per_launch']:.1f} us per {b['config']['frames_per_gpu_per_step']}-frame launch -> {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of {r['peak']:.0f} GB/s ({r['peak_source']})."]
 open(os.path.join(P, f"{tag}_launches_summary.md"), "w").write("\n".join(out) + "\n")
 
 raw = subprocess.run(["ncu", "-i", stages_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -51,7 +51,8 @@ cols = [('gpu__time_duration.sum', 'us'), ('launch__grid_size', 'grid'), ('launc
         ('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'FMA pipe %'), ('l1tex__throughput.avg.pct_of_peak_sustained_active', 'L1/smem %'),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %'), ('dram__bytes_read.sum', 'DRAM rd MB'), ('dram__bytes_write.sum', 'DRAM wr MB'),
         ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM %')]
-nb = [l for l in open(os.path.join(ROOT, "gpurun_out", "ncu_stages.log")) if 'profiled stages over' in l]
+stages_log = sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "gpurun_out", "ncu_stages.log")
+nb = [l for l in open(stages_log) if 'profiled stages over' in l] if os.path.exists(stages_log) else []
 out = [f"# {tag} `ncu --profile-from-start off --set full --clock-control none --import-source on python tools/gpu_stage_profile.py`",
        "One pass of every stage kernel over a resident batch (" + (nb[-1].strip() if nb else "32 frames") + ").", "",
        "| kernel | " + " | ".join(c[1] for c in cols) + " |", "|---|" + "---|" * len(cols)]
@@ -66,12 +67,12 @@ for d in data:
             pass
         vals.append(v)
     out.append(f"| `{name}` | " + " | ".join(vals) + " |")
-fs = [d for d in data if 'k_fast_score' in d[h.index('Kernel Name')]]
+fs = [d for d in data if 'k_fast_cells2' in d[h.index('Kernel Name')]]
 if fs:
-    d = fs[0]
-    rd, wr = float(d[h.index('dram__bytes_read.sum')]), float(d[h.index('dram__bytes_write.sum')])
+    rd = sum(float(d[h.index('dram__bytes_read.sum')]) for d in fs)
+    wr = sum(float(d[h.index('dram__bytes_write.sum')]) for d in fs)
     n = 32
-    out += ["", f"`k_fast_score`: DRAM traffic {rd + wr:.1f} MB per {n}-frame launch = {(rd + wr) / n:.2f} MB/frame (algorithmic 12.84 MB/frame; part of the score map is still dirty in L2 when the kernel ends).",
+    out += ["", f"`k_fast_cells2` (4-band + 5-band launches): DRAM traffic {rd + wr:.1f} MB per {n}-frame batch = {(rd + wr) / n:.2f} MB/frame (algorithmic, fused: 6.42 MB/frame read + 4 B per candidate slot / cell count).",
             "Reading: issue slots and the half-rate ALU pipe are busy, DRAM is not: the kernel is bound by ALU-pipe instruction issue (see DESIGN.md section 4 and r01_pipe_probe.txt)."]
 open(os.path.join(P, f"{tag}_kernels_ncu_full.md"), "w").write("\n".join(out) + "\n")
 print("wrote", [f for f in os.listdir(P) if f.startswith(tag)])
