@@ -117,6 +117,16 @@ int pgb_frames_to_gray(int device, const uint8_t* src, int src_is_device, int n_
                        int formula, uint8_t* dst_gray, int dst_is_device, size_t dst_pitch, size_t dst_frame_stride,
                        void* stream);
 
+/* The same with the container's `rotate` metadata applied first, as VideoImageSequenceSource::fetchNext does
+ * (src/io/image_sequence_reader.cc:113-118 reads it, :186-207 applies it: 90 -> cv::flip(raw.t(), out, 0),
+ * 180 -> cv::flip(raw, out, -1), 270 -> cv::flip(raw.t(), out, 1); anything else is fatal there and PGB_ERR_INVALID here).
+ * src_width x src_height is the DECODED frame; for 90 / 270 the gray output is src_height wide and src_width high
+ * (dst_pitch / dst_frame_stride refer to that).  The flips act on the rotated image, as in the reference's call order. */
+int pgb_frames_to_gray_rotated(int device, const uint8_t* src, int src_is_device, int n_frames, int src_width, int src_height,
+                               int channels, int rgb_order, size_t src_pitch, size_t src_frame_stride, int rotate_degrees,
+                               int vertical_flip, int horizontal_flip, int formula, uint8_t* dst_gray, int dst_is_device,
+                               size_t dst_pitch, size_t dst_frame_stride, void* stream);
+
 /* Synthetic frame source for the long BASELINE configs (SURVEY.md 8d's generator rendered on the device: canvas crop at
  * the ping-pong origin of frame first_t + i, plus deterministic per-frame noise).  Stands where a hardware video decoder
  * would: n_frames tight width x height gray frames appear in device memory (out_dev), ready for pgb_orb_extract

@@ -50,6 +50,8 @@ _SIGS = {
     "pgb_orb_check": (C.c_int, [vp]),
     "pgb_frames_to_gray": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                      C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
+    "pgb_frames_to_gray_rotated": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
     "pgb_synth_frames": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "pgb_device_count": (C.c_int, []),
     "pgb_device_malloc": (vp, [C.c_int, C.c_size_t]),

@@ -12,6 +12,59 @@
 
 namespace pgb {
 
+// The same with the container's `rotate` metadata applied first (VideoImageSequenceSource::fetchNext,
+// src/io/image_sequence_reader.cc:186-207: 90 -> cv::flip(raw.t(), out, 0), 180 -> cv::flip(raw, out, -1),
+// 270 -> cv::flip(raw.t(), out, 1)), then the CLI's flips, then cvtColor.  (w, h) are the OUTPUT dimensions; thread =
+// four output pixels of a row.  For 90 / 270 an output row walks down a source column: a 32 x 32 tile goes through shared
+// memory so that both the source reads and the destination writes are row-contiguous.
+template <int kCh>
+__global__ void __launch_bounds__(256) k_to_gray_rot(const uint8_t* __restrict__ src, size_t srcPitch, size_t srcStride,
+                                                     uint8_t* __restrict__ dst, size_t dstPitch, size_t dstStride, int w, int h,
+                                                     int rgbOrder, int vflip, int hflip, int formula, int rot) {
+  __shared__ uint8_t tile[32][33];
+  const int f = blockIdx.z;
+  const int cr = formula ? 9798 : 4899, cg = formula ? 19235 : 9617, cb = formula ? 3735 : 1868;
+  const int rnd = formula ? 16384 : 8192, sh = formula ? 15 : 14;
+  const int sw = (rot == 90 || rot == 270) ? h : w, shh = (rot == 90 || rot == 270) ? w : h;  // source dimensions
+  // output (y, x) -> rotated image (yr, xr) through the flips -> source (sy, sx)
+  auto src_of = [&](int y, int x, int* sy, int* sx) {
+    const int yr = vflip ? h - 1 - y : y, xr = hflip ? w - 1 - x : x;
+    if (rot == 0) { *sy = yr; *sx = xr; }
+    else if (rot == 90) { *sy = xr; *sx = sw - 1 - yr; }       // out(y, x) = raw(x, w_src - 1 - y)
+    else if (rot == 180) { *sy = shh - 1 - yr; *sx = sw - 1 - xr; }
+    else { *sy = shh - 1 - xr; *sx = yr; }                      // 270: out(y, x) = raw(h_src - 1 - x, y)
+  };
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  const bool transposed = rot == 90 || rot == 270;
+  // load phase: thread (tx, ty + 8k) reads the source pixel that is contiguous along tx
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int a = ty + 8 * k;
+    // not transposed: (y, x) = (y0 + a, x0 + tx); transposed: the source row index follows the output x, so swap roles
+    const int y = transposed ? y0 + tx : y0 + a, x = transposed ? x0 + a : x0 + tx;
+    if (y < h && x < w) {
+      int sy, sx;
+      src_of(y, x, &sy, &sx);
+      const uint8_t* p = src + (size_t)f * srcStride + (size_t)sy * srcPitch + (size_t)sx * kCh;
+      int v;
+      if (kCh == 1) v = p[0];
+      else {
+        const int c0 = p[0], c1 = p[1], c2 = p[2];
+        const int r = rgbOrder ? c0 : c2, b = rgbOrder ? c2 : c0;
+        v = (r * cr + c1 * cg + b * cb + rnd) >> sh;
+      }
+      if (transposed) tile[tx][a] = (uint8_t)v; else tile[a][tx] = (uint8_t)v;   // tile[y - y0][x - x0]
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int y = y0 + ty + 8 * k, x = x0 + tx;
+    if (y < h && x < w) dst[(size_t)f * dstStride + (size_t)y * dstPitch + x] = tile[ty + 8 * k][tx];
+  }
+}
+
 template <int kCh>
 __global__ void __launch_bounds__(256) k_to_gray(const uint8_t* __restrict__ src, size_t srcPitch, size_t srcStride,
                                                  uint8_t* __restrict__ dst, size_t dstPitch, size_t dstStride, int w, int h,
@@ -54,11 +107,27 @@ extern "C" int pgb_frames_to_gray(int device, const uint8_t* src, int src_is_dev
                                   int channels, int rgb_order, size_t src_pitch, size_t src_frame_stride, int vertical_flip,
                                   int horizontal_flip, int formula, uint8_t* dst_gray, int dst_is_device, size_t dst_pitch,
                                   size_t dst_frame_stride, void* stream) {
-  if (n_frames < 0 || width < 0 || height < 0 || (channels != 1 && channels != 3 && channels != 4) || (formula != 0 && formula != 1))
+  return pgb_frames_to_gray_rotated(device, src, src_is_device, n_frames, width, height, channels, rgb_order, src_pitch,
+                                    src_frame_stride, 0, vertical_flip, horizontal_flip, formula, dst_gray, dst_is_device,
+                                    dst_pitch, dst_frame_stride, stream);
+}
+
+extern "C" int pgb_frames_to_gray_rotated(int device, const uint8_t* src, int src_is_device, int n_frames, int src_width,
+                                          int src_height, int channels, int rgb_order, size_t src_pitch, size_t src_frame_stride,
+                                          int rotate_degrees, int vertical_flip, int horizontal_flip, int formula,
+                                          uint8_t* dst_gray, int dst_is_device, size_t dst_pitch, size_t dst_frame_stride,
+                                          void* stream) {
+  if (n_frames < 0 || src_width < 0 || src_height < 0 || (channels != 1 && channels != 3 && channels != 4) || (formula != 0 && formula != 1))
     return fail(PGB_ERR_INVALID, "pgb_frames_to_gray: invalid argument");
+  rotate_degrees %= 360;  // image_sequence_reader.cc:118
+  if (rotate_degrees != 0 && rotate_degrees != 90 && rotate_degrees != 180 && rotate_degrees != 270)
+    return fail(PGB_ERR_INVALID, "Unsupported rotation angle in video metadata: %d. Only multiples of 90 degrees rotations are supported.",
+                rotate_degrees);  // the reference's LOG(FATAL) (:203-206)
+  const bool transposed = rotate_degrees == 90 || rotate_degrees == 270;
+  const int width = transposed ? src_height : src_width, height = transposed ? src_width : src_height;  // output dimensions
   if (n_frames == 0 || width == 0 || height == 0) return PGB_OK;
-  if (!src || !dst_gray || src_pitch < (size_t)width * channels || dst_pitch < (size_t)width ||
-      src_frame_stride < src_pitch * height || dst_frame_stride < dst_pitch * height)
+  if (!src || !dst_gray || src_pitch < (size_t)src_width * channels || dst_pitch < (size_t)width ||
+      src_frame_stride < src_pitch * src_height || dst_frame_stride < dst_pitch * height)
     return fail(PGB_ERR_INVALID, "pgb_frames_to_gray: null buffer or pitch/stride smaller than the image");
   if (use_device(device)) return PGB_ERR_CUDA;
   cudaStream_t s = (cudaStream_t)stream;
@@ -67,17 +136,24 @@ extern "C" int pgb_frames_to_gray(int device, const uint8_t* src, int src_is_dev
   uint8_t* out = dst_gray;
   if (!src_is_device) {
     if (dIn.alloc(src_frame_stride * n_frames)) return PGB_ERR_CUDA;
-    PGB_CUDA(cudaMemcpyAsync(dIn.p, src, src_frame_stride * (n_frames - 1) + src_pitch * height, cudaMemcpyHostToDevice, s));
+    PGB_CUDA(cudaMemcpyAsync(dIn.p, src, src_frame_stride * (n_frames - 1) + src_pitch * src_height, cudaMemcpyHostToDevice, s));
     in = dIn.p;
   }
   if (!dst_is_device) {
     if (dOut.alloc(dst_frame_stride * n_frames)) return PGB_ERR_CUDA;
     out = dOut.p;
   }
+  if (rotate_degrees != 0) {
+    dim3 gridR((width + 31) / 32, (height + 31) / 32, n_frames);
+    if (channels == 1) k_to_gray_rot<1><<<gridR, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula, rotate_degrees);
+    else if (channels == 3) k_to_gray_rot<3><<<gridR, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula, rotate_degrees);
+    else k_to_gray_rot<4><<<gridR, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula, rotate_degrees);
+  } else {
   dim3 grid(((width + 3) / 4 + 255) / 256, height, n_frames);
   if (channels == 1) k_to_gray<1><<<grid, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula);
   else if (channels == 3) k_to_gray<3><<<grid, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula);
   else k_to_gray<4><<<grid, 256, 0, s>>>(in, src_pitch, src_frame_stride, out, dst_pitch, dst_frame_stride, width, height, rgb_order, vertical_flip, horizontal_flip, formula);
+  }
   PGB_CHECK_LAUNCH();
   if (!dst_is_device) {
     PGB_CUDA(cudaMemcpy2DAsync(dst_gray, dst_pitch, dOut.p, dst_pitch, width, (size_t)height, cudaMemcpyDeviceToHost, s));

@@ -130,6 +130,21 @@ class ORBextractor:
         return lw.value, lh.value
 
 
+def frames_to_gray_rotated(frames: np.ndarray, rotate_degrees: int, rgb_order: bool = True, vertical_flip: bool = False,
+                           horizontal_flip: bool = False, formula: int = 0, device: int = 0) -> np.ndarray:
+    """The frame feed after the decoder: the container's `rotate` metadata (image_sequence_reader.cc:113-118, 186-207), then
+    cv::flip, then cvtColor to gray, of (n, h, w[, c]) uint8 frames on the device.  Returns (n, w, h) for 90 / 270."""
+    a = np.ascontiguousarray(frames, np.uint8)
+    if a.ndim == 3:
+        a = a[..., None]
+    n, h, w, c = a.shape
+    oh, ow = (w, h) if rotate_degrees % 360 in (90, 270) else (h, w)
+    out = np.empty((n, oh, ow), np.uint8)
+    check(lib().pgb_frames_to_gray_rotated(device, np_ptr(a), 0, n, w, h, c, int(rgb_order), w * c, w * c * h, int(rotate_degrees),
+                                           int(vertical_flip), int(horizontal_flip), formula, np_ptr(out), 0, ow, ow * oh, None))
+    return out
+
+
 def frames_to_gray(frames: np.ndarray, rgb_order: bool = True, vertical_flip: bool = False, horizontal_flip: bool = False,
                    formula: int = 0, device: int = 0) -> np.ndarray:
     """cv::flip + cvtColor to gray of (n, h, w[, c]) uint8 frames on the device (image_sequence_reader.cc:163-175,

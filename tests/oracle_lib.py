@@ -488,3 +488,17 @@ def to_gray(img, rgb_order=True, vflip=False, hflip=False, formula=0):
     out = np.empty((h, w), np.uint8)
     lib().pgo_to_gray(ptr(a, u8p), w, h, c, int(rgb_order), int(vflip), int(hflip), int(formula), ptr(out, u8p))
     return out
+
+
+def rotate_like_reader(img, rotate_degrees):
+    """The rotation VideoImageSequenceSource::fetchNext applies (src/io/image_sequence_reader.cc:186-207), in numpy:
+    90 -> cv::flip(raw.t(), 0), 180 -> cv::flip(raw, -1), 270 -> cv::flip(raw.t(), 1).  tests/test_oracle_feed.py pins it
+    against cv2.transpose / cv2.flip."""
+    a = np.asarray(img)
+    r = rotate_degrees % 360
+    if r == 0:
+        return a
+    if r == 180:
+        return a[::-1, ::-1]
+    t = a.transpose(1, 0, 2) if a.ndim == 3 else a.T
+    return t[::-1] if r == 90 else t[:, ::-1]

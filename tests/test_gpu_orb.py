@@ -160,6 +160,19 @@ def test_frame_feed_matches_oracle_and_feeds_the_extractor(golden_dir):
                 got = frames_to_gray(fr, bool(rgbo), bool(vf), bool(hf), fm)
                 for i in range(3):
                     assert np.array_equal(got[i], O.to_gray(fr[i], bool(rgbo), bool(vf), bool(hf), fm)), (c, w, h, rgbo, vf, hf, fm)
+    # the container's `rotate` metadata (image_sequence_reader.cc:186-207) ahead of the flips and the conversion
+    from pilotguru_b200.orb import frames_to_gray_rotated
+    for c in (1, 3, 4):
+        for w, h in ((64, 48), (61, 37), (1, 1), (5, 3), (33, 130)):
+            fr = rng.integers(0, 256, (2, h, w, c), dtype=np.uint8)
+            for deg in (0, 90, 180, 270, 450):
+                for rgbo, vf, hf, fm in ((1, 0, 0, 0), (0, 1, 0, 1), (1, 1, 1, 0)):
+                    got = frames_to_gray_rotated(fr, deg, bool(rgbo), bool(vf), bool(hf), fm)
+                    for i in range(2):
+                        want = O.to_gray(np.ascontiguousarray(O.rotate_like_reader(fr[i], deg)), bool(rgbo), bool(vf), bool(hf), fm)
+                        assert got[i].shape == want.shape and np.array_equal(got[i], want), (c, w, h, deg, rgbo, vf, hf, fm)
+    with pytest.raises(Exception, match="Unsupported rotation angle"):
+        frames_to_gray_rotated(rng.integers(0, 256, (1, 4, 4, 3), dtype=np.uint8), 45)
     # colour frame -> gray on the device -> extractor == extractor on the oracle's gray
     base = synth.frame(2, w=320, h=240)
     rgb = np.stack([base, np.roll(base, 1, axis=1), np.roll(base, 2, axis=0)], axis=2)

@@ -27,3 +27,17 @@ def test_to_gray_opencv2_formula():
     gray = rng.integers(0, 256, (40, 50), dtype=np.uint8)
     assert np.array_equal(O.to_gray(gray, vflip=True), gray[::-1])
     assert np.array_equal(O.to_gray(gray, hflip=True), gray[:, ::-1])
+
+
+def test_reader_rotation_matches_cv2():
+    """O.rotate_like_reader restates the switch of VideoImageSequenceSource::fetchNext (image_sequence_reader.cc:186-207) with
+    numpy views; here it is held to the reference's own calls, cv::flip / Mat::t(), through cv2."""
+    cv2 = __import__("pytest").importorskip("cv2")
+    rng = np.random.default_rng(12)
+    for shape in ((37, 61, 3), (48, 64), (1, 5, 3)):
+        raw = rng.integers(0, 256, shape, dtype=np.uint8)
+        want = {0: raw, 90: cv2.flip(cv2.transpose(raw), 0), 180: cv2.flip(raw, -1), 270: cv2.flip(cv2.transpose(raw), 1)}
+        for deg, w in want.items():
+            w = w.reshape(O.rotate_like_reader(raw, deg).shape)   # cv2 drops a trailing unit axis
+            assert np.array_equal(O.rotate_like_reader(raw, deg), w), (shape, deg)
+            assert np.array_equal(O.rotate_like_reader(raw, deg + 360), w)
