@@ -127,6 +127,25 @@ int pgb_frames_to_gray_rotated(int device, const uint8_t* src, int src_is_device
                                int vertical_flip, int horizontal_flip, int formula, uint8_t* dst_gray, int dst_is_device,
                                size_t dst_pitch, size_t dst_frame_stride, void* stream);
 
+/* Frame feed, decode part: VideoImageSequenceSource (src/io/image_sequence_reader.cc:74-208) for Motion-JPEG AVI files.
+ * pgb_video_open demuxes the container on the host (RIFF 'AVI ' / OpenDML 'AVIX', first video stream as
+ * VideoStreamIndexOrDie :63-71 picks it) and indexes the frames; no GPU is needed for open / info.  Any other container or
+ * codec is refused (NULL, pgb_last_error names the FOURCC): this image has nvJPEG, not libav / NVDEC.
+ * pgb_video_read_rgb decodes frames [first_frame, first_frame + n_frames) with nvJPEG (bound at run time) into interleaved
+ * RGB24 DEVICE memory -- the raw_frame_image_ of the reference (:157-170) -- asynchronously on `stream`, and writes the
+ * frames' timestamps in seconds (best-effort pts x time_base, :153-155; host array, may be NULL).  Feed the result to
+ * pgb_frames_to_gray_rotated (channels 3, rgb_order 1, src_is_device 1) with pgb_video_info's rotate_degrees.
+ * A handle is not thread-safe; independent handles on the same file are (frames are independently decodable, which is
+ * what lets optical_trajectories --num_gpus shard a file). */
+typedef struct pgb_video pgb_video;
+pgb_video* pgb_video_open(int device, const char* path);
+int pgb_video_info(pgb_video*, int* width, int* height, int64_t* n_frames, double* fps, int* rotate_degrees);
+/* byte range of a frame's JPEG image inside the file (demuxer parity tests) */
+int pgb_video_frame_span(pgb_video*, int64_t frame, uint64_t* offset, uint32_t* size);
+int pgb_video_read_rgb(pgb_video*, int64_t first_frame, int n_frames, uint8_t* rgb_dev, size_t pitch, size_t frame_stride,
+                       double* timestamps_sec, void* stream);
+void pgb_video_close(pgb_video*);
+
 /* Synthetic frame source for the long BASELINE configs (SURVEY.md 8d's generator rendered on the device: canvas crop at
  * the ping-pong origin of frame first_t + i, plus deterministic per-frame noise).  Stands where a hardware video decoder
  * would: n_frames tight width x height gray frames appear in device memory (out_dev), ready for pgb_orb_extract

@@ -52,6 +52,11 @@ _SIGS = {
                                      C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
     "pgb_frames_to_gray_rotated": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                              C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
+    "pgb_video_open": (vp, [C.c_int, C.c_char_p]),
+    "pgb_video_info": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+    "pgb_video_frame_span": (C.c_int, [vp, C.c_int64, vp, vp]),
+    "pgb_video_read_rgb": (C.c_int, [vp, C.c_int64, C.c_int, vp, C.c_size_t, C.c_size_t, vp, vp]),
+    "pgb_video_close": (None, [vp]),
     "pgb_synth_frames": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "pgb_device_count": (C.c_int, []),
     "pgb_device_malloc": (vp, [C.c_int, C.c_size_t]),

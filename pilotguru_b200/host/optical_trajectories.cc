@@ -12,7 +12,9 @@
 //
 // Scope: the SLAM back end (map initialisation, local BA, loop closing, DBoW2
 // relocalisation) and video decoding are out of scope.  So this binary runs in FLOW-TRACKING mode:
-//   * --in_video takes raw frames:  raw:<path>:<width>x<height> (8-bit gray, frame i at byte i*width*height),
+//   * --in_video takes a Motion-JPEG AVI file (demuxed and decoded on the device through pgb_video_*: the frames the
+//     reference gets from VideoImageSequenceSource; the frame rate comes from the container), or raw frames:
+//     raw:<path>:<width>x<height> (8-bit gray, frame i at byte i*width*height),
 //     raw24:<path>:<width>x<height> (interleaved 24-bit colour, the format the reference's reader hands to the tracker;
 //     channel order from Camera_RGB; flips and the colour conversion run on the device, pgb_frames_to_gray), or
 //     synth:<canvas path>:<canvas width>x<canvas height>:<frames>:<width>x<height> -- the SURVEY 8(d) synthetic sequence
@@ -69,7 +71,8 @@ std::map<std::string, double> ReadSettings(const std::string& path) {
 }
 
 struct Source {
-  enum Kind { kRawGray, kRaw24, kSynth } kind = kRawGray;
+  enum Kind { kRawGray, kRaw24, kSynth, kAvi } kind = kRawGray;
+  double fps = 0;  // kAvi: the container's frame rate (timestamps = pts * time_base, image_sequence_reader.cc:153-155)
   std::string path;
   int width = 0, height = 0, channels = 1;
   int canvasW = 0, canvasH = 0;
@@ -80,14 +83,27 @@ Source ParseSource(const std::string& spec) {
   Source s;
   char path[4096];
   long long n = 0;
+  if (spec.size() > 4 && spec.compare(0, 4, "raw:") != 0 && spec.compare(0, 6, "raw24:") != 0 && spec.compare(0, 6, "synth:") != 0) {
+    // a video FILE, as the reference takes it (VideoImageSequenceSource, image_sequence_reader.cc:74-120): demuxed and
+    // decoded through libpgb200 (Motion-JPEG AVI; any other container / codec is refused there with its name)
+    pgb_video* v = pgb_video_open(0, spec.c_str());
+    PGB_CHECK(v != nullptr) << pgb_last_error()
+                            << " (--in_video takes a Motion-JPEG .avi file, raw:<path>:<w>x<h>, raw24:<path>:<w>x<h> or "
+                               "synth:<canvas>:<cw>x<ch>:<frames>:<w>x<h>)";
+    int rot = 0;
+    PGB_CALL(pgb_video_info(v, &s.width, &s.height, &s.frames, &s.fps, &rot));
+    pgb_video_close(v);
+    s.kind = Source::kAvi; s.channels = 3; s.path = spec;
+    return s;
+  }
   if (sscanf(spec.c_str(), "synth:%4095[^:]:%dx%d:%lld:%dx%d", path, &s.canvasW, &s.canvasH, &n, &s.width, &s.height) == 6) {
     s.kind = Source::kSynth; s.frames = n;
   } else if (sscanf(spec.c_str(), "raw24:%4095[^:]:%dx%d", path, &s.width, &s.height) == 3) {
     s.kind = Source::kRaw24; s.channels = 3;
   } else {
     PGB_CHECK(sscanf(spec.c_str(), "raw:%4095[^:]:%dx%d", path, &s.width, &s.height) == 3)
-        << "--in_video must be raw:<path>:<w>x<h>, raw24:<path>:<w>x<h> or synth:<canvas>:<cw>x<ch>:<frames>:<w>x<h> (video "
-           "decoding is out of scope, see the header comment)";
+        << "--in_video must be a Motion-JPEG .avi file, raw:<path>:<w>x<h>, raw24:<path>:<w>x<h> or "
+           "synth:<canvas>:<cw>x<ch>:<frames>:<w>x<h> (see the header comment)";
   }
   s.path = path;
   PGB_CHECK(s.width > 0 && s.height > 0);
@@ -152,8 +168,14 @@ struct Rank {
     uint8_t* dAllRec = comm ? (uint8_t*)dalloc(recBytes * pgb_comm_size(comm)) : nullptr;
     uint8_t* dCanvas = nullptr;
     uint8_t* hRaw = nullptr;
+    uint8_t* dRgb = nullptr;
+    pgb_video* video = nullptr;
     int fd = -1;
-    if (src->kind == Source::kSynth) {
+    if (src->kind == Source::kAvi) {
+      video = pgb_video_open(device, src->path.c_str());  // one demuxer per rank: Motion-JPEG frames decode independently
+      PGB_CHECK(video != nullptr) << pgb_last_error();
+      dRgb = (uint8_t*)dalloc(inBytes * B);
+    } else if (src->kind == Source::kSynth) {
       std::vector<uint8_t> canvas((size_t)src->canvasW * src->canvasH);
       FILE* f = fopen(src->path.c_str(), "rb");
       PGB_CHECK(f != nullptr) << "cannot open canvas " << src->path;
@@ -237,7 +259,14 @@ struct Rank {
         cv.wait(l, [&] { return !h.busy; });  // the worker is done with this set (two batches ago)
       }
       // ---- frames -> gray on the device -> features in slots 1..n
-      if (src->kind == Source::kSynth) {
+      if (src->kind == Source::kAvi) {
+        // decode (nvJPEG) -> RGB24 on the device -> cv::flip + cvtColor (pgb_frames_to_gray: the decoder hands out RGB order,
+        // image_sequence_reader.cc:157-170) -> extractor; nothing crosses PCIe but the compressed frames
+        PGB_CALL(pgb_video_read_rgb(video, b0, n, dRgb, (size_t)W * 3, inBytes, nullptr, st));
+        PGB_CALL(pgb_frames_to_gray(device, dRgb, 1, n, W, H, 3, 1, (size_t)W * 3, inBytes, cfg->vertical_flip ? 1 : 0,
+                                    cfg->horizontal_flip ? 1 : 0, 0, dGray, 1, W, frameBytes, st));
+        PGB_CALL(pgb_orb_extract(orb, dGray, PGB_IN_DEVICE | PGB_OUT_DEVICE, n, W, H, W, frameBytes, dK + cap, dD + (size_t)cap * 32, dN + 1, cap));
+      } else if (src->kind == Source::kSynth) {
         PGB_CALL(pgb_synth_frames(device, dCanvas, src->canvasW, src->canvasH, (int)b0, n, W, H, dGray, st));
         PGB_CALL(pgb_orb_extract(orb, dGray, PGB_IN_DEVICE | PGB_OUT_DEVICE, n, W, H, W, frameBytes, dK + cap, dD + (size_t)cap * 32, dN + 1, cap));
       } else {
@@ -307,6 +336,8 @@ struct Rank {
     }
     seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
     if (fd >= 0) close(fd);
+    pgb_video_close(video);
+    pgb_device_free(device, dRgb);
     pgb_host_free_pinned(hRaw);
     for (HostSet& h : hs) { pgb_host_free_pinned(h.K); pgb_host_free_pinned(h.N); pgb_host_free_pinned(h.Match); pgb_host_free_pinned(h.Nm); }
     for (void* p : {(void*)dK, (void*)dD, (void*)dN, (void*)dMatch, (void*)dNm, (void*)dFlow, (void*)dGray, (void*)dFirstRec, (void*)dLastRec,
@@ -430,7 +461,9 @@ int main(int argc, char** argv) {
     pgbhost::PoseWithTimestamp pw;
     pw.pose.t[0] = pos[0]; pw.pose.t[1] = pos[1]; pw.pose.t[2] = pos[2];
     pw.pose.qw = std::cos(heading * 0.5); pw.pose.qx = 0; pw.pose.qy = std::sin(heading * 0.5); pw.pose.qz = 0;
-    pw.time_usec = (int64_t)std::llround((double)t * 1e6 / cfg.fps);
+    // a video file carries its own time base (timestamp = pts * time_base, image_sequence_reader.cc:153-155); raw frames
+    // are stamped with the settings file's Camera_fps
+    pw.time_usec = (int64_t)std::llround((double)t * 1e6 / (src.kind == Source::kAvi ? src.fps : cfg.fps));
     pw.is_lost = false;
     pw.frame_id = t;
     trajectory.push_back(pw);
