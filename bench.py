@@ -37,7 +37,7 @@ FAST_K2_BYTES_PER_FRAME = 2 * PYRAMID_PX
 N_CELLS = 6257
 WORKLOAD = ("ORBextractor 1000 keypoints, 1920x1080 synthetic frames, 8-level pyramid + SearchByProjection vs previous "
             "frame (BASELINE configs[1], batched)")
-# pgb_orb_run_stage ids: 0 pyramid, 1 FAST score + cell NMS (fused k_fast_cells), 3 octree, 4 orientation + descriptor;
+# pgb_orb_run_stage ids: 0 pyramid, 1 FAST score + cell NMS (fused k_fast_cells2), 3 octree, 4 orientation + descriptor;
 # 2 = the round-1 unfused pair (k_fast_score -> k_cells) recomputing the same candidates, timed for the A/B only
 STAGES = {"pyramid": 0, "fast_cells": 1, "octree": 3, "orient_desc": 4}
 TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_fast_cells_traffic.json")
@@ -348,7 +348,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "1080p frames/sec ORB extract+match", "value": v, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": per_step},
+            # the same keys as the GPU arm's config (the workload is the same; a step here is a bounded sample of it)
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": per_step, "global_frames_per_step": per_step,
+                       "l2": "n/a (CPU arm)", "schedule": f"one contiguous block of frames per host thread, {cores} threads",
+                       "host_numa_node_rank0": None, "parallelism": "host cores only"},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "build": build,
                              "sample": f"{per_step} frames per step x {args.steps} steps (extract every frame + match every consecutive pair), oracle on {cores} host threads"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -718,7 +721,7 @@ def main():
                            "schedule": ("two steps in flight: consecutive steps alternate over two extractor handles (own streams and scratch), "
                                         "matching (and at N > 1 the boundary all-gather) on a third stream with two feature regions -- "
                                         "the latency-bound kernels of one step (octree, matcher) run under the other step's "
-                                        "throughput-bound ones; measured 2.27 ms single stream -> 2.14 (matcher stream) -> 2.05 ms per 128-frame step")
+                                        "throughput-bound ones (the single-stream time of the same step is reported as ms_per_step_single_stream)")
                                        if not args.one_extractor else "one extractor handle; matcher on a second stream",
                            "host_numa_node_rank0": numa,
                            "parallelism": (f"frames sharded over {world} GPU(s); one NCCL all-gather (pgb_allgather_feats, C-ABI) of the "
@@ -731,7 +734,7 @@ def main():
                         "h2d_box_limit_gbs": h2d / (ms_h2d * 1e-3) / 1e9, "h2d_box_limit_gbs_all_ranks": world * h2d / (ms_h2d * 1e-3) / 1e9},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
-                "roofline": {"kernel": "k_fast_cells (FAST-9 score + per-cell NMS + threshold decision, fused)", "bound": "hbm",
+                "roofline": {"kernel": "k_fast_cells2 (FAST-9 score + per-cell NMS, iniThFAST pass then minThFAST for the empty cells, fused; 4-band + 5-band launches)", "bound": "hbm",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic_pf * B if traffic_pf else None, "peak_source": peak_src,
                              "traffic_source": traffic_src,
