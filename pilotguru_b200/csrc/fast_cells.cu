@@ -3,26 +3,33 @@
 // Reference: ORBextractor::ComputeKeyPointsOctTree, thirdparty/orb-slam2/src/ORBextractor.cc:765-829 (30-px cell grid,
 // cv::FAST(cell view, iniThFAST, nms=true), again with minThFAST when the cell came back empty) over cv::FAST(TYPE_9_16).
 //
-// Why this shape.  The round-1 pair k_fast_score -> k_cells wrote a 6.4 MB/frame score map (96.5 % zeros) and read it
-// back: 12.8 MB/frame of HBM traffic and 4.9 us/frame in k_cells, most of it spent finding the non-zero bytes again
+// Two kernels live here:
+//   * k_fast_cells2<bands> (second half of the file): the hot path.  It follows the reference's own order -- an iniThFAST
+//     pass over the whole tile, a minThFAST pass only for the cells that came back empty -- with both thresholds' flags from
+//     one prefilter, a tile-wide pooled candidate queue of 16-bit entries, scoring rounds dealt round-robin to the warps,
+//     9 CTAs per SM.  Levels whose cells are at most 32 px wide and 8 * bands px high (every level of a 1080p pyramid).
+//   * k_fast_cells<false, 1> (first half): the single-pass kernel of the first half of round 2 -- everything scored at
+//     minThFAST, the thresholds sorted out at emission -- kept as the generic instantiation for levels with larger cells
+//     (other resolutions / scale factors), at one CTA per SM.
+// Both produce the slots / cellCnt layout of the round-1 pair (k_fast_score -> k_cells), so the octree kernel is unchanged,
+// and both are held to that pair bit for bit (tests/test_gpu_orb.py::test_fused_fast_cells_equals_the_unfused_pair).
+//
+// Why the fused shape.  The round-1 pair wrote a 6.4 MB/frame score map (96.5 % zeros) and read it back: 12.8 MB/frame of
+// HBM traffic and 4.9 us/frame in k_cells, most of it spent finding the non-zero bytes again
 // (profiles/r01e_other_kernels_sass_regions.md).  What makes the fusion clean is the reference's own cell semantics:
 // cv::FAST runs on a cell VIEW, so a neighbour outside the cell's tested rectangle counts as score 0 in the 3x3 NMS,
 // and the tested rectangles of the cells tile the level exactly (pitch wCell x hCell from (19, 19)).
 // A tile made of WHOLE cells therefore needs no score halo at all:
-//   * one CTA (4 warps) = one row of up to 8 FAST cells: <= 249 x hCell tested pixels.  The input box (72 words x
-//     (8 * bands + 6) rows, 3-px ring halo) comes in with one 3-D TMA load; the box must start on a 16-byte boundary,
-//     the tile does not, so the 256-px "lane frame" (8 px per lane) starts at the 8-byte boundary at or below the
-//     tile's first pixel and per-lane validity masks cut the frame down to the tested rectangle;
-//   * prefilter / candidate expansion / exact score per 8-row band are the round-1 kernel's (fast_score.cu); the
-//     score goes into a shared-memory tile with a zero guard ring, and the scoring round also compacts the true
-//     corners (52 % of the scored candidates) IN PLACE into the warp's queue as (x, row, score) entries;
-//   * barrier; NMS over the corner lists, one corner per lane: 8 neighbour bytes from the shared tile, neighbours
-//     across a cell boundary masked to 0, survivors set a bit in a per-row bitmap (in the dead code bytes of the queue);
-//   * barrier; emission, warp = cell, lane = tested row: the row's survivor bits inside the cell's x-range, the
-//     subset with score >= iniThFAST, one warp vote for the cell's threshold (survivors at iniTh are exactly the
-//     survivors at minTh with score >= iniTh: one NMS pass serves both thresholds), one warp scan for the reference's
-//     row-major order, then the packed candidates go to the cell's slots -- the same slots / cellCnt layout k_cells
-//     produced, so the octree kernel is unchanged.
+//   * one CTA = one row of up to 8 FAST cells: <= 249 x hCell tested pixels.  The input box (72 words x (8 * bands + 6)
+//     rows, 3-px ring halo) comes in with one 3-D TMA load; the box must start on a 16-byte boundary, the tile does not, so
+//     the 256-px "lane frame" (8 px per lane) starts at the 8-byte boundary at or below the tile's first pixel and
+//     per-lane validity masks cut the frame down to the tested rectangle;
+//   * prefilter / candidate expansion / exact score per 8-row band descend from the round-1 score kernel (fast_score.cu);
+//     the score goes into a shared-memory tile with a zero guard ring;
+//   * barrier; NMS over the corner lists, one corner per lane: 8 neighbour bytes from the shared tile, neighbours across a
+//     cell boundary masked to 0; survivors go to one list per tile;
+//   * barrier; emission: a survivor's slot in its cell is its rank in the reference's row-major order; the packed
+//     candidates go to the cell's slots.
 // Algorithmic bytes per 1080p frame: 6,419,321 B read + 4 B x (cells + candidates) written (SURVEY.md 8d's fused figure).
 #include <cuda_runtime.h>
 
