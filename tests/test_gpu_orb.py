@@ -245,3 +245,35 @@ def test_fused_fast_cells_equals_the_unfused_pair(monkeypatch, size):
     assert np.array_equal(c1, c2)
     for f in range(nfr):
         assert np.array_equal(k1[f, :c1[f]], k2[f, :c1[f]]) and np.array_equal(d1[f, :c1[f]], d2[f, :c1[f]])
+
+
+def test_fused_fast_cells_fuzz_sizes_and_thresholds():
+    """Differential fuzz of the two-tier fused kernel (and the generic single-pass one) against the unfused pair: random level
+    geometries (cells of every class: <= 32 x 32, 33-40 px rows, wider than 32 px), scale factors, level counts and
+    iniThFAST / minThFAST pairs (equal thresholds, minThFAST = 0, a very high iniThFAST that sends every cell to the second
+    tier), on textured, low-contrast and part-noise frames.  Candidates per level must be identical."""
+    from pilotguru_b200.orb import ORBextractor
+    rng = np.random.default_rng(2024)
+    cases = [(1280, 720, 1.2, 8, 20, 7), (811, 607, 1.2, 6, 20, 20), (640, 360, 1.15, 7, 60, 5), (333, 421, 1.3, 4, 12, 0),
+             (1024, 300, 1.2, 5, 255, 30), (260, 260, 1.1, 3, 9, 3), (1919, 517, 1.25, 8, 35, 10), (600, 800, 1.2, 8, 20, 7)]
+    checked = 0
+    for (w, h, sf, nl, ini, mn) in cases:
+        base = synth.frame(int(rng.integers(0, 50)), w=min(w, 1920), h=min(h, 1080)) if w <= 1920 and h <= 1080 else None
+        if base is None or base.shape != (h, w):
+            big = np.tile(synth.frame(3), (2, 1))
+            base = np.ascontiguousarray(big[:h, :w])
+        low = (base.astype(np.float32) * 0.25 + 100).astype(np.uint8)
+        part = base.copy()
+        part[h // 2:, : w // 2] = rng.integers(0, 256, (h - h // 2, w // 2), dtype=np.uint8)
+        part[: h // 3, w // 2:] = 77
+        frames = np.stack([base, low, part])
+        ex = ORBextractor(300, sf, nl, ini, mn, max_width=w, max_height=h, max_batch=3)
+        ex.extract_batch(frames)
+        fused = [[ex.candidates(l, frame=f) for l in range(nl)] for f in range(3)]
+        ex.run_stage(2); ex.check()
+        for f in range(3):
+            for l in range(nl):
+                assert np.array_equal(ex.candidates(l, frame=f), fused[f][l]), (w, h, sf, nl, ini, mn, f, l)
+                checked += len(fused[f][l])
+        ex.close()
+    assert checked > 20000
