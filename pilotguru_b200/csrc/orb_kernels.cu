@@ -150,7 +150,12 @@ __global__ void __launch_bounds__(256) k_pyramid_tiled(OrbGeo g, int level, uint
 //     interpolation; the vertical interpolation is two IMAD + shifts; the four results leave as one 32-bit global store
 //     (a warp writes 128 contiguous bytes).
 // Same integer arithmetic as k_pyramid, bit for bit (all values are non-negative and below 2^27).
-__global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ OrbGeo g, const __grid_constant__ TmapIn tm,
+#ifndef PGB_PY_RPT
+#define PGB_PY_RPT 16
+#endif
+constexpr int kPyRpt = PGB_PY_RPT;  // destination rows per thread (a thread's set-up -- 12 table loads, selectors -- is paid once per kPyRpt rows)
+constexpr int kPyThreads = 64 * (kPyH / kPyRpt);
+__global__ void __launch_bounds__(kPyThreads) k_pyramid_walk(const __grid_constant__ OrbGeo g, const __grid_constant__ TmapIn tm,
                                                       int level, int frame0, uint8_t* __restrict__ pyr,
                                                       const ResizeTab* __restrict__ xtab, const ResizeTab* __restrict__ ytab,
                                                       const int2* __restrict__ tileX, const int2* __restrict__ tileY) {
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
     // the first row of a thread's group of 8
     const ResizeTab tp = ytab[min(max(y0 + tid - 1, 0), D.h - 1)];
     const int p1 = min(max((int)tp.s + 1, 0), S.h - 1) - syLo;
-    const bool reuse = (tid & 7) != 0 && y0 + tid < D.h && p1 == r0;
+    const bool reuse = (tid % kPyRpt) != 0 && y0 + tid < D.h && p1 == r0;
     s_row[tid] = make_uint4((uint32_t)(r0 * kPySrcPitch), (uint32_t)(r1 * kPySrcPitch) | (reuse ? 0x80000000u : 0u), (uint32_t)ty.a0,
                             (uint32_t)ty.a1);
   }
@@ -188,6 +193,11 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
   // is still inside the staged box.
   const int cg = tid & 63, rg = tid >> 6;
   const int gx = x0 + 4 * cg;
+  // Columns beyond the level's width land in the pitch padding (a multiple of 64 >= w).  Threads whose four columns or eight
+  // rows lie entirely outside the level have nothing to compute or write: at 1080p the edge tiles make them 15 % of all
+  // threads (43 % on level 7, whose 536 columns take three 256-wide tiles).  They leave before the coefficient set-up;
+  // the barrier below counts the threads that are still alive (warp 0 -- the TMA issue and the row table -- never leaves).
+  if (gx >= D.pitch || y0 + rg * kPyRpt >= D.h) return;
   uint32_t coef[4];
   int off[4];
   int s0 = 0;
@@ -218,14 +228,13 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
     h[2] = __dp2a_lo(coef[2], cd, 0u) >> 4;
     h[3] = __dp2a_hi(coef[3], cd, 0u) >> 4;
   };
-  uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameStride + D.off + (size_t)(y0 + rg * 8) * D.pitch + gx;
+  uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameStride + D.off + (size_t)(y0 + rg * kPyRpt) * D.pitch + gx;
   size_t dpitch = (size_t)D.pitch;
   asm volatile("" : "+l"(dst), "+l"(dpitch));  // (keeps both in registers: the compiler otherwise rebuilds the address per row)
-  const bool colOk = gx < D.pitch;  // columns beyond the level's width land in the pitch padding (a multiple of 64 >= w)
   uint32_t ha[4], hb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const int ry = rg * 8 + j;
+  for (int j = 0; j < kPyRpt; j++) {
+    const int ry = rg * kPyRpt + j;
     const uint4 rw = s_row[ry];  // warp-uniform: one broadcast load
     if (rw.y & 0x80000000u) {    // warp-uniform branch
 #pragma unroll
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(256) k_pyramid_walk(const __grid_constant__ Or
     asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(out) : "r"(v[3]), "r"(v[2]));
     asm("mad.lo.u32 %0, %0, 256, %1;" : "+r"(out) : "r"(v[1]));
     asm("mad.lo.u32 %0, %0, 256, %1;" : "+r"(out) : "r"(v[0]));
-    if (colOk && y0 + ry < D.h) *reinterpret_cast<uint32_t*>(dst) = out;
+    if (y0 + ry < D.h) *reinterpret_cast<uint32_t*>(dst) = out;
     dst += dpitch;  // a running pointer: two adds per row instead of a 64-bit multiply-add chain
   }
 }
@@ -266,7 +275,7 @@ void launch_pyramid_level(const OrbGeo& g, const TmapIn& tm, int level, int fram
   if (fits) {
     dim3 grid((D.w + kPyW - 1) / kPyW, (D.h + kPyH - 1) / kPyH, nFrames);
     if (g_pyrOld) k_pyramid_tiled<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab, tileX, tileY);
-    else k_pyramid_walk<<<grid, 256, 0, st>>>(g, tm, level, frame0, pyr, xtab, ytab, tileX, tileY);
+    else k_pyramid_walk<<<grid, kPyThreads, 0, st>>>(g, tm, level, frame0, pyr, xtab, ytab, tileX, tileY);
   } else {
     dim3 grid((((D.w + 3) >> 2) + 255) / 256, D.h, nFrames);
     k_pyramid<<<grid, 256, 0, st>>>(g, level, pyr, xtab, ytab);
