@@ -431,6 +431,7 @@ int main(int argc, char** argv) {
   }
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
   for (pgb_comm* c : comms) pgb_comm_destroy(c);
+  const auto post0 = std::chrono::steady_clock::now();
 
   // ---- the sequential part: accumulate the per-pair flows into poses, cut segments where tracking was lost
   double pos[3] = {0, 0, 0}, heading = 0.0;
@@ -475,6 +476,8 @@ int main(int argc, char** argv) {
     fprintf(stderr, "I extract+match: %.3f s on %d GPU(s) = %.0f frames/s (per-rank seconds:", wall, N, src.frames / std::max(wall, 1e-9));
     for (int r = 0; r < N; r++) fprintf(stderr, " %.3f", ranks[r].seconds);
     fprintf(stderr, "); totals: %lld keypoints, %lld matches\n", (long long)total_kps, (long long)total_matches);
+    fprintf(stderr, "I trajectory post-processing + JSON: %.3f s\n",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - post0).count());
   }
   return EXIT_SUCCESS;
 }
