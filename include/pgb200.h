@@ -162,6 +162,12 @@ void* pgb_host_malloc_pinned(size_t bytes);
 void pgb_host_free_pinned(void* p);
 int pgb_memcpy_async(int device, void* dst, const void* src, size_t bytes, int kind, void* stream);
 int pgb_stream_synchronize(int device, void* stream);
+/* Completion markers for callers that keep several batches in flight on one stream: record behind a batch's copies,
+ * synchronize when the host needs that batch's results. */
+void* pgb_event_create(int device);
+int pgb_event_record(int device, void* event, void* stream);
+int pgb_event_synchronize(int device, void* event);
+void pgb_event_destroy(int device, void* event);
 
 /* ------------------------------------------------------------------ matcher -------------------------------- */
 /* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1651-1667) for n pairs of 32-byte descriptors (device or host
@@ -196,6 +202,14 @@ int pgb_match_by_projection(pgb_matcher*, int n_pairs, int cap, const pgb_keypoi
 int pgb_match_consecutive(pgb_matcher*, int n_pairs, int cap, const pgb_keypoint* kps, const uint8_t* desc,
                           const int32_t* counts, const float* flow, float max_x, float max_y, float th,
                           const float* scale_factors, int nlevels, int32_t* match_of_cur, int32_t* n_matches);
+
+/* What optical_trajectories' flow-tracking loop takes from a matched pair (the stand-in for the pose step of
+ * Tracking::TrackWithMotionModel, Tracking.cc:858-919): the median displacement cur - prev of the
+ * matched keypoints, per axis (element n/2 of the sorted displacements), and tracked = n_matches >= 20 (the threshold of
+ * Tracking.cc:884).  Pairs and arrays as in pgb_match_consecutive (its outputs are this call's inputs); flow_xy[pair][2],
+ * tracked[pair]; device buffers, asynchronous on `stream`; cap <= 2048. */
+int pgb_match_median_flow(int device, int n_pairs, int cap, const pgb_keypoint* kps, const int32_t* counts,
+                          const int32_t* match_of_cur, const int32_t* n_matches, float* flow_xy, int32_t* tracked, void* stream);
 
 /* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:407-522) for
  * n_pairs independent frame pairs: level-0 keypoints of F1 search a +-window_size window around prev_matched_xy in

@@ -52,6 +52,11 @@ _SIGS = {
                                      C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
     "pgb_frames_to_gray_rotated": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                              C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_size_t, C.c_size_t, vp]),
+    "pgb_match_median_flow": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "pgb_event_create": (vp, [C.c_int]),
+    "pgb_event_record": (C.c_int, [C.c_int, vp, vp]),
+    "pgb_event_synchronize": (C.c_int, [C.c_int, vp]),
+    "pgb_event_destroy": (None, [C.c_int, vp]),
     "pgb_video_open": (vp, [C.c_int, C.c_char_p]),
     "pgb_video_info": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "pgb_video_frame_span": (C.c_int, [vp, C.c_int64, vp, vp]),

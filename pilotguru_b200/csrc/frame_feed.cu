@@ -248,6 +248,31 @@ extern "C" int pgb_stream_synchronize(int device, void* stream) {
   PGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return PGB_OK;
 }
+// Completion markers for callers that keep several batches in flight on one stream (optical_trajectories): an event is
+// recorded behind a batch's device-to-host copies and waited for when the host needs that batch's results.
+extern "C" void* pgb_event_create(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) { fail(PGB_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { fail(PGB_ERR_CUDA, "cudaEventCreate failed"); return nullptr; }
+  return e;
+}
+extern "C" int pgb_event_record(int device, void* event, void* stream) {
+  if (!event) return fail(PGB_ERR_INVALID, "pgb_event_record: null event");
+  PGB_CUDA(cudaSetDevice(device));
+  PGB_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return PGB_OK;
+}
+extern "C" int pgb_event_synchronize(int device, void* event) {
+  if (!event) return fail(PGB_ERR_INVALID, "pgb_event_synchronize: null event");
+  PGB_CUDA(cudaSetDevice(device));
+  PGB_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+  return PGB_OK;
+}
+extern "C" void pgb_event_destroy(int device, void* event) {
+  if (!event) return;
+  cudaSetDevice(device);
+  cudaEventDestroy((cudaEvent_t)event);
+}
 extern "C" int pgb_device_count(void) {
   int n = 0;
   return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;

@@ -926,6 +926,56 @@ void fill_common(MatchArgs& A, int cap, float minX, float maxX, float minY, floa
 
 }  // namespace
 
+namespace pgb {
+// Median displacement of the matched keypoints of a frame pair (prev = frame p, cur = frame p + 1 of the per-frame
+// arrays): what the flow-tracking loop of optical_trajectories needs from a pair, computed where the matches are
+// instead of after a device-to-host copy of every keypoint.  The value is the element at index n / 2 of the sorted
+// displacements (std::nth_element in the host code this replaces), per axis: an element's rank is the number of elements
+// that are smaller, or equal with a lower index -- one pass of n comparisons per element, no sort.  One CTA per pair.
+constexpr int kFlowCap = 2048;
+__global__ void __launch_bounds__(256) k_median_flow(int cap, const pgb_keypoint* __restrict__ kps, const int32_t* __restrict__ counts,
+                                                     const int32_t* __restrict__ matchOfCur, const int32_t* __restrict__ nMatches,
+                                                     float* __restrict__ flow, int32_t* __restrict__ tracked) {
+  __shared__ float sx[kFlowCap], sy[kFlowCap];
+  __shared__ int sn;
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const pgb_keypoint* prevK = kps + (size_t)p * cap;
+  const pgb_keypoint* curK = kps + (size_t)(p + 1) * cap;
+  const int32_t* m = matchOfCur + (size_t)p * cap;
+  const int nCur = min(counts[p + 1], cap);
+  if (tid == 0) sn = 0;
+  __syncthreads();
+  // compaction in keypoint order is not needed: the median does not depend on the order of the elements
+  for (int t = tid; t < nCur; t += blockDim.x) {
+    const int q = m[t];
+    if (q >= 0) {
+      const int i = atomicAdd(&sn, 1);
+      sx[i] = __fsub_rn(curK[t].x, prevK[q].x);
+      sy[i] = __fsub_rn(curK[t].y, prevK[q].y);
+    }
+  }
+  __syncthreads();
+  const int n = sn, k = n / 2;
+  const bool ok = nMatches[p] >= 20 && n > 0;
+  if (tid == 0) tracked[p] = ok ? 1 : 0;
+  if (!ok) {
+    if (tid < 2) flow[2 * p + tid] = 0.f;
+    return;
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float vx = sx[i], vy = sy[i];
+    int rx = 0, ry = 0;
+    for (int j = 0; j < n; j++) {
+      const float ux = sx[j], uy = sy[j];
+      rx += (ux < vx) || (ux == vx && j < i);
+      ry += (uy < vy) || (uy == vy && j < i);
+    }
+    if (rx == k) flow[2 * p] = vx;      // ranks are a permutation: exactly one element per axis has rank k
+    if (ry == k) flow[2 * p + 1] = vy;
+  }
+}
+}  // namespace pgb
+
 extern "C" {
 
 pgb_matcher* pgb_matcher_create(int device, float nnratio, int check_orientation, int max_feats, int max_batch,
@@ -1034,6 +1084,18 @@ int pgb_match_consecutive(pgb_matcher* m, int n_pairs, int cap, const pgb_keypoi
   A.th = 2 * th;
   A.onlyIfBelow20 = 1;
   return launch_match(m, A, n_pairs);
+}
+
+int pgb_match_median_flow(int device, int n_pairs, int cap, const pgb_keypoint* kps, const int32_t* counts,
+                          const int32_t* match_of_cur, const int32_t* n_matches, float* flow_xy, int32_t* tracked, void* stream) {
+  if (n_pairs < 0 || cap <= 0 || cap > kFlowCap) return fail(PGB_ERR_INVALID, "pgb_match_median_flow: invalid argument (cap <= %d)", kFlowCap);
+  if (n_pairs == 0) return PGB_OK;
+  if (!kps || !counts || !match_of_cur || !n_matches || !flow_xy || !tracked)
+    return fail(PGB_ERR_INVALID, "pgb_match_median_flow: null buffer");
+  PGB_CUDA(cudaSetDevice(device));
+  k_median_flow<<<n_pairs, 256, 0, (cudaStream_t)stream>>>(cap, kps, counts, match_of_cur, n_matches, flow_xy, tracked);
+  PGB_CHECK_LAUNCH();
+  return PGB_OK;
 }
 
 int pgb_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist, int is_device, void* stream) {

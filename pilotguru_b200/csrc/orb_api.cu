@@ -14,6 +14,13 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
 int use_device(int device) {
+  // The capability check runs once per device: cudaGetDeviceProperties costs milliseconds (it queries the driver for
+  // every field), and entry points such as pgb_synth_frames / pgb_frames_to_gray come through here once per batch.
+  static std::atomic<unsigned long long> verified{0};
+  if (device >= 0 && device < 64 && (verified.load(std::memory_order_relaxed) >> device & 1ull)) {
+    PGB_CUDA(cudaSetDevice(device));
+    return PGB_OK;
+  }
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0)
@@ -21,10 +28,12 @@ int use_device(int device) {
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   if (device < 0 || device >= n) return fail(PGB_ERR_INVALID, "device %d out of range (have %d)", device, n);
   PGB_CUDA(cudaSetDevice(device));
-  cudaDeviceProp p;
-  PGB_CUDA(cudaGetDeviceProperties(&p, device));
-  if (p.major != 10)
-    return fail(PGB_ERR_CUDA, "device %d is sm_%d%d; libpgb200 is built for sm_100a only", device, p.major, p.minor);
+  int major = 0, minor = 0;
+  PGB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  PGB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10)
+    return fail(PGB_ERR_CUDA, "device %d is sm_%d%d; libpgb200 is built for sm_100a only", device, major, minor);
+  if (device < 64) verified.fetch_or(1ull << device, std::memory_order_relaxed);
   return PGB_OK;
 }
 

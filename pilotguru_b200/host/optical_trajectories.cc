@@ -190,63 +190,38 @@ struct Rank {
       fd = open(src->path.c_str(), O_RDONLY);
       PGB_CHECK(fd >= 0) << "cannot open " << src->path;
     }
-    // Two sets of pinned result buffers: while the GPU works on batch k + 1, a worker thread turns batch k's keypoints and
-    // matches into per-frame results (the median displacement of ~750 matches per pair costs the host ~40 us, as much as the
-    // GPU needs for the frame; done inline it held the GPU at a third of its rate).
+    // What the trajectory builder needs from a pair -- the median displacement of its matched keypoints -- is computed on
+    // the device (pgb_match_median_flow); a batch sends back 16 bytes per frame instead of every keypoint and match.  Two
+    // sets of pinned result buffers and an event each: batch k + 1 is issued before the host looks at batch k's results,
+    // so the stream never drains between batches.
+    float* dFlowOut = (float*)dalloc((size_t)B * 2 * sizeof(float));
+    int32_t* dTracked = (int32_t*)dalloc((size_t)B * sizeof(int32_t));
     struct HostSet {
-      pgb_keypoint* K; int32_t* N; int32_t* Match; int32_t* Nm;
-      int n = 0, first = 0; int64_t b0 = 0; bool busy = false;
+      int32_t* N; int32_t* Nm; float* Flow; int32_t* Tracked; void* ev;
+      int n = 0, first = 0; int64_t b0 = 0; bool pending = false;
     } hs[2];
     for (HostSet& h : hs) {
-      h.K = (pgb_keypoint*)pgb_host_malloc_pinned((size_t)(B + 1) * cap * sizeof(pgb_keypoint));
       h.N = (int32_t*)pgb_host_malloc_pinned((size_t)(B + 1) * sizeof(int32_t));
-      h.Match = (int32_t*)pgb_host_malloc_pinned((size_t)B * cap * sizeof(int32_t));
       h.Nm = (int32_t*)pgb_host_malloc_pinned((size_t)B * sizeof(int32_t));
-      PGB_CHECK(h.K && h.N && h.Match && h.Nm) << pgb_last_error();
+      h.Flow = (float*)pgb_host_malloc_pinned((size_t)B * 2 * sizeof(float));
+      h.Tracked = (int32_t*)pgb_host_malloc_pinned((size_t)B * sizeof(int32_t));
+      h.ev = pgb_event_create(device);
+      PGB_CHECK(h.N && h.Nm && h.Flow && h.Tracked && h.ev) << pgb_last_error();
     }
-
-    // median displacement of pair (prev slot p, cur slot p + 1) from host copies of keypoints and matches
-    std::vector<float> fx, fy;
-    auto finish_pair = [&](FrameResult& r, const pgb_keypoint* prevK, const pgb_keypoint* curK, int nCur, const int32_t* matchOf, int nMatch) {
-      r.n_matches = nMatch;
-      fx.clear(); fy.clear();
-      for (int t = 0; t < nCur; t++) {
-        const int q = matchOf[t];
-        if (q < 0) continue;
-        fx.push_back(curK[t].x - prevK[q].x);
-        fy.push_back(curK[t].y - prevK[q].y);
-      }
-      r.tracked = nMatch >= 20 && !fx.empty();
-      if (r.tracked) {
-        std::nth_element(fx.begin(), fx.begin() + fx.size() / 2, fx.end());
-        std::nth_element(fy.begin(), fy.begin() + fy.size() / 2, fy.end());
-        r.dx = fx[fx.size() / 2]; r.dy = fy[fy.size() / 2];
-      }
-    };
     auto finish_set = [&](HostSet& h) {
+      PGB_CALL(pgb_event_synchronize(device, h.ev));
       for (int i = 0; i < h.n; i++) {  // frame i of the batch sits in slot i + 1; its pair (slot i, slot i + 1) is matched pair i - first
         FrameResult& r = out[h.b0 + i];
         r.n_kps = h.N[i + 1];
-        if (i >= h.first) finish_pair(r, h.K + (size_t)i * cap, h.K + (size_t)(i + 1) * cap, h.N[i + 1], h.Match + (size_t)(i - h.first) * cap, h.Nm[i - h.first]);
+        if (i >= h.first) {
+          const int p = i - h.first;
+          r.n_matches = h.Nm[p];
+          r.tracked = h.Tracked[p] != 0;
+          if (r.tracked) { r.dx = h.Flow[2 * p]; r.dy = h.Flow[2 * p + 1]; }
+        }
       }
+      h.pending = false;
     };
-    std::mutex mu;
-    std::condition_variable cv;
-    int pending = -1;  // set handed to the worker, -1 = none, -2 = quit
-    std::thread worker([&] {
-      for (;;) {
-        std::unique_lock<std::mutex> l(mu);
-        cv.wait(l, [&] { return pending != -1; });
-        if (pending == -2) return;
-        HostSet& h = hs[pending];
-        pending = -1;
-        l.unlock();
-        finish_set(h);
-        l.lock();
-        h.busy = false;
-        cv.notify_all();
-      }
-    });
 
     const auto wall0 = std::chrono::steady_clock::now();
     bool have_prev = false;
@@ -254,10 +229,9 @@ struct Rank {
     for (int64_t b0 = t0; b0 < t1; b0 += B, k++) {
       const int n = (int)std::min<int64_t>(B, t1 - b0);
       HostSet& h = hs[k & 1];
-      {
-        std::unique_lock<std::mutex> l(mu);
-        cv.wait(l, [&] { return !h.busy; });  // the worker is done with this set (two batches ago)
-      }
+      if (h.pending) finish_set(h);  // the batch before last: its results have long arrived
+      // host-resident sources refill one pinned input buffer: the previous batch's upload must have left it
+      if (hRaw && hs[(k + 1) & 1].pending) PGB_CALL(pgb_event_synchronize(device, hs[(k + 1) & 1].ev));
       // ---- frames -> gray on the device -> features in slots 1..n
       if (src->kind == Source::kAvi) {
         // decode (nvJPEG) -> RGB24 on the device -> cv::flip + cvtColor (pgb_frames_to_gray: the decoder hands out RGB order,
@@ -287,34 +261,25 @@ struct Rank {
       if (np > 0)
         PGB_CALL(pgb_match_consecutive(matcher, np, cap, dK + (size_t)first * cap, dD + (size_t)first * cap * 32, dN + first, dFlow,
                                        (float)W, (float)H, 15.f, sf.data(), cfg->nlevels, dMatch, dNm));
+      if (np > 0)
+        PGB_CALL(pgb_match_median_flow(device, np, cap, dK + (size_t)first * cap, dN + first, dMatch, dNm, dFlowOut, dTracked, st));
       PGB_CALL(pgb_memcpy_async(device, h.N, dN, (size_t)(n + 1) * sizeof(int32_t), 1, st));
-      PGB_CALL(pgb_memcpy_async(device, h.K, dK, (size_t)(n + 1) * cap * sizeof(pgb_keypoint), 1, st));
       if (np > 0) {
-        PGB_CALL(pgb_memcpy_async(device, h.Match, dMatch, (size_t)np * cap * sizeof(int32_t), 1, st));
         PGB_CALL(pgb_memcpy_async(device, h.Nm, dNm, (size_t)np * sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, h.Flow, dFlowOut, (size_t)np * 2 * sizeof(float), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, h.Tracked, dTracked, (size_t)np * sizeof(int32_t), 1, st));
       }
       // slot 0 <- this batch's last frame, for the next batch (stream-ordered after the copies above)
       PGB_CALL(pgb_frame_record_pack(dK, dD, dN, n, cap, dLastRec, st));
       PGB_CALL(pgb_frame_record_unpack(dLastRec, dK, dD, dN, 0, cap, st));
-      PGB_CALL(pgb_orb_check(orb));  // synchronises the stream, surfaces device-side capacity flags
-      h.n = n; h.first = first; h.b0 = b0;
-      {
-        std::unique_lock<std::mutex> l(mu);
-        cv.wait(l, [&] { return pending == -1; });
-        h.busy = true;
-        pending = k & 1;
-        cv.notify_all();
-      }
+      PGB_CALL(pgb_event_record(device, h.ev, st));
+      h.n = n; h.first = first; h.b0 = b0; h.pending = true;
       have_prev = true;
     }
-    {
-      std::unique_lock<std::mutex> l(mu);
-      cv.wait(l, [&] { return pending == -1 && !hs[0].busy && !hs[1].busy; });
-      pending = -2;
-      cv.notify_all();
-    }
-    worker.join();
-    pgb_keypoint* hK = hs[0].K; int32_t* hN = hs[0].N; int32_t* hMatch = hs[0].Match; int32_t* hNm = hs[0].Nm;
+    for (int q = 0; q < 2; q++)
+      if (hs[(k + q) & 1].pending) finish_set(hs[(k + q) & 1]);  // the older of the two first
+    PGB_CALL(pgb_orb_check(orb));  // synchronises the stream, surfaces device-side capacity flags of every batch
+    int32_t* hN = hs[0].N; int32_t* hNm = hs[0].Nm; float* hFlow = hs[0].Flow; int32_t* hTracked = hs[0].Tracked;
     // ---- block boundary: ONE all-gather of every rank's last-frame record; rank r > 0 matches its first frame against
     //      the left neighbour's last frame
     if (comm) {
@@ -324,12 +289,16 @@ struct Rank {
         PGB_CALL(pgb_frame_record_unpack(dAllRec + (size_t)(rank - 1) * recBytes, dK, dD, dN, 0, cap, st));
         PGB_CALL(pgb_frame_record_unpack(dFirstRec, dK, dD, dN, 1, cap, st));
         PGB_CALL(pgb_match_consecutive(matcher, 1, cap, dK, dD, dN, dFlow, (float)W, (float)H, 15.f, sf.data(), cfg->nlevels, dMatch, dNm));
+        PGB_CALL(pgb_match_median_flow(device, 1, cap, dK, dN, dMatch, dNm, dFlowOut, dTracked, st));
         PGB_CALL(pgb_memcpy_async(device, hN, dN, 2 * sizeof(int32_t), 1, st));
-        PGB_CALL(pgb_memcpy_async(device, hK, dK, (size_t)2 * cap * sizeof(pgb_keypoint), 1, st));
-        PGB_CALL(pgb_memcpy_async(device, hMatch, dMatch, (size_t)cap * sizeof(int32_t), 1, st));
         PGB_CALL(pgb_memcpy_async(device, hNm, dNm, sizeof(int32_t), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, hFlow, dFlowOut, 2 * sizeof(float), 1, st));
+        PGB_CALL(pgb_memcpy_async(device, hTracked, dTracked, sizeof(int32_t), 1, st));
         PGB_CALL(pgb_orb_check(orb));
-        finish_pair(out[t0], hK, hK + cap, hN[1], hMatch, hNm[0]);
+        FrameResult& r = out[t0];
+        r.n_matches = hNm[0];
+        r.tracked = hTracked[0] != 0;
+        if (r.tracked) { r.dx = hFlow[0]; r.dy = hFlow[1]; }
       } else {
         PGB_CALL(pgb_stream_synchronize(device, st));
       }
@@ -339,9 +308,9 @@ struct Rank {
     pgb_video_close(video);
     pgb_device_free(device, dRgb);
     pgb_host_free_pinned(hRaw);
-    for (HostSet& h : hs) { pgb_host_free_pinned(h.K); pgb_host_free_pinned(h.N); pgb_host_free_pinned(h.Match); pgb_host_free_pinned(h.Nm); }
+    for (HostSet& h : hs) { pgb_host_free_pinned(h.N); pgb_host_free_pinned(h.Nm); pgb_host_free_pinned(h.Flow); pgb_host_free_pinned(h.Tracked); pgb_event_destroy(device, h.ev); }
     for (void* p : {(void*)dK, (void*)dD, (void*)dN, (void*)dMatch, (void*)dNm, (void*)dFlow, (void*)dGray, (void*)dFirstRec, (void*)dLastRec,
-                    (void*)dAllRec, (void*)dCanvas})
+                    (void*)dAllRec, (void*)dCanvas, (void*)dFlowOut, (void*)dTracked})
       pgb_device_free(device, p);
     pgb_matcher_destroy(matcher);
     pgb_orb_destroy(orb);
