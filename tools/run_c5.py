@@ -35,6 +35,7 @@ ap.add_argument("--compare-one-gpu", action="store_true", help="also run optical
 ap.add_argument("--work", default="/tmp/pgb_c5")
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "c5_summary.json"))
 ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--fit-gpus", type=int, default=1, help="devices fit_motion shards its windows over")
 args = ap.parse_args()
 
 HOST = os.path.join(ROOT, "pilotguru_b200", "host")
@@ -45,9 +46,14 @@ summary = {"config": f"{args.minutes:g} min, {n_frames} frames 1920x1080 @ {args
            "stages_s": {}}
 
 
-def run(name, cmd):
+def run(name, cmd, n_gpus=None):
+    """n_gpus: the devices the binary uses.  The process is shown only those (CUDA_VISIBLE_DEVICES): the driver initialises
+    every VISIBLE device when a process starts (measured on the 8-GPU box: ~6 s for a binary that then works 1 s on one GPU)."""
     t0 = time.time()
-    p = subprocess.run(cmd, capture_output=True, text=True)
+    env = dict(os.environ)
+    if n_gpus is not None:
+        env["CUDA_VISIBLE_DEVICES"] = ",".join(str(i) for i in range(n_gpus))
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env)
     dt = time.time() - t0
     summary["stages_s"][name] = round(dt, 3)
     if p.returncode != 0:
@@ -73,7 +79,7 @@ def optical(n_gpus, sub):
     for f in os.listdir(out):
         os.remove(os.path.join(out, f))
     p = run(f"optical_trajectories ({n_gpus} GPU)", [os.path.join(HOST, "optical_trajectories"), "--vocabulary_file=unused", "--camera_settings", settings,
-                                                    "--out_dir", out, "--in_video=" + spec, f"--num_gpus={n_gpus}", f"--batch={args.batch}", "--logtostderr"])
+                                                    "--out_dir", out, "--in_video=" + spec, f"--num_gpus={n_gpus}", f"--batch={args.batch}", "--logtostderr"], n_gpus)
     line = [l for l in p.stderr.splitlines() if "extract+match:" in l][-1]
     return out, line
 
@@ -109,14 +115,16 @@ if not args.only_frames:
     json.dump({"frames": [{"frame_id": i, "time_usec": int(round(i * 1e6 / args.fps)) + 137} for i in range(n_frames)]}, open(frames_json, "w"))
     summary["stages_s"]["generate IMU/GPS/frames JSON (python)"] = round(time.time() - t0, 3)
     vel, steer, fwd = (os.path.join(args.work, n) for n in ("velocities.json", "steering.json", "forward.json"))
-    run(f"fit_motion ({args.gpus} GPU)", [os.path.join(HOST, "fit_motion"), "--rotations_json", paths["rotations"], "--accelerations_json", paths["accelerations"],
+    # the calibration of a 30-minute drive is 2 ms of kernels: one GPU (BASELINE configs[3] names one), so that the process
+    # pays for one context instead of eight (--fit-gpus N shards the windows anyway)
+    run(f"fit_motion ({args.fit_gpus} GPU)", [os.path.join(HOST, "fit_motion"), "--rotations_json", paths["rotations"], "--accelerations_json", paths["accelerations"],
                                          "--locations_json", paths["locations"], "--velocities_out_json", vel, "--steering_out_json", steer,
-                                         "--forward_axis_out_json", fwd, f"--num_gpus={args.gpus}"])
+                                         "--forward_axis_out_json", fwd, f"--num_gpus={args.fit_gpus}"], args.fit_gpus)
     fv, fs = os.path.join(args.work, "frame_velocities.json"), os.path.join(args.work, "frame_steering.json")
     run("annotate_frames (velocity)", [os.path.join(HOST, "annotate_frames"), "--frames_json", frames_json, "--in_json", vel,
-                                       "--json_root_element_name=velocities", "--json_value_name=speed_m_s", "--out_json", fv])
+                                       "--json_root_element_name=velocities", "--json_value_name=speed_m_s", "--out_json", fv], 1)
     run("annotate_frames (steering)", [os.path.join(HOST, "annotate_frames"), "--frames_json", frames_json, "--in_json", steer,
-                                       "--json_root_element_name=steering", "--json_value_name=angular_velocity", "--out_json", fs])
+                                       "--json_root_element_name=steering", "--json_value_name=angular_velocity", "--out_json", fs], 1)
     jv, js = json.load(open(fv)), json.load(open(fs))
     lv, ls = jv[next(iter(jv))], js[next(iter(js))]
     summary["frames_with_velocity"] = len(lv)
