@@ -146,6 +146,26 @@ class ORBmatcher:
                                           th, np_ptr(sf), len(sf), match_ptr, nmatch_ptr))
 
 
+def median_flow(kps, counts, match_of_cur, n_matches, device: int = 0):
+    """pgb_match_median_flow for host arrays: kps (n_pairs + 1, cap) KP_DTYPE, counts (n_pairs + 1,), match_of_cur (n_pairs, cap),
+    n_matches (n_pairs,) -> (flow (n_pairs, 2) float32, tracked (n_pairs,) bool).  The per-pair quantity optical_trajectories'
+    flow-tracking loop needs: element n/2 of the sorted displacements cur - prev of the matched keypoints, per axis."""
+    import torch
+    dev = f"cuda:{device}"
+    k = torch.from_numpy(np.ascontiguousarray(kps).view(np.uint8)).to(dev)
+    c = torch.from_numpy(np.ascontiguousarray(counts, np.int32)).to(dev)
+    m = torch.from_numpy(np.ascontiguousarray(match_of_cur, np.int32)).to(dev)
+    nm = torch.from_numpy(np.ascontiguousarray(n_matches, np.int32)).to(dev)
+    n_pairs, cap = match_of_cur.shape
+    flow = torch.zeros((n_pairs, 2), dtype=torch.float32, device=dev)
+    tracked = torch.zeros(n_pairs, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(device)
+    check(lib().pgb_match_median_flow(device, n_pairs, cap, k.data_ptr(), c.data_ptr(), m.data_ptr(), nm.data_ptr(), flow.data_ptr(),
+                                      tracked.data_ptr(), st.cuda_stream))
+    st.synchronize()
+    return flow.cpu().numpy(), tracked.cpu().numpy().astype(bool)
+
+
 def featvec_csr(fv):
     """DBoW2::FeatureVector as (node_ids u32 ascending, starts i32 [nodes + 1], indices u32)."""
     if isinstance(fv, dict):

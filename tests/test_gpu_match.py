@@ -255,3 +255,36 @@ def test_search_by_bow_matches_oracle():
     with pytest.raises(PgbError):
         m.SearchByBoW(P["kf_desc"], P["kf_angle"], P["kf_has"], P["kf_fv"], P["f_desc"], P["f_angle"], bad)
     m.close()
+
+
+def test_median_flow_equals_nth_element():
+    """pgb_match_median_flow against the host code it replaced in optical_trajectories (std::nth_element at index n / 2 of the
+    displacements of the matched keypoints, per axis; tracked = at least 20 matches): random match tables incl. duplicated
+    displacements, pairs below the threshold, a pair without matches and a full table."""
+    from pilotguru_b200._lib import KP_DTYPE
+    from pilotguru_b200.matcher import median_flow
+    rng = np.random.default_rng(77)
+    cap, n_pairs = 1033, 9
+    kps = np.zeros((n_pairs + 1, cap), KP_DTYPE)
+    kps["x"] = rng.integers(0, 1920, kps.shape).astype(np.float32) * np.float32(1.2)     # quantised: many equal displacements
+    kps["y"] = rng.random(kps.shape).astype(np.float32) * 1080
+    counts = rng.integers(600, cap + 1, n_pairs + 1).astype(np.int32)
+    counts[3] = cap
+    match = np.full((n_pairs, cap), -1, np.int32)
+    nm = np.zeros(n_pairs, np.int32)
+    for p in range(n_pairs):
+        want = [700, 19, 20, 0, 1000, 33, 512, 21, 5][p]
+        want = min(want, counts[p + 1], counts[p])
+        cur = rng.choice(counts[p + 1], want, replace=False)
+        match[p, cur] = rng.choice(counts[p], want, replace=False)
+        nm[p] = want
+    flow, tracked = median_flow(kps, counts, match, nm)
+    for p in range(n_pairs):
+        t = np.nonzero(match[p, :counts[p + 1]] >= 0)[0]
+        assert tracked[p] == (nm[p] >= 20 and len(t) > 0)
+        if tracked[p]:
+            q = match[p, t]
+            fx = np.sort(kps["x"][p + 1, t] - kps["x"][p, q]); fy = np.sort(kps["y"][p + 1, t] - kps["y"][p, q])
+            assert flow[p, 0] == fx[len(fx) // 2] and flow[p, 1] == fy[len(fy) // 2], p
+        else:
+            assert flow[p, 0] == 0 and flow[p, 1] == 0
