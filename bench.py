@@ -468,7 +468,7 @@ def main():
     # would drive the two handles.  Step k extracts into region k & 1 and waits for the matcher to be done with that region
     # (step k - 2); at N > 1 the boundary exchange (pack, ONE all-gather, unpack) sits on the matcher stream in front of the
     # match.  Results are identical to the serial step (checked below).
-    mstream = torch.cuda.Stream()
+    mstream = torch.cuda.Stream(priority=-1)   # the latency-bound matcher kernels get their CTAs scheduled ahead of the throughput kernels they run under
     mtM = ORBmatcher(0.9, True, max_feats=cap, max_batch=B, device=local, stream=mstream.cuda_stream)
     xchB = FeatureExchange(1, 0, B, cap, device=torch.device("cuda", local))
     ex.extract_ptr(pred.data_ptr(), 3, 1, W, H, W, W * H, xchB.kps_ptr(0), xchB.desc_ptr(0), xchB.counts_ptr(0), cap)

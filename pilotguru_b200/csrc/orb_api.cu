@@ -97,6 +97,10 @@ struct pgb_orb {
   // fused FAST kernel: the small launches (5-band and generic tiles) run on a side stream next to the main one
   cudaStream_t fcSide = nullptr;
   cudaEvent_t evFcFork = nullptr, evFcJoin = nullptr;
+  // octree kernel (one long-lived, latency-bound CTA per level and frame): on a HIGH-PRIORITY side stream, so that with
+  // several handles in flight its CTAs are placed ahead of another handle's throughput kernels instead of behind them
+  cudaStream_t octSide = nullptr;
+  cudaEvent_t evOctFork = nullptr, evOctJoin = nullptr;
   cudaEvent_t evChunk[16] = {};
   int h2dChunk = 16;  // largest H2D/compute pipeline chunk in frames (PGB_H2D_CHUNK)
   int h2dMinChunk = 4;  // smallest chunk of the ramp-down at the end of a batch (PGB_H2D_MIN_CHUNK)
@@ -473,7 +477,17 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         launch_cells(g, n, o->cellTab.p, score, slots, cellCnt, o->err.p, st);
         if (f0 == 0 && n == o->curFrames) o->scoreValid = true;
         break;
-      case 3: launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, st); break;
+      case 3:
+        if (o->octSide) {
+          PGB_CUDA(cudaEventRecord(o->evOctFork, st));
+          PGB_CUDA(cudaStreamWaitEvent(o->octSide, o->evOctFork, 0));
+          launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, o->octSide);
+          PGB_CUDA(cudaEventRecord(o->evOctJoin, o->octSide));
+          PGB_CUDA(cudaStreamWaitEvent(st, o->evOctJoin, 0));
+        } else {
+          launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, st);
+        }
+        break;
       case 4:
         launch_orient_desc(g, n, pyr, staged, lvlCnt, kps + (size_t)f0 * cap, desc + (size_t)f0 * cap * 32, counts + f0,
                            cap, o->err.p, st);
@@ -628,6 +642,14 @@ pgb_orb* pgb_orb_create(int device, int nfeatures, float scale_factor, int nleve
     if (cudaStreamCreateWithFlags(&o->auxStream[a], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&o->evAux[a], cudaEventDisableTiming) != cudaSuccess)
       return bail("cudaStreamCreate/cudaEventCreate failed");
+  if (!getenv("PGB_OCT_NO_SIDE")) {
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&o->octSide, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&o->evOctFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&o->evOctJoin, cudaEventDisableTiming) != cudaSuccess)
+      return bail("cudaStreamCreateWithPriority/cudaEventCreate failed");
+  }
   if (!getenv("PGB_FC_NO_SIDE") &&
       (cudaStreamCreateWithFlags(&o->fcSide, cudaStreamNonBlocking) != cudaSuccess ||
        cudaEventCreateWithFlags(&o->evFcFork, cudaEventDisableTiming) != cudaSuccess ||
@@ -670,6 +692,9 @@ void pgb_orb_destroy(pgb_orb* o) {
       if (o->fcSide) { cudaStreamSynchronize(o->fcSide); cudaStreamDestroy(o->fcSide); }
       if (o->evFcFork) cudaEventDestroy(o->evFcFork);
       if (o->evFcJoin) cudaEventDestroy(o->evFcJoin);
+      if (o->octSide) { cudaStreamSynchronize(o->octSide); cudaStreamDestroy(o->octSide); }
+      if (o->evOctFork) cudaEventDestroy(o->evOctFork);
+      if (o->evOctJoin) cudaEventDestroy(o->evOctJoin);
     }
   }
   for (int k = 0; k < kMaxChunkEvents; k++)
