@@ -70,3 +70,42 @@ def test_truncated_and_foreign_files_are_refused_or_cut(tmp_path, golden_dir):
     cut = video.VideoImageSequenceSource(str(p))
     assert cut.n_frames == 3
     cut.close()
+
+
+def _chunk(cc, body):
+    return cc + struct.pack("<I", len(body)) + body + (b"\x00" if len(body) & 1 else b"")
+
+
+def test_rec_lists_second_stream_and_opendml_segments(tmp_path, golden_dir):
+    """Container shapes the fixture does not have, rebuilt around its JPEG frames: an audio stream in FRONT of the video stream
+    (the frames are then '01dc' chunks: VideoStreamIndexOrDie picks the first VIDEO stream, image_sequence_reader.cc:63-71),
+    frames grouped in 'rec ' lists, an empty chunk (a dropped frame) and a second RIFF 'AVIX' segment (OpenDML) with more frames."""
+    d = open(os.path.join(golden_dir, "mjpeg_256x192.avi"), "rb").read()
+    spans = []
+    _walk(d, 0, len(d), spans)
+    jpegs = [d[o:o + s] for o, s in spans]
+    avih = struct.pack("<14I", 40000, 0, 0, 0x10, 6, 0, 2, 0, 256, 192, 0, 0, 0, 0)
+    auds = _chunk(b"strh", b"auds" + bytes(4) + struct.pack("<10I", 0, 0, 0, 1, 8000, 0, 0, 0, 0, 0) + bytes(8)) + _chunk(b"strf", bytes(18))
+    vids = _chunk(b"strh", b"vids" + b"MJPG" + struct.pack("<10I", 0, 0, 0, 1001, 30000, 0, 6, 0, 0, 0) + bytes(8)) + \
+        _chunk(b"strf", struct.pack("<IiiHH4sIiiII", 40, 256, 192, 1, 24, b"MJPG", 256 * 192 * 3, 0, 0, 0, 0))
+    hdrl = _chunk(b"LIST", b"hdrl" + _chunk(b"avih", avih) + _chunk(b"LIST", b"strl" + auds) + _chunk(b"LIST", b"strl" + vids))
+    rec0 = _chunk(b"LIST", b"rec " + _chunk(b"00wb", bytes(31)) + _chunk(b"01dc", jpegs[0]) + _chunk(b"01dc", b""))
+    rec1 = _chunk(b"LIST", b"rec " + _chunk(b"01dc", jpegs[1]) + _chunk(b"00wb", bytes(8)) + _chunk(b"01db", jpegs[2]))
+    movi0 = _chunk(b"LIST", b"movi" + rec0 + rec1)
+    seg0 = _chunk(b"RIFF", b"AVI " + hdrl + _chunk(b"JUNK", bytes(13)) + movi0 + _chunk(b"idx1", bytes(32)))
+    seg1 = _chunk(b"RIFF", b"AVIX" + _chunk(b"LIST", b"movi" + _chunk(b"01dc", jpegs[3]) + _chunk(b"01dc", jpegs[4])))
+    p = tmp_path / "shapes.avi"
+    p.write_bytes(seg0 + seg1)
+    src = video.VideoImageSequenceSource(str(p))
+    assert src.n_frames == 5 and (src.width, src.height) == (256, 192) and abs(src.fps - 30000 / 1001) < 1e-12
+    blob = p.read_bytes()
+    for i in range(5):
+        off, size = src.frame_span(i)
+        assert blob[off:off + size] == jpegs[i], i
+    src.close()
+    # no video stream at all: the reference's "Inspected all the streams, but no video stream found"
+    only_audio = _chunk(b"RIFF", b"AVI " + _chunk(b"LIST", b"hdrl" + _chunk(b"avih", avih) + _chunk(b"LIST", b"strl" + auds)) + _chunk(b"LIST", b"movi" + _chunk(b"00wb", bytes(16))))
+    q = tmp_path / "audio.avi"
+    q.write_bytes(only_audio)
+    with pytest.raises(PgbError, match="no video stream found"):
+        video.VideoImageSequenceSource(str(q))
