@@ -698,6 +698,18 @@ def main():
     torch.cuda.synchronize()
     for st_ in sets:
         st_.h_counts = st_.h_nmatch = st_.h_kps = st_.h_desc = st_.h_match = None
+    # BASELINE configs[1] as the reference calls it: ONE 1080p frame through ORBextractor::operator() with host arrays in and out
+    # (upload, seven pyramid launches, FAST, octree, descriptors, download of keypoints + descriptors); wall clock, median of 20
+    single_us = None
+    if rank == 0:
+        one = np.ascontiguousarray(frames_np[0])
+        lat = []
+        for i in range(23):
+            t0_ = time.perf_counter()
+            k1_, d1_ = ex(one)
+            lat.append(time.perf_counter() - t0_)
+        single_us = 1e6 * float(np.median(lat[3:]))
+        assert len(k1_) == int(cnt_dev[1]), "single-frame call and batched call disagree on frame 0"
     s0 = st_ = host_frames = None
     import gc
     gc.collect()
@@ -749,7 +761,8 @@ def main():
                              "us_per_launch": stage_us["fast_cells"] * B,
                              "unfused_pair_us_per_frame": unfused_us},
                 "stage_us_per_frame": stage_us,
-                "keypoints_per_frame": float(cnt_dev[1:].mean()), "matches_per_frame": float(nm_dev.mean())}
+                "keypoints_per_frame": float(cnt_dev[1:].mean()), "matches_per_frame": float(nm_dev.mean()),
+                "single_frame_call_us": single_us}
         line["parity_checked"] = parity["checked"]
         line["parity"] = parity
         if not args.no_cpu_baseline and world == 1:
