@@ -28,9 +28,33 @@
 #include <mutex>
 #include <vector>
 
+#include "../../include/pgb200_jpeg_std_dht.h"
 #include "common.cuh"
 
 namespace {
+
+// The typical Huffman tables of ITU-T T.81 Annex K.3 as DHT segments: Motion-JPEG frames in AVI files may omit theirs
+// ("AVI1" frames of capture hardware; libavcodec's mjpeg decoder falls back to these tables as well).
+const unsigned char kStdDht[PGB200_JPEG_STD_DHT_BYTES] = PGB200_JPEG_STD_DHT_INIT;
+
+// Offset of the first SOS marker of a JPEG image and whether a DHT segment precedes it; false if the header is malformed.
+bool jpeg_header_scan(const uint8_t* j, size_t n, size_t* sosAt, bool* hasDht) {
+  if (n < 4 || j[0] != 0xFF || j[1] != 0xD8) return false;
+  size_t i = 2;
+  *hasDht = false;
+  while (i + 4 <= n) {
+    if (j[i] != 0xFF) return false;
+    const uint8_t m = j[i + 1];
+    if (m == 0xFF) { i++; continue; }                                   // fill byte
+    if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { i += 2; continue; }  // markers without a length
+    if (m == 0xDA) { *sosAt = i; return true; }
+    if (m == 0xC4) *hasDht = true;
+    const size_t len = ((size_t)j[i + 2] << 8) | j[i + 3];
+    if (len < 2) return false;
+    i += 2 + len;
+  }
+  return false;
+}
 
 struct NvjpegApi {
   nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t*) = nullptr;
@@ -227,20 +251,27 @@ extern "C" int pgb_video_read_rgb(pgb_video* v, int64_t first_frame, int n_frame
   // the previous call's bitstreams may still be in use by its decode: drain the stream before they are replaced
   PGB_CUDA(cudaStreamSynchronize(s));
   size_t total = 0;
-  for (int i = 0; i < n_frames; i++) total += v->frames[(size_t)(first_frame + i)].size;
+  for (int i = 0; i < n_frames; i++) total += v->frames[(size_t)(first_frame + i)].size + sizeof kStdDht;  // room for inserted tables
   v->bits.resize(total);
   size_t at = 0;
   NvtxRange range("pgb:video:mjpeg_decode");
   for (int i = 0; i < n_frames; i++) {
     const pgb_video::Frame& f = v->frames[(size_t)(first_frame + i)];
     uint8_t* b = v->bits.data() + at;
-    at += f.size;
     if (!pread_all(v->fd, b, f.size, f.off)) return fail(PGB_ERR_INVALID, "%s: short read of frame %lld", v->path.c_str(), (long long)(first_frame + i));
+    size_t fsize = f.size, sosAt = 0;
+    bool hasDht = false;
+    if (jpeg_header_scan(b, fsize, &sosAt, &hasDht) && !hasDht) {  // a frame without Huffman tables: the standard ones go in front of its scan
+      memmove(b + sosAt + sizeof kStdDht, b + sosAt, fsize - sosAt);
+      memcpy(b + sosAt, kStdDht, sizeof kStdDht);
+      fsize += sizeof kStdDht;
+    }
+    at += f.size + sizeof kStdDht;
     int comps = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
     nvjpegChromaSubsampling_t sub;
-    nvjpegStatus_t r = nj->GetImageInfo(v->nj, b, f.size, &comps, &sub, ws, hs);
+    nvjpegStatus_t r = nj->GetImageInfo(v->nj, b, fsize, &comps, &sub, ws, hs);
     if (r != NVJPEG_STATUS_SUCCESS)
-      return fail(PGB_ERR_INVALID, "%s: frame %lld is not a JPEG image nvJPEG can parse (status %d; Motion-JPEG frames without their own Huffman tables are not supported)",
+      return fail(PGB_ERR_INVALID, "%s: frame %lld is not a JPEG image nvJPEG can parse (status %d)",
                   v->path.c_str(), (long long)(first_frame + i), (int)r);
     if (ws[0] != v->width || hs[0] != v->height)
       return fail(PGB_ERR_INVALID, "%s: frame %lld is %dx%d, the stream header says %dx%d", v->path.c_str(), (long long)(first_frame + i), ws[0], hs[0],
@@ -249,7 +280,7 @@ extern "C" int pgb_video_read_rgb(pgb_video* v, int64_t first_frame, int n_frame
     memset(&out, 0, sizeof out);
     out.channel[0] = rgb_dev + (size_t)i * frame_stride;
     out.pitch[0] = pitch;
-    r = nj->Decode(v->nj, v->st, b, f.size, NVJPEG_OUTPUT_RGBI, &out, s);
+    r = nj->Decode(v->nj, v->st, b, fsize, NVJPEG_OUTPUT_RGBI, &out, s);
     if (r != NVJPEG_STATUS_SUCCESS) return fail(PGB_ERR_CUDA, "%s: nvjpegDecode failed on frame %lld (status %d)", v->path.c_str(), (long long)(first_frame + i), (int)r);
     // av_frame_get_best_effort_timestamp * av_q2d(time_base) (:153-155): an AVI video stream's time base is dwScale / dwRate
     // and the pts of frame k is k

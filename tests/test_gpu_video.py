@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from pilotguru_b200 import video
+from pilotguru_b200 import synth, video
 from pilotguru_b200.orb import ORBextractor
 
 pytestmark = pytest.mark.gpu
@@ -88,3 +88,52 @@ def test_optical_trajectories_reads_a_motion_jpeg_file(tmp_path, golden_dir):
     assert [e["time_usec"] for e in a["trajectory"]] == [int(round(i * 1e6 / 25.0)) for i in range(5)]      # the container's 25 fps
     assert [e["time_usec"] for e in r["trajectory"]] == [int(round(i * 1e6 / 30.0)) for i in range(5)]      # Camera_fps for raw frames
     assert [e["pose"] for e in a["trajectory"]] == [e["pose"] for e in r["trajectory"]] and a["plane"] == r["plane"]
+
+
+def test_frames_without_huffman_tables_get_the_standard_ones(tmp_path):
+    """Capture hardware writes Motion-JPEG frames without DHT segments ("AVI1"): the decoder must put the typical tables of
+    ITU-T T.81 Annex K.3 in front of the scan, as libavcodec's mjpeg decoder does.  Frames are encoded here with those tables
+    (libjpeg's defaults, optimisation off), their DHT segments are cut out, the rest goes into an AVI: the decode must equal the
+    decode of the untouched frames (same decoder, same coefficients: bit for bit)."""
+    import struct
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    w, h, n = 160, 120, 3
+
+    def chunk(cc, body):
+        return cc + struct.pack("<I", len(body)) + body + (b"\x00" if len(body) & 1 else b"")
+
+    def avi(frames):
+        avih = struct.pack("<14I", 40000, 0, 0, 0x10, len(frames), 0, 1, 0, w, h, 0, 0, 0, 0)
+        vids = chunk(b"strh", b"vids" + b"MJPG" + struct.pack("<10I", 0, 0, 0, 1, 25, 0, len(frames), 0, 0, 0) + bytes(8)) + \
+            chunk(b"strf", struct.pack("<IiiHH4sIiiII", 40, w, h, 1, 24, b"MJPG", w * h * 3, 0, 0, 0, 0))
+        hdrl = chunk(b"LIST", b"hdrl" + chunk(b"avih", avih) + chunk(b"LIST", b"strl" + vids))
+        return chunk(b"RIFF", b"AVI " + hdrl + chunk(b"LIST", b"movi" + b"".join(chunk(b"00dc", f) for f in frames)))
+
+    def strip_dht(j):
+        out, i = bytearray(j[:2]), 2
+        while j[i + 1] != 0xDA:
+            L = struct.unpack(">H", j[i + 2:i + 4])[0]
+            if j[i + 1] != 0xC4:
+                out += j[i:i + 2 + L]
+            i += 2 + L
+        return bytes(out + j[i:])
+
+    full = []
+    for t in range(n):
+        img = np.clip(synth.frame(t, w=w, h=h)[..., None].astype(np.int32) + rng.integers(-20, 20, (h, w, 3)), 0, 255).astype(np.uint8)
+        ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_OPTIMIZE, 0])
+        full.append(bytes(enc))
+    bare = [strip_dht(j) for j in full]
+    assert all(b"\xff\xc4" not in b[:b.index(b"\xff\xda")] and len(b) == len(j) - 432 for b, j in zip(bare, full))
+    outs = []
+    for name, frames in (("full.avi", full), ("bare.avi", bare)):
+        p = tmp_path / name
+        p.write_bytes(avi(frames))
+        src = video.VideoImageSequenceSource(str(p))
+        assert src.n_frames == n and (src.width, src.height) == (w, h)
+        outs.append(src.read_rgb(0, n)[0])
+        src.close()
+    assert np.array_equal(outs[0], outs[1])
+    ref = cv2.imdecode(np.frombuffer(full[1], np.uint8), cv2.IMREAD_COLOR)[..., ::-1]
+    assert np.abs(O.to_gray(outs[1][1], formula=0).astype(np.int32) - O.to_gray(np.ascontiguousarray(ref), formula=0).astype(np.int32)).max() <= 3
