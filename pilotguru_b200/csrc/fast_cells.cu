@@ -1013,7 +1013,7 @@ int launch_fast_cells(const OrbGeo& g, const TmapIn& tm, const int4* tileTabA, c
   if (int rc = configure_fast_cells(g.fcTilesB > 0 ? g.fcNbB : 0)) return rc;
   // The 4-band launch holds ~97 % of a 1080p pyramid's tiles; the small ones (level 7's 34-px cell rows, levels with
   // cells wider than 32 px) go to a side stream so that their partial waves fill in next to it instead of running alone.
-  const bool fork = side && g.fcTilesA > 0 && (g.fcTilesA5 > 0 || g.fcTilesB > 0);
+  const bool fork = side && nFrames > 4 && g.fcTilesA > 0 && (g.fcTilesA5 > 0 || g.fcTilesB > 0);  // (not worth two event hops for a few frames)
   cudaStream_t s2 = fork ? side : st;
   if (fork) {
     PGB_CUDA(cudaEventRecord(evFork, st));

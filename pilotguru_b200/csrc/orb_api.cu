@@ -478,7 +478,7 @@ int run_stages(pgb_orb* o, int from, int to, pgb_keypoint* kps, uint8_t* desc, i
         if (f0 == 0 && n == o->curFrames) o->scoreValid = true;
         break;
       case 3:
-        if (o->octSide) {
+        if (o->octSide && n > 4) {  // (a handful of frames: the fork / join costs more latency than the priority buys)
           PGB_CUDA(cudaEventRecord(o->evOctFork, st));
           PGB_CUDA(cudaStreamWaitEvent(o->octSide, o->evOctFork, 0));
           launch_octree(g, n, slots, cellCnt, cand, staged, lvlCnt, o->err.p, o->octSide);
