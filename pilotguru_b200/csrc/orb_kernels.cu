@@ -529,7 +529,8 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
   int* vlist = remap + cap;                      // children with >1 points created last pass, creation order
   unsigned long long* best = reinterpret_cast<unsigned long long*>(vlist + cap);  // [cap], 8-aligned by layout
   __shared__ int s_scan[kOctThreads];
-  __shared__ int s_n, s_alive, s_nE, s_nV, s_P, s_seq, s_mode, s_finish, s_prevSize;
+  __shared__ int s_n, s_alive, s_nE, s_nV, s_P, s_seq, s_mode, s_finish, s_prevSize, s_created;
+  __shared__ int s_wsum[kOctThreads / 32];
 
   const int nCells = L.nCols * L.nRows;
   const int* cnt = cellCnt + (size_t)f * g.totalCells + L.cellBase;
@@ -647,23 +648,77 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
       }
     }
     __syncthreads();
-    // (c) sequential bookkeeping
-    if (tid == 0) {
-      int size = alive, P = 0, created = 0;
-      for (int p = 0; p < nE; p++) {
-        int k = 0;
-        for (int q = 0; q < 4; q++) k += (cc[p * 4 + q] > 0);
-        size += k - 1;
-        created += k;
-        P++;
-        if (mode == 1 && size >= N) break;
+    // (c) bookkeeping of the pass, in parallel (it used to be replayed by one thread while 255 waited: 35 % of the kernel's
+    // stall samples sat at the barrier behind it).  The reference's list order is reproduced by prefix sums:
+    //   * expanded node p of the processing order E creates k_p children (its non-empty quadrants), in quadrant order;
+    //     the pass stops after the node with which the list reaches N entries (mode 1: ORBextractor.cc:699-737);
+    //   * children are pushed to the FRONT of the list one by one, so the child with creation ordinal `ord` ends up at
+    //     index created - 1 - ord; the nodes that were not expanded follow in their old order;
+    //   * children with more than one point, in creation order, are the next pass's candidates (vlist).
+    {
+      const int lane = tid & 31, wid = tid >> 5;
+      int* kEx = remap;                          // [nE] exclusive prefix of k (free until the survivors are renumbered)
+      int* gEx = reinterpret_cast<int*>(best);   // [nE] exclusive prefix of the (c > 1) counts (best is unused until the end)
+      auto block_scan = [&](int v, int& carry) {  // exclusive prefix of v over the block (+ carry); carry += block total
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kOctThreads / 32; w++) {
+          const int x = s_wsum[w];
+          if (w < wid) wbase += x;
+          total += x;
+        }
+        __syncthreads();
+        const int ex = carry + wbase + incl - v;
+        carry += total;
+        return ex;
+      };
+      if (tid == 0) s_P = nE;
+      __syncthreads();
+      int carry = 0;
+      for (int base = 0; base < nE; base += kOctThreads) {
+        const int p = base + tid;
+        int k = 0, gq = 0;
+        if (p < nE) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const int c = cc[p * 4 + q]; k += (c > 0); gq += (c > 1); }
+        }
+        const int ex = block_scan(k | (gq << 16), carry);  // both sums stay below 2^15 (at most 4 per node)
+        if (p < nE) {
+          kEx[p] = ex & 0xffff;
+          gEx[p] = ex >> 16;
+          // list size after node p: alive + sum_{j <= p} (k_j - 1); mode 1 stops at the first node that reaches N
+          if (mode == 1 && alive + (ex & 0xffff) + k - (p + 1) >= N) atomicMin(&s_P, p + 1);
+        }
       }
-      if (size > cap) { atomicOr(err, kErrNodeOverflow); s_finish = 2; }
-      else {
-        int ord = 0, nv = 0, nToExpand = 0;
-        for (int p = 0; p < P; p++) {
+      __syncthreads();
+      const int P = s_P;
+      const int seq0 = s_seq;
+      if (P > 0 && tid == ((P - 1) & (kOctThreads - 1))) {  // the last expanded node closes the sums
+        int k = 0, gq = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int c = cc[(P - 1) * 4 + q]; k += (c > 0); gq += (c > 1); }
+        s_created = kEx[P - 1] + k;
+        s_nV = gEx[P - 1] + gq;
+      }
+      if (P == 0 && tid == 0) { s_created = 0; s_nV = 0; }
+      __syncthreads();
+      const int created = s_created, size = alive + created - P, nv = s_nV;
+      if (size > cap) {
+        if (tid == 0) { atomicOr(err, kErrNodeOverflow); s_finish = 2; }
+      } else {
+        for (int p = tid; p < P; p += kOctThreads) {
           const OctNode nd = cur[E[p]];
           const int mx = oct_mid(nd.x0, nd.x1), my = oct_mid(nd.y0, nd.y1);
+          int ord = kEx[p], g = gEx[p];
+#pragma unroll
           for (int q = 0; q < 4; q++) {
             const int c = cc[p * 4 + q];
             if (c <= 0) { childNew[p * 4 + q] = -1; continue; }
@@ -674,25 +729,32 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
             ch.y0 = (q & 2) ? (short)my : nd.y0;
             ch.y1 = (q & 2) ? nd.y1 : (short)my;
             ch.cnt = c;
-            ch.seq = s_seq + ord;
+            ch.seq = seq0 + ord;
             nxt[idx] = ch;
             childNew[p * 4 + q] = idx;
-            if (c > 1) { vlist[nv++] = idx; nToExpand++; }
+            if (c > 1) vlist[g++] = idx;
             ord++;
           }
         }
-        s_seq += ord;
-        int sidx = created;
-        for (int i = 0; i < alive; i++) {
-          const int e = eidx[i];
-          if (e >= 0 && e < P) { remap[i] = -1; continue; }
-          nxt[sidx] = cur[i];
-          remap[i] = sidx++;
+        __syncthreads();  // kEx (= remap) has been read: the survivors may renumber now
+        int scarry = 0;
+        for (int base = 0; base < alive; base += kOctThreads) {
+          const int i = base + tid;
+          bool keep = false;
+          if (i < alive) { const int e = eidx[i]; keep = !(e >= 0 && e < P); }
+          const int ex = block_scan(keep ? 1 : 0, scarry);
+          if (i < alive) {
+            if (keep) { nxt[created + ex] = cur[i]; remap[i] = created + ex; }
+            else remap[i] = -1;
+          }
         }
-        s_alive = size; s_P = P; s_nV = nv;
-        // loop control (ORBextractor.cc:663-737)
-        if (size >= N || size == s_prevSize) s_finish = 1;
-        else if (mode == 0 && (size + nToExpand * 3) > N) s_mode = 1;
+        if (tid == 0) {
+          s_seq = seq0 + created;
+          s_alive = size; s_P = P;
+          // loop control (ORBextractor.cc:663-737)
+          if (size >= N || size == s_prevSize) s_finish = 1;
+          else if (mode == 0 && (size + nv * 3) > N) s_mode = 1;
+        }
       }
     }
     __syncthreads();
