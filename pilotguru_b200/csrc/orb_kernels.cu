@@ -532,6 +532,29 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
   __shared__ int s_n, s_alive, s_nE, s_nV, s_P, s_seq, s_mode, s_finish, s_prevSize, s_created;
   __shared__ int s_wsum[kOctThreads / 32];
 
+  const int lane = tid & 31, wid = tid >> 5;
+  auto block_scan = [&](int v, int& carry) {  // exclusive prefix of v over the block (+ carry); carry += block total
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kOctThreads / 32; w++) {
+      const int x = s_wsum[w];
+      if (w < wid) wbase += x;
+      total += x;
+    }
+    __syncthreads();
+    const int ex = carry + wbase + incl - v;
+    carry += total;
+    return ex;
+  };
+
   const int nCells = L.nCols * L.nRows;
   const int* cnt = cellCnt + (size_t)f * g.totalCells + L.cellBase;
   const uint32_t* slot = slots + (size_t)f * g.slotsPerFrame + L.slotBase;
@@ -542,13 +565,13 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
   const int c0 = min(tid * chunk, nCells), c1 = min(c0 + chunk, nCells);
   int mySum = 0;
   for (int c = c0; c < c1; c++) mySum += cnt[c];
-  s_scan[tid] = mySum;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int i = 0; i < kOctThreads; i++) { int v = s_scan[i]; s_scan[i] = run; run += v; }
-    s_n = run;
-    if (run > L.candCap) { atomicOr(err, kErrCandOverflow); s_n = 0; }
+  {
+    int total = 0;
+    s_scan[tid] = block_scan(mySum, total);
+    if (tid == 0) {
+      s_n = total;
+      if (total > L.candCap) { atomicOr(err, kErrCandOverflow); s_n = 0; }
+    }
   }
   __syncthreads();
   const int n = s_n;
@@ -607,13 +630,15 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
     // (a) processing order
     for (int i = tid; i < alive; i += kOctThreads) eidx[i] = -1;
     __syncthreads();
-    if (mode == 0) {
-      if (tid == 0) {
-        int ne = 0;
-        for (int i = 0; i < alive; i++)
-          if (cur[i].cnt > 1) { E[ne] = i; eidx[i] = ne; ne++; }
-        s_nE = ne; s_prevSize = alive;
+    if (mode == 0) {  // every node with more than one point, in list order
+      int ne = 0;
+      for (int base = 0; base < alive; base += kOctThreads) {
+        const int i = base + tid;
+        const bool split = i < alive && cur[i].cnt > 1;
+        const int ex = block_scan(split ? 1 : 0, ne);
+        if (split) { E[ex] = i; eidx[i] = ex; }
       }
+      if (tid == 0) { s_nE = ne; s_prevSize = alive; }
     } else {
       const int nV = s_nV;
       for (int t = tid; t < nV; t += kOctThreads) {
@@ -656,30 +681,8 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(OrbGeo g, const uint32_t
     //     index created - 1 - ord; the nodes that were not expanded follow in their old order;
     //   * children with more than one point, in creation order, are the next pass's candidates (vlist).
     {
-      const int lane = tid & 31, wid = tid >> 5;
       int* kEx = remap;                          // [nE] exclusive prefix of k (free until the survivors are renumbered)
       int* gEx = reinterpret_cast<int*>(best);   // [nE] exclusive prefix of the (c > 1) counts (best is unused until the end)
-      auto block_scan = [&](int v, int& carry) {  // exclusive prefix of v over the block (+ carry); carry += block total
-        int incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_wsum[wid] = incl;
-        __syncthreads();
-        int wbase = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kOctThreads / 32; w++) {
-          const int x = s_wsum[w];
-          if (w < wid) wbase += x;
-          total += x;
-        }
-        __syncthreads();
-        const int ex = carry + wbase + incl - v;
-        carry += total;
-        return ex;
-      };
       if (tid == 0) s_P = nE;
       __syncthreads();
       int carry = 0;
